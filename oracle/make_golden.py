@@ -1,0 +1,88 @@
+"""TEST INFRASTRUCTURE — generate tests/golden/* from the REAL reference modules.
+
+Run in the build container only (needs /root/reference):  python -m oracle.make_golden
+Weights: oracle.synth_ckpt (seeded, per key).  Inputs: dose_prediction_b200.synth (seeded).
+Outputs are what the reference's own nn.Modules (imported unmodified through ref_loader) return.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from dose_prediction_b200 import synth  # noqa: E402
+from oracle import ref_loader, synth_ckpt  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+DOSE_SEED, SEG_SEED = 0, 1
+
+
+def _np(t):
+    return t.detach().cpu().numpy().astype(np.float32)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.manual_seed(0)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+
+    # ---- drop-in contract: state_dict manifests at the headline size (128^3)
+    for name, mod in (("dose_pyfer", ref_loader.build_dose(128)), ("oar_transeg", ref_loader.build_seg(128)),
+                      ("oar_transeg_2ch", ref_loader.build_seg(128, in_channels=2))):
+        with open(os.path.join(OUT, f"manifest_{name}.json"), "w") as f:
+            json.dump(synth_ckpt.manifest_of(mod), f, indent=0)
+    old = ref_loader.oar_transeg_old()
+    old_model = old.TRANSEG(in_channels=1, out_channels=8, img_size=(96, 96, 96), feature_size=16,
+                            hidden_size=768, mlp_dim=3072, num_heads=12, pos_embed="perceptron",
+                            norm_name="instance", res_block=True, conv_block=True, dropout_rate=0.0)
+    with open(os.path.join(OUT, "manifest_transeg_old_96.json"), "w") as f:
+        json.dump(synth_ckpt.manifest_of(old_model), f, indent=0)
+
+    # ---- 32^3 end-to-end vectors (batch 2 so per-instance statistics are exercised)
+    vol = synth.make_batch(2, 32, seed=1234)
+    dose = ref_loader.build_dose(32).eval()
+    dose.load_state_dict(synth_ckpt.make_state_dict(synth_ckpt.manifest_of(dose), DOSE_SEED), strict=True)
+    seg = ref_loader.build_seg(32).eval()
+    seg.load_state_dict(synth_ckpt.make_state_dict(synth_ckpt.manifest_of(seg), SEG_SEED), strict=True)
+    with torch.no_grad():
+        out = dose(vol["dose_input"])
+        logits = seg(vol["ct"])
+    np.savez_compressed(os.path.join(OUT, "dose32.npz"), out_A=_np(out[0]),
+                        **{f"d{i}": _np(t) for i, t in enumerate(out[1])})
+    np.savez_compressed(os.path.join(OUT, "seg32.npz"), logits=_np(logits))
+
+    # ---- hand-off exactly as LinkedNet.test_step does it (train_light_linked_model.py:152-169)
+    cfg = ref_loader.seg_config()
+    from monai.data import decollate_batch
+    ct, ptv = vol["ct"][:1], vol["ptv"][:1]
+    with torch.no_grad():
+        oars = seg(ct)
+        oars = [cfg.post_pred(i) for i in decollate_batch(oars)][0]
+        oars = torch.permute(oars, (0, 3, 2, 1))
+        ct_t = torch.permute(ct, (0, 1, 4, 3, 2))
+        oars = torch.unsqueeze(oars, dim=0)[:, 1:, :, :, :]
+        structures = torch.cat((ptv, oars, ct_t), dim=1)
+        pred = dose(structures)[1][0]
+    np.savez_compressed(os.path.join(OUT, "cascade32.npz"), structures=_np(structures), dose=_np(pred))
+
+    # ---- GenLoss (loss.py:69-119) on the reference's own outputs
+    loss_mod = ref_loader.loss().GenLoss(im_size=32)
+    with torch.no_grad():
+        val = loss_mod(out, vol["gt"], casecade=True, freez=True, delta1=10, delta2=8)
+    np.savez_compressed(os.path.join(OUT, "genloss32.npz"), loss=np.float64(val.item()))
+
+    # ---- sliding window (monai restatement; seg net built for 32^3 scanned over a 48^3 CT)
+    from monai.inferers import sliding_window_inference
+    ct48 = synth.make_volume(48, seed=77)["ct"]
+    with torch.no_grad():
+        sw = sliding_window_inference(ct48, (32, 32, 32), 4, seg)
+    np.savez_compressed(os.path.join(OUT, "sliding48.npz"), logits=_np(sw[:, :, ::2, ::2, ::2]))
+    print("golden fixtures written to", OUT)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,75 @@
+"""TEST INFRASTRUCTURE — import the reference's model files unmodified (build container only).
+
+Puts `oracle/monai_compat` (for `import monai`) and `/root/reference` on sys.path and imports
+  DosePrediction.Models.Networks.dose_pyfer   (dose_pyfer.py:325 Model)
+  OARSegmentation.Models.Networks.oar_transeg (oar_transeg.py:14 Model)
+  DosePrediction.Train.loss                   (loss.py:50 GenLoss)
+Never used on the GPU box (no /root/reference there) and never by the product.
+"""
+import contextlib
+import importlib
+import io
+import os
+import sys
+
+REFERENCE_ROOT = os.environ.get("DP_REFERENCE_ROOT", "/root/reference")
+_COMPAT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "monai_compat")
+
+
+def available() -> bool:
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "DosePrediction"))
+
+
+def _ensure_path():
+    if not available():
+        raise RuntimeError(f"reference tree not found at {REFERENCE_ROOT}")
+    for p in (REFERENCE_ROOT, _COMPAT):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+
+
+def _imp(name):
+    _ensure_path()
+    with contextlib.redirect_stdout(io.StringIO()):
+        return importlib.import_module(name)
+
+
+def dose_pyfer():
+    return _imp("DosePrediction.Models.Networks.dose_pyfer")
+
+
+def oar_transeg():
+    return _imp("OARSegmentation.Models.Networks.oar_transeg")
+
+
+def oar_transeg_old():
+    return _imp("OARSegmentation.OldModels.Networks.oar_transeg")
+
+
+def loss():
+    return _imp("DosePrediction.Train.loss")
+
+
+def seg_config():
+    return _imp("OARSegmentation.config")
+
+
+def build_dose(img=128, **kw):
+    """Reference DOSE-PYFER with the hot-path ctor args (train_light_pyfer.py:73-83)."""
+    m = dose_pyfer()
+    args = dict(in_ch=9, out_ch=1, list_ch_A=[-1, 16, 32, 64, 128, 256], feature_size=16,
+                img_size=(img, img, img), num_layers=8, num_heads=6, act="mish",
+                mode_multi_dec=True, multiS_conv=True)
+    args.update(kw)
+    with contextlib.redirect_stdout(io.StringIO()):
+        return m.Model(**args)
+
+
+def build_seg(img=128, in_channels=1, **kw):
+    """Reference OAR-TRANSEG with the hot-path ctor args (train_light_transeg.py:110-124)."""
+    m = oar_transeg()
+    args = dict(in_channels=in_channels, out_channels=8, img_size=(img, img, img), feature_size=16,
+                hidden_size=768, mlp_dim=3072, num_heads=12, pos_embed="perceptron",
+                norm_name="instance", res_block=True, conv_block=True, dropout_rate=0.0)
+    args.update(kw)
+    return m.Model(**args)

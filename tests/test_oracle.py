@@ -1,0 +1,106 @@
+"""Oracle pinning (CPU): oracle/torch_ref.py against the fixtures produced by the reference's own
+modules (oracle/make_golden.py), and — when /root/reference is present — against the modules live."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, load_manifest
+from dose_prediction_b200 import synth
+from oracle import ref_loader, synth_ckpt, torch_ref
+
+TOL = 2e-5   # fp32 CPU conv reduction order differs between hosts / thread counts
+
+
+def _resize_manifest(man, tokens):
+    out = []
+    for k, shape, *_ in man:
+        if k.endswith("position_embeddings"):
+            shape = [1, tokens, shape[2]]
+        out.append((k, shape))
+    return out
+
+
+@pytest.fixture(scope="module")
+def dose_sd32():
+    return synth_ckpt.make_state_dict(_resize_manifest(load_manifest("dose_pyfer"), 8), seed=0)
+
+
+@pytest.fixture(scope="module")
+def seg_sd32():
+    return synth_ckpt.make_state_dict(_resize_manifest(load_manifest("oar_transeg"), 8), seed=1)
+
+
+def test_dose_pyfer_matches_reference_fixture(dose_sd32):
+    vol = synth.make_batch(2, 32, seed=1234)
+    g = np.load(os.path.join(GOLDEN, "dose32.npz"))
+    with torch.no_grad():
+        out = torch_ref.dose_pyfer_forward(dose_sd32, vol["dose_input"])
+    assert torch_ref.rel_l2(out[0], torch.from_numpy(g["out_A"])) < TOL
+    for i, t in enumerate(out[1]):
+        assert t.shape == g[f"d{i}"].shape
+        assert torch_ref.rel_l2(t, torch.from_numpy(g[f"d{i}"])) < TOL
+
+
+def test_oar_transeg_matches_reference_fixture(seg_sd32):
+    vol = synth.make_batch(2, 32, seed=1234)
+    g = torch.from_numpy(np.load(os.path.join(GOLDEN, "seg32.npz"))["logits"])
+    with torch.no_grad():
+        out = torch_ref.oar_transeg_forward(seg_sd32, vol["ct"])
+    assert torch_ref.rel_l2(out, g) < TOL
+    assert (out.argmax(1) == g.argmax(1)).float().mean().item() > 0.9999
+
+
+def test_handoff_and_cascade_match_reference_fixture(dose_sd32, seg_sd32):
+    vol = synth.make_batch(2, 32, seed=1234)
+    g = np.load(os.path.join(GOLDEN, "cascade32.npz"))
+    ct, ptv = vol["ct"][:1], vol["ptv"][:1]
+    with torch.no_grad():
+        logits = torch_ref.oar_transeg_forward(seg_sd32, ct)
+        st = torch_ref.handoff(logits, ptv, ct)
+        agree = (st == torch.from_numpy(g["structures"])).float().mean().item()
+        assert agree > 0.9999            # argmax near-ties may flip with the host's fp32 summation order
+        dose = torch_ref.dose_pyfer_forward(dose_sd32, torch.from_numpy(g["structures"]))[1][0]
+    assert torch_ref.rel_l2(dose, torch.from_numpy(g["dose"])) < TOL
+
+
+def test_gen_loss_matches_reference_fixture():
+    vol = synth.make_batch(2, 32, seed=1234)
+    g = np.load(os.path.join(GOLDEN, "dose32.npz"))
+    preds = [torch.from_numpy(g["out_A"]), [torch.from_numpy(g[f"d{i}"]) for i in range(4)]]
+    want = float(np.load(os.path.join(GOLDEN, "genloss32.npz"))["loss"])
+    got = float(torch_ref.gen_loss(preds, vol["gt"]))
+    assert abs(got - want) <= 1e-5 * abs(want)
+
+
+def test_sliding_window_matches_fixture(seg_sd32):
+    ct48 = synth.make_volume(48, seed=77)["ct"]
+    g = torch.from_numpy(np.load(os.path.join(GOLDEN, "sliding48.npz"))["logits"])
+    with torch.no_grad():
+        out = torch_ref.sliding_window_logits(seg_sd32, ct48, roi=32, sw_batch=4)
+    assert torch_ref.rel_l2(out[:, :, ::2, ::2, ::2], g) < TOL
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree only exists in the build container")
+def test_restatement_equals_live_reference_modules():
+    torch.manual_seed(3)
+    m = ref_loader.build_dose(32, act="relu").eval()
+    sd = synth_ckpt.make_state_dict(synth_ckpt.manifest_of(m), seed=5)
+    m.load_state_dict(sd, strict=True)
+    x = synth.make_batch(1, 32, seed=9)["dose_input"]
+    with torch.no_grad():
+        want = m(x)
+        got = torch_ref.dose_pyfer_forward(sd, x, act="relu")
+    assert torch_ref.rel_l2(got[1][0], want[1][0]) < 1e-6
+    m2 = ref_loader.build_dose(32, multiS_conv=False).eval()
+    sd2 = synth_ckpt.make_state_dict(synth_ckpt.manifest_of(m2), seed=6)
+    m2.load_state_dict(sd2, strict=True)
+    with torch.no_grad():
+        assert torch_ref.rel_l2(torch_ref.dose_pyfer_forward(sd2, x, multiS_conv=False)[1][0], m2(x)[1][0]) < 1e-6
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree only exists in the build container")
+def test_manifests_are_current():
+    got = [tuple(e) for e in synth_ckpt.manifest_of(ref_loader.build_seg(128))]
+    assert got == load_manifest("oar_transeg")
