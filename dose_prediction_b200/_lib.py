@@ -1,0 +1,73 @@
+"""ctypes binding of libdose_b200.so (the C ABI declared in include/dose_b200.h).
+
+There is no CPU or eager-PyTorch fallback: if the shared library is missing or a call fails, a
+RuntimeError is raised.
+"""
+import ctypes
+import os
+from ctypes import c_double, c_float, c_int, c_longlong, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdose_b200.so")
+_LIB = None
+
+P = c_void_p
+I = c_int
+L = c_longlong
+F = c_float
+
+_SIGNATURES = {
+    "dp_conv3d_tc": [P, I, P, I, P, I, I, I, I, I, I, I, P, P, I, P, P, P, I, I, P, P, I, P],
+    "dp_conv3d_direct": [P, P, I, I, I, I, I, I, I, I, I, I, P, P, P, I, I, P, P, P, I, I, P, P],
+    "dp_gemm_tc": [P, P, I, I, I, I, I, I, L, I, L, I, I, P, P, I, P, F, I, P, I, P, I, I, I, I, P, P, P, F, P, P],
+    "dp_pack_ncdhw": [P, I, I, L, P, P, I, I, P],
+    "dp_unpack_c8": [P, P, I, I, I, I, L, P, P],
+    "dp_norm_act": [P, P, P, I, I, P, P, P, I, P, P, P, P, I, I, I, P, P, I, I, P, I, I, L, P],
+    "dp_pointwise_conv": [I, P, P, P, P, P, P, P, P, P, P, I, I, L, P, P, P, I, I, P, P, I, P],
+    "dp_deconv2x": [P, P, L, L, L, I, I, I, I, I, I, P, P, P, I, I, P],
+    "dp_upsample2x": [P, P, I, I, I, I, I, I, I, P, P, I, I, P],
+    "dp_layernorm": [P, P, P, I, I, P, P, P],
+    "dp_softmax": [P, I, I, I, P, I, P],
+    "dp_patchify": [P, I, I, I, I, I, I, I, P, P],
+    "dp_handoff": [P, I, P, P, I, I, P, P, I, I, P, P],
+}
+
+
+def exported_symbols():
+    """Every symbol include/dose_b200.h declares (checked by tests/test_abi.py)."""
+    return sorted(list(_SIGNATURES) + ["dp_last_error", "dp_abi_version", "dp_device_sm_count"])
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: the CUDA extension is not built (run __graft_entry__.build()); "
+                "dose_prediction_b200 has no CPU fallback")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, argtypes in _SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.argtypes = argtypes
+            fn.restype = c_int
+        handle.dp_last_error.restype = ctypes.c_char_p
+        handle.dp_abi_version.restype = c_int
+        handle.dp_device_sm_count.restype = c_int
+        _LIB = handle
+    return _LIB
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().dp_last_error().decode(errors="replace")
+        raise RuntimeError(f"libdose_b200 {what} failed (rc={rc}): {msg}")
+
+
+def ptr_array(ptrs):
+    """Host array of device pointers for the multi-source entry points."""
+    arr = (c_void_p * len(ptrs))(*[c_void_p(p) if p else None for p in ptrs])
+    return arr
+
+
+def int_array(vals):
+    return (c_int * len(vals))(*vals)

@@ -1,0 +1,349 @@
+// 3-D convolution (stride 1, k in {1,3,5,7}, dilation d) as an implicit GEMM on tcgen05 tensor cores.
+//
+//   M = 128 output voxels  (a 16(H) x 8(W) patch of one D-plane of one image)
+//   N = C_out              (16..256, multiple of 16)
+//   K = taps x C_in        (consumed 16 channels per tcgen05.mma)
+//
+// Data layout in HBM ("c8"): activations are [N][C/8][D][H][W][8] fp16, i.e. channel-blocked by 8 so
+// that 8 channels of a voxel are one 16-byte vector and voxels along W are 16 bytes apart.  That is
+// exactly the canonical K-major / no-swizzle UMMA core-matrix layout (8 rows x 16 B), which lets one
+// TMA box load of an input halo patch [2 c8-blocks][16+halo rows][8+halo voxels][8 ch] serve EVERY
+// in-plane tap of the kernel: the A operand of tap (kh,kw) is the same shared-memory patch with the
+// descriptor start address advanced by ((kh*dil)*PW + kw*dil)*16 bytes (SBO = patch row pitch,
+// LBO = c8-block pitch).  Halo zero padding comes from TMA out-of-bounds fill; out-of-range D planes
+// are skipped.  Weights are pre-packed per (kd, 16-channel chunk) as [kh][kw][2][C_out][8] fp16 and
+// streamed with 1-D bulk copies.  Accumulators live in TMEM (double buffered), the epilogue applies
+// the folded bias/BatchNorm affine (+ReLU), accumulates InstanceNorm partial sums from the fp32
+// accumulators and writes c8 tensors (fp32 "raw" for a following InstanceNorm, or fp16 hi[/lo]).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..5 =
+// epilogue (TMEM lane quarter = warp_id % 4).  Persistent: each CTA walks tiles blockIdx.x + i*gridDim.x.
+//
+// Reference call sites this replaces (cuDNN via nn.Conv3d): OARSegmentation/Models/Nets/
+// blocks_MDUNet.py:68-71,102-105 (conv_block_3 / conv_block_7), DosePrediction/Models/Networks/c3d.py:16,30,
+// monai dynunet_block.UnetResBlock.conv1/conv2.
+#include "common.cuh"
+#include "dose_b200.h"
+
+namespace dp {
+
+struct ConvTcParams {
+  int N, D, H, W;
+  int k, dil, pad;
+  int n_chunks, cb_total_in;
+  int cout;
+  int kh_s, n_khg;
+  int PW, PHs;
+  int stages;
+  uint32_t a_bytes, a_bytes_al, stage_bytes;
+  int tiles_h, tiles_w, num_tiles;
+  const __half* wpack;
+  const float* scale;
+  const float* shift;
+  int relu;
+  float* out_f32;
+  __half* out_hi;
+  __half* out_lo;
+  int cb_total_out, cb_out_off;
+  double* stats;
+  int* err_flag;
+  uint32_t tmem_cols;
+  uint8_t chunk_cb[96];
+};
+
+constexpr int kConvThreads = 192;
+constexpr int kMaxStages = 8;
+
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ ConvTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  __shared__ uint64_t full_bar[kMaxStages];
+  __shared__ uint64_t empty_bar[kMaxStages];
+  __shared__ uint64_t tmem_full_bar[2];
+  __shared__ uint64_t tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ float stat_acc[4][256][2];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_in);
+    for (int i = 0; i < p.stages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(&tmem_base_smem)),
+                 "r"(p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < 4 * 256 * 2; i += kConvThreads) (&stat_acc[0][0][0])[i] = 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  const int tiles_per_plane = p.tiles_h * p.tiles_w;
+  const uint32_t tap_b_bytes = 32u * static_cast<uint32_t>(p.cout);  // one tap: [2][cout][8] fp16
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        int t = tile;
+        const int tw = t % p.tiles_w; t /= p.tiles_w;
+        const int th = t % p.tiles_h; t /= p.tiles_h;
+        const int d = t % p.D;
+        const int n = t / p.D;
+        const int h0 = th * 16, w0 = tw * 8;
+        for (int kd = 0; kd < p.k; ++kd) {
+          const int dz = d + kd * p.dil - p.pad;
+          if (dz < 0 || dz >= p.D) continue;
+          for (int c = 0; c < p.n_chunks; ++c) {
+            const __half* wsrc =
+                p.wpack + (static_cast<size_t>(kd) * p.n_chunks + c) * (static_cast<size_t>(p.k) * p.k * 16 * p.cout);
+            for (int g = 0; g < p.n_khg; ++g) {
+              const int kh0 = g * p.kh_s;
+              const int cnt = min(p.kh_s, p.k - kh0);
+              if (!mbar_wait(&empty_bar[stage], phase ^ 1, p.err_flag)) goto teardown;
+              uint8_t* sa = smem + static_cast<size_t>(stage) * p.stage_bytes;
+              uint8_t* sb = sa + p.a_bytes_al;
+              const uint32_t b_bytes = static_cast<uint32_t>(cnt * p.k) * tap_b_bytes;
+              mbar_arrive_expect_tx(&full_bar[stage], p.a_bytes + b_bytes);
+              tma_load_5d(sa, &tmap_in, &full_bar[stage], 0, w0 - p.pad, h0 - p.pad + kh0 * p.dil, dz,
+                          n * p.cb_total_in + p.chunk_cb[c]);
+              bulk_load_1d(sb, wsrc + static_cast<size_t>(kh0) * p.k * 16 * p.cout, b_bytes, &full_bar[stage]);
+              if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(128, p.cout);
+      const uint32_t a_lbo = static_cast<uint32_t>(p.PHs * p.PW) * 16u;
+      const uint32_t a_sbo = static_cast<uint32_t>(p.PW) * 16u;
+      const uint32_t b_lbo = static_cast<uint32_t>(p.cout) * 16u;
+      const uint32_t b_sbo = 128u;
+      int stage = 0;
+      uint32_t phase = 0;
+      int iter = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++iter) {
+        int t = tile / tiles_per_plane;
+        const int d = t % p.D;
+        const int slot = iter & 1;
+        if (!mbar_wait(&tmem_empty_bar[slot], ((iter >> 1) & 1) ^ 1, p.err_flag)) goto teardown;
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(slot * p.cout);
+        uint32_t accumulate = 0;
+        for (int kd = 0; kd < p.k; ++kd) {
+          const int dz = d + kd * p.dil - p.pad;
+          if (dz < 0 || dz >= p.D) continue;
+          for (int c = 0; c < p.n_chunks; ++c) {
+            for (int g = 0; g < p.n_khg; ++g) {
+              const int cnt = min(p.kh_s, p.k - g * p.kh_s);
+              if (!mbar_wait(&full_bar[stage], phase, p.err_flag)) goto teardown;
+              tc_fence_after();
+              const uint32_t sa = smem_u32(smem + static_cast<size_t>(stage) * p.stage_bytes);
+              const uint32_t sb = sa + p.a_bytes_al;
+              for (int khl = 0; khl < cnt; ++khl) {
+                for (int kw = 0; kw < p.k; ++kw) {
+                  const uint32_t a_addr = sa + static_cast<uint32_t>((khl * p.dil) * p.PW + kw * p.dil) * 16u;
+                  const uint32_t b_addr = sb + static_cast<uint32_t>(khl * p.k + kw) * tap_b_bytes;
+                  umma_f16_ss(tmem_d, make_smem_desc(a_addr, a_lbo, a_sbo, 0), make_smem_desc(b_addr, b_lbo, b_sbo, 0),
+                              idesc, accumulate);
+                  accumulate = 1;
+                }
+              }
+              umma_commit(&empty_bar[stage]);
+              if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+        umma_commit(&tmem_full_bar[slot]);
+      }
+    }
+  } else {
+    // ===================================================================== epilogue (warps 2..5)
+    const int quarter = warp & 3;
+    const int ew = warp - 2;
+    const int row = quarter * 32 + lane;
+    const int hl = row >> 3, wl = row & 7;
+    int cur_n = -1;
+    int iter = 0;
+    auto flush_stats = [&](int n) {
+      if (p.stats == nullptr || n < 0) return;
+      __syncwarp();
+      for (int c = lane; c < p.cout; c += 32) {
+        atomicAdd(&p.stats[(static_cast<size_t>(n) * p.cout + c) * 2 + 0], static_cast<double>(stat_acc[ew][c][0]));
+        atomicAdd(&p.stats[(static_cast<size_t>(n) * p.cout + c) * 2 + 1], static_cast<double>(stat_acc[ew][c][1]));
+        stat_acc[ew][c][0] = 0.f;
+        stat_acc[ew][c][1] = 0.f;
+      }
+      __syncwarp();
+    };
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++iter) {
+      int t = tile;
+      const int tw = t % p.tiles_w; t /= p.tiles_w;
+      const int th = t % p.tiles_h; t /= p.tiles_h;
+      const int d = t % p.D;
+      const int n = t / p.D;
+      if (n != cur_n) { flush_stats(cur_n); cur_n = n; }
+      const int h = th * 16 + hl, w = tw * 8 + wl;
+      const bool valid = (h < p.H) && (w < p.W);
+      const int slot = iter & 1;
+      if (!mbar_wait(&tmem_full_bar[slot], (iter >> 1) & 1, p.err_flag)) goto teardown;
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(slot * p.cout);
+      const size_t vox = (static_cast<size_t>(d) * p.H + h) * p.W + w;
+      const size_t plane = static_cast<size_t>(p.D) * p.H * p.W;
+      for (int c0 = 0; c0 < p.cout; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr + c0, r);
+        tmem_ld_wait();
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float x = fmaf(__uint_as_float(r[j]), __ldg(&p.scale[c0 + j]), __ldg(&p.shift[c0 + j]));
+          if (p.relu) x = fmaxf(x, 0.f);
+          v[j] = x;
+        }
+        if (p.stats != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float s = valid ? v[j] : 0.f;
+            const float s1 = warp_sum(s);
+            const float s2 = warp_sum(s * s);
+            if (lane == 0) {
+              stat_acc[ew][c0 + j][0] += s1;
+              stat_acc[ew][c0 + j][1] += s2;
+            }
+          }
+        }
+        if (valid) {
+#pragma unroll
+          for (int b = 0; b < 2; ++b) {
+            const size_t cb = static_cast<size_t>(n) * p.cb_total_out + p.cb_out_off + (c0 >> 3) + b;
+            const size_t off = (cb * plane + vox) * 8;
+            if (p.out_f32 != nullptr) {
+              float4* o = reinterpret_cast<float4*>(p.out_f32 + off);
+              o[0] = make_float4(v[b * 8 + 0], v[b * 8 + 1], v[b * 8 + 2], v[b * 8 + 3]);
+              o[1] = make_float4(v[b * 8 + 4], v[b * 8 + 5], v[b * 8 + 6], v[b * 8 + 7]);
+            }
+            if (p.out_hi != nullptr) {
+              __align__(16) __half hi[8];
+              __align__(16) __half lo[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                hi[j] = __float2half_rn(v[b * 8 + j]);
+                lo[j] = __float2half_rn(v[b * 8 + j] - __half2float(hi[j]));
+              }
+              *reinterpret_cast<uint4*>(p.out_hi + off) = *reinterpret_cast<const uint4*>(hi);
+              if (p.out_lo != nullptr) *reinterpret_cast<uint4*>(p.out_lo + off) = *reinterpret_cast<const uint4*>(lo);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[slot]);
+    }
+    flush_stats(cur_n);
+  }
+
+teardown:
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+}  // namespace dp
+
+// =============================================================================== C ABI
+extern "C" int dp_conv3d_tc(const void* in_c8, int cb_total_in, const uint8_t* chunk_cb, int n_chunks,
+                            const void* wpack, int N, int D, int H, int W, int cout, int k, int dil,
+                            const float* scale, const float* shift, int relu, float* out_f32, void* out_hi,
+                            void* out_lo, int cb_total_out, int cb_out_off, double* stats, int* err_flag,
+                            int max_ctas, cudaStream_t stream) {
+  using namespace dp;
+  DP_REQUIRE(cout % 16 == 0 && cout >= 16 && cout <= 256, "dp_conv3d_tc: C_out=%d must be a multiple of 16 in [16,256]", cout);
+  DP_REQUIRE(k >= 1 && k <= 7 && (k & 1), "dp_conv3d_tc: kernel size %d unsupported", k);
+  DP_REQUIRE(n_chunks >= 1 && n_chunks <= 96, "dp_conv3d_tc: n_chunks=%d out of range", n_chunks);
+  DP_REQUIRE(out_f32 != nullptr || out_hi != nullptr, "dp_conv3d_tc: no output tensor given");
+  ConvTcParams p{};
+  p.N = N; p.D = D; p.H = H; p.W = W;
+  p.k = k; p.dil = dil; p.pad = dil * (k - 1) / 2;
+  p.n_chunks = n_chunks; p.cb_total_in = cb_total_in; p.cout = cout;
+  for (int i = 0; i < n_chunks; ++i) p.chunk_cb[i] = chunk_cb[i];
+  p.PW = 8 + (k - 1) * dil;
+  // stage sizing: as many kh rows per stage as fit ~56 KB, then as many stages as fit ~200 KB
+  const int tap_b = 32 * cout;
+  int kh_s = k;
+  auto stage_bytes_for = [&](int s) {
+    const int phs = 16 + (s - 1) * dil;
+    const int a = 2 * phs * p.PW * 16;
+    return ((a + 127) / 128) * 128 + s * k * tap_b;
+  };
+  while (kh_s > 1 && stage_bytes_for(kh_s) > 56 * 1024) --kh_s;
+  p.kh_s = kh_s;
+  p.n_khg = (k + kh_s - 1) / kh_s;
+  p.PHs = 16 + (kh_s - 1) * dil;
+  p.a_bytes = 2u * p.PHs * p.PW * 16u;
+  p.a_bytes_al = ((p.a_bytes + 127u) / 128u) * 128u;
+  p.stage_bytes = ((static_cast<uint32_t>(stage_bytes_for(kh_s)) + 1023u) / 1024u) * 1024u;
+  int stages = static_cast<int>((200u * 1024u) / p.stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  DP_REQUIRE(stages >= 2, "dp_conv3d_tc: stage of %u bytes does not fit twice in shared memory", p.stage_bytes);
+  p.stages = stages;
+  p.tiles_h = (H + 15) / 16;
+  p.tiles_w = (W + 7) / 8;
+  p.num_tiles = N * D * p.tiles_h * p.tiles_w;
+  p.wpack = static_cast<const __half*>(wpack);
+  p.scale = scale; p.shift = shift; p.relu = relu;
+  p.out_f32 = out_f32; p.out_hi = static_cast<__half*>(out_hi); p.out_lo = static_cast<__half*>(out_lo);
+  p.cb_total_out = cb_total_out; p.cb_out_off = cb_out_off;
+  p.stats = stats; p.err_flag = err_flag;
+  uint32_t cols = 32;
+  while (cols < static_cast<uint32_t>(2 * cout)) cols <<= 1;
+  p.tmem_cols = cols;
+
+  CUtensorMap tmap;
+  const uint64_t dims[5] = {8, static_cast<uint64_t>(W), static_cast<uint64_t>(H), static_cast<uint64_t>(D),
+                            static_cast<uint64_t>(N) * cb_total_in};
+  const uint64_t strides[4] = {16, static_cast<uint64_t>(W) * 16, static_cast<uint64_t>(H) * W * 16,
+                               static_cast<uint64_t>(D) * H * W * 16};
+  const uint32_t box[5] = {8, static_cast<uint32_t>(p.PW), static_cast<uint32_t>(p.PHs), 1, 2};
+  if (int rc = encode_tiled(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, in_c8, dims, strides, box,
+                            CU_TENSOR_MAP_SWIZZLE_NONE))
+    return rc;
+
+  const size_t smem = static_cast<size_t>(p.stages) * p.stage_bytes + 1024;
+  static size_t configured = 0;
+  if (smem > configured) {
+    DP_CHECK(cudaFuncSetAttribute(conv3d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    configured = smem;
+  }
+  int grid = sm_count();
+  if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+  if (grid > p.num_tiles) grid = p.num_tiles;
+  conv3d_tc_kernel<<<grid, kConvThreads, smem, stream>>>(tmap, p);
+  DP_CHECK(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,770 @@
+// HBM-bound fused kernels around the tensor-core contractions: layout packing, InstanceNorm apply
+// (+affine, +activation, +residual, +chained statistics), 1x1x1 convolutions with normalise-on-load,
+// 2x transposed convolution, trilinear 2x upsampling, LayerNorm, softmax, patch flattening, the
+// seg-argmax -> dose-input hand-off, and a generic direct convolution (strided convs).
+//
+// Activation layout "c8": [N][C/8][D][H][W][8]; one thread moves one 16-byte (8 x fp16) or 32-byte
+// (8 x fp32) channel vector, threads along W -> fully coalesced.  Per-(n,c) statistics are
+// {sum, sum of squares} in fp64, accumulated with one atomicAdd per block per channel.
+#include "common.cuh"
+#include "dose_b200.h"
+
+namespace dp {
+
+__device__ __forceinline__ void load8(const __half* hi, const __half* lo, size_t off, float (&x)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(hi + off);
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = __half22float2(h[j]);
+    x[2 * j] = f.x;
+    x[2 * j + 1] = f.y;
+  }
+  if (lo != nullptr) {
+    const uint4 v = *reinterpret_cast<const uint4*>(lo + off);
+    const __half2* l = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(l[j]);
+      x[2 * j] += f.x;
+      x[2 * j + 1] += f.y;
+    }
+  }
+}
+__device__ __forceinline__ void load8f(const float* p, size_t off, float (&x)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p + off);
+  const float4 b = *reinterpret_cast<const float4*>(p + off + 4);
+  x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+}
+__device__ __forceinline__ void store8(__half* hi, __half* lo, size_t off, const float (&x)[8]) {
+  __align__(16) __half h[8];
+  __align__(16) __half l[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    h[j] = __float2half_rn(x[j]);
+    l[j] = __float2half_rn(x[j] - __half2float(h[j]));
+  }
+  *reinterpret_cast<uint4*>(hi + off) = *reinterpret_cast<const uint4*>(h);
+  if (lo != nullptr) *reinterpret_cast<uint4*>(lo + off) = *reinterpret_cast<const uint4*>(l);
+}
+// mean / rstd of channel c of image n from fp64 {sum, sumsq}; biased variance, eps 1e-5 (InstanceNorm3d).
+__device__ __forceinline__ void finalize_stats(const double* stats, size_t idx, double inv_count, float& mean,
+                                               float& rstd) {
+  const double s = stats[idx * 2], ss = stats[idx * 2 + 1];
+  const double m = s * inv_count;
+  double var = ss * inv_count - m * m;
+  if (var < 0.0) var = 0.0;
+  mean = static_cast<float>(m);
+  rstd = static_cast<float>(1.0 / sqrt(var + 1e-5));
+}
+
+// Block-wide reduction of 8 channel sums + 8 sums of squares, then one fp64 atomic per channel.
+__device__ __forceinline__ void block_accumulate_stats(const float (&y)[8], bool valid, double* stats, size_t idx0) {
+  __shared__ float red[2][8][8];  // [sum|sq][warp][channel]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float v = valid ? y[j] : 0.f;
+    const float s1 = warp_sum(v), s2 = warp_sum(v * v);
+    if (lane == 0) { red[0][warp][j] = s1; red[1][warp][j] = s2; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    const int which = threadIdx.x >> 3, j = threadIdx.x & 7;
+    float t = 0.f;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) t += red[which][w][j];
+    atomicAdd(&stats[(idx0 + j) * 2 + which], static_cast<double>(t));
+  }
+}
+
+// ------------------------------------------------------------------ NCDHW fp32 -> c8 fp16 (hi[/lo])
+__global__ void pack_ncdhw_kernel(const float* __restrict__ src, int C, long long vox, __half* hi, __half* lo,
+                                  int cb_total, int cb_off, int ncb) {
+  const long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const int cb = blockIdx.y % ncb, n = blockIdx.y / ncb;
+  if (v >= vox) return;
+  float x[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = cb * 8 + j;
+    x[j] = c < C ? src[(static_cast<size_t>(n) * C + c) * vox + v] : 0.f;
+  }
+  store8(hi, lo, ((static_cast<size_t>(n) * cb_total + cb_off + cb) * vox + v) * 8, x);
+}
+
+// ------------------------------------------------------------------ c8 fp16 -> NCDHW fp32
+__global__ void unpack_c8_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, int cb_total, int cb_off,
+                                 int C, long long vox, float* dst) {
+  const long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const int ncb = (C + 7) / 8;
+  const int cb = blockIdx.y % ncb, n = blockIdx.y / ncb;
+  if (v >= vox) return;
+  float x[8];
+  load8(hi, lo, ((static_cast<size_t>(n) * cb_total + cb_off + cb) * vox + v) * 8, x);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = cb * 8 + j;
+    if (c < C) dst[(static_cast<size_t>(n) * C + c) * vox + v] = x[j];
+  }
+}
+
+// ------------------------------------------------------------------ InstanceNorm apply (+residual, +chained stats)
+struct NormActParams {
+  const float* raw_f32; const __half* raw_hi; const __half* raw_lo; int in_cb_total, in_cb_off;
+  const double* stats;            // [N][C][2] of the raw tensor, or null (identity)
+  const float* gamma; const float* beta;
+  int act;
+  // residual: either a plain c8 fp16 tensor, or a raw fp32 tensor with its own instance statistics
+  const __half* res_hi; const __half* res_lo; const float* res_raw; const double* res_stats;
+  int res_cb_total, res_cb_off;
+  int act_after_res;
+  __half* out_hi; __half* out_lo; int out_cb_total, out_cb_off;
+  double* stats_out;              // statistics of the produced tensor (chained InstanceNorm), or null
+  int C, ncb; long long vox;
+};
+
+__global__ void __launch_bounds__(256) norm_act_kernel(const NormActParams p) {
+  const long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const int cb = blockIdx.y % p.ncb, n = blockIdx.y / p.ncb;
+  const bool valid = v < p.vox;
+  const double inv = 1.0 / static_cast<double>(p.vox);
+  __shared__ float s_mean[2][8], s_rstd[2][8];
+  if (threadIdx.x < 16) {
+    const int which = threadIdx.x >> 3, c = cb * 8 + (threadIdx.x & 7);
+    const double* st = which ? p.res_stats : p.stats;
+    float m = 0.f, r = 1.f;
+    if (st != nullptr && c < p.C) finalize_stats(st, static_cast<size_t>(n) * p.C + c, inv, m, r);
+    s_mean[which][threadIdx.x & 7] = m;
+    s_rstd[which][threadIdx.x & 7] = r;
+  }
+  __syncthreads();
+  float y[8];
+  if (valid) {
+    const size_t in_off = ((static_cast<size_t>(n) * p.in_cb_total + p.in_cb_off + cb) * p.vox + v) * 8;
+    if (p.raw_f32) load8f(p.raw_f32, in_off, y); else load8(p.raw_hi, p.raw_lo, in_off, y);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = cb * 8 + j;
+      if (c < p.C) {
+        y[j] = (y[j] - s_mean[0][j]) * s_rstd[0][j];
+        if (p.gamma) y[j] = fmaf(y[j], __ldg(&p.gamma[c]), __ldg(&p.beta[c]));
+        y[j] = act_apply(y[j], p.act);
+      } else {
+        y[j] = 0.f;
+      }
+    }
+    if (p.res_hi || p.res_raw) {
+      float r8[8];
+      const size_t r_off = ((static_cast<size_t>(n) * p.res_cb_total + p.res_cb_off + cb) * p.vox + v) * 8;
+      if (p.res_raw) load8f(p.res_raw, r_off, r8); else load8(p.res_hi, p.res_lo, r_off, r8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = cb * 8 + j;
+        if (c < p.C) {
+          r8[j] = (r8[j] - s_mean[1][j]) * s_rstd[1][j];
+          y[j] = act_apply(y[j] + r8[j], p.act_after_res);
+        }
+      }
+    }
+    if (p.out_hi)
+      store8(p.out_hi, p.out_lo, ((static_cast<size_t>(n) * p.out_cb_total + p.out_cb_off + cb) * p.vox + v) * 8, y);
+  }
+  if (p.stats_out) block_accumulate_stats(y, valid, p.stats_out, static_cast<size_t>(n) * p.C + cb * 8);
+}
+
+// ------------------------------------------------------------------ 1x1x1 convolution, normalise-on-load, <=3 sources
+struct PwSource {
+  const __half* hi; const __half* lo; const float* raw; int cb_total, cb_off, C;
+  const double* stats; int act;          // x <- act((x-mean)*rstd) when stats != null, else act(x)
+};
+struct PointwiseParams {
+  PwSource src[3]; int nsrc;
+  const float* w;       // [C_out][C_in_total] fp32 (C_in_total = sum of source C)
+  const float* bias;    // [C_out] or null
+  int cin_total, cout;
+  long long vox;
+  float* out_raw; int out_cb_total, out_cb_off;     // c8 fp32 (+stats) ...
+  __half* out_hi; __half* out_lo;                   // ... or c8 fp16
+  float* out_planar;                                // ... or NCDHW fp32 [N][C_out][vox]
+  double* stats_out;
+  int out_act;
+};
+constexpr int PW_CO = 16;   // output channels per block pass
+
+__global__ void __launch_bounds__(128) pointwise_kernel(const PointwiseParams p) {
+  extern __shared__ float wsm[];           // [cin_total][PW_CO] weights, then [cin_total] mean, [cin_total] rstd
+  float* s_mean = wsm + p.cin_total * PW_CO;
+  float* s_rstd = s_mean + p.cin_total;
+  const int co0 = blockIdx.y * PW_CO;
+  const int n = blockIdx.z;
+  const double inv = 1.0 / static_cast<double>(p.vox);
+  for (int i = threadIdx.x; i < p.cin_total * PW_CO; i += blockDim.x) {
+    const int ci = i / PW_CO, j = i % PW_CO;
+    wsm[i] = (co0 + j < p.cout) ? p.w[static_cast<size_t>(co0 + j) * p.cin_total + ci] : 0.f;
+  }
+  {
+    int base = 0;
+    for (int s = 0; s < p.nsrc; ++s) {
+      for (int c = threadIdx.x; c < p.src[s].C; c += blockDim.x) {
+        float m = 0.f, r = 1.f;
+        if (p.src[s].stats) finalize_stats(p.src[s].stats, static_cast<size_t>(n) * p.src[s].C + c, inv, m, r);
+        s_mean[base + c] = m;
+        s_rstd[base + c] = r;
+      }
+      base += p.src[s].C;
+    }
+  }
+  __syncthreads();
+  const long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const bool valid = v < p.vox;
+  float acc[PW_CO];
+#pragma unroll
+  for (int j = 0; j < PW_CO; ++j) acc[j] = (p.bias && co0 + j < p.cout) ? __ldg(&p.bias[co0 + j]) : 0.f;
+  int ci_base = 0;
+  for (int s = 0; s < p.nsrc; ++s) {
+    const PwSource& S = p.src[s];
+    const int ncb = (S.C + 7) / 8;
+    for (int cb = 0; cb < ncb; ++cb) {
+      float x[8];
+      if (valid) {
+        const size_t off = ((static_cast<size_t>(n) * S.cb_total + S.cb_off + cb) * p.vox + v) * 8;
+        if (S.raw) load8f(S.raw, off, x); else load8(S.hi, S.lo, off, x);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = cb * 8 + j;
+        if (c < S.C) {
+          const float xv = act_apply((x[j] - s_mean[ci_base + c]) * s_rstd[ci_base + c], S.act);
+          const float4* wr = reinterpret_cast<const float4*>(&wsm[(ci_base + c) * PW_CO]);
+#pragma unroll
+          for (int q = 0; q < PW_CO / 4; ++q) {
+            const float4 w4 = wr[q];
+            acc[4 * q + 0] = fmaf(xv, w4.x, acc[4 * q + 0]);
+            acc[4 * q + 1] = fmaf(xv, w4.y, acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(xv, w4.z, acc[4 * q + 2]);
+            acc[4 * q + 3] = fmaf(xv, w4.w, acc[4 * q + 3]);
+          }
+        }
+      }
+    }
+    ci_base += S.C;
+  }
+#pragma unroll
+  for (int j = 0; j < PW_CO; ++j) acc[j] = act_apply(acc[j], p.out_act);
+  if (valid) {
+    if (p.out_planar) {
+#pragma unroll
+      for (int j = 0; j < PW_CO; ++j)
+        if (co0 + j < p.cout) p.out_planar[(static_cast<size_t>(n) * p.cout + co0 + j) * p.vox + v] = acc[j];
+    }
+#pragma unroll
+    for (int b = 0; b < PW_CO / 8; ++b) {
+      if (co0 + b * 8 >= p.cout) break;
+      const size_t off = ((static_cast<size_t>(n) * p.out_cb_total + p.out_cb_off + (co0 >> 3) + b) * p.vox + v) * 8;
+      float y[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) y[j] = acc[b * 8 + j];
+      if (p.out_raw) {
+        *reinterpret_cast<float4*>(p.out_raw + off) = make_float4(y[0], y[1], y[2], y[3]);
+        *reinterpret_cast<float4*>(p.out_raw + off + 4) = make_float4(y[4], y[5], y[6], y[7]);
+      }
+      if (p.out_hi) store8(p.out_hi, p.out_lo, off, y);
+    }
+  }
+  if (p.stats_out) {
+#pragma unroll
+    for (int b = 0; b < PW_CO / 8; ++b) {
+      if (co0 + b * 8 >= p.cout) break;          // block-uniform
+      float y[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) y[j] = acc[b * 8 + j];
+      block_accumulate_stats(y, valid, p.stats_out, static_cast<size_t>(n) * p.cout + co0 + b * 8);
+      __syncthreads();
+    }
+  }
+}
+
+// ------------------------------------------------------------------ ConvTranspose3d k=2 s=2 (no bias)
+// out[n, co, 2d+i, 2h+j, 2w+l] = sum_ci in[n, ci, d, h, w] * W[ci, co, i, j, l]
+struct DeconvParams {
+  const __half* in_hi; const __half* in_lo;
+  long long in_nstride, in_vstride, in_cbstride;     // element strides (c8: vstride 8; token-major: vstride C)
+  int cin, cout, D, H, W;                            // input spatial dims
+  const float* w;                                    // packed [8 parity][cin][cout] fp32
+  __half* out_hi; __half* out_lo; int out_cb_total, out_cb_off;
+};
+constexpr int DC_CO = 16;
+__global__ void __launch_bounds__(128) deconv2x_kernel(const DeconvParams p) {
+  extern __shared__ float wsm[];   // [cin][DC_CO] for the current parity
+  const int co0 = blockIdx.y * DC_CO, n = blockIdx.z;
+  const long long vox_in = static_cast<long long>(p.D) * p.H * p.W;
+  const long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const bool valid = v < vox_in;
+  const int w = static_cast<int>(v % p.W), h = static_cast<int>((v / p.W) % p.H), d = static_cast<int>(v / (static_cast<long long>(p.W) * p.H));
+  const int ncb = p.cin / 8;
+  const long long vox_out = vox_in * 8;
+  for (int q = 0; q < 8; ++q) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < p.cin * DC_CO; i += blockDim.x) {
+      const int ci = i / DC_CO, j = i % DC_CO;
+      wsm[i] = (co0 + j < p.cout) ? p.w[(static_cast<size_t>(q) * p.cin + ci) * p.cout + co0 + j] : 0.f;
+    }
+    __syncthreads();
+    if (!valid) continue;
+    float acc[DC_CO];
+#pragma unroll
+    for (int j = 0; j < DC_CO; ++j) acc[j] = 0.f;
+    for (int cb = 0; cb < ncb; ++cb) {
+      float x[8];
+      load8(p.in_hi, p.in_lo, static_cast<size_t>(n) * p.in_nstride + v * p.in_vstride + cb * p.in_cbstride, x);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4* wr = reinterpret_cast<const float4*>(&wsm[(cb * 8 + j) * DC_CO]);
+#pragma unroll
+        for (int t = 0; t < DC_CO / 4; ++t) {
+          const float4 w4 = wr[t];
+          acc[4 * t + 0] = fmaf(x[j], w4.x, acc[4 * t + 0]);
+          acc[4 * t + 1] = fmaf(x[j], w4.y, acc[4 * t + 1]);
+          acc[4 * t + 2] = fmaf(x[j], w4.z, acc[4 * t + 2]);
+          acc[4 * t + 3] = fmaf(x[j], w4.w, acc[4 * t + 3]);
+        }
+      }
+    }
+    const int i = q >> 2, j2 = (q >> 1) & 1, l = q & 1;
+    const long long vo = (static_cast<long long>(2 * d + i) * (2 * p.H) + (2 * h + j2)) * (2 * p.W) + (2 * w + l);
+#pragma unroll
+    for (int b = 0; b < DC_CO / 8; ++b) {
+      if (co0 + b * 8 >= p.cout) break;
+      float y[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) y[t] = acc[b * 8 + t];
+      store8(p.out_hi, p.out_lo, ((static_cast<size_t>(n) * p.out_cb_total + p.out_cb_off + (co0 >> 3) + b) * vox_out + vo) * 8, y);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ trilinear 2x, align_corners=True (c3d.py:36)
+__global__ void __launch_bounds__(256)
+upsample2x_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo, int in_cb_total, int in_cb_off,
+                  int ncb, int D, int H, int W, __half* out_hi, __half* out_lo, int out_cb_total, int out_cb_off) {
+  const int Do = 2 * D, Ho = 2 * H, Wo = 2 * W;
+  const long long vox_o = static_cast<long long>(Do) * Ho * Wo, vox_i = static_cast<long long>(D) * H * W;
+  const long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (v >= vox_o) return;
+  const int cb = blockIdx.y % ncb, n = blockIdx.y / ncb;
+  const int wo = static_cast<int>(v % Wo), ho = static_cast<int>((v / Wo) % Ho), dz = static_cast<int>(v / (static_cast<long long>(Wo) * Ho));
+  // torch area_pixel_compute_source_index(align_corners=True): src = dst * (in-1)/(out-1)
+  const float sd = Do > 1 ? static_cast<float>(D - 1) / static_cast<float>(Do - 1) : 0.f;
+  const float sh = Ho > 1 ? static_cast<float>(H - 1) / static_cast<float>(Ho - 1) : 0.f;
+  const float sw = Wo > 1 ? static_cast<float>(W - 1) / static_cast<float>(Wo - 1) : 0.f;
+  const float fd = sd * dz, fh = sh * ho, fw = sw * wo;
+  const int d0 = static_cast<int>(fd), h0 = static_cast<int>(fh), w0 = static_cast<int>(fw);
+  const int d1 = min(d0 + 1, D - 1), h1 = min(h0 + 1, H - 1), w1 = min(w0 + 1, W - 1);
+  const float ld = fd - d0, lh = fh - h0, lw = fw - w0;
+  const size_t base = (static_cast<size_t>(n) * in_cb_total + in_cb_off + cb) * vox_i;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+  for (int corner = 0; corner < 8; ++corner) {
+    const int dd = (corner & 4) ? d1 : d0, hh = (corner & 2) ? h1 : h0, ww = (corner & 1) ? w1 : w0;
+    const float wt = ((corner & 4) ? ld : 1.f - ld) * ((corner & 2) ? lh : 1.f - lh) * ((corner & 1) ? lw : 1.f - lw);
+    float x[8];
+    load8(in_hi, in_lo, (base + (static_cast<size_t>(dd) * H + hh) * W + ww) * 8, x);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = fmaf(wt, x[j], acc[j]);
+  }
+  store8(out_hi, out_lo, ((static_cast<size_t>(n) * out_cb_total + out_cb_off + cb) * vox_o + v) * 8, acc);
+}
+
+// ------------------------------------------------------------------ LayerNorm over the last dim (one warp per row)
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, int rows,
+                 int cols, __half* out_f16, float* out_f32) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = x + static_cast<size_t>(row) * cols;
+  float s = 0.f;
+  for (int c = lane; c < cols; c += 32) s += xr[c];
+  const float mean = warp_sum(s) / cols;
+  float ss = 0.f;
+  for (int c = lane; c < cols; c += 32) { const float d = xr[c] - mean; ss = fmaf(d, d, ss); }
+  const float rstd = rsqrtf(warp_sum(ss) / cols + 1e-5f);
+  for (int c = lane; c < cols; c += 32) {
+    const float y = fmaf((xr[c] - mean) * rstd, gamma[c], beta[c]);
+    if (out_f16) out_f16[static_cast<size_t>(row) * cols + c] = __float2half_rn(y);
+    if (out_f32) out_f32[static_cast<size_t>(row) * cols + c] = y;
+  }
+}
+
+// ------------------------------------------------------------------ row softmax fp32 -> fp16 (one warp per row)
+__global__ void __launch_bounds__(256)
+softmax_kernel(const float* __restrict__ s, int rows, int cols, int ld_in, __half* p, int ld_out) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* sr = s + static_cast<size_t>(row) * ld_in;
+  float mx = -INFINITY;
+  for (int c = lane; c < cols; c += 32) mx = fmaxf(mx, sr[c]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.f;
+  for (int c = lane; c < cols; c += 32) sum += __expf(sr[c] - mx);
+  const float inv = 1.f / warp_sum(sum);
+  for (int c = lane; c < cols; c += 32) p[static_cast<size_t>(row) * ld_out + c] = __float2half_rn(__expf(sr[c] - mx) * inv);
+}
+
+// ------------------------------------------------------------------ 16^3 patch flattening for the "perceptron" embedding
+// einops 'b c (h p1)(w p2)(d p3) -> b (h w d)(p1 p2 p3 c)' restated for the c8 layout: K order is
+// (c8-block, p1, p2, p3, c%8); the Linear weight is permuted identically when packed.
+__global__ void __launch_bounds__(256)
+patchify_kernel(const __half* __restrict__ in, int cb_total, int cb_off, int ncb, int S0, int S1, int S2, __half* out) {
+  const int g0 = S0 / 16, g1 = S1 / 16, g2 = S2 / 16;
+  const long long total = static_cast<long long>(g0) * g1 * g2 * ncb * 16 * 16 * 16;
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  const int n = blockIdx.y;
+  long long t = i;
+  const int p3 = static_cast<int>(t % 16); t /= 16;
+  const int p2 = static_cast<int>(t % 16); t /= 16;
+  const int p1 = static_cast<int>(t % 16); t /= 16;
+  const int cb = static_cast<int>(t % ncb); t /= ncb;
+  const int tok = static_cast<int>(t);
+  const int gz = tok % g2, gy = (tok / g2) % g1, gx = tok / (g2 * g1);
+  const size_t vox = (static_cast<size_t>(gx * 16 + p1) * S1 + (gy * 16 + p2)) * S2 + (gz * 16 + p3);
+  const size_t vol = static_cast<size_t>(S0) * S1 * S2;
+  const uint4 val = *reinterpret_cast<const uint4*>(in + ((static_cast<size_t>(n) * cb_total + cb_off + cb) * vol + vox) * 8);
+  const size_t K = static_cast<size_t>(ncb) * 4096 * 8;
+  const size_t ntok = static_cast<size_t>(g0) * g1 * g2;
+  *reinterpret_cast<uint4*>(out + (static_cast<size_t>(n) * ntok + tok) * K + ((static_cast<size_t>(cb) * 16 + p1) * 16 + p2) * 128 + p3 * 8) = val;
+}
+
+// ------------------------------------------------------------------ cascade hand-off (train_light_linked_model.py:156-167)
+// logits [N,8,X,Y,Z] fp32 -> argmax (first maximum wins) -> 7 one-hot OAR masks, spatially transposed
+// (x,y,z)->(z,y,x), + PTV (not transposed) + CT (transposed) -> dose-net input, written both as the c8
+// fp16 hi/lo tensor the dose net consumes and (optionally) as NCDHW fp32 "structures".
+__global__ void __launch_bounds__(256)
+handoff_kernel(const float* __restrict__ logits, int ncls, const float* __restrict__ ptv, const float* __restrict__ ct,
+               int S, __half* out_hi, __half* out_lo, int out_cb_total, int out_cb_off, float* structures) {
+  // tile over (x, z) for fixed y: source index [x][y][z] (z fastest); destination voxel (a=z, b=y, c=x) (c fastest)
+  __shared__ uint8_t cls[32][33];
+  __shared__ float ctv[32][33];
+  const int n = blockIdx.z / S, y = blockIdx.z % S;
+  const int x0 = blockIdx.y * 32, z0 = blockIdx.x * 32;
+  const size_t vol = static_cast<size_t>(S) * S * S;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  for (int r = ty; r < 32; r += 8) {
+    const int x = x0 + r, z = z0 + tx;
+    if (x < S && z < S) {
+      const size_t v = (static_cast<size_t>(x) * S + y) * S + z;
+      float best = logits[(static_cast<size_t>(n) * ncls) * vol + v];
+      int arg = 0;
+      for (int c = 1; c < ncls; ++c) {
+        const float l = logits[(static_cast<size_t>(n) * ncls + c) * vol + v];
+        if (l > best) { best = l; arg = c; }
+      }
+      cls[r][tx] = static_cast<uint8_t>(arg);
+      ctv[r][tx] = ct[static_cast<size_t>(n) * vol + v];
+    }
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int a = z0 + r, c = x0 + tx;          // destination (a, y, c); source (x=c, y, z=a)
+    if (a < S && c < S) {
+      const size_t vo = (static_cast<size_t>(a) * S + y) * S + c;
+      const int k = cls[tx][r];
+      float ch[16];
+      ch[0] = ptv[static_cast<size_t>(n) * vol + vo];
+#pragma unroll
+      for (int j = 1; j < 8; ++j) ch[j] = (k == j) ? 1.f : 0.f;
+      ch[8] = ctv[tx][r];
+#pragma unroll
+      for (int j = 9; j < 16; ++j) ch[j] = 0.f;
+      float lo8[8], hi8[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { lo8[j] = ch[j]; hi8[j] = ch[8 + j]; }
+      store8(out_hi, out_lo, ((static_cast<size_t>(n) * out_cb_total + out_cb_off) * vol + vo) * 8, lo8);
+      store8(out_hi, out_lo, ((static_cast<size_t>(n) * out_cb_total + out_cb_off + 1) * vol + vo) * 8, hi8);
+      if (structures) {
+#pragma unroll
+        for (int j = 0; j < 9; ++j) structures[(static_cast<size_t>(n) * 9 + j) * vol + vo] = ch[j];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ generic direct convolution (strided convs)
+// out[n,co,do,ho,wo] = bias + sum_{ci,kd,kh,kw} in[n,ci,do*s+kd*dil-pad,...] * w[co,ci,kd,kh,kw]
+// One thread = one output voxel x DC2_CO output channels, fp32 math on fp16 hi(+lo) c8 inputs.
+struct DirectConvParams {
+  const __half* in_hi; const __half* in_lo; int in_cb_total, in_cb_off, cin;
+  int D, H, W, Do, Ho, Wo, k, stride, dil, pad;
+  const float* w;        // packed [tap][cin][cout] fp32
+  const float* scale; const float* shift; int relu; int cout;
+  float* out_raw; __half* out_hi; __half* out_lo; int out_cb_total, out_cb_off;
+  double* stats_out;
+};
+constexpr int DC2_CO = 16;
+constexpr int DC2_CI = 32;   // input channels staged per shared-memory weight tile
+__global__ void __launch_bounds__(128) direct_conv_kernel(const DirectConvParams p) {
+  extern __shared__ float wsm[];   // [taps][DC2_CI][DC2_CO]
+  const int co0 = blockIdx.y * DC2_CO, n = blockIdx.z;
+  const long long vox_o = static_cast<long long>(p.Do) * p.Ho * p.Wo, vox_i = static_cast<long long>(p.D) * p.H * p.W;
+  const long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const bool valid = v < vox_o;
+  const int wo = static_cast<int>(v % p.Wo), ho = static_cast<int>((v / p.Wo) % p.Ho), dd = static_cast<int>(v / (static_cast<long long>(p.Wo) * p.Ho));
+  const int taps = p.k * p.k * p.k;
+  float acc[DC2_CO];
+#pragma unroll
+  for (int j = 0; j < DC2_CO; ++j) acc[j] = 0.f;
+  for (int ci0 = 0; ci0 < p.cin; ci0 += DC2_CI) {
+    const int nci = min(DC2_CI, p.cin - ci0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < taps * nci * DC2_CO; i += blockDim.x) {
+      const int j = i % DC2_CO, ci = (i / DC2_CO) % nci, tap = i / (DC2_CO * nci);
+      wsm[(tap * DC2_CI + ci) * DC2_CO + j] =
+          (co0 + j < p.cout) ? p.w[(static_cast<size_t>(tap) * p.cin + ci0 + ci) * p.cout + co0 + j] : 0.f;
+    }
+    __syncthreads();
+    if (!valid) continue;
+    for (int kd = 0; kd < p.k; ++kd) {
+      const int z = dd * p.stride + kd * p.dil - p.pad;
+      if (z < 0 || z >= p.D) continue;
+      for (int kh = 0; kh < p.k; ++kh) {
+        const int y = ho * p.stride + kh * p.dil - p.pad;
+        if (y < 0 || y >= p.H) continue;
+        for (int kw = 0; kw < p.k; ++kw) {
+          const int x = wo * p.stride + kw * p.dil - p.pad;
+          if (x < 0 || x >= p.W) continue;
+          const int tap = (kd * p.k + kh) * p.k + kw;
+          const size_t vi = (static_cast<size_t>(z) * p.H + y) * p.W + x;
+          for (int cb = 0; cb < nci / 8; ++cb) {
+            float xin[8];
+            load8(p.in_hi, p.in_lo, ((static_cast<size_t>(n) * p.in_cb_total + p.in_cb_off + (ci0 >> 3) + cb) * vox_i + vi) * 8, xin);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4* wr = reinterpret_cast<const float4*>(&wsm[(tap * DC2_CI + cb * 8 + j) * DC2_CO]);
+#pragma unroll
+              for (int t = 0; t < DC2_CO / 4; ++t) {
+                const float4 w4 = wr[t];
+                acc[4 * t + 0] = fmaf(xin[j], w4.x, acc[4 * t + 0]);
+                acc[4 * t + 1] = fmaf(xin[j], w4.y, acc[4 * t + 1]);
+                acc[4 * t + 2] = fmaf(xin[j], w4.z, acc[4 * t + 2]);
+                acc[4 * t + 3] = fmaf(xin[j], w4.w, acc[4 * t + 3]);
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < DC2_CO; ++j) {
+    if (co0 + j < p.cout) {
+      acc[j] = fmaf(acc[j], __ldg(&p.scale[co0 + j]), __ldg(&p.shift[co0 + j]));
+      if (p.relu) acc[j] = fmaxf(acc[j], 0.f);
+    }
+  }
+#pragma unroll
+  for (int b = 0; b < DC2_CO / 8; ++b) {
+    if (co0 + b * 8 >= p.cout) break;
+    float y[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) y[j] = acc[b * 8 + j];
+    if (valid) {
+      const size_t off = ((static_cast<size_t>(n) * p.out_cb_total + p.out_cb_off + (co0 >> 3) + b) * vox_o + v) * 8;
+      if (p.out_raw) {
+        *reinterpret_cast<float4*>(p.out_raw + off) = make_float4(y[0], y[1], y[2], y[3]);
+        *reinterpret_cast<float4*>(p.out_raw + off + 4) = make_float4(y[4], y[5], y[6], y[7]);
+      }
+      if (p.out_hi) store8(p.out_hi, p.out_lo, off, y);
+    }
+    if (p.stats_out) {
+      block_accumulate_stats(y, valid, p.stats_out, static_cast<size_t>(n) * p.cout + co0 + b * 8);
+      __syncthreads();
+    }
+  }
+}
+
+}  // namespace dp
+
+// =============================================================================== C ABI wrappers
+using namespace dp;
+
+static inline unsigned blocks_for(long long n, int threads) { return static_cast<unsigned>((n + threads - 1) / threads); }
+
+extern "C" int dp_pack_ncdhw(const float* src, int N, int C, long long vox, void* hi, void* lo, int cb_total, int cb_off,
+                             cudaStream_t stream) {
+  const int ncb = (C + 7) / 8;
+  DP_REQUIRE(N > 0 && C > 0 && vox > 0, "dp_pack_ncdhw: empty tensor");
+  dim3 grid(blocks_for(vox, 256), N * ncb);
+  pack_ncdhw_kernel<<<grid, 256, 0, stream>>>(src, C, vox, static_cast<__half*>(hi), static_cast<__half*>(lo), cb_total, cb_off, ncb);
+  DP_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dp_unpack_c8(const void* hi, const void* lo, int cb_total, int cb_off, int N, int C, long long vox,
+                            float* dst, cudaStream_t stream) {
+  const int ncb = (C + 7) / 8;
+  dim3 grid(blocks_for(vox, 256), N * ncb);
+  unpack_c8_kernel<<<grid, 256, 0, stream>>>(static_cast<const __half*>(hi), static_cast<const __half*>(lo), cb_total, cb_off, C, vox, dst);
+  DP_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dp_norm_act(const float* raw_f32, const void* raw_hi, const void* raw_lo, int in_cb_total, int in_cb_off,
+                           const double* stats, const float* gamma, const float* beta, int act, const void* res_hi,
+                           const void* res_lo, const float* res_raw, const double* res_stats, int res_cb_total,
+                           int res_cb_off, int act_after_res, void* out_hi, void* out_lo, int out_cb_total,
+                           int out_cb_off, double* stats_out, int N, int C, long long vox, cudaStream_t stream) {
+  DP_REQUIRE(raw_f32 != nullptr || raw_hi != nullptr, "dp_norm_act: no input");
+  NormActParams p{};
+  p.raw_f32 = raw_f32; p.raw_hi = static_cast<const __half*>(raw_hi); p.raw_lo = static_cast<const __half*>(raw_lo);
+  p.in_cb_total = in_cb_total; p.in_cb_off = in_cb_off; p.stats = stats; p.gamma = gamma; p.beta = beta; p.act = act;
+  p.res_hi = static_cast<const __half*>(res_hi); p.res_lo = static_cast<const __half*>(res_lo); p.res_raw = res_raw;
+  p.res_stats = res_stats; p.res_cb_total = res_cb_total; p.res_cb_off = res_cb_off; p.act_after_res = act_after_res;
+  p.out_hi = static_cast<__half*>(out_hi); p.out_lo = static_cast<__half*>(out_lo); p.out_cb_total = out_cb_total;
+  p.out_cb_off = out_cb_off; p.stats_out = stats_out; p.C = C; p.ncb = (C + 7) / 8; p.vox = vox;
+  dim3 grid(blocks_for(vox, 256), N * p.ncb);
+  norm_act_kernel<<<grid, 256, 0, stream>>>(p);
+  DP_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dp_pointwise_conv(int nsrc, const void* const* src_hi, const void* const* src_lo, const float* const* src_raw,
+                                 const int* src_cb_total, const int* src_cb_off, const int* src_C,
+                                 const double* const* src_stats, const int* src_act, const float* w, const float* bias,
+                                 int cout, int N, long long vox, float* out_raw, void* out_hi, void* out_lo,
+                                 int out_cb_total, int out_cb_off, float* out_planar, double* stats_out, int out_act,
+                                 cudaStream_t stream) {
+  DP_REQUIRE(nsrc >= 1 && nsrc <= 3, "dp_pointwise_conv: 1..3 sources supported, got %d", nsrc);
+  PointwiseParams p{};
+  p.nsrc = nsrc;
+  int cin = 0;
+  for (int s = 0; s < nsrc; ++s) {
+    p.src[s].hi = static_cast<const __half*>(src_hi[s]);
+    p.src[s].lo = static_cast<const __half*>(src_lo ? src_lo[s] : nullptr);
+    p.src[s].raw = src_raw ? src_raw[s] : nullptr;
+    p.src[s].cb_total = src_cb_total[s]; p.src[s].cb_off = src_cb_off[s]; p.src[s].C = src_C[s];
+    p.src[s].stats = src_stats ? src_stats[s] : nullptr; p.src[s].act = src_act ? src_act[s] : 0;
+    DP_REQUIRE(p.src[s].hi || p.src[s].raw, "dp_pointwise_conv: source %d has no tensor", s);
+    cin += src_C[s];
+  }
+  p.w = w; p.bias = bias; p.cin_total = cin; p.cout = cout; p.vox = vox;
+  p.out_raw = out_raw; p.out_hi = static_cast<__half*>(out_hi); p.out_lo = static_cast<__half*>(out_lo);
+  p.out_cb_total = out_cb_total; p.out_cb_off = out_cb_off; p.out_planar = out_planar; p.stats_out = stats_out;
+  p.out_act = out_act;
+  const size_t smem = static_cast<size_t>(cin) * (PW_CO + 2) * sizeof(float);
+  DP_REQUIRE(smem <= 96 * 1024, "dp_pointwise_conv: C_in=%d too large", cin);
+  static size_t configured = 48 * 1024;
+  if (smem > configured) {
+    DP_CHECK(cudaFuncSetAttribute(pointwise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    configured = 96 * 1024;
+  }
+  dim3 grid(blocks_for(vox, 128), (cout + PW_CO - 1) / PW_CO, N);
+  pointwise_kernel<<<grid, 128, smem, stream>>>(p);
+  DP_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dp_deconv2x(const void* in_hi, const void* in_lo, long long in_nstride, long long in_vstride,
+                           long long in_cbstride, int cin, int cout, int N, int D, int H, int W, const float* w_packed,
+                           void* out_hi, void* out_lo, int out_cb_total, int out_cb_off, cudaStream_t stream) {
+  DP_REQUIRE(cin % 8 == 0, "dp_deconv2x: C_in=%d must be a multiple of 8", cin);
+  DeconvParams p{};
+  p.in_hi = static_cast<const __half*>(in_hi); p.in_lo = static_cast<const __half*>(in_lo);
+  p.in_nstride = in_nstride; p.in_vstride = in_vstride; p.in_cbstride = in_cbstride;
+  p.cin = cin; p.cout = cout; p.D = D; p.H = H; p.W = W; p.w = w_packed;
+  p.out_hi = static_cast<__half*>(out_hi); p.out_lo = static_cast<__half*>(out_lo);
+  p.out_cb_total = out_cb_total; p.out_cb_off = out_cb_off;
+  const size_t smem = static_cast<size_t>(cin) * DC_CO * sizeof(float);
+  static size_t configured = 48 * 1024;
+  if (smem > configured) {
+    DP_CHECK(cudaFuncSetAttribute(deconv2x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    configured = 96 * 1024;
+  }
+  DP_REQUIRE(smem <= 96 * 1024, "dp_deconv2x: C_in=%d too large", cin);
+  const long long vox = static_cast<long long>(D) * H * W;
+  dim3 grid(blocks_for(vox, 128), (cout + DC_CO - 1) / DC_CO, N);
+  deconv2x_kernel<<<grid, 128, smem, stream>>>(p);
+  DP_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dp_upsample2x(const void* in_hi, const void* in_lo, int in_cb_total, int in_cb_off, int ncb, int N, int D,
+                             int H, int W, void* out_hi, void* out_lo, int out_cb_total, int out_cb_off,
+                             cudaStream_t stream) {
+  const long long vox_o = 8LL * D * H * W;
+  dim3 grid(blocks_for(vox_o, 256), N * ncb);
+  upsample2x_kernel<<<grid, 256, 0, stream>>>(static_cast<const __half*>(in_hi), static_cast<const __half*>(in_lo),
+                                              in_cb_total, in_cb_off, ncb, D, H, W, static_cast<__half*>(out_hi),
+                                              static_cast<__half*>(out_lo), out_cb_total, out_cb_off);
+  DP_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dp_layernorm(const float* x, const float* gamma, const float* beta, int rows, int cols, void* out_f16,
+                            float* out_f32, cudaStream_t stream) {
+  layernorm_kernel<<<blocks_for(rows, 8), 256, 0, stream>>>(x, gamma, beta, rows, cols, static_cast<__half*>(out_f16), out_f32);
+  DP_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dp_softmax(const float* s, int rows, int cols, int ld_in, void* p, int ld_out, cudaStream_t stream) {
+  softmax_kernel<<<blocks_for(rows, 8), 256, 0, stream>>>(s, rows, cols, ld_in, static_cast<__half*>(p), ld_out);
+  DP_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dp_patchify(const void* in_c8, int cb_total, int cb_off, int ncb, int N, int S0, int S1, int S2, void* out,
+                           cudaStream_t stream) {
+  DP_REQUIRE(S0 % 16 == 0 && S1 % 16 == 0 && S2 % 16 == 0, "dp_patchify: volume %dx%dx%d not divisible by the 16^3 patch", S0, S1, S2);
+  const long long total = static_cast<long long>(S0 / 16) * (S1 / 16) * (S2 / 16) * ncb * 4096;
+  dim3 grid(blocks_for(total, 256), N);
+  patchify_kernel<<<grid, 256, 0, stream>>>(static_cast<const __half*>(in_c8), cb_total, cb_off, ncb, S0, S1, S2, static_cast<__half*>(out));
+  DP_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dp_handoff(const float* logits, int ncls, const float* ptv, const float* ct, int N, int S, void* out_hi,
+                          void* out_lo, int out_cb_total, int out_cb_off, float* structures, cudaStream_t stream) {
+  DP_REQUIRE(ncls == 8, "dp_handoff: expects background + 7 OAR classes, got %d", ncls);
+  dim3 grid((S + 31) / 32, (S + 31) / 32, N * S);
+  handoff_kernel<<<grid, 256, 0, stream>>>(logits, ncls, ptv, ct, S, static_cast<__half*>(out_hi), static_cast<__half*>(out_lo),
+                                           out_cb_total, out_cb_off, structures);
+  DP_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dp_conv3d_direct(const void* in_hi, const void* in_lo, int in_cb_total, int in_cb_off, int cin, int N, int D,
+                                int H, int W, int k, int stride, int dil, const float* w_packed, const float* scale,
+                                const float* shift, int relu, int cout, float* out_raw, void* out_hi, void* out_lo,
+                                int out_cb_total, int out_cb_off, double* stats_out, cudaStream_t stream) {
+  DP_REQUIRE(cin % 8 == 0, "dp_conv3d_direct: C_in=%d must be a multiple of 8", cin);
+  DirectConvParams p{};
+  p.in_hi = static_cast<const __half*>(in_hi); p.in_lo = static_cast<const __half*>(in_lo);
+  p.in_cb_total = in_cb_total; p.in_cb_off = in_cb_off; p.cin = cin;
+  p.D = D; p.H = H; p.W = W; p.k = k; p.stride = stride; p.dil = dil; p.pad = dil * (k - 1) / 2;
+  p.Do = (D + 2 * p.pad - dil * (k - 1) - 1) / stride + 1;
+  p.Ho = (H + 2 * p.pad - dil * (k - 1) - 1) / stride + 1;
+  p.Wo = (W + 2 * p.pad - dil * (k - 1) - 1) / stride + 1;
+  p.w = w_packed; p.scale = scale; p.shift = shift; p.relu = relu; p.cout = cout;
+  p.out_raw = out_raw; p.out_hi = static_cast<__half*>(out_hi); p.out_lo = static_cast<__half*>(out_lo);
+  p.out_cb_total = out_cb_total; p.out_cb_off = out_cb_off; p.stats_out = stats_out;
+  const size_t smem = static_cast<size_t>(k) * k * k * DC2_CI * DC2_CO * sizeof(float);
+  DP_REQUIRE(smem <= 200 * 1024, "dp_conv3d_direct: kernel %d too large for the weight tile", k);
+  static size_t configured = 48 * 1024;
+  if (smem > configured) {
+    DP_CHECK(cudaFuncSetAttribute(direct_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    configured = smem;
+  }
+  const long long vox_o = static_cast<long long>(p.Do) * p.Ho * p.Wo;
+  dim3 grid(blocks_for(vox_o, 128), (cout + DC2_CO - 1) / DC2_CO, N);
+  direct_conv_kernel<<<grid, 128, smem, stream>>>(p);
+  DP_CHECK(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,405 @@
+"""Host-side plan builder / executor over the C ABI (include/dose_b200.h).
+
+A `Plan` is built once per (network, input shape): it walks the network graph symbolically, allocates
+every activation buffer statically, packs the module's parameters into the layouts the kernels want
+and records one (function, args) tuple per kernel launch.  `Plan.run()` replays the launches on the
+current CUDA stream (optionally as one CUDA graph).  PyTorch is used for device memory, streams and
+one-time weight re-layout only; every launch inside `run()` is one of our kernels.
+
+Activation layout "c8": fp16 [N][C/8][D][H][W][8]; channel counts are padded to multiples of 16 so a
+tensor-core K step (16 channels) is two channel blocks.  A buffer may carry an fp16 "lo" residue part
+(x ~ hi + lo, ~22 mantissa bits) for the precision-critical layers.
+"""
+import ctypes
+import math
+
+import torch
+
+from . import _lib
+
+ACT_NONE, ACT_RELU, ACT_LRELU, ACT_MISH, ACT_GELU = 0, 1, 2, 3, 4
+ACT_ID = {None: ACT_NONE, "none": ACT_NONE, "relu": ACT_RELU, "lrelu": ACT_LRELU, "mish": ACT_MISH, "gelu": ACT_GELU}
+STATS_DOUBLES = 1 << 20
+EPS = 1e-5
+
+
+def ceil_div(a, b):
+    return (a + b - 1) // b
+
+
+def blocks16(C):
+    """channel blocks reserved for C logical channels (padded to a multiple of 16)."""
+    return 2 * ceil_div(C, 16)
+
+
+class Act:
+    """C logical channels living in channel blocks [cb_off, cb_off+blocks16(C)) of a c8 fp16 buffer;
+    lo_off = first block of the fp16 residue part, or None."""
+    __slots__ = ("buf", "cb_off", "C", "lo_off")
+
+    def __init__(self, buf, cb_off, C, lo_off=None):
+        self.buf, self.cb_off, self.C, self.lo_off = buf, cb_off, C, lo_off
+
+    @property
+    def N(self):
+        return self.buf.shape[0]
+
+    @property
+    def cb_total(self):
+        return self.buf.shape[1]
+
+    @property
+    def dims(self):
+        return tuple(self.buf.shape[2:5])
+
+    @property
+    def vox(self):
+        d = self.dims
+        return d[0] * d[1] * d[2]
+
+    @property
+    def hi_ptr(self):
+        return self.buf.data_ptr()
+
+    @property
+    def lo_ptr(self):
+        if self.lo_off is None:
+            return None
+        return self.buf.data_ptr() + (self.lo_off - self.cb_off) * self.vox * 16
+
+
+class Raw:
+    """fp32 c8 pre-normalisation tensor + its per-(n,c) {sum, sumsq} statistics."""
+    __slots__ = ("t", "C", "stats")
+
+    def __init__(self, t, C, stats):
+        self.t, self.C, self.stats = t, C, stats
+
+    @property
+    def cb_total(self):
+        return self.t.shape[1]
+
+
+class Tokens:
+    """[B, T, C] fp16 token matrix read in place by the transposed convolutions (proj_feat is a no-op)."""
+    __slots__ = ("t", "grid")
+
+    def __init__(self, t, grid):
+        self.t, self.grid = t, grid
+
+
+class Plan:
+    def __init__(self, device):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("dose_prediction_b200 runs on CUDA devices only (no CPU fallback)")
+        self.lib = _lib.lib()
+        self.steps = []
+        self.stats = torch.zeros(STATS_DOUBLES, dtype=torch.float64, device=self.device)
+        self.stats_used = 0
+        self.err = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.keep = []
+        self.pool = {}
+        self.bytes_alloc = 0
+        self.graph = None
+        self.launches = 0
+
+    # ------------------------------------------------------------------ memory
+    def zeros(self, shape, dtype):
+        t = torch.zeros(shape, dtype=dtype, device=self.device)
+        self.bytes_alloc += t.numel() * t.element_size()
+        self.keep.append(t)
+        return t
+
+    def new_buf(self, N, cb_total, dims):
+        return self.zeros((N, cb_total) + tuple(dims) + (8,), torch.float16)
+
+    def new_act(self, N, C, dims, lo=False):
+        nb = blocks16(C)
+        buf = self.new_buf(N, nb * (2 if lo else 1), dims)
+        return Act(buf, 0, C, nb if lo else None)
+
+    def new_concat(self, N, Cs, dims, lo=False):
+        """one buffer holding the channel concatenation of len(Cs) tensors (torch.cat made free)."""
+        nbs = [blocks16(c) for c in Cs]
+        tot = sum(nbs)
+        buf = self.new_buf(N, tot * (2 if lo else 1), dims)
+        acts, off = [], 0
+        for c, nb in zip(Cs, nbs):
+            acts.append(Act(buf, off, c, tot + off if lo else None))
+            off += nb
+        return acts
+
+    def new_stats(self, N, C):
+        n = N * C * 2
+        if self.stats_used + n > STATS_DOUBLES:
+            raise RuntimeError("statistics arena exhausted")
+        s = self.stats[self.stats_used:self.stats_used + n]
+        self.stats_used += n
+        return s
+
+    def get_raw(self, N, C, dims, with_stats=True):
+        key = (N, blocks16(C)) + tuple(dims)
+        free = self.pool.setdefault(key, [])
+        t = free.pop() if free else self.zeros((N, blocks16(C)) + tuple(dims) + (8,), torch.float32)
+        return Raw(t, C, self.new_stats(N, C) if with_stats else None)
+
+    def release(self, raw):
+        key = (raw.t.shape[0], raw.t.shape[1]) + tuple(raw.t.shape[2:5])
+        self.pool[key].append(raw.t)
+
+    def dev(self, t, dtype=torch.float32):
+        t = t.detach().to(device=self.device, dtype=dtype).contiguous()
+        self.keep.append(t)
+        return t
+
+    # ------------------------------------------------------------------ recording / replay
+    def add(self, name, *args):
+        self.steps.append((getattr(self.lib, name), args, name))
+
+    def add_zero(self, t):
+        """re-zero a (split-K / atomic) accumulation target at this point of every replay."""
+        self.steps.append((None, (t,), "zero"))
+
+    def run(self):
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        if self.stats_used:
+            self.stats[:self.stats_used].zero_()
+        n = 0
+        for fn, args, name in self.steps:
+            if fn is None:
+                args[0].zero_()
+                continue
+            rc = fn(*args, s)
+            if rc:
+                _lib.check(rc, name)
+            n += 1
+        self.launches = n
+
+    def check_device_errors(self):
+        if int(self.err.item()) != 0:
+            raise RuntimeError("libdose_b200: an in-kernel mbarrier wait timed out (pipeline protocol error)")
+
+    def capture(self):
+        """Record run() into a CUDA graph (launch-bound replay); falls back to nothing — errors raise."""
+        st = torch.cuda.Stream(self.device)
+        st.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(st):
+            self.run()
+        torch.cuda.current_stream(self.device).wait_stream(st)
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.run()
+        self.graph = g
+
+    def replay(self):
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self.run()
+
+    # ------------------------------------------------------------------ weight packing
+    def pack_conv_tc(self, w, parts, mode):
+        """w [Co,Ci,k,k,k] fp32 -> fp16 [kd][chunk][kh][kw][2][Co][8] + per-chunk input block table.
+        mode p1: x_hi.W_hi;  p2: + x_lo.W_hi;  p3: + x_hi.W_lo  (operand splitting by K expansion)."""
+        w = w.detach().to(self.device, torch.float32)
+        Co, Ci, k = w.shape[0], w.shape[1], w.shape[2]
+        assert Co % 16 == 0, "tensor-core conv needs C_out % 16 == 0"
+        whi = w.half().float()
+        wlo = (w - whi).half().float()
+        terms = {"p1": [("hi", whi)], "p2": [("hi", whi), ("lo", whi)],
+                 "p3": [("hi", whi), ("lo", whi), ("hi", wlo)]}[mode]
+        mats, chunks = [], []
+        for which, wt in terms:
+            base = 0
+            for a in parts:
+                first = a.cb_off if which == "hi" else a.lo_off
+                assert first is not None, "operand split requested but the input has no lo part"
+                for j in range(ceil_div(a.C, 16)):
+                    c0 = base + 16 * j
+                    c1 = min(base + a.C, c0 + 16)
+                    m = torch.zeros((Co, 16, k, k, k), device=self.device)
+                    m[:, :c1 - c0] = wt[:, c0:c1]
+                    mats.append(m)
+                    chunks.append(first + 2 * j)
+                base += a.C
+            assert base == Ci, f"input parts carry {base} channels, weight expects {Ci}"
+        nch = len(mats)
+        W = torch.stack(mats, dim=1).view(Co, nch, 2, 8, k, k, k).permute(4, 1, 5, 6, 2, 0, 3).contiguous().half()
+        self.keep.append(W)
+        assert max(chunks) < 256
+        arr = (ctypes.c_uint8 * nch)(*chunks)
+        self.keep.append(arr)
+        return W, arr, nch
+
+    def affine(self, Co, bias=None, bn=None):
+        """epilogue y = acc*scale + shift from a conv bias and/or eval-mode BatchNorm3d (running stats)."""
+        scale = torch.ones(Co, device=self.device)
+        shift = torch.zeros(Co, device=self.device)
+        if bias is not None:
+            shift = bias.detach().to(self.device, torch.float32).clone()
+        if bn is not None:
+            g = bn.weight.detach().to(self.device, torch.float32)
+            b = bn.bias.detach().to(self.device, torch.float32)
+            rm = bn.running_mean.detach().to(self.device, torch.float32)
+            rv = bn.running_var.detach().to(self.device, torch.float32)
+            s = g / torch.sqrt(rv + bn.eps)
+            shift = (shift - rm) * s + b
+            scale = s
+        scale, shift = scale.contiguous(), shift.contiguous()
+        self.keep += [scale, shift]
+        return scale, shift
+
+    # ------------------------------------------------------------------ kernel emitters
+    def pack_input(self, x, out):
+        """x: static fp32 NCDHW input tensor [N,C,...] -> out Act (hi[/lo])."""
+        N, C = x.shape[0], x.shape[1]
+        self.add("dp_pack_ncdhw", x.data_ptr(), N, C, out.vox, out.hi_ptr, out.lo_ptr, out.cb_total, out.cb_off)
+
+    def unpack(self, a, dst):
+        self.add("dp_unpack_c8", a.hi_ptr, a.lo_ptr, a.cb_total, a.cb_off, a.N, a.C, a.vox, dst.data_ptr())
+
+    def conv_tc(self, parts, weight, k, dil, mode, scale, shift, relu, out_raw=None, out_act=None, stats=None):
+        a0 = parts[0]
+        D, H, W = a0.dims
+        Co = weight.shape[0]
+        wp, chunks, nch = self.pack_conv_tc(weight, parts, mode)
+        if out_raw is not None:
+            of32, ohi, olo, cbt, cbo = out_raw.t.data_ptr(), None, None, out_raw.cb_total, 0
+            st = out_raw.stats if stats is None else stats
+        else:
+            of32, ohi, olo, cbt, cbo = None, out_act.hi_ptr, out_act.lo_ptr, out_act.cb_total, out_act.cb_off
+            st = stats
+        self.add("dp_conv3d_tc", a0.buf.data_ptr(), a0.cb_total, chunks, nch, wp.data_ptr(), a0.N, D, H, W, Co, k, dil,
+                 scale.data_ptr(), shift.data_ptr(), int(relu), of32, ohi, olo, cbt, cbo,
+                 st.data_ptr() if st is not None else None, self.err.data_ptr(), 0)
+
+    def conv_direct(self, a, weight, k, stride, dil, scale, shift, relu, out_raw=None, out_act=None, stats=None):
+        """generic direct conv on one Act whose C is a multiple of 8 (stride-2 convs of net_A)."""
+        D, H, W = a.dims
+        Co, Ci = weight.shape[0], weight.shape[1]
+        cin = ceil_div(a.C, 8) * 8
+        w = torch.zeros((k * k * k, cin, Co), device=self.device)
+        w[:, :Ci] = weight.detach().to(self.device, torch.float32).permute(2, 3, 4, 1, 0).reshape(k * k * k, Ci, Co)
+        self.keep.append(w)
+        if out_raw is not None:
+            of32, ohi, olo, cbt, cbo, st = out_raw.t.data_ptr(), None, None, out_raw.cb_total, 0, out_raw.stats
+        else:
+            of32, ohi, olo, cbt, cbo, st = None, out_act.hi_ptr, out_act.lo_ptr, out_act.cb_total, out_act.cb_off, stats
+        self.add("dp_conv3d_direct", a.hi_ptr, a.lo_ptr, a.cb_total, a.cb_off, cin, a.N, D, H, W, k, stride, dil,
+                 w.data_ptr(), scale.data_ptr(), shift.data_ptr(), int(relu), Co, of32, ohi, olo, cbt, cbo,
+                 st.data_ptr() if st is not None else None)
+
+    def norm_act(self, src, out, stats=None, gamma=None, beta=None, act=None, res=None, res_stats=None,
+                 act_after_res=None, stats_out=None):
+        """out = act_after(act(IN(src)*gamma+beta) [+ IN?(res)]); src: Raw or Act; res: Act or Raw."""
+        if isinstance(src, Raw):
+            rf, rh, rl, icb, ioff, C = src.t.data_ptr(), None, None, src.cb_total, 0, src.C
+            N, vox = src.t.shape[0], src.t.shape[2] * src.t.shape[3] * src.t.shape[4]
+            if stats is None:
+                stats = src.stats
+        else:
+            rf, rh, rl, icb, ioff, C = None, src.hi_ptr, src.lo_ptr, src.cb_total, src.cb_off, src.C
+            N, vox = src.N, src.vox
+        eh = el = er = es = None
+        ecb = eoff = 0
+        if res is not None:
+            if isinstance(res, Raw):
+                er, ecb, eoff = res.t.data_ptr(), res.cb_total, 0
+                es = (res.stats if res_stats is None else res_stats).data_ptr()
+            else:
+                eh, el, ecb, eoff = res.hi_ptr, res.lo_ptr, res.cb_total, res.cb_off
+        oh = ol = None
+        ocb = ooff = 0
+        if out is not None:
+            oh, ol, ocb, ooff = out.hi_ptr, out.lo_ptr, out.cb_total, out.cb_off
+        self.add("dp_norm_act", rf, rh, rl, icb, ioff, stats.data_ptr() if stats is not None else None,
+                 gamma.data_ptr() if gamma is not None else None, beta.data_ptr() if beta is not None else None,
+                 ACT_ID[act], eh, el, er, es, ecb, eoff, ACT_ID[act_after_res], oh, ol, ocb, ooff,
+                 stats_out.data_ptr() if stats_out is not None else None, N, C, vox)
+
+    def pointwise(self, srcs, weight, bias, out_raw=None, out_act=None, out_planar=None, out_act_fn=None):
+        """1x1x1 conv over cat(srcs); srcs: list of (Act|Raw, stats|None, act|None)."""
+        hi, lo, raw, cbt, cbo, Cs, sts, acts = [], [], [], [], [], [], [], []
+        for t, st, act in srcs:
+            if isinstance(t, Raw):
+                hi.append(None); lo.append(None); raw.append(t.t.data_ptr()); cbt.append(t.cb_total); cbo.append(0)
+                N, vox = t.t.shape[0], t.t.shape[2] * t.t.shape[3] * t.t.shape[4]
+            else:
+                hi.append(t.hi_ptr); lo.append(t.lo_ptr); raw.append(None); cbt.append(t.cb_total); cbo.append(t.cb_off)
+                N, vox = t.N, t.vox
+            Cs.append(t.C)
+            sts.append(st.data_ptr() if st is not None else None)
+            acts.append(ACT_ID[act])
+        Co = weight.shape[0]
+        w = self.dev(weight.reshape(Co, -1))
+        assert w.shape[1] == sum(Cs), f"pointwise: weight expects {w.shape[1]} inputs, sources carry {sum(Cs)}"
+        b = self.dev(bias) if bias is not None else None
+        arrs = [_lib.ptr_array(hi), _lib.ptr_array(lo), _lib.ptr_array(raw), _lib.int_array(cbt), _lib.int_array(cbo),
+                _lib.int_array(Cs), _lib.ptr_array(sts), _lib.int_array(acts)]
+        self.keep.append(arrs)
+        of = oh = ol = op = st = None
+        ocb = ooff = 0
+        if out_raw is not None:
+            of, ocb, st = out_raw.t.data_ptr(), out_raw.cb_total, out_raw.stats.data_ptr()
+        if out_act is not None:
+            oh, ol, ocb, ooff = out_act.hi_ptr, out_act.lo_ptr, out_act.cb_total, out_act.cb_off
+        if out_planar is not None:
+            op = out_planar.data_ptr()
+        self.add("dp_pointwise_conv", len(srcs), *arrs, w.data_ptr(), b.data_ptr() if b is not None else None, Co, N,
+                 vox, of, oh, ol, ocb, ooff, op, st, ACT_ID[out_act_fn])
+
+    def deconv2x(self, src, weight, out):
+        """ConvTranspose3d k2 s2 (no bias): src Act or Tokens -> out Act (usually a slice of a concat buffer)."""
+        Ci, Co = weight.shape[0], weight.shape[1]
+        w = self.dev(weight.permute(2, 3, 4, 0, 1).reshape(8, Ci, Co))
+        if isinstance(src, Tokens):
+            B, T, C = src.t.shape
+            D, H, W = src.grid
+            assert C == Ci and C % 8 == 0
+            self.add("dp_deconv2x", src.t.data_ptr(), None, T * C, C, 8, Ci, Co, B, D, H, W, w.data_ptr(),
+                     out.hi_ptr, out.lo_ptr, out.cb_total, out.cb_off)
+        else:
+            D, H, W = src.dims
+            assert src.C == Ci and Ci % 8 == 0
+            vox = src.vox
+            base = src.buf.data_ptr() + src.cb_off * vox * 16
+            lo = None if src.lo_off is None else src.buf.data_ptr() + src.lo_off * vox * 16
+            self.add("dp_deconv2x", base, lo, src.cb_total * vox * 8, 8, vox * 8, Ci, Co, src.N, D, H, W, w.data_ptr(),
+                     out.hi_ptr, out.lo_ptr, out.cb_total, out.cb_off)
+
+    def upsample2x(self, src, out):
+        D, H, W = src.dims
+        self.add("dp_upsample2x", src.hi_ptr, src.lo_ptr, src.cb_total, src.cb_off, ceil_div(src.C, 8), src.N, D, H, W,
+                 out.hi_ptr, out.lo_ptr, out.cb_total, out.cb_off)
+
+    def gemm(self, A, B, M, N, K, *, batch=1, a_batch_rows=0, b_batch_rows=0, c_batch_stride=0, c_batch_period=0,
+             c_batch_stride2=0, ldc=None, split_k=1, bias=None, rowvec=None, row_period=0, resid=None, alpha=1.0,
+             act=None, out_f32=None, atomic=False, out_f16=None, qkv=None):
+        ldc = N if ldc is None else ldc
+        mode_qkv, heads, hd, T, q, k, vt, qs = 0, 0, 0, 0, None, None, None, 1.0
+        if qkv is not None:
+            mode_qkv = 1
+            heads, hd, T, q, k, vt, qs = qkv
+            q, k, vt = q.data_ptr(), k.data_ptr(), vt.data_ptr()
+        p = lambda t: t.data_ptr() if t is not None else None
+        self.add("dp_gemm_tc", p(A), p(B), M, N, K, batch, a_batch_rows, b_batch_rows, c_batch_stride, c_batch_period,
+                 c_batch_stride2, ldc, split_k, p(bias), p(rowvec), row_period, p(resid), float(alpha), ACT_ID[act],
+                 p(out_f32), int(atomic), p(out_f16), mode_qkv, heads, hd, T, q, k, vt, float(qs), self.err.data_ptr())
+
+    def layernorm(self, x, gamma, beta, rows, cols, out_f16=None, out_f32=None):
+        self.add("dp_layernorm", x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), rows, cols,
+                 out_f16.data_ptr() if out_f16 is not None else None, out_f32.data_ptr() if out_f32 is not None else None)
+
+    def softmax(self, s, rows, cols, p):
+        self.add("dp_softmax", s.data_ptr(), rows, cols, cols, p.data_ptr(), cols)
+
+    def patchify(self, a, ncb, out):
+        D, H, W = a.dims
+        self.add("dp_patchify", a.buf.data_ptr(), a.cb_total, a.cb_off, ncb, a.N, D, H, W, out.data_ptr())
+
+    def handoff(self, logits, ptv, ct, out, structures=None):
+        N, ncls, S = logits.shape[0], logits.shape[1], logits.shape[2]
+        self.add("dp_handoff", logits.data_ptr(), ncls, ptv.data_ptr(), ct.data_ptr(), N, S, out.hi_ptr, out.lo_ptr,
+                 out.cb_total, out.cb_off, structures.data_ptr() if structures is not None else None)

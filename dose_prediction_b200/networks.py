@@ -1,0 +1,762 @@
+"""Drop-in nn.Module mirrors of the reference networks, executed by hand-written sm_100a kernels.
+
+Same constructor signatures, forward signatures / return structure and state_dict layout (keys, shapes,
+order — SURVEY Appendix A, tests/golden/manifest_*.json) as
+
+  DosePrediction/Models/Networks/dose_pyfer.py : ViTEncoder :22, PyMSCDecoder :150, MainSubsetModel :245,
+                                                 Model :325, create_pretrained_unet :363
+  DosePrediction/Models/Networks/c3d.py        : SingleConv :11, UpConv :25, Encoder :41, Decoder :75, BaseUNet :118
+  OARSegmentation/Models/Networks/oar_transeg.py : Model :14
+  OARSegmentation/Models/Nets/base_blocks.py   : MultiUnetBasicBlock :12, ModifiedUnetrUpBlock :91, ModifiedUnetOutBlock :144
+  OARSegmentation/Models/Nets/blocks_MDUNet.py : conv_block_3 :64, conv_block_7 :98, conv_3_1 :132
+  monai==0.7.0 (un-vendored dependency)        : ViT, PatchEmbeddingBlock, TransformerBlock, SABlock, MLPBlock,
+                                                 UnetResBlock, UnetrBasicBlock, UnetrPrUpBlock, get_conv_layer
+
+The torch layers below are PARAMETER CONTAINERS only (they give the reference's state_dict and default
+initialisation); their own forward() is never called.  Each top-level forward() builds (once per input
+shape) an engine.Plan — a static schedule of C-ABI kernel launches — and replays it.  Inference
+(eval-mode BatchNorm) only; there is no CPU / eager fallback.
+"""
+from typing import Sequence, Tuple, Union
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .engine import Act, Plan, Raw, Tokens, blocks16, ceil_div
+
+
+def _tuple3(v):
+    if isinstance(v, (list, tuple)):
+        if len(v) != 3:
+            raise ValueError(f"Sequence must have length 3, got {len(v)}.")
+        return tuple(int(x) for x in v)
+    return (int(v),) * 3
+
+
+# =========================================================================== parameter containers
+class _Conv(nn.Sequential):
+    """monai Convolution(conv_only=True): Sequential with a single child named 'conv'."""
+
+    def __init__(self, conv, adn=False):
+        super().__init__()
+        self.add_module("conv", conv)
+        if adn:
+            self.add_module("adn", nn.Sequential())
+
+
+def _conv_layer(cin, cout, k, stride=1, bias=False, transposed=False, adn=False):
+    """monai dynunet_block.get_conv_layer for 3-D: padding (k-s+1)//2, output_padding 2p+s-k."""
+    pad = (k - stride + 1) // 2
+    if transposed:
+        return _Conv(nn.ConvTranspose3d(cin, cout, k, stride=stride, padding=pad, output_padding=2 * pad + stride - k,
+                                        bias=bias), adn)
+    return _Conv(nn.Conv3d(cin, cout, k, stride=stride, padding=pad, bias=bias), adn)
+
+
+class SingleConv(nn.Module):
+    def __init__(self, in_ch, out_ch, kernel_size, stride, padding):
+        super().__init__()
+        self.single_conv = nn.Sequential(
+            nn.Conv3d(in_ch, out_ch, kernel_size=kernel_size, padding=padding, stride=stride, bias=True),
+            nn.InstanceNorm3d(out_ch, affine=True), nn.ReLU(inplace=True))
+
+
+class UpConv(nn.Module):
+    def __init__(self, in_ch, out_ch):
+        super().__init__()
+        self.conv = nn.Sequential(nn.Conv3d(in_ch, out_ch, kernel_size=3, padding=1, stride=1, bias=True),
+                                  nn.InstanceNorm3d(out_ch, affine=True), nn.ReLU(inplace=True))
+
+
+class Encoder(nn.Module):
+    def __init__(self, in_ch, list_ch):
+        super().__init__()
+        chans = [in_ch] + list(list_ch[1:6])
+        for s in range(1, 6):
+            setattr(self, f"encoder_{s}", nn.Sequential(
+                SingleConv(chans[s - 1], chans[s], kernel_size=3, stride=1 if s == 1 else 2, padding=1),
+                SingleConv(chans[s], chans[s], kernel_size=3, stride=1, padding=1)))
+
+
+class Decoder(nn.Module):
+    def __init__(self, list_ch):
+        super().__init__()
+        for s in (4, 3, 2, 1):
+            setattr(self, f"upconv_{s}", UpConv(list_ch[s + 1], list_ch[s]))
+            convs = [SingleConv(2 * list_ch[s], list_ch[s], kernel_size=3, stride=1, padding=1)]
+            if s != 1:
+                convs.append(SingleConv(list_ch[s], list_ch[s], kernel_size=3, stride=1, padding=1))
+            setattr(self, f"decoder_conv_{s}", nn.Sequential(*convs))
+
+
+class BaseUNet(nn.Module):
+    """c3d.py:118 — the cascade's first stage (net_A)."""
+
+    def __init__(self, in_ch, list_ch):
+        super().__init__()
+        self.in_ch, self.list_ch = in_ch, list(list_ch)
+        self.encoder = Encoder(in_ch, list_ch)
+        self.decoder = Decoder(list_ch)
+        for m in self.modules():           # c3d.py:127-142
+            if isinstance(m, nn.Conv3d):
+                nn.init.kaiming_uniform_(m.weight, mode="fan_in", nonlinearity="relu")
+                if m.bias is not None:
+                    nn.init.constant_(m.bias, 0.0)
+            elif isinstance(m, nn.InstanceNorm3d):
+                nn.init.constant_(m.weight, 1.0)
+                nn.init.constant_(m.bias, 0.0)
+
+    def forward(self, x):
+        return _run_single(self, x, _plan_base_unet)
+
+
+class _MLP(nn.Module):
+    def __init__(self, hidden, mlp_dim, p):
+        super().__init__()
+        self.linear1, self.linear2 = nn.Linear(hidden, mlp_dim), nn.Linear(mlp_dim, hidden)
+        self.fn, self.drop1, self.drop2 = nn.GELU(), nn.Dropout(p), nn.Dropout(p)
+
+
+class _SA(nn.Module):
+    def __init__(self, hidden, heads, p):
+        super().__init__()
+        self.num_heads = heads
+        self.out_proj = nn.Linear(hidden, hidden)
+        self.qkv = nn.Linear(hidden, hidden * 3, bias=False)
+        self.drop_output, self.drop_weights = nn.Dropout(p), nn.Dropout(p)
+        self.head_dim = hidden // heads
+        self.scale = self.head_dim ** -0.5
+
+
+class _TransformerBlock(nn.Module):
+    def __init__(self, hidden, mlp_dim, heads, p):
+        super().__init__()
+        self.mlp = _MLP(hidden, mlp_dim, p)
+        self.norm1 = nn.LayerNorm(hidden)
+        self.attn = _SA(hidden, heads, p)
+        self.norm2 = nn.LayerNorm(hidden)
+
+
+class _PatchEmbedding(nn.Module):
+    def __init__(self, in_channels, img_size, patch_size, hidden, pos_embed, p):
+        super().__init__()
+        if pos_embed != "perceptron":
+            raise NotImplementedError("only pos_embed='perceptron' (what both reference nets use) is built; "
+                                      "'conv' is a SURVEY 8(f2) follow-up")
+        for m, q in zip(img_size, patch_size):
+            if m < q:
+                raise ValueError("patch_size should be smaller than img_size.")
+            if m % q != 0:
+                raise ValueError("patch_size should be divisible by img_size for perceptron.")
+        self.n_patches = int(np.prod([i // q for i, q in zip(img_size, patch_size)]))
+        self.patch_dim = int(in_channels * np.prod(patch_size))
+        self.patch_embeddings = nn.Sequential(nn.Identity(), nn.Linear(self.patch_dim, hidden))
+        self.position_embeddings = nn.Parameter(torch.zeros(1, self.n_patches, hidden))
+        self.cls_token = nn.Parameter(torch.zeros(1, 1, hidden))
+        self.dropout = nn.Dropout(p)
+        nn.init.trunc_normal_(self.position_embeddings, mean=0.0, std=0.02, a=-2.0, b=2.0)
+        lin = self.patch_embeddings[1]
+        nn.init.trunc_normal_(lin.weight, mean=0.0, std=0.02, a=-2.0, b=2.0)
+        nn.init.constant_(lin.bias, 0)
+
+
+class ViT(nn.Module):
+    def __init__(self, in_channels, img_size, patch_size, hidden_size=768, mlp_dim=3072, num_layers=12, num_heads=12,
+                 pos_embed="conv", classification=False, dropout_rate=0.0, spatial_dims=3):
+        super().__init__()
+        if not (0 <= dropout_rate <= 1):
+            raise ValueError("dropout_rate should be between 0 and 1.")
+        if hidden_size % num_heads != 0:
+            raise ValueError("hidden_size should be divisible by num_heads.")
+        if classification or spatial_dims != 3:
+            raise NotImplementedError("only the 3-D, non-classification ViT used by the reference nets is built")
+        self.hidden_size, self.mlp_dim, self.num_heads, self.num_layers = hidden_size, mlp_dim, num_heads, num_layers
+        self.patch_embedding = _PatchEmbedding(in_channels, img_size, patch_size, hidden_size, pos_embed, dropout_rate)
+        self.blocks = nn.ModuleList(
+            [_TransformerBlock(hidden_size, mlp_dim, num_heads, dropout_rate) for _ in range(num_layers)])
+        self.norm = nn.LayerNorm(hidden_size)
+
+
+class UnetResBlock(nn.Module):
+    def __init__(self, in_channels, out_channels, kernel_size=3, stride=1):
+        super().__init__()
+        self.conv1 = _conv_layer(in_channels, out_channels, kernel_size, stride)
+        self.conv2 = _conv_layer(out_channels, out_channels, kernel_size, 1)
+        self.conv3 = _conv_layer(in_channels, out_channels, 1, stride)      # always constructed in 0.7.0
+        self.lrelu = nn.LeakyReLU(inplace=True, negative_slope=0.01)
+        self.norm1, self.norm2, self.norm3 = (nn.InstanceNorm3d(out_channels) for _ in range(3))
+        self.downsample = in_channels != out_channels or stride != 1
+
+
+class UnetrBasicBlock(nn.Module):
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.layer = UnetResBlock(in_channels, out_channels)
+
+
+class UnetrPrUpBlock(nn.Module):
+    def __init__(self, in_channels, out_channels, num_layer):
+        super().__init__()
+        self.transp_conv_init = _conv_layer(in_channels, out_channels, 2, 2, transposed=True)
+        self.blocks = nn.ModuleList([
+            nn.Sequential(_conv_layer(out_channels, out_channels, 2, 2, transposed=True),
+                          UnetResBlock(out_channels, out_channels)) for _ in range(num_layer)])
+
+
+def _act_layer(act):
+    return nn.ReLU(inplace=True) if act == "relu" else nn.Mish(inplace=True)
+
+
+class conv_block_3(nn.Module):
+    def __init__(self, ch_in, ch_out, act="relu"):
+        super().__init__()
+        self.conv = nn.Sequential(
+            nn.Conv3d(ch_in, ch_out, kernel_size=3, stride=1, padding=1, bias=True), nn.InstanceNorm3d(ch_out), _act_layer(act),
+            nn.Conv3d(ch_out, ch_out, kernel_size=3, stride=1, padding=1, bias=True), nn.InstanceNorm3d(ch_out), _act_layer(act))
+
+
+class conv_block_7(nn.Module):
+    def __init__(self, ch_in, ch_out):
+        super().__init__()
+        self.conv = nn.Sequential(
+            nn.Conv3d(ch_in, ch_out, kernel_size=7, stride=1, padding=3, bias=True), nn.BatchNorm3d(ch_out), nn.ReLU(inplace=True),
+            nn.Conv3d(ch_out, ch_out, kernel_size=7, stride=1, padding=3, bias=True), nn.BatchNorm3d(ch_out), nn.ReLU(inplace=True))
+
+
+class conv_3_1(nn.Module):
+    def __init__(self, ch_in, ch_out, act):
+        super().__init__()
+        self.act = act
+        self.conv_3 = nn.Sequential(conv_block_3(ch_in, ch_out), nn.InstanceNorm3d(ch_out), _act_layer(act))
+        self.conv_7 = nn.Sequential(conv_block_7(ch_in, ch_out), nn.InstanceNorm3d(ch_out), _act_layer(act))
+        self.conv = nn.Sequential(nn.Conv3d(ch_out * 2, ch_out, kernel_size=1, stride=1, padding=0, bias=True),
+                                  nn.InstanceNorm3d(ch_out), _act_layer(act))
+
+
+class MultiUnetBasicBlock(nn.Module):
+    def __init__(self, in_channels, out_channels, multiS_conv=True, act="relu"):
+        super().__init__()
+        if not multiS_conv:
+            raise NotImplementedError("multiS_conv=False (DualDilatedBlock) is a SURVEY 8(f2) follow-up")
+        self.cov_ = conv_3_1(ch_in=in_channels, ch_out=out_channels, act=act)
+
+
+class ModifiedUnetrUpBlock(nn.Module):
+    def __init__(self, spatial_dims, in_channels, out_channels, upsample_kernel_size, act="relu", norm="instance",
+                 multiS_conv=True):
+        super().__init__()
+        if spatial_dims != 3 or upsample_kernel_size != 2:
+            raise NotImplementedError("only the 3-D, 2x up-sampling block used by the reference nets is built")
+        self.act = act
+        self.transp_conv = _conv_layer(in_channels, out_channels, 2, 2, transposed=True)
+        self.conv_block = MultiUnetBasicBlock(out_channels + out_channels, out_channels, act=act, multiS_conv=multiS_conv)
+
+
+class ModifiedUnetOutBlock(nn.Module):
+    def __init__(self, spatial_dims, in_channels, out_channels, dropout=None):
+        super().__init__()
+        self.conv = _conv_layer(in_channels, out_channels, 1, 1, bias=True, adn=True)
+
+
+# =========================================================================== plan builders (the forward)
+class Precision:
+    """Operand precision recipe (DESIGN.md 'precision'; frozen with oracle/precision_probe.py).
+    conv3: tensor-core mode of 3^3 convs; conv7: of 7^3 convs; lo: store activations as hi+lo pairs."""
+
+    def __init__(self, conv3, conv7, lo):
+        self.conv3, self.conv7, self.lo = conv3, conv7, lo
+
+
+PREC_NET_A = Precision("p3", "p3", True)      # net_A dominates the dose error: ~22-bit operands
+PREC_NET_B = Precision("p1", "p1", False)     # fp16 operands everywhere
+PREC_SEG = Precision("p3", "p1", True)        # seg: fp16 on 7^3 convs and the ViT, ~22-bit elsewhere
+
+
+def _in_conv_norm(P, parts, conv, norm, k, mode, out, act="relu", stride=1, N=None, dims=None):
+    """conv(+bias) -> InstanceNorm(affine?) -> act, for c3d SingleConv/UpConv."""
+    Co = conv.weight.shape[0]
+    scale, shift = P.affine(Co, bias=conv.bias)
+    odims = dims
+    raw = P.get_raw(N, Co, odims)
+    if stride == 1:
+        P.conv_tc(parts, conv.weight, k, 1, mode, scale, shift, False, out_raw=raw)
+    else:
+        assert len(parts) == 1
+        P.conv_direct(parts[0], conv.weight, k, stride, 1, scale, shift, False, out_raw=raw)
+    g = P.dev(norm.weight) if getattr(norm, "weight", None) is not None else None
+    b = P.dev(norm.bias) if getattr(norm, "bias", None) is not None else None
+    P.norm_act(raw, out, gamma=g, beta=b, act=act)
+    P.release(raw)
+
+
+def _emit_base_unet(P, net, x_act, out_act, prec=PREC_NET_A):
+    """c3d.py:144-149: Encoder (:65-72) then Decoder (:99-115); the final decoder tensor lands in out_act."""
+    N, dims0 = x_act.N, x_act.dims
+    ch = net.list_ch
+    lo = prec.lo
+    dims = [tuple(max(1, (d + (1 << s) - 1) >> s) for d in dims0) for s in range(5)]   # stage s+1 spatial dims
+    cat = {}
+    for s in (1, 2, 3, 4):
+        cat[s] = P.new_concat(N, [ch[s], ch[s]], dims[s - 1], lo=lo)       # [upconv_s output | encoder_s output]
+    h = x_act
+    for s in range(1, 6):
+        enc = getattr(net.encoder, f"encoder_{s}")
+        a = P.new_act(N, ch[s], dims[s - 1], lo=lo)
+        _in_conv_norm(P, [h], enc[0].single_conv[0], enc[0].single_conv[1], 3, prec.conv3, a,
+                      stride=1 if s == 1 else 2, N=N, dims=dims[s - 1])
+        dst = cat[s][1] if s <= 4 else P.new_act(N, ch[s], dims[s - 1], lo=lo)
+        _in_conv_norm(P, [a], enc[1].single_conv[0], enc[1].single_conv[1], 3, prec.conv3, dst, N=N, dims=dims[s - 1])
+        h = dst
+    for s in (4, 3, 2, 1):
+        up = P.new_act(N, ch[s + 1], dims[s - 1], lo=lo)
+        P.upsample2x(h, up)                                               # c3d.py:36
+        upc = getattr(net.decoder, f"upconv_{s}").conv
+        _in_conv_norm(P, [up], upc[0], upc[1], 3, prec.conv3, cat[s][0], N=N, dims=dims[s - 1])
+        dec = getattr(net.decoder, f"decoder_conv_{s}")
+        last = (s == 1)
+        d0 = out_act if last else P.new_act(N, ch[s], dims[s - 1], lo=lo)
+        _in_conv_norm(P, cat[s], dec[0].single_conv[0], dec[0].single_conv[1], 3, prec.conv3, d0, N=N, dims=dims[s - 1])
+        h = d0
+        if not last:
+            d1 = P.new_act(N, ch[s], dims[s - 1], lo=lo)
+            _in_conv_norm(P, [h], dec[1].single_conv[0], dec[1].single_conv[1], 3, prec.conv3, d1, N=N, dims=dims[s - 1])
+            h = d1
+    return out_act
+
+
+def _emit_vit(P, vit, parts, N, S, taps):
+    """monai ViT.forward (perceptron patch embedding) -> (LN(x_L) tokens, {layer index: hidden-state tokens})."""
+    hidden, heads, L = vit.hidden_size, vit.num_heads, vit.num_layers
+    hd = hidden // heads
+    grid = tuple(s // 16 for s in S)
+    T = grid[0] * grid[1] * grid[2]
+    M = N * T
+    first = parts[0]
+    ncb = sum(ceil_div(a.C, 8) if i == len(parts) - 1 else blocks16(a.C) for i, a in enumerate(parts))
+    # logical channel -> slot inside the contiguous block range starting at parts[0].cb_off
+    slots, base = [], 0
+    for a in parts:
+        assert a.cb_off == first.cb_off + base // 8 and a.buf is first.buf, "ViT input parts must be adjacent"
+        slots += [base + c for c in range(a.C)]
+        base += blocks16(a.C) * 8
+    K = ncb * 4096 * 8
+    lin = vit.patch_embedding.patch_embeddings[1]
+    Cin = len(slots)
+    w = lin.weight.detach().to(P.device, torch.float32).view(hidden, 16, 16, 16, Cin)
+    wfull = torch.zeros((hidden, 16, 16, 16, ncb * 8), device=P.device)
+    wfull[..., torch.tensor(slots, device=P.device)] = w
+    wpe = wfull.view(hidden, 16, 16, 16, ncb, 8).permute(0, 4, 1, 2, 3, 5).reshape(hidden, K).contiguous().half()
+    del w, wfull
+    P.keep.append(wpe)
+    A = P.zeros((M, K), torch.float16)
+    P.patchify(first, ncb, A)
+    x = P.zeros((M, hidden), torch.float32)
+    pos = P.dev(vit.patch_embedding.position_embeddings.reshape(T, hidden))
+    tiles = ceil_div(M, 128) * ceil_div(hidden, 128)
+    split_k = max(1, min(K // 64, (2 * 148) // tiles))
+    if split_k > 1:
+        P.add_zero(x)
+    P.gemm(A, wpe, M, hidden, K, split_k=split_k, bias=P.dev(lin.bias), rowvec=pos, row_period=T, out_f32=x,
+           atomic=split_k > 1)
+    ln = P.zeros((M, hidden), torch.float16)
+    q = P.zeros((N * heads, T, hd), torch.float16)
+    k = P.zeros((N * heads, T, hd), torch.float16)
+    vt = P.zeros((N * heads, hd, T), torch.float16)
+    scores = P.zeros((N * heads, T, T), torch.float32)
+    probs = P.zeros((N * heads, T, T), torch.float16)
+    o = P.zeros((M, hidden), torch.float16)
+    hmid = P.zeros((M, vit.mlp_dim), torch.float16)
+    hs = {}
+    for i, blk in enumerate(vit.blocks):
+        P.layernorm(x, P.dev(blk.norm1.weight), P.dev(blk.norm1.bias), M, hidden, out_f16=ln)
+        P.gemm(ln, P.dev(blk.attn.qkv.weight, torch.float16), M, 3 * hidden, hidden, qkv=(heads, hd, T, q, k, vt, hd ** -0.5))
+        P.gemm(q, k, T, T, hd, batch=N * heads, a_batch_rows=T, b_batch_rows=T, c_batch_stride=T * T, ldc=T, out_f32=scores)
+        P.softmax(scores, N * heads * T, T, probs)
+        P.gemm(probs, vt, T, hd, T, batch=N * heads, a_batch_rows=T, b_batch_rows=hd, c_batch_stride=T * hidden,
+               c_batch_period=heads, c_batch_stride2=hd, ldc=hidden, out_f16=o)
+        P.gemm(o, P.dev(blk.attn.out_proj.weight, torch.float16), M, hidden, hidden, bias=P.dev(blk.attn.out_proj.bias),
+               resid=x, out_f32=x)
+        P.layernorm(x, P.dev(blk.norm2.weight), P.dev(blk.norm2.bias), M, hidden, out_f16=ln)
+        P.gemm(ln, P.dev(blk.mlp.linear1.weight, torch.float16), M, vit.mlp_dim, hidden, bias=P.dev(blk.mlp.linear1.bias),
+               act="gelu", out_f16=hmid)
+        tap = None
+        if i in taps:
+            tap = P.zeros((N, T, hidden), torch.float16)
+            hs[i] = Tokens(tap, grid)
+        P.gemm(hmid, P.dev(blk.mlp.linear2.weight, torch.float16), M, hidden, vit.mlp_dim, bias=P.dev(blk.mlp.linear2.bias),
+               resid=x, out_f32=x, out_f16=tap)
+    z = P.zeros((N, T, hidden), torch.float16)
+    P.layernorm(x, P.dev(vit.norm.weight), P.dev(vit.norm.bias), M, hidden, out_f16=z)
+    return Tokens(z, grid), hs
+
+
+def _emit_res_block(P, blk, parts, out, prec):
+    """monai UnetResBlock.forward (k3 s1, InstanceNorm no affine, LeakyReLU 0.01)."""
+    N, dims = parts[0].N, parts[0].dims
+    Co = blk.conv1.conv.weight.shape[0]
+    one, zero = P.affine(Co)
+    raw1 = P.get_raw(N, Co, dims)
+    P.conv_tc(parts, blk.conv1.conv.weight, 3, 1, prec.conv3, one, zero, False, out_raw=raw1)
+    a1 = P.new_act(N, Co, dims, lo=prec.lo)
+    P.norm_act(raw1, a1, act="lrelu")
+    P.release(raw1)
+    raw2 = P.get_raw(N, Co, dims)
+    P.conv_tc([a1], blk.conv2.conv.weight, 3, 1, prec.conv3, one, zero, False, out_raw=raw2)
+    if blk.downsample:
+        raw3 = P.get_raw(N, Co, dims)
+        P.pointwise([(a, None, None) for a in parts], blk.conv3.conv.weight, None, out_raw=raw3)
+        P.norm_act(raw2, out, res=raw3, act_after_res="lrelu")
+        P.release(raw3)
+    else:
+        assert len(parts) == 1
+        P.norm_act(raw2, out, res=parts[0], act_after_res="lrelu")
+    P.release(raw2)
+
+
+def _emit_pr_up(P, blk, tokens, out, prec):
+    """monai UnetrPrUpBlock.forward: deconv, then num_layer x (deconv -> UnetResBlock)."""
+    N = tokens.t.shape[0]
+    Co = blk.transp_conv_init.conv.weight.shape[1]
+    dims = tuple(2 * g for g in tokens.grid)
+    n_layers = len(blk.blocks)
+    h = out if n_layers == 0 else P.new_act(N, Co, dims, lo=prec.lo)
+    P.deconv2x(tokens, blk.transp_conv_init.conv.weight, h)
+    for i, seq in enumerate(blk.blocks):
+        dims = tuple(2 * d for d in dims)
+        u = P.new_act(N, Co, dims, lo=prec.lo)
+        P.deconv2x(h, seq[0].conv.weight, u)
+        dst = out if i == n_layers - 1 else P.new_act(N, Co, dims, lo=prec.lo)
+        _emit_res_block(P, seq[1], [u], dst, prec)
+        h = dst
+    return out
+
+
+def _emit_conv_3_1(P, blk, parts, out, prec):
+    """blocks_MDUNet.py:150-157 with conv_block_3 (:64-78) and conv_block_7 (:98-112, eval BatchNorm folded)."""
+    N, dims = parts[0].N, parts[0].dims
+    act = blk.act
+    c3, c7 = blk.conv_3[0].conv, blk.conv_7[0].conv
+    C = c3[0].weight.shape[0]
+    # --- 3^3 branch: conv -> IN -> ReLU -> conv -> IN -> ReLU -> IN -> act
+    raw = P.get_raw(N, C, dims)
+    P.conv_tc(parts, c3[0].weight, 3, 1, prec.conv3, *P.affine(C, bias=c3[0].bias), False, out_raw=raw)
+    a = P.new_act(N, C, dims, lo=prec.lo)
+    P.norm_act(raw, a, act="relu")
+    P.release(raw)
+    raw = P.get_raw(N, C, dims)
+    P.conv_tc([a], c3[3].weight, 3, 1, prec.conv3, *P.affine(C, bias=c3[3].bias), False, out_raw=raw)
+    y3 = P.new_act(N, C, dims, lo=prec.lo)
+    st3 = P.new_stats(N, C)
+    P.norm_act(raw, y3, act="relu", stats_out=st3)
+    P.release(raw)
+    # --- 7^3 branch: conv -> BN -> ReLU -> conv -> BN -> ReLU -> IN -> act
+    a7 = P.new_act(N, C, dims, lo=(prec.conv7 != "p1"))
+    P.conv_tc(parts, c7[0].weight, 7, 1, prec.conv7, *P.affine(C, bias=c7[0].bias, bn=c7[1]), True, out_act=a7)
+    y7 = P.new_act(N, C, dims, lo=prec.lo)
+    st7 = P.new_stats(N, C)
+    P.conv_tc([a7], c7[3].weight, 7, 1, prec.conv7, *P.affine(C, bias=c7[3].bias, bn=c7[4]), True, out_act=y7, stats=st7)
+    # --- cat -> 1^3 conv -> IN -> act
+    raw = P.get_raw(N, C, dims)
+    P.pointwise([(y3, st3, act), (y7, st7, act)], blk.conv[0].weight, blk.conv[0].bias, out_raw=raw)
+    P.norm_act(raw, out, act=act)
+    P.release(raw)
+
+
+def _emit_up_block(P, blk, inp, skip_slot_pair, out, prec):
+    """base_blocks.py:136-141: deconv -> cat(out, skip) -> MultiUnetBasicBlock."""
+    P.deconv2x(inp, blk.transp_conv.conv.weight, skip_slot_pair[0])
+    _emit_conv_3_1(P, blk.conv_block.cov_, skip_slot_pair, out, prec)
+
+
+def _emit_unetr(P, vit, enc_blocks, dec_blocks, parts, taps, prec):
+    """Shared UNETR-shaped body of MainSubsetModel.forward (dose_pyfer.py:311-319) and oar_transeg Model.forward
+    (oar_transeg.py:171-185).  enc_blocks = (res-block, prup2, prup3, prup4); dec_blocks from coarse to fine."""
+    N, dims = parts[0].N, parts[0].dims
+    fs = enc_blocks[0].layer.conv1.conv.weight.shape[0]
+    lo = prec.lo
+    z, hs = _emit_vit(P, vit, parts, N, dims, taps)
+    sizes = [dims, tuple(d // 2 for d in dims), tuple(d // 4 for d in dims), tuple(d // 8 for d in dims)]
+    cats = [P.new_concat(N, [fs << i, fs << i], sizes[i], lo=lo) for i in range(4)]     # [deconv out | skip]
+    _emit_res_block(P, enc_blocks[0].layer, parts, cats[0][1], prec)
+    _emit_pr_up(P, enc_blocks[1], hs[taps[0]], cats[1][1], prec)
+    _emit_pr_up(P, enc_blocks[2], hs[taps[1]], cats[2][1], prec)
+    _emit_pr_up(P, enc_blocks[3], hs[taps[2]], cats[3][1], prec)
+    decs = []
+    inp = z
+    for lvl, blk in zip((3, 2, 1, 0), dec_blocks):
+        out = P.new_act(N, fs << lvl, sizes[lvl], lo=lo)
+        _emit_up_block(P, blk, inp, cats[lvl], out, prec)
+        decs.append(out)
+        inp = out
+    return decs[::-1]          # [dec1 (full res), dec2, dec3, dec4]
+
+
+class _PlanCache:
+    """per-module cache of engine.Plan objects keyed by input shape; rebuilt when parameters change."""
+
+    def __init__(self):
+        self.plans = {}
+        self.version = None
+
+    def get(self, module, key, builder):
+        ver = tuple(t._version for t in list(module.parameters()) + list(module.buffers()))
+        ptrs = tuple(t.data_ptr() for t in module.parameters())
+        if self.version != (ver, ptrs):
+            self.plans.clear()
+            self.version = (ver, ptrs)
+        if key not in self.plans:
+            self.plans[key] = builder()
+        return self.plans[key]
+
+
+def _check_input(module, x, channels):
+    if module.training:
+        raise RuntimeError("dose_prediction_b200: training-mode forward (batch-statistics BatchNorm + backward) is "
+                           "not built yet (SURVEY 8 row a8); call .eval() for the inference path")
+    if not (x.is_cuda and x.dim() == 5):
+        raise RuntimeError("expected a CUDA tensor [B,C,D,H,W]; dose_prediction_b200 has no CPU fallback")
+    if x.shape[1] != channels:
+        raise ValueError(f"expected {channels} input channels, got {x.shape[1]}")
+    return x.detach().to(torch.float32).contiguous()
+
+
+def _run_single(module, x, plan_fn):
+    x = _check_input(module, x, module.in_ch)
+    if not hasattr(module, "_cache"):
+        object.__setattr__(module, "_cache", _PlanCache())
+    plan = module._cache.get(module, (tuple(x.shape), x.device.index), lambda: plan_fn(module, x.shape, x.device))
+    plan.x_in.copy_(x)
+    plan.replay()
+    return plan.result()
+
+
+def _plan_base_unet(net, shape, device):
+    P = Plan(device)
+    N, dims = shape[0], tuple(shape[2:])
+    P.x_in = P.zeros(tuple(shape), torch.float32)
+    x_act = P.new_act(N, net.in_ch, dims, lo=True)
+    P.pack_input(P.x_in, x_act)
+    out = P.new_act(N, net.list_ch[1], dims, lo=True)
+    _emit_base_unet(P, net, x_act, out)
+    y = P.zeros((N, net.list_ch[1]) + dims, torch.float32)
+    P.unpack(out, y)
+    P.result = lambda: y.clone()
+    return P
+
+
+# =========================================================================== DOSE-PYFER
+class ViTEncoder(nn.Module):
+    def __init__(self, in_channels: int, img_size: Union[Sequence[int], int], feature_size: int = 16,
+                 hidden_size: int = 768, mlp_dim: int = 3072, num_heads: int = 12, num_layers: int = 12,
+                 pos_embed: str = "conv", norm_name: Union[Tuple, str] = "instance", conv_block: bool = True,
+                 res_block: bool = True, dropout_rate: float = 0.0, spatial_dims: int = 3) -> None:
+        super().__init__()
+        if not (0 <= dropout_rate <= 1):
+            raise ValueError("dropout_rate should be between 0 and 1.")
+        if hidden_size % num_heads != 0:
+            raise ValueError("hidden_size should be divisible by num_heads.")
+        if not (conv_block and res_block and norm_name == "instance" and spatial_dims == 3):
+            raise NotImplementedError("only conv_block=res_block=True, instance norm, 3-D (the reference config) is built")
+        self.num_layers = num_layers
+        img_size = _tuple3(img_size)
+        self.patch_size = (16, 16, 16)
+        self.feat_size = tuple(i // p for i, p in zip(img_size, self.patch_size))
+        self.hidden_size = hidden_size
+        self.classification = False
+        self.vit = ViT(in_channels=in_channels, img_size=img_size, patch_size=self.patch_size, hidden_size=hidden_size,
+                       mlp_dim=mlp_dim, num_layers=num_layers, num_heads=num_heads, pos_embed=pos_embed,
+                       classification=False, dropout_rate=dropout_rate, spatial_dims=spatial_dims)
+        self.skip1 = UnetrBasicBlock(in_channels, feature_size)
+        self.skip2 = UnetrPrUpBlock(hidden_size, feature_size * 2, num_layer=2)
+        self.skip3 = UnetrPrUpBlock(hidden_size, feature_size * 4, num_layer=1)
+        self.skip4 = UnetrPrUpBlock(hidden_size, feature_size * 8, num_layer=0)
+        self.proj_axes = (0, spatial_dims + 1) + tuple(d + 1 for d in range(spatial_dims))
+        self.proj_view_shape = list(self.feat_size) + [self.hidden_size]
+
+
+class PyMSCDecoder(nn.Module):
+    def __init__(self, feature_size: int = 16, hidden_size: int = 768, norm_name: Union[Tuple, str] = "instance",
+                 spatial_dims: int = 3, mode_multi: bool = False, act="relu", multiS_conv=True) -> None:
+        super().__init__()
+        if not mode_multi:
+            raise NotImplementedError("mode_multi_dec=False (monai UnetrUpBlock decoders) is a SURVEY 8(f2) follow-up")
+        chans = [hidden_size, feature_size * 8, feature_size * 4, feature_size * 2, feature_size]
+        for i, name in enumerate(("decoder4", "decoder3", "decoder2", "decoder1")):
+            setattr(self, name, ModifiedUnetrUpBlock(spatial_dims=spatial_dims, in_channels=chans[i], out_channels=chans[i + 1],
+                                                     upsample_kernel_size=2, act=act, multiS_conv=multiS_conv))
+
+
+class MainSubsetModel(nn.Module):
+    def __init__(self, in_ch, out_ch, img_size, feature_size: int = 16, hidden_size: int = 768, mlp_dim: int = 3072,
+                 num_heads: int = 12, num_layers: int = 12, conv_block: bool = True, res_block: bool = True,
+                 dropout_rate: float = 0.0, mode_multi_dec=False, act="relu", multiS_conv=True):
+        super().__init__()
+        self.in_ch, self.out_ch = in_ch, out_ch
+        self.encoder = ViTEncoder(in_channels=in_ch, img_size=img_size, feature_size=feature_size, hidden_size=hidden_size,
+                                  mlp_dim=mlp_dim, num_heads=num_heads, num_layers=num_layers, pos_embed="perceptron",
+                                  norm_name="instance", res_block=res_block, conv_block=conv_block, dropout_rate=dropout_rate)
+        self.decoder = PyMSCDecoder(feature_size=feature_size, hidden_size=hidden_size, mode_multi=mode_multi_dec, act=act,
+                                    multiS_conv=multiS_conv)
+
+        def to_out(in_feature):
+            return nn.Sequential(nn.Conv3d(in_feature, out_ch, kernel_size=1, padding=0, bias=True))
+
+        self.dose_convertors = nn.ModuleList([to_out(feature_size)])
+        for i in range(1, 4):
+            self.dose_convertors.append(to_out(int(feature_size * np.power(2, i))))
+        self.out = nn.Sequential(nn.Conv3d(feature_size, out_ch, kernel_size=1, padding=0, bias=True))
+
+    def update_config(self, config_hparam):
+        self.encoder.hidden_size = config_hparam["hidden_size"]
+        self.encoder.num_layers = config_hparam["hidden_size"]
+
+    def forward(self, x):
+        return _run_single(self, x, _plan_main_subset)
+
+
+def _emit_main_subset(P, net, parts):
+    enc, dec = net.encoder, net.decoder
+    i = enc.num_layers // 4
+    decs = _emit_unetr(P, enc.vit, (enc.skip1, enc.skip2, enc.skip3, enc.skip4),
+                       (dec.decoder4, dec.decoder3, dec.decoder2, dec.decoder1), parts, (i, 2 * i, 3 * i), PREC_NET_B)
+    outs = []
+    for d, conv in zip(decs, net.dose_convertors):
+        y = P.zeros((d.N, net.out_ch) + d.dims, torch.float32)
+        P.pointwise([(d, None, None)], conv[0].weight, conv[0].bias, out_planar=y)
+        outs.append(y)
+    return outs
+
+
+def _plan_main_subset(net, shape, device):
+    P = Plan(device)
+    N, dims = shape[0], tuple(shape[2:])
+    P.x_in = P.zeros(tuple(shape), torch.float32)
+    x_act = P.new_act(N, net.in_ch, dims, lo=False)
+    P.pack_input(P.x_in, x_act)
+    outs = _emit_main_subset(P, net, [x_act])
+    P.result = lambda: [o.clone() for o in outs]
+    return P
+
+
+class Model(nn.Module):
+    """DOSE-PYFER cascade: C3D net_A -> cat -> ViT/multi-scale-conv net_B (dose_pyfer.py:325-360)."""
+
+    def __init__(self, in_ch, out_ch, list_ch_A, feature_size=16, img_size=(128, 128, 128), num_layers=8, num_heads=6,
+                 act="mish", mode_multi_dec=True, multiS_conv=True):
+        super().__init__()
+        self.in_ch, self.out_ch = in_ch, out_ch
+        self.net_A = BaseUNet(in_ch, list_ch_A)
+        self.net_B = MainSubsetModel(in_ch=in_ch + list_ch_A[1], out_ch=out_ch, feature_size=feature_size,
+                                     img_size=img_size, num_layers=num_layers, num_heads=num_heads, act=act,
+                                     mode_multi_dec=mode_multi_dec, multiS_conv=multiS_conv)
+        self.conv_out_A = nn.Conv3d(list_ch_A[1], out_ch, kernel_size=1, padding=0, bias=True)
+
+    def forward(self, x):
+        """x [B,9,S,S,S] fp32 CUDA -> [output_A [B,1,S^3], [dose_S, dose_S/2, dose_S/4, dose_S/8]]."""
+        return _run_single(self, x, lambda m, shape, dev: plan_dose_pyfer(m, shape, dev))
+
+
+def emit_dose_pyfer(P, model, x_act, a_out):
+    """dose_pyfer.py:355-360 on an already-packed input; (a_out | x_act) share one concat buffer."""
+    _emit_base_unet(P, model.net_A, x_act, a_out)
+    N, dims = x_act.N, x_act.dims
+    out_A = P.zeros((N, model.out_ch) + dims, torch.float32)
+    P.pointwise([(a_out, None, None)], model.conv_out_A.weight, model.conv_out_A.bias, out_planar=out_A)
+    outs = _emit_main_subset(P, model.net_B, [a_out, x_act])
+    return out_A, outs
+
+
+def plan_dose_pyfer(model, shape, device, external_input=False):
+    P = Plan(device)
+    N, dims = shape[0], tuple(shape[2:])
+    a_out, x_act = P.new_concat(N, [model.net_A.list_ch[1], model.in_ch], dims, lo=True)
+    P.x_act = x_act
+    if not external_input:
+        P.x_in = P.zeros(tuple(shape), torch.float32)
+        P.pack_input(P.x_in, x_act)
+    out_A, outs = emit_dose_pyfer(P, model, x_act, a_out)
+    P.outputs = (out_A, outs)
+    P.result = lambda: [out_A.clone(), [o.clone() for o in outs]]
+    return P
+
+
+def create_pretrained_unet(ckpt_file, in_ch, out_ch, list_ch_A, feature_size, img_size, num_layers=8, num_heads=6,
+                           act="mish", mode_multi_dec=True, multiS_conv=True):
+    """dose_pyfer.py:363-407: load the C3D checkpoint's matching keys (net_A.*, conv_out_A.*), strict=False."""
+    pretrain = torch.load(ckpt_file, map_location="cpu")
+    net = Model(in_ch, out_ch, list_ch_A, feature_size=feature_size, img_size=img_size, num_layers=num_layers,
+                num_heads=num_heads, act=act, mode_multi_dec=mode_multi_dec, multiS_conv=multiS_conv)
+    net_dict = net.state_dict()
+    sd = pretrain["network_state_dict"]
+    missing = tuple({k for k in net_dict.keys() if k not in sd})
+    print(f"missing in pretrained: {len(missing)}")
+    inside = tuple({k for k in sd if k in net_dict.keys()})
+    print(f"inside pretrained: {len(inside)}")
+    unused = tuple({k for k in sd if k not in net_dict.keys()})
+    print(f"unused pretrained: {len(unused)}")
+    net.load_state_dict({k: v for k, v in sd.items() if k in net_dict.keys()}, strict=False)
+    return net, inside
+
+
+# =========================================================================== OAR-TRANSEG
+class OARTranseg(nn.Module):
+    """OARSegmentation/Models/Networks/oar_transeg.py:14 `Model` (exported as oar_transeg.Model)."""
+
+    def __init__(self, in_channels: int, out_channels: int, img_size: Union[Sequence[int], int], feature_size: int = 16,
+                 hidden_size: int = 768, mlp_dim: int = 3072, num_heads: int = 12, pos_embed: str = "conv",
+                 norm_name: Union[Tuple, str] = "instance", conv_block: bool = True, res_block: bool = True,
+                 dropout_rate: float = 0.0, spatial_dims: int = 3) -> None:
+        super().__init__()
+        if not (0 <= dropout_rate <= 1):
+            raise ValueError("dropout_rate should be between 0 and 1.")
+        if hidden_size % num_heads != 0:
+            raise ValueError("hidden_size should be divisible by num_heads.")
+        if not (conv_block and res_block and norm_name == "instance" and spatial_dims == 3):
+            raise NotImplementedError("only conv_block=res_block=True, instance norm, 3-D (the reference config) is built")
+        self.in_ch, self.out_channels = in_channels, out_channels
+        self.num_layers = 12
+        img_size = _tuple3(img_size)
+        self.patch_size = (16, 16, 16)
+        self.feat_size = tuple(i // p for i, p in zip(img_size, self.patch_size))
+        self.hidden_size = hidden_size
+        self.classification = False
+        self.vit = ViT(in_channels=in_channels, img_size=img_size, patch_size=self.patch_size, hidden_size=hidden_size,
+                       mlp_dim=mlp_dim, num_layers=self.num_layers, num_heads=num_heads, pos_embed=pos_embed,
+                       classification=False, dropout_rate=dropout_rate, spatial_dims=spatial_dims)
+        self.encoder1 = UnetrBasicBlock(in_channels, feature_size)
+        self.encoder2 = UnetrPrUpBlock(hidden_size, feature_size * 2, num_layer=2)
+        self.encoder3 = UnetrPrUpBlock(hidden_size, feature_size * 4, num_layer=1)
+        self.encoder4 = UnetrPrUpBlock(hidden_size, feature_size * 8, num_layer=0)
+        self.decoder5 = ModifiedUnetrUpBlock(spatial_dims, hidden_size, feature_size * 8, 2)
+        self.decoder4 = ModifiedUnetrUpBlock(spatial_dims, feature_size * 8, feature_size * 4, 2)
+        self.decoder3 = ModifiedUnetrUpBlock(spatial_dims, feature_size * 4, feature_size * 2, 2)
+        self.decoder2 = ModifiedUnetrUpBlock(spatial_dims, feature_size * 2, feature_size, 2)
+        self.out = ModifiedUnetOutBlock(spatial_dims=spatial_dims, in_channels=feature_size, out_channels=out_channels)
+        self.proj_axes = (0, spatial_dims + 1) + tuple(d + 1 for d in range(spatial_dims))
+        self.proj_view_shape = list(self.feat_size) + [self.hidden_size]
+
+    def forward(self, x_in):
+        """x_in [B,in_channels,S,S,S] fp32 CUDA -> logits [B,out_channels,S,S,S] fp32."""
+        return _run_single(self, x_in, lambda m, shape, dev: plan_oar_transeg(m, shape, dev))
+
+
+def emit_oar_transeg(P, model, x_act):
+    decs = _emit_unetr(P, model.vit, (model.encoder1, model.encoder2, model.encoder3, model.encoder4),
+                       (model.decoder5, model.decoder4, model.decoder3, model.decoder2), [x_act], (3, 6, 9), PREC_SEG)
+    d = decs[0]
+    logits = P.zeros((d.N, model.out_channels) + d.dims, torch.float32)
+    P.pointwise([(d, None, None)], model.out.conv.conv.weight, model.out.conv.conv.bias, out_planar=logits)
+    return logits
+
+
+def plan_oar_transeg(model, shape, device):
+    P = Plan(device)
+    N, dims = shape[0], tuple(shape[2:])
+    P.x_in = P.zeros(tuple(shape), torch.float32)
+    x_act = P.new_act(N, model.in_ch, dims, lo=True)
+    P.pack_input(P.x_in, x_act)
+    logits = emit_oar_transeg(P, model, x_act)
+    P.outputs = logits
+    P.result = lambda: logits.clone()
+    return P

@@ -1,0 +1,132 @@
+/* dose_b200.h — C ABI of libdose_b200.so: the sm_100a kernels behind the OAR-TRANSEG -> DOSE-PYFER
+ * hot path of GhTara/Dose_Prediction.
+ *
+ * The reference has no FFI / operator API of its own: every device op on the path is an ATen call made
+ * from nn.Module.forward.  Each entry point below therefore names the ATen call
+ * site(s) it replaces (paths relative to the reference root; "monai:" = monai==0.7.0).
+ *
+ * Conventions
+ *   - plain C types only: device pointers as void* / float* / double*, sizes as int / long long,
+ *     cudaStream_t for ordering.  No torch types.
+ *   - every function returns 0 on success, non-zero on failure; dp_last_error() gives the message.
+ *   - asynchronous on the given stream, never synchronises, never allocates device memory.
+ *   - activation tensors use the "c8" layout [N][C/8][D][H][W][8] (fp16, optionally as a hi/lo pair of
+ *     tensors whose sum carries ~22 mantissa bits; fp32 for pre-normalisation "raw" tensors);
+ *     (cb_total, cb_off) address a channel-block slice of a larger buffer, which is how torch.cat
+ *     (base_blocks.py:139, blocks_MDUNet.py:154, c3d.py:103-112, dose_pyfer.py:357) disappears.
+ *   - per-(n,c) InstanceNorm statistics are double[N][C][2] = {sum, sum of squares}, accumulated by the
+ *     producing kernel and finalised (biased variance, eps 1e-5) by the consumer.
+ *   - err_flag: optional device int set to 1 if an in-kernel mbarrier wait times out (protocol bug).
+ */
+#ifndef DOSE_B200_H_
+#define DOSE_B200_H_
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* activation ids used by the *_act arguments */
+#define DP_ACT_NONE 0
+#define DP_ACT_RELU 1
+#define DP_ACT_LRELU 2 /* LeakyReLU(0.01): monai UnetResBlock.lrelu */
+#define DP_ACT_MISH 3  /* blocks_MDUNet.py:139,143,148 (act='mish') */
+#define DP_ACT_GELU 4  /* erf GELU: monai MLPBlock.fn */
+
+const char* dp_last_error(void);
+int dp_abi_version(void);
+int dp_device_sm_count(void);
+
+/* nn.Conv3d stride 1, odd k<=7, dilation dil, "same" padding, on tcgen05 tensor cores.
+ * Replaces: blocks_MDUNet.py:68,71 (3^3), :102,105 (7^3), :166-187 (dilated), c3d.py:16,30 (stride-1
+ * SingleConv/UpConv convs), monai UnetResBlock.conv1/conv2.  Fused epilogue: y = acc*scale[c]+shift[c]
+ * (conv bias and/or eval-mode BatchNorm3d fold, blocks_MDUNet.py:103,106), optional ReLU, statistics.
+ *   in_c8      input c8 fp16 buffer (cb_total_in channel blocks per image)
+ *   chunk_cb   host array [n_chunks]: first channel block of every 16-channel K chunk (hi/lo operand
+ *              splitting = listing hi blocks, lo blocks, hi blocks again against [Whi;Whi;Wlo])
+ *   wpack      fp16 [k(kd)][n_chunks][k(kh)][k(kw)][2][cout][8]
+ *   out_f32    c8 fp32 output or NULL;  out_hi/out_lo  c8 fp16 output (lo optional) or NULL           */
+int dp_conv3d_tc(const void* in_c8, int cb_total_in, const uint8_t* chunk_cb, int n_chunks, const void* wpack,
+                 int N, int D, int H, int W, int cout, int k, int dil, const float* scale, const float* shift,
+                 int relu, float* out_f32, void* out_hi, void* out_lo, int cb_total_out, int cb_out_off,
+                 double* stats, int* err_flag, int max_ctas, cudaStream_t stream);
+
+/* Generic direct convolution (any stride): c3d.py:49,53,57,61 (stride-2 SingleConv convs).
+ *   w_packed   fp32 [k^3 taps][cin][cout]                                                              */
+int dp_conv3d_direct(const void* in_hi, const void* in_lo, int in_cb_total, int in_cb_off, int cin, int N, int D,
+                     int H, int W, int k, int stride, int dil, const float* w_packed, const float* scale,
+                     const float* shift, int relu, int cout, float* out_raw, void* out_hi, void* out_lo,
+                     int out_cb_total, int out_cb_off, double* stats_out, cudaStream_t stream);
+
+/* nn.Linear / attention contractions: C[M,N] = alpha * A[M,K] . B[N,K]^T (+bias, +rowvec, act, +resid).
+ * Replaces: monai PatchEmbeddingBlock Linear (+position_embeddings), SABlock.qkv / out_proj and both
+ * einsums, MLPBlock.linear1 (+GELU) / linear2 (+residual).  mode_qkv scatters the [M, 3*heads*hd] result
+ * into q [B,heads,T,hd] (scaled by q_scale), k [B,heads,T,hd], v^T [B,heads,hd,T]
+ * (einops "b h (qkv l d) -> qkv b l h d").  Batched: A/B rows advance by a/b_batch_rows per batch entry z,
+ * outputs by z*c_batch_stride, or (z/period)*c_batch_stride + (z%period)*c_batch_stride2 if period>0. */
+int dp_gemm_tc(const void* A, const void* B, int M, int N, int K, int batch, int a_batch_rows, int b_batch_rows,
+               long long c_batch_stride, int c_batch_period, long long c_batch_stride2, int ldc, int split_k, const float* bias, const float* rowvec,
+               int row_period, const float* resid, float alpha, int act, float* out_f32, int atomic,
+               void* out_f16, int mode_qkv, int heads, int hd, int T, void* q, void* k, void* vt, float q_scale,
+               int* err_flag, cudaStream_t stream);
+
+/* NCDHW fp32 <-> c8 fp16 (module-boundary conversion; batch['Input'].float(), train_light_pyfer.py:124) */
+int dp_pack_ncdhw(const float* src, int N, int C, long long vox, void* hi, void* lo, int cb_total, int cb_off,
+                  cudaStream_t stream);
+int dp_unpack_c8(const void* hi, const void* lo, int cb_total, int cb_off, int N, int C, long long vox, float* dst,
+                 cudaStream_t stream);
+
+/* nn.InstanceNorm3d (+affine: c3d.py:17,31) -> activation -> optional residual add (+activation), with
+ * optional statistics of the result for a chained InstanceNorm (blocks_MDUNet.py:136-139).
+ * Residual = c8 fp16 tensor, or raw fp32 tensor normalised with res_stats (monai UnetResBlock.norm3).  */
+int dp_norm_act(const float* raw_f32, const void* raw_hi, const void* raw_lo, int in_cb_total, int in_cb_off,
+                const double* stats, const float* gamma, const float* beta, int act, const void* res_hi,
+                const void* res_lo, const float* res_raw, const double* res_stats, int res_cb_total, int res_cb_off,
+                int act_after_res, void* out_hi, void* out_lo, int out_cb_total, int out_cb_off, double* stats_out,
+                int N, int C, long long vox, cudaStream_t stream);
+
+/* nn.Conv3d k=1 over the channel-concatenation of up to three sources, each normalised/activated on
+ * load: blocks_MDUNet.py:145-157 (cat(x3,x7) -> 1^3), monai UnetResBlock.conv3, heads dose_pyfer.py:290-300,353,
+ * base_blocks.py:151 (seg logits).  Output: raw c8 fp32 (+stats), c8 fp16, or NCDHW fp32 (out_planar).
+ *   w          fp32 [cout][sum of source C]                                                            */
+int dp_pointwise_conv(int nsrc, const void* const* src_hi, const void* const* src_lo, const float* const* src_raw,
+                      const int* src_cb_total, const int* src_cb_off, const int* src_C,
+                      const double* const* src_stats, const int* src_act, const float* w, const float* bias, int cout,
+                      int N, long long vox, float* out_raw, void* out_hi, void* out_lo, int out_cb_total,
+                      int out_cb_off, float* out_planar, double* stats_out, int out_act, cudaStream_t stream);
+
+/* nn.ConvTranspose3d k=2 s=2 no bias (monai get_conv_layer(is_transposed=True): base_blocks.py:118-127,
+ * UnetrPrUpBlock).  Input addressed by element strides so ViT tokens [B,T,C] are read in place
+ * (proj_feat, dose_pyfer.py:118-122, becomes a no-op).  w_packed fp32 [8 parity][cin][cout].          */
+int dp_deconv2x(const void* in_hi, const void* in_lo, long long in_nstride, long long in_vstride,
+                long long in_cbstride, int cin, int cout, int N, int D, int H, int W, const float* w_packed,
+                void* out_hi, void* out_lo, int out_cb_total, int out_cb_off, cudaStream_t stream);
+
+/* F.interpolate(scale_factor=2, mode='trilinear', align_corners=True): c3d.py:36 */
+int dp_upsample2x(const void* in_hi, const void* in_lo, int in_cb_total, int in_cb_off, int ncb, int N, int D, int H,
+                  int W, void* out_hi, void* out_lo, int out_cb_total, int out_cb_off, cudaStream_t stream);
+
+/* nn.LayerNorm(hidden), eps 1e-5 (monai TransformerBlock.norm1/norm2, ViT.norm) */
+int dp_layernorm(const float* x, const float* gamma, const float* beta, int rows, int cols, void* out_f16,
+                 float* out_f32, cudaStream_t stream);
+
+/* softmax(dim=-1) of attention scores (monai SABlock.forward) */
+int dp_softmax(const float* s, int rows, int cols, int ld_in, void* p, int ld_out, cudaStream_t stream);
+
+/* einops Rearrange "b c (h p1)(w p2)(d p3) -> b (h w d)(p1 p2 p3 c)", p=16 (monai PatchEmbeddingBlock),
+ * restated for c8 input: K order (c/8, p1, p2, p3, c%8)                                                */
+int dp_patchify(const void* in_c8, int cb_total, int cb_off, int ncb, int N, int S0, int S1, int S2, void* out,
+                cudaStream_t stream);
+
+/* Cascade hand-off: argmax(8) -> one-hot -> drop background -> permute(0,3,2,1) -> cat(ptv, oars, ct^T)
+ * (train_light_linked_model.py:156-167, OARSegmentation/config.py:70).  Writes the dose net's c8 input
+ * (2 channel blocks: [PTV,7 OARs] [CT,0...]) and optionally NCDHW fp32 structures [N,9,S,S,S].        */
+int dp_handoff(const float* logits, int ncls, const float* ptv, const float* ct, int N, int S, void* out_hi,
+               void* out_lo, int out_cb_total, int out_cb_off, float* structures, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DOSE_B200_H_ */

@@ -17,6 +17,32 @@ import torch.nn.functional as F
 SD = Dict[str, torch.Tensor]
 EPS = 1e-5
 
+# --------------------------------------------------------------------------- operand-precision emulation
+# EMU = None reproduces the reference in exact fp32.  Setting EMU to a callable
+#   EMU(tag: str, kind: str) -> (act_mode, weight_mode),  modes in {"f32", "f16", "hilo"}
+# rounds the operands of every contraction the way the CUDA path stores/feeds them (fp16, or an
+# fp16 hi+lo pair ~ 22 bits) while keeping fp32 accumulation; used by oracle/precision_probe.py to
+# freeze the per-layer precision recipe on CPU before any GPU time is spent.
+EMU = None
+
+
+def _round(x, mode):
+    if mode == "f32":
+        return x
+    hi = x.half().float()
+    if mode == "f16":
+        return hi
+    if mode == "hilo":
+        return hi + (x - hi).half().float()
+    raise ValueError(mode)
+
+
+def _q(x, w, tag, kind):
+    if EMU is None:
+        return x, w
+    am, wm = EMU(tag, kind)
+    return _round(x, am), _round(w, wm)
+
 
 # --------------------------------------------------------------------------- small helpers
 def _act(x, name):
@@ -40,13 +66,21 @@ def _bn_eval(sd, p, x):
 
 
 def _conv(sd, p, x, stride=1, padding=0, dilation=1):
-    return F.conv3d(x, sd[p + "weight"], sd.get(p + "bias"), stride=stride, padding=padding,
-                    dilation=dilation)
+    w = sd[p + "weight"]
+    kind = "conv%d%s" % (w.shape[2], "s2" if stride != 1 else "")
+    x, w = _q(x, w, p, kind)
+    return F.conv3d(x, w, sd.get(p + "bias"), stride=stride, padding=padding, dilation=dilation)
+
+
+def _linear(sd, p, x, bias=True):
+    x, w = _q(x, sd[p + "weight"], p, "linear")
+    return F.linear(x, w, sd[p + "bias"] if bias else None)
 
 
 def _deconv2(sd, p, x):
     """ConvTranspose3d k=2 s=2 no bias (monai get_conv_layer(is_transposed=True))."""
-    return F.conv_transpose3d(x, sd[p + "weight"], None, stride=2)
+    x, w = _q(x, sd[p + "weight"], p, "deconv")
+    return F.conv_transpose3d(x, w, None, stride=2)
 
 
 # --------------------------------------------------------------------------- net_A (C3D U-Net)
@@ -67,6 +101,7 @@ def c3d_base_unet(sd: SD, p: str, x):
         enc.append(h)
     h = enc[4]
     for s in (4, 3, 2, 1):
+        h, _ = _q(h, h, f"{p}decoder.upconv_{s}.", "upsample")
         up = F.interpolate(h, scale_factor=2, mode="trilinear", align_corners=True)  # c3d.py:36
         up = _single_conv(sd, f"{p}decoder.upconv_{s}.conv.", up)
         h = torch.cat((up, enc[s - 1]), dim=1)
@@ -86,7 +121,7 @@ def vit(sd: SD, p: str, x, num_layers: int, num_heads: int, patch: int = 16):
     t = x.reshape(b, c, g[0], patch, g[1], patch, g[2], patch)
     t = t.permute(0, 2, 4, 6, 3, 5, 7, 1).reshape(b, g[0] * g[1] * g[2], patch ** 3 * c)
     q = p + "patch_embedding."
-    t = F.linear(t, sd[q + "patch_embeddings.1.weight"], sd[q + "patch_embeddings.1.bias"])
+    t = _linear(sd, q + "patch_embeddings.1.", t)
     t = t + sd[q + "position_embeddings"]
     hidden = t.shape[-1]
     d = hidden // num_heads
@@ -94,15 +129,21 @@ def vit(sd: SD, p: str, x, num_layers: int, num_heads: int, patch: int = 16):
     for i in range(num_layers):
         q = f"{p}blocks.{i}."
         y = F.layer_norm(t, (hidden,), sd[q + "norm1.weight"], sd[q + "norm1.bias"], EPS)
-        qkv = F.linear(y, sd[q + "attn.qkv.weight"])                      # no bias
+        qkv = _linear(sd, q + "attn.qkv.", y, bias=False)                # no bias
         # 'b h (qkv l d) -> qkv b l h d'
         qkv = qkv.reshape(b, -1, 3, num_heads, d).permute(2, 0, 3, 1, 4)
-        att = torch.softmax(qkv[0] @ qkv[1].transpose(-1, -2) * d ** -0.5, dim=-1)
-        y = (att @ qkv[2]).permute(0, 2, 1, 3).reshape(b, -1, hidden)
-        t = t + F.linear(y, sd[q + "attn.out_proj.weight"], sd[q + "attn.out_proj.bias"])
+        if EMU is None:
+            att = torch.softmax(qkv[0] @ qkv[1].transpose(-1, -2) * d ** -0.5, dim=-1)
+            y = (att @ qkv[2]).permute(0, 2, 1, 3).reshape(b, -1, hidden)
+        else:   # the CUDA path folds the scale into q before rounding q/k/v/p to fp16
+            qq, kk = _q(qkv[0] * d ** -0.5, qkv[1], q + "attn.qk.", "attn")
+            att = torch.softmax(qq @ kk.transpose(-1, -2), dim=-1)
+            att, vv = _q(att, qkv[2], q + "attn.pv.", "attn")
+            y = (att @ vv).permute(0, 2, 1, 3).reshape(b, -1, hidden)
+        t = t + _linear(sd, q + "attn.out_proj.", y)
         y = F.layer_norm(t, (hidden,), sd[q + "norm2.weight"], sd[q + "norm2.bias"], EPS)
-        y = F.gelu(F.linear(y, sd[q + "mlp.linear1.weight"], sd[q + "mlp.linear1.bias"]))
-        t = t + F.linear(y, sd[q + "mlp.linear2.weight"], sd[q + "mlp.linear2.bias"])
+        y = F.gelu(_linear(sd, q + "mlp.linear1.", y))
+        t = t + _linear(sd, q + "mlp.linear2.", y)
         hs.append(t)
     return F.layer_norm(t, (hidden,), sd[p + "norm.weight"], sd[p + "norm.bias"], EPS), hs
 
@@ -118,11 +159,13 @@ def unet_res_block(sd: SD, p: str, x):
     """monai: dynunet_block.UnetResBlock.forward, k=3 s=1, instance norm (no affine), LeakyReLU 0.01;
     conv3/norm3 on the residual only when in_channels != out_channels."""
     w1 = sd[p + "conv1.conv.weight"]
-    y = _act(_inorm(F.conv3d(x, w1, None, padding=1)), "lrelu")
-    y = _inorm(F.conv3d(y, sd[p + "conv2.conv.weight"], None, padding=1))
+    y = _act(_inorm(_conv(sd, p + "conv1.conv.", x, padding=1)), "lrelu")
+    y = _inorm(_conv(sd, p + "conv2.conv.", y, padding=1))
     r = x
     if w1.shape[0] != w1.shape[1]:
-        r = _inorm(F.conv3d(x, sd[p + "conv3.conv.weight"], None))
+        r = _inorm(_conv(sd, p + "conv3.conv.", x))
+    elif EMU is not None:
+        r = _q(x, x, p + "residual.", "store")[0]
     return _act(y + r, "lrelu")
 
 

@@ -1,0 +1,46 @@
+"""The C-ABI library loads on CPU and exports every symbol include/dose_b200.h declares (no compute)."""
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+from dose_prediction_b200 import _lib
+
+
+def _declared():
+    with open(os.path.join(ROOT, "include", "dose_b200.h")) as f:
+        text = f.read()
+    return sorted(set(re.findall(r"\b(dp_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__
+    __graft_entry__.build()
+    handle = _lib.lib()
+    names = _declared()
+    assert names == _lib.exported_symbols()
+    for n in names:
+        assert getattr(handle, n) is not None
+    assert handle.dp_abi_version() == 1
+    assert isinstance(handle.dp_last_error(), bytes)
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(_lib, "_LIB", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _lib.lib()
+
+
+def test_sass_contains_blackwell_tensor_and_tma_instructions():
+    """cuobjdump evidence that the hot kernels are tcgen05/TMA code, not recompiled mma.sync."""
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    import __graft_entry__
+    __graft_entry__.build()
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    assert "UTCHMMA" in sass and "UTMALDG" in sass and "LDTM" in sass
+    assert "HMMA." not in sass.replace("UTCHMMA", "")
