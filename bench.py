@@ -1,0 +1,278 @@
+#!/usr/bin/env python
+"""Headline benchmark: 128^3 cascade volumes/sec (OAR-TRANSEG -> hand-off -> DOSE-PYFER inference).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--size S] [--impl reference]
+
+One "step" = one cascade pass over a batch of B synthetic OpenKBP-shaped volumes per GPU.  Prints ONE
+JSON line (see DESIGN.md "Measurement"):
+  value     whole-job volumes/s with inputs resident in HBM (device-timed, CUDA events, max over ranks)
+  e2e       same metric through CascadePlan.__call__ with pinned HOST inputs (H2D + D2H inside the timing)
+  roofline  the dominant kernel family (tcgen05 implicit-GEMM conv): algorithmic conv FLOPs / summed
+            launch time measured live with CUDA events, against the measured bf16 peak
+  cpu_baseline  the oracle port (oracle/torch_ref.py, fp32, all host threads) on one volume, rank 0, N=1
+`--impl reference` times that CPU port alone (the real reference cannot travel: it needs monai 0.7.0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "cascade_volumes_per_sec_128cubed"
+UNIT = "volumes/s"
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"tflops": float(p.get("bf16_tflops_sustained", p.get("bf16_tflops", 1400.0))), "hbm_gbs": float(p["hbm_gbs"]),
+                "source": "measured (MEASURED_PEAKS.json, sustained bf16)"}
+    return {"tflops": 1400.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md, sustained)"}
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.path = gpu_index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "200"], stdout=open(self.path, "w"),
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        with open(self.path) as f:
+            for line in f:
+                c = [x.strip() for x in line.split(",")]
+                if len(c) < 8:
+                    continue
+                try:
+                    sm.append(float(c[1])); mx.append(float(c[2]))
+                except ValueError:
+                    continue
+                for n, v in zip(names, c[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        os.unlink(self.path)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def _cpu_cascade(seg_sd, dose_sd, vol, torch_ref):
+    import torch
+    with torch.no_grad():
+        logits = torch_ref.oar_transeg_forward(seg_sd, vol["ct"])
+        st = torch_ref.handoff(logits, vol["ptv"], vol["ct"])
+        return torch_ref.dose_pyfer_forward(dose_sd, st)[1][0]
+
+
+def cpu_baseline(seg_sd, dose_sd, size, volumes=1):
+    """oracle port timed on the host cores (reported baseline, not the optimisation target)."""
+    import torch
+
+    from dose_prediction_b200 import synth
+    from oracle import torch_ref
+    torch.set_num_threads(os.cpu_count() or 1)
+    vol = synth.make_volume(size, seed=1234)
+    t0 = time.perf_counter()
+    for _ in range(volumes):
+        _cpu_cascade(seg_sd, dose_sd, vol, torch_ref)
+    dt = time.perf_counter() - t0
+    return {"value": volumes / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{volumes} x {size}^3 cascade volume(s), oracle/torch_ref.py fp32, {dt:.1f} s"}
+
+
+def build_models(size, device=None):
+    import torch
+
+    from dose_prediction_b200 import networks
+    torch.manual_seed(0)
+    dose = networks.Model(9, 1, [-1, 16, 32, 64, 128, 256], feature_size=16, img_size=(size,) * 3, num_layers=8,
+                          num_heads=6, act="mish", mode_multi_dec=True, multiS_conv=True).eval()
+    seg = networks.OARTranseg(1, 8, (size,) * 3, feature_size=16, hidden_size=768, mlp_dim=3072, num_heads=12,
+                              pos_embed="perceptron", norm_name="instance", res_block=True, conv_block=True).eval()
+    if device is not None:
+        dose, seg = dose.to(device), seg.to(device)
+    return seg, dose
+
+
+def run_reference(args):
+    """--impl reference: the CPU implementation of the path on the host cores (rank 0 only)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import torch
+
+    from dose_prediction_b200 import synth
+    from oracle import torch_ref
+    torch.set_num_threads(os.cpu_count() or 1)
+    seg, dose = build_models(args.size)
+    ssd, dsd = seg.state_dict(), dose.state_dict()
+    vol = synth.make_volume(args.size, seed=1234)
+    for _ in range(args.warmup):
+        _cpu_cascade(ssd, dsd, vol, torch_ref)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        _cpu_cascade(ssd, dsd, vol, torch_ref)
+    dt = time.perf_counter() - t0
+    val = args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"cascade OAR-TRANSEG->DOSE-PYFER inference, {args.size}^3, 1 volume per step (bounded sample)",
+                       "batch_per_gpu": 1},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": f"{args.steps} x {args.size}^3 cascade volumes, oracle/torch_ref.py fp32 (reference "
+                                       "modules need monai 0.7.0, absent on the box)"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("DP_BENCH_BATCH", "8")))
+    ap.add_argument("--size", type=int, default=128)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__
+    from dose_prediction_b200 import synth
+    from dose_prediction_b200.cascade import CascadePlan
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    __graft_entry__.build()
+
+    B, S = args.batch, args.size
+    seg, dose = build_models(S, dev)
+    casc = CascadePlan(seg, dose, B, S, dev, graph=False)
+    plan = casc.plan
+    # synthetic volumes: this rank's shard of a job of world*B volumes (weak scaling), pinned on the host
+    vols = synth.make_batch(B, S, seed=1234 + rank * B)
+    ct_h, ptv_h = vols["ct"].pin_memory(), vols["ptv"].pin_memory()
+    out_h = torch.empty((B, 1, S, S, S), dtype=torch.float32).pin_memory()
+    casc.ct.copy_(ct_h)
+    casc.ptv.copy_(ptv_h)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(args.warmup):
+        casc.run()
+    torch.cuda.synchronize(dev)
+    plan.check_device_errors()
+    if not args.no_graph:
+        plan.capture()
+        casc.run()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms = timed(casc.run, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * B * args.steps / (ms / 1e3)
+
+    # ---- end to end through the public call: pinned host inputs in, dose out, every step
+    def e2e_step():
+        casc(ct_h, ptv_h)
+        out_h.copy_(casc.dose, non_blocking=True)
+    e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    e2e_val = world * B * args.steps / (ms_e2e / 1e3)
+
+    # ---- per-kernel-family device time (instrumented eager replay, CUDA events on the launch stream)
+    fam = plan.profile_families(repeats=2)
+    conv_ms = fam.get("dp_conv3d_tc", {}).get("ms", 0.0)
+    conv_launches = fam.get("dp_conv3d_tc", {}).get("launches", 0)
+    peaks = _peaks()
+    conv_flops = plan.flops.get("dp_conv3d_tc", 0.0)
+    achieved = conv_flops / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
+    total_fam = sum(v["ms"] for v in fam.values()) or 1.0
+    roofline = {"kernel": "conv3d_tc_kernel (tcgen05 implicit-GEMM 3^3/7^3 conv)", "bound": "tensor",
+                "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
+                "traffic": None, "peak_source": peaks["source"], "launches_per_step": conv_launches,
+                "avg_launch_ms": conv_ms / max(conv_launches, 1), "algorithmic_flops_per_step": conv_flops,
+                "share_of_step": conv_ms / total_fam}
+    plan.check_device_errors()
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f16", "data": "synthetic",
+                "config": {"workload": f"cascade OAR-TRANSEG->hand-off->DOSE-PYFER inference, {S}^3, batch {B} per GPU "
+                                       "(BASELINE.json configs[2]; configs[1] seg forward is its first half)",
+                           "batch_per_gpu": B, "size": S, "parallelism": f"volume-sharded x{world}, no collective",
+                           "cuda_graph": not args.no_graph,
+                           "l2": f"no flush: per-step working set {plan.bytes_alloc / 2**30:.1f} GiB >> 126 MB L2"},
+                "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                        "h2d_bytes_per_step": 2 * B * S ** 3 * 4, "d2h_bytes_per_step": B * S ** 3 * 4},
+                "gpu_launches": plan.launches * args.steps, "launches_per_step": plan.launches,
+                "roofline": roofline, "kernel_ms_per_step": {k: round(v["ms"], 3) for k, v in sorted(fam.items())},
+                "clocks": clocks}
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline({k: v.cpu() for k, v in seg.state_dict().items()},
+                                                {k: v.cpu() for k, v in dose.state_dict().items()}, S)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

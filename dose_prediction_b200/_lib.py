@@ -28,6 +28,7 @@ _SIGNATURES = {
     "dp_upsample2x": [P, P, I, I, I, I, I, I, I, P, P, I, I, P],
     "dp_layernorm": [P, P, P, I, I, P, P, P],
     "dp_softmax": [P, I, I, I, P, I, P],
+    "dp_splitk_reduce": [P, I, I, I, P, P, I, P, P],
     "dp_patchify": [P, I, I, I, I, I, I, I, P, P],
     "dp_handoff": [P, I, P, P, I, I, P, P, I, I, P, P],
 }

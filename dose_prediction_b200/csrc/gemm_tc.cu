@@ -17,6 +17,7 @@ namespace dp {
 struct GemmParams {
   int M, N, K;
   int batch, split_k, kb_per_split;
+  long long split_stride;              // split-K: partial sums of split s go to out_f32 + s*split_stride (deterministic)
   int a_batch_rows, b_batch_rows;      // row offset per batch entry inside the A / B tensor maps
   long long c_batch_stride;            // element offset per batch entry in the outputs ...
   int c_batch_period; long long c_batch_stride2;   // ... or (z / period) * stride + (z % period) * stride2
@@ -160,7 +161,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const size_t boff = p.c_batch_period > 0
               ? static_cast<size_t>(bz / p.c_batch_period) * p.c_batch_stride + static_cast<size_t>(bz % p.c_batch_period) * p.c_batch_stride2
               : static_cast<size_t>(bz) * p.c_batch_stride;
-          const size_t base = boff + static_cast<size_t>(m) * p.ldc + n0 + c0;
+          const size_t base = boff + static_cast<size_t>(sk) * p.split_stride + static_cast<size_t>(m) * p.ldc + n0 + c0;
           const bool full = (n0 + c0 + 16 <= p.N);
           if (p.resid && lead) {
 #pragma unroll
@@ -218,12 +219,13 @@ extern "C" int dp_gemm_tc(const void* A, const void* B, int M, int N, int K, int
   using namespace dp;
   DP_REQUIRE(K % 8 == 0, "dp_gemm_tc: K=%d must be a multiple of 8 (TMA 16-byte row pitch)", K);
   DP_REQUIRE(batch >= 1 && split_k >= 1, "dp_gemm_tc: bad batch/split_k");
-  DP_REQUIRE(split_k == 1 || (atomic && out_f32 && !out_f16 && !mode_qkv && act == 0),
-             "dp_gemm_tc: split-K needs the fp32 atomic epilogue only");
+  DP_REQUIRE(split_k == 1 || (out_f32 && !atomic && !out_f16 && !mode_qkv && act == 0 && !bias && !rowvec && !resid && batch == 1),
+             "dp_gemm_tc: split-K writes plain fp32 partials [split_k][M][ldc] (finish with dp_splitk_reduce)");
   GemmParams p{};
   p.M = M; p.N = N; p.K = K; p.batch = batch; p.split_k = split_k;
   const int total_kb = (K + BK - 1) / BK;
   p.kb_per_split = (total_kb + split_k - 1) / split_k;
+  p.split_stride = static_cast<long long>(M) * ldc;
   p.a_batch_rows = a_batch_rows; p.b_batch_rows = b_batch_rows; p.c_batch_stride = c_batch_stride; p.c_batch_period = c_batch_period; p.c_batch_stride2 = c_batch_stride2; p.ldc = ldc;
   p.bias = bias; p.rowvec = rowvec; p.row_period = row_period > 0 ? row_period : 1; p.resid = resid;
   p.alpha = alpha; p.act = act; p.out_f32 = out_f32; p.atomic = atomic; p.out_f16 = static_cast<__half*>(out_f16);

@@ -401,6 +401,27 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
   }
 }
 
+// ------------------------------------------------------------------ deterministic split-K finish
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ ws, int splits, long long MN, int N, const float* __restrict__ bias,
+                     const float* __restrict__ rowvec, int row_period, float* out) {
+  const long long i = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) * 4;
+  if (i >= MN) return;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s = 0; s < splits; ++s) {
+    const float4 v = *reinterpret_cast<const float4*>(ws + s * MN + i);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  const int n = static_cast<int>(i % N);
+  const long long m = i / N;
+  if (bias) { acc.x += bias[n]; acc.y += bias[n + 1]; acc.z += bias[n + 2]; acc.w += bias[n + 3]; }
+  if (rowvec) {
+    const float* r = rowvec + (m % row_period) * N + n;
+    acc.x += r[0]; acc.y += r[1]; acc.z += r[2]; acc.w += r[3];
+  }
+  *reinterpret_cast<float4*>(out + i) = acc;
+}
+
 // ------------------------------------------------------------------ row softmax fp32 -> fp16 (one warp per row)
 __global__ void __launch_bounds__(256)
 softmax_kernel(const float* __restrict__ s, int rows, int cols, int ld_in, __half* p, int ld_out) {
@@ -710,6 +731,15 @@ extern "C" int dp_upsample2x(const void* in_hi, const void* in_lo, int in_cb_tot
 extern "C" int dp_layernorm(const float* x, const float* gamma, const float* beta, int rows, int cols, void* out_f16,
                             float* out_f32, cudaStream_t stream) {
   layernorm_kernel<<<blocks_for(rows, 8), 256, 0, stream>>>(x, gamma, beta, rows, cols, static_cast<__half*>(out_f16), out_f32);
+  DP_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dp_splitk_reduce(const float* ws, int splits, int M, int N, const float* bias, const float* rowvec,
+                                int row_period, float* out, cudaStream_t stream) {
+  DP_REQUIRE(N % 4 == 0, "dp_splitk_reduce: N=%d must be a multiple of 4", N);
+  const long long MN = static_cast<long long>(M) * N;
+  splitk_reduce_kernel<<<blocks_for(MN / 4, 256), 256, 0, stream>>>(ws, splits, MN, N, bias, rowvec, row_period > 0 ? row_period : 1, out);
   DP_CHECK(cudaGetLastError());
   return 0;
 }

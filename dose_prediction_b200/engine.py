@@ -103,6 +103,7 @@ class Plan:
         self.bytes_alloc = 0
         self.graph = None
         self.launches = 0
+        self.flops = {}          # algorithmic FLOPs (2*MAC of the reference op) per kernel family, per replay
 
     # ------------------------------------------------------------------ memory
     def zeros(self, shape, dtype):
@@ -175,6 +176,39 @@ class Plan:
                 _lib.check(rc, name)
             n += 1
         self.launches = n
+
+    def count_flops(self, name, flops):
+        self.flops[name] = self.flops.get(name, 0.0) + float(flops)
+
+    def profile_families(self, repeats=1):
+        """device time per kernel family: eager replay with a CUDA-event pair around every launch on the
+        launch stream; returns {family: {"ms": per-replay total, "launches": n}}."""
+        stream = torch.cuda.current_stream(self.device)
+        s = stream.cuda_stream
+        out = {}
+        for _ in range(repeats):
+            if self.stats_used:
+                self.stats[:self.stats_used].zero_()
+            evs = []
+            for fn, args, name in self.steps:
+                if fn is None:
+                    args[0].zero_()
+                    continue
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                rc = fn(*args, s)
+                e1.record(stream)
+                if rc:
+                    _lib.check(rc, name)
+                evs.append((name, e0, e1))
+            torch.cuda.synchronize(self.device)
+            for name, e0, e1 in evs:
+                d = out.setdefault(name, {"ms": 0.0, "launches": 0})
+                d["ms"] += e0.elapsed_time(e1) / repeats
+                d["launches"] += 1
+        for d in out.values():
+            d["launches"] //= repeats
+        return out
 
     def check_device_errors(self):
         if int(self.err.item()) != 0:
@@ -271,6 +305,7 @@ class Plan:
         else:
             of32, ohi, olo, cbt, cbo = None, out_act.hi_ptr, out_act.lo_ptr, out_act.cb_total, out_act.cb_off
             st = stats
+        self.count_flops("dp_conv3d_tc", 2.0 * a0.N * D * H * W * k ** 3 * weight.shape[1] * Co)
         self.add("dp_conv3d_tc", a0.buf.data_ptr(), a0.cb_total, chunks, nch, wp.data_ptr(), a0.N, D, H, W, Co, k, dil,
                  scale.data_ptr(), shift.data_ptr(), int(relu), of32, ohi, olo, cbt, cbo,
                  st.data_ptr() if st is not None else None, self.err.data_ptr(), 0)
@@ -387,6 +422,15 @@ class Plan:
         self.add("dp_gemm_tc", p(A), p(B), M, N, K, batch, a_batch_rows, b_batch_rows, c_batch_stride, c_batch_period,
                  c_batch_stride2, ldc, split_k, p(bias), p(rowvec), row_period, p(resid), float(alpha), ACT_ID[act],
                  p(out_f32), int(atomic), p(out_f16), mode_qkv, heads, hd, T, q, k, vt, float(qs), self.err.data_ptr())
+
+    def gemm_splitk(self, A, B, M, N, K, split_k, out_f32, bias=None, rowvec=None, row_period=0):
+        """deterministic split-K: fp32 partials to a workspace, then one reduction pass (+bias, +rowvec)."""
+        if split_k <= 1:
+            return self.gemm(A, B, M, N, K, bias=bias, rowvec=rowvec, row_period=row_period, out_f32=out_f32)
+        ws = self.zeros((split_k, M, N), torch.float32)
+        self.gemm(A, B, M, N, K, split_k=split_k, out_f32=ws)
+        self.add("dp_splitk_reduce", ws.data_ptr(), split_k, M, N, bias.data_ptr() if bias is not None else None,
+                 rowvec.data_ptr() if rowvec is not None else None, row_period, out_f32.data_ptr())
 
     def layernorm(self, x, gamma, beta, rows, cols, out_f16=None, out_f32=None):
         self.add("dp_layernorm", x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), rows, cols,

@@ -355,10 +355,9 @@ def _emit_vit(P, vit, parts, N, S, taps):
     pos = P.dev(vit.patch_embedding.position_embeddings.reshape(T, hidden))
     tiles = ceil_div(M, 128) * ceil_div(hidden, 128)
     split_k = max(1, min(K // 64, (2 * 148) // tiles))
-    if split_k > 1:
-        P.add_zero(x)
-    P.gemm(A, wpe, M, hidden, K, split_k=split_k, bias=P.dev(lin.bias), rowvec=pos, row_period=T, out_f32=x,
-           atomic=split_k > 1)
+    total_kb = K // 64
+    split_k = ceil_div(total_kb, ceil_div(total_kb, split_k))          # no empty splits
+    P.gemm_splitk(A, wpe, M, hidden, K, split_k, x, bias=P.dev(lin.bias), rowvec=pos, row_period=T)
     ln = P.zeros((M, hidden), torch.float16)
     q = P.zeros((N * heads, T, hd), torch.float16)
     k = P.zeros((N * heads, T, hd), torch.float16)

@@ -65,12 +65,18 @@ int dp_conv3d_direct(const void* in_hi, const void* in_lo, int in_cb_total, int 
  * einsums, MLPBlock.linear1 (+GELU) / linear2 (+residual).  mode_qkv scatters the [M, 3*heads*hd] result
  * into q [B,heads,T,hd] (scaled by q_scale), k [B,heads,T,hd], v^T [B,heads,hd,T]
  * (einops "b h (qkv l d) -> qkv b l h d").  Batched: A/B rows advance by a/b_batch_rows per batch entry z,
- * outputs by z*c_batch_stride, or (z/period)*c_batch_stride + (z%period)*c_batch_stride2 if period>0. */
+ * outputs by z*c_batch_stride, or (z/period)*c_batch_stride + (z%period)*c_batch_stride2 if period>0.
+ * split_k > 1: plain fp32 partial sums go to out_f32[split][M][ldc]; finish with dp_splitk_reduce.      */
 int dp_gemm_tc(const void* A, const void* B, int M, int N, int K, int batch, int a_batch_rows, int b_batch_rows,
                long long c_batch_stride, int c_batch_period, long long c_batch_stride2, int ldc, int split_k, const float* bias, const float* rowvec,
                int row_period, const float* resid, float alpha, int act, float* out_f32, int atomic,
                void* out_f16, int mode_qkv, int heads, int hd, int T, void* q, void* k, void* vt, float q_scale,
                int* err_flag, cudaStream_t stream);
+
+/* Deterministic split-K finish: out[m][n] = sum_s ws[s][m][n] + bias[n] + rowvec[m % row_period][n]
+ * (dp_gemm_tc with split_k > 1 writes the fp32 partials ws[split_k][M][N]; no atomics anywhere). */
+int dp_splitk_reduce(const float* ws, int splits, int M, int N, const float* bias, const float* rowvec, int row_period,
+                     float* out, cudaStream_t stream);
 
 /* NCDHW fp32 <-> c8 fp16 (module-boundary conversion; batch['Input'].float(), train_light_pyfer.py:124) */
 int dp_pack_ncdhw(const float* src, int N, int C, long long vox, void* hi, void* lo, int cb_total, int cb_off,

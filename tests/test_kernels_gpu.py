@@ -1,0 +1,315 @@
+"""Per-kernel parity on a real B200, every call going through the C ABI (engine.Plan emitters).
+
+Floating-point kernels: the comparison target is a plain PyTorch fp32/fp64 evaluation of the same op on
+the operands exactly as the kernel sees them (fp16-rounded where the kernel stores fp16), so the only
+difference left is fp32 accumulation order; tolerances are written per test.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _plan():
+    from dose_prediction_b200.engine import Plan
+    return Plan(torch.device("cuda:0"))
+
+
+def _raw_to_ncdhw(t):
+    n, cb, d, h, w, _ = t.shape
+    return t.permute(0, 1, 5, 2, 3, 4).reshape(n, cb * 8, d, h, w)
+
+
+def _rel(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+
+
+def _h(x):
+    return x.half().float()
+
+
+def _finish(P):
+    torch.cuda.synchronize()
+    P.check_device_errors()
+
+
+def _act_from(P, x, lo):
+    """fp32 NCDHW cuda tensor -> packed Act through dp_pack_ncdhw."""
+    a = P.new_act(x.shape[0], x.shape[1], tuple(x.shape[2:]), lo=lo)
+    P.keep.append(x)
+    P.pack_input(x, a)
+    return a
+
+
+@pytest.mark.parametrize("cin,cout,k,dil,dims,mode", [
+    (16, 16, 3, 1, (16, 16, 16), "p1"),
+    (32, 16, 7, 1, (9, 20, 12), "p1"),          # ragged H/W tiles, 2 K-chunks, full 7x7 stage
+    (16, 64, 7, 1, (8, 16, 16), "p1"),          # kh-group split stages
+    (16, 128, 7, 1, (4, 16, 8), "p1"),          # one kh row per stage
+    (64, 64, 3, 1, (8, 16, 16), "p1"),
+    (128, 256, 3, 1, (4, 8, 8), "p1"),          # H < 16 (masked rows), N = 256
+    (16, 16, 3, 2, (12, 16, 16), "p1"),         # dilation 2
+    (9, 16, 3, 1, (16, 16, 16), "p3"),          # padded input channels + 3-term operand split
+    (32, 32, 3, 1, (8, 16, 8), "p2"),
+])
+def test_conv3d_tc_matches_torch(cin, cout, k, dil, dims, mode):
+    torch.manual_seed(0)
+    dev = torch.device("cuda:0")
+    N = 2
+    x = torch.randn(N, cin, *dims, device=dev)
+    w = torch.randn(cout, cin, k, k, k, device=dev) / (cin * k ** 3) ** 0.5
+    bias = torch.randn(cout, device=dev) * 0.1
+    P = _plan()
+    a = _act_from(P, x, lo=(mode != "p1"))
+    raw = P.get_raw(N, cout, dims)
+    scale, shift = P.affine(cout, bias=bias)
+    P.conv_tc([a], w, k, dil, mode, scale, shift, False, out_raw=raw)
+    P.run()
+    _finish(P)
+    got = _raw_to_ncdhw(raw.t)
+    xe, we = (_h(x), _h(w)) if mode == "p1" else (x, w)
+    want = F.conv3d(xe.double().cpu(), we.double().cpu(), bias.double().cpu(), padding=dil * (k - 1) // 2, dilation=dil)
+    tol = 2e-5 if mode != "p2" else 1e-3        # p2 keeps fp16-rounded weights
+    if mode == "p2":
+        want = F.conv3d(x.double().cpu(), _h(w).double().cpu(), bias.double().cpu(), padding=dil * (k - 1) // 2)
+        tol = 2e-5
+    assert _rel(got.cpu(), want) < tol
+    # statistics accumulated by the epilogue from the fp32 accumulators
+    st = raw.stats.view(N, cout, 2).cpu()
+    assert torch.allclose(st[..., 0], want.sum((2, 3, 4)), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(st[..., 1], (want ** 2).sum((2, 3, 4)), rtol=1e-4, atol=1e-2)
+
+
+def test_conv3d_tc_concat_parts_bn_fold_relu_fp16_out():
+    torch.manual_seed(1)
+    dev = torch.device("cuda:0")
+    N, dims, C = 2, (8, 16, 16), 16
+    xa, xb = torch.randn(N, C, *dims, device=dev), torch.randn(N, C, *dims, device=dev)
+    w = torch.randn(C, 2 * C, 7, 7, 7, device=dev) / (2 * C * 343) ** 0.5
+    bn = torch.nn.BatchNorm3d(C).to(dev).eval()
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5); bn.bias.uniform_(-0.2, 0.2)
+        bn.running_mean.uniform_(-0.2, 0.2); bn.running_var.uniform_(0.5, 1.5)
+    bias = torch.randn(C, device=dev) * 0.1
+    P = _plan()
+    pa, pb = P.new_concat(N, [C, C], dims)
+    P.keep += [xa, xb]
+    P.pack_input(xa, pa)
+    P.pack_input(xb, pb)
+    out = P.new_act(N, C, dims, lo=True)
+    st = P.new_stats(N, C)
+    P.conv_tc([pa, pb], w, 7, 1, "p1", *P.affine(C, bias=bias, bn=bn), True, out_act=out, stats=st)
+    y = torch.zeros(N, C, *dims, device=dev)
+    P.unpack(out, y)
+    P.run()
+    _finish(P)
+    with torch.no_grad():
+        want = F.relu(F.batch_norm(F.conv3d(_h(torch.cat((xa, xb), 1)).double().cpu(), _h(w).double().cpu(),
+                                            bias.double().cpu(), padding=3), bn.running_mean.double().cpu(),
+                                   bn.running_var.double().cpu(), bn.weight.double().cpu(), bn.bias.double().cpu(),
+                                   False, 0.0, bn.eps))
+    assert _rel(y.cpu(), want) < 2e-5           # hi+lo output carries ~22 bits
+    assert torch.allclose(st.view(N, C, 2)[..., 0].cpu(), want.sum((2, 3, 4)), rtol=1e-4, atol=1e-2)
+
+
+@pytest.mark.parametrize("M,N,K,split", [(512, 768, 768, 1), (256, 768, 4096, 4), (8, 768, 32768, 8), (512, 2304, 768, 1)])
+def test_gemm_tc_matches_torch(M, N, K, split):
+    torch.manual_seed(2)
+    dev = torch.device("cuda:0")
+    A = (torch.randn(M, K, device=dev) / K ** 0.5).half()
+    B = torch.randn(N, K, device=dev).half()
+    bias = torch.randn(N, device=dev)
+    P = _plan()
+    out = P.zeros((M, N), torch.float32)
+    P.gemm_splitk(A, B, M, N, K, split, out, bias=bias)
+    P.run()
+    _finish(P)
+    want = A.double().cpu() @ B.double().cpu().t() + bias.double().cpu()
+    assert _rel(out.cpu(), want) < 1e-5
+
+
+def test_gemm_tc_epilogues_gelu_residual_fp16():
+    torch.manual_seed(3)
+    dev = torch.device("cuda:0")
+    M, N, K = 200, 768, 3072
+    A = (torch.randn(M, K, device=dev) / K ** 0.5).half()
+    B = torch.randn(N, K, device=dev).half()
+    bias = torch.randn(N, device=dev)
+    x = torch.randn(M, N, device=dev)
+    x0 = x.clone()
+    P = _plan()
+    h16 = P.zeros((M, N), torch.float16)
+    P.gemm(A, B, M, N, K, bias=bias, resid=x, out_f32=x, out_f16=h16)
+    g16 = P.zeros((M, N), torch.float16)
+    P.gemm(A, B, M, N, K, bias=bias, act="gelu", out_f16=g16)
+    P.run()
+    _finish(P)
+    lin = A.double().cpu() @ B.double().cpu().t() + bias.double().cpu()
+    assert _rel(x.cpu(), lin + x0.double().cpu()) < 1e-5
+    assert _rel(h16.float().cpu(), lin + x0.double().cpu()) < 1e-3
+    assert _rel(g16.float().cpu(), F.gelu(lin)) < 1e-3
+
+
+@pytest.mark.parametrize("T,heads,hd", [(512, 6, 128), (8, 12, 64), (216, 12, 64)])
+def test_attention_pipeline_matches_torch(T, heads, hd):
+    """qkv scatter GEMM -> QK^T -> softmax -> PV, i.e. monai SABlock.forward without the projections."""
+    torch.manual_seed(4)
+    dev = torch.device("cuda:0")
+    Bn, hidden = 2, heads * hd
+    M = Bn * T
+    xin = torch.randn(M, hidden, device=dev).half()
+    wqkv = (torch.randn(3 * hidden, hidden, device=dev) / hidden ** 0.5).half()
+    P = _plan()
+    q = P.zeros((Bn * heads, T, hd), torch.float16)
+    k = P.zeros((Bn * heads, T, hd), torch.float16)
+    vt = P.zeros((Bn * heads, hd, T), torch.float16)
+    s = P.zeros((Bn * heads, T, T), torch.float32)
+    pr = P.zeros((Bn * heads, T, T), torch.float16)
+    o = P.zeros((M, hidden), torch.float16)
+    P.gemm(xin, wqkv, M, 3 * hidden, hidden, qkv=(heads, hd, T, q, k, vt, hd ** -0.5))
+    P.gemm(q, k, T, T, hd, batch=Bn * heads, a_batch_rows=T, b_batch_rows=T, c_batch_stride=T * T, ldc=T, out_f32=s)
+    P.softmax(s, Bn * heads * T, T, pr)
+    P.gemm(pr, vt, T, hd, T, batch=Bn * heads, a_batch_rows=T, b_batch_rows=hd, c_batch_stride=T * hidden,
+           c_batch_period=heads, c_batch_stride2=hd, ldc=hidden, out_f16=o)
+    P.run()
+    _finish(P)
+    qkv = (xin.double().cpu() @ wqkv.double().cpu().t()).reshape(Bn, T, 3, heads, hd).permute(2, 0, 3, 1, 4)
+    att = torch.softmax(qkv[0] @ qkv[1].transpose(-1, -2) * hd ** -0.5, dim=-1)
+    want = (att @ qkv[2]).permute(0, 2, 1, 3).reshape(M, hidden)
+    assert _rel(o.float().cpu(), want) < 4e-3       # q, k, v, p rounded to fp16
+
+
+def test_norm_act_residual_and_chained_stats():
+    torch.manual_seed(5)
+    dev = torch.device("cuda:0")
+    N, C, dims = 2, 16, (8, 16, 16)
+    x = torch.randn(N, C, *dims, device=dev) * 2 + 3
+    r = torch.randn(N, C, *dims, device=dev)
+    g, b = torch.rand(C, device=dev) + 0.5, torch.randn(C, device=dev)
+    P = _plan()
+    a = _act_from(P, x, lo=True)
+    res = _act_from(P, r, lo=True)
+    one, zero = P.affine(C)
+    w = torch.zeros(C, C, 1, 1, 1, device=dev)
+    w[torch.arange(C), torch.arange(C)] = 1.0
+    raw = P.get_raw(N, C, dims)
+    P.pointwise([(a, None, None)], w, None, out_raw=raw)          # identity 1x1 -> raw fp32 + stats
+    out = P.new_act(N, C, dims, lo=True)
+    st2 = P.new_stats(N, C)
+    P.norm_act(raw, out, gamma=g, beta=b, act="relu", res=res, act_after_res="lrelu", stats_out=st2)
+    y = torch.zeros(N, C, *dims, device=dev)
+    P.unpack(out, y)
+    P.run()
+    _finish(P)
+    want = F.leaky_relu(F.relu(F.instance_norm(x.double().cpu(), weight=g.double().cpu(), bias=b.double().cpu(), eps=1e-5))
+                        + r.double().cpu(), 0.01)
+    assert _rel(y.cpu(), want) < 1e-5
+    assert torch.allclose(st2.view(N, C, 2)[..., 1].cpu(), (want ** 2).sum((2, 3, 4)), rtol=1e-4)
+
+
+def test_pointwise_two_sources_with_norm_on_load():
+    torch.manual_seed(6)
+    dev = torch.device("cuda:0")
+    N, C, dims = 2, 32, (8, 8, 16)
+    x3, x7 = torch.randn(N, C, *dims, device=dev) + 1, torch.randn(N, C, *dims, device=dev) * 3
+    w = torch.randn(C, 2 * C, 1, 1, 1, device=dev) / (2 * C) ** 0.5
+    bias = torch.randn(C, device=dev)
+    ident = torch.zeros(C, C, 1, 1, 1, device=dev)
+    ident[torch.arange(C), torch.arange(C)] = 1.0
+    P = _plan()
+    a3, a7 = _act_from(P, x3, True), _act_from(P, x7, True)
+    r3, r7 = P.get_raw(N, C, dims), P.get_raw(N, C, dims)
+    P.pointwise([(a3, None, None)], ident, None, out_raw=r3)
+    P.pointwise([(a7, None, None)], ident, None, out_raw=r7)
+    out = P.get_raw(N, C, dims)
+    P.pointwise([(r3, r3.stats, "mish"), (r7, r7.stats, "mish")], w, bias, out_raw=out)
+    planar = P.zeros((N, 1) + dims, torch.float32)
+    P.pointwise([(a3, None, None)], w[:1, :C], bias[:1], out_planar=planar)
+    P.run()
+    _finish(P)
+    cat = torch.cat((F.mish(F.instance_norm(x3.double().cpu(), eps=1e-5)), F.mish(F.instance_norm(x7.double().cpu(), eps=1e-5))), 1)
+    want = F.conv3d(cat, w.double().cpu(), bias.double().cpu())
+    assert _rel(_raw_to_ncdhw(out.t).cpu(), want) < 1e-5
+    assert _rel(planar.cpu(), F.conv3d(x3.double().cpu(), w[:1, :C].double().cpu(), bias[:1].double().cpu())) < 1e-5
+
+
+def test_deconv2x_c8_and_token_inputs():
+    torch.manual_seed(7)
+    dev = torch.device("cuda:0")
+    from dose_prediction_b200.engine import Tokens
+    N, Ci, Co, dims = 2, 32, 16, (4, 8, 8)
+    x = torch.randn(N, Ci, *dims, device=dev)
+    w = torch.randn(Ci, Co, 2, 2, 2, device=dev) / Ci ** 0.5
+    P = _plan()
+    a = _act_from(P, x, lo=True)
+    slot0, slot1 = P.new_concat(N, [Co, Co], tuple(2 * d for d in dims), lo=True)
+    P.deconv2x(a, w, slot1)
+    y = torch.zeros(N, Co, *[2 * d for d in dims], device=dev)
+    P.unpack(slot1, y)
+    tok = torch.randn(N, 8, 768, device=dev).half()           # [B, T=2*2*2, 768]
+    wt = torch.randn(768, Co, 2, 2, 2, device=dev) / 768 ** 0.5
+    o2 = P.new_act(N, Co, (4, 4, 4))
+    P.deconv2x(Tokens(tok, (2, 2, 2)), wt, o2)
+    y2 = torch.zeros(N, Co, 4, 4, 4, device=dev)
+    P.unpack(o2, y2)
+    P.run()
+    _finish(P)
+    assert _rel(y.cpu(), F.conv_transpose3d(x.double().cpu(), w.double().cpu(), stride=2)) < 1e-5
+    feat = tok.float().view(N, 2, 2, 2, 768).permute(0, 4, 1, 2, 3)
+    assert _rel(y2.cpu(), F.conv_transpose3d(feat.double().cpu(), wt.double().cpu(), stride=2)) < 1e-3
+
+
+def test_upsample_direct_conv_layernorm_patchify():
+    torch.manual_seed(8)
+    dev = torch.device("cuda:0")
+    N, C, dims = 2, 16, (4, 6, 8)
+    x = torch.randn(N, C, *dims, device=dev)
+    P = _plan()
+    a = _act_from(P, x, lo=True)
+    up = P.new_act(N, C, tuple(2 * d for d in dims), lo=True)
+    P.upsample2x(a, up)
+    yu = torch.zeros(N, C, *[2 * d for d in dims], device=dev)
+    P.unpack(up, yu)
+    w = torch.randn(32, C, 3, 3, 3, device=dev) / (C * 27) ** 0.5
+    bias = torch.randn(32, device=dev)
+    raw = P.get_raw(N, 32, (2, 3, 4))
+    P.conv_direct(a, w, 3, 2, 1, *P.affine(32, bias=bias), False, out_raw=raw)
+    rows = torch.randn(37, 768, device=dev) * 2 + 1
+    g, b = torch.rand(768, device=dev) + 0.5, torch.randn(768, device=dev)
+    ln = P.zeros((37, 768), torch.float32)
+    P.layernorm(rows, g, b, 37, 768, out_f32=ln)
+    xv = torch.randn(N, 9, 32, 32, 32, device=dev)
+    av = _act_from(P, xv, lo=False)
+    A = P.zeros((N * 8, 2 * 4096 * 8), torch.float16)
+    P.patchify(av, 2, A)
+    P.run()
+    _finish(P)
+    assert _rel(yu.cpu(), F.interpolate(x.double().cpu(), scale_factor=2, mode="trilinear", align_corners=True)) < 1e-5
+    assert _rel(_raw_to_ncdhw(raw.t).cpu(), F.conv3d(x.double().cpu(), w.double().cpu(), bias.double().cpu(), stride=2, padding=1)) < 1e-5
+    assert _rel(ln.cpu(), F.layer_norm(rows.double().cpu(), (768,), g.double().cpu(), b.double().cpu(), 1e-5)) < 1e-5
+    xp = torch.zeros(N, 16, 32, 32, 32)
+    xp[:, :9] = _h(xv).cpu()
+    want = xp.view(N, 2, 8, 2, 16, 2, 16, 2, 16).permute(0, 3, 5, 7, 1, 4, 6, 8, 2).reshape(N * 8, -1)
+    assert torch.equal(A.float().cpu(), want)      # pure data movement: bit exact
+
+
+def test_handoff_is_bit_exact():
+    from oracle import torch_ref
+    torch.manual_seed(9)
+    dev = torch.device("cuda:0")
+    S = 40
+    logits = torch.randn(1, 8, S, S, S, device=dev)
+    logits[0, :, :4] = 0.0                              # ties -> first index (background) must win
+    ptv, ct = torch.rand(1, 1, S, S, S, device=dev), torch.randn(1, 1, S, S, S, device=dev)
+    P = _plan()
+    out = P.new_act(1, 9, (S, S, S), lo=True)
+    st = P.zeros((1, 9, S, S, S), torch.float32)
+    P.handoff(logits, ptv, ct, out, st)
+    y = torch.zeros(1, 9, S, S, S, device=dev)
+    P.unpack(out, y)
+    P.run()
+    _finish(P)
+    want = torch_ref.handoff(logits.cpu(), ptv.cpu(), ct.cpu())
+    assert torch.equal(st.cpu(), want)
+    assert torch.allclose(y.cpu(), want, rtol=0, atol=1e-6)
