@@ -32,7 +32,8 @@ struct ConvTcParams {
   int k, dil, pad;
   int n_chunks, cb_total_in;
   int cout;
-  int kh_s, n_khg;
+  int kd_s, n_kdg;          // kd planes per stage (1, or k when the whole kernel depth fits one stage)
+  int kh_s, n_khg;          // kh rows per stage
   int PW, PHs;
   int stages;
   uint32_t a_bytes, a_bytes_al, stage_bytes;
@@ -54,6 +55,47 @@ struct ConvTcParams {
 constexpr int kConvThreads = 192;
 constexpr int kMaxStages = 8;
 
+// D[tmem] (+)= A * B with descriptors given as {lo, hi} 32-bit halves (only the start address in lo varies).
+__device__ __forceinline__ void umma_f16_ss_split(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                                  uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// Column sums of a 32(lanes = rows) x 16(columns) register tile with 16 shuffles instead of 80:
+// every step trades half of the remaining columns with the partner lane.  On return lane L holds the
+// sum over all 32 rows of column col16(L) = bits 4..1 of L (lanes L and L^1 hold the same value).
+__device__ __forceinline__ float colsum16(const float (&v)[16], int lane) {
+  float a[8], b[4], c[2];
+  const bool h4 = lane & 16, h3 = lane & 8, h2 = lane & 4, h1 = lane & 2;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float keep = h4 ? v[j + 8] : v[j], send = h4 ? v[j] : v[j + 8];
+    a[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float keep = h3 ? a[j + 4] : a[j], send = h3 ? a[j] : a[j + 4];
+    b[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const float keep = h2 ? b[j + 2] : b[j], send = h2 ? b[j] : b[j + 2];
+    c[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  const float keep = h1 ? c[1] : c[0], send = h1 ? c[0] : c[1];
+  float r = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  r += __shfl_xor_sync(0xffffffffu, r, 1);
+  return r;
+}
+
+template <int KS>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ ConvTcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -64,6 +106,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
   __shared__ uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_smem;
   __shared__ float stat_acc[4][256][2];
+  __shared__ float s_scale[256], s_shift[256];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -88,6 +131,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   for (int i = threadIdx.x; i < 4 * 256 * 2; i += kConvThreads) (&stat_acc[0][0][0])[i] = 0.f;
+  for (int i = threadIdx.x; i < p.cout; i += kConvThreads) { s_scale[i] = p.scale[i]; s_shift[i] = p.shift[i]; }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -95,87 +139,99 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
 
   const int tiles_per_plane = p.tiles_h * p.tiles_w;
   const uint32_t tap_b_bytes = 32u * static_cast<uint32_t>(p.cout);  // one tap: [2][cout][8] fp16
+  const size_t kd_w_halfs = static_cast<size_t>(p.n_chunks) * KS * KS * 16 * p.cout;   // weights of one kd (all chunks)
+  const size_t chunk_w_halfs = static_cast<size_t>(KS) * KS * 16 * p.cout;
 
   if (warp == 0) {
-    // ===================================================================== TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        int t = tile;
-        const int tw = t % p.tiles_w; t /= p.tiles_w;
-        const int th = t % p.tiles_h; t /= p.tiles_h;
-        const int d = t % p.D;
-        const int n = t / p.D;
-        const int h0 = th * 16, w0 = tw * 8;
-        for (int kd = 0; kd < p.k; ++kd) {
-          const int dz = d + kd * p.dil - p.pad;
-          if (dz < 0 || dz >= p.D) continue;
-          for (int c = 0; c < p.n_chunks; ++c) {
-            const __half* wsrc =
-                p.wpack + (static_cast<size_t>(kd) * p.n_chunks + c) * (static_cast<size_t>(p.k) * p.k * 16 * p.cout);
-            for (int g = 0; g < p.n_khg; ++g) {
-              const int kh0 = g * p.kh_s;
-              const int cnt = min(p.kh_s, p.k - kh0);
-              if (!mbar_wait(&empty_bar[stage], phase ^ 1, p.err_flag)) goto teardown;
+    // ===================================================================== TMA producer (warp-uniform loop)
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      int t = tile;
+      const int tw = t % p.tiles_w; t /= p.tiles_w;
+      const int th = t % p.tiles_h; t /= p.tiles_h;
+      const int d = t % p.D;
+      const int n = t / p.D;
+      const int h0 = th * 16, w0 = tw * 8;
+      for (int kdg = 0; kdg < p.n_kdg; ++kdg) {
+        const int kd0 = kdg * p.kd_s;
+        const int dz = d + kd0 * p.dil - p.pad;
+        if (p.kd_s == 1 && (dz < 0 || dz >= p.D)) continue;
+        for (int c = 0; c < p.n_chunks; ++c) {
+          const __half* wsrc = p.wpack + static_cast<size_t>(kd0) * kd_w_halfs + static_cast<size_t>(c) * chunk_w_halfs;
+          for (int g = 0; g < p.n_khg; ++g) {
+            const int kh0 = g * p.kh_s;
+            const int cnt = min(p.kh_s, KS - kh0);
+            if (!mbar_wait(&empty_bar[stage], phase ^ 1, p.err_flag)) goto teardown;
+            if (elect_one()) {
               uint8_t* sa = smem + static_cast<size_t>(stage) * p.stage_bytes;
               uint8_t* sb = sa + p.a_bytes_al;
-              const uint32_t b_bytes = static_cast<uint32_t>(cnt * p.k) * tap_b_bytes;
-              mbar_arrive_expect_tx(&full_bar[stage], p.a_bytes + b_bytes);
+              const uint32_t b_bytes = static_cast<uint32_t>(cnt * KS) * tap_b_bytes;
+              mbar_arrive_expect_tx(&full_bar[stage], p.a_bytes + b_bytes * p.kd_s);
               tma_load_5d(sa, &tmap_in, &full_bar[stage], 0, w0 - p.pad, h0 - p.pad + kh0 * p.dil, dz,
                           n * p.cb_total_in + p.chunk_cb[c]);
-              bulk_load_1d(sb, wsrc + static_cast<size_t>(kh0) * p.k * 16 * p.cout, b_bytes, &full_bar[stage]);
-              if (++stage == p.stages) { stage = 0; phase ^= 1; }
+              for (int kdl = 0; kdl < p.kd_s; ++kdl)
+                bulk_load_1d(sb + kdl * b_bytes, wsrc + kdl * kd_w_halfs + static_cast<size_t>(kh0) * KS * 16 * p.cout,
+                             b_bytes, &full_bar[stage]);
             }
+            __syncwarp();
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================================================================== MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_f16(128, p.cout);
-      const uint32_t a_lbo = static_cast<uint32_t>(p.PHs * p.PW) * 16u;
-      const uint32_t a_sbo = static_cast<uint32_t>(p.PW) * 16u;
-      const uint32_t b_lbo = static_cast<uint32_t>(p.cout) * 16u;
-      const uint32_t b_sbo = 128u;
-      int stage = 0;
-      uint32_t phase = 0;
-      int iter = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++iter) {
-        int t = tile / tiles_per_plane;
-        const int d = t % p.D;
-        const int slot = iter & 1;
-        if (!mbar_wait(&tmem_empty_bar[slot], ((iter >> 1) & 1) ^ 1, p.err_flag)) goto teardown;
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(slot * p.cout);
-        uint32_t accumulate = 0;
-        for (int kd = 0; kd < p.k; ++kd) {
-          const int dz = d + kd * p.dil - p.pad;
-          if (dz < 0 || dz >= p.D) continue;
-          for (int c = 0; c < p.n_chunks; ++c) {
-            for (int g = 0; g < p.n_khg; ++g) {
-              const int cnt = min(p.kh_s, p.k - g * p.kh_s);
-              if (!mbar_wait(&full_bar[stage], phase, p.err_flag)) goto teardown;
-              tc_fence_after();
-              const uint32_t sa = smem_u32(smem + static_cast<size_t>(stage) * p.stage_bytes);
-              const uint32_t sb = sa + p.a_bytes_al;
-              for (int khl = 0; khl < cnt; ++khl) {
-                for (int kw = 0; kw < p.k; ++kw) {
-                  const uint32_t a_addr = sa + static_cast<uint32_t>((khl * p.dil) * p.PW + kw * p.dil) * 16u;
-                  const uint32_t b_addr = sb + static_cast<uint32_t>(khl * p.k + kw) * tap_b_bytes;
-                  umma_f16_ss(tmem_d, make_smem_desc(a_addr, a_lbo, a_sbo, 0), make_smem_desc(b_addr, b_lbo, b_sbo, 0),
-                              idesc, accumulate);
-                  accumulate = 1;
+    // ===================================================================== MMA issuer (warp-uniform loop, one elected lane issues)
+    const uint32_t idesc = make_idesc_f16(128, p.cout);
+    // descriptor halves: lo = start>>4 | LBO>>4 << 16 ; hi = SBO>>4 | version(1) << 14 | layout(0) << 29
+    const uint32_t a_lo_c = (static_cast<uint32_t>(p.kd_s * p.PHs * p.PW) & 0x3FFFu) << 16;   // LBO = c8-block pitch
+    const uint32_t a_hi = (static_cast<uint32_t>(p.PW) & 0x3FFFu) | (1u << 14);               // SBO = patch row pitch
+    const uint32_t b_lo_c = (static_cast<uint32_t>(p.cout) & 0x3FFFu) << 16;                  // LBO = cout*16 B
+    const uint32_t b_hi = 8u | (1u << 14);                                                    // SBO = 128 B
+    const uint32_t tap_b16 = tap_b_bytes >> 4;
+    int stage = 0;
+    uint32_t phase = 0;
+    int iter = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++iter) {
+      const int d = (tile / tiles_per_plane) % p.D;
+      const int slot = iter & 1;
+      if (!mbar_wait(&tmem_empty_bar[slot], ((iter >> 1) & 1) ^ 1, p.err_flag)) goto teardown;
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(slot * p.cout);
+      uint32_t accumulate = 0;
+      for (int kdg = 0; kdg < p.n_kdg; ++kdg) {
+        const int dz = d + kdg * p.kd_s * p.dil - p.pad;
+        if (p.kd_s == 1 && (dz < 0 || dz >= p.D)) continue;
+        for (int c = 0; c < p.n_chunks; ++c) {
+          for (int g = 0; g < p.n_khg; ++g) {
+            const int cnt = min(p.kh_s, KS - g * p.kh_s);
+            if (!mbar_wait(&full_bar[stage], phase, p.err_flag)) goto teardown;
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t sa16 = smem_u32(smem + static_cast<size_t>(stage) * p.stage_bytes) >> 4;
+              uint32_t b16 = sa16 + (p.a_bytes_al >> 4);
+              for (int kdl = 0; kdl < p.kd_s; ++kdl) {
+                for (int khl = 0; khl < cnt; ++khl) {
+                  uint32_t a16 = sa16 + static_cast<uint32_t>((kdl * p.PHs + khl * p.dil) * p.PW);
+#pragma unroll
+                  for (int kw = 0; kw < KS; ++kw) {
+                    umma_f16_ss_split(tmem_d, a_lo_c | (a16 & 0x3FFFu), a_hi, b_lo_c | (b16 & 0x3FFFu), b_hi, idesc, accumulate);
+                    accumulate = 1;
+                    a16 += static_cast<uint32_t>(p.dil);
+                    b16 += tap_b16;
+                  }
                 }
               }
               umma_commit(&empty_bar[stage]);
-              if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
+            __syncwarp();
+            accumulate = 1;
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
         }
-        umma_commit(&tmem_full_bar[slot]);
       }
+      if (elect_one()) umma_commit(&tmem_full_bar[slot]);
+      __syncwarp();
     }
   } else {
     // ===================================================================== epilogue (warps 2..5)
@@ -183,6 +239,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
     const int ew = warp - 2;
     const int row = quarter * 32 + lane;
     const int hl = row >> 3, wl = row & 7;
+    const int mycol = (lane >> 1) & 15;
     int cur_n = -1;
     int iter = 0;
     auto flush_stats = [&](int n) {
@@ -196,6 +253,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
       }
       __syncwarp();
     };
+    const size_t plane = static_cast<size_t>(p.D) * p.H * p.W;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++iter) {
       int t = tile;
       const int tw = t % p.tiles_w; t /= p.tiles_w;
@@ -210,7 +268,6 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(slot * p.cout);
       const size_t vox = (static_cast<size_t>(d) * p.H + h) * p.W + w;
-      const size_t plane = static_cast<size_t>(p.D) * p.H * p.W;
       for (int c0 = 0; c0 < p.cout; c0 += 16) {
         uint32_t r[16];
         tmem_ld16(taddr + c0, r);
@@ -218,20 +275,19 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
         float v[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          float x = fmaf(__uint_as_float(r[j]), __ldg(&p.scale[c0 + j]), __ldg(&p.shift[c0 + j]));
+          float x = fmaf(__uint_as_float(r[j]), s_scale[c0 + j], s_shift[c0 + j]);
           if (p.relu) x = fmaxf(x, 0.f);
-          v[j] = x;
+          v[j] = valid ? x : 0.f;
         }
         if (p.stats != nullptr) {
+          float sq[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float s = valid ? v[j] : 0.f;
-            const float s1 = warp_sum(s);
-            const float s2 = warp_sum(s * s);
-            if (lane == 0) {
-              stat_acc[ew][c0 + j][0] += s1;
-              stat_acc[ew][c0 + j][1] += s2;
-            }
+          for (int j = 0; j < 16; ++j) sq[j] = v[j] * v[j];
+          const float s1 = colsum16(v, lane);
+          const float s2 = colsum16(sq, lane);
+          if ((lane & 1) == 0) {
+            stat_acc[ew][c0 + mycol][0] += s1;
+            stat_acc[ew][c0 + mycol][1] += s2;
           }
         }
         if (valid) {
@@ -295,19 +351,22 @@ extern "C" int dp_conv3d_tc(const void* in_c8, int cb_total_in, const uint8_t* c
   p.PW = 8 + (k - 1) * dil;
   // stage sizing: as many kh rows per stage as fit ~56 KB, then as many stages as fit ~200 KB
   const int tap_b = 32 * cout;
-  int kh_s = k;
-  auto stage_bytes_for = [&](int s) {
+  int kh_s = k, kd_s = (dil == 1) ? k : 1;
+  auto stage_bytes_for = [&](int sd, int s) {
     const int phs = 16 + (s - 1) * dil;
-    const int a = 2 * phs * p.PW * 16;
-    return ((a + 127) / 128) * 128 + s * k * tap_b;
+    const int a = 2 * sd * phs * p.PW * 16;
+    return ((a + 127) / 128) * 128 + sd * s * k * tap_b;
   };
-  while (kh_s > 1 && stage_bytes_for(kh_s) > 56 * 1024) --kh_s;
+  if (stage_bytes_for(kd_s, kh_s) > 64 * 1024) kd_s = 1;     // whole-depth stages only when they stay small
+  while (kh_s > 1 && stage_bytes_for(kd_s, kh_s) > 56 * 1024) --kh_s;
+  p.kd_s = kd_s;
+  p.n_kdg = k / kd_s;
   p.kh_s = kh_s;
   p.n_khg = (k + kh_s - 1) / kh_s;
   p.PHs = 16 + (kh_s - 1) * dil;
-  p.a_bytes = 2u * p.PHs * p.PW * 16u;
+  p.a_bytes = 2u * kd_s * p.PHs * p.PW * 16u;
   p.a_bytes_al = ((p.a_bytes + 127u) / 128u) * 128u;
-  p.stage_bytes = ((static_cast<uint32_t>(stage_bytes_for(kh_s)) + 1023u) / 1024u) * 1024u;
+  p.stage_bytes = ((static_cast<uint32_t>(stage_bytes_for(kd_s, kh_s)) + 1023u) / 1024u) * 1024u;
   int stages = static_cast<int>((200u * 1024u) / p.stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   DP_REQUIRE(stages >= 2, "dp_conv3d_tc: stage of %u bytes does not fit twice in shared memory", p.stage_bytes);
@@ -329,21 +388,30 @@ extern "C" int dp_conv3d_tc(const void* in_c8, int cb_total_in, const uint8_t* c
                             static_cast<uint64_t>(N) * cb_total_in};
   const uint64_t strides[4] = {16, static_cast<uint64_t>(W) * 16, static_cast<uint64_t>(H) * W * 16,
                                static_cast<uint64_t>(D) * H * W * 16};
-  const uint32_t box[5] = {8, static_cast<uint32_t>(p.PW), static_cast<uint32_t>(p.PHs), 1, 2};
+  const uint32_t box[5] = {8, static_cast<uint32_t>(p.PW), static_cast<uint32_t>(p.PHs), static_cast<uint32_t>(p.kd_s), 2};
   if (int rc = encode_tiled(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, in_c8, dims, strides, box,
                             CU_TENSOR_MAP_SWIZZLE_NONE))
     return rc;
 
   const size_t smem = static_cast<size_t>(p.stages) * p.stage_bytes + 1024;
-  static size_t configured = 0;
-  if (smem > configured) {
-    DP_CHECK(cudaFuncSetAttribute(conv3d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    configured = smem;
-  }
   int grid = sm_count();
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
   if (grid > p.num_tiles) grid = p.num_tiles;
-  conv3d_tc_kernel<<<grid, kConvThreads, smem, stream>>>(tmap, p);
+  static bool configured = false;
+  if (!configured) {
+    const int max_smem = 8 * 25 * 1024 + 1024 + 4096;
+    DP_CHECK(cudaFuncSetAttribute(conv3d_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    DP_CHECK(cudaFuncSetAttribute(conv3d_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    DP_CHECK(cudaFuncSetAttribute(conv3d_tc_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    DP_CHECK(cudaFuncSetAttribute(conv3d_tc_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    configured = true;
+  }
+  switch (k) {
+    case 1: conv3d_tc_kernel<1><<<grid, kConvThreads, smem, stream>>>(tmap, p); break;
+    case 3: conv3d_tc_kernel<3><<<grid, kConvThreads, smem, stream>>>(tmap, p); break;
+    case 5: conv3d_tc_kernel<5><<<grid, kConvThreads, smem, stream>>>(tmap, p); break;
+    default: conv3d_tc_kernel<7><<<grid, kConvThreads, smem, stream>>>(tmap, p); break;
+  }
   DP_CHECK(cudaGetLastError());
   return 0;
 }

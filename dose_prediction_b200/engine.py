@@ -180,6 +180,36 @@ class Plan:
     def count_flops(self, name, flops):
         self.flops[name] = self.flops.get(name, 0.0) + float(flops)
 
+    def profile_launches(self):
+        """per-launch device time (CUDA events): list of (family, label, ms) in schedule order."""
+        stream = torch.cuda.current_stream(self.device)
+        s = stream.cuda_stream
+        if self.stats_used:
+            self.stats[:self.stats_used].zero_()
+        evs = []
+        for fn, args, name in self.steps:
+            if fn is None:
+                args[0].zero_()
+                continue
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            rc = fn(*args, s)
+            e1.record(stream)
+            if rc:
+                _lib.check(rc, name)
+            label = ""
+            if name == "dp_conv3d_tc":
+                label = f"N{args[5]} {args[6]}x{args[7]}x{args[8]} cout{args[9]} k{args[10]} dil{args[11]} chunks{args[3]}"
+            elif name == "dp_gemm_tc":
+                label = f"M{args[2]} N{args[3]} K{args[4]} batch{args[5]} split{args[12]}"
+            elif name == "dp_conv3d_direct":
+                label = f"cin{args[4]} N{args[5]} {args[6]}x{args[7]}x{args[8]} k{args[9]} s{args[10]} cout{args[16]}"
+            elif name == "dp_deconv2x":
+                label = f"cin{args[5]} cout{args[6]} N{args[7]} {args[8]}x{args[9]}x{args[10]}"
+            evs.append((name, label, e0, e1))
+        torch.cuda.synchronize(self.device)
+        return [(n, l, e0.elapsed_time(e1)) for n, l, e0, e1 in evs]
+
     def profile_families(self, repeats=1):
         """device time per kernel family: eager replay with a CUDA-event pair around every launch on the
         launch stream; returns {family: {"ms": per-replay total, "launches": n}}."""
