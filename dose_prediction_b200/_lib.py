@@ -18,6 +18,7 @@ F = c_float
 
 _SIGNATURES = {
     "dp_conv3d_tc": [P, I, P, I, P, I, I, I, I, I, I, I, P, P, I, P, P, P, I, I, P, P, I, P],
+    "dp_conv3d_stack": [P, I, P, I, P, I, I, I, I, I, I, P, P, I, P, P, P, I, I, P, P, I, I, P],
     "dp_conv3d_direct": [P, P, I, I, I, I, I, I, I, I, I, I, P, P, P, I, I, P, P, P, I, I, P, P],
     "dp_gemm_tc": [P, P, I, I, I, I, I, I, L, I, L, I, I, P, P, I, P, F, I, P, I, P, I, I, I, I, P, P, P, F, P, P],
     "dp_pack_ncdhw": [P, I, I, L, P, P, I, I, P],
@@ -25,6 +26,7 @@ _SIGNATURES = {
     "dp_norm_act": [P, P, P, I, I, P, P, P, I, P, P, P, P, I, I, I, P, P, I, I, P, I, I, L, P],
     "dp_pointwise_conv": [I, P, P, P, P, P, P, P, P, P, P, I, I, L, P, P, P, I, I, P, P, I, P],
     "dp_deconv2x": [P, P, L, L, L, I, I, I, I, I, I, P, P, P, I, I, P],
+    "dp_deconv2x_gemm": [P, P, I, I, I, I, I, I, P, P, I, I, P, P],
     "dp_upsample2x": [P, P, I, I, I, I, I, I, I, P, P, I, I, P],
     "dp_layernorm": [P, P, P, I, I, P, P, P],
     "dp_softmax": [P, I, I, I, P, I, P],

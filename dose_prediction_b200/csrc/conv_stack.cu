@@ -1,0 +1,478 @@
+// Depth-stacked implicit-GEMM 3-D convolution for small C_out (16 / 32) on tcgen05 tensor cores.
+//
+// Why: with N = C_out = 16 a plain implicit GEMM issues one 128x16x16 MMA per tap and re-reads its 4 KB A
+// operand from shared memory every time — ncu shows the tensor core's shared-memory read pipe at 61 % and
+// the tensor pipe at 13 % (profiles/r1_conv_k7_plain.md).  Here the k taps along D are stacked into the
+// N dimension instead: for one INPUT plane, one in-plane tap (kh,kw) and one 16-channel chunk, a single
+// MMA with B = [W(kd=k-1) | ... | W(kd=0)]  (N = k*C_out = 112 / 224 for 7^3) updates the accumulators of
+// the k OUTPUT planes that input plane contributes to.  The accumulators of consecutive output planes
+// live in a ring of G column groups in TMEM; the window of k planes slides by one group per input plane,
+// so B never has to be rotated.  A is read once per k taps: 4.2x fewer shared-memory wavefronts.
+//
+// A CTA owns T adjacent 16(H) x 8(W) tiles (one wide TMA halo patch, B shared by the T tiles) and marches
+// along a segment of L output planes; work items = (image, D segment, H tile, W tile group), persistent.
+// Ring bookkeeping: every output plane gets a running counter pc; slot = pc % G, parity = (pc / G) & 1.
+//   done_bar[slot]  MMA  -> epilogue   (tcgen05.commit after the last input plane contributing to it)
+//   free_bar[slot]  epilogue -> MMA    (4 epilogue warps have drained it; next owner may start with acc=0)
+// The first MMA that touches a new plane uses accumulate=0 on that plane's group only (the window is
+// split into an old and a new part for that one tap), so TMEM never needs zeroing.
+#include "common.cuh"
+#include "dose_b200.h"
+
+namespace dp {
+
+struct StackParams {
+  int N, D, H, W;
+  int n_chunks, cb_total_in;
+  int cout;                 // N0
+  int T, G, L;              // tiles per CTA, ring slots, segment length
+  int khs, n_khg;           // kh rows per B stage
+  int PH, PWw;
+  int a_stages, b_stages;
+  uint32_t a_bytes, a_stride, b_bytes, b_stride, b_off;
+  int tiles_h, wgroups, nseg, num_items, tiles_w;
+  const __half* wpack;      // [chunk][kh][kw][2][k*cout][8]
+  const float* scale;
+  const float* shift;
+  int relu;
+  float* out_f32;
+  __half* out_hi;
+  __half* out_lo;
+  int cb_total_out, cb_out_off;
+  double* stats;
+  int* err_flag;
+  uint8_t chunk_cb[96];
+};
+
+constexpr int kStackThreads = 192;
+constexpr int kMaxAStages = 4, kMaxBStages = 6, kMaxSlots = 32;
+
+__device__ __forceinline__ void umma_split(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                           uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ float colsum16s(const float (&v)[16], int lane) {
+  float a[8], b[4], c[2];
+  const bool h4 = lane & 16, h3 = lane & 8, h2 = lane & 4, h1 = lane & 2;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float keep = h4 ? v[j + 8] : v[j], send = h4 ? v[j] : v[j + 8];
+    a[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float keep = h3 ? a[j + 4] : a[j], send = h3 ? a[j] : a[j + 4];
+    b[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const float keep = h2 ? b[j + 2] : b[j], send = h2 ? b[j] : b[j + 2];
+    c[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  const float keep = h1 ? c[1] : c[0], send = h1 ? c[0] : c[1];
+  float r = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  r += __shfl_xor_sync(0xffffffffu, r, 1);
+  return r;
+}
+
+struct Item {
+  int n, d0, d1, z0, z1, h0, w0, ntile;
+};
+
+template <int KS>
+__device__ __forceinline__ Item decode_item(const StackParams& p, int item) {
+  constexpr int pad = (KS - 1) / 2;
+  Item it;
+  int t = item;
+  const int wg = t % p.wgroups; t /= p.wgroups;
+  const int th = t % p.tiles_h; t /= p.tiles_h;
+  const int sg = t % p.nseg;
+  it.n = t / p.nseg;
+  it.d0 = sg * p.L;
+  it.d1 = min(p.D, it.d0 + p.L);
+  it.z0 = max(0, it.d0 - pad);
+  it.z1 = min(p.D - 1, it.d1 - 1 + pad);
+  it.h0 = th * 16;
+  it.w0 = wg * p.T * 8;
+  it.ntile = min(p.T, p.tiles_w - wg * p.T);
+  return it;
+}
+
+template <int KS>
+__global__ void __launch_bounds__(kStackThreads, 1)
+conv3d_stack_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ StackParams p) {
+  constexpr int pad = (KS - 1) / 2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  __shared__ uint64_t a_full[kMaxAStages], a_empty[kMaxAStages];
+  __shared__ uint64_t b_full[kMaxBStages], b_empty[kMaxBStages];
+  __shared__ uint64_t done_bar[kMaxSlots], free_bar[kMaxSlots];
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ float stat_acc[4][32][2];
+  __shared__ float s_scale[32], s_shift[32];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int N0 = p.cout;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_in);
+    for (int i = 0; i < p.a_stages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < p.b_stages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < p.G; ++i) { mbar_init(&done_bar[i], 1); mbar_init(&free_bar[i], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(&tmem_base_smem);
+  for (int i = threadIdx.x; i < 4 * 32 * 2; i += kStackThreads) (&stat_acc[0][0][0])[i] = 0.f;
+  for (int i = threadIdx.x; i < N0; i += kStackThreads) { s_scale[i] = p.scale[i]; s_shift[i] = p.shift[i]; }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  const uint32_t tap_b_bytes = 32u * KS * N0;            // one tap: [2][KS*N0][8] fp16
+  const size_t chunk_w_halfs = static_cast<size_t>(KS) * KS * 16 * KS * N0;
+
+  if (warp == 0) {
+    // ===================================================================== producer
+    int ia = 0, ib = 0;
+    uint32_t pa = 0, pb = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      const Item it = decode_item<KS>(p, item);
+      for (int dz = it.z0; dz <= it.z1; ++dz) {
+        for (int c = 0; c < p.n_chunks; ++c) {
+          if (!mbar_wait(&a_empty[ia], pa ^ 1, p.err_flag)) goto teardown;
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&a_full[ia], p.a_bytes);
+            tma_load_5d(smem + static_cast<size_t>(ia) * p.a_stride, &tmap_in, &a_full[ia], 0, it.w0 - pad, it.h0 - pad, dz,
+                        it.n * p.cb_total_in + p.chunk_cb[c]);
+          }
+          __syncwarp();
+          if (++ia == p.a_stages) { ia = 0; pa ^= 1; }
+          for (int g = 0; g < p.n_khg; ++g) {
+            const int kh0 = g * p.khs;
+            const int cnt = min(p.khs, KS - kh0);
+            if (!mbar_wait(&b_empty[ib], pb ^ 1, p.err_flag)) goto teardown;
+            if (elect_one()) {
+              const uint32_t bytes = static_cast<uint32_t>(cnt * KS) * tap_b_bytes;
+              mbar_arrive_expect_tx(&b_full[ib], bytes);
+              bulk_load_1d(smem + p.b_off + static_cast<size_t>(ib) * p.b_stride,
+                           p.wpack + static_cast<size_t>(c) * chunk_w_halfs + static_cast<size_t>(kh0) * KS * (tap_b_bytes / 2),
+                           bytes, &b_full[ib]);
+            }
+            __syncwarp();
+            if (++ib == p.b_stages) { ib = 0; pb ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    const uint32_t idesc0 = make_idesc_f16(128, 0);
+    const uint32_t a_lo_c = (static_cast<uint32_t>(p.PH * p.PWw) & 0x3FFFu) << 16;   // LBO: c8-block pitch
+    const uint32_t a_hi = (static_cast<uint32_t>(p.PWw) & 0x3FFFu) | (1u << 14);     // SBO: patch row pitch
+    const uint32_t b_lo_c = (static_cast<uint32_t>(KS * N0) & 0x3FFFu) << 16;        // LBO: k-half pitch = rows*16 B
+    const uint32_t b_hi = 8u | (1u << 14);                                           // SBO: 128 B
+    const uint32_t tap_b16 = tap_b_bytes >> 4;
+    const int G = p.G;
+    const uint32_t gmask = static_cast<uint32_t>(G - 1);
+    const uint32_t gshift = static_cast<uint32_t>(__ffs(G) - 1);
+    int ia = 0, ib = 0;
+    uint32_t pa = 0, pb = 0;
+    uint32_t pc_base = 0;                      // running plane counter of this item's plane d0
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      const Item it = decode_item<KS>(p, item);
+      for (int dz = it.z0; dz <= it.z1; ++dz) {
+        // output planes fed by this input plane, oldest first
+        const int p_lo = max(dz - pad, it.d0), p_hi = min(dz + pad, it.d1 - 1);
+        const int nw = p_hi - p_lo + 1;
+        const int j0 = p_lo - (dz - pad);                       // B group of p_lo: kd = KS-1-j
+        const int n_new = (dz == it.z0) ? nw : ((dz + pad <= it.d1 - 1) ? 1 : 0);
+        const int n_old = nw - n_new;
+        const uint32_t pc_lo = pc_base + static_cast<uint32_t>(p_lo - it.d0);
+        const int slot_lo = static_cast<int>(pc_lo & gmask);
+        // new planes: their ring slot must have been drained by the epilogue
+        for (int i = n_old; i < nw; ++i) {
+          const uint32_t pc = pc_lo + i;
+          if (!mbar_wait(&free_bar[pc & gmask], ((pc >> gshift) & 1) ^ 1, p.err_flag)) goto teardown;
+        }
+        tc_fence_after();
+        // MMA pieces: contiguous runs of ring slots with one accumulate flag.  Regular taps: the window split
+        // at the ring wrap (<= 2 pieces).  The first tap of this input plane additionally splits old | new.
+        uint32_t pc_d[2], pc_b[2], pc_i[2];      // regular: TMEM column offset, B row offset (16 B units), idesc
+        int npc = 0;
+        uint32_t fp_d[4], fp_b[4], fp_i[4], fp_acc[4];
+        int nfp = 0;
+        {
+          int i0 = 0;
+          while (i0 < nw) {
+            const int s = (slot_lo + i0) & static_cast<int>(gmask);
+            const int len = min(nw - i0, G - s);
+            pc_d[npc] = static_cast<uint32_t>(s * N0);
+            pc_b[npc] = static_cast<uint32_t>((j0 + i0) * N0);
+            pc_i[npc] = idesc0 | (static_cast<uint32_t>((len * N0) >> 3) << 17);
+            ++npc;
+            i0 += len;
+          }
+          for (int r = 0; r < 2; ++r) {
+            int a0 = r == 0 ? 0 : n_old;
+            const int a1 = r == 0 ? n_old : nw;
+            while (a0 < a1) {
+              const int s = (slot_lo + a0) & static_cast<int>(gmask);
+              const int len = min(a1 - a0, G - s);
+              fp_d[nfp] = static_cast<uint32_t>(s * N0);
+              fp_b[nfp] = static_cast<uint32_t>((j0 + a0) * N0);
+              fp_i[nfp] = idesc0 | (static_cast<uint32_t>((len * N0) >> 3) << 17);
+              fp_acc[nfp] = r == 0 ? 1u : 0u;
+              ++nfp;
+              a0 += len;
+            }
+          }
+        }
+        bool first_tap = true;
+        for (int c = 0; c < p.n_chunks; ++c) {
+          if (!mbar_wait(&a_full[ia], pa, p.err_flag)) goto teardown;
+          const uint32_t sa16 = smem_u32(smem + static_cast<size_t>(ia) * p.a_stride) >> 4;
+          for (int g = 0; g < p.n_khg; ++g) {
+            const int kh0 = g * p.khs;
+            const int cnt = min(p.khs, KS - kh0);
+            if (!mbar_wait(&b_full[ib], pb, p.err_flag)) goto teardown;
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t sb16 = smem_u32(smem + p.b_off + static_cast<size_t>(ib) * p.b_stride) >> 4;
+              for (int khl = 0; khl < cnt; ++khl) {
+                uint32_t a_tap = sa16 + static_cast<uint32_t>((kh0 + khl) * p.PWw);
+                uint32_t b_tap = sb16 + static_cast<uint32_t>(khl * KS) * tap_b16;
+#pragma unroll
+                for (int kw = 0; kw < KS; ++kw) {
+                  if (first_tap) {
+                    for (int q = 0; q < nfp; ++q)
+                      for (int t = 0; t < it.ntile; ++t)
+                        umma_split(tmem_base + static_cast<uint32_t>(t * G * N0) + fp_d[q], a_lo_c | ((a_tap + t * 8) & 0x3FFFu), a_hi,
+                                   b_lo_c | ((b_tap + fp_b[q]) & 0x3FFFu), b_hi, fp_i[q], fp_acc[q]);
+                    first_tap = false;
+                  } else {
+                    for (int q = 0; q < npc; ++q)
+                      for (int t = 0; t < it.ntile; ++t)
+                        umma_split(tmem_base + static_cast<uint32_t>(t * G * N0) + pc_d[q], a_lo_c | ((a_tap + t * 8) & 0x3FFFu), a_hi,
+                                   b_lo_c | ((b_tap + pc_b[q]) & 0x3FFFu), b_hi, pc_i[q], 1u);
+                  }
+                  a_tap += 1;
+                  b_tap += tap_b16;
+                }
+              }
+              umma_commit(&b_empty[ib]);
+            }
+            __syncwarp();
+            first_tap = false;
+            if (++ib == p.b_stages) { ib = 0; pb ^= 1; }
+          }
+          if (elect_one()) umma_commit(&a_empty[ia]);
+          __syncwarp();
+          if (++ia == p.a_stages) { ia = 0; pa ^= 1; }
+        }
+        // planes completed by this input plane
+        if (elect_one()) {
+          if (dz < it.z1) {
+            const int pdone = dz - pad;
+            if (pdone >= it.d0) umma_commit(&done_bar[(pc_base + static_cast<uint32_t>(pdone - it.d0)) & gmask]);
+          } else {
+            for (int q = max(it.d0, it.z1 - pad); q < it.d1; ++q)
+              umma_commit(&done_bar[(pc_base + static_cast<uint32_t>(q - it.d0)) & gmask]);
+          }
+        }
+        __syncwarp();
+      }
+      pc_base += static_cast<uint32_t>(it.d1 - it.d0);
+    }
+  } else {
+    // ===================================================================== epilogue (warps 2..5)
+    const int quarter = warp & 3;
+    const int ew = warp - 2;
+    const int row = quarter * 32 + lane;
+    const int hl = row >> 3, wl = row & 7;
+    const int mycol = (lane >> 1) & 15;
+    const int G = p.G;
+    int cur_n = -1;
+    uint32_t pc = 0;
+    auto flush_stats = [&](int n) {
+      if (p.stats == nullptr || n < 0) return;
+      __syncwarp();
+      for (int c = lane; c < N0; c += 32) {
+        atomicAdd(&p.stats[(static_cast<size_t>(n) * N0 + c) * 2 + 0], static_cast<double>(stat_acc[ew][c][0]));
+        atomicAdd(&p.stats[(static_cast<size_t>(n) * N0 + c) * 2 + 1], static_cast<double>(stat_acc[ew][c][1]));
+        stat_acc[ew][c][0] = 0.f;
+        stat_acc[ew][c][1] = 0.f;
+      }
+      __syncwarp();
+    };
+    const size_t plane = static_cast<size_t>(p.D) * p.H * p.W;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      const Item it = decode_item<KS>(p, item);
+      if (it.n != cur_n) { flush_stats(cur_n); cur_n = it.n; }
+      const int h = it.h0 + hl;
+      for (int d = it.d0; d < it.d1; ++d, ++pc) {
+        const int slot = static_cast<int>(pc & static_cast<uint32_t>(G - 1));
+        if (!mbar_wait(&done_bar[slot], (pc >> (__ffs(G) - 1)) & 1, p.err_flag)) goto teardown;
+        tc_fence_after();
+        for (int t = 0; t < it.ntile; ++t) {
+          const int w = it.w0 + t * 8 + wl;
+          const bool valid = (h < p.H) && (w < p.W);
+          const size_t vox = (static_cast<size_t>(d) * p.H + h) * p.W + w;
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>((t * G + slot) * N0);
+          for (int c0 = 0; c0 < N0; c0 += 16) {
+            uint32_t r[16];
+            tmem_ld16(taddr + c0, r);
+            tmem_ld_wait();
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float x = fmaf(__uint_as_float(r[j]), s_scale[c0 + j], s_shift[c0 + j]);
+              if (p.relu) x = fmaxf(x, 0.f);
+              v[j] = valid ? x : 0.f;
+            }
+            if (p.stats != nullptr) {
+              float sq[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) sq[j] = v[j] * v[j];
+              const float s1 = colsum16s(v, lane);
+              const float s2 = colsum16s(sq, lane);
+              if ((lane & 1) == 0) {
+                stat_acc[ew][c0 + mycol][0] += s1;
+                stat_acc[ew][c0 + mycol][1] += s2;
+              }
+            }
+            if (valid) {
+#pragma unroll
+              for (int b = 0; b < 2; ++b) {
+                const size_t cb = static_cast<size_t>(it.n) * p.cb_total_out + p.cb_out_off + (c0 >> 3) + b;
+                const size_t off = (cb * plane + vox) * 8;
+                if (p.out_f32 != nullptr) {
+                  float4* o = reinterpret_cast<float4*>(p.out_f32 + off);
+                  o[0] = make_float4(v[b * 8 + 0], v[b * 8 + 1], v[b * 8 + 2], v[b * 8 + 3]);
+                  o[1] = make_float4(v[b * 8 + 4], v[b * 8 + 5], v[b * 8 + 6], v[b * 8 + 7]);
+                }
+                if (p.out_hi != nullptr) {
+                  __align__(16) __half hi[8];
+                  __align__(16) __half lo[8];
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) {
+                    hi[j] = __float2half_rn(v[b * 8 + j]);
+                    lo[j] = __float2half_rn(v[b * 8 + j] - __half2float(hi[j]));
+                  }
+                  *reinterpret_cast<uint4*>(p.out_hi + off) = *reinterpret_cast<const uint4*>(hi);
+                  if (p.out_lo != nullptr) *reinterpret_cast<uint4*>(p.out_lo + off) = *reinterpret_cast<const uint4*>(lo);
+                }
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&free_bar[slot]);
+      }
+    }
+    flush_stats(cur_n);
+  }
+
+teardown:
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace dp
+
+extern "C" int dp_conv3d_stack(const void* in_c8, int cb_total_in, const uint8_t* chunk_cb, int n_chunks,
+                               const void* wpack_stack, int N, int D, int H, int W, int cout, int k,
+                               const float* scale, const float* shift, int relu, float* out_f32, void* out_hi,
+                               void* out_lo, int cb_total_out, int cb_out_off, double* stats, int* err_flag,
+                               int seg_len, int tiles_per_cta, cudaStream_t stream) {
+  using namespace dp;
+  DP_REQUIRE(k == 3 || k == 7, "dp_conv3d_stack: kernel size %d unsupported (3 or 7)", k);
+  DP_REQUIRE((cout == 16 || cout == 32) && k * cout <= 256, "dp_conv3d_stack: C_out=%d unsupported (16 or 32)", cout);
+  DP_REQUIRE(n_chunks >= 1 && n_chunks <= 96, "dp_conv3d_stack: n_chunks=%d out of range", n_chunks);
+  DP_REQUIRE(out_f32 != nullptr || out_hi != nullptr, "dp_conv3d_stack: no output tensor given");
+  StackParams p{};
+  p.N = N; p.D = D; p.H = H; p.W = W; p.n_chunks = n_chunks; p.cb_total_in = cb_total_in; p.cout = cout;
+  for (int i = 0; i < n_chunks; ++i) p.chunk_cb[i] = chunk_cb[i];
+  p.tiles_h = (H + 15) / 16;
+  p.tiles_w = (W + 7) / 8;
+  // tiles per CTA: share B between as many W tiles as TMEM allows while keeping a ring of >= k+1 slots
+  int T = tiles_per_cta > 0 ? tiles_per_cta : (k == 7 ? 2 : 4);
+  while (T > 1 && (512 / (T * cout)) < k + 1) T >>= 1;
+  if (T > p.tiles_w) T = p.tiles_w;
+  if (T < 1) T = 1;
+  int G = 4;                                     // ring slots: largest power of two that fits TMEM
+  while (G * 2 <= kMaxSlots && G * 2 * T * cout <= 512) G *= 2;
+  p.T = T; p.G = G;
+  DP_REQUIRE(G >= k + 1, "dp_conv3d_stack: TMEM ring too small (G=%d)", G);
+  p.wgroups = (p.tiles_w + T - 1) / T;
+  // segment length: enough work items to balance the SMs, but long segments amortise the (k-1)-plane halo
+  const int sms = sm_count();
+  int L = seg_len > 0 ? seg_len : D;
+  if (seg_len <= 0) {
+    const long long cols = static_cast<long long>(N) * p.tiles_h * p.wgroups;
+    long long nseg = (4LL * sms + cols - 1) / cols;
+    if (nseg < 1) nseg = 1;
+    L = static_cast<int>((D + nseg - 1) / nseg);
+    if (L < 8) L = 8;
+    if (L > D) L = D;
+  }
+  p.L = L;
+  p.nseg = (D + L - 1) / L;
+  p.num_items = N * p.nseg * p.tiles_h * p.wgroups;
+  p.PH = 16 + k - 1;
+  p.PWw = 8 * T + k - 1;
+  p.a_bytes = 2u * p.PH * p.PWw * 16u;
+  p.a_stride = ((p.a_bytes + 1023u) / 1024u) * 1024u;
+  const uint32_t tap_b = 32u * k * cout;
+  p.khs = (k == 3) ? 3 : 1;
+  p.n_khg = (k + p.khs - 1) / p.khs;
+  p.b_bytes = static_cast<uint32_t>(p.khs * k) * tap_b;
+  p.b_stride = ((p.b_bytes + 1023u) / 1024u) * 1024u;
+  p.a_stages = 3;
+  p.b_off = p.a_stages * p.a_stride;
+  int bs = static_cast<int>((205u * 1024u - p.b_off) / p.b_stride);
+  if (bs > kMaxBStages) bs = kMaxBStages;
+  DP_REQUIRE(bs >= 2, "dp_conv3d_stack: weight stage of %u bytes does not fit twice", p.b_stride);
+  p.b_stages = bs;
+  p.wpack = static_cast<const __half*>(wpack_stack);
+  p.scale = scale; p.shift = shift; p.relu = relu;
+  p.out_f32 = out_f32; p.out_hi = static_cast<__half*>(out_hi); p.out_lo = static_cast<__half*>(out_lo);
+  p.cb_total_out = cb_total_out; p.cb_out_off = cb_out_off; p.stats = stats; p.err_flag = err_flag;
+
+  CUtensorMap tmap;
+  const uint64_t dims[5] = {8, static_cast<uint64_t>(W), static_cast<uint64_t>(H), static_cast<uint64_t>(D),
+                            static_cast<uint64_t>(N) * cb_total_in};
+  const uint64_t strides[4] = {16, static_cast<uint64_t>(W) * 16, static_cast<uint64_t>(H) * W * 16,
+                               static_cast<uint64_t>(D) * H * W * 16};
+  const uint32_t box[5] = {8, static_cast<uint32_t>(p.PWw), static_cast<uint32_t>(p.PH), 1, 2};
+  if (int rc = encode_tiled(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, in_c8, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE))
+    return rc;
+
+  const size_t smem = static_cast<size_t>(p.b_off) + static_cast<size_t>(p.b_stages) * p.b_stride + 1024;
+  static bool configured = false;
+  if (!configured) {
+    const int max_smem = 212 * 1024;
+    DP_CHECK(cudaFuncSetAttribute(conv3d_stack_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    DP_CHECK(cudaFuncSetAttribute(conv3d_stack_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    configured = true;
+  }
+  int grid = sms < p.num_items ? sms : p.num_items;
+  if (k == 3) conv3d_stack_kernel<3><<<grid, kStackThreads, smem, stream>>>(tmap, p);
+  else conv3d_stack_kernel<7><<<grid, kStackThreads, smem, stream>>>(tmap, p);
+  DP_CHECK(cudaGetLastError());
+  return 0;
+}

@@ -1,14 +1,17 @@
 // C[M,N] = A[M,K] * B[N,K]^T on tcgen05 tensor cores (fp16 operands, fp32 accumulation in TMEM).
 //
 // Used for every nn.Linear on the hot path (monai PatchEmbeddingBlock "perceptron" Linear, SABlock
-// qkv/out_proj, MLPBlock linear1/linear2) and for the two attention contractions
-// (einsum "blxd,blyd->blxy" and "bhxy,bhyd->bhxd" in monai SABlock.forward).
+// qkv/out_proj, MLPBlock linear1/linear2), for the two attention contractions (einsum "blxd,blyd->blxy"
+// and "bhxy,bhyd->bhxd" in monai SABlock.forward) and for the 2x transposed convolutions that read ViT
+// tokens (deconv = GEMM [voxels, C_in] x [C_in, 8*C_out] with a pixel-shuffle scatter epilogue).
 //
-// Tiles: 128 x 128 x 64, TMA 2-D boxes with 128-byte swizzle, 6-stage mbarrier ring.
+// Persistent: grid = min(#tiles, #SMs); every CTA walks tiles blockIdx.x + i*gridDim.x.  Tiles are
+// 128 x 128 x 64 (TMA 2-D boxes, 128-byte swizzle, 6-stage mbarrier ring that runs ahead across tiles);
+// two 128-column TMEM accumulators so the epilogue of tile i overlaps the main loop of tile i+1.
 // Warp roles (192 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2..5 epilogue.
-// grid = (tiles_n, tiles_m, batch * split_k).  Epilogue options: +bias[n], +rowvec[m % period][n]
-// (position embeddings), GELU(erf), *alpha, +residual (fp32, may alias out_f32), fp32 store or
-// atomicAdd (split-K), fp16 copy, or the q/k/v^T head scatter.
+// Epilogue options: +bias[n], +rowvec[m % period][n] (position embeddings), GELU(erf), *alpha,
+// +residual (fp32, may alias out_f32), fp32 / fp16 stores, deterministic split-K partials, the
+// q/k/v^T head scatter, or the deconv scatter into a c8 tensor.
 #include "common.cuh"
 #include "dose_b200.h"
 
@@ -16,8 +19,9 @@ namespace dp {
 
 struct GemmParams {
   int M, N, K;
-  int batch, split_k, kb_per_split;
-  long long split_stride;              // split-K: partial sums of split s go to out_f32 + s*split_stride (deterministic)
+  int batch, split_k, kb_per_split, total_kb;
+  int tiles_m, tiles_n, num_tiles;
+  long long split_stride;              // split-K: partial sums of split s go to out_f32 + s*split_stride
   int a_batch_rows, b_batch_rows;      // row offset per batch entry inside the A / B tensor maps
   long long c_batch_stride;            // element offset per batch entry in the outputs ...
   int c_batch_period; long long c_batch_stride2;   // ... or (z / period) * stride + (z % period) * stride2
@@ -27,11 +31,14 @@ struct GemmParams {
   const float* resid;
   float alpha;
   int act;
-  float* out_f32; int atomic;
+  float* out_f32;
   __half* out_f16;
-  // qkv scatter (mode_qkv): N = 3*heads*hd, tokens per image T
-  int mode_qkv, heads, hd, T;
+  // qkv scatter (mode 1): N = 3*heads*hd, tokens per image T
+  int mode, heads, hd, T;
   __half* q; __half* kk; __half* vt; float q_scale;
+  // deconv scatter (mode 2): rows = (b, d, h, w) of a [Dg,Hg,Wg] grid, cols = parity*cout + co
+  int Dg, Hg, Wg, cout;
+  __half* dc_hi; __half* dc_lo; int dc_cb_total, dc_cb_off;
   int* err_flag;
 };
 
@@ -40,43 +47,20 @@ constexpr int BM = 128, BN = 128, BK = 64;
 constexpr int kGemmStages = 6;
 constexpr uint32_t kStageA = BM * BK * 2, kStageB = BN * BK * 2, kStage = kStageA + kStageB;
 
-__device__ __forceinline__ void gemm_producer(const CUtensorMap* ta, const CUtensorMap* tb, const GemmParams& p,
-                                              uint8_t* smem, uint64_t* full_bar, uint64_t* empty_bar, int m0, int n0,
-                                              int a_row0, int b_row0, int kb0, int kb1) {
-  int stage = 0;
-  uint32_t phase = 0;
-  for (int kb = kb0; kb < kb1; ++kb) {
-    if (!mbar_wait(&empty_bar[stage], phase ^ 1, p.err_flag)) return;
-    uint8_t* sa = smem + static_cast<size_t>(stage) * kStage;
-    mbar_arrive_expect_tx(&full_bar[stage], kStage);
-    tma_load_2d(sa, ta, &full_bar[stage], kb * BK, a_row0 + m0);
-    tma_load_2d(sa + kStageA, tb, &full_bar[stage], kb * BK, b_row0 + n0);
-    if (++stage == kGemmStages) { stage = 0; phase ^= 1; }
-  }
-}
-
-__device__ __forceinline__ void gemm_mma(const GemmParams& p, uint8_t* smem, uint64_t* full_bar, uint64_t* empty_bar,
-                                         uint64_t* acc_bar, uint32_t tmem_d, int kb0, int kb1) {
-  const uint32_t idesc = make_idesc_f16(BM, BN);
-  int stage = 0;
-  uint32_t phase = 0;
-  uint32_t accumulate = 0;
-  for (int kb = kb0; kb < kb1; ++kb) {
-    if (!mbar_wait(&full_bar[stage], phase, p.err_flag)) return;
-    tc_fence_after();
-    const uint32_t sa = smem_u32(smem + static_cast<size_t>(stage) * kStage);
-    const uint32_t sb = sa + kStageA;
-#pragma unroll
-    for (int k = 0; k < BK / 16; ++k) {
-      // 128B-swizzled K-major tile: 8-row atoms of 1024 B (SBO), advance 32 B per 16-element K step
-      umma_f16_ss(tmem_d, make_smem_desc(sa + k * 32, 16, 1024, 2), make_smem_desc(sb + k * 32, 16, 1024, 2), idesc,
-                  accumulate);
-      accumulate = 1;
-    }
-    umma_commit(&empty_bar[stage]);
-    if (++stage == kGemmStages) { stage = 0; phase ^= 1; }
-  }
-  umma_commit(acc_bar);
+struct GemmTile {
+  int m0, n0, bz, sk, kb0, kb1;
+};
+__device__ __forceinline__ GemmTile gemm_tile(const GemmParams& p, int tile) {
+  GemmTile t;
+  const int tn = tile % p.tiles_n; tile /= p.tiles_n;
+  const int tm = tile % p.tiles_m; tile /= p.tiles_m;
+  t.sk = tile % p.split_k;
+  t.bz = tile / p.split_k;
+  t.m0 = tm * BM;
+  t.n0 = tn * BN;
+  t.kb0 = t.sk * p.kb_per_split;
+  t.kb1 = min(p.total_kb, t.kb0 + p.kb_per_split);
+  return t;
 }
 
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -85,167 +69,246 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[kGemmStages];
   __shared__ uint64_t empty_bar[kGemmStages];
-  __shared__ uint64_t acc_bar;
+  __shared__ uint64_t acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_smem;
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
-  const int z = blockIdx.z;
-  const int bz = z / p.split_k, sk = z % p.split_k;
-  const int total_kb = (p.K + BK - 1) / BK;
-  const int kb0 = sk * p.kb_per_split;
-  const int kb1 = min(total_kb, kb0 + p.kb_per_split);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
     for (int i = 0; i < kGemmStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    mbar_init(&acc_bar, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<BN>(&tmem_base_smem);
+  if (warp == 1) tmem_alloc<2 * BN>(&tmem_base_smem);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
 
-  if (kb0 < kb1) {
-    if (warp == 0) {
-      if (lane == 0)
-        gemm_producer(&tmap_a, &tmap_b, p, smem, full_bar, empty_bar, m0, n0, bz * p.a_batch_rows, bz * p.b_batch_rows,
-                      kb0, kb1);
-    } else if (warp == 1) {
-      if (lane == 0) gemm_mma(p, smem, full_bar, empty_bar, &acc_bar, tmem_base, kb0, kb1);
-    } else {
-      const int quarter = warp & 3;
-      const int m = m0 + quarter * 32 + lane;
-      if (mbar_wait(&acc_bar, 0, p.err_flag)) {
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const GemmTile t = gemm_tile(p, tile);
+      const int a_row = t.bz * p.a_batch_rows + t.m0, b_row = t.bz * p.b_batch_rows + t.n0;
+      for (int kb = t.kb0; kb < t.kb1; ++kb) {
+        if (!mbar_wait(&empty_bar[stage], phase ^ 1, p.err_flag)) goto teardown;
+        if (elect_one()) {
+          uint8_t* sa = smem + static_cast<size_t>(stage) * kStage;
+          mbar_arrive_expect_tx(&full_bar[stage], kStage);
+          tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, a_row);
+          tma_load_2d(sa + kStageA, &tmap_b, &full_bar[stage], kb * BK, b_row);
+        }
+        __syncwarp();
+        if (++stage == kGemmStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    const uint32_t idesc = make_idesc_f16(BM, BN);
+    // 128B-swizzled K-major tiles: 8-row atoms of 1024 B (SBO), 32 B start advance per 16-element K step
+    const uint32_t d_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t d_lo_c = 1u << 16;
+    int stage = 0;
+    uint32_t phase = 0;
+    int iter = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++iter) {
+      const GemmTile t = gemm_tile(p, tile);
+      const int slot = iter & 1;
+      if (!mbar_wait(&acc_empty[slot], ((iter >> 1) & 1) ^ 1, p.err_flag)) goto teardown;
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(slot * BN);
+      uint32_t accumulate = 0;
+      for (int kb = t.kb0; kb < t.kb1; ++kb) {
+        if (!mbar_wait(&full_bar[stage], phase, p.err_flag)) goto teardown;
         tc_fence_after();
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-        const bool lead = (sk == 0);
-        for (int c0 = 0; c0 < BN; c0 += 16) {
-          if (n0 + c0 >= p.N) break;                         // warp-uniform
-          uint32_t r[16];
-          tmem_ld16(taddr + c0, r);
-          tmem_ld_wait();
-          if (m >= p.M) continue;
-          float v[16];
+        if (elect_one()) {
+          const uint32_t sa16 = smem_u32(smem + static_cast<size_t>(stage) * kStage) >> 4;
+          const uint32_t sb16 = sa16 + (kStageA >> 4);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int n = n0 + c0 + j;
-            float x = __uint_as_float(r[j]) * p.alpha;
-            if (n < p.N) {
-              if (lead && p.bias) x += __ldg(&p.bias[n]);
-              if (lead && p.rowvec) x += __ldg(&p.rowvec[static_cast<size_t>(m % p.row_period) * p.N + n]);
-              x = act_apply(x, p.act);
-            }
-            v[j] = x;
+          for (int k = 0; k < BK / 16; ++k) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+                "mov.b64 da, {%1, %2};\n\t"
+                "mov.b64 db, {%3, %2};\n\t"
+                "setp.ne.b32 p, %5, 0;\n\t"
+                "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+                ::"r"(tmem_d), "r"(d_lo_c | ((sa16 + 2u * k) & 0x3FFFu)), "r"(d_hi), "r"(d_lo_c | ((sb16 + 2u * k) & 0x3FFFu)),
+                "r"(idesc), "r"(accumulate)
+                : "memory");
+            accumulate = 1;
           }
-          if (p.mode_qkv) {
-            const int b = m / p.T, t = m % p.T;
-            const int hidden = p.heads * p.hd;
+          umma_commit(&empty_bar[stage]);
+        }
+        __syncwarp();
+        accumulate = 1;
+        if (++stage == kGemmStages) { stage = 0; phase ^= 1; }
+      }
+      if (elect_one()) umma_commit(&acc_full[slot]);
+      __syncwarp();
+    }
+  } else {
+    // ===================================================================== epilogue (warps 2..5)
+    const int quarter = warp & 3;
+    int iter = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++iter) {
+      const GemmTile t = gemm_tile(p, tile);
+      const int slot = iter & 1;
+      const int m = t.m0 + quarter * 32 + lane;
+      const int n0 = t.n0;
+      if (!mbar_wait(&acc_full[slot], (iter >> 1) & 1, p.err_flag)) goto teardown;
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(slot * BN);
+      const bool lead = (t.sk == 0);
+      const float* rv = (p.rowvec && m < p.M) ? p.rowvec + static_cast<size_t>(m % p.row_period) * p.N : nullptr;
+      // deconv / qkv row decomposition hoisted out of the column loop
+      int rb = 0, rt = 0;
+      size_t dc_vox = 0;
+      if (p.mode == 1) { rb = m / p.T; rt = m % p.T; }
+      if (p.mode == 2) {
+        const int vg = p.Dg * p.Hg * p.Wg;
+        rb = m / vg;
+        const int v = m % vg;
+        const int w = v % p.Wg, h = (v / p.Wg) % p.Hg, d = v / (p.Wg * p.Hg);
+        dc_vox = (static_cast<size_t>(2 * d) * (2 * p.Hg) + 2 * h) * (2 * p.Wg) + 2 * w;
+      }
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        if (n0 + c0 >= p.N) break;                         // warp-uniform
+        uint32_t r[16];
+        tmem_ld16(taddr + c0, r);
+        tmem_ld_wait();
+        if (m >= p.M) continue;
+        float v[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int n = n0 + c0 + j;
-              if (n >= p.N) break;
-              const int which = n / hidden, rem = n % hidden;
-              const int hh = rem / p.hd, dd = rem % p.hd;
-              const size_t bh = static_cast<size_t>(b) * p.heads + hh;
-              if (which == 0) p.q[(bh * p.T + t) * p.hd + dd] = __float2half_rn(v[j] * p.q_scale);
-              else if (which == 1) p.kk[(bh * p.T + t) * p.hd + dd] = __float2half_rn(v[j]);
-              else p.vt[(bh * p.hd + dd) * p.T + t] = __float2half_rn(v[j]);
-            }
-            continue;
+        for (int j = 0; j < 16; ++j) {
+          const int n = n0 + c0 + j;
+          float x = __uint_as_float(r[j]) * p.alpha;
+          if (n < p.N) {
+            if (lead && p.bias) x += __ldg(&p.bias[n]);
+            if (lead && rv) x += __ldg(&rv[n]);
+            if (p.act) x = act_apply(x, p.act);
           }
-          const size_t boff = p.c_batch_period > 0
-              ? static_cast<size_t>(bz / p.c_batch_period) * p.c_batch_stride + static_cast<size_t>(bz % p.c_batch_period) * p.c_batch_stride2
-              : static_cast<size_t>(bz) * p.c_batch_stride;
-          const size_t base = boff + static_cast<size_t>(sk) * p.split_stride + static_cast<size_t>(m) * p.ldc + n0 + c0;
-          const bool full = (n0 + c0 + 16 <= p.N);
-          if (p.resid && lead) {
+          v[j] = x;
+        }
+        if (p.mode == 1) {
+          const int hidden = p.heads * p.hd;
+          const int n = n0 + c0;                            // 16 | hd, so the 16 columns share (which, head)
+          const int which = n / hidden, rem = n % hidden;
+          const int hh = rem / p.hd, dd = rem % p.hd;
+          const size_t bh = static_cast<size_t>(rb) * p.heads + hh;
+          if (which == 2) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) p.vt[(bh * p.hd + dd + j) * p.T + rt] = __float2half_rn(v[j]);
+          } else {
+            __half* dst = (which == 0 ? p.q : p.kk) + (bh * p.T + rt) * p.hd + dd;
+            const float sc = which == 0 ? p.q_scale : 1.f;
+            __align__(16) __half h[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) h[j] = __float2half_rn(v[j] * sc);
+            *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(&h[0]);
+            *reinterpret_cast<uint4*>(dst + 8) = *reinterpret_cast<const uint4*>(&h[8]);
+          }
+          continue;
+        }
+        if (p.mode == 2) {
+          const int n = n0 + c0;                            // 16 | cout, so the 16 columns share the parity
+          const int qp = n / p.cout, co = n % p.cout;
+          const size_t vo = dc_vox + (static_cast<size_t>(qp >> 2) * (2 * p.Hg) + ((qp >> 1) & 1)) * (2 * p.Wg) + (qp & 1);
+          const size_t vox_out = static_cast<size_t>(8) * p.Dg * p.Hg * p.Wg;
+#pragma unroll
+          for (int b = 0; b < 2; ++b) {
+            const size_t off = ((static_cast<size_t>(rb) * p.dc_cb_total + p.dc_cb_off + (co >> 3) + b) * vox_out + vo) * 8;
+            __align__(16) __half hi[8];
+            __align__(16) __half lo[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              hi[j] = __float2half_rn(v[b * 8 + j]);
+              lo[j] = __float2half_rn(v[b * 8 + j] - __half2float(hi[j]));
+            }
+            *reinterpret_cast<uint4*>(p.dc_hi + off) = *reinterpret_cast<const uint4*>(hi);
+            if (p.dc_lo) *reinterpret_cast<uint4*>(p.dc_lo + off) = *reinterpret_cast<const uint4*>(lo);
+          }
+          continue;
+        }
+        const size_t boff = p.c_batch_period > 0
+            ? static_cast<size_t>(t.bz / p.c_batch_period) * p.c_batch_stride + static_cast<size_t>(t.bz % p.c_batch_period) * p.c_batch_stride2
+            : static_cast<size_t>(t.bz) * p.c_batch_stride;
+        const size_t base = boff + static_cast<size_t>(t.sk) * p.split_stride + static_cast<size_t>(m) * p.ldc + n0 + c0;
+        const bool full = (n0 + c0 + 16 <= p.N);
+        if (p.resid && lead) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (full || n0 + c0 + j < p.N) v[j] += p.resid[base + j];
+        }
+        if (p.out_f32) {
+          if (full && (p.ldc % 4 == 0)) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+              *reinterpret_cast<float4*>(&p.out_f32[base + j]) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
 #pragma unroll
             for (int j = 0; j < 16; ++j)
-              if (full || n0 + c0 + j < p.N) v[j] += p.resid[base + j];
+              if (n0 + c0 + j < p.N) p.out_f32[base + j] = v[j];
           }
-          if (p.out_f32) {
-            if (p.atomic) {
+        }
+        if (p.out_f16) {
+          if (full && (p.ldc % 8 == 0)) {
+            __align__(16) __half h[16];
 #pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (full || n0 + c0 + j < p.N) atomicAdd(&p.out_f32[base + j], v[j]);
-            } else if (full && (p.ldc % 4 == 0)) {
+            for (int j = 0; j < 16; ++j) h[j] = __float2half_rn(v[j]);
+            *reinterpret_cast<uint4*>(&p.out_f16[base]) = *reinterpret_cast<const uint4*>(&h[0]);
+            *reinterpret_cast<uint4*>(&p.out_f16[base + 8]) = *reinterpret_cast<const uint4*>(&h[8]);
+          } else {
 #pragma unroll
-              for (int j = 0; j < 16; j += 4)
-                *reinterpret_cast<float4*>(&p.out_f32[base + j]) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (n0 + c0 + j < p.N) p.out_f32[base + j] = v[j];
-            }
-          }
-          if (p.out_f16) {
-            if (full && (p.ldc % 8 == 0)) {
-              __align__(16) __half h[16];
-#pragma unroll
-              for (int j = 0; j < 16; ++j) h[j] = __float2half_rn(v[j]);
-              *reinterpret_cast<uint4*>(&p.out_f16[base]) = *reinterpret_cast<const uint4*>(&h[0]);
-              *reinterpret_cast<uint4*>(&p.out_f16[base + 8]) = *reinterpret_cast<const uint4*>(&h[8]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (n0 + c0 + j < p.N) p.out_f16[base + j] = __float2half_rn(v[j]);
-            }
+            for (int j = 0; j < 16; ++j)
+              if (n0 + c0 + j < p.N) p.out_f16[base + j] = __float2half_rn(v[j]);
           }
         }
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[slot]);
     }
   }
+
+teardown:
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<BN>(tmem_base);
+    tmem_dealloc<2 * BN>(tmem_base);
   }
 }
 
-}  // namespace dp
-
-extern "C" int dp_gemm_tc(const void* A, const void* B, int M, int N, int K, int batch, int a_batch_rows,
-                          int b_batch_rows, long long c_batch_stride, int c_batch_period, long long c_batch_stride2, int ldc,
-                          int split_k, const float* bias,
-                          const float* rowvec, int row_period, const float* resid, float alpha, int act,
-                          float* out_f32, int atomic, void* out_f16, int mode_qkv, int heads, int hd, int T, void* q,
-                          void* k, void* vt, float q_scale, int* err_flag, cudaStream_t stream) {
-  using namespace dp;
-  DP_REQUIRE(K % 8 == 0, "dp_gemm_tc: K=%d must be a multiple of 8 (TMA 16-byte row pitch)", K);
-  DP_REQUIRE(batch >= 1 && split_k >= 1, "dp_gemm_tc: bad batch/split_k");
-  DP_REQUIRE(split_k == 1 || (out_f32 && !atomic && !out_f16 && !mode_qkv && act == 0 && !bias && !rowvec && !resid && batch == 1),
-             "dp_gemm_tc: split-K writes plain fp32 partials [split_k][M][ldc] (finish with dp_splitk_reduce)");
-  GemmParams p{};
-  p.M = M; p.N = N; p.K = K; p.batch = batch; p.split_k = split_k;
-  const int total_kb = (K + BK - 1) / BK;
-  p.kb_per_split = (total_kb + split_k - 1) / split_k;
-  p.split_stride = static_cast<long long>(M) * ldc;
-  p.a_batch_rows = a_batch_rows; p.b_batch_rows = b_batch_rows; p.c_batch_stride = c_batch_stride; p.c_batch_period = c_batch_period; p.c_batch_stride2 = c_batch_stride2; p.ldc = ldc;
-  p.bias = bias; p.rowvec = rowvec; p.row_period = row_period > 0 ? row_period : 1; p.resid = resid;
-  p.alpha = alpha; p.act = act; p.out_f32 = out_f32; p.atomic = atomic; p.out_f16 = static_cast<__half*>(out_f16);
-  p.mode_qkv = mode_qkv; p.heads = heads; p.hd = hd; p.T = T > 0 ? T : 1;
-  p.q = static_cast<__half*>(q); p.kk = static_cast<__half*>(k); p.vt = static_cast<__half*>(vt); p.q_scale = q_scale;
-  p.err_flag = err_flag;
-
-  const uint64_t a_rows = static_cast<uint64_t>(batch > 1 && a_batch_rows ? (batch - 1) * static_cast<uint64_t>(a_batch_rows) + M : M);
-  const uint64_t b_rows = static_cast<uint64_t>(batch > 1 && b_batch_rows ? (batch - 1) * static_cast<uint64_t>(b_batch_rows) + N : N);
+static int launch_gemm(const void* A, const void* B, dp::GemmParams& p, int a_batch_rows, int b_batch_rows,
+                       cudaStream_t stream) {
+  DP_REQUIRE(p.K % 8 == 0, "dp_gemm_tc: K=%d must be a multiple of 8 (TMA 16-byte row pitch)", p.K);
+  DP_REQUIRE(p.batch >= 1 && p.split_k >= 1, "dp_gemm_tc: bad batch/split_k");
+  p.total_kb = (p.K + BK - 1) / BK;
+  p.kb_per_split = (p.total_kb + p.split_k - 1) / p.split_k;
+  p.split_k = (p.total_kb + p.kb_per_split - 1) / p.kb_per_split;      // no empty splits
+  p.split_stride = static_cast<long long>(p.M) * p.ldc;
+  p.a_batch_rows = a_batch_rows; p.b_batch_rows = b_batch_rows;
+  p.tiles_m = (p.M + BM - 1) / BM;
+  p.tiles_n = (p.N + BN - 1) / BN;
+  p.num_tiles = p.tiles_m * p.tiles_n * p.batch * p.split_k;
+  const uint64_t a_rows = static_cast<uint64_t>(p.batch > 1 && a_batch_rows ? (p.batch - 1) * static_cast<uint64_t>(a_batch_rows) + p.M : p.M);
+  const uint64_t b_rows = static_cast<uint64_t>(p.batch > 1 && b_batch_rows ? (p.batch - 1) * static_cast<uint64_t>(b_batch_rows) + p.N : p.N);
   CUtensorMap ta, tb;
   {
-    const uint64_t dims[2] = {static_cast<uint64_t>(K), a_rows};
-    const uint64_t strides[1] = {static_cast<uint64_t>(K) * 2};
+    const uint64_t dims[2] = {static_cast<uint64_t>(p.K), a_rows};
+    const uint64_t strides[1] = {static_cast<uint64_t>(p.K) * 2};
     const uint32_t box[2] = {BK, BM};
     if (int rc = encode_tiled(&ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, A, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))
       return rc;
   }
   {
-    const uint64_t dims[2] = {static_cast<uint64_t>(K), b_rows};
-    const uint64_t strides[1] = {static_cast<uint64_t>(K) * 2};
+    const uint64_t dims[2] = {static_cast<uint64_t>(p.K), b_rows};
+    const uint64_t strides[1] = {static_cast<uint64_t>(p.K) * 2};
     const uint32_t box[2] = {BK, BN};
     if (int rc = encode_tiled(&tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, B, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))
       return rc;
@@ -256,8 +319,46 @@ extern "C" int dp_gemm_tc(const void* A, const void* B, int M, int N, int K, int
     DP_CHECK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     configured = true;
   }
-  dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, batch * split_k);
+  int grid = sm_count();
+  if (grid > p.num_tiles) grid = p.num_tiles;
   gemm_tc_kernel<<<grid, kGemmThreads, smem, stream>>>(ta, tb, p);
   DP_CHECK(cudaGetLastError());
   return 0;
+}
+
+}  // namespace dp
+
+extern "C" int dp_gemm_tc(const void* A, const void* B, int M, int N, int K, int batch, int a_batch_rows,
+                          int b_batch_rows, long long c_batch_stride, int c_batch_period, long long c_batch_stride2, int ldc,
+                          int split_k, const float* bias, const float* rowvec, int row_period, const float* resid,
+                          float alpha, int act, float* out_f32, int atomic, void* out_f16, int mode_qkv, int heads,
+                          int hd, int T, void* q, void* k, void* vt, float q_scale, int* err_flag, cudaStream_t stream) {
+  using namespace dp;
+  DP_REQUIRE(!atomic, "dp_gemm_tc: the atomic epilogue was removed (split-K is deterministic: dp_splitk_reduce)");
+  DP_REQUIRE(split_k == 1 || (out_f32 && !out_f16 && !mode_qkv && act == 0 && !bias && !rowvec && !resid && batch == 1),
+             "dp_gemm_tc: split-K writes plain fp32 partials [split_k][M][ldc] (finish with dp_splitk_reduce)");
+  DP_REQUIRE(!mode_qkv || (hd % 16 == 0 && N == 3 * heads * hd), "dp_gemm_tc: qkv scatter needs head_dim %% 16 == 0");
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K; p.batch = batch; p.split_k = split_k;
+  p.c_batch_stride = c_batch_stride; p.c_batch_period = c_batch_period; p.c_batch_stride2 = c_batch_stride2; p.ldc = ldc;
+  p.bias = bias; p.rowvec = rowvec; p.row_period = row_period > 0 ? row_period : 1; p.resid = resid;
+  p.alpha = alpha; p.act = act; p.out_f32 = out_f32; p.out_f16 = static_cast<__half*>(out_f16);
+  p.mode = mode_qkv ? 1 : 0; p.heads = heads; p.hd = hd; p.T = T > 0 ? T : 1;
+  p.q = static_cast<__half*>(q); p.kk = static_cast<__half*>(k); p.vt = static_cast<__half*>(vt); p.q_scale = q_scale;
+  p.err_flag = err_flag;
+  return launch_gemm(A, B, p, a_batch_rows, b_batch_rows, stream);
+}
+
+extern "C" int dp_deconv2x_gemm(const void* tokens, const void* w_nk, int B, int Dg, int Hg, int Wg, int cin, int cout,
+                                void* out_hi, void* out_lo, int out_cb_total, int out_cb_off, int* err_flag,
+                                cudaStream_t stream) {
+  using namespace dp;
+  DP_REQUIRE(cout % 16 == 0 && cin % 8 == 0, "dp_deconv2x_gemm: needs C_out %% 16 == 0 and C_in %% 8 == 0 (got %d, %d)", cout, cin);
+  GemmParams p{};
+  p.M = B * Dg * Hg * Wg; p.N = 8 * cout; p.K = cin; p.batch = 1; p.split_k = 1; p.ldc = p.N;
+  p.row_period = 1; p.alpha = 1.f; p.T = 1;
+  p.mode = 2; p.Dg = Dg; p.Hg = Hg; p.Wg = Wg; p.cout = cout;
+  p.dc_hi = static_cast<__half*>(out_hi); p.dc_lo = static_cast<__half*>(out_lo);
+  p.dc_cb_total = out_cb_total; p.dc_cb_off = out_cb_off; p.err_flag = err_flag;
+  return launch_gemm(tokens, w_nk, p, 0, 0, stream);
 }

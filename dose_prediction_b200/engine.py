@@ -12,6 +12,7 @@ tensor-core K step (16 channels) is two channel blocks.  A buffer may carry an f
 """
 import ctypes
 import math
+import os
 
 import torch
 
@@ -20,6 +21,8 @@ from . import _lib
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_MISH, ACT_GELU = 0, 1, 2, 3, 4
 ACT_ID = {None: ACT_NONE, "none": ACT_NONE, "relu": ACT_RELU, "lrelu": ACT_LRELU, "mish": ACT_MISH, "gelu": ACT_GELU}
 STATS_DOUBLES = 1 << 20
+STACK_TILES = int(os.environ.get("DP_STACK_TILES", "0"))
+STACKED_CONV = os.environ.get("DP_STACKED_CONV", "1") != "0"    # bring-up switch between the two tcgen05 conv kernels
 EPS = 1e-5
 
 
@@ -198,7 +201,9 @@ class Plan:
             if rc:
                 _lib.check(rc, name)
             label = ""
-            if name == "dp_conv3d_tc":
+            if name == "dp_conv3d_stack":
+                label = f"N{args[5]} {args[6]}x{args[7]}x{args[8]} cout{args[9]} k{args[10]} chunks{args[3]}"
+            elif name == "dp_conv3d_tc":
                 label = f"N{args[5]} {args[6]}x{args[7]}x{args[8]} cout{args[9]} k{args[10]} dil{args[11]} chunks{args[3]}"
             elif name == "dp_gemm_tc":
                 label = f"M{args[2]} N{args[3]} K{args[4]} batch{args[5]} split{args[12]}"
@@ -264,7 +269,7 @@ class Plan:
             self.run()
 
     # ------------------------------------------------------------------ weight packing
-    def pack_conv_tc(self, w, parts, mode):
+    def pack_conv_tc(self, w, parts, mode, stacked=False):
         """w [Co,Ci,k,k,k] fp32 -> fp16 [kd][chunk][kh][kw][2][Co][8] + per-chunk input block table.
         mode p1: x_hi.W_hi;  p2: + x_lo.W_hi;  p3: + x_hi.W_lo  (operand splitting by K expansion)."""
         w = w.detach().to(self.device, torch.float32)
@@ -290,7 +295,11 @@ class Plan:
                 base += a.C
             assert base == Ci, f"input parts carry {base} channels, weight expects {Ci}"
         nch = len(mats)
-        W = torch.stack(mats, dim=1).view(Co, nch, 2, 8, k, k, k).permute(4, 1, 5, 6, 2, 0, 3).contiguous().half()
+        W = torch.stack(mats, dim=1).view(Co, nch, 2, 8, k, k, k)
+        if stacked:   # [chunk][kh][kw][khalf][j = k-1-kd][co][e]: the k depth taps become MMA columns
+            W = W.flip(4).permute(1, 5, 6, 2, 4, 0, 3).contiguous().half()
+        else:         # [kd][chunk][kh][kw][khalf][co][e]
+            W = W.permute(4, 1, 5, 6, 2, 0, 3).contiguous().half()
         self.keep.append(W)
         assert max(chunks) < 256
         arr = (ctypes.c_uint8 * nch)(*chunks)
@@ -328,14 +337,22 @@ class Plan:
         a0 = parts[0]
         D, H, W = a0.dims
         Co = weight.shape[0]
-        wp, chunks, nch = self.pack_conv_tc(weight, parts, mode)
+        stacked = STACKED_CONV and dil == 1 and k in (3, 7) and Co in (16, 32)
+        wp, chunks, nch = self.pack_conv_tc(weight, parts, mode, stacked=stacked)
         if out_raw is not None:
             of32, ohi, olo, cbt, cbo = out_raw.t.data_ptr(), None, None, out_raw.cb_total, 0
             st = out_raw.stats if stats is None else stats
         else:
             of32, ohi, olo, cbt, cbo = None, out_act.hi_ptr, out_act.lo_ptr, out_act.cb_total, out_act.cb_off
             st = stats
-        self.count_flops("dp_conv3d_tc", 2.0 * a0.N * D * H * W * k ** 3 * weight.shape[1] * Co)
+        flops = 2.0 * a0.N * D * H * W * k ** 3 * weight.shape[1] * Co
+        if stacked:
+            self.count_flops("dp_conv3d_stack", flops)
+            self.add("dp_conv3d_stack", a0.buf.data_ptr(), a0.cb_total, chunks, nch, wp.data_ptr(), a0.N, D, H, W, Co, k,
+                     scale.data_ptr(), shift.data_ptr(), int(relu), of32, ohi, olo, cbt, cbo,
+                     st.data_ptr() if st is not None else None, self.err.data_ptr(), 0, STACK_TILES)
+            return
+        self.count_flops("dp_conv3d_tc", flops)
         self.add("dp_conv3d_tc", a0.buf.data_ptr(), a0.cb_total, chunks, nch, wp.data_ptr(), a0.N, D, H, W, Co, k, dil,
                  scale.data_ptr(), shift.data_ptr(), int(relu), of32, ohi, olo, cbt, cbo,
                  st.data_ptr() if st is not None else None, self.err.data_ptr(), 0)
@@ -418,6 +435,15 @@ class Plan:
     def deconv2x(self, src, weight, out):
         """ConvTranspose3d k2 s2 (no bias): src Act or Tokens -> out Act (usually a slice of a concat buffer)."""
         Ci, Co = weight.shape[0], weight.shape[1]
+        if isinstance(src, Tokens) and Co % 16 == 0:
+            B, T, C = src.t.shape
+            D, H, W = src.grid
+            assert C == Ci and C % 8 == 0
+            wnk = self.dev(weight.permute(2, 3, 4, 1, 0).reshape(8 * Co, Ci), torch.float16)
+            self.count_flops("dp_deconv2x_gemm", 2.0 * B * T * Ci * Co * 8)
+            self.add("dp_deconv2x_gemm", src.t.data_ptr(), wnk.data_ptr(), B, D, H, W, Ci, Co, out.hi_ptr, out.lo_ptr,
+                     out.cb_total, out.cb_off, self.err.data_ptr())
+            return
         w = self.dev(weight.permute(2, 3, 4, 0, 1).reshape(8, Ci, Co))
         if isinstance(src, Tokens):
             B, T, C = src.t.shape
@@ -442,6 +468,7 @@ class Plan:
     def gemm(self, A, B, M, N, K, *, batch=1, a_batch_rows=0, b_batch_rows=0, c_batch_stride=0, c_batch_period=0,
              c_batch_stride2=0, ldc=None, split_k=1, bias=None, rowvec=None, row_period=0, resid=None, alpha=1.0,
              act=None, out_f32=None, atomic=False, out_f16=None, qkv=None):
+        self.count_flops("dp_gemm_tc", 2.0 * M * N * K * batch)
         ldc = N if ldc is None else ldc
         mode_qkv, heads, hd, T, q, k, vt, qs = 0, 0, 0, 0, None, None, None, 1.0
         if qkv is not None:

@@ -53,6 +53,17 @@ int dp_conv3d_tc(const void* in_c8, int cb_total_in, const uint8_t* chunk_cb, in
                  int relu, float* out_f32, void* out_hi, void* out_lo, int cb_total_out, int cb_out_off,
                  double* stats, int* err_flag, int max_ctas, cudaStream_t stream);
 
+/* Same convolution for C_out in {16,32}, k in {3,7}, dilation 1, with the k depth taps stacked into the MMA
+ * N dimension (N = k*C_out) and a sliding ring of output-plane accumulators in TMEM (conv_stack.cu): the
+ * shared-memory A operand is read once per k taps instead of once per tap.
+ *   wpack_stack  fp16 [n_chunks][k(kh)][k(kw)][2][k*cout][8], row j*cout+co holding W[co, :, kd=k-1-j, kh, kw]
+ *   seg_len      output planes per work item along D (0 = choose for load balance)
+ *   tiles_per_cta  adjacent W tiles sharing one weight stream (0 = default)                             */
+int dp_conv3d_stack(const void* in_c8, int cb_total_in, const uint8_t* chunk_cb, int n_chunks, const void* wpack_stack,
+                    int N, int D, int H, int W, int cout, int k, const float* scale, const float* shift, int relu,
+                    float* out_f32, void* out_hi, void* out_lo, int cb_total_out, int cb_out_off, double* stats,
+                    int* err_flag, int seg_len, int tiles_per_cta, cudaStream_t stream);
+
 /* Generic direct convolution (any stride): c3d.py:49,53,57,61 (stride-2 SingleConv convs).
  *   w_packed   fp32 [k^3 taps][cin][cout]                                                              */
 int dp_conv3d_direct(const void* in_hi, const void* in_lo, int in_cb_total, int in_cb_off, int cin, int N, int D,
@@ -109,6 +120,13 @@ int dp_pointwise_conv(int nsrc, const void* const* src_hi, const void* const* sr
 int dp_deconv2x(const void* in_hi, const void* in_lo, long long in_nstride, long long in_vstride,
                 long long in_cbstride, int cin, int cout, int N, int D, int H, int W, const float* w_packed,
                 void* out_hi, void* out_lo, int out_cb_total, int out_cb_off, cudaStream_t stream);
+
+/* Same transposed convolution as a tcgen05 GEMM [B*Dg*Hg*Wg, cin] x [cin, 8*cout] with a pixel-shuffle
+ * scatter epilogue; used when the input is a ViT token matrix [B, Dg*Hg*Wg, cin] fp16 (cin = 768).
+ *   w_nk  fp16 [8*cout][cin], row (i*4+j*2+l)*cout + co = W[:, co, i, j, l]                           */
+int dp_deconv2x_gemm(const void* tokens, const void* w_nk, int B, int Dg, int Hg, int Wg, int cin, int cout,
+                     void* out_hi, void* out_lo, int out_cb_total, int out_cb_off, int* err_flag,
+                     cudaStream_t stream);
 
 /* F.interpolate(scale_factor=2, mode='trilinear', align_corners=True): c3d.py:36 */
 int dp_upsample2x(const void* in_hi, const void* in_lo, int in_cb_total, int in_cb_off, int ncb, int N, int D, int H,
