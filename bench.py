@@ -238,17 +238,27 @@ def main():
 
     # ---- per-kernel-family device time (instrumented eager replay, CUDA events on the launch stream)
     fam = plan.profile_families(repeats=2)
-    conv_ms = fam.get("dp_conv3d_tc", {}).get("ms", 0.0)
-    conv_launches = fam.get("dp_conv3d_tc", {}).get("launches", 0)
     peaks = _peaks()
-    conv_flops = plan.flops.get("dp_conv3d_tc", 0.0)
-    achieved = conv_flops / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
     total_fam = sum(v["ms"] for v in fam.values()) or 1.0
-    roofline = {"kernel": "conv3d_tc_kernel (tcgen05 implicit-GEMM 3^3/7^3 conv)", "bound": "tensor",
-                "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
-                "traffic": None, "peak_source": peaks["source"], "launches_per_step": conv_launches,
-                "avg_launch_ms": conv_ms / max(conv_launches, 1), "algorithmic_flops_per_step": conv_flops,
-                "share_of_step": conv_ms / total_fam}
+    names = {"dp_conv3d_stack": "conv3d_stack_kernel (tcgen05 depth-stacked implicit-GEMM conv, C_out 16/32)",
+             "dp_conv3d_tc": "conv3d_tc_kernel (tcgen05 implicit-GEMM conv, C_out >= 64 / dilated)",
+             "dp_gemm_tc": "gemm_tc_kernel (tcgen05 GEMM: ViT linears, attention, patch embedding)"}
+
+    def tensor_roofline(key):
+        ms_k = fam.get(key, {}).get("ms", 0.0)
+        n_k = fam.get(key, {}).get("launches", 0)
+        fl = plan.flops.get(key, 0.0)
+        ach = fl / (ms_k / 1e3) / 1e12 if ms_k > 0 else 0.0
+        return {"kernel": names[key], "bound": "tensor", "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s",
+                "frac": ach / peaks["tflops"], "traffic": None, "peak_source": peaks["source"], "launches_per_step": n_k,
+                "avg_launch_ms": ms_k / max(n_k, 1), "algorithmic_flops_per_step": fl, "share_of_step": ms_k / total_fam}
+
+    dominant = max(names, key=lambda k: fam.get(k, {}).get("ms", 0.0))
+    roofline = tensor_roofline(dominant)
+    roofline_other = [tensor_roofline(k) for k in names if k != dominant]
+    conv_fl = plan.flops.get("dp_conv3d_stack", 0.0) + plan.flops.get("dp_conv3d_tc", 0.0)
+    conv_ms = fam.get("dp_conv3d_stack", {}).get("ms", 0.0) + fam.get("dp_conv3d_tc", {}).get("ms", 0.0)
+    conv_pct = conv_fl / (conv_ms / 1e3) / 1e12 / peaks["tflops"] if conv_ms > 0 else 0.0
     plan.check_device_errors()
 
     if rank == 0:
@@ -263,7 +273,8 @@ def main():
                 "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                         "h2d_bytes_per_step": 2 * B * S ** 3 * 4, "d2h_bytes_per_step": B * S ** 3 * 4},
                 "gpu_launches": plan.launches * args.steps, "launches_per_step": plan.launches,
-                "roofline": roofline, "kernel_ms_per_step": {k: round(v["ms"], 3) for k, v in sorted(fam.items())},
+                "roofline": roofline, "roofline_other": roofline_other, "conv_frac_of_tensor_peak": conv_pct,
+                "kernel_ms_per_step": {k: round(v["ms"], 3) for k, v in sorted(fam.items())},
                 "clocks": clocks}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline({k: v.cpu() for k, v in seg.state_dict().items()},

@@ -16,9 +16,11 @@ __device__ __forceinline__ float act_apply(float x, int act) {
   switch (act) {
     case ACT_RELU: return fmaxf(x, 0.f);
     case ACT_LRELU: return x > 0.f ? x : 0.01f * x;
-    case ACT_MISH: {  // x * tanh(softplus(x)), softplus threshold 20 (torch semantics)
-      float sp = x > 20.f ? x : log1pf(__expf(x));
-      return x * tanhf(sp);
+    case ACT_MISH: {  // x * tanh(softplus(x)) = x * u / (u + 2), u = e^x (e^x + 2); softplus threshold 20 (torch)
+      if (x > 20.f) return x;
+      const float t = __expf(x);
+      const float u = t * (t + 2.f);
+      return x * __fdividef(u, u + 2.f);
     }
     case ACT_GELU: return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
     default: return x;

@@ -13,7 +13,7 @@
 // along a segment of L output planes; work items = (image, D segment, H tile, W tile group), persistent.
 // Ring bookkeeping: every output plane gets a running counter pc; slot = pc % G, parity = (pc / G) & 1.
 //   done_bar[slot]  MMA  -> epilogue   (tcgen05.commit after the last input plane contributing to it)
-//   free_bar[slot]  epilogue -> MMA    (4 epilogue warps have drained it; next owner may start with acc=0)
+//   free_bar[slot]  epilogue -> MMA    (8 epilogue warps have drained it; next owner may start with acc=0)
 // The first MMA that touches a new plane uses accumulate=0 on that plane's group only (the window is
 // split into an old and a new part for that one tap), so TMEM never needs zeroing.
 #include "common.cuh"
@@ -44,7 +44,8 @@ struct StackParams {
   uint8_t chunk_cb[96];
 };
 
-constexpr int kStackThreads = 192;
+constexpr int kStackThreads = 320;      // producer + MMA + 8 epilogue warps (2 per TMEM lane quarter)
+constexpr int kStackEpiWarps = 8;
 constexpr int kMaxAStages = 4, kMaxBStages = 6, kMaxSlots = 32;
 
 __device__ __forceinline__ void umma_split(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
@@ -116,7 +117,7 @@ conv3d_stack_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_co
   __shared__ uint64_t b_full[kMaxBStages], b_empty[kMaxBStages];
   __shared__ uint64_t done_bar[kMaxSlots], free_bar[kMaxSlots];
   __shared__ uint32_t tmem_base_smem;
-  __shared__ float stat_acc[4][32][2];
+  __shared__ float stat_acc[kStackEpiWarps][32][2];
   __shared__ float s_scale[32], s_shift[32];
 
   const int warp = threadIdx.x >> 5;
@@ -127,11 +128,11 @@ conv3d_stack_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_co
     tma_prefetch_desc(&tmap_in);
     for (int i = 0; i < p.a_stages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < p.b_stages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i < p.G; ++i) { mbar_init(&done_bar[i], 1); mbar_init(&free_bar[i], 4); }
+    for (int i = 0; i < p.G; ++i) { mbar_init(&done_bar[i], 1); mbar_init(&free_bar[i], kStackEpiWarps); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(&tmem_base_smem);
-  for (int i = threadIdx.x; i < 4 * 32 * 2; i += kStackThreads) (&stat_acc[0][0][0])[i] = 0.f;
+  for (int i = threadIdx.x; i < kStackEpiWarps * 32 * 2; i += kStackThreads) (&stat_acc[0][0][0])[i] = 0.f;
   for (int i = threadIdx.x; i < N0; i += kStackThreads) { s_scale[i] = p.scale[i]; s_shift[i] = p.shift[i]; }
   tc_fence_before();
   __syncthreads();
@@ -294,9 +295,11 @@ conv3d_stack_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_co
       pc_base += static_cast<uint32_t>(it.d1 - it.d0);
     }
   } else {
-    // ===================================================================== epilogue (warps 2..5)
+    // ===================================================================== epilogue (warps 2..9)
+    // two warps per TMEM lane quarter; the pair splits the CTA's W tiles (even / odd)
     const int quarter = warp & 3;
     const int ew = warp - 2;
+    const int tgrp = ew >> 2;
     const int row = quarter * 32 + lane;
     const int hl = row >> 3, wl = row & 7;
     const int mycol = (lane >> 1) & 15;
@@ -323,7 +326,7 @@ conv3d_stack_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_co
         const int slot = static_cast<int>(pc & static_cast<uint32_t>(G - 1));
         if (!mbar_wait(&done_bar[slot], (pc >> (__ffs(G) - 1)) & 1, p.err_flag)) goto teardown;
         tc_fence_after();
-        for (int t = 0; t < it.ntile; ++t) {
+        for (int t = tgrp; t < it.ntile; t += 2) {
           const int w = it.w0 + t * 8 + wl;
           const bool valid = (h < p.H) && (w < p.W);
           const size_t vox = (static_cast<size_t>(d) * p.H + h) * p.W + w;
@@ -410,7 +413,7 @@ extern "C" int dp_conv3d_stack(const void* in_c8, int cb_total_in, const uint8_t
   p.tiles_h = (H + 15) / 16;
   p.tiles_w = (W + 7) / 8;
   // tiles per CTA: share B between as many W tiles as TMEM allows while keeping a ring of >= k+1 slots
-  int T = tiles_per_cta > 0 ? tiles_per_cta : (k == 7 ? 2 : 4);
+  int T = tiles_per_cta > 0 ? tiles_per_cta : 4;   // measured: weight streaming from L2 favours the widest sharing
   while (T > 1 && (512 / (T * cout)) < k + 1) T >>= 1;
   if (T > p.tiles_w) T = p.tiles_w;
   if (T < 1) T = 1;
@@ -423,12 +426,18 @@ extern "C" int dp_conv3d_stack(const void* in_c8, int cb_total_in, const uint8_t
   const int sms = sm_count();
   int L = seg_len > 0 ? seg_len : D;
   if (seg_len <= 0) {
+    // pick the number of D segments minimising (halo overhead) x (round-robin imbalance over the SMs)
     const long long cols = static_cast<long long>(N) * p.tiles_h * p.wgroups;
-    long long nseg = (4LL * sms + cols - 1) / cols;
-    if (nseg < 1) nseg = 1;
-    L = static_cast<int>((D + nseg - 1) / nseg);
-    if (L < 8) L = 8;
-    if (L > D) L = D;
+    double best = 1e30;
+    for (int nseg = 1; nseg <= D; ++nseg) {
+      const int len = (D + nseg - 1) / nseg;
+      if (len < 4 && nseg > 1) break;
+      const int segs = (D + len - 1) / len;
+      const long long items = cols * segs;
+      const double rounds = static_cast<double>((items + sms - 1) / sms);
+      const double cost = rounds * (len + k - 1);          // planes streamed by the busiest SM
+      if (cost < best - 1e-9) { best = cost; L = len; }
+    }
   }
   p.L = L;
   p.nseg = (D + L - 1) / L;

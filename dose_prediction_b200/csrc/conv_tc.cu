@@ -16,8 +16,8 @@
 // the folded bias/BatchNorm affine (+ReLU), accumulates InstanceNorm partial sums from the fp32
 // accumulators and writes c8 tensors (fp32 "raw" for a following InstanceNorm, or fp16 hi[/lo]).
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..5 =
-// epilogue (TMEM lane quarter = warp_id % 4).  Persistent: each CTA walks tiles blockIdx.x + i*gridDim.x.
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..9 =
+// epilogue (TMEM lane quarter = warp_id % 4, two warps per quarter).  Persistent: each CTA walks tiles blockIdx.x + i*gridDim.x.
 //
 // Reference call sites this replaces (cuDNN via nn.Conv3d): OARSegmentation/Models/Nets/
 // blocks_MDUNet.py:68-71,102-105 (conv_block_3 / conv_block_7), DosePrediction/Models/Networks/c3d.py:16,30,
@@ -52,7 +52,8 @@ struct ConvTcParams {
   uint8_t chunk_cb[96];
 };
 
-constexpr int kConvThreads = 192;
+constexpr int kConvThreads = 320;       // producer + MMA + 8 epilogue warps (2 per TMEM lane quarter)
+constexpr int kConvEpiWarps = 8;
 constexpr int kMaxStages = 8;
 
 // D[tmem] (+)= A * B with descriptors given as {lo, hi} 32-bit halves (only the start address in lo varies).
@@ -105,7 +106,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
   __shared__ uint64_t tmem_full_bar[2];
   __shared__ uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_smem;
-  __shared__ float stat_acc[4][256][2];
+  __shared__ float stat_acc[kConvEpiWarps][256][2];
   __shared__ float s_scale[256], s_shift[256];
 
   const int warp = threadIdx.x >> 5;
@@ -119,7 +120,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], 4);
+      mbar_init(&tmem_empty_bar[i], kConvEpiWarps);
     }
     fence_barrier_init();
   }
@@ -130,7 +131,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < 4 * 256 * 2; i += kConvThreads) (&stat_acc[0][0][0])[i] = 0.f;
+  for (int i = threadIdx.x; i < kConvEpiWarps * 256 * 2; i += kConvThreads) (&stat_acc[0][0][0])[i] = 0.f;
   for (int i = threadIdx.x; i < p.cout; i += kConvThreads) { s_scale[i] = p.scale[i]; s_shift[i] = p.shift[i]; }
   tc_fence_before();
   __syncthreads();
@@ -234,9 +235,11 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
       __syncwarp();
     }
   } else {
-    // ===================================================================== epilogue (warps 2..5)
+    // ===================================================================== epilogue (warps 2..9)
+    // two warps per TMEM lane quarter; the pair interleaves the 16-column chunks of the accumulator
     const int quarter = warp & 3;
     const int ew = warp - 2;
+    const int cgrp = ew >> 2;
     const int row = quarter * 32 + lane;
     const int hl = row >> 3, wl = row & 7;
     const int mycol = (lane >> 1) & 15;
@@ -268,7 +271,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(slot * p.cout);
       const size_t vox = (static_cast<size_t>(d) * p.H + h) * p.W + w;
-      for (int c0 = 0; c0 < p.cout; c0 += 16) {
+      for (int c0 = cgrp * 16; c0 < p.cout; c0 += 32) {
         uint32_t r[16];
         tmem_ld16(taddr + c0, r);
         tmem_ld_wait();

@@ -8,7 +8,8 @@
 // Persistent: grid = min(#tiles, #SMs); every CTA walks tiles blockIdx.x + i*gridDim.x.  Tiles are
 // 128 x 128 x 64 (TMA 2-D boxes, 128-byte swizzle, 6-stage mbarrier ring that runs ahead across tiles);
 // two 128-column TMEM accumulators so the epilogue of tile i overlaps the main loop of tile i+1.
-// Warp roles (192 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2..5 epilogue.
+// Warp roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2..9 epilogue
+// (two warps per TMEM lane quarter, each draining 64 of the 128 accumulator columns).
 // Epilogue options: +bias[n], +rowvec[m % period][n] (position embeddings), GELU(erf), *alpha,
 // +residual (fp32, may alias out_f32), fp32 / fp16 stores, deterministic split-K partials, the
 // q/k/v^T head scatter, or the deconv scatter into a c8 tensor.
@@ -42,7 +43,8 @@ struct GemmParams {
   int* err_flag;
 };
 
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;        // producer + MMA + 8 epilogue warps (2 per TMEM lane quarter)
+constexpr int kGemmEpiWarps = 8;
 constexpr int BM = 128, BN = 128, BK = 64;
 constexpr int kGemmStages = 6;
 constexpr uint32_t kStageA = BM * BK * 2, kStageB = BN * BK * 2, kStage = kStageA + kStageB;
@@ -79,7 +81,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
     for (int i = 0; i < kGemmStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kGemmEpiWarps); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<2 * BN>(&tmem_base_smem);
@@ -152,8 +154,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       __syncwarp();
     }
   } else {
-    // ===================================================================== epilogue (warps 2..5)
+    // ===================================================================== epilogue (warps 2..9)
     const int quarter = warp & 3;
+    const int chalf = (warp - 2) >> 2;                      // which 64-column half of the accumulator
+    const bool vecN = (p.N % 16) == 0;
     int iter = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++iter) {
       const GemmTile t = gemm_tile(p, tile);
@@ -164,8 +168,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(slot * BN);
       const bool lead = (t.sk == 0);
-      const float* rv = (p.rowvec && m < p.M) ? p.rowvec + static_cast<size_t>(m % p.row_period) * p.N : nullptr;
-      // deconv / qkv row decomposition hoisted out of the column loop
+      const float* rv = (p.rowvec && lead && m < p.M) ? p.rowvec + static_cast<size_t>(m % p.row_period) * p.N : nullptr;
+      const float* bias = lead ? p.bias : nullptr;
       int rb = 0, rt = 0;
       size_t dc_vox = 0;
       if (p.mode == 1) { rb = m / p.T; rt = m % p.T; }
@@ -176,96 +180,136 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int w = v % p.Wg, h = (v / p.Wg) % p.Hg, d = v / (p.Wg * p.Hg);
         dc_vox = (static_cast<size_t>(2 * d) * (2 * p.Hg) + 2 * h) * (2 * p.Wg) + 2 * w;
       }
-      for (int c0 = 0; c0 < BN; c0 += 16) {
-        if (n0 + c0 >= p.N) break;                         // warp-uniform
-        uint32_t r[16];
-        tmem_ld16(taddr + c0, r);
+      const size_t boff = p.c_batch_period > 0
+          ? static_cast<size_t>(t.bz / p.c_batch_period) * p.c_batch_stride + static_cast<size_t>(t.bz % p.c_batch_period) * p.c_batch_stride2
+          : static_cast<size_t>(t.bz) * p.c_batch_stride;
+      const size_t row_base = boff + static_cast<size_t>(t.sk) * p.split_stride + static_cast<size_t>(m) * p.ldc;
+#pragma unroll 1
+      for (int cc = 0; cc < 4; cc += 2) {
+        // two 16-column chunks in flight per iteration (ILP across the TMEM loads)
+        const int c0 = chalf * 64 + cc * 16;
+        if (n0 + c0 >= p.N) break;                          // warp-uniform
+        uint32_t r[2][16];
+        tmem_ld16(taddr + c0, r[0]);
+        const bool second = (n0 + c0 + 16 < p.N);
+        if (second) tmem_ld16(taddr + c0 + 16, r[1]);
         tmem_ld_wait();
         if (m >= p.M) continue;
-        float v[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int n = n0 + c0 + j;
-          float x = __uint_as_float(r[j]) * p.alpha;
-          if (n < p.N) {
-            if (lead && p.bias) x += __ldg(&p.bias[n]);
-            if (lead && rv) x += __ldg(&rv[n]);
-            if (p.act) x = act_apply(x, p.act);
-          }
-          v[j] = x;
-        }
-        if (p.mode == 1) {
-          const int hidden = p.heads * p.hd;
-          const int n = n0 + c0;                            // 16 | hd, so the 16 columns share (which, head)
-          const int which = n / hidden, rem = n % hidden;
-          const int hh = rem / p.hd, dd = rem % p.hd;
-          const size_t bh = static_cast<size_t>(rb) * p.heads + hh;
-          if (which == 2) {
+        for (int u = 0; u < 2; ++u) {
+          if (u == 1 && !second) break;
+          const int cu = c0 + u * 16;
+          const int n = n0 + cu;
+          const bool full = vecN || (n + 16 <= p.N);
+          float v[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) p.vt[(bh * p.hd + dd + j) * p.T + rt] = __float2half_rn(v[j]);
-          } else {
-            __half* dst = (which == 0 ? p.q : p.kk) + (bh * p.T + rt) * p.hd + dd;
-            const float sc = which == 0 ? p.q_scale : 1.f;
-            __align__(16) __half h[16];
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[u][j]) * p.alpha;
+          if (full) {
+            if (bias) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) h[j] = __float2half_rn(v[j] * sc);
-            *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(&h[0]);
-            *reinterpret_cast<uint4*>(dst + 8) = *reinterpret_cast<const uint4*>(&h[8]);
-          }
-          continue;
-        }
-        if (p.mode == 2) {
-          const int n = n0 + c0;                            // 16 | cout, so the 16 columns share the parity
-          const int qp = n / p.cout, co = n % p.cout;
-          const size_t vo = dc_vox + (static_cast<size_t>(qp >> 2) * (2 * p.Hg) + ((qp >> 1) & 1)) * (2 * p.Wg) + (qp & 1);
-          const size_t vox_out = static_cast<size_t>(8) * p.Dg * p.Hg * p.Wg;
-#pragma unroll
-          for (int b = 0; b < 2; ++b) {
-            const size_t off = ((static_cast<size_t>(rb) * p.dc_cb_total + p.dc_cb_off + (co >> 3) + b) * vox_out + vo) * 8;
-            __align__(16) __half hi[8];
-            __align__(16) __half lo[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              hi[j] = __float2half_rn(v[b * 8 + j]);
-              lo[j] = __float2half_rn(v[b * 8 + j] - __half2float(hi[j]));
+              for (int j = 0; j < 16; j += 4) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n + j));
+                v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+              }
             }
-            *reinterpret_cast<uint4*>(p.dc_hi + off) = *reinterpret_cast<const uint4*>(hi);
-            if (p.dc_lo) *reinterpret_cast<uint4*>(p.dc_lo + off) = *reinterpret_cast<const uint4*>(lo);
-          }
-          continue;
-        }
-        const size_t boff = p.c_batch_period > 0
-            ? static_cast<size_t>(t.bz / p.c_batch_period) * p.c_batch_stride + static_cast<size_t>(t.bz % p.c_batch_period) * p.c_batch_stride2
-            : static_cast<size_t>(t.bz) * p.c_batch_stride;
-        const size_t base = boff + static_cast<size_t>(t.sk) * p.split_stride + static_cast<size_t>(m) * p.ldc + n0 + c0;
-        const bool full = (n0 + c0 + 16 <= p.N);
-        if (p.resid && lead) {
+            if (rv) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (full || n0 + c0 + j < p.N) v[j] += p.resid[base + j];
-        }
-        if (p.out_f32) {
-          if (full && (p.ldc % 4 == 0)) {
-#pragma unroll
-            for (int j = 0; j < 16; j += 4)
-              *reinterpret_cast<float4*>(&p.out_f32[base + j]) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              for (int j = 0; j < 16; j += 4) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(rv + n + j));
+                v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+              }
+            }
           } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (n0 + c0 + j < p.N) p.out_f32[base + j] = v[j];
+            for (int j = 0; j < 16; ++j) {
+              if (n + j < p.N) {
+                if (bias) v[j] += __ldg(&bias[n + j]);
+                if (rv) v[j] += __ldg(&rv[n + j]);
+              }
+            }
           }
-        }
-        if (p.out_f16) {
-          if (full && (p.ldc % 8 == 0)) {
-            __align__(16) __half h[16];
+          if (p.act == ACT_GELU) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) h[j] = __float2half_rn(v[j]);
-            *reinterpret_cast<uint4*>(&p.out_f16[base]) = *reinterpret_cast<const uint4*>(&h[0]);
-            *reinterpret_cast<uint4*>(&p.out_f16[base + 8]) = *reinterpret_cast<const uint4*>(&h[8]);
-          } else {
+            for (int j = 0; j < 16; ++j) v[j] = 0.5f * v[j] * (1.f + erff(v[j] * 0.70710678118654752f));
+          } else if (p.act) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (n0 + c0 + j < p.N) p.out_f16[base + j] = __float2half_rn(v[j]);
+            for (int j = 0; j < 16; ++j) v[j] = act_apply(v[j], p.act);
+          }
+          if (p.mode == 1) {
+            const int hidden = p.heads * p.hd;                // 16 | hd, so the 16 columns share (which, head)
+            const int which = n / hidden, rem = n % hidden;
+            const int hh = rem / p.hd, dd = rem % p.hd;
+            const size_t bh = static_cast<size_t>(rb) * p.heads + hh;
+            if (which == 2) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) p.vt[(bh * p.hd + dd + j) * p.T + rt] = __float2half_rn(v[j]);
+            } else {
+              __half* dst = (which == 0 ? p.q : p.kk) + (bh * p.T + rt) * p.hd + dd;
+              const float sc = which == 0 ? p.q_scale : 1.f;
+              __align__(16) __half h[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) h[j] = __float2half_rn(v[j] * sc);
+              *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(&h[0]);
+              *reinterpret_cast<uint4*>(dst + 8) = *reinterpret_cast<const uint4*>(&h[8]);
+            }
+            continue;
+          }
+          if (p.mode == 2) {
+            const int qp = n / p.cout, co = n % p.cout;       // 16 | cout, so the 16 columns share the parity
+            const size_t vo = dc_vox + (static_cast<size_t>(qp >> 2) * (2 * p.Hg) + ((qp >> 1) & 1)) * (2 * p.Wg) + (qp & 1);
+            const size_t vox_out = static_cast<size_t>(8) * p.Dg * p.Hg * p.Wg;
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+              const size_t off = ((static_cast<size_t>(rb) * p.dc_cb_total + p.dc_cb_off + (co >> 3) + b) * vox_out + vo) * 8;
+              __align__(16) __half hi[8];
+              __align__(16) __half lo[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                hi[j] = __float2half_rn(v[b * 8 + j]);
+                lo[j] = __float2half_rn(v[b * 8 + j] - __half2float(hi[j]));
+              }
+              *reinterpret_cast<uint4*>(p.dc_hi + off) = *reinterpret_cast<const uint4*>(hi);
+              if (p.dc_lo) *reinterpret_cast<uint4*>(p.dc_lo + off) = *reinterpret_cast<const uint4*>(lo);
+            }
+            continue;
+          }
+          const size_t base = row_base + n;
+          if (p.resid && lead) {
+            if (full && (p.ldc % 4 == 0)) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) {
+                const float4 r4 = *reinterpret_cast<const float4*>(&p.resid[base + j]);
+                v[j] += r4.x; v[j + 1] += r4.y; v[j + 2] += r4.z; v[j + 3] += r4.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (n + j < p.N) v[j] += p.resid[base + j];
+            }
+          }
+          if (p.out_f32) {
+            if (full && (p.ldc % 4 == 0)) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4)
+                *reinterpret_cast<float4*>(&p.out_f32[base + j]) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (n + j < p.N) p.out_f32[base + j] = v[j];
+            }
+          }
+          if (p.out_f16) {
+            if (full && (p.ldc % 8 == 0)) {
+              __align__(16) __half h[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) h[j] = __float2half_rn(v[j]);
+              *reinterpret_cast<uint4*>(&p.out_f16[base]) = *reinterpret_cast<const uint4*>(&h[0]);
+              *reinterpret_cast<uint4*>(&p.out_f16[base + 8]) = *reinterpret_cast<const uint4*>(&h[8]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (n + j < p.N) p.out_f16[base + j] = __float2half_rn(v[j]);
+            }
           }
         }
       }
