@@ -60,11 +60,25 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded spin: a protocol bug must surface as an error flag, never as a hung GPU box.
+// mbar_wait      : latency-critical waiter (the MMA-issuing warp) — polls back to back.
+// mbar_wait_relaxed : producer / epilogue warps — sleep between polls so their spin loops do not take
+//                  issue slots from the MMA warp sharing the SM sub-partition (ncu: 72 % of all warp
+//                  samples of the stacked conv kernel sat in these loops).
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* err_flag) {
 #pragma unroll 1
   for (uint32_t it = 0; it < (1u << 22); ++it) {
     if (mbar_try_wait(bar, parity)) return true;
     if (it > 4096) __nanosleep(64);
+  }
+  if (err_flag) atomicExch(err_flag, 1);
+  return false;
+}
+__device__ __forceinline__ bool mbar_wait_relaxed(uint64_t* bar, uint32_t parity, int* err_flag) {
+  if (mbar_try_wait(bar, parity)) return true;
+#pragma unroll 1
+  for (uint32_t it = 0; it < (1u << 22); ++it) {
+    __nanosleep(it < 64 ? 40 : 200);
+    if (mbar_try_wait(bar, parity)) return true;
   }
   if (err_flag) atomicExch(err_flag, 1);
   return false;

@@ -16,6 +16,8 @@
 //   free_bar[slot]  epilogue -> MMA    (8 epilogue warps have drained it; next owner may start with acc=0)
 // The first MMA that touches a new plane uses accumulate=0 on that plane's group only (the window is
 // split into an old and a new part for that one tap), so TMEM never needs zeroing.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "dose_b200.h"
 
@@ -41,6 +43,7 @@ struct StackParams {
   int cb_total_out, cb_out_off;
   double* stats;
   int* err_flag;
+  int debug;                // timing experiments only (DP_STACK_DEBUG): 1 = skip weight copies, 2 = skip patch loads
   uint8_t chunk_cb[96];
 };
 
@@ -150,24 +153,30 @@ conv3d_stack_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_co
       const Item it = decode_item<KS>(p, item);
       for (int dz = it.z0; dz <= it.z1; ++dz) {
         for (int c = 0; c < p.n_chunks; ++c) {
-          if (!mbar_wait(&a_empty[ia], pa ^ 1, p.err_flag)) goto teardown;
+          if (!mbar_wait_relaxed(&a_empty[ia], pa ^ 1, p.err_flag)) goto teardown;
           if (elect_one()) {
-            mbar_arrive_expect_tx(&a_full[ia], p.a_bytes);
-            tma_load_5d(smem + static_cast<size_t>(ia) * p.a_stride, &tmap_in, &a_full[ia], 0, it.w0 - pad, it.h0 - pad, dz,
-                        it.n * p.cb_total_in + p.chunk_cb[c]);
+            if (p.debug & 2) {
+              mbar_arrive(&a_full[ia]);
+            } else {
+              mbar_arrive_expect_tx(&a_full[ia], p.a_bytes);
+              tma_load_5d(smem + static_cast<size_t>(ia) * p.a_stride, &tmap_in, &a_full[ia], 0, it.w0 - pad, it.h0 - pad, dz,
+                          it.n * p.cb_total_in + p.chunk_cb[c]);
+            }
           }
           __syncwarp();
           if (++ia == p.a_stages) { ia = 0; pa ^= 1; }
           for (int g = 0; g < p.n_khg; ++g) {
             const int kh0 = g * p.khs;
             const int cnt = min(p.khs, KS - kh0);
-            if (!mbar_wait(&b_empty[ib], pb ^ 1, p.err_flag)) goto teardown;
+            if (!mbar_wait_relaxed(&b_empty[ib], pb ^ 1, p.err_flag)) goto teardown;
             if (elect_one()) {
               const uint32_t bytes = static_cast<uint32_t>(cnt * KS) * tap_b_bytes;
+              if (p.debug & 1) { mbar_arrive(&b_full[ib]); } else {
               mbar_arrive_expect_tx(&b_full[ib], bytes);
               bulk_load_1d(smem + p.b_off + static_cast<size_t>(ib) * p.b_stride,
                            p.wpack + static_cast<size_t>(c) * chunk_w_halfs + static_cast<size_t>(kh0) * KS * (tap_b_bytes / 2),
                            bytes, &b_full[ib]);
+              }
             }
             __syncwarp();
             if (++ib == p.b_stages) { ib = 0; pb ^= 1; }
@@ -324,7 +333,7 @@ conv3d_stack_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_co
       const int h = it.h0 + hl;
       for (int d = it.d0; d < it.d1; ++d, ++pc) {
         const int slot = static_cast<int>(pc & static_cast<uint32_t>(G - 1));
-        if (!mbar_wait(&done_bar[slot], (pc >> (__ffs(G) - 1)) & 1, p.err_flag)) goto teardown;
+        if (!mbar_wait_relaxed(&done_bar[slot], (pc >> (__ffs(G) - 1)) & 1, p.err_flag)) goto teardown;
         tc_fence_after();
         for (int t = tgrp; t < it.ntile; t += 2) {
           const int w = it.w0 + t * 8 + wl;
@@ -461,6 +470,7 @@ extern "C" int dp_conv3d_stack(const void* in_c8, int cb_total_in, const uint8_t
   p.scale = scale; p.shift = shift; p.relu = relu;
   p.out_f32 = out_f32; p.out_hi = static_cast<__half*>(out_hi); p.out_lo = static_cast<__half*>(out_lo);
   p.cb_total_out = cb_total_out; p.cb_out_off = cb_out_off; p.stats = stats; p.err_flag = err_flag;
+  { const char* dbg = getenv("DP_STACK_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
 
   CUtensorMap tmap;
   const uint64_t dims[5] = {8, static_cast<uint64_t>(W), static_cast<uint64_t>(H), static_cast<uint64_t>(D),

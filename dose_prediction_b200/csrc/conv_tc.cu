@@ -163,7 +163,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
           for (int g = 0; g < p.n_khg; ++g) {
             const int kh0 = g * p.kh_s;
             const int cnt = min(p.kh_s, KS - kh0);
-            if (!mbar_wait(&empty_bar[stage], phase ^ 1, p.err_flag)) goto teardown;
+            if (!mbar_wait_relaxed(&empty_bar[stage], phase ^ 1, p.err_flag)) goto teardown;
             if (elect_one()) {
               uint8_t* sa = smem + static_cast<size_t>(stage) * p.stage_bytes;
               uint8_t* sb = sa + p.a_bytes_al;
@@ -267,7 +267,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
       const int h = th * 16 + hl, w = tw * 8 + wl;
       const bool valid = (h < p.H) && (w < p.W);
       const int slot = iter & 1;
-      if (!mbar_wait(&tmem_full_bar[slot], (iter >> 1) & 1, p.err_flag)) goto teardown;
+      if (!mbar_wait_relaxed(&tmem_full_bar[slot], (iter >> 1) & 1, p.err_flag)) goto teardown;
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(slot * p.cout);
       const size_t vox = (static_cast<size_t>(d) * p.H + h) * p.W + w;

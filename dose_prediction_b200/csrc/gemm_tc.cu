@@ -98,7 +98,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const GemmTile t = gemm_tile(p, tile);
       const int a_row = t.bz * p.a_batch_rows + t.m0, b_row = t.bz * p.b_batch_rows + t.n0;
       for (int kb = t.kb0; kb < t.kb1; ++kb) {
-        if (!mbar_wait(&empty_bar[stage], phase ^ 1, p.err_flag)) goto teardown;
+        if (!mbar_wait_relaxed(&empty_bar[stage], phase ^ 1, p.err_flag)) goto teardown;
         if (elect_one()) {
           uint8_t* sa = smem + static_cast<size_t>(stage) * kStage;
           mbar_arrive_expect_tx(&full_bar[stage], kStage);
@@ -164,7 +164,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int slot = iter & 1;
       const int m = t.m0 + quarter * 32 + lane;
       const int n0 = t.n0;
-      if (!mbar_wait(&acc_full[slot], (iter >> 1) & 1, p.err_flag)) goto teardown;
+      if (!mbar_wait_relaxed(&acc_full[slot], (iter >> 1) & 1, p.err_flag)) goto teardown;
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(slot * BN);
       const bool lead = (t.sk == 0);
