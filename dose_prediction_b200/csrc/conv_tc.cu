@@ -49,7 +49,8 @@ struct ConvTcParams {
   double* stats;
   int* err_flag;
   uint32_t tmem_cols;
-  uint8_t chunk_cb[96];
+  uint8_t chunk_cb[192];
+  uint32_t tap_mask[192];    // per K-chunk bit mask over the k^3 taps (bit (kd*k+kh)*k+kw); zero bits are skipped
 };
 
 constexpr int kConvThreads = 320;       // producer + MMA + 8 epilogue warps (2 per TMEM lane quarter)
@@ -211,13 +212,17 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
             if (elect_one()) {
               const uint32_t sa16 = smem_u32(smem + static_cast<size_t>(stage) * p.stage_bytes) >> 4;
               uint32_t b16 = sa16 + (p.a_bytes_al >> 4);
+              const uint32_t mask = p.tap_mask[c];
               for (int kdl = 0; kdl < p.kd_s; ++kdl) {
                 for (int khl = 0; khl < cnt; ++khl) {
                   uint32_t a16 = sa16 + static_cast<uint32_t>((kdl * p.PHs + khl * p.dil) * p.PW);
+                  const int tap0 = ((kdg * p.kd_s + kdl) * KS + g * p.kh_s + khl) * KS;
 #pragma unroll
                   for (int kw = 0; kw < KS; ++kw) {
-                    umma_f16_ss_split(tmem_d, a_lo_c | (a16 & 0x3FFFu), a_hi, b_lo_c | (b16 & 0x3FFFu), b_hi, idesc, accumulate);
-                    accumulate = 1;
+                    if (KS > 3 || ((mask >> (tap0 + kw)) & 1u)) {
+                      umma_f16_ss_split(tmem_d, a_lo_c | (a16 & 0x3FFFu), a_hi, b_lo_c | (b16 & 0x3FFFu), b_hi, idesc, accumulate);
+                      accumulate = 1;
+                    }
                     a16 += static_cast<uint32_t>(p.dil);
                     b16 += tap_b16;
                   }
@@ -226,7 +231,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
               umma_commit(&empty_bar[stage]);
             }
             __syncwarp();
-            accumulate = 1;
+            accumulate = __any_sync(0xffffffffu, accumulate != 0) ? 1u : 0u;   // only the elected lane issued
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
         }
@@ -340,17 +345,18 @@ extern "C" int dp_conv3d_tc(const void* in_c8, int cb_total_in, const uint8_t* c
                             const void* wpack, int N, int D, int H, int W, int cout, int k, int dil,
                             const float* scale, const float* shift, int relu, float* out_f32, void* out_hi,
                             void* out_lo, int cb_total_out, int cb_out_off, double* stats, int* err_flag,
-                            int max_ctas, cudaStream_t stream) {
+                            int max_ctas, const uint32_t* tap_mask, cudaStream_t stream) {
   using namespace dp;
   DP_REQUIRE(cout % 16 == 0 && cout >= 16 && cout <= 256, "dp_conv3d_tc: C_out=%d must be a multiple of 16 in [16,256]", cout);
   DP_REQUIRE(k >= 1 && k <= 7 && (k & 1), "dp_conv3d_tc: kernel size %d unsupported", k);
-  DP_REQUIRE(n_chunks >= 1 && n_chunks <= 96, "dp_conv3d_tc: n_chunks=%d out of range", n_chunks);
+  DP_REQUIRE(n_chunks >= 1 && n_chunks <= 192, "dp_conv3d_tc: n_chunks=%d out of range", n_chunks);
   DP_REQUIRE(out_f32 != nullptr || out_hi != nullptr, "dp_conv3d_tc: no output tensor given");
   ConvTcParams p{};
   p.N = N; p.D = D; p.H = H; p.W = W;
   p.k = k; p.dil = dil; p.pad = dil * (k - 1) / 2;
   p.n_chunks = n_chunks; p.cb_total_in = cb_total_in; p.cout = cout;
-  for (int i = 0; i < n_chunks; ++i) p.chunk_cb[i] = chunk_cb[i];
+  for (int i = 0; i < n_chunks; ++i) { p.chunk_cb[i] = chunk_cb[i]; p.tap_mask[i] = tap_mask ? tap_mask[i] : 0xFFFFFFFFu; }
+  DP_REQUIRE(tap_mask == nullptr || k <= 3, "dp_conv3d_tc: tap masks are supported for k <= 3 only");
   p.PW = 8 + (k - 1) * dil;
   // stage sizing: as many kh rows per stage as fit ~56 KB, then as many stages as fit ~200 KB
   const int tap_b = 32 * cout;

@@ -55,10 +55,26 @@ __device__ __forceinline__ void finalize_stats(const double* stats, size_t idx, 
   double var = ss * inv_count - m * m;
   if (var < 0.0) var = 0.0;
   mean = static_cast<float>(m);
-  rstd = static_cast<float>(1.0 / sqrt(var + 1e-5));
+  rstd = rsqrtf(static_cast<float>(var) + 1e-5f);     // variance itself is formed in fp64 (cancellation)
 }
 
 // Block-wide reduction of 8 channel sums + 8 sums of squares, then one fp64 atomic per channel.
+__device__ __forceinline__ void block_accumulate_sums(const float (&a1)[8], const float (&a2)[8], double* stats, size_t idx0) {
+  __shared__ float red[2][8][8];  // [sum|sq][warp][channel]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float s1 = warp_sum(a1[j]), s2 = warp_sum(a2[j]);
+    if (lane == 0) { red[0][warp][j] = s1; red[1][warp][j] = s2; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    const int which = threadIdx.x >> 3, j = threadIdx.x & 7;
+    float t = 0.f;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) t += red[which][w][j];
+    atomicAdd(&stats[(idx0 + j) * 2 + which], static_cast<double>(t));
+  }
+}
 __device__ __forceinline__ void block_accumulate_stats(const float (&y)[8], bool valid, double* stats, size_t idx0) {
   __shared__ float red[2][8][8];  // [sum|sq][warp][channel]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -121,12 +137,14 @@ struct NormActParams {
   __half* out_hi; __half* out_lo; int out_cb_total, out_cb_off;
   double* stats_out;              // statistics of the produced tensor (chained InstanceNorm), or null
   int C, ncb; long long vox;
+  // optional second copy in space-to-depth layout: channel block (parity*ncb + cb) of a half-resolution
+  // tensor, parity = (d&1)*4 + (h&1)*2 + (w&1); feeds the stride-2 convs as sparse stride-1 convs
+  __half* s2d_hi; __half* s2d_lo; int s2d_cb_total, s2d_cb_off, D, H, W;
 };
 
+constexpr int NA_IT = 4;      // voxel chunks per block: amortises the statistics prologue
 __global__ void __launch_bounds__(256) norm_act_kernel(const NormActParams p) {
-  const long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   const int cb = blockIdx.y % p.ncb, n = blockIdx.y / p.ncb;
-  const bool valid = v < p.vox;
   const double inv = 1.0 / static_cast<double>(p.vox);
   __shared__ float s_mean[2][8], s_rstd[2][8];
   if (threadIdx.x < 16) {
@@ -138,6 +156,13 @@ __global__ void __launch_bounds__(256) norm_act_kernel(const NormActParams p) {
     s_rstd[which][threadIdx.x & 7] = r;
   }
   __syncthreads();
+  float a1[8], a2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { a1[j] = 0.f; a2[j] = 0.f; }
+#pragma unroll 1
+  for (int it = 0; it < NA_IT; ++it) {
+  const long long v = (blockIdx.x * static_cast<long long>(NA_IT) + it) * blockDim.x + threadIdx.x;
+  const bool valid = v < p.vox;
   float y[8];
   if (valid) {
     const size_t in_off = ((static_cast<size_t>(n) * p.in_cb_total + p.in_cb_off + cb) * p.vox + v) * 8;
@@ -168,8 +193,18 @@ __global__ void __launch_bounds__(256) norm_act_kernel(const NormActParams p) {
     }
     if (p.out_hi)
       store8(p.out_hi, p.out_lo, ((static_cast<size_t>(n) * p.out_cb_total + p.out_cb_off + cb) * p.vox + v) * 8, y);
+    if (p.s2d_hi) {
+      const int w = static_cast<int>(v % p.W), h = static_cast<int>((v / p.W) % p.H), d = static_cast<int>(v / (static_cast<long long>(p.W) * p.H));
+      const int parity = ((d & 1) << 2) | ((h & 1) << 1) | (w & 1);
+      const size_t vh = (static_cast<size_t>(d >> 1) * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1);
+      store8(p.s2d_hi, p.s2d_lo,
+             ((static_cast<size_t>(n) * p.s2d_cb_total + p.s2d_cb_off + parity * p.ncb + cb) * (p.vox >> 3) + vh) * 8, y);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { a1[j] += y[j]; a2[j] = fmaf(y[j], y[j], a2[j]); }
   }
-  if (p.stats_out) block_accumulate_stats(y, valid, p.stats_out, static_cast<size_t>(n) * p.C + cb * 8);
+  }
+  if (p.stats_out) block_accumulate_sums(a1, a2, p.stats_out, static_cast<size_t>(n) * p.C + cb * 8);
 }
 
 // ------------------------------------------------------------------ 1x1x1 convolution, normalise-on-load, <=3 sources
@@ -641,8 +676,11 @@ extern "C" int dp_norm_act(const float* raw_f32, const void* raw_hi, const void*
                            const double* stats, const float* gamma, const float* beta, int act, const void* res_hi,
                            const void* res_lo, const float* res_raw, const double* res_stats, int res_cb_total,
                            int res_cb_off, int act_after_res, void* out_hi, void* out_lo, int out_cb_total,
-                           int out_cb_off, double* stats_out, int N, int C, long long vox, cudaStream_t stream) {
+                           int out_cb_off, double* stats_out, int N, int C, long long vox, void* s2d_hi, void* s2d_lo,
+                           int s2d_cb_total, int s2d_cb_off, int D, int H, int W, cudaStream_t stream) {
   DP_REQUIRE(raw_f32 != nullptr || raw_hi != nullptr, "dp_norm_act: no input");
+  DP_REQUIRE(s2d_hi == nullptr || (D % 2 == 0 && H % 2 == 0 && W % 2 == 0 && static_cast<long long>(D) * H * W == vox && C % 8 == 0),
+             "dp_norm_act: space-to-depth output needs even dims and C %% 8 == 0");
   NormActParams p{};
   p.raw_f32 = raw_f32; p.raw_hi = static_cast<const __half*>(raw_hi); p.raw_lo = static_cast<const __half*>(raw_lo);
   p.in_cb_total = in_cb_total; p.in_cb_off = in_cb_off; p.stats = stats; p.gamma = gamma; p.beta = beta; p.act = act;
@@ -650,7 +688,9 @@ extern "C" int dp_norm_act(const float* raw_f32, const void* raw_hi, const void*
   p.res_stats = res_stats; p.res_cb_total = res_cb_total; p.res_cb_off = res_cb_off; p.act_after_res = act_after_res;
   p.out_hi = static_cast<__half*>(out_hi); p.out_lo = static_cast<__half*>(out_lo); p.out_cb_total = out_cb_total;
   p.out_cb_off = out_cb_off; p.stats_out = stats_out; p.C = C; p.ncb = (C + 7) / 8; p.vox = vox;
-  dim3 grid(blocks_for(vox, 256), N * p.ncb);
+  p.s2d_hi = static_cast<__half*>(s2d_hi); p.s2d_lo = static_cast<__half*>(s2d_lo); p.s2d_cb_total = s2d_cb_total;
+  p.s2d_cb_off = s2d_cb_off; p.D = D; p.H = H > 0 ? H : 1; p.W = W > 0 ? W : 1;
+  dim3 grid(blocks_for(vox, 256 * NA_IT), N * p.ncb);
   norm_act_kernel<<<grid, 256, 0, stream>>>(p);
   DP_CHECK(cudaGetLastError());
   return 0;

@@ -333,11 +333,12 @@ class Plan:
     def unpack(self, a, dst):
         self.add("dp_unpack_c8", a.hi_ptr, a.lo_ptr, a.cb_total, a.cb_off, a.N, a.C, a.vox, dst.data_ptr())
 
-    def conv_tc(self, parts, weight, k, dil, mode, scale, shift, relu, out_raw=None, out_act=None, stats=None):
+    def conv_tc(self, parts, weight, k, dil, mode, scale, shift, relu, out_raw=None, out_act=None, stats=None,
+                tap_mask_fn=None):
         a0 = parts[0]
         D, H, W = a0.dims
         Co = weight.shape[0]
-        stacked = STACKED_CONV and dil == 1 and k in (3, 7) and Co in (16, 32)
+        stacked = STACKED_CONV and dil == 1 and k in (3, 7) and Co in (16, 32) and tap_mask_fn is None
         wp, chunks, nch = self.pack_conv_tc(weight, parts, mode, stacked=stacked)
         if out_raw is not None:
             of32, ohi, olo, cbt, cbo = out_raw.t.data_ptr(), None, None, out_raw.cb_total, 0
@@ -352,10 +353,14 @@ class Plan:
                      scale.data_ptr(), shift.data_ptr(), int(relu), of32, ohi, olo, cbt, cbo,
                      st.data_ptr() if st is not None else None, self.err.data_ptr(), 0, STACK_TILES)
             return
-        self.count_flops("dp_conv3d_tc", flops)
+        masks = None
+        if tap_mask_fn is not None:
+            masks = (ctypes.c_uint32 * nch)(*tap_mask_fn(nch))
+            self.keep.append(masks)
+        self.count_flops("dp_conv3d_tc", flops if tap_mask_fn is None else tap_mask_fn.flops)
         self.add("dp_conv3d_tc", a0.buf.data_ptr(), a0.cb_total, chunks, nch, wp.data_ptr(), a0.N, D, H, W, Co, k, dil,
                  scale.data_ptr(), shift.data_ptr(), int(relu), of32, ohi, olo, cbt, cbo,
-                 st.data_ptr() if st is not None else None, self.err.data_ptr(), 0)
+                 st.data_ptr() if st is not None else None, self.err.data_ptr(), 0, masks)
 
     def conv_direct(self, a, weight, k, stride, dil, scale, shift, relu, out_raw=None, out_act=None, stats=None):
         """generic direct conv on one Act whose C is a multiple of 8 (stride-2 convs of net_A)."""
@@ -374,7 +379,7 @@ class Plan:
                  st.data_ptr() if st is not None else None)
 
     def norm_act(self, src, out, stats=None, gamma=None, beta=None, act=None, res=None, res_stats=None,
-                 act_after_res=None, stats_out=None):
+                 act_after_res=None, stats_out=None, s2d=None):
         """out = act_after(act(IN(src)*gamma+beta) [+ IN?(res)]); src: Raw or Act; res: Act or Raw."""
         if isinstance(src, Raw):
             rf, rh, rl, icb, ioff, C = src.t.data_ptr(), None, None, src.cb_total, 0, src.C
@@ -399,7 +404,10 @@ class Plan:
         self.add("dp_norm_act", rf, rh, rl, icb, ioff, stats.data_ptr() if stats is not None else None,
                  gamma.data_ptr() if gamma is not None else None, beta.data_ptr() if beta is not None else None,
                  ACT_ID[act], eh, el, er, es, ecb, eoff, ACT_ID[act_after_res], oh, ol, ocb, ooff,
-                 stats_out.data_ptr() if stats_out is not None else None, N, C, vox)
+                 stats_out.data_ptr() if stats_out is not None else None, N, C, vox,
+                 s2d.hi_ptr if s2d is not None else None, s2d.lo_ptr if s2d is not None else None,
+                 s2d.cb_total if s2d is not None else 0, s2d.cb_off if s2d is not None else 0,
+                 *(tuple(2 * d for d in s2d.dims) if s2d is not None else (0, 0, 0)))
 
     def pointwise(self, srcs, weight, bias, out_raw=None, out_act=None, out_planar=None, out_act_fn=None):
         """1x1x1 conv over cat(srcs); srcs: list of (Act|Raw, stats|None, act|None)."""

@@ -273,20 +273,59 @@ PREC_NET_B = Precision("p1", "p1", False)     # fp16 operands everywhere
 PREC_SEG = Precision("p3", "p1", True)        # seg: fp16 on 7^3 convs and the ViT, ~22-bit elsewhere
 
 
-def _in_conv_norm(P, parts, conv, norm, k, mode, out, act="relu", stride=1, N=None, dims=None):
-    """conv(+bias) -> InstanceNorm(affine?) -> act, for c3d SingleConv/UpConv."""
+_S2D_TAPS = {0: ((1, 1),), 1: ((0, 0), (1, 2))}     # input parity -> ((tap of the 3^3 stride-1 conv, original tap), ...)
+
+
+def _s2d_weight(w):
+    """3^3 stride-2 pad-1 conv over x  ==  sparse 3^3 stride-1 conv over space_to_depth(x) (8*C channels):
+    out[o] = sum_k W[k] x[2o+k-1]; input 2o+k-1 has parity (k+1)&1 and half-resolution index o + (k-1)>>1."""
+    Co, C = w.shape[0], w.shape[1]
+    wp = torch.zeros((Co, 8, C, 3, 3, 3), dtype=torch.float32, device=w.device)
+    masks = []
+    for cls in range(8):
+        pd, ph, pw = (cls >> 2) & 1, (cls >> 1) & 1, cls & 1
+        m = 0
+        for td, kd in _S2D_TAPS[pd]:
+            for th, kh in _S2D_TAPS[ph]:
+                for tw, kw in _S2D_TAPS[pw]:
+                    wp[:, cls, :, td, th, tw] = w[:, :, kd, kh, kw]
+                    m |= 1 << ((td * 3 + th) * 3 + tw)
+        masks.append(m)
+    return wp.view(Co, 8 * C, 3, 3, 3), masks
+
+
+class _S2DMask:
+    """per-K-chunk tap masks for the sparse space-to-depth conv (chunks are 16 channels, C >= 16 per parity)."""
+
+    def __init__(self, C, class_masks, flops):
+        self.C, self.class_masks, self.flops = C, class_masks, flops
+
+    def __call__(self, nch):
+        per_term = 8 * self.C // 16
+        return [self.class_masks[((i % per_term) * 16) // self.C] for i in range(nch)]
+
+
+def _in_conv_norm(P, parts, conv, norm, k, mode, out, act="relu", stride=1, N=None, dims=None, s2d_in=None, s2d_out=None):
+    """conv(+bias) -> InstanceNorm(affine?) -> act, for c3d SingleConv/UpConv.  Stride-2 convs read the
+    space-to-depth copy `s2d_in` of their input and run as tap-masked stride-1 convs on the tensor cores."""
     Co = conv.weight.shape[0]
     scale, shift = P.affine(Co, bias=conv.bias)
     odims = dims
     raw = P.get_raw(N, Co, odims)
     if stride == 1:
         P.conv_tc(parts, conv.weight, k, 1, mode, scale, shift, False, out_raw=raw)
+    elif s2d_in is not None:
+        w = conv.weight.detach().to(P.device, torch.float32)
+        wp, class_masks = _s2d_weight(w)
+        vox_out = odims[0] * odims[1] * odims[2]
+        fn = _S2DMask(w.shape[1], class_masks, 2.0 * N * vox_out * 27 * w.shape[1] * Co)
+        P.conv_tc([s2d_in], wp, 3, 1, mode, scale, shift, False, out_raw=raw, tap_mask_fn=fn)
     else:
         assert len(parts) == 1
         P.conv_direct(parts[0], conv.weight, k, stride, 1, scale, shift, False, out_raw=raw)
     g = P.dev(norm.weight) if getattr(norm, "weight", None) is not None else None
     b = P.dev(norm.bias) if getattr(norm, "bias", None) is not None else None
-    P.norm_act(raw, out, gamma=g, beta=b, act=act)
+    P.norm_act(raw, out, gamma=g, beta=b, act=act, s2d=s2d_out)
     P.release(raw)
 
 
@@ -300,13 +339,18 @@ def _emit_base_unet(P, net, x_act, out_act, prec=PREC_NET_A):
     for s in (1, 2, 3, 4):
         cat[s] = P.new_concat(N, [ch[s], ch[s]], dims[s - 1], lo=lo)       # [upconv_s output | encoder_s output]
     h = x_act
+    s2d = None                  # space-to-depth copy of the previous stage's output (input of the stride-2 conv)
     for s in range(1, 6):
         enc = getattr(net.encoder, f"encoder_{s}")
         a = P.new_act(N, ch[s], dims[s - 1], lo=lo)
         _in_conv_norm(P, [h], enc[0].single_conv[0], enc[0].single_conv[1], 3, prec.conv3, a,
-                      stride=1 if s == 1 else 2, N=N, dims=dims[s - 1])
+                      stride=1 if s == 1 else 2, N=N, dims=dims[s - 1], s2d_in=s2d)
         dst = cat[s][1] if s <= 4 else P.new_act(N, ch[s], dims[s - 1], lo=lo)
-        _in_conv_norm(P, [a], enc[1].single_conv[0], enc[1].single_conv[1], 3, prec.conv3, dst, N=N, dims=dims[s - 1])
+        s2d = None
+        if s <= 4 and lo and ch[s] % 16 == 0 and all(d % 2 == 0 for d in dims[s - 1]):
+            s2d = P.new_act(N, 8 * ch[s], dims[s], lo=True)
+        _in_conv_norm(P, [a], enc[1].single_conv[0], enc[1].single_conv[1], 3, prec.conv3, dst, N=N, dims=dims[s - 1],
+                      s2d_out=s2d)
         h = dst
     for s in (4, 3, 2, 1):
         up = P.new_act(N, ch[s + 1], dims[s - 1], lo=lo)

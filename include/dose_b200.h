@@ -47,11 +47,13 @@ int dp_device_sm_count(void);
  *   chunk_cb   host array [n_chunks]: first channel block of every 16-channel K chunk (hi/lo operand
  *              splitting = listing hi blocks, lo blocks, hi blocks again against [Whi;Whi;Wlo])
  *   wpack      fp16 [k(kd)][n_chunks][k(kh)][k(kw)][2][cout][8]
- *   out_f32    c8 fp32 output or NULL;  out_hi/out_lo  c8 fp16 output (lo optional) or NULL           */
+ *   out_f32    c8 fp32 output or NULL;  out_hi/out_lo  c8 fp16 output (lo optional) or NULL
+ *   tap_mask   optional host array [n_chunks] (k <= 3): bit (kd*k+kh)*k+kw set = tap present; lets the
+ *              stride-2 convs of c3d.py:49-61 run as sparse 3^3 convs over a space-to-depth input     */
 int dp_conv3d_tc(const void* in_c8, int cb_total_in, const uint8_t* chunk_cb, int n_chunks, const void* wpack,
                  int N, int D, int H, int W, int cout, int k, int dil, const float* scale, const float* shift,
                  int relu, float* out_f32, void* out_hi, void* out_lo, int cb_total_out, int cb_out_off,
-                 double* stats, int* err_flag, int max_ctas, cudaStream_t stream);
+                 double* stats, int* err_flag, int max_ctas, const uint32_t* tap_mask, cudaStream_t stream);
 
 /* Same convolution for C_out in {16,32}, k in {3,7}, dilation 1, with the k depth taps stacked into the MMA
  * N dimension (N = k*C_out) and a sliding ring of output-plane accumulators in TMEM (conv_stack.cu): the
@@ -97,12 +99,15 @@ int dp_unpack_c8(const void* hi, const void* lo, int cb_total, int cb_off, int N
 
 /* nn.InstanceNorm3d (+affine: c3d.py:17,31) -> activation -> optional residual add (+activation), with
  * optional statistics of the result for a chained InstanceNorm (blocks_MDUNet.py:136-139).
- * Residual = c8 fp16 tensor, or raw fp32 tensor normalised with res_stats (monai UnetResBlock.norm3).  */
+ * Residual = c8 fp16 tensor, or raw fp32 tensor normalised with res_stats (monai UnetResBlock.norm3).
+ * s2d_*: optional second copy of the result in space-to-depth layout (channel block parity*C/8 + cb of a
+ * half-resolution tensor) that lets the stride-2 convs (c3d.py:49-61) run on the tensor-core conv kernel. */
 int dp_norm_act(const float* raw_f32, const void* raw_hi, const void* raw_lo, int in_cb_total, int in_cb_off,
                 const double* stats, const float* gamma, const float* beta, int act, const void* res_hi,
                 const void* res_lo, const float* res_raw, const double* res_stats, int res_cb_total, int res_cb_off,
                 int act_after_res, void* out_hi, void* out_lo, int out_cb_total, int out_cb_off, double* stats_out,
-                int N, int C, long long vox, cudaStream_t stream);
+                int N, int C, long long vox, void* s2d_hi, void* s2d_lo, int s2d_cb_total, int s2d_cb_off, int D, int H,
+                int W, cudaStream_t stream);
 
 /* nn.Conv3d k=1 over the channel-concatenation of up to three sources, each normalised/activated on
  * load: blocks_MDUNet.py:145-157 (cat(x3,x7) -> 1^3), monai UnetResBlock.conv3, heads dose_pyfer.py:290-300,353,
