@@ -20,7 +20,7 @@ _SIGNATURES = {
     "dp_conv3d_tc": [P, I, P, I, P, I, I, I, I, I, I, I, P, P, I, P, P, P, I, I, P, P, I, P, P],
     "dp_conv3d_stack": [P, I, P, I, P, I, I, I, I, I, I, P, P, I, P, P, P, I, I, P, P, I, I, P],
     "dp_conv3d_direct": [P, P, I, I, I, I, I, I, I, I, I, I, P, P, P, I, I, P, P, P, I, I, P, P],
-    "dp_gemm_tc": [P, P, I, I, I, I, I, I, L, I, L, I, I, P, P, I, P, F, I, P, I, P, I, I, I, I, P, P, P, F, P, P],
+    "dp_gemm_tc": [P, P, I, I, I, I, I, I, L, I, L, I, I, P, P, I, P, F, I, P, I, P, I, I, I, I, I, P, P, P, F, P, P],
     "dp_pack_ncdhw": [P, I, I, L, P, P, I, I, P],
     "dp_unpack_c8": [P, P, I, I, I, I, L, P, P],
     "dp_norm_act": [P, P, P, I, I, P, P, P, I, P, P, P, P, I, I, I, P, P, I, I, P, I, I, L, P, P, I, I, I, I, I, P],
@@ -32,6 +32,9 @@ _SIGNATURES = {
     "dp_softmax": [P, I, I, I, P, I, P],
     "dp_splitk_reduce": [P, I, I, I, P, P, I, P, P],
     "dp_patchify": [P, I, I, I, I, I, I, I, P, P],
+    "dp_crop_pack": [P, I, I, I, I, I, I, P, P, P, P, P, P, I, I, P],
+    "dp_window_add": [P, I, I, I, P, P, P, P, P, P, I, I, I, P],
+    "dp_div_count": [P, P, L, I, P],
     "dp_handoff": [P, I, P, P, I, I, P, P, I, I, P, P],
 }
 

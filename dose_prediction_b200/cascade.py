@@ -15,19 +15,41 @@ def shard_volumes(num_volumes: int, rank: int, world_size: int):
     return list(range(rank, num_volumes, world_size))
 
 
-class CascadePlan:
-    """seg(ct) -> argmax/one-hot hand-off -> dose(cat(ptv, oars, ct^T)) for a fixed (batch, size)."""
+def sliding_window_starts(size, roi, overlap=0.25):
+    """window origins of monai.inferers.sliding_window_inference (dense_patch_slices / _get_scan_interval) in the
+    reference's iteration order (first spatial dim slowest)."""
+    if size < roi:
+        raise ValueError("volumes smaller than the ROI (padding path of sliding_window_inference) are not built")
+    if size == roi:
+        per_dim = [0]
+    else:
+        interval = max(int(roi * (1 - overlap)), 1)
+        num = -(-(size - roi) // interval) + 1
+        per_dim = [min(k * interval, size - roi) for k in range(num)]
+    return [(a, b, c) for a in per_dim for b in per_dim for c in per_dim]
 
-    def __init__(self, seg_model, dose_model, batch, size, device, keep_structures=False, graph=False):
+
+class CascadePlan:
+    """seg(ct) -> argmax/one-hot hand-off -> dose(cat(ptv, oars, ct^T)) for a fixed (batch, size).
+
+    sw_roi=None runs the seg net directly on the full volume (its img_size must equal `size`); sw_roi=R
+    reproduces the reference's sliding-window call (train_light_linked_model.py:152-154: ROI R, overlap 0.25,
+    constant blending) with the seg net built for R^3, `sw_batch` windows per predictor pass."""
+
+    def __init__(self, seg_model, dose_model, batch, size, device, keep_structures=False, graph=False, sw_roi=None,
+                 sw_batch=8, overlap=0.25):
         if seg_model.training or dose_model.training:
             raise RuntimeError("cascade inference needs both networks in eval() mode")
         P = Plan(device)
         dims = (size, size, size)
         self.ct = P.zeros((batch, 1) + dims, torch.float32)
         self.ptv = P.zeros((batch, 1) + dims, torch.float32)
-        seg_x = P.new_act(batch, seg_model.in_ch, dims, lo=True)
-        P.pack_input(self.ct, seg_x)
-        self.logits = emit_oar_transeg(P, seg_model, seg_x)
+        if sw_roi is None:
+            seg_x = P.new_act(batch, seg_model.in_ch, dims, lo=True)
+            P.pack_input(self.ct, seg_x)
+            self.logits = emit_oar_transeg(P, seg_model, seg_x)
+        else:
+            self.logits = self._emit_sliding_window(P, seg_model, batch, size, sw_roi, sw_batch, overlap)
         a_out, dose_x = P.new_concat(batch, [dose_model.net_A.list_ch[1], dose_model.in_ch], dims, lo=True)
         self.structures = P.zeros((batch, 9) + dims, torch.float32) if keep_structures else None
         P.handoff(self.logits, self.ptv, self.ct, dose_x, self.structures)
@@ -35,6 +57,33 @@ class CascadePlan:
         self.plan = P
         if graph:
             P.capture()
+
+    def _emit_sliding_window(self, P, seg_model, batch, size, roi, sw_batch, overlap):
+        starts = sliding_window_starts(size, roi, overlap)
+        windows = [(b,) + st for b in range(batch) for st in starts]          # reference order: volume-major
+        rdims = (roi, roi, roi)
+        seg_x = P.new_act(sw_batch, seg_model.in_ch, rdims, lo=True)
+        first_step, stats0 = len(P.steps), P.stats_used
+        win_logits = emit_oar_transeg(P, seg_model, seg_x)                     # emitted once, replayed per pass
+        seg_steps = P.steps[first_step:]
+        del P.steps[first_step:]
+        seg_stats = P.stats[stats0:P.stats_used]
+        total = P.zeros((batch, win_logits.shape[1], size, size, size), torch.float32)
+        cnt1 = torch.zeros(size)
+        for s0 in sorted({st[0] for st in starts}):
+            cnt1[s0:s0 + roi] += 1
+        count = P.dev((cnt1[:, None, None] * cnt1[None, :, None] * cnt1[None, None, :]).contiguous())
+        P.add_zero(total)
+        for g in range(0, len(windows), sw_batch):
+            chunk = windows[g:g + sw_batch]
+            P.crop_pack(self.ct, roi, chunk, seg_x)
+            if seg_stats.numel():
+                P.add_zero(seg_stats)
+            P.steps.extend(seg_steps)
+            P.window_add(win_logits, roi, chunk, total)
+        P.div_count(total, count)
+        self.windows = windows
+        return total
 
     @property
     def dose(self):

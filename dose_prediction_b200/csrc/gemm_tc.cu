@@ -35,7 +35,7 @@ struct GemmParams {
   float* out_f32;
   __half* out_f16;
   // qkv scatter (mode 1): N = 3*heads*hd, tokens per image T
-  int mode, heads, hd, T;
+  int mode, heads, hd, T, vt_ld;
   __half* q; __half* kk; __half* vt; float q_scale;
   // deconv scatter (mode 2): rows = (b, d, h, w) of a [Dg,Hg,Wg] grid, cols = parity*cout + co
   int Dg, Hg, Wg, cout;
@@ -242,7 +242,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const size_t bh = static_cast<size_t>(rb) * p.heads + hh;
             if (which == 2) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) p.vt[(bh * p.hd + dd + j) * p.T + rt] = __float2half_rn(v[j]);
+              for (int j = 0; j < 16; ++j) p.vt[(bh * p.hd + dd + j) * p.vt_ld + rt] = __float2half_rn(v[j]);
             } else {
               __half* dst = (which == 0 ? p.q : p.kk) + (bh * p.T + rt) * p.hd + dd;
               const float sc = which == 0 ? p.q_scale : 1.f;
@@ -376,7 +376,7 @@ extern "C" int dp_gemm_tc(const void* A, const void* B, int M, int N, int K, int
                           int b_batch_rows, long long c_batch_stride, int c_batch_period, long long c_batch_stride2, int ldc,
                           int split_k, const float* bias, const float* rowvec, int row_period, const float* resid,
                           float alpha, int act, float* out_f32, int atomic, void* out_f16, int mode_qkv, int heads,
-                          int hd, int T, void* q, void* k, void* vt, float q_scale, int* err_flag, cudaStream_t stream) {
+                          int hd, int T, int vt_ld, void* q, void* k, void* vt, float q_scale, int* err_flag, cudaStream_t stream) {
   using namespace dp;
   DP_REQUIRE(!atomic, "dp_gemm_tc: the atomic epilogue was removed (split-K is deterministic: dp_splitk_reduce)");
   DP_REQUIRE(split_k == 1 || (out_f32 && !out_f16 && !mode_qkv && act == 0 && !bias && !rowvec && !resid && batch == 1),
@@ -387,7 +387,7 @@ extern "C" int dp_gemm_tc(const void* A, const void* B, int M, int N, int K, int
   p.c_batch_stride = c_batch_stride; p.c_batch_period = c_batch_period; p.c_batch_stride2 = c_batch_stride2; p.ldc = ldc;
   p.bias = bias; p.rowvec = rowvec; p.row_period = row_period > 0 ? row_period : 1; p.resid = resid;
   p.alpha = alpha; p.act = act; p.out_f32 = out_f32; p.out_f16 = static_cast<__half*>(out_f16);
-  p.mode = mode_qkv ? 1 : 0; p.heads = heads; p.hd = hd; p.T = T > 0 ? T : 1;
+  p.mode = mode_qkv ? 1 : 0; p.heads = heads; p.hd = hd; p.T = T > 0 ? T : 1; p.vt_ld = vt_ld > 0 ? vt_ld : p.T;
   p.q = static_cast<__half*>(q); p.kk = static_cast<__half*>(k); p.vt = static_cast<__half*>(vt); p.q_scale = q_scale;
   p.err_flag = err_flag;
   return launch_gemm(A, B, p, a_batch_rows, b_batch_rows, stream);

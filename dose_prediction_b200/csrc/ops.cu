@@ -553,6 +553,55 @@ handoff_kernel(const float* __restrict__ logits, int ncls, const float* __restri
   }
 }
 
+// ------------------------------------------------------------------ sliding-window inference plumbing
+// monai.inferers.sliding_window_inference (constant blending) as called at train_light_linked_model.py:152-154:
+// crop ROI windows out of the volume, run the predictor, add every window's logits into the full-size sum in
+// window order (deterministic, like the reference's sequential +=), divide by the per-voxel window count.
+struct WindowList {
+  int n;                      // windows handled by this launch
+  int b[64], x0[64], y0[64], z0[64];
+};
+__global__ void __launch_bounds__(256)
+crop_pack_kernel(const float* __restrict__ src, int C, int S0, int S1, int S2, int R, const WindowList wl, __half* hi,
+                 __half* lo, int cb_total, int cb_off, int ncb) {
+  const long long rv = static_cast<long long>(R) * R * R;
+  const long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (v >= rv) return;
+  const int cb = blockIdx.y % ncb, wi = blockIdx.y / ncb;
+  const int z = static_cast<int>(v % R), y = static_cast<int>((v / R) % R), x = static_cast<int>(v / (static_cast<long long>(R) * R));
+  const size_t vol = static_cast<size_t>(S0) * S1 * S2;
+  const size_t sv = (static_cast<size_t>(wl.x0[wi] + x) * S1 + (wl.y0[wi] + y)) * S2 + (wl.z0[wi] + z);
+  float xv[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = cb * 8 + j;
+    xv[j] = c < C ? src[(static_cast<size_t>(wl.b[wi]) * C + c) * vol + sv] : 0.f;
+  }
+  store8(hi, lo, ((static_cast<size_t>(wi) * cb_total + cb_off + cb) * rv + v) * 8, xv);
+}
+// out[b, c, window region] += win[w, c, :, :, :] for ONE window per volume per launch (no write conflicts)
+__global__ void __launch_bounds__(256)
+window_add_kernel(const float* __restrict__ win, int ncls, int R, const WindowList wl, int win_stride, float* out, int S0,
+                  int S1, int S2, int first) {
+  const long long rv = static_cast<long long>(R) * R * R;
+  const long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (v >= rv) return;
+  const int c = blockIdx.y % ncls, wi = blockIdx.y / ncls;
+  const int z = static_cast<int>(v % R), y = static_cast<int>((v / R) % R), x = static_cast<int>(v / (static_cast<long long>(R) * R));
+  const size_t vol = static_cast<size_t>(S0) * S1 * S2;
+  const size_t ov = (static_cast<size_t>(wl.x0[wi] + x) * S1 + (wl.y0[wi] + y)) * S2 + (wl.z0[wi] + z);
+  float* o = out + (static_cast<size_t>(wl.b[wi]) * ncls + c) * vol + ov;
+  const float val = win[(static_cast<size_t>(wi) * win_stride + c) * rv + v];
+  *o = *o + val;
+}
+__global__ void __launch_bounds__(256)
+div_count_kernel(float* __restrict__ data, const float* __restrict__ count, long long vol, int rows) {
+  const long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (v >= vol) return;
+  const float c = count[v];
+  for (int r = blockIdx.y; r < rows; r += gridDim.y) data[static_cast<size_t>(r) * vol + v] = data[static_cast<size_t>(r) * vol + v] / c;
+}
+
 // ------------------------------------------------------------------ generic direct convolution (strided convs)
 // out[n,co,do,ho,wo] = bias + sum_{ci,kd,kh,kw} in[n,ci,do*s+kd*dil-pad,...] * w[co,ci,kd,kh,kw]
 // One thread = one output voxel x DC2_CO output channels, fp32 math on fp16 hi(+lo) c8 inputs.
@@ -806,6 +855,49 @@ extern "C" int dp_handoff(const float* logits, int ncls, const float* ptv, const
   dim3 grid((S + 31) / 32, (S + 31) / 32, N * S);
   handoff_kernel<<<grid, 256, 0, stream>>>(logits, ncls, ptv, ct, S, static_cast<__half*>(out_hi), static_cast<__half*>(out_lo),
                                            out_cb_total, out_cb_off, structures);
+  DP_CHECK(cudaGetLastError());
+  return 0;
+}
+
+static int fill_windows(WindowList& wl, int n, const int* b, const int* x0, const int* y0, const int* z0) {
+  DP_REQUIRE(n >= 1 && n <= 64, "sliding window: 1..64 windows per launch, got %d", n);
+  wl.n = n;
+  for (int i = 0; i < n; ++i) { wl.b[i] = b[i]; wl.x0[i] = x0[i]; wl.y0[i] = y0[i]; wl.z0[i] = z0[i]; }
+  return 0;
+}
+
+extern "C" int dp_crop_pack(const float* src, int C, int S0, int S1, int S2, int R, int n_win, const int* win_b,
+                            const int* win_x0, const int* win_y0, const int* win_z0, void* hi, void* lo, int cb_total,
+                            int cb_off, cudaStream_t stream) {
+  WindowList wl;
+  if (int rc = fill_windows(wl, n_win, win_b, win_x0, win_y0, win_z0)) return rc;
+  const int ncb = (C + 7) / 8;
+  dim3 grid(blocks_for(static_cast<long long>(R) * R * R, 256), n_win * ncb);
+  crop_pack_kernel<<<grid, 256, 0, stream>>>(src, C, S0, S1, S2, R, wl, static_cast<__half*>(hi), static_cast<__half*>(lo), cb_total, cb_off, ncb);
+  DP_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dp_window_add(const float* win, int ncls, int R, int n_win, const int* win_b, const int* win_x0,
+                             const int* win_y0, const int* win_z0, const int* win_slot, float* out, int S0, int S1, int S2,
+                             cudaStream_t stream) {
+  // one kernel per window, launched in list order: overlapping windows accumulate deterministically in the
+  // reference's order.  win_slot[i] = batch entry of the predictor output that holds window i.
+  WindowList wl;
+  if (int rc = fill_windows(wl, n_win, win_b, win_x0, win_y0, win_z0)) return rc;
+  for (int i = 0; i < n_win; ++i) {
+    WindowList one;
+    one.n = 1; one.b[0] = wl.b[i]; one.x0[0] = wl.x0[i]; one.y0[0] = wl.y0[i]; one.z0[0] = wl.z0[i];
+    dim3 grid(blocks_for(static_cast<long long>(R) * R * R, 256), ncls);
+    window_add_kernel<<<grid, 256, 0, stream>>>(win + static_cast<size_t>(win_slot[i]) * ncls * R * R * R, ncls, R, one, ncls, out, S0, S1, S2, 0);
+  }
+  DP_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dp_div_count(float* data, const float* count, long long vol, int rows, cudaStream_t stream) {
+  dim3 grid(blocks_for(vol, 256), rows < 64 ? rows : 64);
+  div_count_kernel<<<grid, 256, 0, stream>>>(data, count, vol, rows);
   DP_CHECK(cudaGetLastError());
   return 0;
 }

@@ -478,15 +478,16 @@ class Plan:
              act=None, out_f32=None, atomic=False, out_f16=None, qkv=None):
         self.count_flops("dp_gemm_tc", 2.0 * M * N * K * batch)
         ldc = N if ldc is None else ldc
-        mode_qkv, heads, hd, T, q, k, vt, qs = 0, 0, 0, 0, None, None, None, 1.0
+        mode_qkv, heads, hd, T, vt_ld, q, k, vt, qs = 0, 0, 0, 0, 0, None, None, None, 1.0
         if qkv is not None:
             mode_qkv = 1
             heads, hd, T, q, k, vt, qs = qkv
+            vt_ld = vt.shape[-1]
             q, k, vt = q.data_ptr(), k.data_ptr(), vt.data_ptr()
         p = lambda t: t.data_ptr() if t is not None else None
         self.add("dp_gemm_tc", p(A), p(B), M, N, K, batch, a_batch_rows, b_batch_rows, c_batch_stride, c_batch_period,
                  c_batch_stride2, ldc, split_k, p(bias), p(rowvec), row_period, p(resid), float(alpha), ACT_ID[act],
-                 p(out_f32), int(atomic), p(out_f16), mode_qkv, heads, hd, T, q, k, vt, float(qs), self.err.data_ptr())
+                 p(out_f32), int(atomic), p(out_f16), mode_qkv, heads, hd, T, vt_ld, q, k, vt, float(qs), self.err.data_ptr())
 
     def gemm_splitk(self, A, B, M, N, K, split_k, out_f32, bias=None, rowvec=None, row_period=0):
         """deterministic split-K: fp32 partials to a workspace, then one reduction pass (+bias, +rowvec)."""
@@ -502,11 +503,30 @@ class Plan:
                  out_f16.data_ptr() if out_f16 is not None else None, out_f32.data_ptr() if out_f32 is not None else None)
 
     def softmax(self, s, rows, cols, p):
-        self.add("dp_softmax", s.data_ptr(), rows, cols, cols, p.data_ptr(), cols)
+        self.add("dp_softmax", s.data_ptr(), rows, cols, s.shape[-1], p.data_ptr(), p.shape[-1])
 
     def patchify(self, a, ncb, out):
         D, H, W = a.dims
         self.add("dp_patchify", a.buf.data_ptr(), a.cb_total, a.cb_off, ncb, a.N, D, H, W, out.data_ptr())
+
+    def crop_pack(self, src, R, windows, out):
+        """windows: list of (b, x0, y0, z0); window i becomes batch entry i of `out` (an Act of R^3 volumes)."""
+        C, S0, S1, S2 = src.shape[1], src.shape[2], src.shape[3], src.shape[4]
+        arrs = [_lib.int_array([w[k] for w in windows]) for k in range(4)]
+        self.keep.append(arrs)
+        self.add("dp_crop_pack", src.data_ptr(), C, S0, S1, S2, R, len(windows), *arrs, out.hi_ptr, out.lo_ptr,
+                 out.cb_total, out.cb_off)
+
+    def window_add(self, win_logits, R, windows, out_sum):
+        ncls = win_logits.shape[1]
+        arrs = [_lib.int_array([w[k] for w in windows]) for k in range(4)] + [_lib.int_array(list(range(len(windows))))]
+        self.keep.append(arrs)
+        self.add("dp_window_add", win_logits.data_ptr(), ncls, R, len(windows), *arrs, out_sum.data_ptr(),
+                 out_sum.shape[2], out_sum.shape[3], out_sum.shape[4])
+
+    def div_count(self, data, count):
+        vol = count.numel()
+        self.add("dp_div_count", data.data_ptr(), count.data_ptr(), vol, data.numel() // vol)
 
     def handoff(self, logits, ptv, ct, out, structures=None):
         N, ncls, S = logits.shape[0], logits.shape[1], logits.shape[2]

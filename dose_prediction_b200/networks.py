@@ -405,9 +405,10 @@ def _emit_vit(P, vit, parts, N, S, taps):
     ln = P.zeros((M, hidden), torch.float16)
     q = P.zeros((N * heads, T, hd), torch.float16)
     k = P.zeros((N * heads, T, hd), torch.float16)
-    vt = P.zeros((N * heads, hd, T), torch.float16)
+    Tp = ceil_div(T, 8) * 8          # TMA row pitch must be a multiple of 16 B: pad the key axis with zeros
+    vt = P.zeros((N * heads, hd, Tp), torch.float16)
     scores = P.zeros((N * heads, T, T), torch.float32)
-    probs = P.zeros((N * heads, T, T), torch.float16)
+    probs = P.zeros((N * heads, T, Tp), torch.float16)
     o = P.zeros((M, hidden), torch.float16)
     hmid = P.zeros((M, vit.mlp_dim), torch.float16)
     hs = {}
@@ -416,7 +417,7 @@ def _emit_vit(P, vit, parts, N, S, taps):
         P.gemm(ln, P.dev(blk.attn.qkv.weight, torch.float16), M, 3 * hidden, hidden, qkv=(heads, hd, T, q, k, vt, hd ** -0.5))
         P.gemm(q, k, T, T, hd, batch=N * heads, a_batch_rows=T, b_batch_rows=T, c_batch_stride=T * T, ldc=T, out_f32=scores)
         P.softmax(scores, N * heads * T, T, probs)
-        P.gemm(probs, vt, T, hd, T, batch=N * heads, a_batch_rows=T, b_batch_rows=hd, c_batch_stride=T * hidden,
+        P.gemm(probs, vt, T, hd, Tp, batch=N * heads, a_batch_rows=T, b_batch_rows=hd, c_batch_stride=T * hidden,
                c_batch_period=heads, c_batch_stride2=hd, ldc=hidden, out_f16=o)
         P.gemm(o, P.dev(blk.attn.out_proj.weight, torch.float16), M, hidden, hidden, bias=P.dev(blk.attn.out_proj.bias),
                resid=x, out_f32=x)

@@ -76,14 +76,14 @@ int dp_conv3d_direct(const void* in_hi, const void* in_lo, int in_cb_total, int 
 /* nn.Linear / attention contractions: C[M,N] = alpha * A[M,K] . B[N,K]^T (+bias, +rowvec, act, +resid).
  * Replaces: monai PatchEmbeddingBlock Linear (+position_embeddings), SABlock.qkv / out_proj and both
  * einsums, MLPBlock.linear1 (+GELU) / linear2 (+residual).  mode_qkv scatters the [M, 3*heads*hd] result
- * into q [B,heads,T,hd] (scaled by q_scale), k [B,heads,T,hd], v^T [B,heads,hd,T]
+ * into q [B,heads,T,hd] (scaled by q_scale), k [B,heads,T,hd], v^T [B,heads,hd,vt_ld] (vt_ld >= T, 8 | vt_ld)
  * (einops "b h (qkv l d) -> qkv b l h d").  Batched: A/B rows advance by a/b_batch_rows per batch entry z,
  * outputs by z*c_batch_stride, or (z/period)*c_batch_stride + (z%period)*c_batch_stride2 if period>0.
  * split_k > 1: plain fp32 partial sums go to out_f32[split][M][ldc]; finish with dp_splitk_reduce.      */
 int dp_gemm_tc(const void* A, const void* B, int M, int N, int K, int batch, int a_batch_rows, int b_batch_rows,
                long long c_batch_stride, int c_batch_period, long long c_batch_stride2, int ldc, int split_k, const float* bias, const float* rowvec,
                int row_period, const float* resid, float alpha, int act, float* out_f32, int atomic,
-               void* out_f16, int mode_qkv, int heads, int hd, int T, void* q, void* k, void* vt, float q_scale,
+               void* out_f16, int mode_qkv, int heads, int hd, int T, int vt_ld, void* q, void* k, void* vt, float q_scale,
                int* err_flag, cudaStream_t stream);
 
 /* Deterministic split-K finish: out[m][n] = sum_s ws[s][m][n] + bias[n] + rowvec[m % row_period][n]
@@ -154,6 +154,16 @@ int dp_patchify(const void* in_c8, int cb_total, int cb_off, int ncb, int N, int
  * (2 channel blocks: [PTV,7 OARs] [CT,0...]) and optionally NCDHW fp32 structures [N,9,S,S,S].        */
 int dp_handoff(const float* logits, int ncls, const float* ptv, const float* ct, int N, int S, void* out_hi,
                void* out_lo, int out_cb_total, int out_cb_off, float* structures, cudaStream_t stream);
+
+/* monai.inferers.sliding_window_inference (constant blending; train_light_linked_model.py:152-154):
+ * dp_crop_pack     ROI windows (b, x0, y0, z0) of an NCDHW fp32 volume -> c8 predictor input, one batch entry per window
+ * dp_window_add    out[b, :, window] += win[slot]   (one launch per window, reference accumulation order)
+ * dp_div_count     data[r][v] /= count[v]           (count_map of the reference)                        */
+int dp_crop_pack(const float* src, int C, int S0, int S1, int S2, int R, int n_win, const int* win_b, const int* win_x0,
+                 const int* win_y0, const int* win_z0, void* hi, void* lo, int cb_total, int cb_off, cudaStream_t stream);
+int dp_window_add(const float* win, int ncls, int R, int n_win, const int* win_b, const int* win_x0, const int* win_y0,
+                  const int* win_z0, const int* win_slot, float* out, int S0, int S1, int S2, cudaStream_t stream);
+int dp_div_count(float* data, const float* count, long long vol, int rows, cudaStream_t stream);
 
 #ifdef __cplusplus
 }

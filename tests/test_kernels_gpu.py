@@ -151,7 +151,7 @@ def test_gemm_tc_epilogues_gelu_residual_fp16():
     assert _rel(g16.float().cpu(), F.gelu(lin)) < 1e-3
 
 
-@pytest.mark.parametrize("T,heads,hd", [(512, 6, 128), (8, 12, 64), (216, 12, 64)])
+@pytest.mark.parametrize("T,heads,hd", [(512, 6, 128), (8, 12, 64), (216, 12, 64), (27, 6, 128)])
 def test_attention_pipeline_matches_torch(T, heads, hd):
     """qkv scatter GEMM -> QK^T -> softmax -> PV, i.e. monai SABlock.forward without the projections."""
     torch.manual_seed(4)
@@ -163,14 +163,15 @@ def test_attention_pipeline_matches_torch(T, heads, hd):
     P = _plan()
     q = P.zeros((Bn * heads, T, hd), torch.float16)
     k = P.zeros((Bn * heads, T, hd), torch.float16)
-    vt = P.zeros((Bn * heads, hd, T), torch.float16)
+    Tp = (T + 7) // 8 * 8
+    vt = P.zeros((Bn * heads, hd, Tp), torch.float16)
     s = P.zeros((Bn * heads, T, T), torch.float32)
-    pr = P.zeros((Bn * heads, T, T), torch.float16)
+    pr = P.zeros((Bn * heads, T, Tp), torch.float16)
     o = P.zeros((M, hidden), torch.float16)
     P.gemm(xin, wqkv, M, 3 * hidden, hidden, qkv=(heads, hd, T, q, k, vt, hd ** -0.5))
     P.gemm(q, k, T, T, hd, batch=Bn * heads, a_batch_rows=T, b_batch_rows=T, c_batch_stride=T * T, ldc=T, out_f32=s)
     P.softmax(s, Bn * heads * T, T, pr)
-    P.gemm(pr, vt, T, hd, T, batch=Bn * heads, a_batch_rows=T, b_batch_rows=hd, c_batch_stride=T * hidden,
+    P.gemm(pr, vt, T, hd, Tp, batch=Bn * heads, a_batch_rows=T, b_batch_rows=hd, c_batch_stride=T * hidden,
            c_batch_period=heads, c_batch_stride2=hd, ldc=hidden, out_f16=o)
     P.run()
     _finish(P)

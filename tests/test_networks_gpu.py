@@ -133,3 +133,28 @@ def test_batch_entries_are_independent_and_permutation_equivariant():
     single = m(x[1:2])
     assert _rel(perm[1], full[0]) < 1e-5 and _rel(perm[0], full[2]) < 1e-5
     assert _rel(single[0], full[1]) < 1e-5
+
+
+def test_sliding_window_cascade_matches_reference_fixture():
+    """monai sliding_window_inference (ROI 32 over a 48^3 CT, overlap 0.25, constant blending) feeding the
+    hand-off: blended logits vs the fixture produced by the reference seg module under the monai restatement."""
+    from dose_prediction_b200 import synth
+    from dose_prediction_b200.cascade import CascadePlan
+    from oracle import torch_ref
+    ssd = _sd("oar_transeg", 32, 1)
+    dsd = _sd("dose_pyfer", 48, 0)
+    vol = synth.make_volume(48, seed=77)
+    g = torch.from_numpy(np.load(os.path.join(GOLDEN, "sliding48.npz"))["logits"])
+    casc = CascadePlan(_seg_model(32, ssd), _dose_model(48, dsd), 1, 48, "cuda:0", keep_structures=True, sw_roi=32, sw_batch=4)
+    dose = casc(vol["ct"].cuda(), vol["ptv"].cuda()).clone()
+    torch.cuda.synchronize()
+    casc.plan.check_device_errors()
+    logits = casc.logits.cpu()
+    assert _rel(logits[:, :, ::2, ::2, ::2], g) < LOGIT_TOL
+    with torch.no_grad():
+        want_logits = torch_ref.sliding_window_logits(ssd, vol["ct"], roi=32, sw_batch=4)
+        st = torch_ref.handoff(logits, vol["ptv"], vol["ct"])
+        want_dose = torch_ref.dose_pyfer_forward(dsd, casc.structures.cpu())[1][0]
+    assert (logits.argmax(1) == want_logits.argmax(1)).float().mean().item() >= ARGMAX_MIN
+    assert torch.equal(casc.structures.cpu(), st)            # hand-off of the blended logits is bit exact
+    assert _rel(dose, want_dose) < DOSE_TOL
