@@ -234,23 +234,70 @@ class conv_3_1(nn.Module):
                                   nn.InstanceNorm3d(ch_out), _act_layer(act))
 
 
-class MultiUnetBasicBlock(nn.Module):
-    def __init__(self, in_channels, out_channels, multiS_conv=True, act="relu"):
+class _dilated_block(nn.Module):
+    """blocks_MDUNet.py:64-78 / :160-191: conv(dil) -> IN -> act -> conv(dil) -> IN -> act."""
+
+    def __init__(self, ch_in, ch_out, dil, act="relu"):
         super().__init__()
-        if not multiS_conv:
-            raise NotImplementedError("multiS_conv=False (DualDilatedBlock) is a SURVEY 8(f2) follow-up")
-        self.cov_ = conv_3_1(ch_in=in_channels, ch_out=out_channels, act=act)
+        self.dil = dil
+        self.conv = nn.Sequential(
+            nn.Conv3d(ch_in, ch_out, kernel_size=3, stride=1, padding=dil, dilation=dil, bias=True), nn.InstanceNorm3d(ch_out), _act_layer(act),
+            nn.Conv3d(ch_out, ch_out, kernel_size=3, stride=1, padding=dil, dilation=dil, bias=True), nn.InstanceNorm3d(ch_out), _act_layer(act))
+
+
+class DualDilatedBlock(nn.Module):
+    """blocks_MDUNet.py:194-215 (multiS_conv=False): dilation 1/2/3 branches -> cat -> 1^3 conv -> IN -> act."""
+
+    def __init__(self, ch_in, ch_out, act="relu"):
+        super().__init__()
+        self.act = act
+        self.conv_3 = _dilated_block(ch_in, ch_out, 1, act)
+        self.conv_5 = _dilated_block(ch_in, ch_out, 2, act)
+        self.conv_7 = _dilated_block(ch_in, ch_out, 3, act)
+        self.conv = nn.Sequential(nn.Conv3d(ch_out * 3, ch_out, kernel_size=1, stride=1, padding=0, bias=True),
+                                  nn.InstanceNorm3d(ch_out), _act_layer(act))
+
+
+class _conv_block_bn(nn.Module):
+    """OldModels/Nets/blocks_MDUNet.py:64-78,98-112: conv -> BN -> ReLU -> conv -> BN -> ReLU (k = 3 or 7)."""
+
+    def __init__(self, ch_in, ch_out, k):
+        super().__init__()
+        self.conv = nn.Sequential(
+            nn.Conv3d(ch_in, ch_out, kernel_size=k, stride=1, padding=k // 2, bias=True), nn.BatchNorm3d(ch_out), nn.ReLU(inplace=True),
+            nn.Conv3d(ch_out, ch_out, kernel_size=k, stride=1, padding=k // 2, bias=True), nn.BatchNorm3d(ch_out), nn.ReLU(inplace=True))
+
+
+class conv_3_1_old(nn.Module):
+    """OldModels/Nets/blocks_MDUNet.py:132-147 — the layout the reference's trained TRANSEG checkpoints use."""
+
+    def __init__(self, ch_in, ch_out):
+        super().__init__()
+        self.conv_3 = _conv_block_bn(ch_in, ch_out, 3)
+        self.conv_7 = _conv_block_bn(ch_in, ch_out, 7)
+        self.conv = nn.Conv3d(ch_out * 2, ch_out, kernel_size=1, stride=1, padding=0, bias=True)
+
+
+class MultiUnetBasicBlock(nn.Module):
+    def __init__(self, in_channels, out_channels, multiS_conv=True, act="relu", old=False):
+        super().__init__()
+        if old:
+            self.cov_ = conv_3_1_old(in_channels, out_channels)
+        elif multiS_conv:
+            self.cov_ = conv_3_1(ch_in=in_channels, ch_out=out_channels, act=act)
+        else:
+            self.cov_ = DualDilatedBlock(ch_in=in_channels, ch_out=out_channels, act=act)
 
 
 class ModifiedUnetrUpBlock(nn.Module):
     def __init__(self, spatial_dims, in_channels, out_channels, upsample_kernel_size, act="relu", norm="instance",
-                 multiS_conv=True):
+                 multiS_conv=True, old=False):
         super().__init__()
         if spatial_dims != 3 or upsample_kernel_size != 2:
             raise NotImplementedError("only the 3-D, 2x up-sampling block used by the reference nets is built")
         self.act = act
         self.transp_conv = _conv_layer(in_channels, out_channels, 2, 2, transposed=True)
-        self.conv_block = MultiUnetBasicBlock(out_channels + out_channels, out_channels, act=act, multiS_conv=multiS_conv)
+        self.conv_block = MultiUnetBasicBlock(out_channels + out_channels, out_channels, act=act, multiS_conv=multiS_conv, old=old)
 
 
 class ModifiedUnetOutBlock(nn.Module):
@@ -507,10 +554,58 @@ def _emit_conv_3_1(P, blk, parts, out, prec):
     P.release(raw)
 
 
+def _emit_dual_dilated(P, blk, parts, out, prec):
+    """blocks_MDUNet.py:206-215: three dilated branches; their last IN+act is applied on load by the 1^3 conv."""
+    N, dims = parts[0].N, parts[0].dims
+    act = blk.act
+    C = blk.conv_3.conv[0].weight.shape[0]
+    srcs, raws = [], []
+    for br in (blk.conv_3, blk.conv_5, blk.conv_7):
+        c = br.conv
+        raw = P.get_raw(N, C, dims)
+        P.conv_tc(parts, c[0].weight, 3, br.dil, prec.conv3, *P.affine(C, bias=c[0].bias), False, out_raw=raw)
+        a = P.new_act(N, C, dims, lo=prec.lo)
+        P.norm_act(raw, a, act=act)
+        P.release(raw)
+        raw = P.get_raw(N, C, dims)
+        P.conv_tc([a], c[3].weight, 3, br.dil, prec.conv3, *P.affine(C, bias=c[3].bias), False, out_raw=raw)
+        srcs.append((raw, raw.stats, act))
+        raws.append(raw)
+    o = P.get_raw(N, C, dims)
+    P.pointwise(srcs, blk.conv[0].weight, blk.conv[0].bias, out_raw=o)
+    for r in raws:
+        P.release(r)
+    P.norm_act(o, out, act=act)
+    P.release(o)
+
+
+def _emit_conv_3_1_old(P, blk, parts, out, prec):
+    """OldModels conv_3_1: every norm is an eval-mode BatchNorm, folded with ReLU into the conv epilogues;
+    the closing 1^3 conv has no norm / activation."""
+    N, dims = parts[0].N, parts[0].dims
+    C = blk.conv.weight.shape[0]
+    ys = []
+    for br, k, mode in ((blk.conv_3, 3, prec.conv3), (blk.conv_7, 7, prec.conv7)):
+        c = br.conv
+        lo = mode != "p1"
+        a = P.new_act(N, C, dims, lo=lo)
+        P.conv_tc(parts, c[0].weight, k, 1, mode, *P.affine(C, bias=c[0].bias, bn=c[1]), True, out_act=a)
+        y = P.new_act(N, C, dims, lo=prec.lo)
+        P.conv_tc([a], c[3].weight, k, 1, mode, *P.affine(C, bias=c[3].bias, bn=c[4]), True, out_act=y)
+        ys.append((y, None, None))
+    P.pointwise(ys, blk.conv.weight, blk.conv.bias, out_act=out)
+
+
 def _emit_up_block(P, blk, inp, skip_slot_pair, out, prec):
     """base_blocks.py:136-141: deconv -> cat(out, skip) -> MultiUnetBasicBlock."""
     P.deconv2x(inp, blk.transp_conv.conv.weight, skip_slot_pair[0])
-    _emit_conv_3_1(P, blk.conv_block.cov_, skip_slot_pair, out, prec)
+    cov = blk.conv_block.cov_
+    if isinstance(cov, conv_3_1_old):
+        _emit_conv_3_1_old(P, cov, skip_slot_pair, out, prec)
+    elif isinstance(cov, DualDilatedBlock):
+        _emit_dual_dilated(P, cov, skip_slot_pair, out, prec)
+    else:
+        _emit_conv_3_1(P, cov, skip_slot_pair, out, prec)
 
 
 def _emit_unetr(P, vit, enc_blocks, dec_blocks, parts, taps, prec):
@@ -750,7 +845,7 @@ class OARTranseg(nn.Module):
     def __init__(self, in_channels: int, out_channels: int, img_size: Union[Sequence[int], int], feature_size: int = 16,
                  hidden_size: int = 768, mlp_dim: int = 3072, num_heads: int = 12, pos_embed: str = "conv",
                  norm_name: Union[Tuple, str] = "instance", conv_block: bool = True, res_block: bool = True,
-                 dropout_rate: float = 0.0, spatial_dims: int = 3) -> None:
+                 dropout_rate: float = 0.0, spatial_dims: int = 3, _old_blocks: bool = False) -> None:
         super().__init__()
         if not (0 <= dropout_rate <= 1):
             raise ValueError("dropout_rate should be between 0 and 1.")
@@ -772,10 +867,10 @@ class OARTranseg(nn.Module):
         self.encoder2 = UnetrPrUpBlock(hidden_size, feature_size * 2, num_layer=2)
         self.encoder3 = UnetrPrUpBlock(hidden_size, feature_size * 4, num_layer=1)
         self.encoder4 = UnetrPrUpBlock(hidden_size, feature_size * 8, num_layer=0)
-        self.decoder5 = ModifiedUnetrUpBlock(spatial_dims, hidden_size, feature_size * 8, 2)
-        self.decoder4 = ModifiedUnetrUpBlock(spatial_dims, feature_size * 8, feature_size * 4, 2)
-        self.decoder3 = ModifiedUnetrUpBlock(spatial_dims, feature_size * 4, feature_size * 2, 2)
-        self.decoder2 = ModifiedUnetrUpBlock(spatial_dims, feature_size * 2, feature_size, 2)
+        self.decoder5 = ModifiedUnetrUpBlock(spatial_dims, hidden_size, feature_size * 8, 2, old=_old_blocks)
+        self.decoder4 = ModifiedUnetrUpBlock(spatial_dims, feature_size * 8, feature_size * 4, 2, old=_old_blocks)
+        self.decoder3 = ModifiedUnetrUpBlock(spatial_dims, feature_size * 4, feature_size * 2, 2, old=_old_blocks)
+        self.decoder2 = ModifiedUnetrUpBlock(spatial_dims, feature_size * 2, feature_size, 2, old=_old_blocks)
         self.out = ModifiedUnetOutBlock(spatial_dims=spatial_dims, in_channels=feature_size, out_channels=out_channels)
         self.proj_axes = (0, spatial_dims + 1) + tuple(d + 1 for d in range(spatial_dims))
         self.proj_view_shape = list(self.feat_size) + [self.hidden_size]
@@ -783,6 +878,18 @@ class OARTranseg(nn.Module):
     def forward(self, x_in):
         """x_in [B,in_channels,S,S,S] fp32 CUDA -> logits [B,out_channels,S,S,S] fp32."""
         return _run_single(self, x_in, lambda m, shape, dev: plan_oar_transeg(m, shape, dev))
+
+
+class TRANSEG(OARTranseg):
+    """OARSegmentation/OldModels/Networks/oar_transeg.py:14 — the variant train_light_transeg.py:20,110 and the
+    cascade LinkedNet (train_light_linked_model.py:89) instantiate; BatchNorm in both decoder branches, bare 1^3."""
+
+    def __init__(self, in_channels: int, out_channels: int, img_size: Union[Sequence[int], int], feature_size: int = 16,
+                 hidden_size: int = 768, mlp_dim: int = 3072, num_heads: int = 12, pos_embed: str = "conv",
+                 norm_name: Union[Tuple, str] = "instance", conv_block: bool = True, res_block: bool = True,
+                 dropout_rate: float = 0.0, spatial_dims: int = 3) -> None:
+        super().__init__(in_channels, out_channels, img_size, feature_size, hidden_size, mlp_dim, num_heads, pos_embed,
+                         norm_name, conv_block, res_block, dropout_rate, spatial_dims, _old_blocks=True)
 
 
 def emit_oar_transeg(P, model, x_act):

@@ -55,6 +55,14 @@ def main():
                         **{f"d{i}": _np(t) for i, t in enumerate(out[1])})
     np.savez_compressed(os.path.join(OUT, "seg32.npz"), logits=_np(logits))
 
+    # ---- the OldModels TRANSEG (what the reference's seg checkpoints / LinkedNet use), 32^3
+    old32 = old.TRANSEG(in_channels=1, out_channels=8, img_size=(32, 32, 32), feature_size=16, hidden_size=768, mlp_dim=3072,
+                        num_heads=12, pos_embed="perceptron", norm_name="instance", res_block=True, conv_block=True,
+                        dropout_rate=0.0).eval()
+    old32.load_state_dict(synth_ckpt.make_state_dict(synth_ckpt.manifest_of(old32), 2), strict=True)
+    with torch.no_grad():
+        np.savez_compressed(os.path.join(OUT, "seg_old32.npz"), logits=_np(old32(vol["ct"][:1])))
+
     # ---- hand-off exactly as LinkedNet.test_step does it (train_light_linked_model.py:152-169)
     cfg = ref_loader.seg_config()
     from monai.data import decollate_batch

@@ -206,26 +206,40 @@ def dual_dilated_block(sd: SD, p: str, x, act: str):
     return _act(_inorm(y), act)
 
 
-def modified_unetr_up_block(sd: SD, p: str, inp, skip, act: str, multiS_conv: bool = True):
-    """OARSegmentation/Models/Nets/base_blocks.py:136-141."""
+def conv_3_1_old(sd: SD, p: str, x):
+    """OARSegmentation/OldModels/Nets/blocks_MDUNet.py:132-147 (conv_block_3 :64-78 and conv_block_7 :98-112 both
+    conv->BN->ReLU twice; bare 1^3 conv, no norm/activation after it)."""
+    outs = []
+    for name, pad in (("conv_3", 1), ("conv_7", 3)):
+        q = f"{p}{name}.conv."
+        y = F.relu(_bn_eval(sd, q + "1.", _conv(sd, q + "0.", x, padding=pad)))
+        y = F.relu(_bn_eval(sd, q + "4.", _conv(sd, q + "3.", y, padding=pad)))
+        outs.append(y)
+    return _conv(sd, p + "conv.", torch.cat(outs, dim=1))
+
+
+def modified_unetr_up_block(sd: SD, p: str, inp, skip, act: str, multiS_conv: bool = True, old: bool = False):
+    """OARSegmentation/Models/Nets/base_blocks.py:136-141 (OldModels/Nets/base_blocks.py:127-132 when old)."""
     out = torch.cat((_deconv2(sd, p + "transp_conv.conv.", inp), skip), dim=1)
+    if old:
+        return conv_3_1_old(sd, p + "conv_block.cov_.", out)
     blk = conv_3_1 if multiS_conv else dual_dilated_block
     return blk(sd, p + "conv_block.cov_.", out, act)
 
 
 # --------------------------------------------------------------------------- whole networks
-def oar_transeg_forward(sd: SD, x, num_heads: int = 12, num_layers: int = 12):
-    """OARSegmentation/Models/Networks/oar_transeg.py:171-185."""
+def oar_transeg_forward(sd: SD, x, num_heads: int = 12, num_layers: int = 12, old: bool = False):
+    """OARSegmentation/Models/Networks/oar_transeg.py:171-185 (old=True: OldModels/Networks/oar_transeg.py TRANSEG)."""
     grid = [s // 16 for s in x.shape[2:]]
     z, hs = vit(sd, "vit.", x, num_layers, num_heads)
     enc1 = unet_res_block(sd, "encoder1.layer.", x)
     enc2 = unetr_pr_up_block(sd, "encoder2.", proj_feat(hs[3], grid), 2)
     enc3 = unetr_pr_up_block(sd, "encoder3.", proj_feat(hs[6], grid), 1)
     enc4 = unetr_pr_up_block(sd, "encoder4.", proj_feat(hs[9], grid), 0)
-    d = modified_unetr_up_block(sd, "decoder5.", proj_feat(z, grid), enc4, "relu")
-    d = modified_unetr_up_block(sd, "decoder4.", d, enc3, "relu")
-    d = modified_unetr_up_block(sd, "decoder3.", d, enc2, "relu")
-    d = modified_unetr_up_block(sd, "decoder2.", d, enc1, "relu")
+    d = modified_unetr_up_block(sd, "decoder5.", proj_feat(z, grid), enc4, "relu", old=old)
+    d = modified_unetr_up_block(sd, "decoder4.", d, enc3, "relu", old=old)
+    d = modified_unetr_up_block(sd, "decoder3.", d, enc2, "relu", old=old)
+    d = modified_unetr_up_block(sd, "decoder2.", d, enc1, "relu", old=old)
     return _conv(sd, "out.conv.conv.", d)
 
 

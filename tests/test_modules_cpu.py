@@ -65,3 +65,17 @@ def test_synthetic_checkpoint_is_deterministic():
     a, b = synth_ckpt.make_state_dict(man, 3), synth_ckpt.make_state_dict(man, 3)
     assert all(torch.equal(a[k], b[k]) for k in a)
     assert not torch.equal(a[man[0][0]], synth_ckpt.make_state_dict(man, 4)[man[0][0]])
+
+
+def test_old_transeg_state_dict_layout_matches_reference_manifest():
+    m = networks.TRANSEG(in_channels=1, out_channels=8, img_size=(96, 96, 96), feature_size=16, hidden_size=768, mlp_dim=3072,
+                         num_heads=12, pos_embed="perceptron", norm_name="instance", res_block=True, conv_block=True)
+    assert _manifest_of(m) == _want("transeg_old_96")
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree only exists in the build container")
+def test_variant_constructors_match_live_reference_layout():
+    ref = ref_loader.build_dose(32, multiS_conv=False, act="relu")
+    ours = networks.Model(9, 1, [-1, 16, 32, 64, 128, 256], img_size=(32, 32, 32), multiS_conv=False, act="relu")
+    assert _manifest_of(ours) == _manifest_of(ref)
+    ours.load_state_dict(ref.state_dict(), strict=True)

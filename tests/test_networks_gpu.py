@@ -158,3 +158,31 @@ def test_sliding_window_cascade_matches_reference_fixture():
     assert (logits.argmax(1) == want_logits.argmax(1)).float().mean().item() >= ARGMAX_MIN
     assert torch.equal(casc.structures.cpu(), st)            # hand-off of the blended logits is bit exact
     assert _rel(dose, want_dose) < DOSE_TOL
+
+
+def test_old_transeg_32_matches_reference_fixture():
+    from dose_prediction_b200 import networks, synth
+    from oracle import synth_ckpt
+    man = [(k, ([1, 8, s[2]] if k.endswith("position_embeddings") else s)) for k, s, *_ in load_manifest("transeg_old_96")]
+    sd = synth_ckpt.make_state_dict(man, seed=2)
+    m = networks.TRANSEG(1, 8, (32,) * 3, pos_embed="perceptron").eval()
+    m.load_state_dict(sd, strict=True)
+    g = torch.from_numpy(np.load(os.path.join(GOLDEN, "seg_old32.npz"))["logits"])
+    out = m.to("cuda:0")(synth.make_batch(2, 32, seed=1234)["ct"][:1].cuda()).cpu()
+    assert _rel(out, g) < LOGIT_TOL
+    assert (out.argmax(1) == g.argmax(1)).float().mean().item() >= ARGMAX_MIN
+
+
+def test_dose_pyfer_dual_dilated_relu_variant_matches_oracle():
+    """multiS_conv=False (DualDilatedBlock, dilation 1/2/3) + act='relu' — reachable through tune_light_pyfer.py:161-162."""
+    from dose_prediction_b200 import networks, synth
+    from oracle import synth_ckpt, torch_ref
+    m = networks.Model(9, 1, [-1, 16, 32, 64, 128, 256], img_size=(32,) * 3, multiS_conv=False, act="relu").eval()
+    sd = synth_ckpt.make_state_dict(synth_ckpt.manifest_of(m), seed=7)
+    m.load_state_dict(sd, strict=True)
+    x = synth.make_batch(1, 32, seed=5)["dose_input"]
+    with torch.no_grad():
+        want = torch_ref.dose_pyfer_forward(sd, x, act="relu", multiS_conv=False)
+    out = m.to("cuda:0")(x.cuda())
+    assert _rel(out[1][0], want[1][0]) < DOSE_TOL
+    assert _rel(out[0], want[0]) < DOSE_TOL

@@ -104,3 +104,13 @@ def test_restatement_equals_live_reference_modules():
 def test_manifests_are_current():
     got = [tuple(e) for e in synth_ckpt.manifest_of(ref_loader.build_seg(128))]
     assert got == load_manifest("oar_transeg")
+
+
+def test_transeg_old_matches_reference_fixture():
+    man = [(k, ([1, 8, s[2]] if k.endswith("position_embeddings") else s)) for k, s, *_ in load_manifest("transeg_old_96")]
+    sd = synth_ckpt.make_state_dict(man, seed=2)
+    vol = synth.make_batch(2, 32, seed=1234)
+    g = torch.from_numpy(np.load(os.path.join(GOLDEN, "seg_old32.npz"))["logits"])
+    with torch.no_grad():
+        out = torch_ref.oar_transeg_forward(sd, vol["ct"][:1], old=True)
+    assert torch_ref.rel_l2(out, g) < TOL
