@@ -141,9 +141,9 @@ class _TransformerBlock(nn.Module):
 class _PatchEmbedding(nn.Module):
     def __init__(self, in_channels, img_size, patch_size, hidden, pos_embed, p):
         super().__init__()
-        if pos_embed != "perceptron":
-            raise NotImplementedError("only pos_embed='perceptron' (what both reference nets use) is built; "
-                                      "'conv' is a SURVEY 8(f2) follow-up")
+        if pos_embed not in ("perceptron", "conv"):
+            raise ValueError(f"unsupported pos_embed {pos_embed!r}")
+        self.pos_embed = pos_embed
         for m, q in zip(img_size, patch_size):
             if m < q:
                 raise ValueError("patch_size should be smaller than img_size.")
@@ -151,14 +151,18 @@ class _PatchEmbedding(nn.Module):
                 raise ValueError("patch_size should be divisible by img_size for perceptron.")
         self.n_patches = int(np.prod([i // q for i, q in zip(img_size, patch_size)]))
         self.patch_dim = int(in_channels * np.prod(patch_size))
-        self.patch_embeddings = nn.Sequential(nn.Identity(), nn.Linear(self.patch_dim, hidden))
+        if pos_embed == "conv":      # monai: Conv3d(kernel = stride = patch) then flatten(2).transpose(-1,-2)
+            self.patch_embeddings = nn.Conv3d(in_channels, hidden, kernel_size=patch_size, stride=patch_size)
+        else:
+            self.patch_embeddings = nn.Sequential(nn.Identity(), nn.Linear(self.patch_dim, hidden))
         self.position_embeddings = nn.Parameter(torch.zeros(1, self.n_patches, hidden))
         self.cls_token = nn.Parameter(torch.zeros(1, 1, hidden))
         self.dropout = nn.Dropout(p)
         nn.init.trunc_normal_(self.position_embeddings, mean=0.0, std=0.02, a=-2.0, b=2.0)
-        lin = self.patch_embeddings[1]
-        nn.init.trunc_normal_(lin.weight, mean=0.0, std=0.02, a=-2.0, b=2.0)
-        nn.init.constant_(lin.bias, 0)
+        if pos_embed == "perceptron":
+            lin = self.patch_embeddings[1]
+            nn.init.trunc_normal_(lin.weight, mean=0.0, std=0.02, a=-2.0, b=2.0)
+            nn.init.constant_(lin.bias, 0)
 
 
 class ViT(nn.Module):
@@ -187,6 +191,26 @@ class UnetResBlock(nn.Module):
         self.lrelu = nn.LeakyReLU(inplace=True, negative_slope=0.01)
         self.norm1, self.norm2, self.norm3 = (nn.InstanceNorm3d(out_channels) for _ in range(3))
         self.downsample = in_channels != out_channels or stride != 1
+
+
+class UnetBasicBlock(nn.Module):
+    """monai dynunet_block.UnetBasicBlock: conv -> IN -> lrelu -> conv -> IN -> lrelu (k3, no bias)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=3, stride=1):
+        super().__init__()
+        self.conv1 = _conv_layer(in_channels, out_channels, kernel_size, stride)
+        self.conv2 = _conv_layer(out_channels, out_channels, kernel_size, 1)
+        self.lrelu = nn.LeakyReLU(inplace=True, negative_slope=0.01)
+        self.norm1, self.norm2 = nn.InstanceNorm3d(out_channels), nn.InstanceNorm3d(out_channels)
+
+
+class UnetrUpBlock(nn.Module):
+    """monai unetr_block.UnetrUpBlock (res_block=False), the decoder of PyMSCDecoder(mode_multi=False)."""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.transp_conv = _conv_layer(in_channels, out_channels, 2, 2, transposed=True)
+        self.conv_block = UnetBasicBlock(out_channels + out_channels, out_channels)
 
 
 class UnetrBasicBlock(nn.Module):
@@ -432,9 +456,13 @@ def _emit_vit(P, vit, parts, N, S, taps):
         slots += [base + c for c in range(a.C)]
         base += blocks16(a.C) * 8
     K = ncb * 4096 * 8
-    lin = vit.patch_embedding.patch_embeddings[1]
     Cin = len(slots)
-    w = lin.weight.detach().to(P.device, torch.float32).view(hidden, 16, 16, 16, Cin)
+    if vit.patch_embedding.pos_embed == "conv":      # Conv3d weight [hidden, C, 16,16,16] == Linear over (c, p1, p2, p3)
+        lin = vit.patch_embedding.patch_embeddings
+        w = lin.weight.detach().to(P.device, torch.float32).permute(0, 2, 3, 4, 1).contiguous()
+    else:
+        lin = vit.patch_embedding.patch_embeddings[1]
+        w = lin.weight.detach().to(P.device, torch.float32).view(hidden, 16, 16, 16, Cin)
     wfull = torch.zeros((hidden, 16, 16, 16, ncb * 8), device=P.device)
     wfull[..., torch.tensor(slots, device=P.device)] = w
     wpe = wfull.view(hidden, 16, 16, 16, ncb, 8).permute(0, 4, 1, 2, 3, 5).reshape(hidden, K).contiguous().half()
@@ -596,9 +624,27 @@ def _emit_conv_3_1_old(P, blk, parts, out, prec):
     P.pointwise(ys, blk.conv.weight, blk.conv.bias, out_act=out)
 
 
+def _emit_basic_block(P, blk, parts, out, prec):
+    """monai UnetBasicBlock.forward."""
+    N, dims = parts[0].N, parts[0].dims
+    Co = blk.conv1.conv.weight.shape[0]
+    one, zero = P.affine(Co)
+    raw = P.get_raw(N, Co, dims)
+    P.conv_tc(parts, blk.conv1.conv.weight, 3, 1, prec.conv3, one, zero, False, out_raw=raw)
+    a = P.new_act(N, Co, dims, lo=prec.lo)
+    P.norm_act(raw, a, act="lrelu")
+    P.release(raw)
+    raw = P.get_raw(N, Co, dims)
+    P.conv_tc([a], blk.conv2.conv.weight, 3, 1, prec.conv3, one, zero, False, out_raw=raw)
+    P.norm_act(raw, out, act="lrelu")
+    P.release(raw)
+
+
 def _emit_up_block(P, blk, inp, skip_slot_pair, out, prec):
-    """base_blocks.py:136-141: deconv -> cat(out, skip) -> MultiUnetBasicBlock."""
+    """base_blocks.py:136-141: deconv -> cat(out, skip) -> MultiUnetBasicBlock (or monai UnetrUpBlock.forward)."""
     P.deconv2x(inp, blk.transp_conv.conv.weight, skip_slot_pair[0])
+    if isinstance(blk, UnetrUpBlock):
+        return _emit_basic_block(P, blk.conv_block, skip_slot_pair, out, prec)
     cov = blk.conv_block.cov_
     if isinstance(cov, conv_3_1_old):
         _emit_conv_3_1_old(P, cov, skip_slot_pair, out, prec)
@@ -718,12 +764,14 @@ class PyMSCDecoder(nn.Module):
     def __init__(self, feature_size: int = 16, hidden_size: int = 768, norm_name: Union[Tuple, str] = "instance",
                  spatial_dims: int = 3, mode_multi: bool = False, act="relu", multiS_conv=True) -> None:
         super().__init__()
-        if not mode_multi:
-            raise NotImplementedError("mode_multi_dec=False (monai UnetrUpBlock decoders) is a SURVEY 8(f2) follow-up")
         chans = [hidden_size, feature_size * 8, feature_size * 4, feature_size * 2, feature_size]
         for i, name in enumerate(("decoder4", "decoder3", "decoder2", "decoder1")):
-            setattr(self, name, ModifiedUnetrUpBlock(spatial_dims=spatial_dims, in_channels=chans[i], out_channels=chans[i + 1],
-                                                     upsample_kernel_size=2, act=act, multiS_conv=multiS_conv))
+            if mode_multi:
+                blk = ModifiedUnetrUpBlock(spatial_dims=spatial_dims, in_channels=chans[i], out_channels=chans[i + 1],
+                                           upsample_kernel_size=2, act=act, multiS_conv=multiS_conv)
+            else:
+                blk = UnetrUpBlock(chans[i], chans[i + 1])
+            setattr(self, name, blk)
 
 
 class MainSubsetModel(nn.Module):

@@ -121,7 +121,11 @@ def vit(sd: SD, p: str, x, num_layers: int, num_heads: int, patch: int = 16):
     t = x.reshape(b, c, g[0], patch, g[1], patch, g[2], patch)
     t = t.permute(0, 2, 4, 6, 3, 5, 7, 1).reshape(b, g[0] * g[1] * g[2], patch ** 3 * c)
     q = p + "patch_embedding."
-    t = _linear(sd, q + "patch_embeddings.1.", t)
+    if q + "patch_embeddings.weight" in sd:       # pos_embed="conv": Conv3d(kernel=stride=patch), flatten(2).transpose
+        xq, wq = _q(x, sd[q + "patch_embeddings.weight"], q + "patch_embeddings.", "linear")
+        t = F.conv3d(xq, wq, sd[q + "patch_embeddings.bias"], stride=patch).flatten(2).transpose(-1, -2)
+    else:
+        t = _linear(sd, q + "patch_embeddings.1.", t)
     t = t + sd[q + "position_embeddings"]
     hidden = t.shape[-1]
     d = hidden // num_heads
@@ -167,6 +171,12 @@ def unet_res_block(sd: SD, p: str, x):
     elif EMU is not None:
         r = _q(x, x, p + "residual.", "store")[0]
     return _act(y + r, "lrelu")
+
+
+def unet_basic_block(sd: SD, p: str, x):
+    """monai: dynunet_block.UnetBasicBlock.forward (k3 s1, instance norm, LeakyReLU 0.01)."""
+    y = _act(_inorm(_conv(sd, p + "conv1.conv.", x, padding=1)), "lrelu")
+    return _act(_inorm(_conv(sd, p + "conv2.conv.", y, padding=1)), "lrelu")
 
 
 def unetr_pr_up_block(sd: SD, p: str, x, num_layer: int):
@@ -221,6 +231,8 @@ def conv_3_1_old(sd: SD, p: str, x):
 def modified_unetr_up_block(sd: SD, p: str, inp, skip, act: str, multiS_conv: bool = True, old: bool = False):
     """OARSegmentation/Models/Nets/base_blocks.py:136-141 (OldModels/Nets/base_blocks.py:127-132 when old)."""
     out = torch.cat((_deconv2(sd, p + "transp_conv.conv.", inp), skip), dim=1)
+    if p + "conv_block.conv1.conv.weight" in sd:   # monai UnetrUpBlock (PyMSCDecoder mode_multi=False, dose_pyfer.py:164-171)
+        return unet_basic_block(sd, p + "conv_block.", out)
     if old:
         return conv_3_1_old(sd, p + "conv_block.cov_.", out)
     blk = conv_3_1 if multiS_conv else dual_dilated_block

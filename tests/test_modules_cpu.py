@@ -79,3 +79,9 @@ def test_variant_constructors_match_live_reference_layout():
     ours = networks.Model(9, 1, [-1, 16, 32, 64, 128, 256], img_size=(32, 32, 32), multiS_conv=False, act="relu")
     assert _manifest_of(ours) == _manifest_of(ref)
     ours.load_state_dict(ref.state_dict(), strict=True)
+    ref2 = ref_loader.build_dose(32, mode_multi_dec=False)
+    ours2 = networks.Model(9, 1, [-1, 16, 32, 64, 128, 256], img_size=(32, 32, 32), mode_multi_dec=False)
+    assert _manifest_of(ours2) == _manifest_of(ref2)
+    ref3 = ref_loader.build_seg(32, pos_embed="conv")
+    ours3 = networks.OARTranseg(1, 8, (32, 32, 32), pos_embed="conv")
+    assert _manifest_of(ours3) == _manifest_of(ref3)

@@ -186,3 +186,26 @@ def test_dose_pyfer_dual_dilated_relu_variant_matches_oracle():
     out = m.to("cuda:0")(x.cuda())
     assert _rel(out[1][0], want[1][0]) < DOSE_TOL
     assert _rel(out[0], want[0]) < DOSE_TOL
+
+
+def test_unetr_up_block_decoder_and_conv_patch_embedding_variants_match_oracle():
+    """mode_multi_dec=False (monai UnetrUpBlock decoders, dose_pyfer.py:164-230) and pos_embed='conv'."""
+    from dose_prediction_b200 import networks, synth
+    from oracle import synth_ckpt, torch_ref
+    m = networks.Model(9, 1, [-1, 16, 32, 64, 128, 256], img_size=(32,) * 3, mode_multi_dec=False).eval()
+    sd = synth_ckpt.make_state_dict(synth_ckpt.manifest_of(m), seed=8)
+    m.load_state_dict(sd, strict=True)
+    x = synth.make_batch(1, 32, seed=6)["dose_input"]
+    with torch.no_grad():
+        want = torch_ref.dose_pyfer_forward(sd, x)
+    out = m.to("cuda:0")(x.cuda())
+    assert all(_rel(a, b) < DOSE_TOL for a, b in zip(out[1], want[1]))
+    s = networks.OARTranseg(1, 8, (32,) * 3, pos_embed="conv").eval()
+    ssd = synth_ckpt.make_state_dict(synth_ckpt.manifest_of(s), seed=9)
+    s.load_state_dict(ssd, strict=True)
+    ct = synth.make_batch(1, 32, seed=6)["ct"]
+    with torch.no_grad():
+        want_l = torch_ref.oar_transeg_forward(ssd, ct)
+    got = s.to("cuda:0")(ct.cuda()).cpu()
+    assert _rel(got, want_l) < LOGIT_TOL
+    assert (got.argmax(1) == want_l.argmax(1)).float().mean().item() >= ARGMAX_MIN
