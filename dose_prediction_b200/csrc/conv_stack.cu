@@ -6,8 +6,11 @@
 // N dimension instead: for one INPUT plane, one in-plane tap (kh,kw) and one 16-channel chunk, a single
 // MMA with B = [W(kd=k-1) | ... | W(kd=0)]  (N = k*C_out = 112 / 224 for 7^3) updates the accumulators of
 // the k OUTPUT planes that input plane contributes to.  The accumulators of consecutive output planes
-// live in a ring of G column groups in TMEM; the window of k planes slides by one group per input plane,
-// so B never has to be rotated.  A is read once per k taps: 4.2x fewer shared-memory wavefronts.
+// live in a ring of G = k+1 column groups per tile in TMEM (slot = plane counter mod G).  The weights are
+// stored in G pre-rotated copies, each with one all-zero group, so that for input plane dz the copy
+// rot = slot(dz - pad) has, at row block s, exactly the depth tap that ring slot s needs (and zeros for the
+// one slot that is being drained): a single MMA with N = G*C_out covers the whole ring — no wrap-around
+// splits, B is never rotated at run time (the producer just picks the copy).  A is read once per k taps.
 //
 // A CTA owns T adjacent 16(H) x 8(W) tiles (one wide TMA halo patch, B shared by the T tiles) and marches
 // along a segment of L output planes; work items = (image, D segment, H tile, W tile group), persistent.
@@ -28,12 +31,12 @@ struct StackParams {
   int n_chunks, cb_total_in;
   int cout;                 // N0
   int T, G, L;              // tiles per CTA, ring slots, segment length
-  int khs, n_khg;           // kh rows per B stage
+  int tps, n_bst;           // taps per weight stage, weight stages per (plane, chunk)
   int PH, PWw;
   int a_stages, b_stages;
   uint32_t a_bytes, a_stride, b_bytes, b_stride, b_off;
   int tiles_h, wgroups, nseg, num_items, tiles_w;
-  const __half* wpack;      // [chunk][kh][kw][2][k*cout][8]
+  const __half* wpack;      // [G rotations][chunk][kh][kw][2][G*cout][8]
   const float* scale;
   const float* shift;
   int relu;
@@ -87,6 +90,18 @@ __device__ __forceinline__ float colsum16s(const float (&v)[16], int lane) {
   return r;
 }
 
+// NT consecutive kw taps x TT tiles, fully unrolled with constant operand offsets (lets ptxas batch the
+// descriptor moves): tap j of tile t uses A start + j + 8t, B start + j*tap_b16, accumulator tmem + t*tile_cols.
+template <int NT, int TT>
+__device__ __forceinline__ void issue_taps(uint32_t tmem, uint32_t tile_cols, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                           uint32_t b_hi, uint32_t tap_b16, uint32_t idesc) {
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+#pragma unroll
+    for (int t = 0; t < TT; ++t) umma_split(tmem + t * tile_cols, a_lo + j + t * 8, a_hi, b_lo + j * tap_b16, b_hi, idesc, 1u);
+  }
+}
+
 struct Item {
   int n, d0, d1, z0, z1, h0, w0, ntile;
 };
@@ -110,7 +125,7 @@ __device__ __forceinline__ Item decode_item(const StackParams& p, int item) {
   return it;
 }
 
-template <int KS>
+template <int KS, int TT>
 __global__ void __launch_bounds__(kStackThreads, 1)
 conv3d_stack_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ StackParams p) {
   constexpr int pad = (KS - 1) / 2;
@@ -131,7 +146,7 @@ conv3d_stack_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_co
     tma_prefetch_desc(&tmap_in);
     for (int i = 0; i < p.a_stages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < p.b_stages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i < p.G; ++i) { mbar_init(&done_bar[i], 1); mbar_init(&free_bar[i], kStackEpiWarps); }
+    for (int i = 0; i <= KS; ++i) { mbar_init(&done_bar[i], 1); mbar_init(&free_bar[i], kStackEpiWarps); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(&tmem_base_smem);
@@ -142,16 +157,22 @@ conv3d_stack_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
 
-  const uint32_t tap_b_bytes = 32u * KS * N0;            // one tap: [2][KS*N0][8] fp16
-  const size_t chunk_w_halfs = static_cast<size_t>(KS) * KS * 16 * KS * N0;
+  constexpr int G = KS + 1;                               // ring slots per tile (power of two for k = 3, 7)
+  constexpr uint32_t gmask = G - 1;
+  constexpr uint32_t gshift = (G == 8) ? 3 : 2;
+  const uint32_t tap_b_bytes = 32u * G * N0;              // one tap: [2][G*N0][8] fp16
+  const size_t chunk_w_halfs = static_cast<size_t>(KS) * KS * 16 * G * N0;
+  const size_t rot_w_halfs = chunk_w_halfs * p.n_chunks;
 
   if (warp == 0) {
     // ===================================================================== producer
     int ia = 0, ib = 0;
     uint32_t pa = 0, pb = 0;
+    uint32_t pc_base = 0;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
       const Item it = decode_item<KS>(p, item);
       for (int dz = it.z0; dz <= it.z1; ++dz) {
+        const uint32_t rot = (pc_base + static_cast<uint32_t>(dz - pad - it.d0)) & gmask;   // slot of (virtual) plane dz-pad
         for (int c = 0; c < p.n_chunks; ++c) {
           if (!mbar_wait_relaxed(&a_empty[ia], pa ^ 1, p.err_flag)) goto teardown;
           if (elect_one()) {
@@ -165,17 +186,19 @@ conv3d_stack_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_co
           }
           __syncwarp();
           if (++ia == p.a_stages) { ia = 0; pa ^= 1; }
-          for (int g = 0; g < p.n_khg; ++g) {
-            const int kh0 = g * p.khs;
-            const int cnt = min(p.khs, KS - kh0);
+          const __half* wsrc = p.wpack + rot * rot_w_halfs + static_cast<size_t>(c) * chunk_w_halfs;
+          for (int g = 0; g < p.n_bst; ++g) {
+            const int t0 = g * p.tps;
+            const int cnt = min(p.tps, KS * KS - t0);
             if (!mbar_wait_relaxed(&b_empty[ib], pb ^ 1, p.err_flag)) goto teardown;
             if (elect_one()) {
-              const uint32_t bytes = static_cast<uint32_t>(cnt * KS) * tap_b_bytes;
-              if (p.debug & 1) { mbar_arrive(&b_full[ib]); } else {
-              mbar_arrive_expect_tx(&b_full[ib], bytes);
-              bulk_load_1d(smem + p.b_off + static_cast<size_t>(ib) * p.b_stride,
-                           p.wpack + static_cast<size_t>(c) * chunk_w_halfs + static_cast<size_t>(kh0) * KS * (tap_b_bytes / 2),
-                           bytes, &b_full[ib]);
+              const uint32_t bytes = static_cast<uint32_t>(cnt) * tap_b_bytes;
+              if (p.debug & 1) {
+                mbar_arrive(&b_full[ib]);
+              } else {
+                mbar_arrive_expect_tx(&b_full[ib], bytes);
+                bulk_load_1d(smem + p.b_off + static_cast<size_t>(ib) * p.b_stride, wsrc + static_cast<size_t>(t0) * (tap_b_bytes / 2), bytes,
+                             &b_full[ib]);
               }
             }
             __syncwarp();
@@ -183,51 +206,56 @@ conv3d_stack_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_co
           }
         }
       }
+      pc_base += static_cast<uint32_t>(it.d1 - it.d0);
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
+    // One elected thread runs this role.  Issue cost is ~5.5 cycles per SASS instruction of THIS thread
+    // (scripts/micro/mma_rate.cu), so the interior-plane path is fully unrolled per kernel row.
+    if (elect_one()) {
     const uint32_t idesc0 = make_idesc_f16(128, 0);
+    const uint32_t idesc_full = idesc0 | (static_cast<uint32_t>((G * N0) >> 3) << 17);
     const uint32_t a_lo_c = (static_cast<uint32_t>(p.PH * p.PWw) & 0x3FFFu) << 16;   // LBO: c8-block pitch
     const uint32_t a_hi = (static_cast<uint32_t>(p.PWw) & 0x3FFFu) | (1u << 14);     // SBO: patch row pitch
-    const uint32_t b_lo_c = (static_cast<uint32_t>(KS * N0) & 0x3FFFu) << 16;        // LBO: k-half pitch = rows*16 B
+    const uint32_t b_lo_c = (static_cast<uint32_t>(G * N0) & 0x3FFFu) << 16;         // LBO: k-half pitch = rows*16 B
     const uint32_t b_hi = 8u | (1u << 14);                                           // SBO: 128 B
     const uint32_t tap_b16 = tap_b_bytes >> 4;
-    const int G = p.G;
-    const uint32_t gmask = static_cast<uint32_t>(G - 1);
-    const uint32_t gshift = static_cast<uint32_t>(__ffs(G) - 1);
+    const uint32_t tile_cols = static_cast<uint32_t>(G * N0);
+    const uint32_t smem16 = smem_u32(smem) >> 4;
+    const uint32_t a_stride16 = p.a_stride >> 4, b_stride16 = p.b_stride >> 4, b_off16 = p.b_off >> 4;
     int ia = 0, ib = 0;
     uint32_t pa = 0, pb = 0;
     uint32_t pc_base = 0;                      // running plane counter of this item's plane d0
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
       const Item it = decode_item<KS>(p, item);
+      const bool all_tiles = (it.ntile == TT);
       for (int dz = it.z0; dz <= it.z1; ++dz) {
         // output planes fed by this input plane, oldest first
         const int p_lo = max(dz - pad, it.d0), p_hi = min(dz + pad, it.d1 - 1);
         const int nw = p_hi - p_lo + 1;
-        const int j0 = p_lo - (dz - pad);                       // B group of p_lo: kd = KS-1-j
         const int n_new = (dz == it.z0) ? nw : ((dz + pad <= it.d1 - 1) ? 1 : 0);
         const int n_old = nw - n_new;
         const uint32_t pc_lo = pc_base + static_cast<uint32_t>(p_lo - it.d0);
         const int slot_lo = static_cast<int>(pc_lo & gmask);
+        const bool fast = (nw == KS) && all_tiles;            // interior plane: one MMA per tile covers the ring
         // new planes: their ring slot must have been drained by the epilogue
         for (int i = n_old; i < nw; ++i) {
           const uint32_t pc = pc_lo + i;
           if (!mbar_wait(&free_bar[pc & gmask], ((pc >> gshift) & 1) ^ 1, p.err_flag)) goto teardown;
         }
         tc_fence_after();
-        // MMA pieces: contiguous runs of ring slots with one accumulate flag.  Regular taps: the window split
-        // at the ring wrap (<= 2 pieces).  The first tap of this input plane additionally splits old | new.
-        uint32_t pc_d[2], pc_b[2], pc_i[2];      // regular: TMEM column offset, B row offset (16 B units), idesc
+        // MMA pieces = contiguous runs of ring slots with one accumulate flag (B row block == ring slot in the
+        // rotated weight copy).  pc_*: regular taps of a clipped window; fp_*: first tap (old | new planes).
+        uint32_t pc_o[2], pc_i[2];
         int npc = 0;
-        uint32_t fp_d[4], fp_b[4], fp_i[4], fp_acc[4];
+        uint32_t fp_o[4], fp_i[4], fp_acc[4];
         int nfp = 0;
         {
           int i0 = 0;
           while (i0 < nw) {
-            const int s = (slot_lo + i0) & static_cast<int>(gmask);
-            const int len = min(nw - i0, G - s);
-            pc_d[npc] = static_cast<uint32_t>(s * N0);
-            pc_b[npc] = static_cast<uint32_t>((j0 + i0) * N0);
+            const int sl = (slot_lo + i0) & static_cast<int>(gmask);
+            const int len = min(nw - i0, G - sl);
+            pc_o[npc] = static_cast<uint32_t>(sl * N0);
             pc_i[npc] = idesc0 | (static_cast<uint32_t>((len * N0) >> 3) << 17);
             ++npc;
             i0 += len;
@@ -236,10 +264,9 @@ conv3d_stack_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_co
             int a0 = r == 0 ? 0 : n_old;
             const int a1 = r == 0 ? n_old : nw;
             while (a0 < a1) {
-              const int s = (slot_lo + a0) & static_cast<int>(gmask);
-              const int len = min(a1 - a0, G - s);
-              fp_d[nfp] = static_cast<uint32_t>(s * N0);
-              fp_b[nfp] = static_cast<uint32_t>((j0 + a0) * N0);
+              const int sl = (slot_lo + a0) & static_cast<int>(gmask);
+              const int len = min(a1 - a0, G - sl);
+              fp_o[nfp] = static_cast<uint32_t>(sl * N0);
               fp_i[nfp] = idesc0 | (static_cast<uint32_t>((len * N0) >> 3) << 17);
               fp_acc[nfp] = r == 0 ? 1u : 0u;
               ++nfp;
@@ -250,58 +277,68 @@ conv3d_stack_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_co
         bool first_tap = true;
         for (int c = 0; c < p.n_chunks; ++c) {
           if (!mbar_wait(&a_full[ia], pa, p.err_flag)) goto teardown;
-          const uint32_t sa16 = smem_u32(smem + static_cast<size_t>(ia) * p.a_stride) >> 4;
-          for (int g = 0; g < p.n_khg; ++g) {
-            const int kh0 = g * p.khs;
-            const int cnt = min(p.khs, KS - kh0);
+          const uint32_t a_c = a_lo_c + smem16 + static_cast<uint32_t>(ia) * a_stride16;
+          int kh = 0, kw = 0;
+          uint32_t a_row = a_c;                                  // descriptor low word of (kh, kw = 0), tile 0
+          for (int g = 0; g < p.n_bst; ++g) {
+            const int cnt = min(p.tps, KS * KS - g * p.tps);
             if (!mbar_wait(&b_full[ib], pb, p.err_flag)) goto teardown;
             tc_fence_after();
-            if (elect_one()) {
-              const uint32_t sb16 = smem_u32(smem + p.b_off + static_cast<size_t>(ib) * p.b_stride) >> 4;
-              for (int khl = 0; khl < cnt; ++khl) {
-                uint32_t a_tap = sa16 + static_cast<uint32_t>((kh0 + khl) * p.PWw);
-                uint32_t b_tap = sb16 + static_cast<uint32_t>(khl * KS) * tap_b16;
-#pragma unroll
-                for (int kw = 0; kw < KS; ++kw) {
-                  if (first_tap) {
-                    for (int q = 0; q < nfp; ++q)
-                      for (int t = 0; t < it.ntile; ++t)
-                        umma_split(tmem_base + static_cast<uint32_t>(t * G * N0) + fp_d[q], a_lo_c | ((a_tap + t * 8) & 0x3FFFu), a_hi,
-                                   b_lo_c | ((b_tap + fp_b[q]) & 0x3FFFu), b_hi, fp_i[q], fp_acc[q]);
-                    first_tap = false;
-                  } else {
-                    for (int q = 0; q < npc; ++q)
-                      for (int t = 0; t < it.ntile; ++t)
-                        umma_split(tmem_base + static_cast<uint32_t>(t * G * N0) + pc_d[q], a_lo_c | ((a_tap + t * 8) & 0x3FFFu), a_hi,
-                                   b_lo_c | ((b_tap + pc_b[q]) & 0x3FFFu), b_hi, pc_i[q], 1u);
-                  }
-                  a_tap += 1;
-                  b_tap += tap_b16;
-                }
-              }
-              umma_commit(&b_empty[ib]);
+            uint32_t b_lo = b_lo_c + smem16 + b_off16 + static_cast<uint32_t>(ib) * b_stride16;
+            int tl = 0;
+            if (first_tap) {
+              for (int q = 0; q < nfp; ++q)
+                for (int t = 0; t < it.ntile; ++t)
+                  umma_split(tmem_base + t * tile_cols + fp_o[q], a_row + kw + t * 8, a_hi, b_lo + fp_o[q], b_hi, fp_i[q], fp_acc[q]);
+              first_tap = false;
+              b_lo += tap_b16;
+              if (++kw == KS) { kw = 0; ++kh; a_row += p.PWw; }
+              tl = 1;
             }
-            __syncwarp();
-            first_tap = false;
+            if (fast) {
+              while (tl < cnt) {
+                const int seg = min(cnt - tl, KS - kw);           // taps left in this kernel row
+                const uint32_t a_lo = a_row + kw;
+                switch (seg) {
+                  case 7: issue_taps<7, TT>(tmem_base, tile_cols, a_lo, a_hi, b_lo, b_hi, tap_b16, idesc_full); break;
+                  case 6: issue_taps<6, TT>(tmem_base, tile_cols, a_lo, a_hi, b_lo, b_hi, tap_b16, idesc_full); break;
+                  case 5: issue_taps<5, TT>(tmem_base, tile_cols, a_lo, a_hi, b_lo, b_hi, tap_b16, idesc_full); break;
+                  case 4: issue_taps<4, TT>(tmem_base, tile_cols, a_lo, a_hi, b_lo, b_hi, tap_b16, idesc_full); break;
+                  case 3: issue_taps<3, TT>(tmem_base, tile_cols, a_lo, a_hi, b_lo, b_hi, tap_b16, idesc_full); break;
+                  case 2: issue_taps<2, TT>(tmem_base, tile_cols, a_lo, a_hi, b_lo, b_hi, tap_b16, idesc_full); break;
+                  default: issue_taps<1, TT>(tmem_base, tile_cols, a_lo, a_hi, b_lo, b_hi, tap_b16, idesc_full); break;
+                }
+                tl += seg;
+                b_lo += seg * tap_b16;
+                kw += seg;
+                if (kw == KS) { kw = 0; a_row += p.PWw; }
+              }
+            } else {
+              for (; tl < cnt; ++tl) {
+                for (int q = 0; q < npc; ++q)
+                  for (int t = 0; t < it.ntile; ++t)
+                    umma_split(tmem_base + t * tile_cols + pc_o[q], a_row + kw + t * 8, a_hi, b_lo + pc_o[q], b_hi, pc_i[q], 1u);
+                b_lo += tap_b16;
+                if (++kw == KS) { kw = 0; a_row += p.PWw; }
+              }
+            }
+            umma_commit(&b_empty[ib]);
             if (++ib == p.b_stages) { ib = 0; pb ^= 1; }
           }
-          if (elect_one()) umma_commit(&a_empty[ia]);
-          __syncwarp();
+          umma_commit(&a_empty[ia]);
           if (++ia == p.a_stages) { ia = 0; pa ^= 1; }
         }
         // planes completed by this input plane
-        if (elect_one()) {
-          if (dz < it.z1) {
-            const int pdone = dz - pad;
-            if (pdone >= it.d0) umma_commit(&done_bar[(pc_base + static_cast<uint32_t>(pdone - it.d0)) & gmask]);
-          } else {
-            for (int q = max(it.d0, it.z1 - pad); q < it.d1; ++q)
-              umma_commit(&done_bar[(pc_base + static_cast<uint32_t>(q - it.d0)) & gmask]);
-          }
+        if (dz < it.z1) {
+          const int pdone = dz - pad;
+          if (pdone >= it.d0) umma_commit(&done_bar[(pc_base + static_cast<uint32_t>(pdone - it.d0)) & gmask]);
+        } else {
+          for (int q = max(it.d0, it.z1 - pad); q < it.d1; ++q)
+            umma_commit(&done_bar[(pc_base + static_cast<uint32_t>(q - it.d0)) & gmask]);
         }
-        __syncwarp();
       }
       pc_base += static_cast<uint32_t>(it.d1 - it.d0);
+    }
     }
   } else {
     // ===================================================================== epilogue (warps 2..9)
@@ -312,7 +349,6 @@ conv3d_stack_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_co
     const int row = quarter * 32 + lane;
     const int hl = row >> 3, wl = row & 7;
     const int mycol = (lane >> 1) & 15;
-    const int G = p.G;
     int cur_n = -1;
     uint32_t pc = 0;
     auto flush_stats = [&](int n) {
@@ -332,8 +368,8 @@ conv3d_stack_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_co
       if (it.n != cur_n) { flush_stats(cur_n); cur_n = it.n; }
       const int h = it.h0 + hl;
       for (int d = it.d0; d < it.d1; ++d, ++pc) {
-        const int slot = static_cast<int>(pc & static_cast<uint32_t>(G - 1));
-        if (!mbar_wait_relaxed(&done_bar[slot], (pc >> (__ffs(G) - 1)) & 1, p.err_flag)) goto teardown;
+        const int slot = static_cast<int>(pc & gmask);
+        if (!mbar_wait_relaxed(&done_bar[slot], (pc >> gshift) & 1, p.err_flag)) goto teardown;
         tc_fence_after();
         for (int t = tgrp; t < it.ntile; t += 2) {
           const int w = it.w0 + t * 8 + wl;
@@ -413,7 +449,7 @@ extern "C" int dp_conv3d_stack(const void* in_c8, int cb_total_in, const uint8_t
                                int seg_len, int tiles_per_cta, cudaStream_t stream) {
   using namespace dp;
   DP_REQUIRE(k == 3 || k == 7, "dp_conv3d_stack: kernel size %d unsupported (3 or 7)", k);
-  DP_REQUIRE((cout == 16 || cout == 32) && k * cout <= 256, "dp_conv3d_stack: C_out=%d unsupported (16 or 32)", cout);
+  DP_REQUIRE((cout == 16 || cout == 32) && (k + 1) * cout <= 256, "dp_conv3d_stack: C_out=%d unsupported (16 or 32)", cout);
   DP_REQUIRE(n_chunks >= 1 && n_chunks <= 96, "dp_conv3d_stack: n_chunks=%d out of range", n_chunks);
   DP_REQUIRE(out_f32 != nullptr || out_hi != nullptr, "dp_conv3d_stack: no output tensor given");
   StackParams p{};
@@ -422,14 +458,13 @@ extern "C" int dp_conv3d_stack(const void* in_c8, int cb_total_in, const uint8_t
   p.tiles_h = (H + 15) / 16;
   p.tiles_w = (W + 7) / 8;
   // tiles per CTA: share B between as many W tiles as TMEM allows while keeping a ring of >= k+1 slots
-  int T = tiles_per_cta > 0 ? tiles_per_cta : 4;   // measured: weight streaming from L2 favours the widest sharing
-  while (T > 1 && (512 / (T * cout)) < k + 1) T >>= 1;
-  if (T > p.tiles_w) T = p.tiles_w;
-  if (T < 1) T = 1;
-  int G = 4;                                     // ring slots: largest power of two that fits TMEM
-  while (G * 2 <= kMaxSlots && G * 2 * T * cout <= 512) G *= 2;
+  const int G = k + 1;                           // ring slots per tile (8 or 4)
+  int T = tiles_per_cta > 0 ? tiles_per_cta : 4;   // adjacent W tiles sharing one weight stream
+  while (T > 1 && T * G * cout > 512) T >>= 1;
+  while (T > 1 && T > p.tiles_w) T >>= 1;          // T in {1, 2, 4}
+  if (T == 3) T = 2;
   p.T = T; p.G = G;
-  DP_REQUIRE(G >= k + 1, "dp_conv3d_stack: TMEM ring too small (G=%d)", G);
+  DP_REQUIRE(T * G * cout <= 512, "dp_conv3d_stack: accumulator ring does not fit TMEM");
   p.wgroups = (p.tiles_w + T - 1) / T;
   // segment length: enough work items to balance the SMs, but long segments amortise the (k-1)-plane halo
   const int sms = sm_count();
@@ -455,10 +490,12 @@ extern "C" int dp_conv3d_stack(const void* in_c8, int cb_total_in, const uint8_t
   p.PWw = 8 * T + k - 1;
   p.a_bytes = 2u * p.PH * p.PWw * 16u;
   p.a_stride = ((p.a_bytes + 1023u) / 1024u) * 1024u;
-  const uint32_t tap_b = 32u * k * cout;
-  p.khs = (k == 3) ? 3 : 1;
-  p.n_khg = (k + p.khs - 1) / p.khs;
-  p.b_bytes = static_cast<uint32_t>(p.khs * k) * tap_b;
+  const uint32_t tap_b = 32u * G * cout;
+  p.tps = (k == 3) ? 9 : static_cast<int>((30u * 1024u) / tap_b);     // ~30 KB weight stages
+  if (p.tps < 1) p.tps = 1;
+  if (p.tps > k * k) p.tps = k * k;
+  p.n_bst = (k * k + p.tps - 1) / p.tps;
+  p.b_bytes = static_cast<uint32_t>(p.tps) * tap_b;
   p.b_stride = ((p.b_bytes + 1023u) / 1024u) * 1024u;
   p.a_stages = 3;
   p.b_off = p.a_stages * p.a_stride;
@@ -482,16 +519,23 @@ extern "C" int dp_conv3d_stack(const void* in_c8, int cb_total_in, const uint8_t
     return rc;
 
   const size_t smem = static_cast<size_t>(p.b_off) + static_cast<size_t>(p.b_stages) * p.b_stride + 1024;
+  typedef void (*KernelFn)(const CUtensorMap, const StackParams);
+  KernelFn fn = nullptr;
+  if (k == 3) fn = T == 4 ? conv3d_stack_kernel<3, 4> : (T == 2 ? conv3d_stack_kernel<3, 2> : conv3d_stack_kernel<3, 1>);
+  else fn = T == 4 ? conv3d_stack_kernel<7, 4> : (T == 2 ? conv3d_stack_kernel<7, 2> : conv3d_stack_kernel<7, 1>);
   static bool configured = false;
   if (!configured) {
     const int max_smem = 212 * 1024;
-    DP_CHECK(cudaFuncSetAttribute(conv3d_stack_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    DP_CHECK(cudaFuncSetAttribute(conv3d_stack_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    DP_CHECK(cudaFuncSetAttribute(conv3d_stack_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    DP_CHECK(cudaFuncSetAttribute(conv3d_stack_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    DP_CHECK(cudaFuncSetAttribute(conv3d_stack_kernel<3, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    DP_CHECK(cudaFuncSetAttribute(conv3d_stack_kernel<7, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    DP_CHECK(cudaFuncSetAttribute(conv3d_stack_kernel<7, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    DP_CHECK(cudaFuncSetAttribute(conv3d_stack_kernel<7, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     configured = true;
   }
   int grid = sms < p.num_items ? sms : p.num_items;
-  if (k == 3) conv3d_stack_kernel<3><<<grid, kStackThreads, smem, stream>>>(tmap, p);
-  else conv3d_stack_kernel<7><<<grid, kStackThreads, smem, stream>>>(tmap, p);
+  fn<<<grid, kStackThreads, smem, stream>>>(tmap, p);
   DP_CHECK(cudaGetLastError());
   return 0;
 }

@@ -296,8 +296,16 @@ class Plan:
             assert base == Ci, f"input parts carry {base} channels, weight expects {Ci}"
         nch = len(mats)
         W = torch.stack(mats, dim=1).view(Co, nch, 2, 8, k, k, k)
-        if stacked:   # [chunk][kh][kw][khalf][j = k-1-kd][co][e]: the k depth taps become MMA columns
-            W = W.flip(4).permute(1, 5, 6, 2, 4, 0, 3).contiguous().half()
+        if stacked:
+            # depth taps become MMA columns; G = k+1 pre-rotated copies, ring slot s of copy r holding depth tap
+            # kd = k-1-j with j = (s - r) mod G, and zeros for j == k: [rot][chunk][kh][kw][khalf][s][co][e]
+            G = k + 1
+            Z = torch.cat((W.flip(4), torch.zeros_like(W[:, :, :, :, :1])), dim=4)            # dim 4 indexed by j
+            rots = []
+            for r in range(G):
+                idx = torch.tensor([(sl - r) % G for sl in range(G)], device=self.device)
+                rots.append(Z.index_select(4, idx).permute(1, 5, 6, 2, 4, 0, 3))
+            W = torch.stack(rots, dim=0).contiguous().half()
         else:         # [kd][chunk][kh][kw][khalf][co][e]
             W = W.permute(4, 1, 5, 6, 2, 0, 3).contiguous().half()
         self.keep.append(W)
