@@ -228,12 +228,23 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     value = world * B * args.steps / (ms / 1e3)
 
-    # ---- end to end through the public call: pinned host inputs in, dose out, every step
+    # ---- end to end through the public API (CascadeStream): every step copies its inputs from pinned host memory
+    # and its dose result back to pinned host memory; copies of neighbouring steps overlap the kernels
+    from dose_prediction_b200.cascade import CascadeStream
+    pipe = CascadeStream(casc)
+
     def e2e_step():
-        casc(ct_h, ptv_h)
-        out_h.copy_(casc.dose, non_blocking=True)
-    e2e_step()
-    ms_e2e = timed(e2e_step, args.steps)
+        pipe.submit(ct_h, ptv_h)
+    for _ in range(2):
+        e2e_step()
+    pipe.flush()
+    torch.cuda.synchronize(dev)
+
+    def e2e_run():
+        for _ in range(args.steps):
+            e2e_step()
+        pipe.flush()                                   # the last result has reached the host inside the timed region
+    ms_e2e = timed(e2e_run, 1)
     e2e_val = world * B * args.steps / (ms_e2e / 1e3)
 
     # ---- per-kernel-family device time (instrumented eager replay, CUDA events on the launch stream)

@@ -100,6 +100,69 @@ class CascadePlan:
         return self.outs[0]
 
 
+class CascadeStream:
+    """Double-buffered host<->device pipeline around a CascadePlan: the H2D copy of batch i+1 and the D2H copy of
+    result i-1 run on side streams while batch i computes, so PCIe time disappears behind the kernels.
+
+        stream = CascadeStream(casc)
+        for ct, ptv in batches:            # pinned host tensors [B,1,S,S,S]
+            out = stream.submit(ct, ptv)   # returns the pinned host dose of the PREVIOUS submit (or None)
+        last = stream.flush()
+    """
+
+    def __init__(self, casc):
+        self.casc = casc
+        dev = casc.plan.device
+        self.dev = dev
+        self.h2d, self.d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        shape = tuple(casc.ct.shape)
+        self.stage = [(torch.empty(shape, device=dev), torch.empty(shape, device=dev)) for _ in range(2)]
+        self.out_dev = [torch.empty(tuple(casc.dose.shape), device=dev) for _ in range(2)]
+        self.out_host = [torch.empty(tuple(casc.dose.shape)).pin_memory() for _ in range(2)]
+        self.staged = [torch.cuda.Event() for _ in range(2)]
+        self.computed = [torch.cuda.Event() for _ in range(2)]
+        self.copied = [torch.cuda.Event() for _ in range(2)]
+        self.consumed = [torch.cuda.Event() for _ in range(2)]
+        self.i = 0
+        self.pending = None
+
+    def submit(self, ct_host, ptv_host):
+        k = self.i & 1
+        main = torch.cuda.current_stream(self.dev)
+        with torch.cuda.stream(self.h2d):
+            if self.i >= 2:
+                self.h2d.wait_event(self.consumed[k])       # staging buffer k was read two submits ago
+            self.stage[k][0].copy_(ct_host, non_blocking=True)
+            self.stage[k][1].copy_(ptv_host, non_blocking=True)
+            self.staged[k].record(self.h2d)
+        main.wait_event(self.staged[k])
+        self.casc.ct.copy_(self.stage[k][0], non_blocking=True)      # device-to-device, ~50 us
+        self.casc.ptv.copy_(self.stage[k][1], non_blocking=True)
+        self.consumed[k].record(main)
+        self.casc.plan.replay()
+        if self.i >= 2:
+            main.wait_event(self.copied[k])                 # result buffer k must have left the device
+        self.out_dev[k].copy_(self.casc.dose, non_blocking=True)
+        self.computed[k].record(main)
+        with torch.cuda.stream(self.d2h):
+            self.d2h.wait_event(self.computed[k])
+            self.out_host[k].copy_(self.out_dev[k], non_blocking=True)
+            self.copied[k].record(self.d2h)
+        prev, self.pending = self.pending, k
+        self.i += 1
+        if prev is None:
+            return None
+        self.copied[prev].synchronize()
+        return self.out_host[prev]
+
+    def flush(self):
+        if self.pending is None:
+            return None
+        self.copied[self.pending].synchronize()
+        out, self.pending = self.out_host[self.pending], None
+        return out
+
+
 def postprocess_dose(prediction, possible_dose_mask):
     """train_light_linked_model.py:171-173: zero outside the mask / negative values, scale to Gy."""
     prediction = prediction.clone()

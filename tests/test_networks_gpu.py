@@ -209,3 +209,22 @@ def test_unetr_up_block_decoder_and_conv_patch_embedding_variants_match_oracle()
     got = s.to("cuda:0")(ct.cuda()).cpu()
     assert _rel(got, want_l) < LOGIT_TOL
     assert (got.argmax(1) == want_l.argmax(1)).float().mean().item() >= ARGMAX_MIN
+
+
+def test_cascade_stream_pipeline_returns_the_same_doses_in_order():
+    """CascadeStream overlaps H2D / compute / D2H of neighbouring batches; results must be those of plain calls."""
+    from dose_prediction_b200 import synth
+    from dose_prediction_b200.cascade import CascadePlan, CascadeStream
+    casc = CascadePlan(_seg_model(32, _sd("oar_transeg", 32, 1)), _dose_model(32, _sd("dose_pyfer", 32, 0)), 2, 32, "cuda:0")
+    batches = [synth.make_batch(2, 32, seed=100 + 10 * i) for i in range(4)]
+    want = [casc(b["ct"].cuda(), b["ptv"].cuda()).cpu().clone() for b in batches]
+    pipe = CascadeStream(casc)
+    got = []
+    for b in batches:
+        out = pipe.submit(b["ct"].pin_memory(), b["ptv"].pin_memory())
+        if out is not None:
+            got.append(out.clone())
+    got.append(pipe.flush().clone())
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
