@@ -29,7 +29,8 @@ namespace dp {
 struct StackParams {
   int N, D, H, W;
   int n_chunks, cb_total_in;
-  int cout;                 // N0
+  int cout;                 // N0: MMA columns per ring slot
+  int fold;                 // 1: output channel c = column c + column c + N0/2 (W_hi | W_lo operand split folded into N)
   int T, G, L;              // tiles per CTA, ring slots, segment length
   int tps, n_bst;           // taps per weight stage, weight stages per (plane, chunk)
   int PH, PWw;
@@ -141,6 +142,7 @@ conv3d_stack_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_co
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int N0 = p.cout;
+  const int NO = p.fold ? (N0 >> 1) : N0;     // output channels
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_in);
@@ -151,7 +153,7 @@ conv3d_stack_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_co
   }
   if (warp == 1) tmem_alloc<512>(&tmem_base_smem);
   for (int i = threadIdx.x; i < kStackEpiWarps * 32 * 2; i += kStackThreads) (&stat_acc[0][0][0])[i] = 0.f;
-  for (int i = threadIdx.x; i < N0; i += kStackThreads) { s_scale[i] = p.scale[i]; s_shift[i] = p.shift[i]; }
+  for (int i = threadIdx.x; i < NO; i += kStackThreads) { s_scale[i] = p.scale[i]; s_shift[i] = p.shift[i]; }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -354,9 +356,9 @@ conv3d_stack_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_co
     auto flush_stats = [&](int n) {
       if (p.stats == nullptr || n < 0) return;
       __syncwarp();
-      for (int c = lane; c < N0; c += 32) {
-        atomicAdd(&p.stats[(static_cast<size_t>(n) * N0 + c) * 2 + 0], static_cast<double>(stat_acc[ew][c][0]));
-        atomicAdd(&p.stats[(static_cast<size_t>(n) * N0 + c) * 2 + 1], static_cast<double>(stat_acc[ew][c][1]));
+      for (int c = lane; c < NO; c += 32) {
+        atomicAdd(&p.stats[(static_cast<size_t>(n) * NO + c) * 2 + 0], static_cast<double>(stat_acc[ew][c][0]));
+        atomicAdd(&p.stats[(static_cast<size_t>(n) * NO + c) * 2 + 1], static_cast<double>(stat_acc[ew][c][1]));
         stat_acc[ew][c][0] = 0.f;
         stat_acc[ew][c][1] = 0.f;
       }
@@ -376,10 +378,18 @@ conv3d_stack_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_co
           const bool valid = (h < p.H) && (w < p.W);
           const size_t vox = (static_cast<size_t>(d) * p.H + h) * p.W + w;
           const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>((t * G + slot) * N0);
-          for (int c0 = 0; c0 < N0; c0 += 16) {
+          for (int c0 = 0; c0 < NO; c0 += 16) {
             uint32_t r[16];
             tmem_ld16(taddr + c0, r);
-            tmem_ld_wait();
+            if (p.fold) {
+              uint32_t r2[16];
+              tmem_ld16(taddr + NO + c0, r2);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+            } else {
+              tmem_ld_wait();
+            }
             float v[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -446,14 +456,17 @@ extern "C" int dp_conv3d_stack(const void* in_c8, int cb_total_in, const uint8_t
                                const void* wpack_stack, int N, int D, int H, int W, int cout, int k,
                                const float* scale, const float* shift, int relu, float* out_f32, void* out_hi,
                                void* out_lo, int cb_total_out, int cb_out_off, double* stats, int* err_flag,
-                               int seg_len, int tiles_per_cta, cudaStream_t stream) {
+                               int seg_len, int tiles_per_cta, int fold, cudaStream_t stream) {
   using namespace dp;
   DP_REQUIRE(k == 3 || k == 7, "dp_conv3d_stack: kernel size %d unsupported (3 or 7)", k);
-  DP_REQUIRE((cout == 16 || cout == 32) && (k + 1) * cout <= 256, "dp_conv3d_stack: C_out=%d unsupported (16 or 32)", cout);
+  DP_REQUIRE(cout == 16 || (cout == 32 && !fold), "dp_conv3d_stack: C_out=%d unsupported (16, or 32 without fold)", cout);
+  const int cout_out = cout;
+  cout = fold ? 2 * cout : cout;                 // MMA columns per ring slot
   DP_REQUIRE(n_chunks >= 1 && n_chunks <= 96, "dp_conv3d_stack: n_chunks=%d out of range", n_chunks);
   DP_REQUIRE(out_f32 != nullptr || out_hi != nullptr, "dp_conv3d_stack: no output tensor given");
   StackParams p{};
-  p.N = N; p.D = D; p.H = H; p.W = W; p.n_chunks = n_chunks; p.cb_total_in = cb_total_in; p.cout = cout;
+  p.N = N; p.D = D; p.H = H; p.W = W; p.n_chunks = n_chunks; p.cb_total_in = cb_total_in; p.cout = cout; p.fold = fold ? 1 : 0;
+  (void)cout_out;
   for (int i = 0; i < n_chunks; ++i) p.chunk_cb[i] = chunk_cb[i];
   p.tiles_h = (H + 15) / 16;
   p.tiles_w = (W + 7) / 8;

@@ -22,6 +22,7 @@ ACT_NONE, ACT_RELU, ACT_LRELU, ACT_MISH, ACT_GELU = 0, 1, 2, 3, 4
 ACT_ID = {None: ACT_NONE, "none": ACT_NONE, "relu": ACT_RELU, "lrelu": ACT_LRELU, "mish": ACT_MISH, "gelu": ACT_GELU}
 STATS_DOUBLES = 1 << 20
 STACK_TILES = int(os.environ.get("DP_STACK_TILES", "0"))
+FOLD_P3 = os.environ.get("DP_FOLD_P3", "1") != "0"
 STACKED_CONV = os.environ.get("DP_STACKED_CONV", "1") != "0"    # bring-up switch between the two tcgen05 conv kernels
 EPS = 1e-5
 
@@ -277,8 +278,12 @@ class Plan:
         assert Co % 16 == 0, "tensor-core conv needs C_out % 16 == 0"
         whi = w.half().float()
         wlo = (w - whi).half().float()
-        terms = {"p1": [("hi", whi)], "p2": [("hi", whi), ("lo", whi)],
-                 "p3": [("hi", whi), ("lo", whi), ("hi", wlo)]}[mode]
+        if mode == "p3f":     # 3-term split folded into N: hi chunks see [W_hi | W_lo], lo chunks [W_hi | 0]
+            terms = [("hi", torch.cat((whi, wlo), 0)), ("lo", torch.cat((whi, torch.zeros_like(whi)), 0))]
+            Co = 2 * Co
+        else:
+            terms = {"p1": [("hi", whi)], "p2": [("hi", whi), ("lo", whi)],
+                     "p3": [("hi", whi), ("lo", whi), ("hi", wlo)]}[mode]
         mats, chunks = [], []
         for which, wt in terms:
             base = 0
@@ -347,7 +352,8 @@ class Plan:
         D, H, W = a0.dims
         Co = weight.shape[0]
         stacked = STACKED_CONV and dil == 1 and k in (3, 7) and Co in (16, 32) and tap_mask_fn is None
-        wp, chunks, nch = self.pack_conv_tc(weight, parts, mode, stacked=stacked)
+        fold = stacked and mode == "p3" and Co == 16 and FOLD_P3
+        wp, chunks, nch = self.pack_conv_tc(weight, parts, "p3f" if fold else mode, stacked=stacked)
         if out_raw is not None:
             of32, ohi, olo, cbt, cbo = out_raw.t.data_ptr(), None, None, out_raw.cb_total, 0
             st = out_raw.stats if stats is None else stats
@@ -359,7 +365,7 @@ class Plan:
             self.count_flops("dp_conv3d_stack", flops)
             self.add("dp_conv3d_stack", a0.buf.data_ptr(), a0.cb_total, chunks, nch, wp.data_ptr(), a0.N, D, H, W, Co, k,
                      scale.data_ptr(), shift.data_ptr(), int(relu), of32, ohi, olo, cbt, cbo,
-                     st.data_ptr() if st is not None else None, self.err.data_ptr(), 0, STACK_TILES)
+                     st.data_ptr() if st is not None else None, self.err.data_ptr(), 0, STACK_TILES, int(fold))
             return
         masks = None
         if tap_mask_fn is not None:

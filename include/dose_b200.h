@@ -60,11 +60,13 @@ int dp_conv3d_tc(const void* in_c8, int cb_total_in, const uint8_t* chunk_cb, in
  * shared-memory A operand is read once per k taps instead of once per tap.
  *   wpack_stack  fp16 [n_chunks][k(kh)][k(kw)][2][k*cout][8], row j*cout+co holding W[co, :, kd=k-1-j, kh, kw]
  *   seg_len      output planes per work item along D (0 = choose for load balance)
- *   tiles_per_cta  adjacent W tiles sharing one weight stream (0 = default)                             */
+ *   tiles_per_cta  adjacent W tiles sharing one weight stream (0 = default)
+ *   fold         1 (cout == 16): weights carry 2*cout rows per slot ([W_hi | W_lo] for hi chunks, [W_hi | 0] for
+ *                lo chunks); the epilogue adds the two halves — the 3-term operand split in 2 MMAs per chunk  */
 int dp_conv3d_stack(const void* in_c8, int cb_total_in, const uint8_t* chunk_cb, int n_chunks, const void* wpack_stack,
                     int N, int D, int H, int W, int cout, int k, const float* scale, const float* shift, int relu,
                     float* out_f32, void* out_hi, void* out_lo, int cb_total_out, int cb_out_off, double* stats,
-                    int* err_flag, int seg_len, int tiles_per_cta, cudaStream_t stream);
+                    int* err_flag, int seg_len, int tiles_per_cta, int fold, cudaStream_t stream);
 
 /* Generic direct convolution (any stride): c3d.py:49,53,57,61 (stride-2 SingleConv convs).
  *   w_packed   fp32 [k^3 taps][cin][cout]                                                              */
