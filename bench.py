@@ -108,14 +108,14 @@ def cpu_baseline(seg_sd, dose_sd, size, volumes=1):
             "sample": f"{volumes} x {size}^3 cascade volume(s), oracle/torch_ref.py fp32, {dt:.1f} s"}
 
 
-def build_models(size, device=None):
+def build_models(size, device=None, seg_size=None):
     import torch
 
     from dose_prediction_b200 import networks
     torch.manual_seed(0)
     dose = networks.Model(9, 1, [-1, 16, 32, 64, 128, 256], feature_size=16, img_size=(size,) * 3, num_layers=8,
                           num_heads=6, act="mish", mode_multi_dec=True, multiS_conv=True).eval()
-    seg = networks.OARTranseg(1, 8, (size,) * 3, feature_size=16, hidden_size=768, mlp_dim=3072, num_heads=12,
+    seg = networks.OARTranseg(1, 8, (seg_size or size,) * 3, feature_size=16, hidden_size=768, mlp_dim=3072, num_heads=12,
                               pos_embed="perceptron", norm_name="instance", res_block=True, conv_block=True).eval()
     if device is not None:
         dose, seg = dose.to(device), seg.to(device)
@@ -163,6 +163,8 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--sw-roi", type=int, default=0,
+                    help="run the seg stage as the reference does: sliding 96^3-style windows of this ROI (0 = direct)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     if args.impl == "reference":
@@ -186,8 +188,8 @@ def main():
     __graft_entry__.build()
 
     B, S = args.batch, args.size
-    seg, dose = build_models(S, dev)
-    casc = CascadePlan(seg, dose, B, S, dev, graph=False)
+    seg, dose = build_models(S, dev, seg_size=args.sw_roi or None)
+    casc = CascadePlan(seg, dose, B, S, dev, graph=False, sw_roi=args.sw_roi or None)
     plan = casc.plan
     # synthetic volumes: this rank's shard of a job of world*B volumes (weak scaling), pinned on the host
     vols = synth.make_batch(B, S, seed=1234 + rank * B)
@@ -265,8 +267,26 @@ def main():
                 "avg_launch_ms": ms_k / max(n_k, 1), "algorithmic_flops_per_step": fl, "share_of_step": ms_k / total_fam}
 
     dominant = max(names, key=lambda k: fam.get(k, {}).get("ms", 0.0))
-    roofline = tensor_roofline(dominant)
-    roofline_other = [tensor_roofline(k) for k in names if k != dominant]
+    roofline_family = [tensor_roofline(k) for k in names]
+    # the dominant KERNEL LAUNCH: heaviest launch shape of the dominant family, timed live (CUDA events)
+    per_launch = [r for r in plan.profile_launches() if r[0] == dominant]
+    by_shape = {}
+    for n_, label, ms_l, fl in per_launch:
+        d = by_shape.setdefault(label, {"ms": 0.0, "n": 0, "flops": fl})
+        d["ms"] += ms_l
+        d["n"] += 1
+    top_label, top = max(by_shape.items(), key=lambda kv: kv[1]["ms"])
+    avg_ms = top["ms"] / top["n"]
+    ach = top["flops"] / (avg_ms / 1e3) / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(f"{dominant} {top_label}")
+    roofline = {"kernel": names[dominant], "launch": top_label, "bound": "tensor", "achieved": ach, "peak": peaks["tflops"],
+                "unit": "TFLOP/s", "frac": ach / peaks["tflops"], "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write)",
+                "peak_source": peaks["source"], "launches_per_step": top["n"], "avg_launch_ms": avg_ms,
+                "algorithmic_flops_per_launch": top["flops"], "share_of_step": top["ms"] / total_fam}
     conv_fl = plan.flops.get("dp_conv3d_stack", 0.0) + plan.flops.get("dp_conv3d_tc", 0.0)
     conv_ms = fam.get("dp_conv3d_stack", {}).get("ms", 0.0) + fam.get("dp_conv3d_tc", {}).get("ms", 0.0)
     conv_pct = conv_fl / (conv_ms / 1e3) / 1e12 / peaks["tflops"] if conv_ms > 0 else 0.0
@@ -278,16 +298,19 @@ def main():
                 "dtype": "f16", "data": "synthetic",
                 "config": {"workload": f"cascade OAR-TRANSEG->hand-off->DOSE-PYFER inference, {S}^3, batch {B} per GPU "
                                        "(BASELINE.json configs[2]; configs[1] seg forward is its first half)",
-                           "batch_per_gpu": B, "size": S, "parallelism": f"volume-sharded x{world}, no collective",
+                           "batch_per_gpu": B, "size": S,
+                           "seg_stage": (f"sliding window ROI {args.sw_roi}, overlap 0.25 (as train_light_linked_model.py:152)"
+                                         if args.sw_roi else "direct full-volume forward"),
+                           "parallelism": f"volume-sharded x{world}, no collective",
                            "cuda_graph": not args.no_graph,
                            "l2": f"no flush: per-step working set {plan.bytes_alloc / 2**30:.1f} GiB >> 126 MB L2"},
                 "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                         "h2d_bytes_per_step": 2 * B * S ** 3 * 4, "d2h_bytes_per_step": B * S ** 3 * 4},
                 "gpu_launches": plan.launches * args.steps, "launches_per_step": plan.launches,
-                "roofline": roofline, "roofline_other": roofline_other, "conv_frac_of_tensor_peak": conv_pct,
+                "roofline": roofline, "roofline_families": roofline_family, "conv_frac_of_tensor_peak": conv_pct,
                 "kernel_ms_per_step": {k: round(v["ms"], 3) for k, v in sorted(fam.items())},
                 "clocks": clocks}
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and not args.sw_roi:
             line["cpu_baseline"] = cpu_baseline({k: v.cpu() for k, v in seg.state_dict().items()},
                                                 {k: v.cpu() for k, v in dose.state_dict().items()}, S)
         print(json.dumps(line), flush=True)

@@ -108,6 +108,8 @@ class Plan:
         self.graph = None
         self.launches = 0
         self.flops = {}          # algorithmic FLOPs (2*MAC of the reference op) per kernel family, per replay
+        self.step_flops = []     # the same per recorded launch (parallel to self.steps)
+        self._pending_flops = 0.0
 
     # ------------------------------------------------------------------ memory
     def zeros(self, shape, dtype):
@@ -161,10 +163,13 @@ class Plan:
     # ------------------------------------------------------------------ recording / replay
     def add(self, name, *args):
         self.steps.append((getattr(self.lib, name), args, name))
+        self.step_flops.append(self._pending_flops)
+        self._pending_flops = 0.0
 
     def add_zero(self, t):
         """re-zero a (split-K / atomic) accumulation target at this point of every replay."""
         self.steps.append((None, (t,), "zero"))
+        self.step_flops.append(0.0)
 
     def run(self):
         s = torch.cuda.current_stream(self.device).cuda_stream
@@ -182,7 +187,9 @@ class Plan:
         self.launches = n
 
     def count_flops(self, name, flops):
+        """call right before the add() of the launch that performs `flops` algorithmic FLOPs."""
         self.flops[name] = self.flops.get(name, 0.0) + float(flops)
+        self._pending_flops = float(flops)
 
     def profile_launches(self):
         """per-launch device time (CUDA events): list of (family, label, ms) in schedule order."""
@@ -214,7 +221,8 @@ class Plan:
                 label = f"cin{args[5]} cout{args[6]} N{args[7]} {args[8]}x{args[9]}x{args[10]}"
             evs.append((name, label, e0, e1))
         torch.cuda.synchronize(self.device)
-        return [(n, l, e0.elapsed_time(e1)) for n, l, e0, e1 in evs]
+        fl = [f for (fn, _, _), f in zip(self.steps, self.step_flops) if fn is not None]
+        return [(n, l, e0.elapsed_time(e1), f) for (n, l, e0, e1), f in zip(evs, fl)]
 
     def profile_families(self, repeats=1):
         """device time per kernel family: eager replay with a CUDA-event pair around every launch on the

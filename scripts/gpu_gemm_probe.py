@@ -21,7 +21,7 @@ def main():
     for _ in range(3):
         P.run()
     torch.cuda.synchronize()
-    for n, l, ms in P.profile_launches():
+    for n, l, ms, _ in P.profile_launches():
         print(f"{ms:8.4f} ms {n} {l}")
     P.check_device_errors()
 

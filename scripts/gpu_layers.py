@@ -27,12 +27,12 @@ def main():
     rows = casc.plan.profile_launches()
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", f"layers_{tag}.csv"), "w") as f:
-        f.write("idx,family,label,ms\n")
-        for i, (n, l, ms) in enumerate(rows):
-            f.write(f"{i},{n},{l},{ms:.4f}\n")
+        f.write("idx,family,label,ms,gflop\n")
+        for i, (n, l, ms, fl) in enumerate(rows):
+            f.write(f"{i},{n},{l},{ms:.4f},{fl / 1e9:.3f}\n")
     tot = sum(r[2] for r in rows)
     print(f"total {tot:.2f} ms for batch {B}; top launches:")
-    for n, l, ms in sorted(rows, key=lambda r: -r[2])[:40]:
+    for n, l, ms, fl in sorted(rows, key=lambda r: -r[2])[:40]:
         print(f"  {ms:8.3f} ms  {n:18s} {l}")
     casc.plan.check_device_errors()
 
