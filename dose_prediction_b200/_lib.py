@@ -36,6 +36,28 @@ _SIGNATURES = {
     "dp_window_add": [P, I, I, I, P, P, P, P, P, P, I, I, I, P],
     "dp_div_count": [P, P, L, I, P],
     "dp_handoff": [P, I, P, P, I, I, P, P, I, I, P, P],
+    # ---- training step
+    "dp_norm_act_bwd": [P, P, P, I, I, P, P, P, I, P, P, P, P, I, I, I, I, P, P, P, P, I, I, P, I, P, P, I, I, P, P, I, I,
+                        I, I, L, P],
+    "dp_batch_combine": [P, I, I, I, L, P, P, F, P],
+    "dp_affine_grad": [P, I, I, P, P, F, P],
+    "dp_grad_finalize": [P, P, L, F, P],
+    "dp_conv3d_wgrad": [P, I, P, P, P, I, P, I, I, I, I, I, I, I, I, I, I, P, I, P],
+    "dp_small_wgrad": [I, P, P, P, P, I, I, I, P, P, I, I, I, P, I, I, I, I, I, P, L, L, L, P, P],
+    "dp_deconv2x_bwd_data": [I, P, P, P, P, I, I, I, P, I, I, I, I, I, P, I, I, P, P],
+    "dp_head_bwd": [P, P, P, I, I, I, P, I, L, P, I, I, P, P, P],
+    "dp_masked_l1": [P, P, I, I, I, P, I, F, P, P],
+    "dp_genloss_finalize": [P, I, F, F, P, P],
+    "dp_adamw": [P, P, P, P, L, F, F, F, F, F, I, F, P, P],
+    "dp_grad_check": [P, L, P, P],
+    "dp_layernorm_bwd": [P, P, P, P, I, I, P, P, P, P],
+    "dp_softmax_bwd": [P, I, P, I, I, I, P, I, P],
+    "dp_act_fwd": [P, L, I, P, P],
+    "dp_act_bwd": [P, P, L, I, P, P, P],
+    "dp_transpose": [P, I, L, I, I, I, P, L, I, I, F, P],
+    "dp_heads": [P, I, P, I, I, I, I, I, I, I, I, F, P],
+    "dp_colsum": [P, I, L, P, P],
+    "dp_add": [P, P, L, P, P, P],
 }
 
 

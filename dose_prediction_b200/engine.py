@@ -110,6 +110,8 @@ class Plan:
         self.flops = {}          # algorithmic FLOPs (2*MAC of the reference op) per kernel family, per replay
         self.step_flops = []     # the same per recorded launch (parallel to self.steps)
         self._pending_flops = 0.0
+        self.training = False    # training plans re-derive packed weights from the live parameters every step
+        self.refresh = []        # (packed tensor, function returning its new value)
 
     # ------------------------------------------------------------------ memory
     def zeros(self, shape, dtype):
@@ -171,6 +173,25 @@ class Plan:
         self.steps.append((None, (t,), "zero"))
         self.step_flops.append(0.0)
 
+    def add_py(self, fn):
+        """host-side plumbing (parameter-layout conversion, collectives) at this point of every replay."""
+        self.steps.append((None, (fn,), "py"))
+        self.step_flops.append(0.0)
+
+    def derived(self, fn):
+        """a tensor computed from live parameters (packed / transposed / fp16 copy): kept, and in training
+        plans recomputed in place by refresh_weights() after every optimizer step."""
+        t = fn().contiguous()
+        self.keep.append(t)
+        if self.training:
+            self.refresh.append((t, fn))
+        return t
+
+    def refresh_weights(self):
+        with torch.no_grad():
+            for t, fn in self.refresh:
+                t.copy_(fn())
+
     def run(self):
         s = torch.cuda.current_stream(self.device).cuda_stream
         if self.stats_used:
@@ -178,7 +199,10 @@ class Plan:
         n = 0
         for fn, args, name in self.steps:
             if fn is None:
-                args[0].zero_()
+                if name == "py":
+                    args[0]()
+                else:
+                    args[0].zero_()
                 continue
             rc = fn(*args, s)
             if rc:
@@ -200,7 +224,7 @@ class Plan:
         evs = []
         for fn, args, name in self.steps:
             if fn is None:
-                args[0].zero_()
+                args[0]() if name == "py" else args[0].zero_()
                 continue
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
@@ -236,7 +260,7 @@ class Plan:
             evs = []
             for fn, args, name in self.steps:
                 if fn is None:
-                    args[0].zero_()
+                    args[0]() if name == "py" else args[0].zero_()
                     continue
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(stream)
@@ -278,10 +302,11 @@ class Plan:
             self.run()
 
     # ------------------------------------------------------------------ weight packing
-    def pack_conv_tc(self, w, parts, mode, stacked=False):
-        """w [Co,Ci,k,k,k] fp32 -> fp16 [kd][chunk][kh][kw][2][Co][8] + per-chunk input block table.
-        mode p1: x_hi.W_hi;  p2: + x_lo.W_hi;  p3: + x_hi.W_lo  (operand splitting by K expansion)."""
-        w = w.detach().to(self.device, torch.float32)
+    def pack_conv_tc(self, w, parts, mode, stacked=False, _values_only=False):
+        """w [Co,Ci,k,k,k] fp32 (or a function returning it) -> fp16 [kd][chunk][kh][kw][2][Co][8] + per-chunk
+        input block table.  mode p1: x_hi.W_hi;  p2: + x_lo.W_hi;  p3: + x_hi.W_lo  (operand splitting by K expansion)."""
+        w_src = w
+        w = (w() if callable(w) else w).detach().to(self.device, torch.float32)
         Co, Ci, k = w.shape[0], w.shape[1], w.shape[2]
         assert Co % 16 == 0, "tensor-core conv needs C_out % 16 == 0"
         whi = w.half().float()
@@ -321,7 +346,11 @@ class Plan:
             W = torch.stack(rots, dim=0).contiguous().half()
         else:         # [kd][chunk][kh][kw][khalf][co][e]
             W = W.permute(4, 1, 5, 6, 2, 0, 3).contiguous().half()
+        if _values_only:
+            return W
         self.keep.append(W)
+        if self.training:
+            self.refresh.append((W, lambda: self.pack_conv_tc(w_src, parts, mode, stacked, _values_only=True)))
         assert max(chunks) < 256
         arr = (ctypes.c_uint8 * nch)(*chunks)
         self.keep.append(arr)
@@ -358,7 +387,8 @@ class Plan:
                 tap_mask_fn=None):
         a0 = parts[0]
         D, H, W = a0.dims
-        Co = weight.shape[0]
+        wshape = (weight() if callable(weight) else weight).shape
+        Co = wshape[0]
         stacked = STACKED_CONV and dil == 1 and k in (3, 7) and Co in (16, 32) and tap_mask_fn is None
         fold = stacked and mode == "p3" and Co == 16 and FOLD_P3
         wp, chunks, nch = self.pack_conv_tc(weight, parts, "p3f" if fold else mode, stacked=stacked)
@@ -368,7 +398,7 @@ class Plan:
         else:
             of32, ohi, olo, cbt, cbo = None, out_act.hi_ptr, out_act.lo_ptr, out_act.cb_total, out_act.cb_off
             st = stats
-        flops = 2.0 * a0.N * D * H * W * k ** 3 * weight.shape[1] * Co
+        flops = 2.0 * a0.N * D * H * W * k ** 3 * wshape[1] * Co
         if stacked:
             self.count_flops("dp_conv3d_stack", flops)
             self.add("dp_conv3d_stack", a0.buf.data_ptr(), a0.cb_total, chunks, nch, wp.data_ptr(), a0.N, D, H, W, Co, k,
@@ -454,7 +484,8 @@ class Plan:
         of = oh = ol = op = st = None
         ocb = ooff = 0
         if out_raw is not None:
-            of, ocb, st = out_raw.t.data_ptr(), out_raw.cb_total, out_raw.stats.data_ptr()
+            of, ocb = out_raw.t.data_ptr(), out_raw.cb_total
+            st = out_raw.stats.data_ptr() if out_raw.stats is not None else None
         if out_act is not None:
             oh, ol, ocb, ooff = out_act.hi_ptr, out_act.lo_ptr, out_act.cb_total, out_act.cb_off
         if out_planar is not None:
@@ -469,12 +500,12 @@ class Plan:
             B, T, C = src.t.shape
             D, H, W = src.grid
             assert C == Ci and C % 8 == 0
-            wnk = self.dev(weight.permute(2, 3, 4, 1, 0).reshape(8 * Co, Ci), torch.float16)
+            wnk = self.derived(lambda: weight.detach().to(self.device).permute(2, 3, 4, 1, 0).reshape(8 * Co, Ci).half())
             self.count_flops("dp_deconv2x_gemm", 2.0 * B * T * Ci * Co * 8)
             self.add("dp_deconv2x_gemm", src.t.data_ptr(), wnk.data_ptr(), B, D, H, W, Ci, Co, out.hi_ptr, out.lo_ptr,
                      out.cb_total, out.cb_off, self.err.data_ptr())
             return
-        w = self.dev(weight.permute(2, 3, 4, 0, 1).reshape(8, Ci, Co))
+        w = self.derived(lambda: weight.detach().to(self.device, torch.float32).permute(2, 3, 4, 0, 1).reshape(8, Ci, Co))
         if isinstance(src, Tokens):
             B, T, C = src.t.shape
             D, H, W = src.grid

@@ -1,0 +1,679 @@
+"""DOSE-PYFER training step on the C ABI.
+
+Mirrors `Pyfer.training_step` + `configure_optimizers` (DosePrediction/Train/train_light_pyfer.py:85-88,122-143,
+194-197) with `GenLoss(mode='train', casecade=True, freez=True)` (DosePrediction/Train/loss.py:69-119):
+
+    train-mode forward (net_A frozen; net_B BatchNorm3d layers use batch statistics and update their running
+    statistics) -> deep-supervised masked L1 -> backward through net_B -> [grad all-reduce over ranks] -> AdamW.
+
+`TrainPlan` extends the inference `Plan` with a tape: every forward emitter also registers the emitter of its
+backward launches; the tape is unrolled in reverse once, so a training step is one static launch list like the
+inference plans.  Convolution data gradients run through the same tcgen05 kernels as the forward pass (flipped /
+transposed weights), token-side gradients through the tcgen05 GEMM; everything else is in csrc/train.cu.
+PyTorch is used for memory, the per-step re-packing of parameters into kernel layouts and the NCCL all-reduce.
+
+Numerics: forward as the inference path of net_B (fp16 operands, fp32 accumulation); gradients are carried as
+fp32 between kernels and as fp16 (static loss scale) into the tensor-core dgrad / wgrad operands.
+Biases of convolutions that feed a normalisation layer have a mathematically zero gradient; it is written as 0
+(the reference's autograd produces rounding noise there).
+"""
+import ctypes
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .engine import ACT_ID, Act, Plan, Raw, Tokens, blocks16, ceil_div
+from . import networks as nw
+
+ARENA_DOUBLES = 1 << 22
+
+
+class TrainPlan(Plan):
+    def __init__(self, device, loss_scale):
+        super().__init__(device)
+        self.training = True
+        self.loss_scale = float(loss_scale)
+        self.tape = []
+        self.act_grads = {}      # (buffer ptr, cb_off) -> [(fp32 c8 tensor, cb_total, cb_off)]
+        self.raw_grad = {}       # raw tensor ptr -> Act holding the fp16 gradient of that pre-norm tensor
+        self.tok_grads = {}      # token tensor ptr -> [fp32 [B,T,C] gradients]
+        self.planar_grad = {}    # planar output ptr -> fp32 gradient
+        self.arena = self.zeros((ARENA_DOUBLES,), torch.float64)
+        self.arena_used = 0
+        self.grad_of = {}        # id(parameter) -> fp32 view into the flat gradient buffer
+        self.finalizers = []
+
+    # ------------------------------------------------------------------ bookkeeping
+    def get_raw(self, N, C, dims, with_stats=True):
+        if not self.training:                 # frozen sub-network: pooled like the inference plans
+            return super().get_raw(N, C, dims, with_stats)
+        t = self.zeros((N, blocks16(C)) + tuple(dims) + (8,), torch.float32)    # kept for the backward pass
+        return Raw(t, C, self.new_stats(N, C) if with_stats else None)
+
+    def release(self, raw):
+        if not self.training:
+            super().release(raw)
+
+    def new_graw(self, N, C, dims):
+        return self.get_raw(N, C, dims, with_stats=False)
+
+    @staticmethod
+    def _key(a):
+        return (a.buf.data_ptr(), a.cb_off)
+
+    def add_act_grad(self, a, src):
+        self.act_grads.setdefault(self._key(a), []).append(src)
+
+    def arena_alloc(self, n):
+        n = (n + 1) // 2 * 2
+        if self.arena_used + n > ARENA_DOUBLES:
+            raise RuntimeError("gradient accumulation arena exhausted")
+        v = self.arena[self.arena_used:self.arena_used + n]
+        self.arena_used += n
+        return v
+
+    def grad(self, p):
+        return self.grad_of[id(p)]
+
+    def small_grad(self, p):
+        """fp64 accumulator for a small parameter; converted into the flat gradient at the end of backward."""
+        acc = self.arena_alloc(p.numel())
+        g = self.grad(p)
+        self.finalizers.append((acc, g, p.numel()))
+        return acc
+
+    def _gsum(self, srcs, f16=None):
+        assert len(srcs) <= 3, "a tensor with more than three gradient contributions"
+        ptrs = _lib.ptr_array([t.data_ptr() for t, _, _ in srcs] or [0])
+        cbt = _lib.int_array([c for _, c, _ in srcs] or [0])
+        cbo = _lib.int_array([o for _, _, o in srcs] or [0])
+        self.keep.append((ptrs, cbt, cbo))
+        if f16 is None:
+            return (len(srcs), ptrs, cbt, cbo, None, 0, 0)
+        return (len(srcs), ptrs, cbt, cbo, f16.buf.data_ptr(), f16.cb_total, f16.cb_off)
+
+    def ones(self, n):
+        return self.zeros((n,), torch.float32).fill_(1.0)
+
+    # ------------------------------------------------------------------ differentiable emitters
+    def t_conv(self, parts, conv, k, dil=1, need_dgrad=True):
+        """nn.Conv3d (stride 1) on fp16 operands -> Raw (+ instance statistics).  Backward: wgrad + dgrad."""
+        a0 = parts[0]
+        N, dims = a0.N, a0.dims
+        w = conv.weight
+        Co, Ci = w.shape[0], w.shape[1]
+        raw = self.get_raw(N, Co, dims)
+        shift = conv.bias if conv.bias is not None else self.zeros((Co,), torch.float32)
+        self.conv_tc(parts, lambda: w, k, dil, "p1", self.ones(Co), shift.detach(), False, out_raw=raw)
+
+        def bwd():
+            g16 = self.raw_grad.pop(raw.t.data_ptr())
+            self.conv_wgrad(parts, g16, w, k, dil)
+            if need_dgrad:
+                assert Ci % 16 == 0
+                graw = self.new_graw(N, Ci, dims)
+                self.conv_tc([g16], lambda: w.detach().flip(2, 3, 4).transpose(0, 1), k, dil, "p1", self.ones(Ci),
+                             self.zeros((Ci,), torch.float32), False, out_raw=graw)
+                off = 0
+                for a in parts:
+                    self.add_act_grad(a, (graw.t, graw.cb_total, off // 8))
+                    off += a.C
+        self.tape.append(bwd)
+        return raw
+
+    def conv_wgrad(self, parts, g16, w, k, dil):
+        a0 = parts[0]
+        D, H, W = a0.dims
+        Co, Ci = w.shape[0], w.shape[1]
+        cbs, ci0, nci, base = [], [], [], 0
+        for a in parts:
+            assert a.buf is a0.buf
+            for j in range(ceil_div(a.C, 16)):
+                cbs.append(a.cb_off + 2 * j)
+                ci0.append(base + 16 * j)
+                nci.append(min(16, a.C - 16 * j))
+            base += a.C
+        assert base == Ci
+        blocks = k * k * len(cbs) * (Co // 16)
+        rows = a0.N * D * H
+        splits = max(1, min(ceil_div(rows, 64), (3 * 148) // blocks))
+        ws = self.zeros((splits, w.numel()), torch.float32)
+        arrs = ((ctypes.c_uint8 * len(cbs))(*cbs), _lib.int_array(ci0), _lib.int_array(nci))
+        self.keep.append(arrs)
+        self.count_flops("dp_conv3d_wgrad", 2.0 * a0.N * D * H * W * k ** 3 * Ci * Co)
+        self.add("dp_conv3d_wgrad", a0.buf.data_ptr(), a0.cb_total, *arrs, len(cbs), g16.buf.data_ptr(), g16.cb_total,
+                 g16.cb_off, a0.N, D, H, W, Ci, Co, k, dil, ws.data_ptr(), splits)
+        self.add("dp_splitk_reduce", ws.data_ptr(), splits, 1, w.numel(), None, None, 0, self.grad(w).data_ptr())
+
+    def t_norm(self, src, out, act=None, res=None, act_after_res=None, bn=None, stats=None, stats_out=None):
+        """InstanceNorm3d (or train-mode BatchNorm3d `bn`) + activation (+ residual) -> out Act."""
+        if isinstance(src, Raw):
+            N, C = src.t.shape[0], src.C
+            vox = src.t.shape[2] * src.t.shape[3] * src.t.shape[4]
+            dims = tuple(src.t.shape[2:5])
+            st = src.stats
+        else:
+            N, C, vox, dims, st = src.N, src.C, src.vox, src.dims, stats
+        gamma = beta = None
+        if bn is not None:
+            self.add("dp_batch_combine", st.data_ptr(), N, C, 2, vox, bn.running_mean.data_ptr(), bn.running_var.data_ptr(),
+                     float(bn.momentum))
+            gamma, beta = bn.weight.detach(), bn.bias.detach()
+        self.norm_act(src, out, stats=st, gamma=gamma, beta=beta, act=act, res=res, act_after_res=act_after_res,
+                      stats_out=stats_out)
+
+        def bwd():
+            dy = self.act_grads.pop(self._key(out))
+            bsum = self.zeros((N * C * 6,), torch.float64)
+            self.add_zero(bsum)
+            if isinstance(src, Raw):
+                fwd = (src.t.data_ptr(), None, None, src.cb_total, 0)
+            else:
+                fwd = (None, src.hi_ptr, src.lo_ptr, src.cb_total, src.cb_off)
+            eh = el = er = es = None
+            ecb = eoff = 0
+            if res is not None:
+                if isinstance(res, Raw):
+                    er, ecb, es = res.t.data_ptr(), res.cb_total, res.stats.data_ptr()
+                else:
+                    eh, el, ecb, eoff = res.hi_ptr, res.lo_ptr, res.cb_total, res.cb_off
+            common = fwd + (st.data_ptr() if st is not None else None,
+                            gamma.data_ptr() if gamma is not None else None, beta.data_ptr() if beta is not None else None,
+                            ACT_ID[act], eh, el, er, es, ecb, eoff, ACT_ID[act_after_res]) + self._gsum(dy)
+            # outputs of the apply pass
+            dxh = dxf = drh = drf = None
+            dxcb = dxoff = drcb = droff = 0
+            if isinstance(src, Raw):
+                g16 = self.new_act(N, C, dims)
+                self.raw_grad[src.t.data_ptr()] = g16
+                dxh, dxcb = g16.buf.data_ptr(), g16.cb_total
+            else:
+                gr = self.new_graw(N, C, dims)
+                self.add_act_grad(src, (gr.t, gr.cb_total, 0))
+                dxf, dxcb = gr.t.data_ptr(), gr.cb_total
+            if res is not None:
+                if isinstance(res, Raw):
+                    r16 = self.new_act(N, C, dims)
+                    self.raw_grad[res.t.data_ptr()] = r16
+                    drh, drcb = r16.buf.data_ptr(), r16.cb_total
+                else:
+                    gr = self.new_graw(N, C, dims)
+                    self.add_act_grad(res, (gr.t, gr.cb_total, 0))
+                    drf, drcb = gr.t.data_ptr(), gr.cb_total
+            tail = (dxh, dxf, dxcb, dxoff, drh, drf, drcb, droff, N, C, vox)
+            self.add("dp_norm_act_bwd", *common, bsum.data_ptr(), 0, *tail)
+            if bn is not None:
+                self.add("dp_batch_combine", bsum.data_ptr(), N, C, 6, vox, None, None, 0.0)
+            self.add("dp_norm_act_bwd", *common, bsum.data_ptr(), 1, *tail)
+            if bn is not None:
+                self.add("dp_affine_grad", bsum.data_ptr(), N, C, self.grad(bn.weight).data_ptr(),
+                         self.grad(bn.bias).data_ptr(), 1.0)
+        self.tape.append(bwd)
+
+    def t_pointwise(self, srcs, conv, need_dgrad=True):
+        """nn.Conv3d k=1 over cat(srcs) -> Raw."""
+        a0 = srcs[0]
+        N, dims = a0.N, a0.dims
+        w, b = conv.weight, conv.bias
+        Co, Ci = w.shape[0], w.shape[1]
+        raw = self.get_raw(N, Co, dims)
+        self.pointwise([(a, None, None) for a in srcs], w.detach(), b.detach() if b is not None else None, out_raw=raw)
+
+        def bwd():
+            g16 = self.raw_grad.pop(raw.t.data_ptr())
+            if need_dgrad:
+                graw = self.new_graw(N, Ci, dims)
+                wT = self.derived(lambda: w.detach().reshape(Co, Ci).t().contiguous())
+                self.pointwise([(g16, None, None)], wT, None, out_raw=graw)
+            dw = self.small_grad(w)
+            db = self.small_grad(b) if b is not None else None
+            off = 0
+            for i, a in enumerate(srcs):
+                if need_dgrad:
+                    self.add_act_grad(a, (graw.t, graw.cb_total, off // 8))
+                self.add("dp_small_wgrad", *self._gsum([], g16), Co, a.hi_ptr, a.lo_ptr, a.cb_total, a.cb_off, a.C, None,
+                         N, dims[0], dims[1], dims[2], 0, dw.data_ptr() + off * 8, Ci, 1, 0,
+                         db.data_ptr() if (db is not None and i == 0) else None)
+                off += a.C
+        self.tape.append(bwd)
+        return raw
+
+    def t_head(self, a, conv):
+        """dose head: 1x1x1 conv C -> 1, planar fp32 output."""
+        w, b = conv.weight, conv.bias
+        y = self.zeros((a.N, w.shape[0]) + a.dims, torch.float32)
+        self.pointwise([(a, None, None)], w.detach(), b.detach(), out_planar=y)
+
+        def bwd():
+            g = self.planar_grad.pop(y.data_ptr())
+            graw = self.new_graw(a.N, a.C, a.dims)
+            self.add("dp_head_bwd", g.data_ptr(), a.hi_ptr, a.lo_ptr, a.cb_total, a.cb_off, a.C, w.data_ptr(), a.N, a.vox,
+                     graw.t.data_ptr(), graw.cb_total, 0, self.small_grad(w).data_ptr(), self.small_grad(b).data_ptr())
+            self.add_act_grad(a, (graw.t, graw.cb_total, 0))
+        self.tape.append(bwd)
+        return y
+
+    def t_deconv(self, src, w, out):
+        """ConvTranspose3d k2 s2 (no bias): src Act or Tokens -> out Act."""
+        Ci, Co = w.shape[0], w.shape[1]
+        self.deconv2x(src, w, out)
+
+        def bwd():
+            dy = self.act_grads.pop(self._key(out))
+            wb = self.derived(lambda: w.detach().permute(2, 3, 4, 1, 0).reshape(8, Co, Ci).contiguous())
+            dw = self.small_grad(w)
+            if isinstance(src, Tokens):
+                B, T, C = src.t.shape
+                D, H, W = src.grid
+                dtok = self.zeros((B, T, C), torch.float32)
+                self.add("dp_deconv2x_bwd_data", *self._gsum(dy), Co, wb.data_ptr(), Ci, B, D, H, W, None, 0, 0, dtok.data_ptr())
+                self.tok_grads.setdefault(src.t.data_ptr(), []).append(dtok)
+                self.add("dp_small_wgrad", *self._gsum(dy), Co, None, None, 0, 0, C, src.t.data_ptr(), B, D, H, W, 1,
+                         dw.data_ptr(), 8, Co * 8, 1, None)
+            else:
+                D, H, W = src.dims
+                graw = self.new_graw(src.N, Ci, src.dims)
+                self.add("dp_deconv2x_bwd_data", *self._gsum(dy), Co, wb.data_ptr(), Ci, src.N, D, H, W, graw.t.data_ptr(),
+                         graw.cb_total, 0, None)
+                self.add_act_grad(src, (graw.t, graw.cb_total, 0))
+                self.add("dp_small_wgrad", *self._gsum(dy), Co, src.hi_ptr, src.lo_ptr, src.cb_total, src.cb_off, src.C, None,
+                         src.N, D, H, W, 1, dw.data_ptr(), 8, Co * 8, 1, None)
+        self.tape.append(bwd)
+
+    # ------------------------------------------------------------------ token-side helpers
+    def transpose(self, src, R, C, dst, batch=1, src_bs=0, dst_bs=0, ld_src=None, ld_dst=None, scale=1.0):
+        self.add("dp_transpose", src.data_ptr(), int(src.dtype == torch.float32), src_bs, ld_src or C, R, C, dst.data_ptr(),
+                 dst_bs, ld_dst or R, batch, float(scale))
+
+    def heads(self, src, dst, B, T, heads, hd, ld, col0, merge, scale=1.0):
+        self.add("dp_heads", src.data_ptr(), int(src.dtype == torch.float32), dst.data_ptr(),
+                 int(dst.dtype == torch.float32), B, T, heads, hd, ld, col0, int(merge), float(scale))
+
+    def colsum(self, a, rows, cols, p):
+        self.add("dp_colsum", a.data_ptr(), rows, cols, self.small_grad(p).data_ptr())
+
+    def linear_bwd(self, lin, x16, dy32, M, want_dx=True, dx_f16=False):
+        """y = x W^T (+b): returns dx (fp32, or fp16 if dx_f16); writes dW, db.  x16 [M,in] fp16, dy32 [M,out] fp32."""
+        w = lin.weight
+        out_f, in_f = w.shape
+        dy16 = self.zeros((M, out_f), torch.float16)
+        self.add("dp_add", dy32.data_ptr(), None, M * out_f, None, dy16.data_ptr())
+        dyT = self.zeros((out_f, M), torch.float16)
+        self.transpose(dy32, M, out_f, dyT)
+        xT = self.zeros((in_f, M), torch.float16)
+        self.transpose(x16, M, in_f, xT)
+        self.gemm(dyT, xT, out_f, in_f, M, out_f32=self.grad(w))
+        if lin.bias is not None:
+            self.colsum(dy32, M, out_f, lin.bias)
+        if not want_dx:
+            return None
+        wT = self.derived(lambda: w.detach().t().contiguous().half())          # [in, out]
+        if dx_f16:
+            dx = self.zeros((M, in_f), torch.float16)
+            self.gemm(dy16, wT, M, in_f, out_f, out_f16=dx)
+        else:
+            dx = self.zeros((M, in_f), torch.float32)
+            self.gemm(dy16, wT, M, in_f, out_f, out_f32=dx)
+        return dx
+
+    def t_vit(self, vit, parts, N, S, taps):
+        """monai ViT forward (perceptron patch embedding) with every intermediate kept + its backward."""
+        P = self
+        hidden, heads, L = vit.hidden_size, vit.num_heads, vit.num_layers
+        hd = hidden // heads
+        grid = tuple(s // 16 for s in S)
+        T = grid[0] * grid[1] * grid[2]
+        M = N * T
+        Tp = ceil_div(T, 8) * 8
+        first = parts[0]
+        ncb = sum(ceil_div(a.C, 8) if i == len(parts) - 1 else blocks16(a.C) for i, a in enumerate(parts))
+        slots, base = [], 0
+        for a in parts:
+            assert a.cb_off == first.cb_off + base // 8 and a.buf is first.buf, "ViT input parts must be adjacent"
+            slots += [base + c for c in range(a.C)]
+            base += blocks16(a.C) * 8
+        K = ncb * 4096 * 8
+        Cin = len(slots)
+        pe = vit.patch_embedding
+        assert pe.pos_embed == "perceptron", "training path: perceptron patch embedding (dose_pyfer.py:55-67)"
+        lin = pe.patch_embeddings[1]
+        slot_idx = torch.tensor(slots, device=P.device)
+
+        def pack_pe():
+            w = lin.weight.detach().view(hidden, 16, 16, 16, Cin)
+            wfull = torch.zeros((hidden, 16, 16, 16, ncb * 8), device=P.device)
+            wfull[..., slot_idx] = w
+            return wfull.view(hidden, 16, 16, 16, ncb, 8).permute(0, 4, 1, 2, 3, 5).reshape(hidden, K).half()
+        wpe = P.derived(pack_pe)
+        A = P.zeros((M, K), torch.float16)
+        P.patchify(first, ncb, A)
+        x0 = P.zeros((M, hidden), torch.float32)
+        pos = pe.position_embeddings.detach().reshape(T, hidden)
+        tiles = ceil_div(M, 128) * ceil_div(hidden, 128)
+        total_kb = K // 64
+        split_k = max(1, min(total_kb, (2 * 148) // tiles))
+        split_k = ceil_div(total_kb, ceil_div(total_kb, split_k))
+        P.gemm_splitk(A, wpe, M, hidden, K, split_k, x0, bias=lin.bias.detach(), rowvec=pos, row_period=T)
+        scores = P.zeros((N * heads, T, T), torch.float32)
+        saved = []
+        hs = {}
+        x = x0
+        f16 = lambda *shape: P.zeros(shape, torch.float16)
+        for i, blk in enumerate(vit.blocks):
+            ln1 = f16(M, hidden)
+            P.layernorm(x, blk.norm1.weight.detach(), blk.norm1.bias.detach(), M, hidden, out_f16=ln1)
+            q, k, vt = f16(N * heads, T, hd), f16(N * heads, T, hd), f16(N * heads, hd, Tp)
+            wqkv = P.derived(lambda blk=blk: blk.attn.qkv.weight.detach().half())
+            P.gemm(ln1, wqkv, M, 3 * hidden, hidden, qkv=(heads, hd, T, q, k, vt, hd ** -0.5))
+            P.gemm(q, k, T, T, hd, batch=N * heads, a_batch_rows=T, b_batch_rows=T, c_batch_stride=T * T, ldc=T, out_f32=scores)
+            probs = f16(N * heads, T, Tp)
+            P.softmax(scores, N * heads * T, T, probs)
+            o = f16(M, hidden)
+            P.gemm(probs, vt, T, hd, Tp, batch=N * heads, a_batch_rows=T, b_batch_rows=hd, c_batch_stride=T * hidden,
+                   c_batch_period=heads, c_batch_stride2=hd, ldc=hidden, out_f16=o)
+            xm = P.zeros((M, hidden), torch.float32)
+            wo = P.derived(lambda blk=blk: blk.attn.out_proj.weight.detach().half())
+            P.gemm(o, wo, M, hidden, hidden, bias=blk.attn.out_proj.bias.detach(), resid=x, out_f32=xm)
+            ln2 = f16(M, hidden)
+            P.layernorm(xm, blk.norm2.weight.detach(), blk.norm2.bias.detach(), M, hidden, out_f16=ln2)
+            u = P.zeros((M, vit.mlp_dim), torch.float32)
+            w1 = P.derived(lambda blk=blk: blk.mlp.linear1.weight.detach().half())
+            P.gemm(ln2, w1, M, vit.mlp_dim, hidden, bias=blk.mlp.linear1.bias.detach(), out_f32=u)
+            h = f16(M, vit.mlp_dim)
+            P.add("dp_act_fwd", u.data_ptr(), M * vit.mlp_dim, ACT_ID["gelu"], h.data_ptr())
+            xo = P.zeros((M, hidden), torch.float32)
+            tap = None
+            if i in taps:
+                tap = f16(N, T, hidden)
+                hs[i] = Tokens(tap, grid)
+            w2 = P.derived(lambda blk=blk: blk.mlp.linear2.weight.detach().half())
+            P.gemm(h, w2, M, hidden, vit.mlp_dim, bias=blk.mlp.linear2.bias.detach(), resid=xm, out_f32=xo, out_f16=tap)
+            saved.append(dict(x_in=x, ln1=ln1, q=q, k=k, vt=vt, probs=probs, o=o, xm=xm, ln2=ln2, u=u, h=h, tap=tap))
+            x = xo
+        z = f16(N, T, hidden)
+        P.layernorm(x, vit.norm.weight.detach(), vit.norm.bias.detach(), M, hidden, out_f16=z)
+        x_last = x
+
+        def sum_tok(ts):
+            g = ts[0]
+            for t in ts[1:]:
+                s = P.zeros((M, hidden), torch.float32)
+                P.add("dp_add", g.data_ptr(), t.data_ptr(), M * hidden, s.data_ptr(), None)
+                g = s
+            return g
+
+        def bwd():
+            f32 = lambda *shape: P.zeros(shape, torch.float32)
+            dz = sum_tok(P.tok_grads.pop(z.data_ptr()))
+            dx = f32(M, hidden)
+            P.add("dp_layernorm_bwd", x_last.data_ptr(), vit.norm.weight.data_ptr(), dz.data_ptr(), None, M, hidden,
+                  dx.data_ptr(), P.small_grad(vit.norm.weight).data_ptr(), P.small_grad(vit.norm.bias).data_ptr())
+            BH = N * heads
+            for i in reversed(range(L)):
+                blk, sv = vit.blocks[i], saved[i]
+                if sv["tap"] is not None:
+                    dx = sum_tok([dx] + P.tok_grads.pop(sv["tap"].data_ptr()))
+                # ---- MLP branch: xo = xm + linear2(gelu(linear1(LN2(xm))))
+                dh = P.linear_bwd(blk.mlp.linear2, sv["h"], dx, M)
+                du = f32(M, vit.mlp_dim)
+                P.add("dp_act_bwd", sv["u"].data_ptr(), dh.data_ptr(), M * vit.mlp_dim, ACT_ID["gelu"], du.data_ptr(), None)
+                dln2 = P.linear_bwd(blk.mlp.linear1, sv["ln2"], du, M)
+                dxm = f32(M, hidden)
+                P.add("dp_layernorm_bwd", sv["xm"].data_ptr(), blk.norm2.weight.data_ptr(), dln2.data_ptr(), dx.data_ptr(), M,
+                      hidden, dxm.data_ptr(), P.small_grad(blk.norm2.weight).data_ptr(), P.small_grad(blk.norm2.bias).data_ptr())
+                # ---- attention branch: xm = x_in + out_proj(softmax(q k^T) v)
+                do16 = P.linear_bwd(blk.attn.out_proj, sv["o"], dxm, M, dx_f16=True)
+                doh = P.zeros((BH, T, hd), torch.float16)
+                P.heads(do16, doh, N, T, heads, hd, hidden, 0, merge=False)
+                v16 = P.zeros((BH, T, hd), torch.float16)
+                P.transpose(sv["vt"], hd, T, v16, batch=BH, src_bs=hd * Tp, dst_bs=T * hd, ld_src=Tp, ld_dst=hd)
+                dP = f32(BH, T, T)
+                P.gemm(doh, v16, T, T, hd, batch=BH, a_batch_rows=T, b_batch_rows=T, c_batch_stride=T * T, ldc=T, out_f32=dP)
+                dS = P.zeros((BH, T, Tp), torch.float16)
+                P.add("dp_softmax_bwd", sv["probs"].data_ptr(), Tp, dP.data_ptr(), T, BH * T, T, dS.data_ptr(), Tp)
+                kT = P.zeros((BH, hd, Tp), torch.float16)
+                P.transpose(sv["k"], T, hd, kT, batch=BH, src_bs=T * hd, dst_bs=hd * Tp, ld_src=hd, ld_dst=Tp)
+                qT = P.zeros((BH, hd, Tp), torch.float16)
+                P.transpose(sv["q"], T, hd, qT, batch=BH, src_bs=T * hd, dst_bs=hd * Tp, ld_src=hd, ld_dst=Tp)
+                dST = P.zeros((BH, T, Tp), torch.float16)
+                P.transpose(dS, T, T, dST, batch=BH, src_bs=T * Tp, dst_bs=T * Tp, ld_src=Tp, ld_dst=Tp)
+                PT = P.zeros((BH, T, Tp), torch.float16)
+                P.transpose(sv["probs"], T, T, PT, batch=BH, src_bs=T * Tp, dst_bs=T * Tp, ld_src=Tp, ld_dst=Tp)
+                dohT = P.zeros((BH, hd, Tp), torch.float16)
+                P.transpose(doh, T, hd, dohT, batch=BH, src_bs=T * hd, dst_bs=hd * Tp, ld_src=hd, ld_dst=Tp)
+                dq, dk, dv = f32(BH, T, hd), f32(BH, T, hd), f32(BH, T, hd)
+                bat = dict(batch=BH, a_batch_rows=T, b_batch_rows=hd, c_batch_stride=T * hd, ldc=hd)
+                P.gemm(dS, kT, T, hd, Tp, out_f32=dq, **bat)
+                P.gemm(dST, qT, T, hd, Tp, out_f32=dk, **bat)
+                P.gemm(PT, dohT, T, hd, Tp, out_f32=dv, **bat)
+                dqkv = f32(M, 3 * hidden)
+                P.heads(dq, dqkv, N, T, heads, hd, 3 * hidden, 0, merge=True, scale=hd ** -0.5)
+                P.heads(dk, dqkv, N, T, heads, hd, 3 * hidden, hidden, merge=True)
+                P.heads(dv, dqkv, N, T, heads, hd, 3 * hidden, 2 * hidden, merge=True)
+                dln1 = P.linear_bwd(blk.attn.qkv, sv["ln1"], dqkv, M)
+                dxi = f32(M, hidden)
+                P.add("dp_layernorm_bwd", sv["x_in"].data_ptr(), blk.norm1.weight.data_ptr(), dln1.data_ptr(), dxm.data_ptr(),
+                      M, hidden, dxi.data_ptr(), P.small_grad(blk.norm1.weight).data_ptr(), P.small_grad(blk.norm1.bias).data_ptr())
+                dx = dxi
+            # ---- patch embedding: x0 = A Wpe^T + b + pos
+            P.colsum(dx, M, hidden, lin.bias)
+            P.add("dp_colsum", dx.data_ptr(), N, T * hidden, P.small_grad(pe.position_embeddings).data_ptr())
+            dxT = P.zeros((hidden, M), torch.float16)
+            P.transpose(dx, M, hidden, dxT)
+            AT = P.zeros((K, M), torch.float16)
+            P.transpose(A, M, K, AT)
+            dwp = f32(hidden, K)
+            P.gemm(dxT, AT, hidden, K, M, out_f32=dwp)
+            gw = P.grad(lin.weight)
+
+            def unpack_pe():
+                g = dwp.view(hidden, ncb, 16, 16, 16, 8).permute(0, 2, 3, 4, 1, 5).reshape(hidden, 16, 16, 16, ncb * 8)
+                gw.view(hidden, 16, 16, 16, Cin).copy_(g[..., slot_idx])
+            P.add_py(unpack_pe)
+        P.tape.append(bwd)
+        return Tokens(z, grid), hs
+
+
+# --------------------------------------------------------------------------- train-mode network emitters
+def _t_res_block(P, blk, parts, out, need_dgrad=True):
+    """monai UnetResBlock.forward (k3 s1, InstanceNorm, LeakyReLU 0.01) with backward."""
+    N, dims = parts[0].N, parts[0].dims
+    Co = blk.conv1.conv.weight.shape[0]
+    raw1 = P.t_conv(parts, blk.conv1.conv, 3, need_dgrad=need_dgrad)
+    a1 = P.new_act(N, Co, dims)
+    P.t_norm(raw1, a1, act="lrelu")
+    raw2 = P.t_conv([a1], blk.conv2.conv, 3)
+    if blk.downsample:
+        raw3 = P.t_pointwise(parts, blk.conv3.conv, need_dgrad=need_dgrad)
+        P.t_norm(raw2, out, res=raw3, act_after_res="lrelu")
+    else:
+        assert len(parts) == 1
+        P.t_norm(raw2, out, res=parts[0], act_after_res="lrelu")
+
+
+def _t_pr_up(P, blk, tokens, out):
+    N = tokens.t.shape[0]
+    Co = blk.transp_conv_init.conv.weight.shape[1]
+    dims = tuple(2 * g for g in tokens.grid)
+    n_layers = len(blk.blocks)
+    h = out if n_layers == 0 else P.new_act(N, Co, dims)
+    P.t_deconv(tokens, blk.transp_conv_init.conv.weight, h)
+    for i, seq in enumerate(blk.blocks):
+        dims = tuple(2 * d for d in dims)
+        u = P.new_act(N, Co, dims)
+        P.t_deconv(h, seq[0].conv.weight, u)
+        dst = out if i == n_layers - 1 else P.new_act(N, Co, dims)
+        _t_res_block(P, seq[1], [u], dst)
+        h = dst
+
+
+def _t_conv_3_1(P, blk, parts, out):
+    """blocks_MDUNet.py:132-157 in train mode: the BatchNorm3d layers of conv_block_7 use batch statistics."""
+    N, dims = parts[0].N, parts[0].dims
+    act = blk.act
+    c3, c7 = blk.conv_3[0].conv, blk.conv_7[0].conv
+    C = c3[0].weight.shape[0]
+    z3, z7 = P.new_concat(N, [C, C], dims)
+    raw = P.t_conv(parts, c3[0], 3)
+    a = P.new_act(N, C, dims)
+    P.t_norm(raw, a, act="relu")
+    raw = P.t_conv([a], c3[3], 3)
+    y3, st3 = P.new_act(N, C, dims), P.new_stats(N, C)
+    P.t_norm(raw, y3, act="relu", stats_out=st3)
+    P.t_norm(y3, z3, act=act, stats=st3)
+    raw = P.t_conv(parts, c7[0], 7)
+    a7 = P.new_act(N, C, dims)
+    P.t_norm(raw, a7, act="relu", bn=c7[1])
+    raw = P.t_conv([a7], c7[3], 7)
+    y7, st7 = P.new_act(N, C, dims), P.new_stats(N, C)
+    P.t_norm(raw, y7, act="relu", bn=c7[4], stats_out=st7)
+    P.t_norm(y7, z7, act=act, stats=st7)
+    raw = P.t_pointwise([z3, z7], blk.conv[0])
+    P.t_norm(raw, out, act=act)
+
+
+def _t_main_subset(P, net, parts):
+    """MainSubsetModel.forward (dose_pyfer.py:311-319) in train mode; returns the four planar dose outputs."""
+    enc, dec = net.encoder, net.decoder
+    vit = enc.vit
+    N, dims = parts[0].N, parts[0].dims
+    i = enc.num_layers // 4
+    taps = (i, 2 * i, 3 * i)
+    fs = enc.skip1.layer.conv1.conv.weight.shape[0]
+    z, hs = P.t_vit(vit, parts, N, dims, taps)
+    sizes = [dims, tuple(d // 2 for d in dims), tuple(d // 4 for d in dims), tuple(d // 8 for d in dims)]
+    cats = [P.new_concat(N, [fs << l, fs << l], sizes[l]) for l in range(4)]
+    _t_res_block(P, enc.skip1.layer, parts, cats[0][1], need_dgrad=False)
+    _t_pr_up(P, enc.skip2, hs[taps[0]], cats[1][1])
+    _t_pr_up(P, enc.skip3, hs[taps[1]], cats[2][1])
+    _t_pr_up(P, enc.skip4, hs[taps[2]], cats[3][1])
+    decs, inp = [], z
+    for lvl, blk in zip((3, 2, 1, 0), (dec.decoder4, dec.decoder3, dec.decoder2, dec.decoder1)):
+        if not isinstance(blk.conv_block.cov_, nw.conv_3_1):
+            raise RuntimeError("training path covers the multi-scale decoder (mode_multi_dec=True, multiS_conv=True)")
+        out = P.new_act(N, fs << lvl, sizes[lvl])
+        P.t_deconv(inp, blk.transp_conv.conv.weight, cats[lvl][0])
+        _t_conv_3_1(P, blk.conv_block.cov_, cats[lvl], out)
+        decs.append(out)
+        inp = out
+    return [P.t_head(d, conv[0]) for d, conv in zip(decs[::-1], net.dose_convertors)]
+
+
+class DoseTrainer:
+    """One DOSE-PYFER training step per call: `loss = trainer.step(input_[B,9,S,S,S], gt[B,2,S,S,S])`.
+
+    model: dose_prediction_b200.networks.Model on a CUDA device (parameters are re-homed into one flat fp32
+    buffer; state_dict() keeps working).  freeze=True as in the reference (net_A / conv_out_A get no gradient)."""
+
+    def __init__(self, model, batch, size, lr=1e-4, weight_decay=1e-4, delta1=10.0, delta2=8.0, freeze=True,
+                 betas=(0.9, 0.999), eps=1e-8, loss_scale=4096.0, process_group=None):
+        if not freeze:
+            raise RuntimeError("training path: freeze=True only (net_A frozen, train_light_pyfer.py:85-88)")
+        dev = next(model.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("dose_prediction_b200 trains on CUDA devices only (no CPU fallback)")
+        self.model, self.device, self.batch, self.size = model, dev, batch, size
+        self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
+        self.delta1, self.delta2, self.loss_scale = delta1, delta2, float(loss_scale)
+        self.group = process_group
+        self.step_count = 0
+        for n, p in model.named_parameters():
+            p.requires_grad_(not (n.startswith("net_A") or n.startswith("conv_out_A")))
+        self.params = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+        total = sum((p.numel() + 3) // 4 * 4 for _, p in self.params)
+        self.flat_p = torch.zeros(total, device=dev)
+        self.flat_g = torch.zeros(total, device=dev)
+        self.flat_m = torch.zeros(total, device=dev)
+        self.flat_v = torch.zeros(total, device=dev)
+        self.found_inf = torch.zeros(1, dtype=torch.int32, device=dev)
+        P = TrainPlan(dev, loss_scale)
+        off = 0
+        self.offsets = {}
+        with torch.no_grad():
+            for n, p in self.params:
+                k = p.numel()
+                view = self.flat_p[off:off + k].view(p.shape)
+                view.copy_(p.data.to(dev, torch.float32))
+                p.data = view
+                P.grad_of[id(p)] = self.flat_g[off:off + k].view(p.shape)
+                self.offsets[n] = (off, k)
+                off += (k + 3) // 4 * 4
+        self.total = total
+        self.P = P
+        self._emit()
+
+    def _emit(self):
+        P, m = self.P, self.model
+        N, S = self.batch, self.size
+        dims = (S, S, S)
+        P.x_in = P.zeros((N, m.in_ch) + dims, torch.float32)
+        P.gt = P.zeros((N, 2) + dims, torch.float32)
+        a_out, x_act = P.new_concat(N, [m.net_A.list_ch[1], m.in_ch], dims, lo=True)
+        P.add_zero(self.flat_g)
+        P.add_zero(P.arena)
+        P.pack_input(P.x_in, x_act)
+        P.training = False          # frozen net_A: inference emitter, weights packed once (InstanceNorm: no running stats)
+        nw._emit_base_unet(P, m.net_A, x_act, a_out)
+        self.out_A = P.zeros((N, m.out_ch) + dims, torch.float32)
+        P.pointwise([(a_out, None, None)], m.conv_out_A.weight, m.conv_out_A.bias, out_planar=self.out_A)
+        P.training = True
+        outs = _t_main_subset(P, m.net_B, [a_out, x_act])
+        self.outs = outs
+        # ---- GenLoss forward
+        acc = P.zeros((2 * len(outs),), torch.float64)
+        P.add_zero(acc)
+        self.loss = P.zeros((1,), torch.float32)
+        sizes = [o.shape[2] for o in outs]
+        for i, o in enumerate(outs):
+            P.add("dp_masked_l1", o.data_ptr(), P.gt.data_ptr(), N, S, sizes[i], acc[2 * i:].data_ptr(), 0, 0.0, None)
+        P.add("dp_genloss_finalize", acc.data_ptr(), len(outs), float(self.delta1), float(self.delta2), self.loss.data_ptr())
+        # ---- backward
+        for i, o in enumerate(outs):
+            g = P.zeros(tuple(o.shape), torch.float32)
+            coef = self.loss_scale * (self.delta1 if i == 0 else self.delta2 / (len(outs) - 1))
+            P.add("dp_masked_l1", o.data_ptr(), P.gt.data_ptr(), N, S, sizes[i], acc[2 * i:].data_ptr(), 1, float(coef),
+                  g.data_ptr())
+            P.planar_grad[o.data_ptr()] = g
+        for bwd in reversed(P.tape):
+            bwd()
+        for acc64, g, n in P.finalizers:
+            P.add("dp_grad_finalize", acc64.data_ptr(), g.data_ptr(), n, 1.0)
+        self.fwd_bwd_steps = len(P.steps)
+
+    def _allreduce(self):
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            dist.all_reduce(self.flat_g, group=self.group)
+            self.flat_g.div_(dist.get_world_size(self.group))
+
+    def forward_backward(self, x, gt):
+        """forward + loss + backward; gradients (times loss_scale) are left in the flat gradient buffer."""
+        P = self.P
+        P.x_in.copy_(x.to(torch.float32), non_blocking=True)
+        P.gt.copy_(gt.to(torch.float32), non_blocking=True)
+        P.refresh_weights()
+        P.run()
+        self._allreduce()
+        return self.loss
+
+    def step(self, x, gt):
+        loss = self.forward_backward(x, gt)
+        self.step_count += 1
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        lib = self.P.lib
+        self.found_inf.zero_()
+        _lib.check(lib.dp_grad_check(self.flat_g.data_ptr(), self.total, self.found_inf.data_ptr(), s), "dp_grad_check")
+        _lib.check(lib.dp_adamw(self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.flat_m.data_ptr(), self.flat_v.data_ptr(),
+                                self.total, self.lr, self.betas[0], self.betas[1], self.eps, self.wd, self.step_count,
+                                1.0 / self.loss_scale, self.found_inf.data_ptr(), s), "dp_adamw")
+        return loss
+
+    def grads(self):
+        """{parameter name: unscaled fp32 gradient} (copies; for tests / inspection)."""
+        return {n: (self.flat_g[o:o + k] / self.loss_scale).view(p.shape).clone() for (n, p), (o, k) in
+                zip(self.params, (self.offsets[n] for n, _ in self.params))}
+
+    def outputs(self):
+        return [self.out_A.clone(), [o.clone() for o in self.outs]]

@@ -167,6 +167,110 @@ int dp_window_add(const float* win, int ncls, int R, int n_win, const int* win_b
                   const int* win_z0, const int* win_slot, float* out, int S0, int S1, int S2, cudaStream_t stream);
 int dp_div_count(float* data, const float* count, long long vol, int rows, cudaStream_t stream);
 
+/* ======================================================================== training step
+ * Pyfer.training_step (train_light_pyfer.py:122-143): train-mode forward, GenLoss (loss.py:69-119), backward
+ * through net_B (net_A frozen, train_light_pyfer.py:85-88) and the optimizer update (:194-197).  The forward
+ * convolutions, dgrad convolutions (same kernels, transposed/flipped weights) and the token GEMMs run through
+ * the entry points above; the entry points below are the autograd / loss / optimizer pieces ATen provides
+ * to the reference.
+ *
+ * "gradient sum": the upstream gradient of a tensor with several consumers arrives as up to three fp32 c8
+ * tensors (n_g, g_f32[], g_cb_total[], g_cb_off[]) and/or one fp16 c8 tensor (g_f16, g16_cb_total,
+ * g16_cb_off); the kernels add them on load (what autograd's AccumulateGrad / add_ nodes do).            */
+
+/* Backward of dp_norm_act (native_batch_norm_backward / instance_norm backward + threshold / leaky_relu /
+ * mish backward + the residual add of monai UnetResBlock.forward).  Same forward operands as dp_norm_act; the
+ * forward values are recomputed from the saved pre-normalisation tensor.  phase 0 accumulates
+ * bsum[N][C][6] = {sum g, sum g*xh, sum g_res, sum g_res*eh, dgamma, dbeta} (zero it first); phase 1 writes
+ * dx (fp16 c8 for the tensor-core dgrad/wgrad kernels, or fp32 c8) and the residual-branch gradient.
+ * For train-mode BatchNorm3d (blocks_MDUNet.py:103,106) run dp_batch_combine on stats / bsum between the
+ * phases.                                                                                              */
+int dp_norm_act_bwd(const float* raw_f32, const void* raw_hi, const void* raw_lo, int in_cb_total, int in_cb_off,
+                    const double* stats, const float* gamma, const float* beta, int act, const void* res_hi,
+                    const void* res_lo, const float* res_raw, const double* res_stats, int res_cb_total,
+                    int res_cb_off, int act_after_res, int n_dy, const float* const* dy_f32, const int* dy_cb_total,
+                    const int* dy_cb_off, const void* dy_f16, int dy16_cb_total, int dy16_cb_off, double* bsum,
+                    int phase, void* dx_hi, float* dx_f32, int dx_cb_total, int dx_cb_off, void* dres_hi,
+                    float* dres_f32, int dres_cb_total, int dres_cb_off, int N, int C, long long vox,
+                    cudaStream_t stream);
+
+/* nn.BatchNorm3d in train mode: replace the per-(n,c) slots [N][C][k] by their mean over n (so the
+ * per-instance consumers see batch statistics) and, for k == 2 with running_mean != NULL, update the running
+ * statistics (momentum, unbiased variance) exactly like torch.batch_norm(training=True).                */
+int dp_batch_combine(double* slots, int N, int C, int k, long long vox, float* running_mean, float* running_var,
+                     float momentum, cudaStream_t stream);
+
+/* dgamma / dbeta of an affine norm from bsum slots 4, 5 (summed over n), times scale */
+int dp_affine_grad(const double* bsum, int N, int C, float* dgamma, float* dbeta, float scale, cudaStream_t stream);
+
+/* grad[i] = acc[i] * scale: converts the fp64 accumulation arena of the small parameter gradients */
+int dp_grad_finalize(const double* acc, float* grad, long long n, float scale, cudaStream_t stream);
+
+/* Weight gradient of nn.Conv3d (stride 1, k in {1,3,7}, dilation dil): slow_conv3d / cudnn wgrad of
+ * blocks_MDUNet.py:68-71,102-105, monai UnetResBlock.conv1/conv2.  x: c8 fp16 forward input (16-channel chunks
+ * chunk_cb[] holding logical channels chunk_ci0[] .. +chunk_nci[]), g: c8 fp16 gradient of the conv output.
+ * Writes `splits` fp32 partials ws[splits][cout][cin][k][k][k] (sum them with dp_splitk_reduce).        */
+int dp_conv3d_wgrad(const void* x_c8, int x_cb_total, const uint8_t* chunk_cb, const int* chunk_ci0,
+                    const int* chunk_nci, int n_chunks, const void* g_c8, int g_cb_total, int g_cb_off, int N, int D,
+                    int H, int W, int cin, int cout, int k, int dil, float* ws, int splits, cudaStream_t stream);
+
+/* Weight (+bias) gradient of the 1x1x1 convolutions (blocks_MDUNet.py:145-157, monai UnetResBlock.conv3) and,
+ * with deconv = 1, of nn.ConvTranspose3d k2 s2 (base_blocks.py:118-127, monai UnetrPrUpBlock):
+ * dw[co*dw_co_stride + ci*dw_ci_stride + o*dw_o_stride] += sum g[co][child_o(v)] * x[ci][v]  (fp64 atomics).
+ * x is a c8 fp16 tensor, or a token matrix [N][D*H*W][x_C] fp16 (x_tok).                                 */
+int dp_small_wgrad(int n_g, const float* const* g_f32, const int* g_cb_total, const int* g_cb_off, const void* g_f16,
+                   int g16_cb_total, int g16_cb_off, int g_C, const void* x_hi, const void* x_lo, int x_cb_total,
+                   int x_cb_off, int x_C, const void* x_tok, int N, int D, int H, int W, int deconv, double* dw,
+                   long long dw_co_stride, long long dw_ci_stride, long long dw_o_stride, double* dbias,
+                   cudaStream_t stream);
+
+/* Data gradient of nn.ConvTranspose3d k2 s2: dx[ci][v] = sum_{o,co} g[co][child_o(v)] * W[ci][co][o].
+ * w fp32 [8][Co][Ci]; output fp32 c8 (dx_c8) or fp32 tokens [N][D*H*W][Ci] (dx_tok).                     */
+int dp_deconv2x_bwd_data(int n_g, const float* const* g_f32, const int* g_cb_total, const int* g_cb_off,
+                         const void* g_f16, int g16_cb_total, int g16_cb_off, int Co, const float* w, int Ci, int N,
+                         int D, int H, int W, float* dx_c8, int dx_cb_total, int dx_cb_off, float* dx_tok,
+                         cudaStream_t stream);
+
+/* Backward of the dose heads (1x1x1 conv C -> 1, dose_pyfer.py:290-300,316-317): g planar fp32 [N][vox];
+ * dx (fp32 c8) = g*w[c]; dw[c] += sum g*x[c]; db += sum g  (fp64 accumulators).                          */
+int dp_head_bwd(const float* g, const void* x_hi, const void* x_lo, int x_cb_total, int x_cb_off, int C,
+                const float* w, int N, long long vox, float* dx, int dx_cb_total, int dx_cb_off, double* dw,
+                double* db, cudaStream_t stream);
+
+/* GenLoss (loss.py:57-119): masked L1 of one prediction scale s^3 against the GT [N][2][S^3] (dose, possible-dose
+ * mask), the GT resampled like loss.py:63-64 (trilinear align_corners=True / nearest-exact).  phase 0:
+ * acc[0] += sum |p-t|, acc[1] += #mask;  phase 1: dpred = coef * sign(p-t) / acc[1].                     */
+int dp_masked_l1(const float* pred, const float* gt, int N, int S, int s, double* acc, int phase, float coef,
+                 float* dpred, cudaStream_t stream);
+/* loss = delta1 * acc[0]/acc[1] + delta2 * mean_{i>=1} acc[2i]/acc[2i+1]   (loss.py:96-112) */
+int dp_genloss_finalize(const double* acc, int n_scales, float delta1, float delta2, float* loss, cudaStream_t stream);
+
+/* Fused AdamW over a flat fp32 parameter buffer (configure_optimizers, train_light_pyfer.py:194-197; fp32
+ * optimizer state, decoupled weight decay).  inv_scale undoes the static loss scaling; when *found_inf != 0
+ * (dp_grad_check) the update is skipped.                                                                */
+int dp_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+             float weight_decay, int step, float inv_scale, const int* found_inf, cudaStream_t stream);
+int dp_grad_check(const float* g, long long n, int* found_inf, cudaStream_t stream);
+
+/* Token-side backward pieces of monai ViT (nn.LayerNorm, softmax, GELU backward; layout shuffles that feed
+ * the dgrad / wgrad GEMMs of dp_gemm_tc, which wants both operands K-major).                             */
+int dp_layernorm_bwd(const float* x, const float* gamma, const float* dy, const float* add, int rows, int cols,
+                     float* dx, double* dgamma, double* dbeta, cudaStream_t stream);
+int dp_softmax_bwd(const void* probs, int ld_p, const float* dprobs, int ld_dp, int rows, int cols, void* ds, int ld_ds,
+                   cudaStream_t stream);
+int dp_act_fwd(const float* u, long long n, int act, void* y_f16, cudaStream_t stream);
+int dp_act_bwd(const float* u, const float* dh, long long n, int act, float* du_f32, void* du_f16, cudaStream_t stream);
+/* dst[b][c][r] = scale * src[b][r][c] (fp32 or fp16 source, fp16 destination with row pitch ld_dst) */
+int dp_transpose(const void* src, int src_f32, long long src_batch_stride, int ld_src, int R, int C, void* dst_f16,
+                 long long dst_batch_stride, int ld_dst, int batch, float scale, cudaStream_t stream);
+/* split (merge = 0) rows [B][T][ld] (columns col0 + head*hd + d) into [B*heads][T][hd], or merge back */
+int dp_heads(const void* src, int src_f32, void* dst, int dst_f32, int B, int T, int heads, int hd, int ld, int col0,
+             int merge, float scale, cudaStream_t stream);
+/* out[c] += sum_r a[r][c] (bias / position-embedding gradients, fp64 accumulators) */
+int dp_colsum(const float* a, int rows, long long cols, double* out, cudaStream_t stream);
+/* y = a + b (b optional), fp32 and/or fp16 outputs */
+int dp_add(const float* a, const float* b, long long n, float* y_f32, void* y_f16, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 from dose_prediction_b200 import synth  # noqa: E402
-from oracle import ref_loader, synth_ckpt  # noqa: E402
+from oracle import ref_loader, synth_ckpt, torch_ref  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
 DOSE_SEED, SEG_SEED = 0, 1
@@ -82,6 +82,35 @@ def main():
     with torch.no_grad():
         val = loss_mod(out, vol["gt"], casecade=True, freez=True, delta1=10, delta2=8)
     np.savez_compressed(os.path.join(OUT, "genloss32.npz"), loss=np.float64(val.item()))
+
+    # ---- training step (train_light_pyfer.py:85-88,122-143): reference modules in train mode + GenLoss + autograd,
+    # then one AdamW step; per-parameter gradient norms, sampled gradient / updated-parameter entries, BN running stats
+    tm = ref_loader.build_dose(32).train()
+    tm.load_state_dict(synth_ckpt.make_state_dict(synth_ckpt.manifest_of(tm), DOSE_SEED), strict=True)
+    for n, p_ in tm.named_parameters():
+        if "net_A" in n or "conv_out_A" in n:
+            p_.requires_grad = False
+    params = [(n, p_) for n, p_ in tm.named_parameters() if p_.requires_grad]
+    opt = torch.optim.AdamW([p_ for _, p_ in params], lr=1e-4, weight_decay=1e-4)
+    loss = loss_mod(tm(vol["dose_input"]), vol["gt"], casecade=True, freez=True, delta1=10, delta2=8)
+    loss.backward()
+    rec = {"loss": np.float64(loss.item())}
+    names, norms = [], []
+    for n, p_ in params:
+        g_ = p_.grad if p_.grad is not None else torch.zeros_like(p_)
+        names.append(n)
+        norms.append(float(g_.double().norm()))
+        rec["g/" + n] = _np(g_.flatten()[torch_ref.sample_idx(g_.numel())])
+    opt.step()
+    for n, p_ in params:
+        rec["p/" + n] = _np(p_.detach().flatten()[torch_ref.sample_idx(p_.numel())])
+    bn = "net_B.decoder.decoder1.conv_block.cov_.conv_7.0.conv.1."
+    sd_after = tm.state_dict()
+    rec["running_mean"] = _np(sd_after[bn + "running_mean"])
+    rec["running_var"] = _np(sd_after[bn + "running_var"])
+    rec["names"] = np.array(names)
+    rec["norms"] = np.array(norms, dtype=np.float64)
+    np.savez_compressed(os.path.join(OUT, "train32.npz"), **rec)
 
     # ---- sliding window (monai restatement; seg net built for 32^3 scanned over a 48^3 CT)
     from monai.inferers import sliding_window_inference

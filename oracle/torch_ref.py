@@ -60,7 +60,17 @@ def _inorm(x, w=None, b=None):
     return F.instance_norm(x, weight=w, bias=b, eps=EPS)
 
 
+# BN_TRAIN = None: eval-mode BatchNorm3d (running statistics).  BN_TRAIN = {}: train mode (batch statistics,
+# momentum 0.1); the updated running statistics are collected in the dict under the state_dict keys.
+BN_TRAIN = None
+
+
 def _bn_eval(sd, p, x):
+    if BN_TRAIN is not None:
+        rm, rv = sd[p + "running_mean"].clone(), sd[p + "running_var"].clone()
+        y = F.batch_norm(x, rm, rv, sd[p + "weight"], sd[p + "bias"], training=True, momentum=0.1, eps=EPS)
+        BN_TRAIN[p + "running_mean"], BN_TRAIN[p + "running_var"] = rm, rv
+        return y
     return F.batch_norm(x, sd[p + "running_mean"], sd[p + "running_var"], sd[p + "weight"],
                         sd[p + "bias"], training=False, eps=EPS)
 
@@ -337,6 +347,44 @@ def gen_loss(predictions, gt, delta1=10.0, delta2=8.0):
     l_ds = l_ds / (len(preds) - 1)
     sel = mask > 0
     return delta1 * F.l1_loss(preds[0][sel], gt_dose[sel]) + delta2 * l_ds
+
+
+def dose_pyfer_train_step(sd: SD, x, gt, lr=1e-4, weight_decay=1e-4, delta1=10.0, delta2=8.0, betas=(0.9, 0.999),
+                          eps=1e-8, **kw):
+    """Pyfer.training_step + one optimizer step (DosePrediction/Train/train_light_pyfer.py:85-88,122-143,194-197):
+    train-mode forward (freeze=True: net_A.* / conv_out_A.* get no gradient), GenLoss, autograd, AdamW with fp32
+    state (the reference's bnb Adam8bit quantises the same update's state to 8 bit; not restated).
+    Returns (loss, {name: grad}, {name: updated parameter or running statistic}, forward outputs)."""
+    global BN_TRAIN
+    is_buffer = lambda k: k.endswith("running_mean") or k.endswith("running_var") or k.endswith("num_batches_tracked")
+    leaf = {k: v.detach().clone() for k, v in sd.items()}
+    train_keys = [k for k in leaf if not (k.startswith("net_A") or k.startswith("conv_out_A")) and not is_buffer(k)
+                  and leaf[k].is_floating_point()]
+    for k in train_keys:
+        leaf[k].requires_grad_(True)
+    BN_TRAIN = {}
+    try:
+        out = dose_pyfer_forward(leaf, x, **kw)
+        loss = gen_loss(out, gt, delta1, delta2)
+        loss.backward()
+        new_stats = dict(BN_TRAIN)
+    finally:
+        BN_TRAIN = None
+    grads = {k: (leaf[k].grad if leaf[k].grad is not None else torch.zeros_like(leaf[k])) for k in train_keys}
+    params = [leaf[k] for k in train_keys]
+    for p_, k in zip(params, train_keys):
+        p_.grad = grads[k]
+    torch.optim.AdamW(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay).step()
+    new = {k: leaf[k].detach() for k in train_keys}
+    new.update(new_stats)
+    outs = [out[0].detach(), [o.detach() for o in out[1]]]
+    return loss.detach(), grads, new, outs
+
+
+def sample_idx(numel, k=64):
+    """k evenly spaced flat indices (integer arithmetic; used by the training fixtures)."""
+    k = min(k, numel)
+    return torch.arange(k, dtype=torch.long) * ((numel - 1) // max(k - 1, 1))
 
 
 def rel_l2(a, b):

@@ -26,6 +26,32 @@ def test_library_exports_every_declared_symbol():
     assert isinstance(handle.dp_last_error(), bytes)
 
 
+def test_ctypes_signatures_match_the_header():
+    """argument count and kind (pointer / int / long long / float) of every ctypes signature == include/dose_b200.h."""
+    import ctypes
+    with open(os.path.join(ROOT, "include", "dose_b200.h")) as f:
+        text = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
+    seen = 0
+    for m in re.finditer(r"\bint\s+(dp_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", text):
+        name, args = m.group(1), [a.strip() for a in m.group(2).split(",")]
+        if name not in _lib._SIGNATURES:
+            continue
+        sig = _lib._SIGNATURES[name]
+        assert len(args) == len(sig), name
+        for a, t in zip(args, sig):
+            if "*" in a or "cudaStream_t" in a:
+                exp = ctypes.c_void_p
+            elif a.startswith("long long"):
+                exp = ctypes.c_longlong
+            elif a.startswith("float"):
+                exp = ctypes.c_float
+            else:
+                exp = ctypes.c_int
+            assert exp is t, (name, a)
+        seen += 1
+    assert seen == len(_lib._SIGNATURES)
+
+
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "_LIB", None)
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))

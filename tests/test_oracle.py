@@ -74,6 +74,29 @@ def test_gen_loss_matches_reference_fixture():
     assert abs(got - want) <= 1e-5 * abs(want)
 
 
+def test_train_step_matches_reference_fixture(dose_sd32):
+    """oracle train step (train-mode BN, GenLoss, autograd, AdamW) == the reference modules' own autograd."""
+    vol = synth.make_batch(2, 32, seed=1234)
+    g = np.load(os.path.join(GOLDEN, "train32.npz"))
+    loss, grads, new, _ = torch_ref.dose_pyfer_train_step(dose_sd32, vol["dose_input"], vol["gt"], lr=1e-4, weight_decay=1e-4)
+    assert abs(float(loss) - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    names, norms = list(g["names"]), g["norms"]
+    assert sorted(names) == sorted(grads)
+    gmax = norms.max()
+    for n, want in zip(names, norms):
+        got = float(grads[n].double().norm())
+        assert abs(got - want) <= 2e-3 * want + 1e-6 * gmax, n
+        idx = torch_ref.sample_idx(grads[n].numel())
+        ref = torch.from_numpy(g["g/" + n])
+        assert (grads[n].flatten()[idx] - ref).abs().max() <= 5e-3 * ref.abs().max() + 1e-6 * gmax, n
+    bn = "net_B.decoder.decoder1.conv_block.cov_.conv_7.0.conv.1."
+    assert torch_ref.rel_l2(new[bn + "running_mean"], torch.from_numpy(g["running_mean"])) < 1e-4
+    assert torch_ref.rel_l2(new[bn + "running_var"], torch.from_numpy(g["running_var"])) < 1e-4
+    w = "net_B.decoder.decoder1.conv_block.cov_.conv_7.0.conv.0.weight"
+    idx = torch_ref.sample_idx(new[w].numel())
+    assert (new[w].flatten()[idx] - torch.from_numpy(g["p/" + w])).abs().max() < 2.5e-4      # lr * O(1) per Adam step
+
+
 def test_sliding_window_matches_fixture(seg_sd32):
     ct48 = synth.make_volume(48, seed=77)["ct"]
     g = torch.from_numpy(np.load(os.path.join(GOLDEN, "sliding48.npz"))["logits"])
