@@ -568,7 +568,10 @@ class DoseTrainer:
     buffer; state_dict() keeps working).  freeze=True as in the reference (net_A / conv_out_A get no gradient)."""
 
     def __init__(self, model, batch, size, lr=1e-4, weight_decay=1e-4, delta1=10.0, delta2=8.0, freeze=True,
-                 betas=(0.9, 0.999), eps=1e-8, loss_scale=4096.0, process_group=None):
+                 betas=(0.9, 0.999), eps=1e-8, loss_scale=4096.0, process_group=None, probe=None):
+        """probe (tests only): list of four tensors R_i shaped like the dose outputs; the backward pass then starts
+        from dL/dpred_i = R_i (a linear loss sum <pred_i, R_i>) instead of the GenLoss gradient, whose sign()
+        makes gradient parity ill-conditioned."""
         if not freeze:
             raise RuntimeError("training path: freeze=True only (net_A frozen, train_light_pyfer.py:85-88)")
         dev = next(model.parameters()).device
@@ -578,6 +581,7 @@ class DoseTrainer:
         self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
         self.delta1, self.delta2, self.loss_scale = delta1, delta2, float(loss_scale)
         self.group = process_group
+        self.probe = probe
         self.step_count = 0
         for n, p in model.named_parameters():
             p.requires_grad_(not (n.startswith("net_A") or n.startswith("conv_out_A")))
@@ -633,8 +637,12 @@ class DoseTrainer:
         for i, o in enumerate(outs):
             g = P.zeros(tuple(o.shape), torch.float32)
             coef = self.loss_scale * (self.delta1 if i == 0 else self.delta2 / (len(outs) - 1))
-            P.add("dp_masked_l1", o.data_ptr(), P.gt.data_ptr(), N, S, sizes[i], acc[2 * i:].data_ptr(), 1, float(coef),
-                  g.data_ptr())
+            if self.probe is not None:
+                r = (self.probe[i].to(self.device, torch.float32) * self.loss_scale).contiguous()
+                P.add_py(lambda g=g, r=r: g.copy_(r))
+            else:
+                P.add("dp_masked_l1", o.data_ptr(), P.gt.data_ptr(), N, S, sizes[i], acc[2 * i:].data_ptr(), 1, float(coef),
+                      g.data_ptr())
             P.planar_grad[o.data_ptr()] = g
         for bwd in reversed(P.tape):
             bwd()

@@ -350,7 +350,7 @@ def gen_loss(predictions, gt, delta1=10.0, delta2=8.0):
 
 
 def dose_pyfer_train_step(sd: SD, x, gt, lr=1e-4, weight_decay=1e-4, delta1=10.0, delta2=8.0, betas=(0.9, 0.999),
-                          eps=1e-8, **kw):
+                          eps=1e-8, probe=None, **kw):
     """Pyfer.training_step + one optimizer step (DosePrediction/Train/train_light_pyfer.py:85-88,122-143,194-197):
     train-mode forward (freeze=True: net_A.* / conv_out_A.* get no gradient), GenLoss, autograd, AdamW with fp32
     state (the reference's bnb Adam8bit quantises the same update's state to 8 bit; not restated).
@@ -366,7 +366,10 @@ def dose_pyfer_train_step(sd: SD, x, gt, lr=1e-4, weight_decay=1e-4, delta1=10.0
     try:
         out = dose_pyfer_forward(leaf, x, **kw)
         loss = gen_loss(out, gt, delta1, delta2)
-        loss.backward()
+        if probe is not None:      # linear loss sum <pred_i, R_i>: smooth gradients for backward-pass parity tests
+            sum((o * r).sum() for o, r in zip(out[1], probe)).backward()
+        else:
+            loss.backward()
         new_stats = dict(BN_TRAIN)
     finally:
         BN_TRAIN = None
