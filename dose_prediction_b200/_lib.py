@@ -43,6 +43,7 @@ _SIGNATURES = {
     "dp_affine_grad": [P, I, I, P, P, F, P],
     "dp_grad_finalize": [P, P, L, F, P],
     "dp_conv3d_wgrad": [P, I, P, P, P, I, P, I, I, I, I, I, I, I, I, I, I, P, I, P],
+    "dp_conv3d_wgrad_tc": [P, I, P, P, P, I, P, I, I, I, I, I, I, I, I, I, P, I, P, P],
     "dp_small_wgrad": [I, P, P, P, P, I, I, I, P, P, I, I, I, P, I, I, I, I, I, P, L, L, L, P, P],
     "dp_deconv2x_bwd_data": [I, P, P, P, P, I, I, I, P, I, I, I, I, I, P, I, I, P, P],
     "dp_head_bwd": [P, P, P, I, I, I, P, I, L, P, I, I, P, P, P],

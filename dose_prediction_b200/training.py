@@ -19,6 +19,7 @@ Biases of convolutions that feed a normalisation layer have a mathematically zer
 """
 import ctypes
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -28,6 +29,7 @@ from .engine import ACT_ID, Act, Plan, Raw, Tokens, blocks16, ceil_div
 from . import networks as nw
 
 ARENA_DOUBLES = 1 << 22
+WGRAD_TC = os.environ.get("DP_WGRAD_TC", "1") != "0"      # bring-up switch: tcgen05 vs CUDA-core conv weight gradient
 
 
 class TrainPlan(Plan):
@@ -136,15 +138,25 @@ class TrainPlan(Plan):
                 nci.append(min(16, a.C - 16 * j))
             base += a.C
         assert base == Ci
-        blocks = k * k * len(cbs) * (Co // 16)
-        rows = a0.N * D * H
-        splits = max(1, min(ceil_div(rows, 64), (3 * 148) // blocks))
-        ws = self.zeros((splits, w.numel()), torch.float32)
         arrs = ((ctypes.c_uint8 * len(cbs))(*cbs), _lib.int_array(ci0), _lib.int_array(nci))
         self.keep.append(arrs)
-        self.count_flops("dp_conv3d_wgrad", 2.0 * a0.N * D * H * W * k ** 3 * Ci * Co)
-        self.add("dp_conv3d_wgrad", a0.buf.data_ptr(), a0.cb_total, *arrs, len(cbs), g16.buf.data_ptr(), g16.cb_total,
-                 g16.cb_off, a0.N, D, H, W, Ci, Co, k, dil, ws.data_ptr(), splits)
+        flops = 2.0 * a0.N * D * H * W * k ** 3 * Ci * Co
+        if WGRAD_TC and dil == 1 and k in (3, 7):
+            types = len(cbs) * (Co // 16) * (4 if k == 7 else 1)
+            row_blocks = a0.N * D * ceil_div(H, 12) * ceil_div(W, 64)
+            splits = max(1, min(row_blocks // 2, 148 // types if types <= 148 else 1))
+            ws = self.zeros((splits, w.numel()), torch.float32)
+            self.count_flops("dp_conv3d_wgrad_tc", flops)
+            self.add("dp_conv3d_wgrad_tc", a0.buf.data_ptr(), a0.cb_total, *arrs, len(cbs), g16.buf.data_ptr(), g16.cb_total,
+                     g16.cb_off, a0.N, D, H, W, Ci, Co, k, ws.data_ptr(), splits, self.err.data_ptr())
+        else:
+            blocks = k * k * len(cbs) * (Co // 16)
+            rows = a0.N * D * H
+            splits = max(1, min(ceil_div(rows, 64), (3 * 148) // blocks))
+            ws = self.zeros((splits, w.numel()), torch.float32)
+            self.count_flops("dp_conv3d_wgrad", flops)
+            self.add("dp_conv3d_wgrad", a0.buf.data_ptr(), a0.cb_total, *arrs, len(cbs), g16.buf.data_ptr(), g16.cb_total,
+                     g16.cb_off, a0.N, D, H, W, Ci, Co, k, dil, ws.data_ptr(), splits)
         self.add("dp_splitk_reduce", ws.data_ptr(), splits, 1, w.numel(), None, None, 0, self.grad(w).data_ptr())
 
     def t_norm(self, src, out, act=None, res=None, act_after_res=None, bn=None, stats=None, stats_out=None):

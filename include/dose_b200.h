@@ -214,6 +214,14 @@ int dp_conv3d_wgrad(const void* x_c8, int x_cb_total, const uint8_t* chunk_cb, c
                     const int* chunk_nci, int n_chunks, const void* g_c8, int g_cb_total, int g_cb_off, int N, int D,
                     int H, int W, int cin, int cout, int k, int dil, float* ws, int splits, cudaStream_t stream);
 
+/* The same weight gradient on tcgen05 tensor cores (k in {3,7}, dilation 1): both operands are read MN-major
+ * straight from the c8 layout (K = 16 voxels along W), the 16 M blocks are the x row at 16 overlapping one-voxel
+ * shifts (the kw taps), the N dimension stacks the k rows of the g plane (the kh taps); accumulators stay in
+ * TMEM over the CTA's whole share of the volume (wgrad_tc.cu).  Same partial-sum output as dp_conv3d_wgrad. */
+int dp_conv3d_wgrad_tc(const void* x_c8, int x_cb_total, const uint8_t* chunk_cb, const int* chunk_ci0,
+                       const int* chunk_nci, int n_chunks, const void* g_c8, int g_cb_total, int g_cb_off, int N, int D,
+                       int H, int W, int cin, int cout, int k, float* ws, int splits, int* err_flag, cudaStream_t stream);
+
 /* Weight (+bias) gradient of the 1x1x1 convolutions (blocks_MDUNet.py:145-157, monai UnetResBlock.conv3) and,
  * with deconv = 1, of nn.ConvTranspose3d k2 s2 (base_blocks.py:118-127, monai UnetrPrUpBlock):
  * dw[co*dw_co_stride + ci*dw_ci_stride + o*dw_o_stride] += sum g[co][child_o(v)] * x[ci][v]  (fp64 atomics).

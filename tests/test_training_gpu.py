@@ -164,13 +164,19 @@ def test_instance_norm_of_activation_backward():
     assert _rel(_c8_to_ncdhw(gt, C), xd.grad) < 1e-5
 
 
-@pytest.mark.parametrize("cin,cout,k,dil,dims", [
-    (16, 16, 3, 1, (6, 8, 16)),
-    (32, 16, 7, 1, (5, 9, 20)),
-    (25, 16, 3, 1, (4, 8, 8)),            # two parts (16 + 9 channels), like the encoder1 input
-    (64, 32, 3, 2, (6, 6, 8)),
+@pytest.mark.parametrize("cin,cout,k,dil,dims,tc", [
+    (16, 16, 3, 1, (6, 8, 16), True),
+    (32, 16, 7, 1, (5, 9, 20), True),
+    (25, 16, 3, 1, (4, 8, 8), True),            # two parts (16 + 9 channels), like the encoder1 input
+    (16, 32, 7, 1, (9, 40, 80), True),          # several row blocks, two W tiles, two C_out tiles
+    (32, 32, 3, 1, (8, 30, 4), True),           # W < 16 (deep decoder levels of small volumes)
+    (64, 32, 3, 2, (6, 6, 8), True),            # dilated: CUDA-core kernel
+    (16, 16, 3, 1, (6, 8, 16), False),
+    (32, 16, 7, 1, (5, 9, 20), False),
 ])
-def test_conv_wgrad_and_dgrad_match_autograd(cin, cout, k, dil, dims):
+def test_conv_wgrad_and_dgrad_match_autograd(cin, cout, k, dil, dims, tc, monkeypatch):
+    from dose_prediction_b200 import training
+    monkeypatch.setattr(training, "WGRAD_TC", tc)
     torch.manual_seed(3)
     N = 2
     x = torch.randn(N, cin, *dims, device=DEV)
