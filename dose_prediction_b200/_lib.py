@@ -51,6 +51,8 @@ _SIGNATURES = {
     "dp_genloss_finalize": [P, I, F, F, P, P],
     "dp_adamw": [P, P, P, P, L, F, F, F, F, F, I, F, P, P],
     "dp_grad_check": [P, L, P, P],
+    "dp_pack_conv_weight": [P, I, I, I, I, P, P, I, I, P, P],
+    "dp_cast_f16": [P, L, P, P],
     "dp_layernorm_bwd": [P, P, P, P, I, I, P, P, P, P],
     "dp_softmax_bwd": [P, I, P, I, I, I, P, I, P],
     "dp_act_fwd": [P, L, I, P, P],

@@ -850,6 +850,60 @@ __global__ void __launch_bounds__(256) add_kernel(const float* a, const float* b
   if (y16) y16[i] = __float2half_rn(v);
 }
 
+
+// ------------------------------------------------------------------ conv weight packing for the tensor-core kernels
+// fp32 [Co][Ci][k][k][k] (optionally read transposed + flipped: the dgrad weights) -> the fp16 operand layouts of
+// conv_tc.cu ([kd][chunk][kh][kw][2][Co][8]) and conv_stack.cu ([rot][chunk][kh][kw][2][slot][Co][8], slot s of
+// rotation r holding depth tap k-1-j, j = (s-r) mod (k+1), zeros for j == k).  One thread per output element.
+struct PackParams {
+  const float* w; int Co, Ci, k; long long s_co, s_ci; int flip;
+  int16_t chunk_ci0[192]; uint8_t chunk_nci[192]; int n_chunks;
+  int stacked; __half* out; long long total;
+};
+__global__ void __launch_bounds__(256) pack_conv_weight_kernel(const PackParams p) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= p.total) return;
+  const int k = p.k;
+  long long r = i;
+  const int e = static_cast<int>(r % 8); r /= 8;
+  const int co = static_cast<int>(r % p.Co); r /= p.Co;
+  int kd;
+  bool zero = false;
+  int khalf, kw, kh, chunk;
+  if (p.stacked) {
+    const int G = k + 1;
+    const int slot = static_cast<int>(r % G); r /= G;
+    khalf = static_cast<int>(r % 2); r /= 2;
+    kw = static_cast<int>(r % k); r /= k;
+    kh = static_cast<int>(r % k); r /= k;
+    chunk = static_cast<int>(r % p.n_chunks); r /= p.n_chunks;
+    const int rot = static_cast<int>(r);
+    const int j = (slot - rot + G) % G;
+    zero = j == k;
+    kd = k - 1 - j;
+  } else {
+    khalf = static_cast<int>(r % 2); r /= 2;
+    kw = static_cast<int>(r % k); r /= k;
+    kh = static_cast<int>(r % k); r /= k;
+    chunk = static_cast<int>(r % p.n_chunks); r /= p.n_chunks;
+    kd = static_cast<int>(r);
+  }
+  const int cl = khalf * 8 + e;
+  float v = 0.f;
+  if (!zero && cl < p.chunk_nci[chunk]) {
+    const int ci = p.chunk_ci0[chunk] + cl;
+    const int a = p.flip ? k - 1 - kd : kd, b = p.flip ? k - 1 - kh : kh, c = p.flip ? k - 1 - kw : kw;
+    v = p.w[co * p.s_co + ci * p.s_ci + (static_cast<long long>(a) * k + b) * k + c];
+  }
+  p.out[i] = __float2half_rn(v);
+}
+
+// dst = fp16(src) (optionally transposed [R][C] -> [C][R]) for the GEMM weight operands
+__global__ void __launch_bounds__(256) cast_f16_kernel(const float* src, long long n, __half* dst) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i < n) dst[i] = __float2half_rn(src[i]);
+}
+
 static inline unsigned nblk(long long n, int threads) { return static_cast<unsigned>((n + threads - 1) / threads); }
 
 }  // namespace dp
@@ -1067,4 +1121,28 @@ extern "C" int dp_colsum(const float* a, int rows, long long cols, double* out, 
 extern "C" int dp_add(const float* a, const float* b, long long n, float* y_f32, void* y_f16, cudaStream_t stream) {
   add_kernel<<<nblk(n, 256), 256, 0, stream>>>(a, b, n, y_f32, static_cast<__half*>(y_f16));
   return check_cuda(cudaGetLastError(), "add");
+}
+
+extern "C" int dp_pack_conv_weight(const float* w, int cout, int cin, int k, int transpose_flip, const int* chunk_ci0,
+                                   const int* chunk_nci, int n_chunks, int stacked, void* out, cudaStream_t stream) {
+  DP_REQUIRE(n_chunks >= 1 && n_chunks <= 192, "pack_conv_weight: 1..192 chunks");
+  PackParams p{};
+  p.w = w; p.Co = cout; p.Ci = cin; p.k = k; p.flip = transpose_flip;
+  const long long taps = static_cast<long long>(k) * k * k;
+  // logical (cout, cin) index into the stored tensor: [cout][cin][taps], or [cin][cout][taps] read transposed
+  p.s_co = transpose_flip ? taps : taps * cin;
+  p.s_ci = transpose_flip ? taps * cout : taps;
+  for (int i = 0; i < n_chunks; ++i) {
+    p.chunk_ci0[i] = static_cast<int16_t>(chunk_ci0[i]);
+    p.chunk_nci[i] = static_cast<uint8_t>(chunk_nci[i]);
+  }
+  p.n_chunks = n_chunks; p.stacked = stacked; p.out = static_cast<__half*>(out);
+  p.total = static_cast<long long>(stacked ? (k + 1) * (k + 1) : k) * n_chunks * k * k * 2 * cout * 8;
+  pack_conv_weight_kernel<<<nblk(p.total, 256), 256, 0, stream>>>(p);
+  return check_cuda(cudaGetLastError(), "pack_conv_weight");
+}
+
+extern "C" int dp_cast_f16(const float* src, long long n, void* dst, cudaStream_t stream) {
+  cast_f16_kernel<<<nblk(n, 256), 256, 0, stream>>>(src, n, static_cast<__half*>(dst));
+  return check_cuda(cudaGetLastError(), "cast_f16");
 }

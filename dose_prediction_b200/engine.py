@@ -92,6 +92,18 @@ class Tokens:
         self.t, self.grid = t, grid
 
 
+class LiveWeight:
+    """a conv weight parameter that changes between replays (training): calling it gives the tensor the conv
+    should see now (the parameter, or its transposed + flipped view for the data-gradient conv)."""
+
+    def __init__(self, param, transpose_flip=False):
+        self.param, self.transpose_flip = param, transpose_flip
+
+    def __call__(self):
+        w = self.param.detach()
+        return w.flip(2, 3, 4).transpose(0, 1) if self.transpose_flip else w
+
+
 class Plan:
     def __init__(self, device):
         self.device = torch.device(device)
@@ -112,6 +124,7 @@ class Plan:
         self._pending_flops = 0.0
         self.training = False    # training plans re-derive packed weights from the live parameters every step
         self.refresh = []        # (packed tensor, function returning its new value)
+        self.refresh_launches = []   # (C entry point name, args): device-side re-packing of live parameters
 
     # ------------------------------------------------------------------ memory
     def zeros(self, shape, dtype):
@@ -188,9 +201,24 @@ class Plan:
         return t
 
     def refresh_weights(self):
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        for name, args in self.refresh_launches:
+            rc = getattr(self.lib, name)(*args, s)
+            if rc:
+                _lib.check(rc, name)
         with torch.no_grad():
             for t, fn in self.refresh:
                 t.copy_(fn())
+
+    def derived_f16(self, param, transpose=False):
+        """fp16 copy of a live fp32 parameter ([out,in], or its transpose), refreshed on the device every step."""
+        if transpose or not self.training:
+            return self.derived(lambda: (param.detach().to(self.device).t() if transpose else param.detach().to(self.device)).half())
+        src = param.detach()
+        t = src.half().contiguous()
+        self.keep.append(t)
+        self.refresh_launches.append(("dp_cast_f16", (src.data_ptr(), src.numel(), t.data_ptr())))
+        return t
 
     def run(self):
         s = torch.cuda.current_stream(self.device).cuda_stream
@@ -350,7 +378,19 @@ class Plan:
             return W
         self.keep.append(W)
         if self.training:
-            self.refresh.append((W, lambda: self.pack_conv_tc(w_src, parts, mode, stacked, _values_only=True)))
+            if isinstance(w_src, LiveWeight) and mode == "p1" and w_src.param.is_cuda and w_src.param.dtype == torch.float32:
+                ci0, nci, base = [], [], 0
+                for a in parts:
+                    for j in range(ceil_div(a.C, 16)):
+                        ci0.append(base + 16 * j)
+                        nci.append(min(16, a.C - 16 * j))
+                    base += a.C
+                arrs = (_lib.int_array(ci0), _lib.int_array(nci))
+                self.keep.append(arrs)
+                self.refresh_launches.append(("dp_pack_conv_weight", (w_src.param.data_ptr(), Co, Ci, k, int(w_src.transpose_flip),
+                                                                      *arrs, nch, int(stacked), W.data_ptr())))
+            else:
+                self.refresh.append((W, lambda: self.pack_conv_tc(w_src, parts, mode, stacked, _values_only=True)))
         assert max(chunks) < 256
         arr = (ctypes.c_uint8 * nch)(*chunks)
         self.keep.append(arr)

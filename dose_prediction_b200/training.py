@@ -25,7 +25,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .engine import ACT_ID, Act, Plan, Raw, Tokens, blocks16, ceil_div
+from .engine import ACT_ID, Act, LiveWeight, Plan, Raw, Tokens, blocks16, ceil_div
 from . import networks as nw
 
 ARENA_DOUBLES = 1 << 22
@@ -108,7 +108,7 @@ class TrainPlan(Plan):
         Co, Ci = w.shape[0], w.shape[1]
         raw = self.get_raw(N, Co, dims)
         shift = conv.bias if conv.bias is not None else self.zeros((Co,), torch.float32)
-        self.conv_tc(parts, lambda: w, k, dil, "p1", self.ones(Co), shift.detach(), False, out_raw=raw)
+        self.conv_tc(parts, LiveWeight(w), k, dil, "p1", self.ones(Co), shift.detach(), False, out_raw=raw)
 
         def bwd():
             g16 = self.raw_grad.pop(raw.t.data_ptr())
@@ -116,7 +116,7 @@ class TrainPlan(Plan):
             if need_dgrad:
                 assert Ci % 16 == 0
                 graw = self.new_graw(N, Ci, dims)
-                self.conv_tc([g16], lambda: w.detach().flip(2, 3, 4).transpose(0, 1), k, dil, "p1", self.ones(Ci),
+                self.conv_tc([g16], LiveWeight(w, transpose_flip=True), k, dil, "p1", self.ones(Ci),
                              self.zeros((Ci,), torch.float32), False, out_raw=graw)
                 off = 0
                 for a in parts:
@@ -321,7 +321,7 @@ class TrainPlan(Plan):
             self.colsum(dy32, M, out_f, lin.bias)
         if not want_dx:
             return None
-        wT = self.derived(lambda: w.detach().t().contiguous().half())          # [in, out]
+        wT = self.derived_f16(w, transpose=True)          # [in, out]
         if dx_f16:
             dx = self.zeros((M, in_f), torch.float16)
             self.gemm(dy16, wT, M, in_f, out_f, out_f16=dx)
@@ -377,7 +377,7 @@ class TrainPlan(Plan):
             ln1 = f16(M, hidden)
             P.layernorm(x, blk.norm1.weight.detach(), blk.norm1.bias.detach(), M, hidden, out_f16=ln1)
             q, k, vt = f16(N * heads, T, hd), f16(N * heads, T, hd), f16(N * heads, hd, Tp)
-            wqkv = P.derived(lambda blk=blk: blk.attn.qkv.weight.detach().half())
+            wqkv = P.derived_f16(blk.attn.qkv.weight)
             P.gemm(ln1, wqkv, M, 3 * hidden, hidden, qkv=(heads, hd, T, q, k, vt, hd ** -0.5))
             P.gemm(q, k, T, T, hd, batch=N * heads, a_batch_rows=T, b_batch_rows=T, c_batch_stride=T * T, ldc=T, out_f32=scores)
             probs = f16(N * heads, T, Tp)
@@ -386,12 +386,12 @@ class TrainPlan(Plan):
             P.gemm(probs, vt, T, hd, Tp, batch=N * heads, a_batch_rows=T, b_batch_rows=hd, c_batch_stride=T * hidden,
                    c_batch_period=heads, c_batch_stride2=hd, ldc=hidden, out_f16=o)
             xm = P.zeros((M, hidden), torch.float32)
-            wo = P.derived(lambda blk=blk: blk.attn.out_proj.weight.detach().half())
+            wo = P.derived_f16(blk.attn.out_proj.weight)
             P.gemm(o, wo, M, hidden, hidden, bias=blk.attn.out_proj.bias.detach(), resid=x, out_f32=xm)
             ln2 = f16(M, hidden)
             P.layernorm(xm, blk.norm2.weight.detach(), blk.norm2.bias.detach(), M, hidden, out_f16=ln2)
             u = P.zeros((M, vit.mlp_dim), torch.float32)
-            w1 = P.derived(lambda blk=blk: blk.mlp.linear1.weight.detach().half())
+            w1 = P.derived_f16(blk.mlp.linear1.weight)
             P.gemm(ln2, w1, M, vit.mlp_dim, hidden, bias=blk.mlp.linear1.bias.detach(), out_f32=u)
             h = f16(M, vit.mlp_dim)
             P.add("dp_act_fwd", u.data_ptr(), M * vit.mlp_dim, ACT_ID["gelu"], h.data_ptr())
@@ -400,7 +400,7 @@ class TrainPlan(Plan):
             if i in taps:
                 tap = f16(N, T, hidden)
                 hs[i] = Tokens(tap, grid)
-            w2 = P.derived(lambda blk=blk: blk.mlp.linear2.weight.detach().half())
+            w2 = P.derived_f16(blk.mlp.linear2.weight)
             P.gemm(h, w2, M, hidden, vit.mlp_dim, bias=blk.mlp.linear2.bias.detach(), resid=xm, out_f32=xo, out_f16=tap)
             saved.append(dict(x_in=x, ln1=ln1, q=q, k=k, vt=vt, probs=probs, o=o, xm=xm, ln2=ln2, u=u, h=h, tap=tap))
             x = xo

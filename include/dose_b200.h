@@ -260,6 +260,14 @@ int dp_adamw(float* p, const float* g, float* m, float* v, long long n, float lr
              float weight_decay, int step, float inv_scale, const int* found_inf, cudaStream_t stream);
 int dp_grad_check(const float* g, long long n, int* found_inf, cudaStream_t stream);
 
+/* Per-step re-packing of the live fp32 parameters into the kernels' fp16 operand layouts (what the inference
+ * plans do once on the host side): conv weights [cout][cin][k][k][k] -> dp_conv3d_tc / dp_conv3d_stack layout for
+ * 16-channel chunks holding logical input channels chunk_ci0[] .. +chunk_nci[]; transpose_flip = 1 reads the
+ * stored tensor as the dgrad weights W'[ci][co][k-1-kd][k-1-kh][k-1-kw] (cout/cin are the packed conv's dims). */
+int dp_pack_conv_weight(const float* w, int cout, int cin, int k, int transpose_flip, const int* chunk_ci0,
+                        const int* chunk_nci, int n_chunks, int stacked, void* out, cudaStream_t stream);
+int dp_cast_f16(const float* src, long long n, void* dst, cudaStream_t stream);
+
 /* Token-side backward pieces of monai ViT (nn.LayerNorm, softmax, GELU backward; layout shuffles that feed
  * the dgrad / wgrad GEMMs of dp_gemm_tc, which wants both operands K-major).                             */
 int dp_layernorm_bwd(const float* x, const float* gamma, const float* dy, const float* add, int rows, int cols,

@@ -199,6 +199,10 @@ def test_conv_wgrad_and_dgrad_match_autograd(cin, cout, k, dil, dims, tc, monkey
     g16 = _act_of(P, g)
     P.raw_grad[raw.t.data_ptr()] = g16
     P.tape[-1]()
+    with torch.no_grad():
+        conv.weight.mul_(1.5)               # the parameters changed since the plan was built ...
+    assert len(P.refresh_launches) == (2 if need else 1) and not P.refresh
+    P.refresh_weights()                     # ... and are re-packed on the device (dp_pack_conv_weight)
     P.run()
     _finish(P)
     xd = x.half().double().cpu().requires_grad_(True)
