@@ -153,6 +153,127 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def run_train(args):
+    """--workload train: BASELINE.json configs[3], the DOSE-PYFER training step (forward + GenLoss + backward through
+    net_B + AdamW), batch 2 per GPU, data-parallel with one NCCL all-reduce of the flat gradient buffer."""
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__
+    from dose_prediction_b200 import synth
+    from dose_prediction_b200.training import DoseTrainer
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    B, S = (args.batch if args.batch_given else 2), args.size
+    metric, unit = "dose_pyfer_train_samples_per_sec_128cubed", "samples/s"
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        from oracle import torch_ref
+        torch.set_num_threads(os.cpu_count() or 1)
+        size = min(S, 64)
+        _, dose = build_models(size)
+        sd = dose.state_dict()
+        vol = synth.make_batch(1, size, seed=1234)
+        t0 = time.perf_counter()
+        for _ in range(max(1, args.steps)):
+            torch_ref.dose_pyfer_train_step(sd, vol["dose_input"], vol["gt"])
+        dt = (time.perf_counter() - t0) / max(1, args.steps)
+        val = (size / S) ** 3 / dt
+        sample = (f"{max(1, args.steps)} training step(s), batch 1, {size}^3, oracle/torch_ref.py autograd fp32; value scaled by "
+                  f"({size}/{S})^3 to {S}^3-equivalent samples/s")
+        print(json.dumps({"impl": "reference", "metric": metric, "value": val, "unit": unit, "n_gpus": args.gpus,
+                          "steps": args.steps, "warmup": 0, "ms_per_step": 1e3 * dt, "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": f"DOSE-PYFER training step, bounded CPU sample ({sample})"},
+                          "cpu_baseline": {"value": val, "unit": unit, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+                          "e2e": {"value": val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+        return
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    __graft_entry__.build()
+    _, dose = build_models(S, dev)
+    dose.train()
+    tr = DoseTrainer(dose, B, S, lr=1e-4, weight_decay=1e-4)
+    vols = synth.make_batch(B, S, seed=1234 + rank * B)
+    x_h, gt_h = vols["dose_input"].pin_memory(), vols["gt"].pin_memory()
+    x_d, gt_d = x_h.to(dev), gt_h.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(args.warmup):
+        tr.step(x_d, gt_d)
+    torch.cuda.synchronize(dev)
+    tr.P.check_device_errors()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms = timed(lambda: tr.step(x_d, gt_d), args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * B * args.steps / (ms / 1e3)
+    losses = []
+
+    def e2e_step():                      # host batch in (pinned), scalar loss out, every step
+        losses.append(float(tr.step(x_h.to(dev, non_blocking=True), gt_h.to(dev, non_blocking=True))))
+    ms_e2e = timed(e2e_step, args.steps)
+    e2e_val = world * B * args.steps / (ms_e2e / 1e3)
+    peaks = _peaks()
+    P = tr.P
+    fam = P.profile_families()
+    total_fam = sum(v["ms"] for v in fam.values()) or 1.0
+    rows = [r for r in P.profile_launches() if r[3] > 0]
+    top = max(rows, key=lambda r: r[2])
+    ach = top[3] / (top[2] / 1e3) / 1e12
+    tc_fams = ("dp_conv3d_wgrad_tc", "dp_conv3d_stack", "dp_conv3d_tc", "dp_gemm_tc")
+    fam_roof = [{"kernel": k, "achieved": P.flops.get(k, 0.0) / (fam[k]["ms"] / 1e3) / 1e12, "unit": "TFLOP/s",
+                 "frac": P.flops.get(k, 0.0) / (fam[k]["ms"] / 1e3) / 1e12 / peaks["tflops"], "ms_per_step": fam[k]["ms"],
+                 "launches_per_step": fam[k]["launches"]} for k in tc_fams if k in fam]
+    if rank == 0:
+        line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f16", "data": "synthetic",
+                "config": {"workload": f"DOSE-PYFER training step (train-mode forward, GenLoss, backward through net_B, AdamW), "
+                                       f"{S}^3, batch {B} per GPU (BASELINE.json configs[3])", "batch_per_gpu": B, "size": S,
+                           "parallelism": f"data-parallel x{world}, one NCCL all-reduce of the flat fp32 gradient buffer "
+                                          f"({tr.total} elements)" if world > 1 else "single GPU",
+                           "loss_scale": tr.loss_scale, "trainable_parameters": tr.total,
+                           "l2": f"no flush: per-step working set {P.bytes_alloc / 2**30:.1f} GiB >> 126 MB L2"},
+                "e2e": {"value": e2e_val, "unit": unit, "ms_per_step": ms_e2e / args.steps,
+                        "h2d_bytes_per_step": B * 11 * S ** 3 * 4, "d2h_bytes_per_step": 4, "last_loss": losses[-1]},
+                "gpu_launches": (P.launches + 2) * args.steps, "launches_per_step": P.launches + 2,
+                "roofline": {"kernel": top[0], "launch": top[1], "bound": "tensor", "achieved": ach, "peak": peaks["tflops"],
+                             "unit": "TFLOP/s", "frac": ach / peaks["tflops"], "traffic": None, "peak_source": peaks["source"],
+                             "avg_launch_ms": top[2], "algorithmic_flops_per_launch": top[3], "share_of_step": top[2] / total_fam},
+                "roofline_families": fam_roof,
+                "kernel_ms_per_step": {k: round(v["ms"], 3) for k, v in sorted(fam.items())},
+                "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -163,10 +284,15 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--workload", default="cascade", choices=["cascade", "train"],
+                    help="cascade (default, the headline metric) or train (BASELINE.json configs[3]: DOSE-PYFER training step)")
     ap.add_argument("--sw-roi", type=int, default=0,
                     help="run the seg stage as the reference does: sliding 96^3-style windows of this ROI (0 = direct)")
     args = ap.parse_args()
+    args.batch_given = any(a == "--batch" or a.startswith("--batch=") for a in sys.argv[1:])
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+    if args.workload == "train":
+        return run_train(args)
     if args.impl == "reference":
         return run_reference(args)
 

@@ -573,6 +573,19 @@ def _t_main_subset(P, net, parts):
     return [P.t_head(d, conv[0]) for d, conv in zip(decs[::-1], net.dose_convertors)]
 
 
+def allreduce_mean_(flat, group=None):
+    """Data-parallel gradient exchange: ONE all-reduce (sum) of the flat gradient buffer, then / world size — what
+    Lightning's DDP strategy does for the reference (train_light_pyfer.py trainer setup).  No-op without a group."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return flat
+    world = dist.get_world_size(group)
+    if world > 1:
+        dist.all_reduce(flat, group=group)
+        flat.div_(world)
+    return flat
+
+
 class DoseTrainer:
     """One DOSE-PYFER training step per call: `loss = trainer.step(input_[B,9,S,S,S], gt[B,2,S,S,S])`.
 
@@ -663,10 +676,7 @@ class DoseTrainer:
         self.fwd_bwd_steps = len(P.steps)
 
     def _allreduce(self):
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
-            dist.all_reduce(self.flat_g, group=self.group)
-            self.flat_g.div_(dist.get_world_size(self.group))
+        allreduce_mean_(self.flat_g, self.group)
 
     def forward_backward(self, x, gt):
         """forward + loss + backward; gradients (times loss_scale) are left in the flat gradient buffer."""
