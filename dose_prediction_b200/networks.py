@@ -697,8 +697,8 @@ class _PlanCache:
 
 def _check_input(module, x, channels):
     if module.training:
-        raise RuntimeError("dose_prediction_b200: training-mode forward (batch-statistics BatchNorm + backward) is "
-                           "not built yet (SURVEY 8 row a8); call .eval() for the inference path")
+        raise RuntimeError("dose_prediction_b200: module.forward is the inference path (call .eval()); the training step "
+                           "(train-mode forward + loss + backward + AdamW) runs through training.DoseTrainer.step()")
     if not (x.is_cuda and x.dim() == 5):
         raise RuntimeError("expected a CUDA tensor [B,C,D,H,W]; dose_prediction_b200 has no CPU fallback")
     if x.shape[1] != channels:
