@@ -49,6 +49,8 @@ _SIGNATURES = {
     "dp_head_bwd": [P, P, P, I, I, I, P, I, L, P, I, I, P, P, P],
     "dp_masked_l1": [P, P, I, I, I, P, I, F, P, P],
     "dp_genloss_finalize": [P, I, F, F, P, P],
+    "dp_dice_ce": [P, I, P, I, I, L, P, I, F, P, I, P],
+    "dp_dice_ce_finalize": [P, I, I, L, P, P],
     "dp_adamw": [P, P, P, P, L, F, F, F, F, F, I, F, P, P],
     "dp_grad_check": [P, L, P, P],
     "dp_pack_conv_weight": [P, I, I, I, I, P, P, I, I, P, P],

@@ -904,6 +904,85 @@ __global__ void __launch_bounds__(256) cast_f16_kernel(const float* src, long lo
   if (i < n) dst[i] = __float2half_rn(src[i]);
 }
 
+
+// ------------------------------------------------------------------ DiceCELoss (monai 0.7.0, to_onehot_y, softmax)
+// logits: c8 fp32, C <= 8 classes in channel block 0; label: fp32 class index per voxel [N][vox].
+// acc: double[N][8][3] = {sum p*t, sum t, sum p} followed by one double = sum of -log p[label].
+// phase 0 accumulates acc; phase 1 writes coef * dLoss/dlogit as fp16 c8 (block 0), where
+// Loss = mean_{n,c} (1 - (2 I + eps) / (G + P + eps)) + mean_voxels CE.
+__global__ void __launch_bounds__(256) dice_ce_kernel(const float* logits, int cb_total, const float* label, int N, int C,
+                                                      long long vox, double* acc, int phase, float coef, __half* g16,
+                                                      int g_cb_total) {
+  const int n = blockIdx.y;
+  const long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const bool valid = v < vox;
+  float p[8], t[8];
+  float ce = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { p[j] = 0.f; t[j] = 0.f; }
+  if (valid) {
+    float z[8];
+    t_load8f(logits, (static_cast<size_t>(n) * cb_total * vox + v) * 8, z);
+    const int lab = static_cast<int>(label[static_cast<size_t>(n) * vox + v]);
+    float m = -3.0e38f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) if (j < C) m = fmaxf(m, z[j]);
+    float ssum = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { p[j] = j < C ? __expf(z[j] - m) : 0.f; ssum += p[j]; }
+    const float inv = 1.f / ssum;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { p[j] *= inv; t[j] = (j == lab) ? 1.f : 0.f; }
+    float zl = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) if (j == lab) zl = z[j];
+    ce = -(zl - m - __logf(ssum));
+  }
+  if (phase == 0) {
+    float a[3][8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { a[0][j] = p[j] * t[j]; a[1][j] = t[j]; a[2][j] = p[j]; }
+    block_reduce64<3>(a, acc, static_cast<size_t>(n) * 8, 3, 0, C);
+    __shared__ float red[8];
+    const float s = warp_sum(ce);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double tsum = 0.0;
+      for (int w = 0; w < 8; ++w) tsum += static_cast<double>(red[w]);
+      atomicAdd(&acc[static_cast<size_t>(N) * 24], tsum);
+    }
+    return;
+  }
+  if (!valid) return;
+  float a[8], dot = 0.f;
+  const float w_dice = 1.f / (static_cast<float>(N) * C);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    a[j] = 0.f;
+    if (j < C) {
+      const double* q = acc + (static_cast<size_t>(n) * 8 + j) * 3;
+      const float I = static_cast<float>(q[0]), D = static_cast<float>(q[1] + q[2]) + 1e-5f;
+      a[j] = -w_dice * (2.f * t[j] * D - (2.f * I + 1e-5f)) / (D * D);
+      dot = fmaf(a[j], p[j], dot);
+    }
+  }
+  const float w_ce = 1.f / (static_cast<float>(N) * static_cast<float>(vox));
+  float g[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) g[j] = j < C ? coef * (p[j] * (a[j] - dot) + w_ce * (p[j] - t[j])) : 0.f;
+  t_store8h(g16, (static_cast<size_t>(n) * g_cb_total * vox + v) * 8, g);
+}
+__global__ void dice_ce_finalize_kernel(const double* acc, int N, int C, long long vox, float* loss) {
+  double dice = 0.0;
+  for (int n = 0; n < N; ++n)
+    for (int c = 0; c < C; ++c) {
+      const double* q = acc + (static_cast<size_t>(n) * 8 + c) * 3;
+      dice += 1.0 - (2.0 * q[0] + 1e-5) / (q[1] + q[2] + 1e-5);
+    }
+  *loss = static_cast<float>(dice / (static_cast<double>(N) * C) + acc[static_cast<size_t>(N) * 24] / (static_cast<double>(N) * vox));
+}
+
 static inline unsigned nblk(long long n, int threads) { return static_cast<unsigned>((n + threads - 1) / threads); }
 
 }  // namespace dp
@@ -1145,4 +1224,19 @@ extern "C" int dp_pack_conv_weight(const float* w, int cout, int cin, int k, int
 extern "C" int dp_cast_f16(const float* src, long long n, void* dst, cudaStream_t stream) {
   cast_f16_kernel<<<nblk(n, 256), 256, 0, stream>>>(src, n, static_cast<__half*>(dst));
   return check_cuda(cudaGetLastError(), "cast_f16");
+}
+
+extern "C" int dp_dice_ce(const float* logits_c8, int cb_total, const float* label, int N, int C, long long vox, double* acc,
+                          int phase, float coef, void* g_f16, int g_cb_total, cudaStream_t stream) {
+  DP_REQUIRE(C >= 2 && C <= 8, "dice_ce: 2..8 classes (got %d)", C);
+  DP_REQUIRE(phase == 0 || g_f16 != nullptr, "dice_ce: backward needs the gradient tensor");
+  dim3 grid(nblk(vox, 256), static_cast<unsigned>(N));
+  dice_ce_kernel<<<grid, 256, 0, stream>>>(logits_c8, cb_total, label, N, C, vox, acc, phase, coef, static_cast<__half*>(g_f16),
+                                          g_cb_total);
+  return check_cuda(cudaGetLastError(), "dice_ce");
+}
+
+extern "C" int dp_dice_ce_finalize(const double* acc, int N, int C, long long vox, float* loss, cudaStream_t stream) {
+  dice_ce_finalize_kernel<<<1, 1, 0, stream>>>(acc, N, C, vox, loss);
+  return check_cuda(cudaGetLastError(), "dice_ce_finalize");
 }

@@ -56,3 +56,10 @@ def make_volume(size: int = 128, seed: int = 1234):
 def make_batch(batch: int, size: int = 128, seed: int = 1234):
     vols = [make_volume(size, seed + i) for i in range(batch)]
     return {k: torch.cat([v[k] for v in vols]) for k in vols[0]}
+
+
+def oar_labels(oars):
+    """[B,7,...] binary OAR masks -> [B,1,...] fp32 class-index map (0 = background, k+1 = OAR k), the 'OARs' label
+    volume the seg training step consumes (OARSegmentation/train_light_transeg.py:185)."""
+    idx = torch.arange(1, oars.shape[1] + 1, dtype=oars.dtype).view(1, -1, 1, 1, 1)
+    return (oars * idx).amax(dim=1, keepdim=True).contiguous()

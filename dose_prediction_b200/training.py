@@ -546,31 +546,37 @@ def _t_conv_3_1(P, blk, parts, out):
     P.t_norm(raw, out, act=act)
 
 
-def _t_main_subset(P, net, parts):
-    """MainSubsetModel.forward (dose_pyfer.py:311-319) in train mode; returns the four planar dose outputs."""
-    enc, dec = net.encoder, net.decoder
-    vit = enc.vit
+def _t_unetr(P, vit, enc_blocks, dec_blocks, parts, taps):
+    """UNETR-shaped body shared by MainSubsetModel.forward (dose_pyfer.py:311-319) and oar_transeg Model.forward
+    (oar_transeg.py:171-185) in train mode; returns the decoder outputs [full res, /2, /4, /8]."""
     N, dims = parts[0].N, parts[0].dims
-    i = enc.num_layers // 4
-    taps = (i, 2 * i, 3 * i)
-    fs = enc.skip1.layer.conv1.conv.weight.shape[0]
+    fs = enc_blocks[0].layer.conv1.conv.weight.shape[0]
     z, hs = P.t_vit(vit, parts, N, dims, taps)
     sizes = [dims, tuple(d // 2 for d in dims), tuple(d // 4 for d in dims), tuple(d // 8 for d in dims)]
     cats = [P.new_concat(N, [fs << l, fs << l], sizes[l]) for l in range(4)]
-    _t_res_block(P, enc.skip1.layer, parts, cats[0][1], need_dgrad=False)
-    _t_pr_up(P, enc.skip2, hs[taps[0]], cats[1][1])
-    _t_pr_up(P, enc.skip3, hs[taps[1]], cats[2][1])
-    _t_pr_up(P, enc.skip4, hs[taps[2]], cats[3][1])
+    _t_res_block(P, enc_blocks[0].layer, parts, cats[0][1], need_dgrad=False)
+    _t_pr_up(P, enc_blocks[1], hs[taps[0]], cats[1][1])
+    _t_pr_up(P, enc_blocks[2], hs[taps[1]], cats[2][1])
+    _t_pr_up(P, enc_blocks[3], hs[taps[2]], cats[3][1])
     decs, inp = [], z
-    for lvl, blk in zip((3, 2, 1, 0), (dec.decoder4, dec.decoder3, dec.decoder2, dec.decoder1)):
-        if not isinstance(blk.conv_block.cov_, nw.conv_3_1):
+    for lvl, blk in zip((3, 2, 1, 0), dec_blocks):
+        if not (hasattr(blk, "conv_block") and isinstance(getattr(blk.conv_block, "cov_", None), nw.conv_3_1)):
             raise RuntimeError("training path covers the multi-scale decoder (mode_multi_dec=True, multiS_conv=True)")
         out = P.new_act(N, fs << lvl, sizes[lvl])
         P.t_deconv(inp, blk.transp_conv.conv.weight, cats[lvl][0])
         _t_conv_3_1(P, blk.conv_block.cov_, cats[lvl], out)
         decs.append(out)
         inp = out
-    return [P.t_head(d, conv[0]) for d, conv in zip(decs[::-1], net.dose_convertors)]
+    return decs[::-1]
+
+
+def _t_main_subset(P, net, parts):
+    """MainSubsetModel.forward (dose_pyfer.py:311-319) in train mode; returns the four planar dose outputs."""
+    enc, dec = net.encoder, net.decoder
+    i = enc.num_layers // 4
+    decs = _t_unetr(P, enc.vit, (enc.skip1, enc.skip2, enc.skip3, enc.skip4),
+                    (dec.decoder4, dec.decoder3, dec.decoder2, dec.decoder1), parts, (i, 2 * i, 3 * i))
+    return [P.t_head(d, conv[0]) for d, conv in zip(decs, net.dose_convertors)]
 
 
 def allreduce_mean_(flat, group=None):
@@ -586,30 +592,21 @@ def allreduce_mean_(flat, group=None):
     return flat
 
 
-class DoseTrainer:
-    """One DOSE-PYFER training step per call: `loss = trainer.step(input_[B,9,S,S,S], gt[B,2,S,S,S])`.
+class _Trainer:
+    """Shared host side of the training steps: re-homes the trainable parameters into one flat fp32 buffer
+    (+ flat gradient / Adam moment buffers), builds the static launch list once, replays it per step."""
 
-    model: dose_prediction_b200.networks.Model on a CUDA device (parameters are re-homed into one flat fp32
-    buffer; state_dict() keeps working).  freeze=True as in the reference (net_A / conv_out_A get no gradient)."""
-
-    def __init__(self, model, batch, size, lr=1e-4, weight_decay=1e-4, delta1=10.0, delta2=8.0, freeze=True,
-                 betas=(0.9, 0.999), eps=1e-8, loss_scale=4096.0, process_group=None, probe=None):
-        """probe (tests only): list of four tensors R_i shaped like the dose outputs; the backward pass then starts
-        from dL/dpred_i = R_i (a linear loss sum <pred_i, R_i>) instead of the GenLoss gradient, whose sign()
-        makes gradient parity ill-conditioned."""
-        if not freeze:
-            raise RuntimeError("training path: freeze=True only (net_A frozen, train_light_pyfer.py:85-88)")
+    def _setup(self, model, trainable, lr, weight_decay, betas, eps, loss_scale, process_group):
         dev = next(model.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("dose_prediction_b200 trains on CUDA devices only (no CPU fallback)")
-        self.model, self.device, self.batch, self.size = model, dev, batch, size
+        self.model, self.device = model, dev
         self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
-        self.delta1, self.delta2, self.loss_scale = delta1, delta2, float(loss_scale)
+        self.loss_scale = float(loss_scale)
         self.group = process_group
-        self.probe = probe
         self.step_count = 0
         for n, p in model.named_parameters():
-            p.requires_grad_(not (n.startswith("net_A") or n.startswith("conv_out_A")))
+            p.requires_grad_(bool(trainable(n)))
         self.params = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
         total = sum((p.numel() + 3) // 4 * 4 for _, p in self.params)
         self.flat_p = torch.zeros(total, device=dev)
@@ -631,6 +628,55 @@ class DoseTrainer:
                 off += (k + 3) // 4 * 4
         self.total = total
         self.P = P
+        self.loss = P.zeros((1,), torch.float32)
+
+    def _finish_emit(self):
+        P = self.P
+        for bwd in reversed(P.tape):
+            bwd()
+        for acc64, g, n in P.finalizers:
+            P.add("dp_grad_finalize", acc64.data_ptr(), g.data_ptr(), n, 1.0)
+
+    def _run(self):
+        P = self.P
+        P.refresh_weights()
+        P.run()
+        allreduce_mean_(self.flat_g, self.group)
+        return self.loss
+
+    def _optimizer_step(self):
+        self.step_count += 1
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        lib = self.P.lib
+        self.found_inf.zero_()
+        _lib.check(lib.dp_grad_check(self.flat_g.data_ptr(), self.total, self.found_inf.data_ptr(), s), "dp_grad_check")
+        _lib.check(lib.dp_adamw(self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.flat_m.data_ptr(), self.flat_v.data_ptr(),
+                                self.total, self.lr, self.betas[0], self.betas[1], self.eps, self.wd, self.step_count,
+                                1.0 / self.loss_scale, self.found_inf.data_ptr(), s), "dp_adamw")
+
+    def grads(self):
+        """{parameter name: unscaled fp32 gradient} (copies; for tests / inspection)."""
+        return {n: (self.flat_g[o:o + k] / self.loss_scale).view(p.shape).clone()
+                for (n, p), (o, k) in ((np_, self.offsets[np_[0]]) for np_ in self.params)}
+
+
+class DoseTrainer(_Trainer):
+    """One DOSE-PYFER training step per call: `loss = trainer.step(input_[B,9,S,S,S], gt[B,2,S,S,S])`.
+
+    model: dose_prediction_b200.networks.Model on a CUDA device (parameters are re-homed into one flat fp32
+    buffer; state_dict() keeps working).  freeze=True as in the reference (net_A / conv_out_A get no gradient)."""
+
+    def __init__(self, model, batch, size, lr=1e-4, weight_decay=1e-4, delta1=10.0, delta2=8.0, freeze=True,
+                 betas=(0.9, 0.999), eps=1e-8, loss_scale=4096.0, process_group=None, probe=None):
+        """probe (tests only): list of four tensors R_i shaped like the dose outputs; the backward pass then starts
+        from dL/dpred_i = R_i (a linear loss sum <pred_i, R_i>) instead of the GenLoss gradient, whose sign()
+        makes gradient parity ill-conditioned."""
+        if not freeze:
+            raise RuntimeError("training path: freeze=True only (net_A frozen, train_light_pyfer.py:85-88)")
+        self.batch, self.size = batch, size
+        self.delta1, self.delta2, self.probe = delta1, delta2, probe
+        self._setup(model, lambda n: not (n.startswith("net_A") or n.startswith("conv_out_A")), lr, weight_decay, betas, eps,
+                    loss_scale, process_group)
         self._emit()
 
     def _emit(self):
@@ -653,7 +699,6 @@ class DoseTrainer:
         # ---- GenLoss forward
         acc = P.zeros((2 * len(outs),), torch.float64)
         P.add_zero(acc)
-        self.loss = P.zeros((1,), torch.float32)
         sizes = [o.shape[2] for o in outs]
         for i, o in enumerate(outs):
             P.add("dp_masked_l1", o.data_ptr(), P.gt.data_ptr(), N, S, sizes[i], acc[2 * i:].data_ptr(), 0, 0.0, None)
@@ -669,41 +714,78 @@ class DoseTrainer:
                 P.add("dp_masked_l1", o.data_ptr(), P.gt.data_ptr(), N, S, sizes[i], acc[2 * i:].data_ptr(), 1, float(coef),
                       g.data_ptr())
             P.planar_grad[o.data_ptr()] = g
-        for bwd in reversed(P.tape):
-            bwd()
-        for acc64, g, n in P.finalizers:
-            P.add("dp_grad_finalize", acc64.data_ptr(), g.data_ptr(), n, 1.0)
-        self.fwd_bwd_steps = len(P.steps)
-
-    def _allreduce(self):
-        allreduce_mean_(self.flat_g, self.group)
+        self._finish_emit()
 
     def forward_backward(self, x, gt):
         """forward + loss + backward; gradients (times loss_scale) are left in the flat gradient buffer."""
-        P = self.P
-        P.x_in.copy_(x.to(torch.float32), non_blocking=True)
-        P.gt.copy_(gt.to(torch.float32), non_blocking=True)
-        P.refresh_weights()
-        P.run()
-        self._allreduce()
-        return self.loss
+        self.P.x_in.copy_(x.to(torch.float32), non_blocking=True)
+        self.P.gt.copy_(gt.to(torch.float32), non_blocking=True)
+        return self._run()
 
     def step(self, x, gt):
         loss = self.forward_backward(x, gt)
-        self.step_count += 1
-        s = torch.cuda.current_stream(self.device).cuda_stream
-        lib = self.P.lib
-        self.found_inf.zero_()
-        _lib.check(lib.dp_grad_check(self.flat_g.data_ptr(), self.total, self.found_inf.data_ptr(), s), "dp_grad_check")
-        _lib.check(lib.dp_adamw(self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.flat_m.data_ptr(), self.flat_v.data_ptr(),
-                                self.total, self.lr, self.betas[0], self.betas[1], self.eps, self.wd, self.step_count,
-                                1.0 / self.loss_scale, self.found_inf.data_ptr(), s), "dp_adamw")
+        self._optimizer_step()
         return loss
-
-    def grads(self):
-        """{parameter name: unscaled fp32 gradient} (copies; for tests / inspection)."""
-        return {n: (self.flat_g[o:o + k] / self.loss_scale).view(p.shape).clone() for (n, p), (o, k) in
-                zip(self.params, (self.offsets[n] for n, _ in self.params))}
 
     def outputs(self):
         return [self.out_A.clone(), [o.clone() for o in self.outs]]
+
+
+class SegTrainer(_Trainer):
+    """One OAR-TRANSEG training step per call (`Transeg.training_step` + `configure_optimizers`,
+    OARSegmentation/train_light_transeg.py:184-198): `loss = trainer.step(ct[B,1,S,S,S], label[B,1,S,S,S])` with
+    DiceCELoss(to_onehot_y=True, softmax=True) and AdamW(1e-4, weight_decay 1e-5); every parameter is trained.
+    model: dose_prediction_b200.networks.OARTranseg (the Models/ variant with the multi-scale conv_3_1 decoder)."""
+
+    def __init__(self, model, batch, size, lr=1e-4, weight_decay=1e-5, betas=(0.9, 0.999), eps=1e-8, loss_scale=4096.0,
+                 process_group=None, probe=None):
+        self.batch, self.size, self.probe = batch, size, probe
+        self._setup(model, lambda n: True, lr, weight_decay, betas, eps, loss_scale, process_group)
+        self._emit()
+
+    def _emit(self):
+        P, m = self.P, self.model
+        N, S = self.batch, self.size
+        dims = (S, S, S)
+        vox = S ** 3
+        C = m.out_channels
+        P.x_in = P.zeros((N, m.in_ch) + dims, torch.float32)
+        P.label = P.zeros((N, 1) + dims, torch.float32)
+        x_act = P.new_act(N, m.in_ch, dims)
+        P.add_zero(self.flat_g)
+        P.add_zero(P.arena)
+        P.pack_input(P.x_in, x_act)
+        decs = _t_unetr(P, m.vit, (m.encoder1, m.encoder2, m.encoder3, m.encoder4),
+                        (m.decoder5, m.decoder4, m.decoder3, m.decoder2), [x_act], (3, 6, 9))
+        raw = P.t_pointwise([decs[0]], m.out.conv.conv)          # logits, c8 fp32 (C classes in block 0)
+        self.logits_raw = raw
+        acc = P.zeros((N * 24 + 2,), torch.float64)
+        P.add_zero(acc)
+        P.add("dp_dice_ce", raw.t.data_ptr(), raw.cb_total, P.label.data_ptr(), N, C, vox, acc.data_ptr(), 0, 0.0, None, 0)
+        P.add("dp_dice_ce_finalize", acc.data_ptr(), N, C, vox, self.loss.data_ptr())
+        g16 = P.new_act(N, C, dims)
+        if self.probe is not None:
+            r = (self.probe.to(self.device, torch.float32) * self.loss_scale).contiguous()
+            P.keep.append(r)
+            P.pack_input(r, g16)
+        else:
+            P.add("dp_dice_ce", raw.t.data_ptr(), raw.cb_total, P.label.data_ptr(), N, C, vox, acc.data_ptr(), 1,
+                  self.loss_scale, g16.buf.data_ptr(), g16.cb_total)
+        P.raw_grad[raw.t.data_ptr()] = g16
+        self._finish_emit()
+
+    def forward_backward(self, ct, label):
+        self.P.x_in.copy_(ct.to(torch.float32), non_blocking=True)
+        self.P.label.copy_(label.to(torch.float32), non_blocking=True)
+        return self._run()
+
+    def step(self, ct, label):
+        loss = self.forward_backward(ct, label)
+        self._optimizer_step()
+        return loss
+
+    def logits(self):
+        """[B,C,S,S,S] fp32 logits of the last forward (copy)."""
+        t, C = self.logits_raw.t, self.model.out_channels
+        n, cb, d, h, w, _ = t.shape
+        return t.permute(0, 1, 5, 2, 3, 4).reshape(n, cb * 8, d, h, w)[:, :C].clone()

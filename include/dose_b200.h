@@ -253,6 +253,14 @@ int dp_masked_l1(const float* pred, const float* gt, int N, int S, int s, double
 /* loss = delta1 * acc[0]/acc[1] + delta2 * mean_{i>=1} acc[2i]/acc[2i+1]   (loss.py:96-112) */
 int dp_genloss_finalize(const double* acc, int n_scales, float delta1, float delta2, float* loss, cudaStream_t stream);
 
+/* Seg training loss: monai 0.7.0 DiceCELoss(to_onehot_y=True, softmax=True) as used at
+ * OARSegmentation/train_light_transeg.py:148,186.  logits: c8 fp32 with C <= 8 classes in channel block 0; label:
+ * fp32 class index per voxel.  acc = double[N*24 + 1].  phase 0 accumulates {sum p*t, sum t, sum p} per (n,c) and
+ * the cross-entropy sum; phase 1 writes coef * dLoss/dlogit as fp16 c8.                                         */
+int dp_dice_ce(const float* logits_c8, int cb_total, const float* label, int N, int C, long long vox, double* acc,
+               int phase, float coef, void* g_f16, int g_cb_total, cudaStream_t stream);
+int dp_dice_ce_finalize(const double* acc, int N, int C, long long vox, float* loss, cudaStream_t stream);
+
 /* Fused AdamW over a flat fp32 parameter buffer (configure_optimizers, train_light_pyfer.py:194-197; fp32
  * optimizer state, decoupled weight decay).  inv_scale undoes the static loss scaling; when *found_inf != 0
  * (dp_grad_check) the update is skipped.                                                                */

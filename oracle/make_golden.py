@@ -112,6 +112,24 @@ def main():
     rec["norms"] = np.array(norms, dtype=np.float64)
     np.savez_compressed(os.path.join(OUT, "train32.npz"), **rec)
 
+    # ---- seg training step (train_light_transeg.py:184-198): the reference module in train mode + autograd; the loss is
+    # oracle.torch_ref.dice_ce_loss (monai's DiceCELoss is an un-vendored dependency, restated there)
+    sm = ref_loader.build_seg(32).train()
+    sm.load_state_dict(synth_ckpt.make_state_dict(synth_ckpt.manifest_of(sm), SEG_SEED), strict=True)
+    label = synth.oar_labels(vol["oars"])
+    sloss = torch_ref.dice_ce_loss(sm(vol["ct"]), label)
+    sloss.backward()
+    srec = {"loss": np.float64(sloss.item())}
+    snames, snorms = [], []
+    for n, p_ in sm.named_parameters():
+        g_ = p_.grad if p_.grad is not None else torch.zeros_like(p_)
+        snames.append(n)
+        snorms.append(float(g_.double().norm()))
+        srec["g/" + n] = _np(g_.flatten()[torch_ref.sample_idx(g_.numel())])
+    srec["names"] = np.array(snames)
+    srec["norms"] = np.array(snorms, dtype=np.float64)
+    np.savez_compressed(os.path.join(OUT, "segtrain32.npz"), **srec)
+
     # ---- sliding window (monai restatement; seg net built for 32^3 scanned over a 48^3 CT)
     from monai.inferers import sliding_window_inference
     ct48 = synth.make_volume(48, seed=77)["ct"]

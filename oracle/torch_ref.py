@@ -384,6 +384,51 @@ def dose_pyfer_train_step(sd: SD, x, gt, lr=1e-4, weight_decay=1e-4, delta1=10.0
     return loss.detach(), grads, new, outs
 
 
+def dice_ce_loss(logits, label, smooth=1e-5):
+    """monai==0.7.0 losses.DiceCELoss(to_onehot_y=True, softmax=True) as called at
+    OARSegmentation/train_light_transeg.py:148,186 (un-vendored dependency, restated from its published source):
+    DiceLoss(include_background=True, softmax over channels, reduction over the spatial dims per (n,c),
+    smooth_nr = smooth_dr = 1e-5, mean over (n,c)) + nn.CrossEntropyLoss (mean over voxels); label [B,1,...] holds
+    class indices."""
+    n_cls = logits.shape[1]
+    idx = label[:, 0].long()
+    onehot = F.one_hot(idx, n_cls).permute(0, 4, 1, 2, 3).to(logits.dtype)
+    p = torch.softmax(logits, dim=1)
+    dims = (2, 3, 4)
+    inter = (onehot * p).sum(dims)
+    denom = onehot.sum(dims) + p.sum(dims)
+    dice = (1.0 - (2.0 * inter + smooth) / (denom + smooth)).mean()
+    return dice + F.cross_entropy(logits, idx)
+
+
+def oar_transeg_train_step(sd: SD, x, label, lr=1e-4, weight_decay=1e-5, betas=(0.9, 0.999), eps=1e-8, probe=None, **kw):
+    """Transeg.training_step + configure_optimizers (OARSegmentation/train_light_transeg.py:184-198): train-mode
+    forward (BatchNorm3d batch statistics in conv_block_7), DiceCELoss, autograd, torch.optim.AdamW(1e-4, wd 1e-5).
+    Returns (loss, {name: grad}, {name: updated parameter or running statistic}, logits)."""
+    global BN_TRAIN
+    is_buffer = lambda k: k.endswith("running_mean") or k.endswith("running_var") or k.endswith("num_batches_tracked")
+    leaf = {k: v.detach().clone() for k, v in sd.items()}
+    train_keys = [k for k in leaf if not is_buffer(k) and leaf[k].is_floating_point()]
+    for k in train_keys:
+        leaf[k].requires_grad_(True)
+    BN_TRAIN = {}
+    try:
+        logits = oar_transeg_forward(leaf, x, **kw)
+        loss = dice_ce_loss(logits, label)
+        ((logits * probe).sum() if probe is not None else loss).backward()
+        new_stats = dict(BN_TRAIN)
+    finally:
+        BN_TRAIN = None
+    grads = {k: (leaf[k].grad if leaf[k].grad is not None else torch.zeros_like(leaf[k])) for k in train_keys}
+    params = [leaf[k] for k in train_keys]
+    for p_, k in zip(params, train_keys):
+        p_.grad = grads[k]
+    torch.optim.AdamW(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay).step()
+    new = {k: leaf[k].detach() for k in train_keys}
+    new.update(new_stats)
+    return loss.detach(), grads, new, logits.detach()
+
+
 def sample_idx(numel, k=64):
     """k evenly spaced flat indices (integer arithmetic; used by the training fixtures)."""
     k = min(k, numel)

@@ -97,6 +97,22 @@ def test_train_step_matches_reference_fixture(dose_sd32):
     assert (new[w].flatten()[idx] - torch.from_numpy(g["p/" + w])).abs().max() < 2.5e-4      # lr * O(1) per Adam step
 
 
+def test_seg_train_step_matches_reference_fixture(seg_sd32):
+    """oracle seg train step (train-mode BN, DiceCE, autograd) == the reference module's own autograd."""
+    vol = synth.make_batch(2, 32, seed=1234)
+    g = np.load(os.path.join(GOLDEN, "segtrain32.npz"))
+    loss, grads, _, _ = torch_ref.oar_transeg_train_step(seg_sd32, vol["ct"], synth.oar_labels(vol["oars"]))
+    assert abs(float(loss) - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    names, norms = list(g["names"]), g["norms"]
+    assert sorted(names) == sorted(grads)
+    gmax = norms.max()
+    for n, want in zip(names, norms):
+        assert abs(float(grads[n].double().norm()) - want) <= 2e-3 * want + 1e-6 * gmax, n
+        ref = torch.from_numpy(g["g/" + n])
+        got = grads[n].flatten()[torch_ref.sample_idx(grads[n].numel())]
+        assert (got - ref).abs().max() <= 5e-3 * ref.abs().max() + 1e-6 * gmax, n
+
+
 def test_sliding_window_matches_fixture(seg_sd32):
     ct48 = synth.make_volume(48, seed=77)["ct"]
     g = torch.from_numpy(np.load(os.path.join(GOLDEN, "sliding48.npz"))["logits"])

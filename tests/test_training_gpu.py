@@ -489,3 +489,73 @@ def test_training_reduces_the_loss():
     tr.P.check_device_errors()
     assert all(l == l for l in losses)
     assert losses[-1] < 0.9 * losses[0], losses
+
+
+def test_dice_ce_forward_backward_matches_oracle():
+    from dose_prediction_b200 import _lib, synth
+    from oracle import torch_ref
+    lib = _lib.lib()
+    torch.manual_seed(9)
+    N, C, S = 2, 8, 16
+    vol = synth.make_batch(N, S, seed=21)
+    label = synth.oar_labels(vol["oars"])
+    logits = (torch.randn(N, C, S, S, S) * 2).requires_grad_(True)
+    loss = torch_ref.dice_ce_loss(logits, label)
+    loss.backward()
+    s = torch.cuda.current_stream().cuda_stream
+    zc = _ncdhw_to_c8(logits.detach().to(DEV))
+    lab = label.to(DEV).contiguous()
+    acc = torch.zeros(N * 24 + 2, dtype=torch.float64, device=DEV)
+    out = torch.zeros(1, device=DEV)
+    g16 = torch.zeros(N, 2, S, S, S, 8, dtype=torch.float16, device=DEV)
+    vox = S ** 3
+    _lib.check(lib.dp_dice_ce(zc.data_ptr(), zc.shape[1], lab.data_ptr(), N, C, vox, acc.data_ptr(), 0, 0.0, None, 0, s))
+    _lib.check(lib.dp_dice_ce_finalize(acc.data_ptr(), N, C, vox, out.data_ptr(), s))
+    _lib.check(lib.dp_dice_ce(zc.data_ptr(), zc.shape[1], lab.data_ptr(), N, C, vox, acc.data_ptr(), 1, 4096.0, g16.data_ptr(), 2, s))
+    torch.cuda.synchronize()
+    assert abs(float(out) - float(loss)) <= 1e-5 * abs(float(loss))
+    assert _rel(_c8_to_ncdhw(g16.float(), C) / 4096.0, logits.grad) < 1e-3        # fp16 storage of the gradient
+
+
+def _seg_model(size):
+    from dose_prediction_b200 import networks
+    from oracle import synth_ckpt
+    tokens = (size // 16) ** 3
+    man = [(k, ([1, tokens, s[2]] if k.endswith("position_embeddings") else s)) for k, s, *_ in load_manifest("oar_transeg")]
+    sd = synth_ckpt.make_state_dict(man, seed=1)
+    model = networks.OARTranseg(1, 8, (size,) * 3, pos_embed="perceptron")
+    model.load_state_dict(sd, strict=True)
+    return model.to(DEV).train(), sd
+
+
+def test_seg_training_step_matches_oracle_32():
+    """One Transeg.training_step (DiceCE) + AdamW at 32^3, batch 2, vs the oracle's autograd; then the loss goes down."""
+    from dose_prediction_b200 import synth
+    from dose_prediction_b200.training import SegTrainer
+    from oracle import torch_ref
+    model, sd = _seg_model(32)
+    vol = synth.make_batch(2, 32, seed=1234)
+    label = synth.oar_labels(vol["oars"])
+    loss_ref, grads_ref, new_ref, logits_ref = torch_ref.oar_transeg_train_step(sd, vol["ct"], label)
+    tr = SegTrainer(model, 2, 32)
+    ct, lab = vol["ct"].to(DEV), label.to(DEV)
+    loss = tr.step(ct, lab)
+    torch.cuda.synchronize()
+    tr.P.check_device_errors()
+    assert abs(float(loss) - float(loss_ref)) <= 2e-3 * abs(float(loss_ref))
+    assert _rel(tr.logits(), logits_ref) < 1e-2
+    g = tr.grads()
+    gmax = max(float(v.norm()) for v in grads_ref.values())
+    checked = 0
+    for n, ref in grads_ref.items():
+        if float(ref.norm()) < 1e-4 * gmax:
+            assert float(g[n].norm()) < 1e-3 * gmax, n
+            continue
+        cos = float(F.cosine_similarity(g[n].flatten().double().cpu(), ref.flatten().double(), dim=0))
+        assert cos > 0.99, (n, cos)
+        assert abs(float(g[n].norm()) / float(ref.norm()) - 1.0) < 0.08, n
+        checked += 1
+    assert checked > 150
+    losses = [float(loss)] + [float(tr.step(ct, lab)) for _ in range(7)]
+    print("seg losses", losses)
+    assert losses[-1] < 0.9 * losses[0], losses
