@@ -63,12 +63,16 @@ _SIGNATURES = {
     "dp_heads": [P, I, P, I, I, I, I, I, I, I, I, F, P],
     "dp_colsum": [P, I, L, P, P],
     "dp_add": [P, P, L, P, P, P],
+    # ---- on-device evaluation
+    "dp_dose_postprocess": [P, P, L, F, P, P],
+    "dp_dose_stats": [P, P, P, L, P, I, P, P, P, P, P],
+    "dp_dvh_metrics": [P, P, P, I, P, L, F, P, P, P, P],
 }
 
 
 def exported_symbols():
     """Every symbol include/dose_b200.h declares (checked by tests/test_abi.py)."""
-    return sorted(list(_SIGNATURES) + ["dp_last_error", "dp_abi_version", "dp_device_sm_count"])
+    return sorted(list(_SIGNATURES) + ["dp_last_error", "dp_abi_version", "dp_device_sm_count", "dp_dvh_workspace_bytes"])
 
 
 def lib():
@@ -86,6 +90,7 @@ def lib():
         handle.dp_last_error.restype = ctypes.c_char_p
         handle.dp_abi_version.restype = c_int
         handle.dp_device_sm_count.restype = c_int
+        handle.dp_dvh_workspace_bytes.restype = c_longlong
         _LIB = handle
     return _LIB
 

@@ -63,3 +63,13 @@ def oar_labels(oars):
     volume the seg training step consumes (OARSegmentation/train_light_transeg.py:185)."""
     idx = torch.arange(1, oars.shape[1] + 1, dtype=oars.dtype).view(1, -1, 1, 1, 1)
     return (oars * idx).amax(dim=1, keepdim=True).contiguous()
+
+
+def structures(vol):
+    """{structure name: [B,1,...] binary mask} in the reference's naming (evaluate_openKBP.py:176-186): the seven
+    OARs and the three nested targets PTV70 / PTV63 / PTV56 (PTV map values 1.0 / 0.9 / 0.8)."""
+    names = ["Brainstem", "SpinalCord", "RightParotid", "LeftParotid", "Esophagus", "Larynx", "Mandible"]
+    out = {n: vol["oars"][:, i:i + 1].contiguous() for i, n in enumerate(names)}
+    for n, val in (("PTV70", 1.0), ("PTV63", 0.9), ("PTV56", 0.8)):
+        out[n] = (vol["ptv"] - val).abs().lt(1e-6).float()
+    return out

@@ -295,6 +295,28 @@ int dp_colsum(const float* a, int rows, long long cols, double* out, cudaStream_
 /* y = a + b (b optional), fp32 and/or fp16 outputs */
 int dp_add(const float* a, const float* b, long long n, float* y_f32, void* y_f16, cudaStream_t stream);
 
+/* ======================================================================== on-device evaluation
+ * What Pyfer.test_step / LinkedNet.test_step do with numpy after a D2H copy (train_light_pyfer.py:210-216,
+ * train_light_linked_model.py:171-176, DosePrediction/Evaluate/evaluate_openKBP.py).                       */
+
+/* out = (mask < 1 || pred < 0) ? 0 : pred * scale      (train_light_pyfer.py:210-213) */
+int dp_dose_postprocess(const float* pred, const float* mask, long long n, float scale, float* out, cudaStream_t stream);
+
+/* get_3D_Dose_dif (evaluate_openKBP.py:42-48) and IVS (:17-39) at the n_levels ascending isodose levels (device
+ * double[n_levels], np.linspace(0, 70, 101) in the reference).  acc: double[2], hist: uint64[3*(n_levels+1)]
+ * scratch; ivs: float[n_levels], dose_dif: float[1].                                                          */
+int dp_dose_stats(const float* pred, const float* gt, const float* mask, long long n, const double* levels, int n_levels,
+                  double* acc, unsigned long long* hist, float* ivs, float* dose_dif, cudaStream_t stream);
+
+/* get_DVH_metrics (evaluate_openKBP.py:51-81) for n_struct ROI masks [n_struct][vox] (fp32, > 0 = inside) of the
+ * predicted and the ground-truth dose at once: exact np.percentile(linear) order statistics by a three-pass
+ * radix select.  is_target: device int[n_struct] (1 = PTV: D1, D95, D99, mean; 0 = OAR: D_0.1cc, mean).
+ * out: float[n_struct][2 (pred, gt)][5] = {q0, q1, q2, unused, mean}; dvh_dif: float[1] = mean |gt - pred| over the
+ * metrics of all non-empty structures (:206-222).  workspace: dp_dvh_workspace_bytes() bytes.                 */
+long long dp_dvh_workspace_bytes(void);
+int dp_dvh_metrics(const float* pred, const float* gt, const float* masks, int n_struct, const int* is_target, long long vox,
+                   float voxels_in_tenth_of_cc, void* workspace, float* out, float* dvh_dif, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

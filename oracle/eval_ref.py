@@ -1,0 +1,55 @@
+"""TEST INFRASTRUCTURE — numpy restatement of the reference's per-volume evaluation
+(DosePrediction/Evaluate/evaluate_openKBP.py).  Pinned against the reference file itself by tests/test_oracle.py
+(imported through oracle.ref_loader with stand-ins for its unused SimpleITK / matplotlib imports)."""
+import numpy as np
+
+OARS = ["Brainstem", "SpinalCord", "RightParotid", "LeftParotid", "Esophagus", "Larynx", "Mandible"]
+TARGETS = ["PTV70", "PTV63", "PTV56"]
+
+
+def postprocess(prediction, possible_dose_mask):
+    """train_light_pyfer.py:210-213."""
+    p = np.array(prediction, dtype=np.float32, copy=True)
+    p[np.logical_or(possible_dose_mask < 1, p < 0)] = 0
+    return 70.0 * p
+
+
+def dose_dif(pred, gt, possible_dose_mask):
+    """evaluate_openKBP.py:42-48 get_3D_Dose_dif."""
+    sel = possible_dose_mask > 0
+    return float(np.mean(np.abs(pred[sel] - gt[sel])))
+
+
+def ivs(pred, gt, level):
+    """evaluate_openKBP.py:17-39 IVS (possible_dose_mask=None as called at :166)."""
+    a, b = pred >= level, gt >= level
+    return 2 * np.sum(a * b) / (np.sum(a) + np.sum(b))
+
+
+def dvh_metrics(dose, mask, mode, spacing):
+    """evaluate_openKBP.py:51-81 get_DVH_metrics."""
+    roi = dose[mask > 0]
+    if mode == "target":
+        return {"D1": np.percentile(roi, 99), "D95": np.percentile(roi, 5), "D99": np.percentile(roi, 1), "mean": np.mean(roi)}
+    vt = np.maximum(1, np.round(100 / np.prod(spacing)))
+    return {"D_0.1_cc": np.percentile(roi, 100 - vt / len(roi) * 100), "mean": np.mean(roi)}
+
+
+def evaluate(pred, gt, possible_dose_mask, structures, spacing):
+    """evaluate_openKBP.py:149-222 get_Dose_score_and_DVH_score_batch for one volume (arrays [D,H,W])."""
+    out = {"dose_dif": dose_dif(pred, gt, possible_dose_mask),
+           "ivs": [ivs(pred, gt, lv) for lv in np.linspace(0, 70, 101)], "table": {}}
+    difs = []
+    for name in OARS + TARGETS:
+        if name not in structures:
+            break
+        m = structures[name]
+        if np.any(m):
+            mode = "target" if name in TARGETS else "OAR"
+            a, b = dvh_metrics(pred, m, mode, spacing), dvh_metrics(gt, m, mode, spacing)
+            for k in b:
+                difs.append(abs(b[k] - a[k]))
+                out["table"]["pre" + name + "_" + k] = float(a[k])
+                out["table"]["gt_" + name + "_" + k] = float(b[k])
+    out["dvh_dif"] = float(np.mean(difs))
+    return out

@@ -130,6 +130,33 @@ def main():
     srec["norms"] = np.array(snorms, dtype=np.float64)
     np.savez_compressed(os.path.join(OUT, "segtrain32.npz"), **srec)
 
+    # ---- per-volume evaluation (evaluate_openKBP.py): the reference's own numpy functions on a synthetic prediction
+    ev = ref_loader.evaluate()
+    v64 = synth.make_volume(64, seed=99)
+    gt_gy = (v64["gt"][0, 0].numpy() * 70).astype(np.float32)
+    pmask = v64["gt"][0, 1].numpy()
+    rng = np.random.default_rng(7)
+    raw_pred = (gt_gy / 70 + rng.normal(0, 0.03, gt_gy.shape)).astype(np.float32)
+    pred_gy = raw_pred.copy()
+    pred_gy[np.logical_or(pmask < 1, pred_gy < 0)] = 0            # train_light_pyfer.py:210-213
+    pred_gy = 70. * pred_gy
+    erec = {"dose_dif": np.float64(ev.get_3D_Dose_dif(pred_gy, gt_gy, pmask)),
+            "ivs": np.array([ev.IVS(pred_gy, gt_gy, lv) for lv in np.linspace(0, 70, 101)], dtype=np.float64)}
+    sp = (3.906, 3.906, 2.5)
+    difs = []
+    for name, m in synth.structures(v64).items():
+        m = m[0, 0].numpy()
+        if not np.any(m):
+            continue
+        mode = "target" if name.startswith("PTV") else "OAR"
+        a, b = ev.get_DVH_metrics(pred_gy, m, mode=mode, spacing=sp), ev.get_DVH_metrics(gt_gy, m, mode=mode, spacing=sp)
+        for k_ in b:
+            erec["pre" + name + "_" + k_] = np.float64(a[k_])
+            erec["gt_" + name + "_" + k_] = np.float64(b[k_])
+            difs.append(abs(b[k_] - a[k_]))
+    erec["dvh_dif"] = np.float64(np.mean(difs))
+    np.savez_compressed(os.path.join(OUT, "eval64.npz"), **erec)
+
     # ---- sliding window (monai restatement; seg net built for 32^3 scanned over a 48^3 CT)
     from monai.inferers import sliding_window_inference
     ct48 = synth.make_volume(48, seed=77)["ct"]

@@ -50,6 +50,27 @@ def loss():
     return _imp("DosePrediction.Train.loss")
 
 
+def evaluate():
+    """DosePrediction/Evaluate/evaluate_openKBP.py, unmodified.  Its module-level imports of SimpleITK, matplotlib and
+    monai.metrics are unused by the functions the oracle is pinned against (IVS, get_3D_Dose_dif, get_DVH_metrics);
+    stand-in modules are registered for whichever of them is not installed."""
+    import types
+    for name in ("SimpleITK", "matplotlib", "matplotlib.pyplot", "matplotlib.colors", "monai.metrics"):
+        _ensure_path()
+        try:
+            importlib.import_module(name)
+        except Exception:
+            m = types.ModuleType(name)
+            if name == "monai.metrics":
+                m.DiceMetric = lambda *a, **k: None
+            sys.modules[name] = m
+            if "." in name:
+                parent, child = name.rsplit(".", 1)
+                if parent in sys.modules:
+                    setattr(sys.modules[parent], child, m)
+    return _imp("DosePrediction.Evaluate.evaluate_openKBP")
+
+
 def seg_config():
     return _imp("OARSegmentation.config")
 

@@ -1,0 +1,74 @@
+"""On-device evaluation vs the oracle (oracle/eval_ref.py) and the fixture made from the reference's
+own evaluate_openKBP.py functions (tests/golden/eval64.npz).  Integer work (ROI sizes, histograms, order statistics)
+is exact; the reported floats agree to fp32 rounding (tolerances below)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _inputs(size, seed):
+    from dose_prediction_b200 import synth
+    v = synth.make_volume(size, seed=seed)
+    gt_gy = (v["gt"][0, 0].numpy() * 70).astype(np.float32)
+    pmask = v["gt"][0, 1].numpy()
+    raw = (gt_gy / 70 + np.random.default_rng(7).normal(0, 0.03, gt_gy.shape)).astype(np.float32)
+    return v, raw, gt_gy, pmask
+
+
+def test_evaluator_matches_reference_fixture_and_oracle():
+    from dose_prediction_b200 import synth
+    from dose_prediction_b200.evaluation import DoseEvaluator
+    from oracle import eval_ref
+    v, raw, gt_gy, pmask = _inputs(64, 99)
+    ev = DoseEvaluator(DEV)
+    pred = ev.postprocess(torch.from_numpy(raw).to(DEV), torch.from_numpy(pmask).to(DEV))
+    want_pred = eval_ref.postprocess(raw, pmask)
+    assert np.array_equal(pred.cpu().numpy(), want_pred)                      # bit-exact post-processing
+    st = synth.structures(v)
+    res = ev.evaluate(pred, torch.from_numpy(gt_gy), torch.from_numpy(pmask), st)
+    torch.cuda.synchronize()
+    g = np.load(os.path.join(GOLDEN, "eval64.npz"))
+    assert abs(float(res["dose_dif"]) - float(g["dose_dif"])) <= 2e-6 * float(g["dose_dif"])
+    assert np.allclose(res["ivs"].cpu().numpy(), g["ivs"], rtol=0, atol=1e-6)
+    table = ev.dvh_table(res)
+    keys = [k for k in g.files if k.startswith("pre") or k.startswith("gt_")]
+    assert sorted(keys) == sorted(table)
+    for k in keys:
+        assert abs(table[k] - float(g[k])) <= 2e-6 * max(1.0, abs(float(g[k]))), k
+    assert abs(float(res["dvh_dif"]) - float(g["dvh_dif"])) <= 1e-5
+
+
+def test_evaluator_edge_cases():
+    """empty structures are skipped, tiny ROIs (n = 1, 2) and negative / zero doses select the right order statistics."""
+    from dose_prediction_b200.evaluation import DoseEvaluator
+    from oracle import eval_ref
+    rng = np.random.default_rng(3)
+    S = 24
+    pred = rng.normal(20, 15, (S, S, S)).astype(np.float32)
+    gt = rng.normal(20, 15, (S, S, S)).astype(np.float32)
+    pred[rng.random(pred.shape) < 0.2] = 0.0
+    pmask = (rng.random(pred.shape) < 0.7).astype(np.float32)
+    st = {"Brainstem": np.zeros((S, S, S), np.float32), "SpinalCord": np.zeros((S, S, S), np.float32),
+          "RightParotid": (rng.random(pred.shape) < 0.1).astype(np.float32), "PTV70": np.zeros((S, S, S), np.float32),
+          "PTV63": (rng.random(pred.shape) < 0.3).astype(np.float32)}
+    st["SpinalCord"][3, 4, 5] = 1.0                      # n = 1
+    st["PTV70"][1, 1, 1] = st["PTV70"][2, 2, 2] = 1.0    # n = 2
+    ev = DoseEvaluator(DEV)
+    res = ev.evaluate(torch.from_numpy(pred).to(DEV), torch.from_numpy(gt), torch.from_numpy(pmask),
+                      {k: torch.from_numpy(m) for k, m in st.items()})
+    torch.cuda.synchronize()
+    want = eval_ref.evaluate(pred, gt, pmask, st, (3.906, 3.906, 2.5))
+    table = ev.dvh_table(res)
+    assert sorted(table) == sorted(want["table"])
+    for k, val in want["table"].items():
+        assert abs(table[k] - val) <= 2e-6 * max(1.0, abs(val)), k
+    assert abs(float(res["dose_dif"]) - want["dose_dif"]) <= 2e-6 * want["dose_dif"]
+    assert np.allclose(res["ivs"].cpu().numpy(), np.array(want["ivs"]), rtol=0, atol=1e-6)
+    assert abs(float(res["dvh_dif"]) - want["dvh_dif"]) <= 1e-5

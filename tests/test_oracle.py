@@ -113,6 +113,31 @@ def test_seg_train_step_matches_reference_fixture(seg_sd32):
         assert (got - ref).abs().max() <= 5e-3 * ref.abs().max() + 1e-6 * gmax, n
 
 
+def _eval_inputs():
+    v = synth.make_volume(64, seed=99)
+    gt_gy = (v["gt"][0, 0].numpy() * 70).astype(np.float32)
+    pmask = v["gt"][0, 1].numpy()
+    raw = (gt_gy / 70 + np.random.default_rng(7).normal(0, 0.03, gt_gy.shape)).astype(np.float32)
+    return v, raw, gt_gy, pmask
+
+
+def test_evaluation_matches_reference_fixture():
+    """oracle/eval_ref.py == the reference's own evaluate_openKBP.py functions (fixture made from them)."""
+    from oracle import eval_ref
+    v, raw, gt_gy, pmask = _eval_inputs()
+    g = np.load(os.path.join(GOLDEN, "eval64.npz"))
+    pred = eval_ref.postprocess(raw, pmask)
+    st = {k: m[0, 0].numpy() for k, m in synth.structures(v).items()}
+    out = eval_ref.evaluate(pred, gt_gy, pmask, st, (3.906, 3.906, 2.5))
+    assert abs(out["dose_dif"] - float(g["dose_dif"])) < 1e-6
+    assert np.allclose(out["ivs"], g["ivs"], rtol=0, atol=1e-12)
+    assert abs(out["dvh_dif"] - float(g["dvh_dif"])) < 1e-5
+    keys = [k for k in g.files if k.startswith("pre") or k.startswith("gt_")]
+    assert sorted(keys) == sorted(out["table"]) and len(keys) == 2 * (7 * 2 + 3 * 4)
+    for k in keys:
+        assert abs(out["table"][k] - float(g[k])) <= 1e-5 * max(1.0, abs(float(g[k]))), k
+
+
 def test_sliding_window_matches_fixture(seg_sd32):
     ct48 = synth.make_volume(48, seed=77)["ct"]
     g = torch.from_numpy(np.load(os.path.join(GOLDEN, "sliding48.npz"))["logits"])
