@@ -56,7 +56,11 @@ class DoseEvaluator:
         _lib.check(self.lib.dp_dose_stats(p.data_ptr(), g.data_ptr(), m.data_ptr(), vox, self.levels.data_ptr(), self.n_levels,
                                           self.acc.data_ptr(), self.hist.data_ptr(), ivs_out.data_ptr(), dose_dif.data_ptr(), s),
                    "dp_dose_stats")
-        names = [n for n in STRUCTURES if n in structures]
+        names = []
+        for n in STRUCTURES:                      # the reference stops at the first structure the batch does not carry
+            if n not in structures:               # (evaluate_openKBP.py:188-189 `break`)
+                break
+            names.append(n)
         masks = torch.stack([structures[n].to(dev).reshape(-1).float() for n in names]).contiguous()
         is_target = torch.tensor([int(n in TARGET_NAMES) for n in names], dtype=torch.int32, device=dev)
         vt = max(1.0, float(np.round(100.0 / float(np.prod(spacing)))))

@@ -46,7 +46,7 @@ def test_evaluator_matches_reference_fixture_and_oracle():
 
 
 def test_evaluator_edge_cases():
-    """empty structures are skipped, tiny ROIs (n = 1, 2) and negative / zero doses select the right order statistics."""
+    """empty structures are skipped, tiny ROIs (n = 2, 4) and negative / zero doses select the right order statistics."""
     from dose_prediction_b200.evaluation import DoseEvaluator
     from oracle import eval_ref
     rng = np.random.default_rng(3)
@@ -58,7 +58,10 @@ def test_evaluator_edge_cases():
     st = {"Brainstem": np.zeros((S, S, S), np.float32), "SpinalCord": np.zeros((S, S, S), np.float32),
           "RightParotid": (rng.random(pred.shape) < 0.1).astype(np.float32), "PTV70": np.zeros((S, S, S), np.float32),
           "PTV63": (rng.random(pred.shape) < 0.3).astype(np.float32)}
-    st["SpinalCord"][3, 4, 5] = 1.0                      # n = 1
+    for n in ("LeftParotid", "Esophagus", "Larynx", "Mandible", "PTV56"):
+        st[n] = np.zeros((S, S, S), np.float32)
+    st["Mandible"][5:9, 5:9, 5:9] = 1.0
+    st["SpinalCord"][3, 4, 5:9] = 1.0                    # n = 4 (an OAR below 3 voxels makes the reference's np.percentile raise)
     st["PTV70"][1, 1, 1] = st["PTV70"][2, 2, 2] = 1.0    # n = 2
     ev = DoseEvaluator(DEV)
     res = ev.evaluate(torch.from_numpy(pred).to(DEV), torch.from_numpy(gt), torch.from_numpy(pmask),
