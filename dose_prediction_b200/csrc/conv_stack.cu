@@ -51,8 +51,10 @@ struct StackParams {
   uint8_t chunk_cb[96];
 };
 
-constexpr int kStackThreads = 320;      // producer + MMA + 8 epilogue warps (2 per TMEM lane quarter)
+constexpr int kStackThreads = 352;      // producer + MMA + 8 epilogue warps (2 per TMEM lane quarter) + second MMA issuer
 constexpr int kStackEpiWarps = 8;
+constexpr int kStackMmaWarpB = 10;      // issues the MMAs of the upper half of the CTA's tiles (single-thread issue is the
+                                        // limiter: ncu shows ~100 cycles per MMA against a 64-cycle tensor floor)
 constexpr int kMaxAStages = 4, kMaxBStages = 6, kMaxSlots = 32;
 
 __device__ __forceinline__ void umma_split(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
@@ -146,9 +148,10 @@ conv3d_stack_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_co
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_in);
-    for (int i = 0; i < p.a_stages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < p.b_stages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i <= KS; ++i) { mbar_init(&done_bar[i], 1); mbar_init(&free_bar[i], kStackEpiWarps); }
+    constexpr uint32_t n_issuers = TT >= 2 ? 2 : 1;
+    for (int i = 0; i < p.a_stages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], n_issuers); }
+    for (int i = 0; i < p.b_stages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], n_issuers); }
+    for (int i = 0; i <= KS; ++i) { mbar_init(&done_bar[i], n_issuers); mbar_init(&free_bar[i], kStackEpiWarps); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(&tmem_base_smem);
@@ -210,10 +213,14 @@ conv3d_stack_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_co
       }
       pc_base += static_cast<uint32_t>(it.d1 - it.d0);
     }
-  } else if (warp == 1) {
-    // ===================================================================== MMA issuer
-    // One elected thread runs this role.  Issue cost is ~5.5 cycles per SASS instruction of THIS thread
-    // (scripts/micro/mma_rate.cu), so the interior-plane path is fully unrolled per kernel row.
+  } else if (warp == 1 || (warp == kStackMmaWarpB && TT >= 2)) {
+    // ===================================================================== MMA issuers
+    // One elected thread per issuing warp runs this role.  Issue cost is ~5.5 cycles per SASS instruction of THAT
+    // thread (scripts/micro/mma_rate.cu), so the interior-plane path is fully unrolled per kernel row, and for
+    // T >= 2 the CTA's tiles are split between two issuing warps (on different SM sub-partitions): both follow
+    // the same barrier protocol, every hand-off barrier counts two arrivals.
+    constexpr int TTs = TT >= 2 ? TT / 2 : TT;                 // tiles per issuer
+    const int t_off = (warp == 1) ? 0 : TTs;
     if (elect_one()) {
     const uint32_t idesc0 = make_idesc_f16(128, 0);
     const uint32_t idesc_full = idesc0 | (static_cast<uint32_t>((G * N0) >> 3) << 17);
@@ -225,12 +232,15 @@ conv3d_stack_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_co
     const uint32_t tile_cols = static_cast<uint32_t>(G * N0);
     const uint32_t smem16 = smem_u32(smem) >> 4;
     const uint32_t a_stride16 = p.a_stride >> 4, b_stride16 = p.b_stride >> 4, b_off16 = p.b_off >> 4;
+    const uint32_t tm0 = tmem_base + static_cast<uint32_t>(t_off) * tile_cols;       // this issuer's first tile
+    const uint32_t a_toff = static_cast<uint32_t>(t_off) * 8;
     int ia = 0, ib = 0;
     uint32_t pa = 0, pb = 0;
     uint32_t pc_base = 0;                      // running plane counter of this item's plane d0
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
       const Item it = decode_item<KS>(p, item);
-      const bool all_tiles = (it.ntile == TT);
+      const int my_tiles = max(0, min(TTs, it.ntile - t_off));
+      const bool all_tiles = (my_tiles == TTs);
       for (int dz = it.z0; dz <= it.z1; ++dz) {
         // output planes fed by this input plane, oldest first
         const int p_lo = max(dz - pad, it.d0), p_hi = min(dz + pad, it.d1 - 1);
@@ -290,8 +300,8 @@ conv3d_stack_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_co
             int tl = 0;
             if (first_tap) {
               for (int q = 0; q < nfp; ++q)
-                for (int t = 0; t < it.ntile; ++t)
-                  umma_split(tmem_base + t * tile_cols + fp_o[q], a_row + kw + t * 8, a_hi, b_lo + fp_o[q], b_hi, fp_i[q], fp_acc[q]);
+                for (int t = 0; t < my_tiles; ++t)
+                  umma_split(tm0 + t * tile_cols + fp_o[q], a_row + a_toff + kw + t * 8, a_hi, b_lo + fp_o[q], b_hi, fp_i[q], fp_acc[q]);
               first_tap = false;
               b_lo += tap_b16;
               if (++kw == KS) { kw = 0; ++kh; a_row += p.PWw; }
@@ -300,15 +310,15 @@ conv3d_stack_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_co
             if (fast) {
               while (tl < cnt) {
                 const int seg = min(cnt - tl, KS - kw);           // taps left in this kernel row
-                const uint32_t a_lo = a_row + kw;
+                const uint32_t a_lo = a_row + a_toff + kw;
                 switch (seg) {
-                  case 7: issue_taps<7, TT>(tmem_base, tile_cols, a_lo, a_hi, b_lo, b_hi, tap_b16, idesc_full); break;
-                  case 6: issue_taps<6, TT>(tmem_base, tile_cols, a_lo, a_hi, b_lo, b_hi, tap_b16, idesc_full); break;
-                  case 5: issue_taps<5, TT>(tmem_base, tile_cols, a_lo, a_hi, b_lo, b_hi, tap_b16, idesc_full); break;
-                  case 4: issue_taps<4, TT>(tmem_base, tile_cols, a_lo, a_hi, b_lo, b_hi, tap_b16, idesc_full); break;
-                  case 3: issue_taps<3, TT>(tmem_base, tile_cols, a_lo, a_hi, b_lo, b_hi, tap_b16, idesc_full); break;
-                  case 2: issue_taps<2, TT>(tmem_base, tile_cols, a_lo, a_hi, b_lo, b_hi, tap_b16, idesc_full); break;
-                  default: issue_taps<1, TT>(tmem_base, tile_cols, a_lo, a_hi, b_lo, b_hi, tap_b16, idesc_full); break;
+                  case 7: issue_taps<7, TTs>(tm0, tile_cols, a_lo, a_hi, b_lo, b_hi, tap_b16, idesc_full); break;
+                  case 6: issue_taps<6, TTs>(tm0, tile_cols, a_lo, a_hi, b_lo, b_hi, tap_b16, idesc_full); break;
+                  case 5: issue_taps<5, TTs>(tm0, tile_cols, a_lo, a_hi, b_lo, b_hi, tap_b16, idesc_full); break;
+                  case 4: issue_taps<4, TTs>(tm0, tile_cols, a_lo, a_hi, b_lo, b_hi, tap_b16, idesc_full); break;
+                  case 3: issue_taps<3, TTs>(tm0, tile_cols, a_lo, a_hi, b_lo, b_hi, tap_b16, idesc_full); break;
+                  case 2: issue_taps<2, TTs>(tm0, tile_cols, a_lo, a_hi, b_lo, b_hi, tap_b16, idesc_full); break;
+                  default: issue_taps<1, TTs>(tm0, tile_cols, a_lo, a_hi, b_lo, b_hi, tap_b16, idesc_full); break;
                 }
                 tl += seg;
                 b_lo += seg * tap_b16;
@@ -318,8 +328,8 @@ conv3d_stack_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_co
             } else {
               for (; tl < cnt; ++tl) {
                 for (int q = 0; q < npc; ++q)
-                  for (int t = 0; t < it.ntile; ++t)
-                    umma_split(tmem_base + t * tile_cols + pc_o[q], a_row + kw + t * 8, a_hi, b_lo + pc_o[q], b_hi, pc_i[q], 1u);
+                  for (int t = 0; t < my_tiles; ++t)
+                    umma_split(tm0 + t * tile_cols + pc_o[q], a_row + a_toff + kw + t * 8, a_hi, b_lo + pc_o[q], b_hi, pc_i[q], 1u);
                 b_lo += tap_b16;
                 if (++kw == KS) { kw = 0; a_row += p.PWw; }
               }
@@ -342,7 +352,7 @@ conv3d_stack_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_co
       pc_base += static_cast<uint32_t>(it.d1 - it.d0);
     }
     }
-  } else {
+  } else if (warp >= 2 && warp < 2 + kStackEpiWarps) {
     // ===================================================================== epilogue (warps 2..9)
     // two warps per TMEM lane quarter; the pair splits the CTA's W tiles (even / odd)
     const int quarter = warp & 3;
