@@ -160,6 +160,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
         const int dz = d + kd0 * p.dil - p.pad;
         if (p.kd_s == 1 && (dz < 0 || dz >= p.D)) continue;
         for (int c = 0; c < p.n_chunks; ++c) {
+          if (KS <= 3 && p.kd_s == 1 && ((p.tap_mask[c] >> (kd0 * KS * KS)) & ((1u << (KS * KS)) - 1u)) == 0u) continue;   // no tap of this depth
           const __half* wsrc = p.wpack + static_cast<size_t>(kd0) * kd_w_halfs + static_cast<size_t>(c) * chunk_w_halfs;
           for (int g = 0; g < p.n_khg; ++g) {
             const int kh0 = g * p.kh_s;
@@ -205,6 +206,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
         const int dz = d + kdg * p.kd_s * p.dil - p.pad;
         if (p.kd_s == 1 && (dz < 0 || dz >= p.D)) continue;
         for (int c = 0; c < p.n_chunks; ++c) {
+          if (KS <= 3 && p.kd_s == 1 && ((p.tap_mask[c] >> (kdg * KS * KS)) & ((1u << (KS * KS)) - 1u)) == 0u) continue;
           for (int g = 0; g < p.n_khg; ++g) {
             const int cnt = min(p.kh_s, KS - g * p.kh_s);
             if (!mbar_wait(&full_bar[stage], phase, p.err_flag)) goto teardown;
@@ -360,7 +362,7 @@ extern "C" int dp_conv3d_tc(const void* in_c8, int cb_total_in, const uint8_t* c
   p.PW = 8 + (k - 1) * dil;
   // stage sizing: as many kh rows per stage as fit ~56 KB, then as many stages as fit ~200 KB
   const int tap_b = 32 * cout;
-  int kh_s = k, kd_s = (dil == 1) ? k : 1;
+  int kh_s = k, kd_s = (dil == 1 && tap_mask == nullptr) ? k : 1;   // tap-masked (space-to-depth) convs: per-depth stages, empty ones skipped
   auto stage_bytes_for = [&](int sd, int s) {
     const int phs = 16 + (s - 1) * dil;
     const int a = 2 * sd * phs * p.PW * 16;

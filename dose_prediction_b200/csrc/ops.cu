@@ -47,6 +47,45 @@ __device__ __forceinline__ void store8(__half* hi, __half* lo, size_t off, const
   *reinterpret_cast<uint4*>(hi + off) = *reinterpret_cast<const uint4*>(h);
   if (lo != nullptr) *reinterpret_cast<uint4*>(lo + off) = *reinterpret_cast<const uint4*>(l);
 }
+
+// one switch per 8 values (the per-element switch of act_apply cost more instructions than the arithmetic)
+__device__ __forceinline__ void act8(float (&y)[8], int act) {
+  switch (act) {
+    case ACT_RELU:
+#pragma unroll
+      for (int j = 0; j < 8; ++j) y[j] = fmaxf(y[j], 0.f);
+      break;
+    case ACT_LRELU:
+#pragma unroll
+      for (int j = 0; j < 8; ++j) y[j] = y[j] > 0.f ? y[j] : 0.01f * y[j];
+      break;
+    case ACT_MISH:
+#pragma unroll
+      for (int j = 0; j < 8; ++j) y[j] = act_apply(y[j], ACT_MISH);
+      break;
+    case ACT_GELU:
+#pragma unroll
+      for (int j = 0; j < 8; ++j) y[j] = act_apply(y[j], ACT_GELU);
+      break;
+    default: break;
+  }
+}
+// hi = fp16(x), lo = fp16(x - hi) with the packed two-at-a-time conversions
+__device__ __forceinline__ void store8p(__half* hi, __half* lo, size_t off, const float (&x)[8]) {
+  __align__(16) __half2 h[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(x[2 * j], x[2 * j + 1]);
+  *reinterpret_cast<uint4*>(hi + off) = *reinterpret_cast<const uint4*>(h);
+  if (lo != nullptr) {
+    __align__(16) __half2 l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(h[j]);
+      l[j] = __floats2half2_rn(x[2 * j] - f.x, x[2 * j + 1] - f.y);
+    }
+    *reinterpret_cast<uint4*>(lo + off) = *reinterpret_cast<const uint4*>(l);
+  }
+}
 // mean / rstd of channel c of image n from fp64 {sum, sumsq}; biased variance, eps 1e-5 (InstanceNorm3d).
 __device__ __forceinline__ void finalize_stats(const double* stats, size_t idx, double inv_count, float& mean,
                                                float& rstd) {
@@ -136,75 +175,81 @@ struct NormActParams {
   int act_after_res;
   __half* out_hi; __half* out_lo; int out_cb_total, out_cb_off;
   double* stats_out;              // statistics of the produced tensor (chained InstanceNorm), or null
-  int C, ncb; long long vox;
+  int C, ncb; long long vox; double inv_vox;
   // optional second copy in space-to-depth layout: channel block (parity*ncb + cb) of a half-resolution
   // tensor, parity = (d&1)*4 + (h&1)*2 + (w&1); feeds the stride-2 convs as sparse stride-1 convs
   __half* s2d_hi; __half* s2d_lo; int s2d_cb_total, s2d_cb_off, D, H, W;
 };
 
 constexpr int NA_IT = 4;      // voxel chunks per block: amortises the statistics prologue
-__global__ void __launch_bounds__(256) norm_act_kernel(const NormActParams p) {
+// ncu (profiles/r1_norm_pointwise_ncu.md): the first version of this kernel was INSTRUCTION bound (sm throughput 78 %,
+// 400 thread-instructions per 8-channel vector: per-element channel predicates, a per-element activation switch,
+// scalar fp16 conversions).  Channels beyond C are neutralised through the per-channel constants instead
+// (rstd = 0 -> 0), the activation switch is hoisted out of the element loop, conversions are packed.
+__global__ void __launch_bounds__(256, 4) norm_act_kernel(const NormActParams p) {
   const int cb = blockIdx.y % p.ncb, n = blockIdx.y / p.ncb;
-  const double inv = 1.0 / static_cast<double>(p.vox);
-  __shared__ float s_mean[2][8], s_rstd[2][8];
+  const double inv = p.inv_vox;                    // 1/vox from the host: no fp64 division on the device
+  __shared__ float s_mean[2][8], s_rstd[2][8], s_gamma[8], s_beta[8];
   if (threadIdx.x < 16) {
-    const int which = threadIdx.x >> 3, c = cb * 8 + (threadIdx.x & 7);
+    const int which = threadIdx.x >> 3, j = threadIdx.x & 7, c = cb * 8 + j;
     const double* st = which ? p.res_stats : p.stats;
     float m = 0.f, r = 1.f;
     if (st != nullptr && c < p.C) finalize_stats(st, static_cast<size_t>(n) * p.C + c, inv, m, r);
-    s_mean[which][threadIdx.x & 7] = m;
-    s_rstd[which][threadIdx.x & 7] = r;
+    if (c >= p.C) r = 0.f;                          // padded channels: (x - 0) * 0 = 0 through every activation
+    s_mean[which][j] = m;
+    s_rstd[which][j] = r;
+    if (which == 0) {
+      s_gamma[j] = (p.gamma && c < p.C) ? p.gamma[c] : 1.f;
+      s_beta[j] = (p.gamma && c < p.C) ? p.beta[c] : 0.f;
+    }
   }
   __syncthreads();
+  float mean0[8], rstd0[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { mean0[j] = s_mean[0][j]; rstd0[j] = s_rstd[0][j]; }
+  const bool has_res = p.res_hi || p.res_raw;
+  const bool affine = p.gamma != nullptr;
+  const bool want_stats = p.stats_out != nullptr;
   float a1[8], a2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { a1[j] = 0.f; a2[j] = 0.f; }
+  const size_t in_base = (static_cast<size_t>(n) * p.in_cb_total + p.in_cb_off + cb) * p.vox;
+  const size_t out_base = (static_cast<size_t>(n) * p.out_cb_total + p.out_cb_off + cb) * p.vox;
 #pragma unroll 1
   for (int it = 0; it < NA_IT; ++it) {
-  const long long v = (blockIdx.x * static_cast<long long>(NA_IT) + it) * blockDim.x + threadIdx.x;
-  const bool valid = v < p.vox;
-  float y[8];
-  if (valid) {
-    const size_t in_off = ((static_cast<size_t>(n) * p.in_cb_total + p.in_cb_off + cb) * p.vox + v) * 8;
-    if (p.raw_f32) load8f(p.raw_f32, in_off, y); else load8(p.raw_hi, p.raw_lo, in_off, y);
+    const long long v = (blockIdx.x * static_cast<long long>(NA_IT) + it) * blockDim.x + threadIdx.x;
+    if (v >= p.vox) break;
+    float y[8];
+    if (p.raw_f32) load8f(p.raw_f32, (in_base + v) * 8, y); else load8(p.raw_hi, p.raw_lo, (in_base + v) * 8, y);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = cb * 8 + j;
-      if (c < p.C) {
-        y[j] = (y[j] - s_mean[0][j]) * s_rstd[0][j];
-        if (p.gamma) y[j] = fmaf(y[j], __ldg(&p.gamma[c]), __ldg(&p.beta[c]));
-        y[j] = act_apply(y[j], p.act);
-      } else {
-        y[j] = 0.f;
-      }
+    for (int j = 0; j < 8; ++j) y[j] = (y[j] - mean0[j]) * rstd0[j];
+    if (affine) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) y[j] = fmaf(y[j], s_gamma[j], s_beta[j]);
     }
-    if (p.res_hi || p.res_raw) {
+    act8(y, p.act);
+    if (has_res) {
       float r8[8];
       const size_t r_off = ((static_cast<size_t>(n) * p.res_cb_total + p.res_cb_off + cb) * p.vox + v) * 8;
       if (p.res_raw) load8f(p.res_raw, r_off, r8); else load8(p.res_hi, p.res_lo, r_off, r8);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int c = cb * 8 + j;
-        if (c < p.C) {
-          r8[j] = (r8[j] - s_mean[1][j]) * s_rstd[1][j];
-          y[j] = act_apply(y[j] + r8[j], p.act_after_res);
-        }
-      }
+      for (int j = 0; j < 8; ++j) y[j] += (r8[j] - s_mean[1][j]) * s_rstd[1][j];
+      act8(y, p.act_after_res);
     }
-    if (p.out_hi)
-      store8(p.out_hi, p.out_lo, ((static_cast<size_t>(n) * p.out_cb_total + p.out_cb_off + cb) * p.vox + v) * 8, y);
+    if (p.out_hi) store8p(p.out_hi, p.out_lo, (out_base + v) * 8, y);
     if (p.s2d_hi) {
       const int w = static_cast<int>(v % p.W), h = static_cast<int>((v / p.W) % p.H), d = static_cast<int>(v / (static_cast<long long>(p.W) * p.H));
       const int parity = ((d & 1) << 2) | ((h & 1) << 1) | (w & 1);
       const size_t vh = (static_cast<size_t>(d >> 1) * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1);
-      store8(p.s2d_hi, p.s2d_lo,
-             ((static_cast<size_t>(n) * p.s2d_cb_total + p.s2d_cb_off + parity * p.ncb + cb) * (p.vox >> 3) + vh) * 8, y);
+      store8p(p.s2d_hi, p.s2d_lo,
+              ((static_cast<size_t>(n) * p.s2d_cb_total + p.s2d_cb_off + parity * p.ncb + cb) * (p.vox >> 3) + vh) * 8, y);
     }
+    if (want_stats) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { a1[j] += y[j]; a2[j] = fmaf(y[j], y[j], a2[j]); }
+      for (int j = 0; j < 8; ++j) { a1[j] += y[j]; a2[j] = fmaf(y[j], y[j], a2[j]); }
+    }
   }
-  }
-  if (p.stats_out) block_accumulate_sums(a1, a2, p.stats_out, static_cast<size_t>(n) * p.C + cb * 8);
+  if (want_stats) block_accumulate_sums(a1, a2, p.stats_out, static_cast<size_t>(n) * p.C + cb * 8);
 }
 
 // ------------------------------------------------------------------ 1x1x1 convolution, normalise-on-load, <=3 sources
@@ -217,7 +262,7 @@ struct PointwiseParams {
   const float* w;       // [C_out][C_in_total] fp32 (C_in_total = sum of source C)
   const float* bias;    // [C_out] or null
   int cin_total, cout;
-  long long vox;
+  long long vox; double inv_vox;
   float* out_raw; int out_cb_total, out_cb_off;     // c8 fp32 (+stats) ...
   __half* out_hi; __half* out_lo;                   // ... or c8 fp16
   float* out_planar;                                // ... or NCDHW fp32 [N][C_out][vox]
@@ -225,71 +270,85 @@ struct PointwiseParams {
   int out_act;
 };
 constexpr int PW_CO = 16;   // output channels per block pass
+constexpr int PW_IT = 4;    // voxel chunks per block: amortises the weight / statistics prologue and the stats atomics
 
-__global__ void __launch_bounds__(128) pointwise_kernel(const PointwiseParams p) {
-  extern __shared__ float wsm[];           // [cin_total][PW_CO] weights, then [cin_total] mean, [cin_total] rstd
-  float* s_mean = wsm + p.cin_total * PW_CO;
-  float* s_rstd = s_mean + p.cin_total;
+// Shared-memory weights are indexed by PADDED input channel (every source rounded up to whole 8-channel blocks, zero
+// rows for the padding), so the inner loop needs no channel predicates; the activation switch runs once per 8-vector.
+__global__ void __launch_bounds__(128, 6) pointwise_kernel(const PointwiseParams p) {
+  extern __shared__ float wsm[];           // [cin_pad][PW_CO] weights, then [cin_pad] mean, [cin_pad] rstd
+  int cin_pad = 0;
+  for (int s = 0; s < p.nsrc; ++s) cin_pad += ((p.src[s].C + 7) / 8) * 8;
+  float* s_mean = wsm + cin_pad * PW_CO;
+  float* s_rstd = s_mean + cin_pad;
   const int co0 = blockIdx.y * PW_CO;
   const int n = blockIdx.z;
-  const double inv = 1.0 / static_cast<double>(p.vox);
-  for (int i = threadIdx.x; i < p.cin_total * PW_CO; i += blockDim.x) {
-    const int ci = i / PW_CO, j = i % PW_CO;
-    wsm[i] = (co0 + j < p.cout) ? p.w[static_cast<size_t>(co0 + j) * p.cin_total + ci] : 0.f;
-  }
+  const double inv = p.inv_vox;
   {
-    int base = 0;
+    int base = 0, lbase = 0;               // padded / logical first channel of the source
     for (int s = 0; s < p.nsrc; ++s) {
-      for (int c = threadIdx.x; c < p.src[s].C; c += blockDim.x) {
+      const int Cs = p.src[s].C, Cp = ((Cs + 7) / 8) * 8;
+      for (int i = threadIdx.x; i < Cp * PW_CO; i += blockDim.x) {
+        const int c = i / PW_CO, j = i % PW_CO;
+        wsm[(base + c) * PW_CO + j] =
+            (c < Cs && co0 + j < p.cout) ? p.w[static_cast<size_t>(co0 + j) * p.cin_total + lbase + c] : 0.f;
+      }
+      for (int c = threadIdx.x; c < Cp; c += blockDim.x) {
         float m = 0.f, r = 1.f;
-        if (p.src[s].stats) finalize_stats(p.src[s].stats, static_cast<size_t>(n) * p.src[s].C + c, inv, m, r);
+        if (p.src[s].stats && c < Cs) finalize_stats(p.src[s].stats, static_cast<size_t>(n) * Cs + c, inv, m, r);
         s_mean[base + c] = m;
         s_rstd[base + c] = r;
       }
-      base += p.src[s].C;
+      base += Cp;
+      lbase += Cs;
     }
   }
   __syncthreads();
-  const long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  const bool valid = v < p.vox;
-  float acc[PW_CO];
+  float st1[PW_CO], st2[PW_CO];
 #pragma unroll
-  for (int j = 0; j < PW_CO; ++j) acc[j] = (p.bias && co0 + j < p.cout) ? __ldg(&p.bias[co0 + j]) : 0.f;
-  int ci_base = 0;
-  for (int s = 0; s < p.nsrc; ++s) {
-    const PwSource& S = p.src[s];
-    const int ncb = (S.C + 7) / 8;
-    for (int cb = 0; cb < ncb; ++cb) {
-      float x[8];
-      if (valid) {
+  for (int j = 0; j < PW_CO; ++j) { st1[j] = 0.f; st2[j] = 0.f; }
+  const bool want_stats = p.stats_out != nullptr;
+#pragma unroll 1
+  for (int it = 0; it < PW_IT; ++it) {
+    const long long v = (blockIdx.x * static_cast<long long>(PW_IT) + it) * blockDim.x + threadIdx.x;
+    if (v >= p.vox) break;
+    float acc[PW_CO];
+#pragma unroll
+    for (int j = 0; j < PW_CO; ++j) acc[j] = (p.bias && co0 + j < p.cout) ? __ldg(&p.bias[co0 + j]) : 0.f;
+    int base = 0;
+    for (int s = 0; s < p.nsrc; ++s) {
+      const PwSource& S = p.src[s];
+      const int ncb = (S.C + 7) / 8;
+      const bool norm = S.stats != nullptr;
+      for (int cb = 0; cb < ncb; ++cb) {
+        float x[8];
         const size_t off = ((static_cast<size_t>(n) * S.cb_total + S.cb_off + cb) * p.vox + v) * 8;
         if (S.raw) load8f(S.raw, off, x); else load8(S.hi, S.lo, off, x);
-      } else {
+        const float* mr = s_mean + base + cb * 8;
+        if (norm) {
+          const float* rr = s_rstd + base + cb * 8;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) x[j] = 0.f;
-      }
+          for (int j = 0; j < 8; ++j) x[j] = (x[j] - mr[j]) * rr[j];
+        }
+        act8(x, S.act);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int c = cb * 8 + j;
-        if (c < S.C) {
-          const float xv = act_apply((x[j] - s_mean[ci_base + c]) * s_rstd[ci_base + c], S.act);
-          const float4* wr = reinterpret_cast<const float4*>(&wsm[(ci_base + c) * PW_CO]);
+        for (int j = 0; j < 8; ++j) {
+          const float4* wr = reinterpret_cast<const float4*>(&wsm[(base + cb * 8 + j) * PW_CO]);
 #pragma unroll
           for (int q = 0; q < PW_CO / 4; ++q) {
             const float4 w4 = wr[q];
-            acc[4 * q + 0] = fmaf(xv, w4.x, acc[4 * q + 0]);
-            acc[4 * q + 1] = fmaf(xv, w4.y, acc[4 * q + 1]);
-            acc[4 * q + 2] = fmaf(xv, w4.z, acc[4 * q + 2]);
-            acc[4 * q + 3] = fmaf(xv, w4.w, acc[4 * q + 3]);
+            acc[4 * q + 0] = fmaf(x[j], w4.x, acc[4 * q + 0]);
+            acc[4 * q + 1] = fmaf(x[j], w4.y, acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(x[j], w4.z, acc[4 * q + 2]);
+            acc[4 * q + 3] = fmaf(x[j], w4.w, acc[4 * q + 3]);
           }
         }
       }
+      base += ncb * 8;
     }
-    ci_base += S.C;
-  }
+    if (p.out_act != ACT_NONE) {
 #pragma unroll
-  for (int j = 0; j < PW_CO; ++j) acc[j] = act_apply(acc[j], p.out_act);
-  if (valid) {
+      for (int j = 0; j < PW_CO; ++j) acc[j] = act_apply(acc[j], p.out_act);
+    }
     if (p.out_planar) {
 #pragma unroll
       for (int j = 0; j < PW_CO; ++j)
@@ -306,17 +365,21 @@ __global__ void __launch_bounds__(128) pointwise_kernel(const PointwiseParams p)
         *reinterpret_cast<float4*>(p.out_raw + off) = make_float4(y[0], y[1], y[2], y[3]);
         *reinterpret_cast<float4*>(p.out_raw + off + 4) = make_float4(y[4], y[5], y[6], y[7]);
       }
-      if (p.out_hi) store8(p.out_hi, p.out_lo, off, y);
+      if (p.out_hi) store8p(p.out_hi, p.out_lo, off, y);
+    }
+    if (want_stats) {
+#pragma unroll
+      for (int j = 0; j < PW_CO; ++j) { st1[j] += acc[j]; st2[j] = fmaf(acc[j], acc[j], st2[j]); }
     }
   }
-  if (p.stats_out) {
+  if (want_stats) {
 #pragma unroll
     for (int b = 0; b < PW_CO / 8; ++b) {
       if (co0 + b * 8 >= p.cout) break;          // block-uniform
-      float y[8];
+      float y1[8], y2[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) y[j] = acc[b * 8 + j];
-      block_accumulate_stats(y, valid, p.stats_out, static_cast<size_t>(n) * p.cout + co0 + b * 8);
+      for (int j = 0; j < 8; ++j) { y1[j] = st1[b * 8 + j]; y2[j] = st2[b * 8 + j]; }
+      block_accumulate_sums(y1, y2, p.stats_out, static_cast<size_t>(n) * p.cout + co0 + b * 8);
       __syncthreads();
     }
   }
@@ -736,7 +799,7 @@ extern "C" int dp_norm_act(const float* raw_f32, const void* raw_hi, const void*
   p.res_hi = static_cast<const __half*>(res_hi); p.res_lo = static_cast<const __half*>(res_lo); p.res_raw = res_raw;
   p.res_stats = res_stats; p.res_cb_total = res_cb_total; p.res_cb_off = res_cb_off; p.act_after_res = act_after_res;
   p.out_hi = static_cast<__half*>(out_hi); p.out_lo = static_cast<__half*>(out_lo); p.out_cb_total = out_cb_total;
-  p.out_cb_off = out_cb_off; p.stats_out = stats_out; p.C = C; p.ncb = (C + 7) / 8; p.vox = vox;
+  p.out_cb_off = out_cb_off; p.stats_out = stats_out; p.C = C; p.ncb = (C + 7) / 8; p.vox = vox; p.inv_vox = 1.0 / static_cast<double>(vox);
   p.s2d_hi = static_cast<__half*>(s2d_hi); p.s2d_lo = static_cast<__half*>(s2d_lo); p.s2d_cb_total = s2d_cb_total;
   p.s2d_cb_off = s2d_cb_off; p.D = D; p.H = H > 0 ? H : 1; p.W = W > 0 ? W : 1;
   dim3 grid(blocks_for(vox, 256 * NA_IT), N * p.ncb);
@@ -764,18 +827,20 @@ extern "C" int dp_pointwise_conv(int nsrc, const void* const* src_hi, const void
     DP_REQUIRE(p.src[s].hi || p.src[s].raw, "dp_pointwise_conv: source %d has no tensor", s);
     cin += src_C[s];
   }
-  p.w = w; p.bias = bias; p.cin_total = cin; p.cout = cout; p.vox = vox;
+  p.w = w; p.bias = bias; p.cin_total = cin; p.cout = cout; p.vox = vox; p.inv_vox = 1.0 / static_cast<double>(vox);
   p.out_raw = out_raw; p.out_hi = static_cast<__half*>(out_hi); p.out_lo = static_cast<__half*>(out_lo);
   p.out_cb_total = out_cb_total; p.out_cb_off = out_cb_off; p.out_planar = out_planar; p.stats_out = stats_out;
   p.out_act = out_act;
-  const size_t smem = static_cast<size_t>(cin) * (PW_CO + 2) * sizeof(float);
+  int cin_pad = 0;
+  for (int s = 0; s < nsrc; ++s) cin_pad += ((src_C[s] + 7) / 8) * 8;
+  const size_t smem = static_cast<size_t>(cin_pad) * (PW_CO + 2) * sizeof(float);
   DP_REQUIRE(smem <= 96 * 1024, "dp_pointwise_conv: C_in=%d too large", cin);
   static size_t configured = 48 * 1024;
   if (smem > configured) {
     DP_CHECK(cudaFuncSetAttribute(pointwise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     configured = 96 * 1024;
   }
-  dim3 grid(blocks_for(vox, 128), (cout + PW_CO - 1) / PW_CO, N);
+  dim3 grid(blocks_for(vox, 128 * PW_IT), (cout + PW_CO - 1) / PW_CO, N);
   pointwise_kernel<<<grid, 128, smem, stream>>>(p);
   DP_CHECK(cudaGetLastError());
   return 0;

@@ -153,13 +153,13 @@ struct NormBwdParams {
   int phase;             // 0: reductions into bsum;  1: apply
   __half* dx_hi; float* dx_f32; int dx_cb_total, dx_cb_off;
   __half* dres_hi; float* dres_f32; int dres_cb_total, dres_cb_off;
-  int C, ncb; long long vox;
+  int C, ncb; long long vox; double inv_vox;
 };
 constexpr int NB_IT = 4;
 
 __global__ void __launch_bounds__(256) norm_act_bwd_kernel(const NormBwdParams p) {
   const int cb = blockIdx.y % p.ncb, n = blockIdx.y / p.ncb;
-  const double inv = 1.0 / static_cast<double>(p.vox);
+  const double inv = p.inv_vox;
   __shared__ float s_mean[2][8], s_rstd[2][8], s_sum[4][8], s_g[8], s_b[8];
   if (threadIdx.x < 16) {
     const int which = threadIdx.x >> 3, j = threadIdx.x & 7, c = cb * 8 + j;
@@ -1009,7 +1009,7 @@ extern "C" int dp_norm_act_bwd(const float* raw_f32, const void* raw_hi, const v
   p.bsum = bsum; p.phase = phase;
   p.dx_hi = static_cast<__half*>(dx_hi); p.dx_f32 = dx_f32; p.dx_cb_total = dx_cb_total; p.dx_cb_off = dx_cb_off;
   p.dres_hi = static_cast<__half*>(dres_hi); p.dres_f32 = dres_f32; p.dres_cb_total = dres_cb_total; p.dres_cb_off = dres_cb_off;
-  p.C = C; p.ncb = (C + 7) / 8; p.vox = vox;
+  p.C = C; p.ncb = (C + 7) / 8; p.vox = vox; p.inv_vox = 1.0 / static_cast<double>(vox);
   dim3 grid(nblk(vox, 256 * NB_IT), static_cast<unsigned>(N * p.ncb));
   norm_act_bwd_kernel<<<grid, 256, 0, stream>>>(p);
   return check_cuda(cudaGetLastError(), "norm_act_bwd");
