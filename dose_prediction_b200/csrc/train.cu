@@ -157,7 +157,38 @@ struct NormBwdParams {
 };
 constexpr int NB_IT = 4;
 
-__global__ void __launch_bounds__(256) norm_act_bwd_kernel(const NormBwdParams p) {
+// d act(t)/dt for 8 values with one switch (the per-element switch dominated the instruction count)
+__device__ __forceinline__ void act_grad8(const float (&t)[8], int act, float (&d)[8]) {
+  switch (act) {
+    case ACT_RELU:
+#pragma unroll
+      for (int j = 0; j < 8; ++j) d[j] = t[j] > 0.f ? 1.f : 0.f;
+      break;
+    case ACT_LRELU:
+#pragma unroll
+      for (int j = 0; j < 8; ++j) d[j] = t[j] > 0.f ? 1.f : 0.01f;
+      break;
+    case ACT_MISH:
+#pragma unroll
+      for (int j = 0; j < 8; ++j) d[j] = act_grad(t[j], ACT_MISH);
+      break;
+    case ACT_GELU:
+#pragma unroll
+      for (int j = 0; j < 8; ++j) d[j] = act_grad(t[j], ACT_GELU);
+      break;
+    default:
+#pragma unroll
+      for (int j = 0; j < 8; ++j) d[j] = 1.f;
+      break;
+  }
+}
+__device__ __forceinline__ void act_fwd8(float (&y)[8], int act) {
+  if (act == ACT_NONE) return;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) y[j] = act_apply(y[j], act);
+}
+
+__global__ void __launch_bounds__(256, 2) norm_act_bwd_kernel(const NormBwdParams p) {
   const int cb = blockIdx.y % p.ncb, n = blockIdx.y / p.ncb;
   const double inv = p.inv_vox;
   __shared__ float s_mean[2][8], s_rstd[2][8], s_sum[4][8], s_g[8], s_b[8];
@@ -166,6 +197,7 @@ __global__ void __launch_bounds__(256) norm_act_bwd_kernel(const NormBwdParams p
     const double* st = which ? p.res_stats : p.stats;
     float m = 0.f, r = 1.f;
     if (st != nullptr && c < p.C) t_finalize(st, static_cast<size_t>(n) * p.C + c, inv, m, r);
+    if (c >= p.C) r = 0.f;            // padded channels: every product below becomes 0 (their upstream gradient is 0 too)
     s_mean[which][j] = m;
     s_rstd[which][j] = r;
     if (which == 0) {
@@ -181,61 +213,72 @@ __global__ void __launch_bounds__(256) norm_act_bwd_kernel(const NormBwdParams p
   }
   __syncthreads();
   const bool has_res = p.res_hi || p.res_raw;
+  const bool affine = p.gamma != nullptr;
+  const bool res_norm = p.res_stats != nullptr;
+  const bool main_norm = p.stats != nullptr;
   float acc[6][8];
 #pragma unroll
   for (int k = 0; k < 6; ++k)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[k][j] = 0.f;
+  const size_t in_base = (static_cast<size_t>(n) * p.in_cb_total + p.in_cb_off + cb) * p.vox;
 #pragma unroll 1
   for (int it = 0; it < NB_IT; ++it) {
     const long long v = (blockIdx.x * static_cast<long long>(NB_IT) + it) * blockDim.x + threadIdx.x;
-    if (v >= p.vox) continue;
-    float x[8], g[8], e[8], gt[8], gz[8];
-    const size_t in_off = ((static_cast<size_t>(n) * p.in_cb_total + p.in_cb_off + cb) * p.vox + v) * 8;
-    if (p.raw_f32) t_load8f(p.raw_f32, in_off, x); else t_load8(p.raw_hi, p.raw_lo, in_off, x);
+    if (v >= p.vox) break;
+    float x[8], g[8], e[8], t[8], d[8];
+    if (p.raw_f32) t_load8f(p.raw_f32, (in_base + v) * 8, x); else t_load8(p.raw_hi, p.raw_lo, (in_base + v) * 8, x);
     load_grad8(p.dy, n, cb, p.vox, v, g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      x[j] = (x[j] - s_mean[0][j]) * s_rstd[0][j];                    // xh
+      t[j] = affine ? fmaf(x[j], s_g[j], s_b[j]) : x[j];
+    }
     if (has_res) {
       const size_t r_off = ((static_cast<size_t>(n) * p.res_cb_total + p.res_cb_off + cb) * p.vox + v) * 8;
       if (p.res_raw) t_load8f(p.res_raw, r_off, e); else t_load8(p.res_hi, p.res_lo, r_off, e);
-    }
+      float z[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = cb * 8 + j;
-      if (c >= p.C) { x[j] = 0.f; gt[j] = 0.f; gz[j] = 0.f; e[j] = 0.f; continue; }
-      x[j] = (x[j] - s_mean[0][j]) * s_rstd[0][j];                    // xh
-      const float t = fmaf(x[j], s_g[j], s_b[j]);
-      float gg = g[j];
-      if (has_res) {
-        e[j] = (e[j] - s_mean[1][j]) * s_rstd[1][j];                  // eh
-        gg *= act_grad(act_apply(t, p.act) + e[j], p.act_after_res);
-      }
-      gz[j] = gg;
-      const float g0 = gg * act_grad(t, p.act);
-      acc[4][j] += g0 * x[j];
-      acc[5][j] += g0;
-      gt[j] = g0 * s_g[j];
+      for (int j = 0; j < 8; ++j) { e[j] = (e[j] - s_mean[1][j]) * s_rstd[1][j]; z[j] = t[j]; }     // eh
+      act_fwd8(z, p.act);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) z[j] += e[j];
+      act_grad8(z, p.act_after_res, d);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] *= d[j];                        // gz
     }
+    act_grad8(t, p.act, d);
+    float gt[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) gt[j] = g[j] * d[j];                   // g0
     if (p.phase == 0) {
+      if (affine) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        acc[0][j] += gt[j];
-        acc[1][j] = fmaf(gt[j], x[j], acc[1][j]);
-        acc[2][j] += gz[j];
-        acc[3][j] = fmaf(gz[j], e[j], acc[3][j]);
+        for (int j = 0; j < 8; ++j) { acc[4][j] = fmaf(gt[j], x[j], acc[4][j]); acc[5][j] += gt[j]; gt[j] *= s_g[j]; }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { acc[0][j] += gt[j]; acc[1][j] = fmaf(gt[j], x[j], acc[1][j]); }
+      if (res_norm) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { acc[2][j] += g[j]; acc[3][j] = fmaf(g[j], e[j], acc[3][j]); }
       }
     } else {
+      if (affine) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) gt[j] *= s_g[j];
+      }
       float o[8];
       if (p.dx_hi || p.dx_f32) {
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          o[j] = p.stats ? s_rstd[0][j] * (gt[j] - s_sum[0][j] - x[j] * s_sum[1][j]) : gt[j];
+          o[j] = main_norm ? s_rstd[0][j] * (gt[j] - s_sum[0][j] - x[j] * s_sum[1][j]) : gt[j];
         const size_t off = ((static_cast<size_t>(n) * p.dx_cb_total + p.dx_cb_off + cb) * p.vox + v) * 8;
         if (p.dx_hi) t_store8h(p.dx_hi, off, o); else t_store8f(p.dx_f32, off, o);
       }
       if (has_res && (p.dres_hi || p.dres_f32)) {
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          o[j] = p.res_stats ? s_rstd[1][j] * (gz[j] - s_sum[2][j] - e[j] * s_sum[3][j]) : gz[j];
+          o[j] = res_norm ? s_rstd[1][j] * (g[j] - s_sum[2][j] - e[j] * s_sum[3][j]) : g[j];
         const size_t off = ((static_cast<size_t>(n) * p.dres_cb_total + p.dres_cb_off + cb) * p.vox + v) * 8;
         if (p.dres_hi) t_store8h(p.dres_hi, off, o); else t_store8f(p.dres_f32, off, o);
       }
