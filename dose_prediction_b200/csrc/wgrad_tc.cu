@@ -23,13 +23,15 @@
 namespace dp {
 
 constexpr int kWgThreads = 192;
-constexpr int kWgXStages = 4;
+constexpr int kWgXStages = 6;
 
 struct WgradTcParams {
   int N, D, H, W, Ci, Co, k;
   uint8_t chunk_cb[64]; int16_t chunk_ci0[64]; uint8_t chunk_nci[64]; int n_chunks;
   int g_cb_off;
   int w_tile, n_wt, rb, n_hb;     // voxels per W tile, tiles per row, x rows per block, blocks per plane
+  int xr;                         // x rows per TMA stage (several for narrow volumes: the per-row barrier round trip
+                                  // is what limits the deep decoder levels, not the MMAs)
   int kdp, n_kdg;                 // depth taps per CTA, number of depth-tap groups
   int splits; long long wsize; float* ws; int* err_flag;
   uint32_t g_plane_bytes, g_buf_bytes, x_stage_bytes, x_box_bytes;
@@ -103,7 +105,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_con
                       &g_full[buf], w0 * 2, p.g_cb_off + cot * 2, h0 - P, dg, n);
         }
         const int rows = min(p.rb, p.H - h0);
-        for (int i = 0; i < rows; ++i) {
+        for (int i = 0; i < rows; i += p.xr) {
           if (!mbar_wait_relaxed(&x_empty[xs], xph ^ 1, p.err_flag)) break;
           mbar_arrive_expect_tx(&x_full[xs], p.x_box_bytes);
           tma_load_5d(x_buf + xs * static_cast<size_t>(p.x_stage_bytes), &x_map, &x_full[xs], (w0 - P) * 2,
@@ -133,25 +135,30 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_con
         if (!mbar_wait(&g_full[buf], gph, p.err_flag)) break;
         const uint32_t gb = smem_u32(g_buf + buf * static_cast<size_t>(p.g_buf_bytes));
         const int rows = min(p.rb, p.H - h0);
-        for (int i = 0; i < rows; ++i) {
+        for (int i0 = 0; i0 < rows; i0 += p.xr) {
           if (!mbar_wait(&x_full[xs], xph, p.err_flag)) { ok = false; break; }
           tc_fence_after();
-          const uint32_t xb = smem_u32(x_buf + xs * static_cast<size_t>(p.x_stage_bytes));
-          for (int kdi = 0; kdi < n_kd; ++kdi) {
-            const int dg = d - (kd0 + kdi) + P;
-            if (dg < 0 || dg >= p.D) continue;               // all-zero plane
+          const uint32_t xs_base = smem_u32(x_buf + xs * static_cast<size_t>(p.x_stage_bytes));
+          const int nr = min(p.xr, rows - i0);
+          for (int r = 0; r < nr; ++r) {
+            const int i = i0 + r;
+            const uint32_t xb = xs_base + static_cast<uint32_t>(r) * 2 * x_cb_bytes;
+            for (int kdi = 0; kdi < n_kd; ++kdi) {
+              const int dg = d - (kd0 + kdi) + P;
+              if (dg < 0 || dg >= p.D) continue;               // all-zero plane
 #pragma unroll 1
-            for (int cb = 0; cb < 2; ++cb) {
-              const int acc = kdi * 2 + cb;
-              const uint32_t tcol = tmem_base + static_cast<uint32_t>(acc * ncols);
-              uint32_t accum = (started >> acc) & 1u;
-              for (int ks = 0; ks < ksteps; ++ks) {
-                const uint64_t da = make_smem_desc(xb + cb * x_cb_bytes + ks * 256, 128, 16, 0);
-                const uint64_t db = make_smem_desc(gb + kdi * p.g_plane_bytes + i * g_row_bytes + ks * 256, 128, g_cob_bytes, 0);
-                umma_f16_ss(tcol, da, db, idesc, accum);
-                accum = 1;
+              for (int cb = 0; cb < 2; ++cb) {
+                const int acc = kdi * 2 + cb;
+                const uint32_t tcol = tmem_base + static_cast<uint32_t>(acc * ncols);
+                uint32_t accum = (started >> acc) & 1u;
+                for (int ks = 0; ks < ksteps; ++ks) {
+                  const uint64_t da = make_smem_desc(xb + cb * x_cb_bytes + ks * 256, 128, 16, 0);
+                  const uint64_t db = make_smem_desc(gb + kdi * p.g_plane_bytes + i * g_row_bytes + ks * 256, 128, g_cob_bytes, 0);
+                  umma_f16_ss(tcol, da, db, idesc, accum);
+                  accum = 1;
+                }
+                started |= 1u << acc;
               }
-              started |= 1u << acc;
             }
           }
           umma_commit(&x_empty[xs]);
@@ -242,7 +249,8 @@ extern "C" int dp_conv3d_wgrad_tc(const void* x_c8, int x_cb_total, const uint8_
   p.n_hb = (H + p.rb - 1) / p.rb;
   p.g_plane_bytes = static_cast<uint32_t>(g_rows) * row_bytes;
   p.g_buf_bytes = (p.g_plane_bytes * p.kdp + 1023u) & ~1023u;
-  p.x_box_bytes = static_cast<uint32_t>(2 * (p.w_tile + 16) * 16);     // what one x TMA box transfers
+  p.xr = std::max(1, std::min(8, 64 / p.w_tile));
+  p.x_box_bytes = static_cast<uint32_t>(p.xr * 2 * (p.w_tile + 16) * 16);     // what one x TMA box transfers
   p.x_stage_bytes = (p.x_box_bytes + 1023u) & ~1023u;
 
   CUtensorMap x_map, g_map;
@@ -251,7 +259,7 @@ extern "C" int dp_conv3d_wgrad_tc(const void* x_c8, int x_cb_total, const uint8_
     const uint64_t dims[5] = {static_cast<uint64_t>(W) * 2, static_cast<uint64_t>(x_cb_total), static_cast<uint64_t>(H),
                               static_cast<uint64_t>(D), static_cast<uint64_t>(N)};
     const uint64_t strides[4] = {vox16, static_cast<uint64_t>(W) * 16, static_cast<uint64_t>(H) * W * 16, vox16 * x_cb_total};
-    const uint32_t box[5] = {static_cast<uint32_t>((p.w_tile + 16) * 2), 2, 1, 1, 1};
+    const uint32_t box[5] = {static_cast<uint32_t>((p.w_tile + 16) * 2), 2, static_cast<uint32_t>(p.xr), 1, 1};
     if (int rc = encode_tiled(&x_map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 5, x_c8, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE))
       return rc;
   }
