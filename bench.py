@@ -413,6 +413,11 @@ def main():
                 "unit": "TFLOP/s", "frac": ach / peaks["tflops"], "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write)",
                 "peak_source": peaks["source"], "launches_per_step": top["n"], "avg_launch_ms": avg_ms,
                 "algorithmic_flops_per_launch": top["flops"], "share_of_step": top["ms"] / total_fam}
+    # HBM-bound fused kernels: algorithmic bytes (every input and output moved once) / summed launch time
+    hbm_families = [{"kernel": k, "bound": "hbm", "achieved": plan.bytes[k] / (fam[k]["ms"] / 1e3) / 1e9, "peak": peaks["hbm_gbs"],
+                     "unit": "GB/s", "frac": plan.bytes[k] / (fam[k]["ms"] / 1e3) / 1e9 / peaks["hbm_gbs"],
+                     "algorithmic_bytes_per_step": plan.bytes[k], "ms_per_step": fam[k]["ms"], "launches_per_step": fam[k]["launches"]}
+                    for k in sorted(plan.bytes, key=lambda k: -fam.get(k, {"ms": 0})["ms"]) if k in fam and fam[k]["ms"] > 0]
     conv_fl = plan.flops.get("dp_conv3d_stack", 0.0) + plan.flops.get("dp_conv3d_tc", 0.0)
     conv_ms = fam.get("dp_conv3d_stack", {}).get("ms", 0.0) + fam.get("dp_conv3d_tc", {}).get("ms", 0.0)
     conv_pct = conv_fl / (conv_ms / 1e3) / 1e12 / peaks["tflops"] if conv_ms > 0 else 0.0
@@ -434,6 +439,7 @@ def main():
                         "h2d_bytes_per_step": 2 * B * S ** 3 * 4, "d2h_bytes_per_step": B * S ** 3 * 4},
                 "gpu_launches": plan.launches * args.steps, "launches_per_step": plan.launches,
                 "roofline": roofline, "roofline_families": roofline_family, "conv_frac_of_tensor_peak": conv_pct,
+                "roofline_hbm_families": hbm_families,
                 "kernel_ms_per_step": {k: round(v["ms"], 3) for k, v in sorted(fam.items())},
                 "clocks": clocks}
         if world == 1 and not args.no_cpu_baseline and not args.sw_roi:

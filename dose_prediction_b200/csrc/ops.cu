@@ -385,6 +385,115 @@ __global__ void __launch_bounds__(128, 6) pointwise_kernel(const PointwiseParams
   }
 }
 
+// ------------------------------------------------------------------ 1x1x1 convolution, weights in the constant bank
+// ncu on pointwise_kernel: the 128 LDS.128 weight fetches per voxel saturate the shared-memory return path (512 B
+// per warp instruction even when every lane reads the same address), 3-4x more time than the FMAs need.  For the
+// inference plans the weights are known on the host, so this variant receives the 16 output channels' weights of
+// one pass as KERNEL PARAMETERS: they sit in the constant bank and are consumed directly as FFMA operands (no load
+// instruction at all).  NCB = padded input channel blocks (compile time, so every weight offset is an immediate).
+struct PwBlock {
+  const __half* hi; const __half* lo; const float* raw;   // already offset to this channel block of image 0
+  long long n_stride;                                      // elements between images
+  const double* stats; int stat_c0, stat_C;                // instance statistics of the source (or null), channel of j = 0
+  int act;
+};
+template <int NCB>
+struct PwConstParams {
+  PwBlock blk[NCB];
+  float w[NCB * 8][PW_CO];
+  float bias[PW_CO];
+  int cout, co0;
+  long long vox; double inv_vox;
+  float* out_raw; int out_cb_total, out_cb_off;
+  __half* out_hi; __half* out_lo;
+  float* out_planar;
+  double* stats_out;
+  int out_act;
+};
+
+template <int NCB>
+__global__ void __launch_bounds__(128, 6) pointwise_cw_kernel(const __grid_constant__ PwConstParams<NCB> p) {
+  __shared__ __align__(16) float s_mean[NCB * 8], s_rstd[NCB * 8];
+  const int n = blockIdx.z;
+  const int co0 = p.co0;
+  for (int i = threadIdx.x; i < NCB * 8; i += blockDim.x) {
+    const PwBlock& B = p.blk[i >> 3];
+    const int c = B.stat_c0 + (i & 7);
+    float m = 0.f, r = 1.f;
+    if (B.stats && c < B.stat_C) finalize_stats(B.stats, static_cast<size_t>(n) * B.stat_C + c, p.inv_vox, m, r);
+    s_mean[i] = m;
+    s_rstd[i] = r;
+  }
+  __syncthreads();
+  float st1[PW_CO], st2[PW_CO];
+#pragma unroll
+  for (int j = 0; j < PW_CO; ++j) { st1[j] = 0.f; st2[j] = 0.f; }
+  const bool want_stats = p.stats_out != nullptr;
+#pragma unroll 1
+  for (int it = 0; it < PW_IT; ++it) {
+    const long long v = (blockIdx.x * static_cast<long long>(PW_IT) + it) * blockDim.x + threadIdx.x;
+    if (v >= p.vox) break;
+    float acc[PW_CO];
+#pragma unroll
+    for (int j = 0; j < PW_CO; ++j) acc[j] = p.bias[j];
+#pragma unroll
+    for (int b = 0; b < NCB; ++b) {
+      const PwBlock& B = p.blk[b];
+      float x[8];
+      const size_t off = static_cast<size_t>(n) * B.n_stride + static_cast<size_t>(v) * 8;
+      if (B.raw) load8f(B.raw, off, x); else load8(B.hi, B.lo, off, x);
+      if (B.stats) {
+        const float4 m0 = *reinterpret_cast<const float4*>(&s_mean[b * 8]), m1 = *reinterpret_cast<const float4*>(&s_mean[b * 8 + 4]);
+        const float4 r0 = *reinterpret_cast<const float4*>(&s_rstd[b * 8]), r1 = *reinterpret_cast<const float4*>(&s_rstd[b * 8 + 4]);
+        x[0] = (x[0] - m0.x) * r0.x; x[1] = (x[1] - m0.y) * r0.y; x[2] = (x[2] - m0.z) * r0.z; x[3] = (x[3] - m0.w) * r0.w;
+        x[4] = (x[4] - m1.x) * r1.x; x[5] = (x[5] - m1.y) * r1.y; x[6] = (x[6] - m1.z) * r1.z; x[7] = (x[7] - m1.w) * r1.w;
+      }
+      act8(x, B.act);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int q = 0; q < PW_CO; ++q) acc[q] = fmaf(x[j], p.w[b * 8 + j][q], acc[q]);
+    }
+    if (p.out_act != ACT_NONE) {
+#pragma unroll
+      for (int j = 0; j < PW_CO; ++j) acc[j] = act_apply(acc[j], p.out_act);
+    }
+    if (p.out_planar) {
+#pragma unroll
+      for (int j = 0; j < PW_CO; ++j)
+        if (co0 + j < p.cout) p.out_planar[(static_cast<size_t>(n) * p.cout + co0 + j) * p.vox + v] = acc[j];
+    }
+#pragma unroll
+    for (int b = 0; b < PW_CO / 8; ++b) {
+      if (co0 + b * 8 >= p.cout) break;
+      const size_t off = ((static_cast<size_t>(n) * p.out_cb_total + p.out_cb_off + (co0 >> 3) + b) * p.vox + v) * 8;
+      float y[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) y[j] = acc[b * 8 + j];
+      if (p.out_raw) {
+        *reinterpret_cast<float4*>(p.out_raw + off) = make_float4(y[0], y[1], y[2], y[3]);
+        *reinterpret_cast<float4*>(p.out_raw + off + 4) = make_float4(y[4], y[5], y[6], y[7]);
+      }
+      if (p.out_hi) store8p(p.out_hi, p.out_lo, off, y);
+    }
+    if (want_stats) {
+#pragma unroll
+      for (int j = 0; j < PW_CO; ++j) { st1[j] += acc[j]; st2[j] = fmaf(acc[j], acc[j], st2[j]); }
+    }
+  }
+  if (want_stats) {
+#pragma unroll
+    for (int b = 0; b < PW_CO / 8; ++b) {
+      if (co0 + b * 8 >= p.cout) break;          // block-uniform
+      float y1[8], y2[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { y1[j] = st1[b * 8 + j]; y2[j] = st2[b * 8 + j]; }
+      block_accumulate_sums(y1, y2, p.stats_out, static_cast<size_t>(n) * p.cout + co0 + b * 8);
+      __syncthreads();
+    }
+  }
+}
+
 // ------------------------------------------------------------------ ConvTranspose3d k=2 s=2 (no bias)
 // out[n, co, 2d+i, 2h+j, 2w+l] = sum_ci in[n, ci, d, h, w] * W[ci, co, i, j, l]
 struct DeconvParams {
@@ -844,6 +953,86 @@ extern "C" int dp_pointwise_conv(int nsrc, const void* const* src_hi, const void
   pointwise_kernel<<<grid, 128, smem, stream>>>(p);
   DP_CHECK(cudaGetLastError());
   return 0;
+}
+
+template <int NCB>
+static int launch_pointwise_cw(int nsrc, const void* const* src_hi, const void* const* src_lo, const float* const* src_raw,
+                               const int* src_cb_total, const int* src_cb_off, const int* src_C,
+                               const double* const* src_stats, const int* src_act, const float* w_host, const float* bias_host,
+                               int cin, int cout, int N, long long vox, float* out_raw, void* out_hi, void* out_lo,
+                               int out_cb_total, int out_cb_off, float* out_planar, double* stats_out, int out_act,
+                               cudaStream_t stream) {
+  PwConstParams<NCB> p{};
+  int b = 0;
+  int lbase[NCB];
+  for (int s = 0; s < nsrc; ++s) {
+    const int nb = (src_C[s] + 7) / 8;
+    int l0 = 0;
+    for (int t = 0; t < s; ++t) l0 += src_C[t];
+    for (int cb = 0; cb < nb; ++cb, ++b) {
+      PwBlock& B = p.blk[b];
+      const size_t blk_off = static_cast<size_t>(src_cb_off[s] + cb) * vox * 8;
+      B.hi = src_hi[s] ? static_cast<const __half*>(src_hi[s]) + blk_off : nullptr;
+      B.lo = (src_lo && src_lo[s]) ? static_cast<const __half*>(src_lo[s]) + blk_off : nullptr;
+      B.raw = (src_raw && src_raw[s]) ? src_raw[s] + blk_off : nullptr;
+      B.n_stride = static_cast<long long>(src_cb_total[s]) * vox * 8;
+      B.stats = src_stats ? src_stats[s] : nullptr;
+      B.stat_c0 = cb * 8; B.stat_C = src_C[s];
+      B.act = src_act ? src_act[s] : 0;
+      lbase[b] = (cb * 8 < src_C[s]) ? l0 + cb * 8 : -1;
+      // logical channels of this block: l0 + cb*8 .. min(l0 + C, ...) ; remember how many are real
+      B.stat_C = src_C[s];
+    }
+  }
+  p.cout = cout; p.vox = vox; p.inv_vox = 1.0 / static_cast<double>(vox);
+  p.out_raw = out_raw; p.out_hi = static_cast<__half*>(out_hi); p.out_lo = static_cast<__half*>(out_lo);
+  p.out_cb_total = out_cb_total; p.out_cb_off = out_cb_off; p.out_planar = out_planar; p.stats_out = stats_out;
+  p.out_act = out_act;
+  dim3 grid(blocks_for(vox, 128 * PW_IT), 1, N);
+  for (int co0 = 0; co0 < cout; co0 += PW_CO) {
+    p.co0 = co0;
+    for (int bb = 0; bb < NCB; ++bb)
+      for (int j = 0; j < 8; ++j) {
+        const int valid_c = p.blk[bb].stat_C - p.blk[bb].stat_c0;           // real channels left in this block
+        for (int q = 0; q < PW_CO; ++q)
+          p.w[bb * 8 + j][q] = (j < valid_c && co0 + q < cout) ? w_host[static_cast<size_t>(co0 + q) * cin + lbase[bb] + j] : 0.f;
+      }
+    for (int q = 0; q < PW_CO; ++q) p.bias[q] = (bias_host && co0 + q < cout) ? bias_host[co0 + q] : 0.f;
+    pointwise_cw_kernel<NCB><<<grid, 128, 0, stream>>>(p);
+    DP_CHECK(cudaGetLastError());
+  }
+  return 0;
+}
+
+extern "C" int dp_pointwise_conv_cw(int nsrc, const void* const* src_hi, const void* const* src_lo, const float* const* src_raw,
+                                    const int* src_cb_total, const int* src_cb_off, const int* src_C,
+                                    const double* const* src_stats, const int* src_act, const float* w_host,
+                                    const float* bias_host, int cout, int N, long long vox, float* out_raw, void* out_hi,
+                                    void* out_lo, int out_cb_total, int out_cb_off, float* out_planar, double* stats_out,
+                                    int out_act, cudaStream_t stream) {
+  DP_REQUIRE(nsrc >= 1 && nsrc <= 3, "dp_pointwise_conv_cw: 1..3 sources supported, got %d", nsrc);
+  int cin = 0, ncb = 0;
+  for (int s = 0; s < nsrc; ++s) {
+    DP_REQUIRE(src_hi[s] || (src_raw && src_raw[s]), "dp_pointwise_conv_cw: source %d has no tensor", s);
+    cin += src_C[s];
+    ncb += (src_C[s] + 7) / 8;
+  }
+#define DP_PW_CW(NCB_)                                                                                                      \
+  return launch_pointwise_cw<NCB_>(nsrc, src_hi, src_lo, src_raw, src_cb_total, src_cb_off, src_C, src_stats, src_act, w_host, \
+                                   bias_host, cin, cout, N, vox, out_raw, out_hi, out_lo, out_cb_total, out_cb_off,          \
+                                   out_planar, stats_out, out_act, stream)
+  switch (ncb) {
+    case 1: DP_PW_CW(1);
+    case 2: DP_PW_CW(2);
+    case 3: DP_PW_CW(3);
+    case 4: DP_PW_CW(4);
+    case 6: DP_PW_CW(6);
+    case 8: DP_PW_CW(8);
+    default: break;
+  }
+#undef DP_PW_CW
+  set_error("dp_pointwise_conv_cw: %d input channel blocks not instantiated (1,2,3,4,6,8); use dp_pointwise_conv", ncb);
+  return 1;
 }
 
 extern "C" int dp_deconv2x(const void* in_hi, const void* in_lo, long long in_nstride, long long in_vstride,

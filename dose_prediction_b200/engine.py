@@ -23,6 +23,7 @@ ACT_ID = {None: ACT_NONE, "none": ACT_NONE, "relu": ACT_RELU, "lrelu": ACT_LRELU
 STATS_DOUBLES = 1 << 20
 STACK_TILES = int(os.environ.get("DP_STACK_TILES", "0"))
 FOLD_P3 = os.environ.get("DP_FOLD_P3", "1") != "0"
+POINTWISE_CW = os.environ.get("DP_POINTWISE_CW", "1") != "0"     # bring-up switch: constant-bank weights for static 1^3 convs
 STACKED_CONV = os.environ.get("DP_STACKED_CONV", "1") != "0"    # bring-up switch between the two tcgen05 conv kernels
 EPS = 1e-5
 
@@ -122,6 +123,7 @@ class Plan:
         self.flops = {}          # algorithmic FLOPs (2*MAC of the reference op) per kernel family, per replay
         self.step_flops = []     # the same per recorded launch (parallel to self.steps)
         self._pending_flops = 0.0
+        self.bytes = {}          # algorithmic HBM bytes (inputs + outputs once) per HBM-bound kernel family, per replay
         self.training = False    # training plans re-derive packed weights from the live parameters every step
         self.refresh = []        # (packed tensor, function returning its new value)
         self.refresh_launches = []   # (C entry point name, args): device-side re-packing of live parameters
@@ -237,6 +239,9 @@ class Plan:
                 _lib.check(rc, name)
             n += 1
         self.launches = n
+
+    def count_bytes(self, name, nbytes):
+        self.bytes[name] = self.bytes.get(name, 0.0) + float(nbytes)
 
     def count_flops(self, name, flops):
         """call right before the add() of the launch that performs `flops` algorithmic FLOPs."""
@@ -493,6 +498,13 @@ class Plan:
         ocb = ooff = 0
         if out is not None:
             oh, ol, ocb, ooff = out.hi_ptr, out.lo_ptr, out.cb_total, out.cb_off
+        cpad = ceil_div(C, 8) * 8
+
+        def _bytes(t):          # bytes per voxel-channel of a tensor as stored
+            if t is None:
+                return 0
+            return 4 if isinstance(t, Raw) else (4 if t.lo_off is not None else 2)
+        self.count_bytes("dp_norm_act", N * vox * cpad * (_bytes(src) + _bytes(res) + _bytes(out) + _bytes(s2d)))
         self.add("dp_norm_act", rf, rh, rl, icb, ioff, stats.data_ptr() if stats is not None else None,
                  gamma.data_ptr() if gamma is not None else None, beta.data_ptr() if beta is not None else None,
                  ACT_ID[act], eh, el, er, es, ecb, eoff, ACT_ID[act_after_res], oh, ol, ocb, ooff,
@@ -530,6 +542,28 @@ class Plan:
             oh, ol, ocb, ooff = out_act.hi_ptr, out_act.lo_ptr, out_act.cb_total, out_act.cb_off
         if out_planar is not None:
             op = out_planar.data_ptr()
+        in_b = sum((ceil_div(t.C, 8) * 8) * (4 if isinstance(t, Raw) or t.lo_off is not None else 2) for t, _, _ in srcs)
+        out_b = 0
+        if out_raw is not None:
+            out_b += 4 * ceil_div(Co, 8) * 8
+        if out_act is not None:
+            out_b += (4 if out_act.lo_off is not None else 2) * ceil_div(Co, 8) * 8
+        if out_planar is not None:
+            out_b += 4 * Co
+        ncb = sum(ceil_div(c, 8) for c in Cs)
+        use_cw = not self.training and ncb in (1, 2, 3, 4, 6, 8) and POINTWISE_CW
+        self.count_bytes("dp_pointwise_conv_cw" if use_cw else "dp_pointwise_conv", N * vox * (in_b * ceil_div(Co, 16) + out_b))
+        if use_cw:
+            # static weights: hand them over as kernel parameters (constant bank) instead of device pointers
+            wh = weight.detach().reshape(Co, -1).to("cpu", torch.float32).contiguous()
+            bh = bias.detach().to("cpu", torch.float32).contiguous() if bias is not None else None
+            wa = (ctypes.c_float * wh.numel())(*wh.flatten().tolist())
+            ba = (ctypes.c_float * Co)(*bh.tolist()) if bh is not None else None
+            self.keep.append((wa, ba))
+            self.add("dp_pointwise_conv_cw", len(srcs), *arrs, ctypes.cast(wa, ctypes.c_void_p),
+                     ctypes.cast(ba, ctypes.c_void_p) if ba is not None else None, Co, N, vox, of, oh, ol, ocb, ooff, op, st,
+                     ACT_ID[out_act_fn])
+            return
         self.add("dp_pointwise_conv", len(srcs), *arrs, w.data_ptr(), b.data_ptr() if b is not None else None, Co, N,
                  vox, of, oh, ol, ocb, ooff, op, st, ACT_ID[out_act_fn])
 
@@ -546,6 +580,9 @@ class Plan:
                      out.cb_total, out.cb_off, self.err.data_ptr())
             return
         w = self.derived(lambda: weight.detach().to(self.device, torch.float32).permute(2, 3, 4, 0, 1).reshape(8, Ci, Co))
+        n_in = (src.t.shape[0] * src.t.shape[1]) if isinstance(src, Tokens) else src.N * src.vox
+        in_bpc = 2 if isinstance(src, Tokens) or src.lo_off is None else 4
+        self.count_bytes("dp_deconv2x", n_in * (Ci * in_bpc + 8 * blocks16(Co) * 8 * (4 if out.lo_off is not None else 2)))
         if isinstance(src, Tokens):
             B, T, C = src.t.shape
             D, H, W = src.grid
@@ -563,6 +600,8 @@ class Plan:
 
     def upsample2x(self, src, out):
         D, H, W = src.dims
+        bpc = 4 if src.lo_off is not None else 2
+        self.count_bytes("dp_upsample2x", src.N * src.vox * ceil_div(src.C, 8) * 8 * bpc * (1 + 8))
         self.add("dp_upsample2x", src.hi_ptr, src.lo_ptr, src.cb_total, src.cb_off, ceil_div(src.C, 8), src.N, D, H, W,
                  out.hi_ptr, out.lo_ptr, out.cb_total, out.cb_off)
 
@@ -623,5 +662,7 @@ class Plan:
 
     def handoff(self, logits, ptv, ct, out, structures=None):
         N, ncls, S = logits.shape[0], logits.shape[1], logits.shape[2]
+        self.count_bytes("dp_handoff", N * S ** 3 * (4 * (ncls + 2) + 16 * (4 if out.lo_off is not None else 2)
+                                                     + (36 if structures is not None else 0)))
         self.add("dp_handoff", logits.data_ptr(), ncls, ptv.data_ptr(), ct.data_ptr(), N, S, out.hi_ptr, out.lo_ptr,
                  out.cb_total, out.cb_off, structures.data_ptr() if structures is not None else None)

@@ -121,6 +121,17 @@ int dp_pointwise_conv(int nsrc, const void* const* src_hi, const void* const* sr
                       int N, long long vox, float* out_raw, void* out_hi, void* out_lo, int out_cb_total,
                       int out_cb_off, float* out_planar, double* stats_out, int out_act, cudaStream_t stream);
 
+/* The same 1^3 convolution for weights that are known on the HOST at launch time (inference plans): w_host
+ * [cout][sum of source C] and bias_host [cout] (or NULL) are host pointers; 16 output channels' weights per launch
+ * travel as kernel parameters and are consumed from the constant bank as FFMA operands (no weight loads: the
+ * shared-memory return path was what bounded dp_pointwise_conv).  Padded input channel blocks (8 channels each, per
+ * source) must number 1, 2, 3, 4, 6 or 8.                                                                     */
+int dp_pointwise_conv_cw(int nsrc, const void* const* src_hi, const void* const* src_lo, const float* const* src_raw,
+                         const int* src_cb_total, const int* src_cb_off, const int* src_C,
+                         const double* const* src_stats, const int* src_act, const float* w_host, const float* bias_host,
+                         int cout, int N, long long vox, float* out_raw, void* out_hi, void* out_lo, int out_cb_total,
+                         int out_cb_off, float* out_planar, double* stats_out, int out_act, cudaStream_t stream);
+
 /* nn.ConvTranspose3d k=2 s=2 no bias (monai get_conv_layer(is_transposed=True): base_blocks.py:118-127,
  * UnetrPrUpBlock).  Input addressed by element strides so ViT tokens [B,T,C] are read in place
  * (proj_feat, dose_pyfer.py:118-122, becomes a no-op).  w_packed fp32 [8 parity][cin][cout].          */
