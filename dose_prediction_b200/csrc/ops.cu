@@ -37,15 +37,20 @@ __device__ __forceinline__ void load8f(const float* p, size_t off, float (&x)[8]
   x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
 }
 __device__ __forceinline__ void store8(__half* hi, __half* lo, size_t off, const float (&x)[8]) {
-  __align__(16) __half h[8];
-  __align__(16) __half l[8];
+  // hi = fp16(x), lo = fp16(x - hi), with the packed two-at-a-time conversions (same rounding as the scalar ones)
+  __align__(16) __half2 h[4];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    h[j] = __float2half_rn(x[j]);
-    l[j] = __float2half_rn(x[j] - __half2float(h[j]));
-  }
+  for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(x[2 * j], x[2 * j + 1]);
   *reinterpret_cast<uint4*>(hi + off) = *reinterpret_cast<const uint4*>(h);
-  if (lo != nullptr) *reinterpret_cast<uint4*>(lo + off) = *reinterpret_cast<const uint4*>(l);
+  if (lo != nullptr) {
+    __align__(16) __half2 l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(h[j]);
+      l[j] = __floats2half2_rn(x[2 * j] - f.x, x[2 * j + 1] - f.y);
+    }
+    *reinterpret_cast<uint4*>(lo + off) = *reinterpret_cast<const uint4*>(l);
+  }
 }
 
 // one switch per 8 values (the per-element switch of act_apply cost more instructions than the arithmetic)
@@ -549,6 +554,54 @@ __global__ void __launch_bounds__(128) deconv2x_kernel(const DeconvParams p) {
 #pragma unroll
       for (int t = 0; t < 8; ++t) y[t] = acc[b * 8 + t];
       store8(p.out_hi, p.out_lo, ((static_cast<size_t>(n) * p.out_cb_total + p.out_cb_off + (co0 >> 3) + b) * vox_out + vo) * 8, y);
+    }
+  }
+}
+
+// ConvTranspose3d k2 s2 with static weights in the constant bank (see pointwise_cw_kernel): the input vector of a
+// voxel stays in registers for all parities of the launch, weights are FFMA uniform operands, and a thread writes the
+// two W-neighbours (l = 0, 1) back to back so every 32-byte sector is filled by one thread.
+template <int NCB, int NPAR>
+struct DeconvConstParams {
+  const __half* in_hi; const __half* in_lo;
+  long long in_nstride, in_cbstride;                 // c8 input: element strides between images / channel blocks
+  int D, H, W, cout, co0, q0;                        // q0 = first parity of this launch
+  __half* out_hi; __half* out_lo; int out_cb_total, out_cb_off;
+  float w[NPAR][NCB * 8][DC_CO];
+};
+template <int NCB, int NPAR>
+__global__ void __launch_bounds__(128) deconv2x_cw_kernel(const __grid_constant__ DeconvConstParams<NCB, NPAR> p) {
+  const int n = blockIdx.z;
+  const long long vox_in = static_cast<long long>(p.D) * p.H * p.W;
+  const long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (v >= vox_in) return;
+  const int w = static_cast<int>(v % p.W), h = static_cast<int>((v / p.W) % p.H), d = static_cast<int>(v / (static_cast<long long>(p.W) * p.H));
+  float x[NCB][8];
+#pragma unroll
+  for (int cb = 0; cb < NCB; ++cb)
+    load8(p.in_hi, p.in_lo, static_cast<size_t>(n) * p.in_nstride + static_cast<size_t>(v) * 8 + cb * p.in_cbstride, x[cb]);
+  const long long vox_out = vox_in * 8;
+#pragma unroll
+  for (int qq = 0; qq < NPAR; ++qq) {
+    float acc[DC_CO];
+#pragma unroll
+    for (int j = 0; j < DC_CO; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int cb = 0; cb < NCB; ++cb)
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int t = 0; t < DC_CO; ++t) acc[t] = fmaf(x[cb][j], p.w[qq][cb * 8 + j][t], acc[t]);
+    const int q = p.q0 + qq;
+    const int i = q >> 2, j2 = (q >> 1) & 1, l = q & 1;
+    const long long vo = (static_cast<long long>(2 * d + i) * (2 * p.H) + (2 * h + j2)) * (2 * p.W) + (2 * w + l);
+#pragma unroll
+    for (int b = 0; b < DC_CO / 8; ++b) {
+      if (p.co0 + b * 8 >= p.cout) break;
+      float y[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) y[t] = acc[b * 8 + t];
+      store8p(p.out_hi, p.out_lo, ((static_cast<size_t>(n) * p.out_cb_total + p.out_cb_off + (p.co0 >> 3) + b) * vox_out + vo) * 8, y);
     }
   }
 }
@@ -1057,6 +1110,43 @@ extern "C" int dp_deconv2x(const void* in_hi, const void* in_lo, long long in_ns
   deconv2x_kernel<<<grid, 128, smem, stream>>>(p);
   DP_CHECK(cudaGetLastError());
   return 0;
+}
+
+template <int NCB, int NPAR>
+static int launch_deconv_cw(const void* in_hi, const void* in_lo, long long in_nstride, long long in_cbstride, int cout, int N,
+                            int D, int H, int W, const float* w_host, void* out_hi, void* out_lo, int out_cb_total,
+                            int out_cb_off, cudaStream_t stream) {
+  thread_local static DeconvConstParams<NCB, NPAR> p;      // 16 KB: kept off the stack; every launch copies it
+  p.in_hi = static_cast<const __half*>(in_hi); p.in_lo = static_cast<const __half*>(in_lo);
+  p.in_nstride = in_nstride; p.in_cbstride = in_cbstride; p.D = D; p.H = H; p.W = W; p.cout = cout;
+  p.out_hi = static_cast<__half*>(out_hi); p.out_lo = static_cast<__half*>(out_lo);
+  p.out_cb_total = out_cb_total; p.out_cb_off = out_cb_off;
+  const int cin = NCB * 8;
+  dim3 grid(blocks_for(static_cast<long long>(D) * H * W, 128), 1, N);
+  for (int co0 = 0; co0 < cout; co0 += DC_CO)
+    for (int q0 = 0; q0 < 8; q0 += NPAR) {
+      p.co0 = co0; p.q0 = q0;
+      for (int qq = 0; qq < NPAR; ++qq)
+        for (int ci = 0; ci < cin; ++ci)
+          for (int t = 0; t < DC_CO; ++t)
+            p.w[qq][ci][t] = (co0 + t < cout) ? w_host[(static_cast<size_t>(q0 + qq) * cin + ci) * cout + co0 + t] : 0.f;
+      deconv2x_cw_kernel<NCB, NPAR><<<grid, 128, 0, stream>>>(p);
+      DP_CHECK(cudaGetLastError());
+    }
+  return 0;
+}
+
+extern "C" int dp_deconv2x_cw(const void* in_hi, const void* in_lo, long long in_nstride, long long in_cbstride, int cin,
+                              int cout, int N, int D, int H, int W, const float* w_host_packed, void* out_hi, void* out_lo,
+                              int out_cb_total, int out_cb_off, cudaStream_t stream) {
+  if (cin == 32)
+    return launch_deconv_cw<4, 8>(in_hi, in_lo, in_nstride, in_cbstride, cout, N, D, H, W, w_host_packed, out_hi, out_lo,
+                                  out_cb_total, out_cb_off, stream);
+  if (cin == 64)
+    return launch_deconv_cw<8, 4>(in_hi, in_lo, in_nstride, in_cbstride, cout, N, D, H, W, w_host_packed, out_hi, out_lo,
+                                  out_cb_total, out_cb_off, stream);
+  set_error("dp_deconv2x_cw: C_in=%d not instantiated (32, 64); use dp_deconv2x", cin);
+  return 1;
 }
 
 extern "C" int dp_upsample2x(const void* in_hi, const void* in_lo, int in_cb_total, int in_cb_off, int ncb, int N, int D,

@@ -582,7 +582,9 @@ class Plan:
         w = self.derived(lambda: weight.detach().to(self.device, torch.float32).permute(2, 3, 4, 0, 1).reshape(8, Ci, Co))
         n_in = (src.t.shape[0] * src.t.shape[1]) if isinstance(src, Tokens) else src.N * src.vox
         in_bpc = 2 if isinstance(src, Tokens) or src.lo_off is None else 4
-        self.count_bytes("dp_deconv2x", n_in * (Ci * in_bpc + 8 * blocks16(Co) * 8 * (4 if out.lo_off is not None else 2)))
+        nb_ = n_in * (Ci * in_bpc + 8 * blocks16(Co) * 8 * (4 if out.lo_off is not None else 2))
+        cw_ = (not self.training) and (not isinstance(src, Tokens)) and Ci in (32, 64) and POINTWISE_CW
+        self.count_bytes("dp_deconv2x_cw" if cw_ else "dp_deconv2x", nb_)
         if isinstance(src, Tokens):
             B, T, C = src.t.shape
             D, H, W = src.grid
@@ -595,6 +597,13 @@ class Plan:
             vox = src.vox
             base = src.buf.data_ptr() + src.cb_off * vox * 16
             lo = None if src.lo_off is None else src.buf.data_ptr() + src.lo_off * vox * 16
+            if not self.training and Ci in (32, 64) and POINTWISE_CW:
+                wh = weight.detach().to("cpu", torch.float32).permute(2, 3, 4, 0, 1).reshape(-1).contiguous()
+                wa = (ctypes.c_float * wh.numel())(*wh.tolist())
+                self.keep.append(wa)
+                self.add("dp_deconv2x_cw", base, lo, src.cb_total * vox * 8, vox * 8, Ci, Co, src.N, D, H, W,
+                         ctypes.cast(wa, ctypes.c_void_p), out.hi_ptr, out.lo_ptr, out.cb_total, out.cb_off)
+                return
             self.add("dp_deconv2x", base, lo, src.cb_total * vox * 8, 8, vox * 8, Ci, Co, src.N, D, H, W, w.data_ptr(),
                      out.hi_ptr, out.lo_ptr, out.cb_total, out.cb_off)
 

@@ -139,6 +139,13 @@ int dp_deconv2x(const void* in_hi, const void* in_lo, long long in_nstride, long
                 long long in_cbstride, int cin, int cout, int N, int D, int H, int W, const float* w_packed,
                 void* out_hi, void* out_lo, int out_cb_total, int out_cb_off, cudaStream_t stream);
 
+/* dp_deconv2x for a c8 input and weights known on the HOST (w_host_packed fp32 [8 parity][cin][cout], host pointer):
+ * weights travel as kernel parameters (constant bank), the voxel's input vector stays in registers for all
+ * parities.  C_in in {32, 64}.                                                                                  */
+int dp_deconv2x_cw(const void* in_hi, const void* in_lo, long long in_nstride, long long in_cbstride, int cin, int cout,
+                   int N, int D, int H, int W, const float* w_host_packed, void* out_hi, void* out_lo, int out_cb_total,
+                   int out_cb_off, cudaStream_t stream);
+
 /* Same transposed convolution as a tcgen05 GEMM [B*Dg*Hg*Wg, cin] x [cin, 8*cout] with a pixel-shuffle
  * scatter epilogue; used when the input is a ViT token matrix [B, Dg*Hg*Wg, cin] fp16 (cin = 768).
  *   w_nk  fp16 [8*cout][cin], row (i*4+j*2+l)*cout + co = W[:, co, i, j, l]                           */
