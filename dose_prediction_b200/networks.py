@@ -341,7 +341,9 @@ class Precision:
 
 PREC_NET_A = Precision("p3", "p3", True)      # net_A dominates the dose error: ~22-bit operands
 PREC_NET_B = Precision("p1", "p1", False)     # fp16 operands everywhere
-PREC_SEG = Precision("p3", "p1", True)        # seg: fp16 on 7^3 convs and the ViT, ~22-bit elsewhere
+PREC_SEG = Precision("p3", "p1", True)        # seg: fp16 on 7^3 convs and the ViT, ~22-bit elsewhere ...
+PREC_SEG_DEEP = Precision("p1", "p1", False)  # ... except the two coarsest levels (<= 1/4 resolution): plain fp16
+                                              # (oracle/precision_probe.py: argmax agreement unchanged, 99.95 / 99.91 %)
 
 
 _S2D_TAPS = {0: ((1, 1),), 1: ((0, 0), (1, 2))}     # input parity -> ((tap of the 3^3 stride-1 conv, original tap), ...)
@@ -654,24 +656,25 @@ def _emit_up_block(P, blk, inp, skip_slot_pair, out, prec):
         _emit_conv_3_1(P, cov, skip_slot_pair, out, prec)
 
 
-def _emit_unetr(P, vit, enc_blocks, dec_blocks, parts, taps, prec):
+def _emit_unetr(P, vit, enc_blocks, dec_blocks, parts, taps, prec, prec_deep=None):
     """Shared UNETR-shaped body of MainSubsetModel.forward (dose_pyfer.py:311-319) and oar_transeg Model.forward
-    (oar_transeg.py:171-185).  enc_blocks = (res-block, prup2, prup3, prup4); dec_blocks from coarse to fine."""
+    (oar_transeg.py:171-185).  enc_blocks = (res-block, prup2, prup3, prup4); dec_blocks from coarse to fine.
+    prec_deep: precision recipe of the two coarsest levels (1/4 and 1/8 resolution), default = prec."""
     N, dims = parts[0].N, parts[0].dims
     fs = enc_blocks[0].layer.conv1.conv.weight.shape[0]
-    lo = prec.lo
+    precs = [prec, prec, prec_deep or prec, prec_deep or prec]          # per level, fine -> coarse
     z, hs = _emit_vit(P, vit, parts, N, dims, taps)
     sizes = [dims, tuple(d // 2 for d in dims), tuple(d // 4 for d in dims), tuple(d // 8 for d in dims)]
-    cats = [P.new_concat(N, [fs << i, fs << i], sizes[i], lo=lo) for i in range(4)]     # [deconv out | skip]
-    _emit_res_block(P, enc_blocks[0].layer, parts, cats[0][1], prec)
-    _emit_pr_up(P, enc_blocks[1], hs[taps[0]], cats[1][1], prec)
-    _emit_pr_up(P, enc_blocks[2], hs[taps[1]], cats[2][1], prec)
-    _emit_pr_up(P, enc_blocks[3], hs[taps[2]], cats[3][1], prec)
+    cats = [P.new_concat(N, [fs << i, fs << i], sizes[i], lo=precs[i].lo) for i in range(4)]     # [deconv out | skip]
+    _emit_res_block(P, enc_blocks[0].layer, parts, cats[0][1], precs[0])
+    _emit_pr_up(P, enc_blocks[1], hs[taps[0]], cats[1][1], precs[1])
+    _emit_pr_up(P, enc_blocks[2], hs[taps[1]], cats[2][1], precs[2])
+    _emit_pr_up(P, enc_blocks[3], hs[taps[2]], cats[3][1], precs[3])
     decs = []
     inp = z
     for lvl, blk in zip((3, 2, 1, 0), dec_blocks):
-        out = P.new_act(N, fs << lvl, sizes[lvl], lo=lo)
-        _emit_up_block(P, blk, inp, cats[lvl], out, prec)
+        out = P.new_act(N, fs << lvl, sizes[lvl], lo=precs[lvl].lo)
+        _emit_up_block(P, blk, inp, cats[lvl], out, precs[lvl])
         decs.append(out)
         inp = out
     return decs[::-1]          # [dec1 (full res), dec2, dec3, dec4]
@@ -942,7 +945,8 @@ class TRANSEG(OARTranseg):
 
 def emit_oar_transeg(P, model, x_act):
     decs = _emit_unetr(P, model.vit, (model.encoder1, model.encoder2, model.encoder3, model.encoder4),
-                       (model.decoder5, model.decoder4, model.decoder3, model.decoder2), [x_act], (3, 6, 9), PREC_SEG)
+                       (model.decoder5, model.decoder4, model.decoder3, model.decoder2), [x_act], (3, 6, 9), PREC_SEG,
+                       prec_deep=PREC_SEG_DEEP)
     d = decs[0]
     logits = P.zeros((d.N, model.out_channels) + d.dims, torch.float32)
     P.pointwise([(d, None, None)], model.out.conv.conv.weight, model.out.conv.conv.bias, out_planar=logits)

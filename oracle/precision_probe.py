@@ -33,9 +33,16 @@ def recipe_dose(tag, kind):
     return "f16", "f16"
 
 
+SEG_DEEP = ("decoder5.", "decoder4.", "encoder4.", "encoder3.")     # the 16^3 / 32^3 levels (at 128^3 input)
+
+
 def recipe_seg(tag, kind):
     if kind == "conv7" or kind in ("linear", "attn"):
         return "f16", "f16"
+    if tag.startswith(SEG_DEEP) and kind in ("conv3", "conv1", "store", "deconv"):
+        return "f16", ("f16" if kind == "conv3" else "f32")      # deep levels: plain fp16 operands / storage
+    if tag.startswith("decoder3.transp_conv"):                    # reads decoder4's fp16-stored output
+        return "f16", "f32"
     if kind == "deconv":
         tokens = "transp_conv_init" in tag or tag.startswith("decoder5.transp_conv")
         return ("f16" if tokens else "hilo"), "f32"
