@@ -261,7 +261,8 @@ def run_train(args):
                            "l2": f"no flush: per-step working set {P.bytes_alloc / 2**30:.1f} GiB >> 126 MB L2"},
                 "e2e": {"value": e2e_val, "unit": unit, "ms_per_step": ms_e2e / args.steps,
                         "h2d_bytes_per_step": B * 11 * S ** 3 * 4, "d2h_bytes_per_step": 4, "last_loss": losses[-1]},
-                "gpu_launches": (P.launches + 2) * args.steps, "launches_per_step": P.launches + 2,
+                "gpu_launches": (P.kernels_per_step + 2 + len(P.refresh_launches)) * args.steps,
+                "launches_per_step": P.kernels_per_step + 2 + len(P.refresh_launches),
                 "roofline": {"kernel": top[0], "launch": top[1], "bound": "tensor", "achieved": ach, "peak": peaks["tflops"],
                              "unit": "TFLOP/s", "frac": ach / peaks["tflops"], "traffic": None, "peak_source": peaks["source"],
                              "avg_launch_ms": top[2], "algorithmic_flops_per_launch": top[3], "share_of_step": top[2] / total_fam},
@@ -437,7 +438,7 @@ def main():
                            "l2": f"no flush: per-step working set {plan.bytes_alloc / 2**30:.1f} GiB >> 126 MB L2"},
                 "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                         "h2d_bytes_per_step": 2 * B * S ** 3 * 4, "d2h_bytes_per_step": B * S ** 3 * 4},
-                "gpu_launches": plan.launches * args.steps, "launches_per_step": plan.launches,
+                "gpu_launches": plan.kernels_per_step * args.steps, "launches_per_step": plan.kernels_per_step,
                 "roofline": roofline, "roofline_families": roofline_family, "conv_frac_of_tensor_peak": conv_pct,
                 "roofline_hbm_families": hbm_families,
                 "kernel_ms_per_step": {k: round(v["ms"], 3) for k, v in sorted(fam.items())},

@@ -65,9 +65,10 @@ class CascadePlan:
         seg_x = P.new_act(sw_batch, seg_model.in_ch, rdims, lo=True)
         first_step, stats0 = len(P.steps), P.stats_used
         win_logits = emit_oar_transeg(P, seg_model, seg_x)                     # emitted once, replayed per pass
-        seg_steps, seg_flops = P.steps[first_step:], P.step_flops[first_step:]
+        seg_steps, seg_flops, seg_kernels = P.steps[first_step:], P.step_flops[first_step:], P.step_kernels[first_step:]
         del P.steps[first_step:]
         del P.step_flops[first_step:]
+        del P.step_kernels[first_step:]
         fam0 = dict(P.flops)
         seg_stats = P.stats[stats0:P.stats_used]
         total = P.zeros((batch, win_logits.shape[1], size, size, size), torch.float32)
@@ -83,6 +84,7 @@ class CascadePlan:
                 P.add_zero(seg_stats)
             P.steps.extend(seg_steps)
             P.step_flops.extend(seg_flops)
+            P.step_kernels.extend(seg_kernels)
             if g > 0:                                  # the emission above already counted one pass
                 for name, fl in fam0.items():
                     P.flops[name] = P.flops.get(name, 0.0) + fl

@@ -122,6 +122,7 @@ class Plan:
         self.launches = 0
         self.flops = {}          # algorithmic FLOPs (2*MAC of the reference op) per kernel family, per replay
         self.step_flops = []     # the same per recorded launch (parallel to self.steps)
+        self.step_kernels = []   # device kernels per recorded C-ABI call (parallel to self.steps; 0 for host-side steps)
         self._pending_flops = 0.0
         self.bytes = {}          # algorithmic HBM bytes (inputs + outputs once) per HBM-bound kernel family, per replay
         self.training = False    # training plans re-derive packed weights from the live parameters every step
@@ -178,7 +179,9 @@ class Plan:
         return t
 
     # ------------------------------------------------------------------ recording / replay
-    def add(self, name, *args):
+    def add(self, name, *args, kernels=1):
+        """record one C-ABI call; `kernels` = device kernels that call launches (for the gpu_launches claim)."""
+        self.step_kernels.append(kernels)
         self.steps.append((getattr(self.lib, name), args, name))
         self.step_flops.append(self._pending_flops)
         self._pending_flops = 0.0
@@ -187,11 +190,17 @@ class Plan:
         """re-zero a (split-K / atomic) accumulation target at this point of every replay."""
         self.steps.append((None, (t,), "zero"))
         self.step_flops.append(0.0)
+        self.step_kernels.append(0)
+
+    @property
+    def kernels_per_step(self):
+        return sum(self.step_kernels)
 
     def add_py(self, fn):
         """host-side plumbing (parameter-layout conversion, collectives) at this point of every replay."""
         self.steps.append((None, (fn,), "py"))
         self.step_flops.append(0.0)
+        self.step_kernels.append(0)
 
     def derived(self, fn):
         """a tensor computed from live parameters (packed / transposed / fp16 copy): kept, and in training
@@ -562,7 +571,7 @@ class Plan:
             self.keep.append((wa, ba))
             self.add("dp_pointwise_conv_cw", len(srcs), *arrs, ctypes.cast(wa, ctypes.c_void_p),
                      ctypes.cast(ba, ctypes.c_void_p) if ba is not None else None, Co, N, vox, of, oh, ol, ocb, ooff, op, st,
-                     ACT_ID[out_act_fn])
+                     ACT_ID[out_act_fn], kernels=ceil_div(Co, 16))
             return
         self.add("dp_pointwise_conv", len(srcs), *arrs, w.data_ptr(), b.data_ptr() if b is not None else None, Co, N,
                  vox, of, oh, ol, ocb, ooff, op, st, ACT_ID[out_act_fn])
@@ -602,7 +611,8 @@ class Plan:
                 wa = (ctypes.c_float * wh.numel())(*wh.tolist())
                 self.keep.append(wa)
                 self.add("dp_deconv2x_cw", base, lo, src.cb_total * vox * 8, vox * 8, Ci, Co, src.N, D, H, W,
-                         ctypes.cast(wa, ctypes.c_void_p), out.hi_ptr, out.lo_ptr, out.cb_total, out.cb_off)
+                         ctypes.cast(wa, ctypes.c_void_p), out.hi_ptr, out.lo_ptr, out.cb_total, out.cb_off,
+                         kernels=ceil_div(Co, 16) * (1 if Ci == 32 else 2))
                 return
             self.add("dp_deconv2x", base, lo, src.cb_total * vox * 8, 8, vox * 8, Ci, Co, src.N, D, H, W, w.data_ptr(),
                      out.hi_ptr, out.lo_ptr, out.cb_total, out.cb_off)
