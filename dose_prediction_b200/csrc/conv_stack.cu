@@ -258,34 +258,25 @@ conv3d_stack_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_co
         tc_fence_after();
         // MMA pieces = contiguous runs of ring slots with one accumulate flag (B row block == ring slot in the
         // rotated weight copy).  pc_*: regular taps of a clipped window; fp_*: first tap (old | new planes).
-        uint32_t pc_o[2], pc_i[2];
-        int npc = 0;
-        uint32_t fp_o[4], fp_i[4], fp_acc[4];
-        int nfp = 0;
-        {
-          int i0 = 0;
-          while (i0 < nw) {
-            const int sl = (slot_lo + i0) & static_cast<int>(gmask);
-            const int len = min(nw - i0, G - sl);
-            pc_o[npc] = static_cast<uint32_t>(sl * N0);
-            pc_i[npc] = idesc0 | (static_cast<uint32_t>((len * N0) >> 3) << 17);
-            ++npc;
-            i0 += len;
-          }
-          for (int r = 0; r < 2; ++r) {
-            int a0 = r == 0 ? 0 : n_old;
-            const int a1 = r == 0 ? n_old : nw;
-            while (a0 < a1) {
-              const int sl = (slot_lo + a0) & static_cast<int>(gmask);
-              const int len = min(a1 - a0, G - sl);
-              fp_o[nfp] = static_cast<uint32_t>(sl * N0);
-              fp_i[nfp] = idesc0 | (static_cast<uint32_t>((len * N0) >> 3) << 17);
-              fp_acc[nfp] = r == 0 ? 1u : 0u;
-              ++nfp;
-              a0 += len;
-            }
-          }
-        }
+        // A window of ring slots wraps at most once, so every range is one or two runs; everything stays in
+        // registers (dynamically indexed arrays would live in local memory, and this is the single-thread
+        // critical path).
+        auto run_of = [&](int a0, int a1, uint32_t& o0, uint32_t& i0, uint32_t& o1, uint32_t& i1) -> int {
+          if (a1 <= a0) return 0;
+          const int sl = (slot_lo + a0) & static_cast<int>(gmask);
+          const int len = min(a1 - a0, G - sl);
+          o0 = static_cast<uint32_t>(sl * N0);
+          i0 = idesc0 | (static_cast<uint32_t>((len * N0) >> 3) << 17);
+          if (a0 + len >= a1) return 1;
+          o1 = 0u;                                                   // the wrapped remainder starts at ring slot 0
+          i1 = idesc0 | (static_cast<uint32_t>(((a1 - a0 - len) * N0) >> 3) << 17);
+          return 2;
+        };
+        uint32_t pc_o[2] = {0, 0}, pc_i[2] = {0, 0};
+        const int npc = run_of(0, nw, pc_o[0], pc_i[0], pc_o[1], pc_i[1]);
+        uint32_t fo_o[2] = {0, 0}, fo_i[2] = {0, 0}, fn_o[2] = {0, 0}, fn_i[2] = {0, 0};
+        const int nfo = run_of(0, n_old, fo_o[0], fo_i[0], fo_o[1], fo_i[1]);       // old planes: accumulate
+        const int nfn = run_of(n_old, nw, fn_o[0], fn_i[0], fn_o[1], fn_i[1]);      // new planes: overwrite
         bool first_tap = true;
         for (int c = 0; c < p.n_chunks; ++c) {
           if (!mbar_wait(&a_full[ia], pa, p.err_flag)) goto teardown;
@@ -299,15 +290,28 @@ conv3d_stack_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_co
             uint32_t b_lo = b_lo_c + smem16 + b_off16 + static_cast<uint32_t>(ib) * b_stride16;
             int tl = 0;
             if (first_tap) {
-              for (int q = 0; q < nfp; ++q)
-                for (int t = 0; t < my_tiles; ++t)
-                  umma_split(tm0 + t * tile_cols + fp_o[q], a_row + a_toff + kw + t * 8, a_hi, b_lo + fp_o[q], b_hi, fp_i[q], fp_acc[q]);
+#pragma unroll
+              for (int q = 0; q < 2; ++q) {
+                if (q < nfo)
+                  for (int t = 0; t < my_tiles; ++t)
+                    umma_split(tm0 + t * tile_cols + fo_o[q], a_row + a_toff + kw + t * 8, a_hi, b_lo + fo_o[q], b_hi, fo_i[q], 1u);
+                if (q < nfn)
+                  for (int t = 0; t < my_tiles; ++t)
+                    umma_split(tm0 + t * tile_cols + fn_o[q], a_row + a_toff + kw + t * 8, a_hi, b_lo + fn_o[q], b_hi, fn_i[q], 0u);
+              }
               first_tap = false;
               b_lo += tap_b16;
               if (++kw == KS) { kw = 0; ++kh; a_row += p.PWw; }
               tl = 1;
             }
-            if (fast) {
+            if (fast && KS == 3 && tl == 0 && cnt == KS * KS) {
+              // a whole 3x3 tap plane in one go (no per-row loop / switch on the issuing thread)
+#pragma unroll
+              for (int r3 = 0; r3 < 3; ++r3)
+                issue_taps<3, TTs>(tm0, tile_cols, a_row + a_toff + r3 * p.PWw, a_hi, b_lo + r3 * 3 * tap_b16, b_hi, tap_b16, idesc_full);
+              a_row += 3 * p.PWw;
+              tl = cnt;
+            } else if (fast) {
               while (tl < cnt) {
                 const int seg = min(cnt - tl, KS - kw);           // taps left in this kernel row
                 const uint32_t a_lo = a_row + a_toff + kw;
@@ -327,9 +331,11 @@ conv3d_stack_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_co
               }
             } else {
               for (; tl < cnt; ++tl) {
-                for (int q = 0; q < npc; ++q)
-                  for (int t = 0; t < my_tiles; ++t)
-                    umma_split(tm0 + t * tile_cols + pc_o[q], a_row + a_toff + kw + t * 8, a_hi, b_lo + pc_o[q], b_hi, pc_i[q], 1u);
+#pragma unroll
+                for (int q = 0; q < 2; ++q)
+                  if (q < npc)
+                    for (int t = 0; t < my_tiles; ++t)
+                      umma_split(tm0 + t * tile_cols + pc_o[q], a_row + a_toff + kw + t * 8, a_hi, b_lo + pc_o[q], b_hi, pc_i[q], 1u);
                 b_lo += tap_b16;
                 if (++kw == KS) { kw = 0; a_row += p.PWw; }
               }
