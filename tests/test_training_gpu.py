@@ -559,3 +559,32 @@ def test_seg_training_step_matches_oracle_32():
     losses = [float(loss)] + [float(tr.step(ct, lab)) for _ in range(7)]
     print("seg losses", losses)
     assert all(b < a for a, b in zip(losses, losses[1:])) and losses[-1] < losses[0] - 0.1, losses     # lr 1e-4: slow but monotone
+
+
+def test_training_step_matches_oracle_64():
+    """64^3, batch 1: several W tiles / row blocks per wgrad launch and 64 ViT tokens; loss and the heavy layers' gradients."""
+    from dose_prediction_b200 import synth
+    from dose_prediction_b200.training import DoseTrainer
+    from oracle import torch_ref
+    model, sd = _dose_model(64)
+    vol = synth.make_batch(1, 64, seed=77)
+    loss_ref, grads_ref, _, outs_ref = torch_ref.dose_pyfer_train_step(sd, vol["dose_input"], vol["gt"])
+    tr = DoseTrainer(model, 1, 64)
+    loss = tr.forward_backward(vol["dose_input"].to(DEV), vol["gt"].to(DEV))
+    torch.cuda.synchronize()
+    tr.P.check_device_errors()
+    assert abs(float(loss) - float(loss_ref)) <= 2e-3 * abs(float(loss_ref))
+    assert _rel(tr.outputs()[1][0], outs_ref[1][0]) < 1e-2
+    g = tr.grads()
+    for n in ("net_B.decoder.decoder1.conv_block.cov_.conv_7.0.conv.0.weight",
+              "net_B.decoder.decoder1.conv_block.cov_.conv_3.0.conv.3.weight",
+              "net_B.decoder.decoder2.conv_block.cov_.conv_7.0.conv.3.weight",
+              "net_B.decoder.decoder4.conv_block.cov_.conv_7.0.conv.0.weight",
+              "net_B.encoder.skip1.layer.conv1.conv.weight",
+              "net_B.encoder.vit.blocks.7.mlp.linear1.weight",
+              "net_B.encoder.vit.patch_embedding.patch_embeddings.1.weight",
+              "net_B.decoder.decoder3.transp_conv.conv.weight",
+              "net_B.dose_convertors.0.0.weight"):
+        cos = float(F.cosine_similarity(g[n].flatten().double().cpu(), grads_ref[n].flatten().double(), dim=0))
+        assert cos > 0.99, (n, cos)
+        assert abs(float(g[n].norm()) / float(grads_ref[n].norm()) - 1.0) < 0.06, n
