@@ -37,7 +37,8 @@ struct ConvTcParams {
   int PW, PHs;
   int stages;
   uint32_t a_bytes, a_bytes_al, stage_bytes;
-  int tiles_h, tiles_w, num_tiles;
+  int tiles_h, tiles_w, num_tiles;   // num_tiles counts tile GROUPS: T adjacent W tiles share one stage (weights read once)
+  int T, groups_w;
   const __half* wpack;
   const float* scale;
   const float* shift;
@@ -97,7 +98,7 @@ __device__ __forceinline__ float colsum16(const float (&v)[16], int lane) {
   return r;
 }
 
-template <int KS>
+template <int KS, int TG>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ ConvTcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -139,7 +140,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
 
-  const int tiles_per_plane = p.tiles_h * p.tiles_w;
+  const int tiles_per_plane = p.tiles_h * p.groups_w;          // tile groups per D plane
   const uint32_t tap_b_bytes = 32u * static_cast<uint32_t>(p.cout);  // one tap: [2][cout][8] fp16
   const size_t kd_w_halfs = static_cast<size_t>(p.n_chunks) * KS * KS * 16 * p.cout;   // weights of one kd (all chunks)
   const size_t chunk_w_halfs = static_cast<size_t>(KS) * KS * 16 * p.cout;
@@ -150,7 +151,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       int t = tile;
-      const int tw = t % p.tiles_w; t /= p.tiles_w;
+      const int tw = (t % p.groups_w) * p.T; t /= p.groups_w;
       const int th = t % p.tiles_h; t /= p.tiles_h;
       const int d = t % p.D;
       const int n = t / p.D;
@@ -197,10 +198,11 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
     int iter = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++iter) {
       const int d = (tile / tiles_per_plane) % p.D;
+      const int ntile = min(p.T, p.tiles_w - (tile % p.groups_w) * p.T);
       const int slot = iter & 1;
       if (!mbar_wait(&tmem_empty_bar[slot], ((iter >> 1) & 1) ^ 1, p.err_flag)) goto teardown;
       tc_fence_after();
-      const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(slot * p.cout);
+      const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(slot * p.T * p.cout);
       uint32_t accumulate = 0;
       for (int kdg = 0; kdg < p.n_kdg; ++kdg) {
         const int dz = d + kdg * p.kd_s * p.dil - p.pad;
@@ -222,7 +224,11 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
 #pragma unroll
                   for (int kw = 0; kw < KS; ++kw) {
                     if (KS > 3 || ((mask >> (tap0 + kw)) & 1u)) {
-                      umma_f16_ss_split(tmem_d, a_lo_c | (a16 & 0x3FFFu), a_hi, b_lo_c | (b16 & 0x3FFFu), b_hi, idesc, accumulate);
+#pragma unroll
+                      for (int tt = 0; tt < TG; ++tt)
+                        if (TG == 1 || tt < ntile)
+                          umma_f16_ss_split(tmem_d + static_cast<uint32_t>(tt * p.cout), a_lo_c | ((a16 + tt * 8) & 0x3FFFu), a_hi,
+                                            b_lo_c | (b16 & 0x3FFFu), b_hi, idesc, accumulate);
                       accumulate = 1;
                     }
                     a16 += static_cast<uint32_t>(p.dil);
@@ -266,17 +272,19 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
     const size_t plane = static_cast<size_t>(p.D) * p.H * p.W;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++iter) {
       int t = tile;
-      const int tw = t % p.tiles_w; t /= p.tiles_w;
+      const int tw0 = (t % p.groups_w) * p.T; t /= p.groups_w;
       const int th = t % p.tiles_h; t /= p.tiles_h;
       const int d = t % p.D;
       const int n = t / p.D;
       if (n != cur_n) { flush_stats(cur_n); cur_n = n; }
-      const int h = th * 16 + hl, w = tw * 8 + wl;
-      const bool valid = (h < p.H) && (w < p.W);
+      const int ntile = min(p.T, p.tiles_w - tw0);
       const int slot = iter & 1;
       if (!mbar_wait_relaxed(&tmem_full_bar[slot], (iter >> 1) & 1, p.err_flag)) goto teardown;
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(slot * p.cout);
+      for (int tt = 0; tt < ntile; ++tt) {
+      const int h = th * 16 + hl, w = (tw0 + tt) * 8 + wl;
+      const bool valid = (h < p.H) && (w < p.W);
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>((slot * p.T + tt) * p.cout);
       const size_t vox = (static_cast<size_t>(d) * p.H + h) * p.W + w;
       for (int c0 = cgrp * 16; c0 < p.cout; c0 += 32) {
         uint32_t r[16];
@@ -324,6 +332,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
           }
         }
       }
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[slot]);
@@ -359,7 +368,16 @@ extern "C" int dp_conv3d_tc(const void* in_c8, int cb_total_in, const uint8_t* c
   p.n_chunks = n_chunks; p.cb_total_in = cb_total_in; p.cout = cout;
   for (int i = 0; i < n_chunks; ++i) { p.chunk_cb[i] = chunk_cb[i]; p.tap_mask[i] = tap_mask ? tap_mask[i] : 0xFFFFFFFFu; }
   DP_REQUIRE(tap_mask == nullptr || k <= 3, "dp_conv3d_tc: tap masks are supported for k <= 3 only");
-  p.PW = 8 + (k - 1) * dil;
+  // W-tile groups: for k <= 3 the layer is bound by the L2 -> SM weight stream (every 128-voxel tile re-reads all
+  // weights), so T adjacent tiles share one stage; bounded by the double-buffered accumulators (2*T*cout <= 512 columns)
+  p.tiles_w = (W + 7) / 8;
+  int T = 1;
+  if (k <= 3) T = cout <= 64 ? 4 : (cout <= 128 ? 2 : 1);
+  else if (k == 7 && cout <= 128) T = 2;
+  while (T > 1 && T > p.tiles_w) T >>= 1;
+  p.T = T;
+  p.groups_w = (p.tiles_w + T - 1) / T;
+  p.PW = 8 * T + (k - 1) * dil;
   // stage sizing: as many kh rows per stage as fit ~56 KB, then as many stages as fit ~200 KB
   const int tap_b = 32 * cout;
   int kh_s = k, kd_s = (dil == 1 && tap_mask == nullptr) ? k : 1;   // tap-masked (space-to-depth) convs: per-depth stages, empty ones skipped
@@ -383,15 +401,14 @@ extern "C" int dp_conv3d_tc(const void* in_c8, int cb_total_in, const uint8_t* c
   DP_REQUIRE(stages >= 2, "dp_conv3d_tc: stage of %u bytes does not fit twice in shared memory", p.stage_bytes);
   p.stages = stages;
   p.tiles_h = (H + 15) / 16;
-  p.tiles_w = (W + 7) / 8;
-  p.num_tiles = N * D * p.tiles_h * p.tiles_w;
+  p.num_tiles = N * D * p.tiles_h * p.groups_w;
   p.wpack = static_cast<const __half*>(wpack);
   p.scale = scale; p.shift = shift; p.relu = relu;
   p.out_f32 = out_f32; p.out_hi = static_cast<__half*>(out_hi); p.out_lo = static_cast<__half*>(out_lo);
   p.cb_total_out = cb_total_out; p.cb_out_off = cb_out_off;
   p.stats = stats; p.err_flag = err_flag;
   uint32_t cols = 32;
-  while (cols < static_cast<uint32_t>(2 * cout)) cols <<= 1;
+  while (cols < static_cast<uint32_t>(2 * T * cout)) cols <<= 1;
   p.tmem_cols = cols;
 
   CUtensorMap tmap;
@@ -411,18 +428,21 @@ extern "C" int dp_conv3d_tc(const void* in_c8, int cb_total_in, const uint8_t* c
   static bool configured = false;
   if (!configured) {
     const int max_smem = 8 * 25 * 1024 + 1024 + 4096;
-    DP_CHECK(cudaFuncSetAttribute(conv3d_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    DP_CHECK(cudaFuncSetAttribute(conv3d_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    DP_CHECK(cudaFuncSetAttribute(conv3d_tc_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    DP_CHECK(cudaFuncSetAttribute(conv3d_tc_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+#define DP_TC_ATTR(K_, T_) DP_CHECK(cudaFuncSetAttribute(conv3d_tc_kernel<K_, T_>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem))
+    DP_TC_ATTR(1, 1); DP_TC_ATTR(1, 2); DP_TC_ATTR(1, 4);
+    DP_TC_ATTR(3, 1); DP_TC_ATTR(3, 2); DP_TC_ATTR(3, 4);
+    DP_TC_ATTR(5, 1); DP_TC_ATTR(7, 1); DP_TC_ATTR(7, 2);
+#undef DP_TC_ATTR
     configured = true;
   }
+#define DP_TC_LAUNCH(K_, T_) conv3d_tc_kernel<K_, T_><<<grid, kConvThreads, smem, stream>>>(tmap, p)
   switch (k) {
-    case 1: conv3d_tc_kernel<1><<<grid, kConvThreads, smem, stream>>>(tmap, p); break;
-    case 3: conv3d_tc_kernel<3><<<grid, kConvThreads, smem, stream>>>(tmap, p); break;
-    case 5: conv3d_tc_kernel<5><<<grid, kConvThreads, smem, stream>>>(tmap, p); break;
-    default: conv3d_tc_kernel<7><<<grid, kConvThreads, smem, stream>>>(tmap, p); break;
+    case 1: if (T == 4) DP_TC_LAUNCH(1, 4); else if (T == 2) DP_TC_LAUNCH(1, 2); else DP_TC_LAUNCH(1, 1); break;
+    case 3: if (T == 4) DP_TC_LAUNCH(3, 4); else if (T == 2) DP_TC_LAUNCH(3, 2); else DP_TC_LAUNCH(3, 1); break;
+    case 5: DP_TC_LAUNCH(5, 1); break;
+    default: if (T == 2) DP_TC_LAUNCH(7, 2); else DP_TC_LAUNCH(7, 1); break;
   }
+#undef DP_TC_LAUNCH
   DP_CHECK(cudaGetLastError());
   return 0;
 }
