@@ -14,7 +14,8 @@
 // A CTA owns one (16-channel chunk of C_in, 16-channel tile of C_out, group of KDP depth taps) and keeps its
 // 2*KDP accumulators (ci block x kd) in TMEM for its whole share of the volume; partial results of the `splits`
 // CTAs of a type go to ws[split] and are summed by dp_splitk_reduce (deterministic).
-// Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue (TMEM lane quarters).
+// Warp roles: warp 0 TMA producer, warps 1 and 6 MMA issuers (one per 8-channel block of the chunk: single-thread issue
+// was the limiter, ncu: 130 cycles per MMA against a 56-cycle tensor floor), warps 2-5 epilogue (TMEM lane quarters).
 #include <algorithm>
 
 #include "common.cuh"
@@ -22,8 +23,22 @@
 
 namespace dp {
 
-constexpr int kWgThreads = 192;
+constexpr int kWgThreads = 224;       // producer, MMA issuer A, 4 epilogue warps, MMA issuer B
+constexpr int kWgMmaWarpB = 6;
 constexpr int kWgXStages = 6;
+
+// tcgen05.mma with the two shared-memory descriptors given as 32-bit halves (only the start address in lo varies)
+__device__ __forceinline__ void wg_umma(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                        uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 
 struct WgradTcParams {
   int N, D, H, W, Ci, Co, k;
@@ -44,7 +59,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_con
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   __shared__ uint64_t g_full[2], g_empty[2], x_full[kWgXStages], x_empty[kWgXStages], done_bar;
   __shared__ uint32_t tmem_base_smem;
-  __shared__ uint32_t started_smem;
+  __shared__ uint32_t started_smem[2];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k = p.k, P = k / 2;
@@ -68,10 +83,10 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_con
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&x_map);
     tma_prefetch_desc(&g_map);
-    for (int i = 0; i < 2; ++i) { mbar_init(&g_full[i], 1); mbar_init(&g_empty[i], 1); }
-    for (int i = 0; i < kWgXStages; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
-    mbar_init(&done_bar, 1);
-    started_smem = 0;
+    for (int i = 0; i < 2; ++i) { mbar_init(&g_full[i], 1); mbar_init(&g_empty[i], 2); }
+    for (int i = 0; i < kWgXStages; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 2); }
+    mbar_init(&done_bar, 2);
+    started_smem[0] = started_smem[1] = 0;
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(&tmem_base_smem);
@@ -114,14 +129,18 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_con
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================================================================== MMA issuer
+  } else if (warp == 1 || warp == kWgMmaWarpB) {
+    // ===================================================================== MMA issuers (cb = 0 / cb = 1)
     if (elect_one()) {
+      const int cb = (warp == 1) ? 0 : 1;
       // both operands MN-major (idesc bits 15, 16), fp16 in, fp32 accumulate
       const uint32_t idesc = make_idesc_f16(128, ncols) | (1u << 15) | (1u << 16);
       const uint32_t x_cb_bytes = static_cast<uint32_t>(p.w_tile + 16) * 16;
       const uint32_t g_cob_bytes = static_cast<uint32_t>(p.w_tile) * 16;
-      const uint32_t g_row_bytes = 2 * g_cob_bytes;
+      const uint32_t g_row16 = (2 * g_cob_bytes) >> 4;
+      // descriptor halves (see make_smem_desc): lo = start>>4 | LBO>>4 << 16, hi = SBO>>4 | version 1 << 14
+      const uint32_t a_lo_c = (128u >> 4) << 16, a_hi = (16u >> 4) | (1u << 14);
+      const uint32_t b_lo_c = (128u >> 4) << 16, b_hi = (g_cob_bytes >> 4) | (1u << 14);
       const int ksteps = p.w_tile / 16;
       uint32_t started = 0;
       int xs = 0; uint32_t xph = 0;
@@ -133,32 +152,29 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_con
         const int buf = it & 1;
         const uint32_t gph = (it >> 1) & 1;
         if (!mbar_wait(&g_full[buf], gph, p.err_flag)) break;
-        const uint32_t gb = smem_u32(g_buf + buf * static_cast<size_t>(p.g_buf_bytes));
+        const uint32_t gb16 = smem_u32(g_buf + buf * static_cast<size_t>(p.g_buf_bytes)) >> 4;
         const int rows = min(p.rb, p.H - h0);
         for (int i0 = 0; i0 < rows; i0 += p.xr) {
           if (!mbar_wait(&x_full[xs], xph, p.err_flag)) { ok = false; break; }
           tc_fence_after();
-          const uint32_t xs_base = smem_u32(x_buf + xs * static_cast<size_t>(p.x_stage_bytes));
+          const uint32_t xs16 = (smem_u32(x_buf + xs * static_cast<size_t>(p.x_stage_bytes)) + cb * x_cb_bytes) >> 4;
           const int nr = min(p.xr, rows - i0);
           for (int r = 0; r < nr; ++r) {
-            const int i = i0 + r;
-            const uint32_t xb = xs_base + static_cast<uint32_t>(r) * 2 * x_cb_bytes;
+            const uint32_t xa = a_lo_c | ((xs16 + static_cast<uint32_t>(r) * ((2 * x_cb_bytes) >> 4)) & 0x3FFFu);
             for (int kdi = 0; kdi < n_kd; ++kdi) {
               const int dg = d - (kd0 + kdi) + P;
               if (dg < 0 || dg >= p.D) continue;               // all-zero plane
-#pragma unroll 1
-              for (int cb = 0; cb < 2; ++cb) {
-                const int acc = kdi * 2 + cb;
-                const uint32_t tcol = tmem_base + static_cast<uint32_t>(acc * ncols);
-                uint32_t accum = (started >> acc) & 1u;
-                for (int ks = 0; ks < ksteps; ++ks) {
-                  const uint64_t da = make_smem_desc(xb + cb * x_cb_bytes + ks * 256, 128, 16, 0);
-                  const uint64_t db = make_smem_desc(gb + kdi * p.g_plane_bytes + i * g_row_bytes + ks * 256, 128, g_cob_bytes, 0);
-                  umma_f16_ss(tcol, da, db, idesc, accum);
-                  accum = 1;
-                }
-                started |= 1u << acc;
+              const int acc = kdi * 2 + cb;
+              const uint32_t tcol = tmem_base + static_cast<uint32_t>(acc * ncols);
+              const uint32_t gbl = b_lo_c | ((gb16 + static_cast<uint32_t>(kdi) * (p.g_plane_bytes >> 4) +
+                                              static_cast<uint32_t>(i0 + r) * g_row16) & 0x3FFFu);
+              uint32_t accum = (started >> acc) & 1u;
+#pragma unroll 4
+              for (int ks = 0; ks < ksteps; ++ks) {
+                wg_umma(tcol, xa + ks * 16, a_hi, gbl + ks * 16, b_hi, idesc, accum);
+                accum = 1;
               }
+              started |= 1u << acc;
             }
           }
           umma_commit(&x_empty[xs]);
@@ -166,17 +182,18 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_con
         }
         umma_commit(&g_empty[buf]);
       }
-      *reinterpret_cast<volatile uint32_t*>(&started_smem) = started;
+      *reinterpret_cast<volatile uint32_t*>(&started_smem[cb]) = started;
       __threadfence_block();
       umma_commit(&done_bar);
     }
     __syncwarp();
-  } else {
+  } else if (warp >= 2 && warp < 6) {
     // ===================================================================== epilogue: TMEM -> ws[split]
     mbar_wait_relaxed(&done_bar, 0, p.err_flag);
     tc_fence_after();
     __syncwarp();
-    const uint32_t started = *reinterpret_cast<volatile uint32_t*>(&started_smem);
+    const uint32_t started = *reinterpret_cast<volatile uint32_t*>(&started_smem[0]) |
+                             *reinterpret_cast<volatile uint32_t*>(&started_smem[1]);
     const int q = warp & 3;
     const int m = q * 32 + lane;             // accumulator row = s*8 + c
     const int s = m >> 3, c = m & 7;
