@@ -335,6 +335,20 @@ long long dp_dvh_workspace_bytes(void);
 int dp_dvh_metrics(const float* pred, const float* gt, const float* masks, int n_struct, const int* is_target, long long vox,
                    float voxels_in_tenth_of_cc, void* workspace, float* out, float* dvh_dif, cudaStream_t stream);
 
+/* ======================================================================== input pipeline
+ * The numpy / monai transforms of DosePrediction/DataLoader/dataloader_OpenKBP_monai.py:160-243 after the files
+ * are read.  dp_prepare_input: raw arrays [A][B][C] (masks uint8, NULL = structure absent; CT int16 or fp32 HU;
+ * dose fp32 Gy) -> Input [9][C][B][A] = [PTV (70/70, 63/70, 56/70 merge, :113-125), 7 OARs, clip(CT)/1000 + ct_shift
+ * (:137-146, RandShiftIntensityd :189-193)] and GT [2][C][B][A] = [dose/70, dose_mask] (:128-134,:195-201), including
+ * Transposed(indices=[2,1,0]) (:173).  ptv_u8 / oar_u8: HOST arrays of 3 / 7 device pointers.
+ * dp_flip_rot90: out = np.rot90(np.flip(in, flipped spatial axes), k, axes=(0,1)) per channel (RandFlipd x3 :214-228,
+ * RandRotate90d :229-233) for in [C][S0][S1][S2]; out is [C][S1][S0][S2] when k is odd.                       */
+int dp_prepare_input(const void* const* ptv_u8, const void* const* oar_u8, const void* ct_i16, const float* ct_f32,
+                     const float* dose, const void* dose_mask_u8, int A, int B, int C, float a_min, float a_max,
+                     float ct_shift, float* input, float* gt, cudaStream_t stream);
+int dp_flip_rot90(const float* in, float* out, int C, int S0, int S1, int S2, int flip0, int flip1, int flip2, int k,
+                  cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -157,6 +157,23 @@ def main():
     erec["dvh_dif"] = np.float64(np.mean(difs))
     np.savez_compressed(os.path.join(OUT, "eval64.npz"), **erec)
 
+    # ---- input pipeline: the reference's own transform classes (dataloader_OpenKBP_monai.py:84-146) on a small raw case
+    dl = ref_loader.dataloader()
+    rng = np.random.default_rng(11)
+    shp = (12, 10, 16)
+    raw = {"CT": rng.integers(-2000, 3000, shp).astype(np.int16), "dose": (rng.random(shp) * 75).astype(np.float32),
+           "dose_mask": (rng.random(shp) < 0.6).astype(np.uint8)}
+    for n in ("Brainstem", "SpinalCord", "LeftParotid", "Mandible", "PTV70", "PTV56"):
+        raw[n] = (rng.random(shp) < 0.2).astype(np.uint8)
+    dd = {k_: np.transpose(v_, (2, 1, 0)) for k_, v_ in raw.items()}          # monai Transposed(indices=[2,1,0])
+    dd = dl.Empty2FullOAR()(dd)
+    dd = dl.NormalizePTVTr()(dd)
+    dd = dl.MyIntensityNormalTransform(a_min=-1024, a_max=1500)(dd)
+    dd = dl.NormalizeDoseTr()(dd)
+    inp_ref = np.stack([dd["PTV"]] + [dd[n] for n in dl.OAR_NAMES] + [dd["CT"]]).astype(np.float32)     # ConcatItemsd 'Input'
+    gt_ref = np.stack([dd["dose"], dd["dose_mask"]]).astype(np.float32)                                   # ConcatItemsd 'GT'
+    np.savez_compressed(os.path.join(OUT, "pipeline12.npz"), input=inp_ref, gt=gt_ref)
+
     # ---- sliding window (monai restatement; seg net built for 32^3 scanned over a 48^3 CT)
     from monai.inferers import sliding_window_inference
     ct48 = synth.make_volume(48, seed=77)["ct"]

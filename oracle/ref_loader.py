@@ -71,6 +71,24 @@ def evaluate():
     return _imp("DosePrediction.Evaluate.evaluate_openKBP")
 
 
+def dataloader():
+    """DosePrediction/DataLoader/dataloader_OpenKBP_monai.py, unmodified.  The monai names it imports at module level
+    (dictionary transforms, datasets) are only used inside prepare_data / get_dataset; placeholders are registered for
+    the ones oracle/monai_compat does not restate, so that the reference's OWN transform classes (Empty2FullOAR,
+    NormalizePTVTr, MyIntensityNormalTransform, NormalizeDoseTr) can be imported and run."""
+    _ensure_path()
+    import monai.data
+    import monai.transforms
+    for mod, names in ((monai.data, ("Dataset", "DataLoader", "CacheDataset", "list_data_collate")),
+                       (monai.transforms, ("Compose", "LoadImaged", "ToTensord", "AddChanneld", "Orientationd", "ConcatItemsd",
+                                           "DeleteItemsd", "RandCropByPosNegLabeld", "RandFlipd", "RandShiftIntensityd",
+                                           "RandRotate90d", "Transposed"))):
+        for n in names:
+            if not hasattr(mod, n):
+                setattr(mod, n, type(n, (), {"__init__": lambda self, *a, **k: None}))
+    return _imp("DosePrediction.DataLoader.dataloader_OpenKBP_monai")
+
+
 def seg_config():
     return _imp("OARSegmentation.config")
 

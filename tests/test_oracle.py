@@ -138,6 +138,20 @@ def test_evaluation_matches_reference_fixture():
         assert abs(out["table"][k] - float(g[k])) <= 1e-5 * max(1.0, abs(float(g[k]))), k
 
 
+def test_input_pipeline_matches_reference_fixture():
+    """oracle/pipeline_ref.py == the reference's own transform classes (fixture made by running them)."""
+    from oracle import pipeline_ref
+    rng = np.random.default_rng(11)
+    shp = (12, 10, 16)
+    raw = {"CT": rng.integers(-2000, 3000, shp).astype(np.int16), "dose": (rng.random(shp) * 75).astype(np.float32),
+           "dose_mask": (rng.random(shp) < 0.6).astype(np.uint8)}
+    for n in ("Brainstem", "SpinalCord", "LeftParotid", "Mandible", "PTV70", "PTV56"):
+        raw[n] = (rng.random(shp) < 0.2).astype(np.uint8)
+    g = np.load(os.path.join(GOLDEN, "pipeline12.npz"))
+    inp, gt = pipeline_ref.prepare(raw)
+    assert np.array_equal(inp, g["input"]) and np.array_equal(gt, g["gt"])
+
+
 def test_sliding_window_matches_fixture(seg_sd32):
     ct48 = synth.make_volume(48, seed=77)["ct"]
     g = torch.from_numpy(np.load(os.path.join(GOLDEN, "sliding48.npz"))["logits"])
