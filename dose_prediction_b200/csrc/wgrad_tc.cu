@@ -253,8 +253,8 @@ extern "C" int dp_conv3d_wgrad_tc(const void* x_c8, int x_cb_total, const uint8_
   }
   p.g_cb_off = g_cb_off; p.ws = ws; p.splits = splits; p.err_flag = err_flag;
   p.wsize = static_cast<long long>(cout) * cin * k * k * k;
-  p.w_tile = std::min(64, (W + 15) / 16 * 16);
-  p.n_wt = (W + p.w_tile - 1) / p.w_tile;
+  p.n_wt = (W + 63) / 64;                                           // W tiles of <= 64 voxels, balanced: 96 -> 2 x 48
+  p.w_tile = ((W + p.n_wt - 1) / p.n_wt + 15) / 16 * 16;
   p.kdp = k == 7 ? 2 : 3;
   p.n_kdg = (k + p.kdp - 1) / p.kdp;
   // x rows per block: as many as fit two g buffers in ~170 KB of shared memory (and at most H)
