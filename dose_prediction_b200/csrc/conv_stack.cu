@@ -47,7 +47,7 @@ struct StackParams {
   int cb_total_out, cb_out_off;
   double* stats;
   int* err_flag;
-  int debug;                // timing experiments only (DP_STACK_DEBUG): 1 = skip weight copies, 2 = skip patch loads
+  int debug;                // timing experiments only (DP_STACK_DEBUG): 1 = skip weight copies, 2 = skip patch loads, 4 = skip epilogue work
   uint8_t chunk_cb[96];
 };
 
@@ -389,7 +389,7 @@ conv3d_stack_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_co
         const int slot = static_cast<int>(pc & gmask);
         if (!mbar_wait_relaxed(&done_bar[slot], (pc >> gshift) & 1, p.err_flag)) goto teardown;
         tc_fence_after();
-        for (int t = tgrp; t < it.ntile; t += 2) {
+        for (int t = tgrp; t < it.ntile && !(p.debug & 4); t += 2) {     // debug 4: epilogue only hands the slot back
           const int w = it.w0 + t * 8 + wl;
           const bool valid = (h < p.H) && (w < p.W);
           const size_t vox = (static_cast<size_t>(d) * p.H + h) * p.W + w;
