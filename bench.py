@@ -39,6 +39,29 @@ def _peaks():
     return {"tflops": 1400.0, "hbm_gbs": 6650.0, "tflops_burst": None, "source": "fallback (B200_PROFILING.md, sustained)"}
 
 
+_JSON_OUT = None
+
+
+def _claim_stdout():
+    """stdout must carry exactly ONE JSON line, but libraries write to fd 1 too (NCCL prints its version banner
+    there at communicator creation).  Keep a private handle on the real stdout and point fd 1 at stderr."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
+def _quiet_nccl():
+    pass
+
+
 class ClockSampler:
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -151,7 +174,7 @@ def run_reference(args):
                              "sample": f"{args.steps} x {args.size}^3 cascade volumes, oracle/torch_ref.py fp32 (reference "
                                        "modules need monai 0.7.0, absent on the box)"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def run_train(args):
@@ -185,17 +208,18 @@ def run_train(args):
         val = (size / S) ** 3 / dt
         sample = (f"{max(1, args.steps)} training step(s), batch 1, {size}^3, oracle/torch_ref.py autograd fp32; value scaled by "
                   f"({size}/{S})^3 to {S}^3-equivalent samples/s")
-        print(json.dumps({"impl": "reference", "metric": metric, "value": val, "unit": unit, "n_gpus": args.gpus,
+        _emit({"impl": "reference", "metric": metric, "value": val, "unit": unit, "n_gpus": args.gpus,
                           "steps": args.steps, "warmup": 0, "ms_per_step": 1e3 * dt, "higher_is_better": True,
                           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                           "config": {"workload": f"DOSE-PYFER training step, bounded CPU sample ({sample})"},
                           "cpu_baseline": {"value": val, "unit": unit, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
-                          "e2e": {"value": val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+                          "e2e": {"value": val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
         return
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        _quiet_nccl()
         dist.init_process_group("nccl", device_id=dev)
     __graft_entry__.build()
     _, dose = build_models(S, dev)
@@ -270,7 +294,7 @@ def run_train(args):
                 "roofline_families": fam_roof,
                 "kernel_ms_per_step": {k: round(v["ms"], 3) for k, v in sorted(fam.items())},
                 "clocks": clocks}
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -291,6 +315,7 @@ def main():
     ap.add_argument("--sw-roi", type=int, default=0,
                     help="run the seg stage as the reference does: sliding 96^3-style windows of this ROI (0 = direct)")
     args = ap.parse_args()
+    _claim_stdout()
     args.batch_given = any(a == "--batch" or a.startswith("--batch=") for a in sys.argv[1:])
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     if args.workload == "train":
@@ -312,6 +337,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        _quiet_nccl()
         dist.init_process_group("nccl", device_id=dev)
     __graft_entry__.build()
 
@@ -448,7 +474,7 @@ def main():
         if world == 1 and not args.no_cpu_baseline and not args.sw_roi:
             line["cpu_baseline"] = cpu_baseline({k: v.cpu() for k, v in seg.state_dict().items()},
                                                 {k: v.cpu() for k, v in dose.state_dict().items()}, S)
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
