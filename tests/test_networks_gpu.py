@@ -92,7 +92,7 @@ def test_cascade_32_matches_reference_fixture_and_graph_replay():
     assert _rel(dose2, dose) < 1e-5
 
 
-@pytest.mark.parametrize("size", [64, 128])
+@pytest.mark.parametrize("size", [64, 80, 128])      # 80: ragged tiles / tile groups at every level (80, 40, 20, 10)
 def test_both_networks_match_oracle_at_size(size):
     from dose_prediction_b200 import synth
     from oracle import torch_ref
