@@ -485,12 +485,13 @@ class Plan:
                  st.data_ptr() if st is not None else None)
 
     def norm_act(self, src, out, stats=None, gamma=None, beta=None, act=None, res=None, res_stats=None,
-                 act_after_res=None, stats_out=None, s2d=None):
-        """out = act_after(act(IN(src)*gamma+beta) [+ IN?(res)]); src: Raw or Act; res: Act or Raw."""
+                 act_after_res=None, stats_out=None, s2d=None, identity=False):
+        """out = act_after(act(IN(src)*gamma+beta) [+ IN?(res)]); src: Raw or Act; res: Act or Raw.
+        identity=True: no normalisation (plain fp32 -> fp16 conversion + activation)."""
         if isinstance(src, Raw):
             rf, rh, rl, icb, ioff, C = src.t.data_ptr(), None, None, src.cb_total, 0, src.C
             N, vox = src.t.shape[0], src.t.shape[2] * src.t.shape[3] * src.t.shape[4]
-            if stats is None:
+            if stats is None and not identity:
                 stats = src.stats
         else:
             rf, rh, rl, icb, ioff, C = None, src.hi_ptr, src.lo_ptr, src.cb_total, src.cb_off, src.C

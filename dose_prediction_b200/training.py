@@ -159,13 +159,14 @@ class TrainPlan(Plan):
                      g16.cb_off, a0.N, D, H, W, Ci, Co, k, dil, ws.data_ptr(), splits)
         self.add("dp_splitk_reduce", ws.data_ptr(), splits, 1, w.numel(), None, None, 0, self.grad(w).data_ptr())
 
-    def t_norm(self, src, out, act=None, res=None, act_after_res=None, bn=None, stats=None, stats_out=None):
-        """InstanceNorm3d (or train-mode BatchNorm3d `bn`) + activation (+ residual) -> out Act."""
+    def t_norm(self, src, out, act=None, res=None, act_after_res=None, bn=None, stats=None, stats_out=None, identity=False):
+        """InstanceNorm3d (or train-mode BatchNorm3d `bn`) + activation (+ residual) -> out Act.
+        identity=True: no normalisation (the block output is the raw conv output, OldModels conv_3_1)."""
         if isinstance(src, Raw):
             N, C = src.t.shape[0], src.C
             vox = src.t.shape[2] * src.t.shape[3] * src.t.shape[4]
             dims = tuple(src.t.shape[2:5])
-            st = src.stats
+            st = None if identity else src.stats
         else:
             N, C, vox, dims, st = src.N, src.C, src.vox, src.dims, stats
         gamma = beta = None
@@ -174,7 +175,7 @@ class TrainPlan(Plan):
                      float(bn.momentum))
             gamma, beta = bn.weight.detach(), bn.bias.detach()
         self.norm_act(src, out, stats=st, gamma=gamma, beta=beta, act=act, res=res, act_after_res=act_after_res,
-                      stats_out=stats_out)
+                      stats_out=stats_out, identity=identity)
 
         def bwd():
             dy = self.act_grads.pop(self._key(out))
@@ -546,6 +547,23 @@ def _t_conv_3_1(P, blk, parts, out):
     P.t_norm(raw, out, act=act)
 
 
+def _t_conv_3_1_old(P, blk, parts, out):
+    """OARSegmentation/OldModels/Nets/blocks_MDUNet.py:132-147 in train mode: both branches conv -> BN -> ReLU twice
+    (batch statistics), then a bare 1^3 conv."""
+    N, dims = parts[0].N, parts[0].dims
+    C = blk.conv.weight.shape[0]
+    ys = P.new_concat(N, [C, C], dims)
+    for (br, k), y in zip(((blk.conv_3, 3), (blk.conv_7, 7)), ys):
+        c = br.conv
+        raw = P.t_conv(parts, c[0], k)
+        a = P.new_act(N, C, dims)
+        P.t_norm(raw, a, act="relu", bn=c[1])
+        raw = P.t_conv([a], c[3], k)
+        P.t_norm(raw, y, act="relu", bn=c[4])
+    raw = P.t_pointwise(ys, blk.conv)
+    P.t_norm(raw, out, identity=True)
+
+
 def _t_unetr(P, vit, enc_blocks, dec_blocks, parts, taps):
     """UNETR-shaped body shared by MainSubsetModel.forward (dose_pyfer.py:311-319) and oar_transeg Model.forward
     (oar_transeg.py:171-185) in train mode; returns the decoder outputs [full res, /2, /4, /8]."""
@@ -560,11 +578,15 @@ def _t_unetr(P, vit, enc_blocks, dec_blocks, parts, taps):
     _t_pr_up(P, enc_blocks[3], hs[taps[2]], cats[3][1])
     decs, inp = [], z
     for lvl, blk in zip((3, 2, 1, 0), dec_blocks):
-        if not (hasattr(blk, "conv_block") and isinstance(getattr(blk.conv_block, "cov_", None), nw.conv_3_1)):
+        cov = getattr(getattr(blk, "conv_block", None), "cov_", None)
+        if not isinstance(cov, (nw.conv_3_1, nw.conv_3_1_old)):
             raise RuntimeError("training path covers the multi-scale decoder (mode_multi_dec=True, multiS_conv=True)")
         out = P.new_act(N, fs << lvl, sizes[lvl])
         P.t_deconv(inp, blk.transp_conv.conv.weight, cats[lvl][0])
-        _t_conv_3_1(P, blk.conv_block.cov_, cats[lvl], out)
+        if isinstance(cov, nw.conv_3_1_old):
+            _t_conv_3_1_old(P, cov, cats[lvl], out)
+        else:
+            _t_conv_3_1(P, cov, cats[lvl], out)
         decs.append(out)
         inp = out
     return decs[::-1]
@@ -735,7 +757,7 @@ class SegTrainer(_Trainer):
     """One OAR-TRANSEG training step per call (`Transeg.training_step` + `configure_optimizers`,
     OARSegmentation/train_light_transeg.py:184-198): `loss = trainer.step(ct[B,1,S,S,S], label[B,1,S,S,S])` with
     DiceCELoss(to_onehot_y=True, softmax=True) and AdamW(1e-4, weight_decay 1e-5); every parameter is trained.
-    model: dose_prediction_b200.networks.OARTranseg (the Models/ variant with the multi-scale conv_3_1 decoder)."""
+    model: dose_prediction_b200.networks.OARTranseg (Models/, mode_model=0) or networks.TRANSEG (OldModels/, mode_model=1)."""
 
     def __init__(self, model, batch, size, lr=1e-4, weight_decay=1e-5, betas=(0.9, 0.999), eps=1e-8, loss_scale=4096.0,
                  process_group=None, probe=None):

@@ -588,3 +588,38 @@ def test_training_step_matches_oracle_64():
         cos = float(F.cosine_similarity(g[n].flatten().double().cpu(), grads_ref[n].flatten().double(), dim=0))
         assert cos > 0.99, (n, cos)
         assert abs(float(g[n].norm()) / float(grads_ref[n].norm()) - 1.0) < 0.06, n
+
+
+def test_old_transeg_training_step_matches_oracle_32():
+    """OldModels TRANSEG (train_light_transeg.py mode_model=1; BatchNorm in both decoder branches, bare 1^3 conv)."""
+    from dose_prediction_b200 import networks, synth
+    from dose_prediction_b200.training import SegTrainer
+    from oracle import synth_ckpt, torch_ref
+    man = [(k, ([1, 8, s[2]] if k.endswith("position_embeddings") else s)) for k, s, *_ in load_manifest("transeg_old_96")]
+    sd = synth_ckpt.make_state_dict(man, seed=2)
+    model = networks.TRANSEG(1, 8, (32,) * 3, pos_embed="perceptron")
+    model.load_state_dict(sd, strict=True)
+    model = model.to(DEV).train()
+    vol = synth.make_batch(2, 32, seed=1234)
+    label = synth.oar_labels(vol["oars"])
+    loss_ref, grads_ref, new_ref, logits_ref = torch_ref.oar_transeg_train_step(sd, vol["ct"], label, old=True)
+    tr = SegTrainer(model, 2, 32)
+    loss = tr.step(vol["ct"].to(DEV), label.to(DEV))
+    torch.cuda.synchronize()
+    tr.P.check_device_errors()
+    assert abs(float(loss) - float(loss_ref)) <= 2e-3 * abs(float(loss_ref))
+    assert _rel(tr.logits(), logits_ref) < 1e-2
+    g = tr.grads()
+    gmax = max(float(v.norm()) for v in grads_ref.values())
+    checked = 0
+    for n, ref in grads_ref.items():
+        if float(ref.norm()) < 1e-4 * gmax:
+            continue
+        cos = float(F.cosine_similarity(g[n].flatten().double().cpu(), ref.flatten().double(), dim=0))
+        assert cos > 0.99, (n, cos)
+        checked += 1
+    assert checked > 60
+    bn = "decoder2.conv_block.cov_.conv_3.conv.1."
+    after = model.state_dict()
+    assert _rel(after[bn + "running_mean"], new_ref[bn + "running_mean"]) < 1e-3
+    assert _rel(after[bn + "running_var"], new_ref[bn + "running_var"]) < 1e-3
