@@ -69,6 +69,7 @@ _SIGNATURES = {
     "dp_dose_postprocess": [P, P, L, F, P, P],
     "dp_dose_stats": [P, P, P, L, P, I, P, P, P, P, P],
     "dp_dvh_metrics": [P, P, P, I, P, L, F, P, P, P, P],
+    "dp_dice_metric": [P, P, I, I, L, P, P, P, P],
     # ---- input pipeline
     "dp_prepare_input": [P, P, P, P, P, P, I, I, I, F, F, F, P, P, P],
     "dp_flip_rot90": [P, P, I, I, I, I, I, I, I, I, P],

@@ -210,6 +210,52 @@ __global__ void dvh_scan_kernel(int n_struct, int pass, const int* is_target, fl
   }
 }
 
+// ------------------------------------------------------------------ seg validation: Dice per (volume, class)
+// monai 0.7.0 DiceMetric(include_background=False) on post_pred = one-hot(argmax) vs the label map
+// (OARSegmentation/train_light_transeg.py:199-216, config.py:69-70): counts[n][c] = {|pred==c & label==c|, |label==c|, |pred==c|}
+__global__ void __launch_bounds__(256) dice_counts_kernel(const float* logits, const float* label, int C, long long vox,
+                                                          unsigned long long* counts) {
+  __shared__ unsigned int sh[16][3];
+  const int n = blockIdx.y;
+  if (threadIdx.x < 48) (&sh[0][0])[threadIdx.x] = 0u;
+  __syncthreads();
+  for (long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v < vox;
+       v += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float* z = logits + static_cast<size_t>(n) * C * vox + v;
+    int best = 0;
+    float bv = z[0];
+    for (int c = 1; c < C; ++c) {
+      const float x = z[static_cast<size_t>(c) * vox];
+      if (x > bv) { bv = x; best = c; }                    // first maximum wins (torch.argmax)
+    }
+    const int lab = static_cast<int>(label[static_cast<size_t>(n) * vox + v]);
+    atomicAdd(&sh[best][2], 1u);
+    if (lab >= 0 && lab < C) {
+      atomicAdd(&sh[lab][1], 1u);
+      if (lab == best) atomicAdd(&sh[lab][0], 1u);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < C * 3) {
+    const unsigned int val = (&sh[0][0])[threadIdx.x];
+    if (val) atomicAdd(&counts[static_cast<size_t>(n) * 48 + threadIdx.x], static_cast<unsigned long long>(val));
+  }
+}
+// dice[n][c] = 2 I / (G + P) (NaN when the class is absent from the label, like monai); mean over the non-NaN foreground entries
+__global__ void dice_finalize_kernel(const unsigned long long* counts, int N, int C, float* dice, float* mean_dice) {
+  double sum = 0.0;
+  int cnt = 0;
+  for (int n = 0; n < N; ++n)
+    for (int c = 0; c < C; ++c) {
+      const unsigned long long* q = counts + static_cast<size_t>(n) * 48 + c * 3;
+      float d = nanf("");
+      if (q[1] > 0) d = static_cast<float>(2.0 * static_cast<double>(q[0]) / static_cast<double>(q[1] + q[2]));
+      dice[n * C + c] = d;
+      if (c >= 1 && q[1] > 0) { sum += d; ++cnt; }
+    }
+  *mean_dice = cnt ? static_cast<float>(sum / cnt) : nanf("");
+}
+
 static inline unsigned eblk(long long n, int threads, unsigned cap) {
   const long long b = (n + threads - 1) / threads;
   return static_cast<unsigned>(b < cap ? b : cap);
@@ -259,4 +305,15 @@ extern "C" int dp_dvh_metrics(const float* pred, const float* gt, const float* m
     DP_CHECK(cudaGetLastError());
   }
   return 0;
+}
+
+extern "C" int dp_dice_metric(const float* logits, const float* label, int N, int C, long long vox, unsigned long long* counts,
+                              float* dice, float* mean_dice, cudaStream_t stream) {
+  DP_REQUIRE(C >= 2 && C <= 16, "dice_metric: 2..16 classes");
+  DP_CHECK(cudaMemsetAsync(counts, 0, static_cast<size_t>(N) * 48 * sizeof(unsigned long long), stream));
+  dim3 grid(eblk(vox, 256, 4 * 148), static_cast<unsigned>(N));
+  dice_counts_kernel<<<grid, 256, 0, stream>>>(logits, label, C, vox, counts);
+  DP_CHECK(cudaGetLastError());
+  dice_finalize_kernel<<<1, 1, 0, stream>>>(counts, N, C, dice, mean_dice);
+  return check_cuda(cudaGetLastError(), "dice_metric");
 }

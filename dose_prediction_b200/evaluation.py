@@ -84,3 +84,22 @@ class DoseEvaluator:
                 out["pre" + n + "_" + mname] = float(dvh[i, 0, c])
                 out["gt_" + n + "_" + mname] = float(dvh[i, 1, c])
         return out
+
+
+def dice_metric(logits, label):
+    """Mean foreground Dice of one-hot(argmax(logits)) vs the label map, as Transeg.validation_step computes it with
+    monai's DiceMetric(include_background=False) (OARSegmentation/train_light_transeg.py:199-216).
+    logits [N,C,D,H,W] fp32 CUDA, label [N,1,D,H,W] class indices.  Returns (mean_dice [1], dice [N,C]) on the device."""
+    if not logits.is_cuda:
+        raise RuntimeError("dose_prediction_b200 evaluates on CUDA devices only (no CPU fallback)")
+    lib = _lib.lib()
+    x = logits.contiguous().float()
+    lab = label.to(x.device).contiguous().float()
+    N, C = x.shape[0], x.shape[1]
+    vox = x.numel() // (N * C)
+    counts = torch.zeros(N * 48, dtype=torch.int64, device=x.device)
+    dice = torch.zeros((N, C), device=x.device)
+    mean = torch.zeros(1, device=x.device)
+    _lib.check(lib.dp_dice_metric(x.data_ptr(), lab.data_ptr(), N, C, vox, counts.data_ptr(), dice.data_ptr(), mean.data_ptr(),
+                                  torch.cuda.current_stream(x.device).cuda_stream), "dp_dice_metric")
+    return mean, dice

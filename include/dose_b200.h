@@ -349,6 +349,13 @@ int dp_prepare_input(const void* const* ptv_u8, const void* const* oar_u8, const
 int dp_flip_rot90(const float* in, float* out, int C, int S0, int S1, int S2, int flip0, int flip1, int flip2, int k,
                   cudaStream_t stream);
 
+/* Seg validation metric: monai 0.7.0 DiceMetric(include_background=False, reduction="mean") on one-hot(argmax(logits))
+ * vs the label map (OARSegmentation/train_light_transeg.py:199-216).  logits: NCDHW fp32 [N][C][vox]; label: fp32 class
+ * index [N][vox]; counts: uint64[N*48] scratch; dice: float[N][C] (NaN where the class is absent from the label);
+ * mean_dice: float[1], mean over the non-NaN foreground entries.                                               */
+int dp_dice_metric(const float* logits, const float* label, int N, int C, long long vox, unsigned long long* counts,
+                   float* dice, float* mean_dice, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

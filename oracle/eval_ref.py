@@ -53,3 +53,20 @@ def evaluate(pred, gt, possible_dose_mask, structures, spacing):
                 out["table"]["gt_" + name + "_" + k] = float(b[k])
     out["dvh_dif"] = float(np.mean(difs))
     return out
+
+
+def dice_metric(logits, label):
+    """monai 0.7.0 DiceMetric(include_background=False, reduction="mean", get_not_nans=False) applied to
+    post_pred = AsDiscrete(argmax=True, to_onehot=True) and post_label (OARSegmentation/config.py:69-70,
+    train_light_transeg.py:199-216): compute_meandice gives 2|y & y_pred| / (|y| + |y_pred|) per (batch, class), NaN when
+    the class is absent from y; the mean ignores NaNs.  (un-vendored monai code, restated.)"""
+    n_cls = logits.shape[1]
+    pred = logits.argmax(1)
+    lab = label[:, 0].astype(np.int64)
+    vals = []
+    for b in range(logits.shape[0]):
+        for c in range(1, n_cls):
+            y, yp = lab[b] == c, pred[b] == c
+            if y.sum() > 0:
+                vals.append(2.0 * np.logical_and(y, yp).sum() / (y.sum() + yp.sum()))
+    return float(np.mean(vals)) if vals else float("nan")

@@ -75,3 +75,20 @@ def test_evaluator_edge_cases():
     assert abs(float(res["dose_dif"]) - want["dose_dif"]) <= 2e-6 * want["dose_dif"]
     assert np.allclose(res["ivs"].cpu().numpy(), np.array(want["ivs"]), rtol=0, atol=1e-6)
     assert abs(float(res["dvh_dif"]) - want["dvh_dif"]) <= 1e-5
+
+
+def test_dice_metric_matches_oracle():
+    from dose_prediction_b200 import synth
+    from dose_prediction_b200.evaluation import dice_metric
+    from oracle import eval_ref
+    vol = synth.make_batch(2, 32, seed=8)
+    label = synth.oar_labels(vol["oars"])
+    label[1][label[1] == 3] = 0                                   # class 3 absent from the second volume
+    torch.manual_seed(0)
+    onehot = torch.nn.functional.one_hot(label[:, 0].long(), 8).permute(0, 4, 1, 2, 3).float()
+    logits = 2.0 * onehot + torch.randn(2, 8, 32, 32, 32)
+    mean, dice = dice_metric(logits.to(DEV), label.to(DEV))
+    torch.cuda.synchronize()
+    want = eval_ref.dice_metric(logits.numpy(), label.numpy())
+    assert abs(float(mean) - want) < 1e-6
+    assert torch.isnan(dice[1, 3]).item() and not torch.isnan(dice[0, 3]).item()
