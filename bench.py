@@ -116,7 +116,7 @@ def _cpu_cascade(seg_sd, dose_sd, vol, torch_ref):
         return torch_ref.dose_pyfer_forward(dose_sd, st)[1][0]
 
 
-def cpu_baseline(seg_sd, dose_sd, size, volumes=1):
+def cpu_baseline(seg_sd, dose_sd, size, volumes=3):
     """oracle port timed on the host cores (reported baseline, not the optimisation target)."""
     import torch
 
