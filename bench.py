@@ -62,6 +62,15 @@ def _quiet_nccl():
     pass
 
 
+def _build_once(entry, dist, world, local):
+    """compile (if stale) on local rank 0 only; the other ranks wait, then just load the library."""
+    if world > 1:
+        if local == 0:
+            entry.build()
+        dist.barrier()
+    entry.build()
+
+
 class ClockSampler:
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -221,7 +230,7 @@ def run_train(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         _quiet_nccl()
         dist.init_process_group("nccl", device_id=dev)
-    __graft_entry__.build()
+    _build_once(__graft_entry__, dist, world, local)
     _, dose = build_models(S, dev)
     dose.train()
     tr = DoseTrainer(dose, B, S, lr=1e-4, weight_decay=1e-4)
@@ -339,7 +348,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         _quiet_nccl()
         dist.init_process_group("nccl", device_id=dev)
-    __graft_entry__.build()
+    _build_once(__graft_entry__, dist, world, local)
 
     B, S = args.batch, args.size
     seg, dose = build_models(S, dev, seg_size=args.sw_roi or None)
