@@ -29,6 +29,7 @@ from .engine import ACT_ID, Act, LiveWeight, Plan, Raw, Tokens, blocks16, ceil_d
 from . import networks as nw
 
 ARENA_DOUBLES = 1 << 22
+DDP_OVERLAP = os.environ.get("DP_DDP_OVERLAP", "1") != "0"  # all-reduce the decoder/head gradients while the encoder backward runs
 WGRAD_TC = os.environ.get("DP_WGRAD_TC", "1") != "0"      # bring-up switch: tcgen05 vs CUDA-core conv weight gradient
 
 
@@ -576,6 +577,7 @@ def _t_unetr(P, vit, enc_blocks, dec_blocks, parts, taps):
     _t_pr_up(P, enc_blocks[1], hs[taps[0]], cats[1][1])
     _t_pr_up(P, enc_blocks[2], hs[taps[1]], cats[2][1])
     _t_pr_up(P, enc_blocks[3], hs[taps[2]], cats[3][1])
+    P.tape.append(("mark", "decoders"))          # everything recorded after this point runs its backward before it
     decs, inp = [], z
     for lvl, blk in zip((3, 2, 1, 0), dec_blocks):
         cov = getattr(getattr(blk, "conv_block", None), "cov_", None)
@@ -653,17 +655,48 @@ class _Trainer:
         self.loss = P.zeros((1,), torch.float32)
 
     def _finish_emit(self):
+        """unroll the tape in reverse; small-parameter gradients are finalised right after the op that produced them,
+        so that at the "decoders done" mark the tail of the flat gradient buffer is complete and its all-reduce can
+        start while the encoder / ViT backward is still running."""
         P = self.P
-        for bwd in reversed(P.tape):
-            bwd()
-        for acc64, g, n in P.finalizers:
-            P.add("dp_grad_finalize", acc64.data_ptr(), g.data_ptr(), n, 1.0)
+        done = 0
+        for entry in reversed(P.tape):
+            if isinstance(entry, tuple) and entry[0] == "mark":
+                if entry[1] == "decoders" and self.tail_off is not None:
+                    P.add_py(self._start_tail_allreduce)
+                continue
+            entry()
+            for acc64, g, n in P.finalizers[done:]:
+                P.add("dp_grad_finalize", acc64.data_ptr(), g.data_ptr(), n, 1.0)
+            done = len(P.finalizers)
+
+    def _set_tail(self, prefixes):
+        """flat-buffer offset where the parameters of the modules whose backward runs FIRST begin (they must form the
+        tail of the buffer: named_parameters() lists encoders before decoders and heads)."""
+        names = [n for n, _ in self.params]
+        first = next((i for i, n in enumerate(names) if n.startswith(prefixes)), None)
+        self.tail_off = None
+        if first is not None and all(n.startswith(prefixes) for n in names[first:]) and DDP_OVERLAP:
+            self.tail_off = self.offsets[names[first]][0]
+        self._tail_work = None
+
+    def _start_tail_allreduce(self):
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            self._tail_work = dist.all_reduce(self.flat_g[self.tail_off:], group=self.group, async_op=True)
 
     def _run(self):
         P = self.P
         P.refresh_weights()
         P.run()
-        allreduce_mean_(self.flat_g, self.group)
+        if self._tail_work is not None:            # bucket 2 (decoders + heads) has been in flight since the mark
+            import torch.distributed as dist
+            dist.all_reduce(self.flat_g[:self.tail_off], group=self.group)
+            self._tail_work.wait()
+            self._tail_work = None
+            self.flat_g.div_(dist.get_world_size(self.group))
+        else:
+            allreduce_mean_(self.flat_g, self.group)
         return self.loss
 
     def _optimizer_step(self):
@@ -699,6 +732,7 @@ class DoseTrainer(_Trainer):
         self.delta1, self.delta2, self.probe = delta1, delta2, probe
         self._setup(model, lambda n: not (n.startswith("net_A") or n.startswith("conv_out_A")), lr, weight_decay, betas, eps,
                     loss_scale, process_group)
+        self._set_tail(("net_B.decoder.", "net_B.dose_convertors.", "net_B.out."))
         self._emit()
 
     def _emit(self):
@@ -763,6 +797,7 @@ class SegTrainer(_Trainer):
                  process_group=None, probe=None):
         self.batch, self.size, self.probe = batch, size, probe
         self._setup(model, lambda n: True, lr, weight_decay, betas, eps, loss_scale, process_group)
+        self._set_tail(("decoder5.", "decoder4.", "decoder3.", "decoder2.", "out."))
         self._emit()
 
     def _emit(self):
