@@ -45,13 +45,19 @@ struct GemmParams {
 
 constexpr int kGemmThreads = 320;        // producer + MMA + 8 epilogue warps (2 per TMEM lane quarter)
 constexpr int kGemmEpiWarps = 8;
-constexpr int BM = 128, BN = 128, BK = 64;
-constexpr int kGemmStages = 6;
-constexpr uint32_t kStageA = BM * BK * 2, kStageB = BN * BK * 2, kStage = kStageA + kStageB;
+constexpr int BM = 128, BK = 64;
+constexpr uint32_t kStageA = BM * BK * 2;
+// N tile: 128 (6 stages) or 256 (4 stages).  The ViT GEMMs are bound by the L2 -> SM operand stream (a 128 x 128
+// tile of a K = 768 problem pulls 393 KB for 1.6 us of MMA work); a 128 x 256 tile moves 25 % fewer bytes per FLOP.
+template <int BN> struct GemmCfg {
+  static constexpr int kStages = BN == 256 ? 4 : 6;
+  static constexpr uint32_t kStageB = BN * BK * 2, kStage = kStageA + kStageB;
+};
 
 struct GemmTile {
   int m0, n0, bz, sk, kb0, kb1;
 };
+template <int BN>
 __device__ __forceinline__ GemmTile gemm_tile(const GemmParams& p, int tile) {
   GemmTile t;
   const int tn = tile % p.tiles_n; tile /= p.tiles_n;
@@ -65,9 +71,12 @@ __device__ __forceinline__ GemmTile gemm_tile(const GemmParams& p, int tile) {
   return t;
 }
 
+template <int BN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ GemmParams p) {
+  constexpr int kGemmStages = GemmCfg<BN>::kStages;
+  constexpr uint32_t kStage = GemmCfg<BN>::kStage;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[kGemmStages];
   __shared__ uint64_t empty_bar[kGemmStages];
@@ -95,7 +104,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const GemmTile t = gemm_tile(p, tile);
+      const GemmTile t = gemm_tile<BN>(p, tile);
       const int a_row = t.bz * p.a_batch_rows + t.m0, b_row = t.bz * p.b_batch_rows + t.n0;
       for (int kb = t.kb0; kb < t.kb1; ++kb) {
         if (!mbar_wait_relaxed(&empty_bar[stage], phase ^ 1, p.err_flag)) goto teardown;
@@ -119,7 +128,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint32_t phase = 0;
     int iter = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++iter) {
-      const GemmTile t = gemm_tile(p, tile);
+      const GemmTile t = gemm_tile<BN>(p, tile);
       const int slot = iter & 1;
       if (!mbar_wait(&acc_empty[slot], ((iter >> 1) & 1) ^ 1, p.err_flag)) goto teardown;
       tc_fence_after();
@@ -156,11 +165,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   } else {
     // ===================================================================== epilogue (warps 2..9)
     const int quarter = warp & 3;
-    const int chalf = (warp - 2) >> 2;                      // which 64-column half of the accumulator
+    const int chalf = (warp - 2) >> 2;                      // which half of the accumulator's columns
     const bool vecN = (p.N % 16) == 0;
     int iter = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++iter) {
-      const GemmTile t = gemm_tile(p, tile);
+      const GemmTile t = gemm_tile<BN>(p, tile);
       const int slot = iter & 1;
       const int m = t.m0 + quarter * 32 + lane;
       const int n0 = t.n0;
@@ -185,9 +194,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           : static_cast<size_t>(t.bz) * p.c_batch_stride;
       const size_t row_base = boff + static_cast<size_t>(t.sk) * p.split_stride + static_cast<size_t>(m) * p.ldc;
 #pragma unroll 1
-      for (int cc = 0; cc < 4; cc += 2) {
+      for (int cc = 0; cc < BN / 32; cc += 2) {
         // two 16-column chunks in flight per iteration (ILP across the TMEM loads)
-        const int c0 = chalf * 64 + cc * 16;
+        const int c0 = chalf * (BN / 2) + cc * 16;
         if (n0 + c0 >= p.N) break;                          // warp-uniform
         uint32_t r[2][16];
         tmem_ld16(taddr + c0, r[0]);
@@ -328,8 +337,9 @@ teardown:
   }
 }
 
-static int launch_gemm(const void* A, const void* B, dp::GemmParams& p, int a_batch_rows, int b_batch_rows,
-                       cudaStream_t stream) {
+template <int BN>
+static int launch_gemm_bn(const void* A, const void* B, dp::GemmParams& p, int a_batch_rows, int b_batch_rows,
+                          cudaStream_t stream) {
   DP_REQUIRE(p.K % 8 == 0, "dp_gemm_tc: K=%d must be a multiple of 8 (TMA 16-byte row pitch)", p.K);
   DP_REQUIRE(p.batch >= 1 && p.split_k >= 1, "dp_gemm_tc: bad batch/split_k");
   p.total_kb = (p.K + BK - 1) / BK;
@@ -357,17 +367,30 @@ static int launch_gemm(const void* A, const void* B, dp::GemmParams& p, int a_ba
     if (int rc = encode_tiled(&tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, B, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))
       return rc;
   }
-  const size_t smem = static_cast<size_t>(kGemmStages) * kStage + 1024;
+  const size_t smem = static_cast<size_t>(GemmCfg<BN>::kStages) * GemmCfg<BN>::kStage + 1024;
   static bool configured = false;
   if (!configured) {
-    DP_CHECK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    DP_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     configured = true;
   }
   int grid = sm_count();
   if (grid > p.num_tiles) grid = p.num_tiles;
-  gemm_tc_kernel<<<grid, kGemmThreads, smem, stream>>>(ta, tb, p);
+  gemm_tc_kernel<BN><<<grid, kGemmThreads, smem, stream>>>(ta, tb, p);
   DP_CHECK(cudaGetLastError());
   return 0;
+}
+
+static int launch_gemm(const void* A, const void* B, dp::GemmParams& p, int a_batch_rows, int b_batch_rows,
+                       cudaStream_t stream) {
+  // wide-N problems with enough 256-wide tiles to fill the machine take the 128 x 256 tile
+  static const bool wide_ok = getenv("DP_GEMM_BN256") == nullptr || atoi(getenv("DP_GEMM_BN256")) != 0;
+  const long long tiles256 = static_cast<long long>((p.M + BM - 1) / BM) * ((p.N + 255) / 256) * p.batch * p.split_k;
+  // measured (batch-8 ViT, M = 4096): N = 768, K = 131072: 714 -> 1096 TFLOP/s; N = 3072 / 2304, K = 768: +8 %;
+  // N = 768, K = 768 (96 wide tiles, short K): -5 %, so under one wave of wide tiles only long-K problems take them
+  static const int min_tiles = getenv("DP_GEMM_BN256_MIN") ? atoi(getenv("DP_GEMM_BN256_MIN")) : (sm_count() * 5) / 8;
+  if (wide_ok && p.N % 256 == 0 && tiles256 >= min_tiles && (tiles256 >= sm_count() || p.K >= 2048))
+    return launch_gemm_bn<256>(A, B, p, a_batch_rows, b_batch_rows, stream);
+  return launch_gemm_bn<128>(A, B, p, a_batch_rows, b_batch_rows, stream);
 }
 
 }  // namespace dp

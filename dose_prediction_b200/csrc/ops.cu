@@ -607,37 +607,69 @@ __global__ void __launch_bounds__(128) deconv2x_cw_kernel(const __grid_constant_
 }
 
 // ------------------------------------------------------------------ trilinear 2x, align_corners=True (c3d.py:36)
+// One thread writes the two W-neighbours wo = 2k, 2k+1 (one full 32-byte sector per plane): with align_corners the
+// source column of output 2k lies in (k-1, k] and that of 2k+1 in [k, k+1/2), so the pair reads the three columns
+// k-1, k, k+1 of four (d, h) lines -- 12 gathers for two outputs instead of 16.  Grid: x = (ho, k), y = dz,
+// z = (image, channel block); all index arithmetic is 32-bit.
 __global__ void __launch_bounds__(256)
 upsample2x_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo, int in_cb_total, int in_cb_off,
                   int ncb, int D, int H, int W, __half* out_hi, __half* out_lo, int out_cb_total, int out_cb_off) {
   const int Do = 2 * D, Ho = 2 * H, Wo = 2 * W;
-  const long long vox_o = static_cast<long long>(Do) * Ho * Wo, vox_i = static_cast<long long>(D) * H * W;
-  const long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  if (v >= vox_o) return;
-  const int cb = blockIdx.y % ncb, n = blockIdx.y / ncb;
-  const int wo = static_cast<int>(v % Wo), ho = static_cast<int>((v / Wo) % Ho), dz = static_cast<int>(v / (static_cast<long long>(Wo) * Ho));
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= static_cast<unsigned>(W) * Ho) return;
+  const int k = static_cast<int>(t % static_cast<unsigned>(W)), ho = static_cast<int>(t / static_cast<unsigned>(W));
+  const int dz = blockIdx.y;
+  const int cb = blockIdx.z % ncb, n = blockIdx.z / ncb;
   // torch area_pixel_compute_source_index(align_corners=True): src = dst * (in-1)/(out-1)
   const float sd = Do > 1 ? static_cast<float>(D - 1) / static_cast<float>(Do - 1) : 0.f;
   const float sh = Ho > 1 ? static_cast<float>(H - 1) / static_cast<float>(Ho - 1) : 0.f;
   const float sw = Wo > 1 ? static_cast<float>(W - 1) / static_cast<float>(Wo - 1) : 0.f;
-  const float fd = sd * dz, fh = sh * ho, fw = sw * wo;
-  const int d0 = static_cast<int>(fd), h0 = static_cast<int>(fh), w0 = static_cast<int>(fw);
-  const int d1 = min(d0 + 1, D - 1), h1 = min(h0 + 1, H - 1), w1 = min(w0 + 1, W - 1);
-  const float ld = fd - d0, lh = fh - h0, lw = fw - w0;
-  const size_t base = (static_cast<size_t>(n) * in_cb_total + in_cb_off + cb) * vox_i;
-  float acc[8];
+  const float fd = sd * dz, fh = sh * ho;
+  const int d0 = static_cast<int>(fd), h0 = static_cast<int>(fh);
+  const int d1 = min(d0 + 1, D - 1), h1 = min(h0 + 1, H - 1);
+  const float ld = fd - d0, lh = fh - h0;
+  // per output of the pair: weights on the columns (k-1, k, k+1)
+  float cw[2][3];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-#pragma unroll
-  for (int corner = 0; corner < 8; ++corner) {
-    const int dd = (corner & 4) ? d1 : d0, hh = (corner & 2) ? h1 : h0, ww = (corner & 1) ? w1 : w0;
-    const float wt = ((corner & 4) ? ld : 1.f - ld) * ((corner & 2) ? lh : 1.f - lh) * ((corner & 1) ? lw : 1.f - lw);
-    float x[8];
-    load8(in_hi, in_lo, (base + (static_cast<size_t>(dd) * H + hh) * W + ww) * 8, x);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = fmaf(wt, x[j], acc[j]);
+  for (int o = 0; o < 2; ++o) {
+    const float fw = sw * (2 * k + o);
+    const int w0 = static_cast<int>(fw);
+    const float lw = fw - w0;
+    const int pos = w0 - (k - 1);                       // 0 or 1
+    cw[o][0] = pos == 0 ? 1.f - lw : 0.f;
+    cw[o][1] = pos == 0 ? lw : 1.f - lw;
+    cw[o][2] = pos == 0 ? 0.f : lw;
   }
-  store8(out_hi, out_lo, ((static_cast<size_t>(n) * out_cb_total + out_cb_off + cb) * vox_o + v) * 8, acc);
+  const int col[3] = {max(k - 1, 0), k, min(k + 1, W - 1)};
+  const size_t vox_i = static_cast<size_t>(D) * H * W;
+  const size_t base = (static_cast<size_t>(n) * in_cb_total + in_cb_off + cb) * vox_i;
+  float acc[2][8];
+#pragma unroll
+  for (int o = 0; o < 2; ++o)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[o][j] = 0.f;
+#pragma unroll
+  for (int line = 0; line < 4; ++line) {
+    const int dd = (line & 2) ? d1 : d0, hh = (line & 1) ? h1 : h0;
+    const float wl = ((line & 2) ? ld : 1.f - ld) * ((line & 1) ? lh : 1.f - lh);
+    const size_t row = base + (static_cast<size_t>(dd) * H + hh) * W;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float x[8];
+      load8(in_hi, in_lo, (row + col[c]) * 8, x);
+      const float w_even = wl * cw[0][c], w_odd = wl * cw[1][c];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc[0][j] = fmaf(w_even, x[j], acc[0][j]);
+        acc[1][j] = fmaf(w_odd, x[j], acc[1][j]);
+      }
+    }
+  }
+  const size_t vox_o = vox_i * 8;
+  const size_t o0 = ((static_cast<size_t>(n) * out_cb_total + out_cb_off + cb) * vox_o +
+                     (static_cast<size_t>(dz) * Ho + ho) * Wo + 2 * k) * 8;
+  store8(out_hi, out_lo, o0, acc[0]);
+  store8(out_hi, out_lo, o0 + 8, acc[1]);
 }
 
 // ------------------------------------------------------------------ LayerNorm over the last dim (one warp per row)
@@ -1152,8 +1184,8 @@ extern "C" int dp_deconv2x_cw(const void* in_hi, const void* in_lo, long long in
 extern "C" int dp_upsample2x(const void* in_hi, const void* in_lo, int in_cb_total, int in_cb_off, int ncb, int N, int D,
                              int H, int W, void* out_hi, void* out_lo, int out_cb_total, int out_cb_off,
                              cudaStream_t stream) {
-  const long long vox_o = 8LL * D * H * W;
-  dim3 grid(blocks_for(vox_o, 256), N * ncb);
+  DP_REQUIRE(2 * D <= 65535 && N * ncb <= 65535, "dp_upsample2x: grid limits (2D=%d, N*ncb=%d)", 2 * D, N * ncb);
+  dim3 grid(blocks_for(2LL * H * W, 256), 2 * D, N * ncb);
   upsample2x_kernel<<<grid, 256, 0, stream>>>(static_cast<const __half*>(in_hi), static_cast<const __half*>(in_lo),
                                               in_cb_total, in_cb_off, ncb, D, H, W, static_cast<__half*>(out_hi),
                                               static_cast<__half*>(out_lo), out_cb_total, out_cb_off);
