@@ -21,6 +21,7 @@ _SIGNATURES = {
     "dp_conv3d_stack": [P, I, P, I, P, I, I, I, I, I, I, P, P, I, P, P, P, I, I, P, P, I, I, I, P],
     "dp_conv3d_direct": [P, P, I, I, I, I, I, I, I, I, I, I, P, P, P, I, I, P, P, P, I, I, P, P],
     "dp_gemm_tc": [P, P, I, I, I, I, I, I, L, I, L, I, I, P, P, I, P, F, I, P, I, P, I, I, I, I, I, P, P, P, F, P, P],
+    "dp_attention": [P, P, P, I, I, I, I, I, P, I, P, P],
     "dp_pack_ncdhw": [P, I, I, L, P, P, I, I, P],
     "dp_unpack_c8": [P, P, I, I, I, I, L, P, P],
     "dp_norm_act": [P, P, P, I, I, P, P, P, I, P, P, P, P, I, I, I, P, P, I, I, P, I, I, L, P, P, I, I, I, I, I, P],

@@ -6,7 +6,8 @@
 // tokens (deconv = GEMM [voxels, C_in] x [C_in, 8*C_out] with a pixel-shuffle scatter epilogue).
 //
 // Persistent: grid = min(#tiles, #SMs); every CTA walks tiles blockIdx.x + i*gridDim.x.  Tiles are
-// 128 x 128 x 64 (TMA 2-D boxes, 128-byte swizzle, 6-stage mbarrier ring that runs ahead across tiles);
+// 128 x 128 x 64, or 128 x 256 x 64 for wide-N problems (TMA 2-D boxes, 128-byte swizzle, 6- / 4-stage mbarrier ring
+// that runs ahead across tiles);
 // two 128-column TMEM accumulators so the epilogue of tile i overlaps the main loop of tile i+1.
 // Warp roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2..9 epilogue
 // (two warps per TMEM lane quarter, each draining 64 of the 128 accumulator columns).

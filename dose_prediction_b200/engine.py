@@ -281,6 +281,8 @@ class Plan:
                 label = f"N{args[5]} {args[6]}x{args[7]}x{args[8]} cout{args[9]} k{args[10]} dil{args[11]} chunks{args[3]}"
             elif name == "dp_gemm_tc":
                 label = f"M{args[2]} N{args[3]} K{args[4]} batch{args[5]} split{args[12]}"
+            elif name == "dp_attention":
+                label = f"B{args[3]} heads{args[4]} T{args[5]} hd{args[7]}"
             elif name == "dp_conv3d_direct":
                 label = f"cin{args[4]} N{args[5]} {args[6]}x{args[7]}x{args[8]} k{args[9]} s{args[10]} cout{args[16]}"
             elif name == "dp_deconv2x":
@@ -653,6 +655,12 @@ class Plan:
     def layernorm(self, x, gamma, beta, rows, cols, out_f16=None, out_f32=None):
         self.add("dp_layernorm", x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), rows, cols,
                  out_f16.data_ptr() if out_f16 is not None else None, out_f32.data_ptr() if out_f32 is not None else None)
+
+    def attention(self, q, k, vt, batch, heads, T, hd, out):
+        """fused softmax(q k^T) v -> merged heads (monai SABlock.forward); q is pre-scaled by the qkv GEMM epilogue"""
+        self.count_flops("dp_attention", 4.0 * batch * heads * T * T * hd)
+        self.add("dp_attention", q.data_ptr(), k.data_ptr(), vt.data_ptr(), batch, heads, T, vt.shape[-1], hd,
+                 out.data_ptr(), out.shape[-1], self.err.data_ptr())
 
     def softmax(self, s, rows, cols, p):
         self.add("dp_softmax", s.data_ptr(), rows, cols, s.shape[-1], p.data_ptr(), p.shape[-1])

@@ -17,6 +17,7 @@ initialisation); their own forward() is never called.  Each top-level forward() 
 shape) an engine.Plan — a static schedule of C-ABI kernel launches — and replays it.  Inference
 (eval-mode BatchNorm) only; there is no CPU / eager fallback.
 """
+import os
 from typing import Sequence, Tuple, Union
 
 import numpy as np
@@ -484,18 +485,23 @@ def _emit_vit(P, vit, parts, N, S, taps):
     k = P.zeros((N * heads, T, hd), torch.float16)
     Tp = ceil_div(T, 8) * 8          # TMA row pitch must be a multiple of 16 B: pad the key axis with zeros
     vt = P.zeros((N * heads, hd, Tp), torch.float16)
-    scores = P.zeros((N * heads, T, T), torch.float32)
-    probs = P.zeros((N * heads, T, Tp), torch.float16)
+    fused = hd in (64, 128) and os.environ.get("DP_FUSED_ATTENTION", "1") != "0"
+    if not fused:
+        scores = P.zeros((N * heads, T, T), torch.float32)
+        probs = P.zeros((N * heads, T, Tp), torch.float16)
     o = P.zeros((M, hidden), torch.float16)
     hmid = P.zeros((M, vit.mlp_dim), torch.float16)
     hs = {}
     for i, blk in enumerate(vit.blocks):
         P.layernorm(x, P.dev(blk.norm1.weight), P.dev(blk.norm1.bias), M, hidden, out_f16=ln)
         P.gemm(ln, P.dev(blk.attn.qkv.weight, torch.float16), M, 3 * hidden, hidden, qkv=(heads, hd, T, q, k, vt, hd ** -0.5))
-        P.gemm(q, k, T, T, hd, batch=N * heads, a_batch_rows=T, b_batch_rows=T, c_batch_stride=T * T, ldc=T, out_f32=scores)
-        P.softmax(scores, N * heads * T, T, probs)
-        P.gemm(probs, vt, T, hd, Tp, batch=N * heads, a_batch_rows=T, b_batch_rows=hd, c_batch_stride=T * hidden,
-               c_batch_period=heads, c_batch_stride2=hd, ldc=hidden, out_f16=o)
+        if fused:
+            P.attention(q, k, vt, N, heads, T, hd, o)
+        else:
+            P.gemm(q, k, T, T, hd, batch=N * heads, a_batch_rows=T, b_batch_rows=T, c_batch_stride=T * T, ldc=T, out_f32=scores)
+            P.softmax(scores, N * heads * T, T, probs)
+            P.gemm(probs, vt, T, hd, Tp, batch=N * heads, a_batch_rows=T, b_batch_rows=hd, c_batch_stride=T * hidden,
+                   c_batch_period=heads, c_batch_stride2=hd, ldc=hidden, out_f16=o)
         P.gemm(o, P.dev(blk.attn.out_proj.weight, torch.float16), M, hidden, hidden, bias=P.dev(blk.attn.out_proj.bias),
                resid=x, out_f32=x)
         P.layernorm(x, P.dev(blk.norm2.weight), P.dev(blk.norm2.bias), M, hidden, out_f16=ln)

@@ -88,6 +88,14 @@ int dp_gemm_tc(const void* A, const void* B, int M, int N, int K, int batch, int
                void* out_f16, int mode_qkv, int heads, int hd, int T, int vt_ld, void* q, void* k, void* vt, float q_scale,
                int* err_flag, cudaStream_t stream);
 
+/* Fused attention of monai SABlock.forward for one ViT layer: out[b*T + t][h*hd + d] = softmax_y(q . k^T)[t][y] v[y][d]
+ * (einsum "blxd,blyd->blxy" * scale, softmax(-1), einsum "bhxy,bhyd->bhxd", rearrange "b h l d -> b l (h d)"), with
+ * q (pre-scaled), k [batch*heads][T][hd] and v^T [batch*heads][hd][vt_ld] as written by dp_gemm_tc(mode_qkv).
+ * Scores and probabilities stay in TMEM / shared memory.  hd in {64, 128}; other head sizes use
+ * dp_gemm_tc + dp_softmax + dp_gemm_tc.                                                                     */
+int dp_attention(const void* q, const void* k, const void* vt, int batch, int heads, int T, int vt_ld, int hd,
+                 void* out, int ld_out, int* err_flag, cudaStream_t stream);
+
 /* Deterministic split-K finish: out[m][n] = sum_s ws[s][m][n] + bias[n] + rowvec[m % row_period][n]
  * (dp_gemm_tc with split_k > 1 writes the fp32 partials ws[split_k][M][N]; no atomics anywhere). */
 int dp_splitk_reduce(const float* ws, int splits, int M, int N, const float* bias, const float* rowvec, int row_period,

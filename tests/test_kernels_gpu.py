@@ -181,6 +181,34 @@ def test_attention_pipeline_matches_torch(T, heads, hd):
     assert _rel(o.float().cpu(), want) < 4e-3       # q, k, v, p rounded to fp16
 
 
+@pytest.mark.parametrize("T,heads,hd", [(512, 6, 128), (512, 12, 64), (8, 12, 64), (216, 12, 64), (27, 6, 128), (1728, 3, 64)])
+def test_fused_attention_matches_torch_and_the_unfused_pipeline(T, heads, hd):
+    """dp_attention (scores / probabilities never leave the SM) == monai SABlock.forward without the projections."""
+    torch.manual_seed(4)
+    dev = torch.device("cuda:0")
+    Bn, hidden = 2, heads * hd
+    M = Bn * T
+    xin = torch.randn(M, hidden, device=dev).half()
+    wqkv = (torch.randn(3 * hidden, hidden, device=dev) / hidden ** 0.5).half()
+    wqkv[:hidden] *= 3.0                             # sharper softmax: exercises the max subtraction
+    P = _plan()
+    q = P.zeros((Bn * heads, T, hd), torch.float16)
+    k = P.zeros((Bn * heads, T, hd), torch.float16)
+    Tp = (T + 7) // 8 * 8
+    vt = P.zeros((Bn * heads, hd, Tp), torch.float16)
+    o = P.zeros((M, hidden), torch.float16)
+    o.fill_(float("nan"))
+    P.gemm(xin, wqkv, M, 3 * hidden, hidden, qkv=(heads, hd, T, q, k, vt, hd ** -0.5))
+    P.attention(q, k, vt, Bn, heads, T, hd, o)
+    P.run()
+    _finish(P)
+    qkv = (xin.double().cpu() @ wqkv.double().cpu().t()).reshape(Bn, T, 3, heads, hd).permute(2, 0, 3, 1, 4)
+    att = torch.softmax(qkv[0] @ qkv[1].transpose(-1, -2) * hd ** -0.5, dim=-1)
+    want = (att @ qkv[2]).permute(0, 2, 1, 3).reshape(M, hidden)
+    assert torch.isfinite(o).all()
+    assert _rel(o.float().cpu(), want) < 4e-3       # q, k, v, p rounded to fp16
+
+
 def test_norm_act_residual_and_chained_stats():
     torch.manual_seed(5)
     dev = torch.device("cuda:0")
