@@ -418,7 +418,8 @@ def main():
     total_fam = sum(v["ms"] for v in fam.values()) or 1.0
     names = {"dp_conv3d_stack": "conv3d_stack_kernel (tcgen05 depth-stacked implicit-GEMM conv, C_out 16/32)",
              "dp_conv3d_tc": "conv3d_tc_kernel (tcgen05 implicit-GEMM conv, C_out >= 64 / dilated)",
-             "dp_gemm_tc": "gemm_tc_kernel (tcgen05 GEMM: ViT linears, attention, patch embedding)"}
+             "dp_gemm_tc": "gemm_tc_kernel (tcgen05 GEMM: ViT linears, patch embedding, token deconvs)",
+             "dp_attention": "attention_kernel (tcgen05 QK^T / PV with the softmax in TMEM + smem)"}
 
     def tensor_roofline(key):
         ms_k = fam.get(key, {}).get("ms", 0.0)

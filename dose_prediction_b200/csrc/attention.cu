@@ -5,7 +5,7 @@
 // Exact two-pass softmax instead of an online rescale: pass 1 recomputes S = Q K_j^T per 128-key block and keeps
 // only the running row maximum m (thread = query row, so no shuffles and no exponentials); pass 2 recomputes S,
 // writes P = exp(S - m) as fp16 into a 128B-swizzled K-major smem tile and accumulates O += P V_j in TMEM.  The
-// row sum l is accumulated from the rounded fp16 P, and O is divided by l in the epilogue.  QK^T is 2 % of the
+// row sum l is accumulated in fp32 next to it, and O is divided by l in the epilogue.  QK^T is 2 % of the
 // ViT's FLOPs, so computing it twice is cheaper than a TMEM round trip of O per key block.
 //
 // Operands: q, k [BH][T][HD] fp16 (q pre-scaled by hd^-0.5 in the qkv GEMM epilogue), v^T [BH][HD][Tp] fp16 (zero
@@ -55,6 +55,20 @@ __device__ __forceinline__ void attn_umma(uint32_t tmem_d, uint32_t a16, uint32_
       "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
       ::"r"(tmem_d), "r"(d_lo_c | (a16 & 0x3FFFu)), "r"(d_hi), "r"(d_lo_c | (b16 & 0x3FFFu)), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// keys >= valid of a 32-column score slab -> -inf
+__device__ __forceinline__ void mask_keys(uint32_t (&r)[2][16], int c0, int valid) {
+#pragma unroll
+  for (int u = 0; u < 2; ++u)
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (c0 + u * 16 + i >= valid) r[u][i] = 0xff800000u;
 }
 
 template <int HD>
@@ -175,7 +189,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     // ---- pass 1: row maximum
     for (int it = 0; it < nkb; ++it) {
       const int valid = min(128, p.T - it * 128);
-      if (!mbar_wait_relaxed(&s_full, it & 1, p.err_flag)) goto teardown;
+      if (!mbar_wait(&s_full, it & 1, p.err_flag)) goto teardown;
       tc_fence_after();
 #pragma unroll 1
       for (int c0 = 0; c0 < 128; c0 += 32) {
@@ -183,11 +197,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         tmem_ld16(t_s + c0, r[0]);
         tmem_ld16(t_s + c0 + 16, r[1]);
         tmem_ld_wait();
+        if (valid < 128) mask_keys(r, c0, valid);                   // warp-uniform: only the ragged last block
 #pragma unroll
         for (int u = 0; u < 2; ++u)
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (c0 + u * 16 + i < valid) m = fmaxf(m, __uint_as_float(r[u][i]));
+          for (int i = 0; i < 16; ++i) m = fmaxf(m, __uint_as_float(r[u][i]));
       }
       tc_fence_before();
       __syncwarp();
@@ -195,14 +209,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     }
     // ---- pass 2: P = exp(S - m) -> smem, l = sum P
     const float mb = m * kLog2e;
-    float l = 0.f;
+    float l0 = 0.f, l1 = 0.f;
     uint8_t* prow = sP + row * 128;
     for (int j = 0; j < nkb; ++j) {
       const int it = nkb + j;
       const int valid = min(128, p.T - j * 128);
-      if (!mbar_wait_relaxed(&s_full, it & 1, p.err_flag)) goto teardown;
+      if (!mbar_wait(&s_full, it & 1, p.err_flag)) goto teardown;
       tc_fence_after();
-      if (!mbar_wait_relaxed(&p_empty, (j & 1) ^ 1, p.err_flag)) goto teardown;     // P V_{j-1} has read the tile
+      if (!mbar_wait(&p_empty, (j & 1) ^ 1, p.err_flag)) goto teardown;     // P V_{j-1} has read the tile
 #pragma unroll 1
       for (int c0 = 0; c0 < 128; c0 += 32) {
         uint32_t r[2][16];
@@ -214,17 +228,17 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           __syncwarp();
           if (lane == 0) mbar_arrive(&s_empty);
         }
+        if (valid < 128) mask_keys(r, c0, valid);                   // exp2(-inf) = 0
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
           __align__(16) __half2 h[8];
 #pragma unroll
           for (int i = 0; i < 16; i += 2) {
-            const int c = c0 + u * 16 + i;
-            const float e0 = c < valid ? exp2f(fmaf(__uint_as_float(r[u][i]), kLog2e, -mb)) : 0.f;
-            const float e1 = c + 1 < valid ? exp2f(fmaf(__uint_as_float(r[u][i + 1]), kLog2e, -mb)) : 0.f;
+            const float e0 = ex2_approx(fmaf(__uint_as_float(r[u][i]), kLog2e, -mb));
+            const float e1 = ex2_approx(fmaf(__uint_as_float(r[u][i + 1]), kLog2e, -mb));
             h[i >> 1] = __floats2half2_rn(e0, e1);
-            const float2 f = __half22float2(h[i >> 1]);
-            l += f.x + f.y;
+            l0 += e0;                                               // two chains; the fp16 rounding of P averages out
+            l1 += e1;                                               // over the row (relative 2^-12 / sqrt(T))
           }
           // keys c0 + u*16 .. +15 = 16-byte units 2*(c0%64/16 ...) of chunk c0/64; 128B swizzle: unit ^= row & 7
           const int chunk = c0 >> 6, unit0 = ((c0 & 63) >> 3) + u * 2;
@@ -241,7 +255,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     if (!mbar_wait_relaxed(&o_full, 0, p.err_flag)) goto teardown;
     tc_fence_after();
     {
-      const float inv_l = 1.f / l;
+      const float inv_l = 1.f / (l0 + l1);
       const int t = q0 + row;
       const int b = bh / p.heads, hh = bh % p.heads;
       __half* dst = p.out + (static_cast<size_t>(b) * p.T + t) * p.ld_out + hh * HD;
