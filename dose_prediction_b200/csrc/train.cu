@@ -368,6 +368,10 @@ __global__ void __launch_bounds__(256) small_wgrad_kernel(const SmallWgradParams
   const long long per = (total + p.vsplit - 1) / p.vsplit;
   const long long v_begin = split * per, v_end = min(total, v_begin + per);
   const long long gvox = p.deconv ? p.vox * 8 : p.vox;
+  // (image, voxel) of the tile's first voxel: one 64-bit division per tile, then increments (the staging loop used
+  // to spend more instructions on 64-bit div / mod per item than the FMA loop on arithmetic)
+  int n_base = static_cast<int>(v_begin / p.vox);
+  long long v_base = v_begin - n_base * p.vox;
   for (long long base = v_begin; base < v_end; base += SW_V) {
     // stage: 64 voxels x (2 co blocks + 4 ci blocks) of 8 channels
     for (int i = threadIdx.x; i < SW_V * 6; i += blockDim.x) {
@@ -377,15 +381,18 @@ __global__ void __launch_bounds__(256) small_wgrad_kernel(const SmallWgradParams
 #pragma unroll
       for (int j = 0; j < 8; ++j) t[j] = 0.f;
       if (gv < v_end) {
-        const int n = static_cast<int>(gv / p.vox);
-        const long long v = gv % p.vox;
+        int n = n_base;
+        long long v = v_base + vi;
+        while (v >= p.vox) { v -= p.vox; ++n; }
         if (blk < 2) {
           const int cb = (co0 >> 3) + blk;
           if (cb * 8 < p.g_C) {
             long long vo = v;
             if (p.deconv) {
-              const int w = static_cast<int>(v % p.W), h = static_cast<int>((v / p.W) % p.H);
-              const int d = static_cast<int>(v / (static_cast<long long>(p.W) * p.H));
+              const unsigned v32 = static_cast<unsigned>(v), hw = static_cast<unsigned>(p.W) * p.H;
+              const int d = static_cast<int>(v32 / hw);
+              const unsigned r2 = v32 - d * hw;
+              const int h = static_cast<int>(r2 / p.W), w = static_cast<int>(r2 - h * p.W);
               vo = (static_cast<long long>(2 * d + (o >> 2)) * (2 * p.H) + 2 * h + ((o >> 1) & 1)) * (2 * p.W) + 2 * w + (o & 1);
             }
             load_grad8(p.g, n, cb, gvox, vo, t);
@@ -430,6 +437,8 @@ __global__ void __launch_bounds__(256) small_wgrad_kernel(const SmallWgradParams
       for (int vi = 0; vi < SW_V; ++vi) bsum += gs[vi][threadIdx.x];
     }
     __syncthreads();
+    v_base += SW_V;
+    while (v_base >= p.vox) { v_base -= p.vox; ++n_base; }
   }
 #pragma unroll
   for (int a = 0; a < 4; ++a)
