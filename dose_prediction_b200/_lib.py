@@ -28,6 +28,7 @@ _SIGNATURES = {
     "dp_pointwise_conv": [I, P, P, P, P, P, P, P, P, P, P, I, I, L, P, P, P, I, I, P, P, I, P],
     "dp_pointwise_conv_cw": [I, P, P, P, P, P, P, P, P, P, P, I, I, L, P, P, P, I, I, P, P, I, P],
     "dp_deconv2x": [P, P, L, L, L, I, I, I, I, I, I, P, P, P, I, I, P],
+    "dp_deconv2x_tc": [P, I, P, I, P, I, I, I, I, I, I, I, P, P, P, P, I, I, P, P],
     "dp_deconv2x_cw": [P, P, L, L, I, I, I, I, I, I, P, P, P, I, I, P],
     "dp_deconv2x_gemm": [P, P, I, I, I, I, I, I, P, P, I, I, P, P],
     "dp_upsample2x": [P, P, I, I, I, I, I, I, I, P, P, I, I, P],

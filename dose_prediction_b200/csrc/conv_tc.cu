@@ -47,6 +47,8 @@ struct ConvTcParams {
   __half* out_hi;
   __half* out_lo;
   int cb_total_out, cb_out_off;
+  int dc_co, dc_q0;          // > 0: ConvTranspose3d k2 s2 as a 1^3 conv with columns (parity q - dc_q0) * dc_co + co, scattered to
+                             // the output voxel (2d + (q >> 2), 2h + ((q >> 1) & 1), 2w + (q & 1)) of a [2D, 2H, 2W] tensor
   double* stats;
   int* err_flag;
   uint32_t tmem_cols;
@@ -311,8 +313,17 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
         if (valid) {
 #pragma unroll
           for (int b = 0; b < 2; ++b) {
-            const size_t cb = static_cast<size_t>(n) * p.cb_total_out + p.cb_out_off + (c0 >> 3) + b;
-            const size_t off = (cb * plane + vox) * 8;
+            size_t off;
+            if (p.dc_co > 0) {
+              const int col = c0 + b * 8;
+              const int q = p.dc_q0 + col / p.dc_co, co = col % p.dc_co;
+              const size_t cb = static_cast<size_t>(n) * p.cb_total_out + p.cb_out_off + (co >> 3);
+              const size_t vo = (static_cast<size_t>(2 * d + (q >> 2)) * (2 * p.H) + 2 * h + ((q >> 1) & 1)) * (2 * p.W) + 2 * w + (q & 1);
+              off = (cb * (8 * plane) + vo) * 8;
+            } else {
+              const size_t cb = static_cast<size_t>(n) * p.cb_total_out + p.cb_out_off + (c0 >> 3) + b;
+              off = (cb * plane + vox) * 8;
+            }
             if (p.out_f32 != nullptr) {
               float4* o = reinterpret_cast<float4*>(p.out_f32 + off);
               o[0] = make_float4(v[b * 8 + 0], v[b * 8 + 1], v[b * 8 + 2], v[b * 8 + 3]);
@@ -352,12 +363,12 @@ teardown:
 }  // namespace dp
 
 // =============================================================================== C ABI
-extern "C" int dp_conv3d_tc(const void* in_c8, int cb_total_in, const uint8_t* chunk_cb, int n_chunks,
-                            const void* wpack, int N, int D, int H, int W, int cout, int k, int dil,
-                            const float* scale, const float* shift, int relu, float* out_f32, void* out_hi,
-                            void* out_lo, int cb_total_out, int cb_out_off, double* stats, int* err_flag,
-                            int max_ctas, const uint32_t* tap_mask, cudaStream_t stream) {
-  using namespace dp;
+namespace dp {
+static int launch_conv_tc(const void* in_c8, int cb_total_in, const uint8_t* chunk_cb, int n_chunks,
+                          const void* wpack, int N, int D, int H, int W, int cout, int k, int dil,
+                          const float* scale, const float* shift, int relu, float* out_f32, void* out_hi,
+                          void* out_lo, int cb_total_out, int cb_out_off, double* stats, int* err_flag,
+                          int max_ctas, const uint32_t* tap_mask, int dc_co, int dc_q0, cudaStream_t stream) {
   DP_REQUIRE(cout % 16 == 0 && cout >= 16 && cout <= 256, "dp_conv3d_tc: C_out=%d must be a multiple of 16 in [16,256]", cout);
   DP_REQUIRE(k >= 1 && k <= 7 && (k & 1), "dp_conv3d_tc: kernel size %d unsupported", k);
   DP_REQUIRE(n_chunks >= 1 && n_chunks <= 192, "dp_conv3d_tc: n_chunks=%d out of range", n_chunks);
@@ -407,6 +418,7 @@ extern "C" int dp_conv3d_tc(const void* in_c8, int cb_total_in, const uint8_t* c
   p.out_f32 = out_f32; p.out_hi = static_cast<__half*>(out_hi); p.out_lo = static_cast<__half*>(out_lo);
   p.cb_total_out = cb_total_out; p.cb_out_off = cb_out_off;
   p.stats = stats; p.err_flag = err_flag;
+  p.dc_co = dc_co; p.dc_q0 = dc_q0;
   uint32_t cols = 32;
   while (cols < static_cast<uint32_t>(2 * T * cout)) cols <<= 1;
   p.tmem_cols = cols;
@@ -445,4 +457,27 @@ extern "C" int dp_conv3d_tc(const void* in_c8, int cb_total_in, const uint8_t* c
 #undef DP_TC_LAUNCH
   DP_CHECK(cudaGetLastError());
   return 0;
+}
+}  // namespace dp
+
+extern "C" int dp_conv3d_tc(const void* in_c8, int cb_total_in, const uint8_t* chunk_cb, int n_chunks,
+                            const void* wpack, int N, int D, int H, int W, int cout, int k, int dil,
+                            const float* scale, const float* shift, int relu, float* out_f32, void* out_hi,
+                            void* out_lo, int cb_total_out, int cb_out_off, double* stats, int* err_flag,
+                            int max_ctas, const uint32_t* tap_mask, cudaStream_t stream) {
+  return dp::launch_conv_tc(in_c8, cb_total_in, chunk_cb, n_chunks, wpack, N, D, H, W, cout, k, dil, scale, shift, relu,
+                            out_f32, out_hi, out_lo, cb_total_out, cb_out_off, stats, err_flag, max_ctas, tap_mask, 0, 0,
+                            stream);
+}
+
+extern "C" int dp_deconv2x_tc(const void* in_c8, int cb_total_in, const uint8_t* chunk_cb, int n_chunks,
+                              const void* wpack, int N, int D, int H, int W, int cout, int q0, int nq,
+                              const float* scale, const float* shift, void* out_hi, void* out_lo, int cb_total_out,
+                              int cb_out_off, int* err_flag, cudaStream_t stream) {
+  using namespace dp;
+  DP_REQUIRE(cout % 16 == 0 && nq >= 1 && q0 >= 0 && q0 + nq <= 8 && nq * cout <= 256,
+             "dp_deconv2x_tc: C_out=%d, parities [%d, %d) do not fit one 256-column launch", cout, q0, q0 + nq);
+  DP_REQUIRE(out_hi != nullptr, "dp_deconv2x_tc: no output tensor given");
+  return launch_conv_tc(in_c8, cb_total_in, chunk_cb, n_chunks, wpack, N, D, H, W, nq * cout, 1, 1, scale, shift, 0,
+                        nullptr, out_hi, out_lo, cb_total_out, cb_out_off, nullptr, err_flag, 0, nullptr, cout, q0, stream);
 }

@@ -24,6 +24,7 @@ STATS_DOUBLES = 1 << 20
 STACK_TILES = int(os.environ.get("DP_STACK_TILES", "0"))
 FOLD_P3 = os.environ.get("DP_FOLD_P3", "1") != "0"
 POINTWISE_CW = os.environ.get("DP_POINTWISE_CW", "1") != "0"     # bring-up switch: constant-bank weights for static 1^3 convs
+DECONV_TC = os.environ.get("DP_DECONV_TC", "1") != "0"          # bring-up switch: k2s2 transposed convs of c8 inputs on the tensor cores
 STACKED_CONV = os.environ.get("DP_STACKED_CONV", "1") != "0"    # bring-up switch between the two tcgen05 conv kernels
 EPS = 1e-5
 
@@ -590,6 +591,26 @@ class Plan:
             self.count_flops("dp_deconv2x_gemm", 2.0 * B * T * Ci * Co * 8)
             self.add("dp_deconv2x_gemm", src.t.data_ptr(), wnk.data_ptr(), B, D, H, W, Ci, Co, out.hi_ptr, out.lo_ptr,
                      out.cb_total, out.cb_off, self.err.data_ptr())
+            return
+        if (not self.training) and isinstance(src, Act) and DECONV_TC and Ci % 16 == 0 and Co % 16 == 0 and Co <= 256 \
+                and src.C == Ci:
+            # 1^3 implicit GEMM with 8*Co columns (<= 256 per launch) and a scatter epilogue; operand precision follows
+            # the input: hi/lo activations take the 3-term split like the 3^3 convs of the same net
+            D, H, W = src.dims
+            mode = "p3" if src.lo_off is not None else "p1"
+            nq = min(8, 256 // Co)
+            in_bpc = 4 if src.lo_off is not None else 2
+            self.count_bytes("dp_deconv2x_tc", src.N * src.vox * (Ci * in_bpc + 8 * Co * (4 if out.lo_off is not None else 2)))
+            for q0 in range(0, 8, nq):
+                def wq(q0=q0):
+                    wn = weight.detach().to(self.device, torch.float32).permute(2, 3, 4, 1, 0).reshape(8 * Co, Ci)
+                    return wn[q0 * Co:(q0 + nq) * Co].reshape(nq * Co, Ci, 1, 1, 1)
+                wp, chunks, nch = self.pack_conv_tc(wq, [src], mode)
+                scale, shift = self.affine(nq * Co)
+                self.count_flops("dp_deconv2x_tc", 2.0 * src.N * src.vox * Ci * Co * nq)
+                self.add("dp_deconv2x_tc", src.buf.data_ptr(), src.cb_total, chunks, nch, wp.data_ptr(), src.N, D, H, W, Co,
+                         q0, nq, scale.data_ptr(), shift.data_ptr(), out.hi_ptr, out.lo_ptr, out.cb_total, out.cb_off,
+                         self.err.data_ptr())
             return
         w = self.derived(lambda: weight.detach().to(self.device, torch.float32).permute(2, 3, 4, 0, 1).reshape(8, Ci, Co))
         n_in = (src.t.shape[0] * src.t.shape[1]) if isinstance(src, Tokens) else src.N * src.vox

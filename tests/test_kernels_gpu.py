@@ -289,6 +289,31 @@ def test_deconv2x_c8_and_token_inputs():
     assert _rel(y2.cpu(), F.conv_transpose3d(feat.double().cpu(), wt.double().cpu(), stride=2)) < 1e-3
 
 
+@pytest.mark.parametrize("Ci,Co,dims,lo,tc", [
+    (32, 16, (4, 8, 8), True, True), (64, 32, (4, 6, 10), True, True), (64, 64, (3, 5, 8), False, True),
+    (128, 64, (2, 4, 4), False, True), (32, 16, (4, 8, 8), True, False), (64, 32, (4, 6, 10), False, False)])
+def test_deconv2x_tensor_core_and_constant_bank_paths(Ci, Co, dims, lo, tc, monkeypatch):
+    """ConvTranspose3d k2 s2 of a c8 tensor: dp_deconv2x_tc (1^3 implicit GEMM + scatter epilogue) and dp_deconv2x_cw."""
+    from dose_prediction_b200 import engine
+    monkeypatch.setattr(engine, "DECONV_TC", tc)
+    torch.manual_seed(17)
+    dev = torch.device("cuda:0")
+    N = 2
+    x = torch.randn(N, Ci, *dims, device=dev)
+    w = torch.randn(Ci, Co, 2, 2, 2, device=dev) / Ci ** 0.5
+    P = _plan()
+    a = _act_from(P, x, lo=lo)
+    slot0, slot1 = P.new_concat(N, [Co, Co], tuple(2 * d for d in dims), lo=lo)
+    P.deconv2x(a, w, slot1)
+    y = torch.zeros(N, Co, *[2 * d for d in dims], device=dev)
+    P.unpack(slot1, y)
+    P.run()
+    _finish(P)
+    xin = x if lo else _h(x)
+    want = F.conv_transpose3d(xin.double().cpu(), w.double().cpu(), stride=2)
+    assert _rel(y.cpu(), want) < (1e-5 if lo else 1.5e-3)      # lo: ~22-bit operands; else fp16 weights / outputs
+
+
 def test_upsample_direct_conv_layernorm_patchify():
     torch.manual_seed(8)
     dev = torch.device("cuda:0")
