@@ -188,6 +188,21 @@ __host__ __device__ __forceinline__ uint32_t make_idesc_f16(int m, int n) {
   return d;
 }
 
+// 32-byte (one full sector) global accesses: a c8 fp32 voxel is 8 floats = 32 B; written as two 16-byte stores every
+// instruction of a warp touches half sectors only (measured on the transposed-conv scatter: 0.32 -> 0.13 ms).
+__device__ __forceinline__ void st_global_v8f(float* p, const float (&y)[8]) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(y[0]), "f"(y[1]), "f"(y[2]), "f"(y[3]),
+               "f"(y[4]), "f"(y[5]), "f"(y[6]), "f"(y[7]) : "memory");
+}
+__device__ __forceinline__ void ld_global_v8f(const float* p, float (&y)[8]) {
+  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=f"(y[0]), "=f"(y[1]), "=f"(y[2]), "=f"(y[3]),
+               "=f"(y[4]), "=f"(y[5]), "=f"(y[6]), "=f"(y[7]) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void st_global_v8u(void* p, const uint32_t (&v)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+               "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -430,9 +430,10 @@ conv3d_stack_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_co
                 const size_t cb = static_cast<size_t>(it.n) * p.cb_total_out + p.cb_out_off + (c0 >> 3) + b;
                 const size_t off = (cb * plane + vox) * 8;
                 if (p.out_f32 != nullptr) {
-                  float4* o = reinterpret_cast<float4*>(p.out_f32 + off);
-                  o[0] = make_float4(v[b * 8 + 0], v[b * 8 + 1], v[b * 8 + 2], v[b * 8 + 3]);
-                  o[1] = make_float4(v[b * 8 + 4], v[b * 8 + 5], v[b * 8 + 6], v[b * 8 + 7]);
+                  float y8[8];
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) y8[j] = v[b * 8 + j];
+                  st_global_v8f(p.out_f32 + off, y8);
                 }
                 if (p.out_hi != nullptr) {
                   __align__(16) __half hi[8];

@@ -288,6 +288,42 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
       const bool valid = (h < p.H) && (w < p.W);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>((slot * p.T + tt) * p.cout);
       const size_t vox = (static_cast<size_t>(d) * p.H + h) * p.W + w;
+      if (p.dc_co > 0) {
+        // transposed conv: the W-neighbours l = 0 / 1 of an output voxel pair are the column chunks c and c + dc_co;
+        // one thread converts both and writes whole 32-byte sectors (st.global.v8) per channel block
+        const int cpq = p.dc_co >> 4;
+        const int npairs = p.cout >> 5;
+        for (int pi = cgrp; pi < npairs; pi += 2) {
+          const int qe = (pi / cpq) * 2, cc = pi % cpq;
+          const int c_even = (qe * cpq + cc) * 16;
+          uint32_t r[2][16];
+          tmem_ld16(taddr + c_even, r[0]);
+          tmem_ld16(taddr + c_even + p.dc_co, r[1]);
+          tmem_ld_wait();
+          if (!valid) continue;
+          const int q = p.dc_q0 + qe;
+          const size_t vo = (static_cast<size_t>(2 * d + (q >> 2)) * (2 * p.H) + 2 * h + ((q >> 1) & 1)) * (2 * p.W) + 2 * w;
+#pragma unroll
+          for (int b = 0; b < 2; ++b) {
+            const size_t cb = static_cast<size_t>(n) * p.cb_total_out + p.cb_out_off + cc * 2 + b;
+            const size_t off = (cb * (8 * plane) + vo) * 8;
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+              for (int j = 0; j < 8; j += 2) {
+                const float x0 = __uint_as_float(r[u][b * 8 + j]), x1 = __uint_as_float(r[u][b * 8 + j + 1]);
+                const __half2 h2 = __floats2half2_rn(x0, x1);
+                const float2 back = __half22float2(h2);
+                const __half2 l2 = __floats2half2_rn(x0 - back.x, x1 - back.y);
+                hi[u * 4 + (j >> 1)] = *reinterpret_cast<const uint32_t*>(&h2);
+                lo[u * 4 + (j >> 1)] = *reinterpret_cast<const uint32_t*>(&l2);
+              }
+            st_global_v8u(p.out_hi + off, hi);
+            if (p.out_lo != nullptr) st_global_v8u(p.out_lo + off, lo);
+          }
+        }
+      } else
       for (int c0 = cgrp * 16; c0 < p.cout; c0 += 32) {
         uint32_t r[16];
         tmem_ld16(taddr + c0, r);
@@ -313,21 +349,13 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
         if (valid) {
 #pragma unroll
           for (int b = 0; b < 2; ++b) {
-            size_t off;
-            if (p.dc_co > 0) {
-              const int col = c0 + b * 8;
-              const int q = p.dc_q0 + col / p.dc_co, co = col % p.dc_co;
-              const size_t cb = static_cast<size_t>(n) * p.cb_total_out + p.cb_out_off + (co >> 3);
-              const size_t vo = (static_cast<size_t>(2 * d + (q >> 2)) * (2 * p.H) + 2 * h + ((q >> 1) & 1)) * (2 * p.W) + 2 * w + (q & 1);
-              off = (cb * (8 * plane) + vo) * 8;
-            } else {
-              const size_t cb = static_cast<size_t>(n) * p.cb_total_out + p.cb_out_off + (c0 >> 3) + b;
-              off = (cb * plane + vox) * 8;
-            }
+            const size_t cb = static_cast<size_t>(n) * p.cb_total_out + p.cb_out_off + (c0 >> 3) + b;
+            const size_t off = (cb * plane + vox) * 8;
             if (p.out_f32 != nullptr) {
-              float4* o = reinterpret_cast<float4*>(p.out_f32 + off);
-              o[0] = make_float4(v[b * 8 + 0], v[b * 8 + 1], v[b * 8 + 2], v[b * 8 + 3]);
-              o[1] = make_float4(v[b * 8 + 4], v[b * 8 + 5], v[b * 8 + 6], v[b * 8 + 7]);
+              float y8[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) y8[j] = v[b * 8 + j];
+              st_global_v8f(p.out_f32 + off, y8);
             }
             if (p.out_hi != nullptr) {
               __align__(16) __half hi[8];
@@ -475,7 +503,7 @@ extern "C" int dp_deconv2x_tc(const void* in_c8, int cb_total_in, const uint8_t*
                               const float* scale, const float* shift, void* out_hi, void* out_lo, int cb_total_out,
                               int cb_out_off, int* err_flag, cudaStream_t stream) {
   using namespace dp;
-  DP_REQUIRE(cout % 16 == 0 && nq >= 1 && q0 >= 0 && q0 + nq <= 8 && nq * cout <= 256,
+  DP_REQUIRE(cout % 16 == 0 && nq >= 2 && (nq & 1) == 0 && q0 >= 0 && (q0 & 1) == 0 && q0 + nq <= 8 && nq * cout <= 256,
              "dp_deconv2x_tc: C_out=%d, parities [%d, %d) do not fit one 256-column launch", cout, q0, q0 + nq);
   DP_REQUIRE(out_hi != nullptr, "dp_deconv2x_tc: no output tensor given");
   return launch_conv_tc(in_c8, cb_total_in, chunk_cb, n_chunks, wpack, N, D, H, W, nq * cout, 1, 1, scale, shift, 0,

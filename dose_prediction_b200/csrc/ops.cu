@@ -32,9 +32,7 @@ __device__ __forceinline__ void load8(const __half* hi, const __half* lo, size_t
   }
 }
 __device__ __forceinline__ void load8f(const float* p, size_t off, float (&x)[8]) {
-  const float4 a = *reinterpret_cast<const float4*>(p + off);
-  const float4 b = *reinterpret_cast<const float4*>(p + off + 4);
-  x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+  ld_global_v8f(p + off, x);
 }
 __device__ __forceinline__ void store8(__half* hi, __half* lo, size_t off, const float (&x)[8]) {
   // hi = fp16(x), lo = fp16(x - hi), with the packed two-at-a-time conversions (same rounding as the scalar ones)
@@ -367,8 +365,7 @@ __global__ void __launch_bounds__(128, 6) pointwise_kernel(const PointwiseParams
 #pragma unroll
       for (int j = 0; j < 8; ++j) y[j] = acc[b * 8 + j];
       if (p.out_raw) {
-        *reinterpret_cast<float4*>(p.out_raw + off) = make_float4(y[0], y[1], y[2], y[3]);
-        *reinterpret_cast<float4*>(p.out_raw + off + 4) = make_float4(y[4], y[5], y[6], y[7]);
+        st_global_v8f(p.out_raw + off, y);
       }
       if (p.out_hi) store8p(p.out_hi, p.out_lo, off, y);
     }
@@ -476,8 +473,7 @@ __global__ void __launch_bounds__(128, 6) pointwise_cw_kernel(const __grid_const
 #pragma unroll
       for (int j = 0; j < 8; ++j) y[j] = acc[b * 8 + j];
       if (p.out_raw) {
-        *reinterpret_cast<float4*>(p.out_raw + off) = make_float4(y[0], y[1], y[2], y[3]);
-        *reinterpret_cast<float4*>(p.out_raw + off + 4) = make_float4(y[4], y[5], y[6], y[7]);
+        st_global_v8f(p.out_raw + off, y);
       }
       if (p.out_hi) store8p(p.out_hi, p.out_lo, off, y);
     }
@@ -668,8 +664,20 @@ upsample2x_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ i
   const size_t vox_o = vox_i * 8;
   const size_t o0 = ((static_cast<size_t>(n) * out_cb_total + out_cb_off + cb) * vox_o +
                      (static_cast<size_t>(dz) * Ho + ho) * Wo + 2 * k) * 8;
-  store8(out_hi, out_lo, o0, acc[0]);
-  store8(out_hi, out_lo, o0 + 8, acc[1]);
+  // the two voxels are one 32-byte sector per plane
+  uint32_t hi[8], lo[8];
+#pragma unroll
+  for (int o = 0; o < 2; ++o)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __half2 h2 = __floats2half2_rn(acc[o][2 * j], acc[o][2 * j + 1]);
+      const float2 f = __half22float2(h2);
+      const __half2 l2 = __floats2half2_rn(acc[o][2 * j] - f.x, acc[o][2 * j + 1] - f.y);
+      hi[o * 4 + j] = *reinterpret_cast<const uint32_t*>(&h2);
+      lo[o * 4 + j] = *reinterpret_cast<const uint32_t*>(&l2);
+    }
+  st_global_v8u(out_hi + o0, hi);
+  if (out_lo != nullptr) st_global_v8u(out_lo + o0, lo);
 }
 
 // ------------------------------------------------------------------ LayerNorm over the last dim (one warp per row)
@@ -940,8 +948,7 @@ __global__ void __launch_bounds__(128) direct_conv_kernel(const DirectConvParams
     if (valid) {
       const size_t off = ((static_cast<size_t>(n) * p.out_cb_total + p.out_cb_off + (co0 >> 3) + b) * vox_o + v) * 8;
       if (p.out_raw) {
-        *reinterpret_cast<float4*>(p.out_raw + off) = make_float4(y[0], y[1], y[2], y[3]);
-        *reinterpret_cast<float4*>(p.out_raw + off + 4) = make_float4(y[4], y[5], y[6], y[7]);
+        st_global_v8f(p.out_raw + off, y);
       }
       if (p.out_hi) store8(p.out_hi, p.out_lo, off, y);
     }

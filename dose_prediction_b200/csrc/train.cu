@@ -39,9 +39,7 @@ __device__ __forceinline__ void t_load8(const __half* hi, const __half* lo, size
   }
 }
 __device__ __forceinline__ void t_load8f(const float* p, size_t off, float (&x)[8]) {
-  const float4 a = *reinterpret_cast<const float4*>(p + off);
-  const float4 b = *reinterpret_cast<const float4*>(p + off + 4);
-  x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+  ld_global_v8f(p + off, x);          // c8 fp32 voxel = one 32-byte sector (tensors are 32-byte aligned)
 }
 __device__ __forceinline__ void t_store8h(__half* hi, size_t off, const float (&x)[8]) {
   __align__(16) __half h[8];
@@ -50,8 +48,7 @@ __device__ __forceinline__ void t_store8h(__half* hi, size_t off, const float (&
   *reinterpret_cast<uint4*>(hi + off) = *reinterpret_cast<const uint4*>(h);
 }
 __device__ __forceinline__ void t_store8f(float* p, size_t off, const float (&y)[8]) {
-  *reinterpret_cast<float4*>(p + off) = make_float4(y[0], y[1], y[2], y[3]);
-  *reinterpret_cast<float4*>(p + off + 4) = make_float4(y[4], y[5], y[6], y[7]);
+  st_global_v8f(p + off, y);
 }
 __device__ __forceinline__ void t_finalize(const double* stats, size_t idx, double inv_count, float& mean, float& rstd) {
   const double s = stats[idx * 2], ss = stats[idx * 2 + 1];

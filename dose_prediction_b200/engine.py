@@ -592,7 +592,7 @@ class Plan:
             self.add("dp_deconv2x_gemm", src.t.data_ptr(), wnk.data_ptr(), B, D, H, W, Ci, Co, out.hi_ptr, out.lo_ptr,
                      out.cb_total, out.cb_off, self.err.data_ptr())
             return
-        if (not self.training) and isinstance(src, Act) and DECONV_TC and Ci % 16 == 0 and Co % 16 == 0 and Co <= 256 \
+        if (not self.training) and isinstance(src, Act) and DECONV_TC and Ci % 16 == 0 and Co % 16 == 0 and Co <= 128 \
                 and src.C == Ci:
             # 1^3 implicit GEMM with 8*Co columns (<= 256 per launch) and a scatter epilogue; operand precision follows
             # the input: hi/lo activations take the 3-term split like the 3^3 convs of the same net

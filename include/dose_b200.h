@@ -158,7 +158,8 @@ int dp_deconv2x_cw(const void* in_hi, const void* in_lo, long long in_nstride, l
  * UnetrPrUpBlock / UnetrUpBlock transp_conv) for a c8 input on the tensor cores: a 1^3 implicit GEMM of dp_conv3d_tc
  * with nq * cout columns (parities q0 .. q0+nq-1; column (q - q0) * cout + co = W[:, co, q>>2, (q>>1)&1, q&1]) whose
  * epilogue scatters every 8-channel group to its output voxel.  wpack / chunk_cb as for dp_conv3d_tc with k = 1
- * (operand-split chunks included); nq * cout <= 256, 16 | cout.                                                  */
+ * (operand-split chunks included); nq * cout <= 256, 16 | cout, q0 and nq even (the W-neighbour parities q, q+1 are
+ * written together as full 32-byte sectors).                                                                     */
 int dp_deconv2x_tc(const void* in_c8, int cb_total_in, const uint8_t* chunk_cb, int n_chunks, const void* wpack, int N,
                    int D, int H, int W, int cout, int q0, int nq, const float* scale, const float* shift, void* out_hi,
                    void* out_lo, int cb_total_out, int cb_out_off, int* err_flag, cudaStream_t stream);
