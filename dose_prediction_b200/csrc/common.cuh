@@ -203,6 +203,21 @@ __device__ __forceinline__ void st_global_v8u(void* p, const uint32_t (&v)[8]) {
                "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
 }
 
+// packed fp32 pairs: fma.rn.f32x2 (FFMA2) does two IEEE fp32 FMAs per issued instruction
+__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long fma_f32x2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
