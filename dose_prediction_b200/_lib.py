@@ -17,7 +17,7 @@ L = c_longlong
 F = c_float
 
 _SIGNATURES = {
-    "dp_conv3d_tc": [P, I, P, I, P, I, I, I, I, I, I, I, P, P, I, P, P, P, I, I, P, P, I, P, P],
+    "dp_conv3d_tc": [P, I, P, I, P, I, I, I, I, I, I, I, P, P, I, P, P, P, I, I, P, P, I, P, I, P],
     "dp_conv3d_stack": [P, I, P, I, P, I, I, I, I, I, I, P, P, I, P, P, P, I, I, P, P, I, I, I, P],
     "dp_conv3d_direct": [P, P, I, I, I, I, I, I, I, I, I, I, P, P, P, I, I, P, P, P, I, I, P, P],
     "dp_gemm_tc": [P, P, I, I, I, I, I, I, L, I, L, I, I, P, P, I, P, F, I, P, I, P, I, I, I, I, I, P, P, P, F, P, P],

@@ -47,6 +47,8 @@ struct ConvTcParams {
   __half* out_hi;
   __half* out_lo;
   int cb_total_out, cb_out_off;
+  int fold;                  // 1: cout = 2 * C_out MMA columns per tile, output channel c = column c + column c + C_out
+                             // (3-term operand split with [W_hi | W_lo] stacked in N: hi chunks are read once)
   int dc_co, dc_q0;          // > 0: ConvTranspose3d k2 s2 as a 1^3 conv with columns (parity q - dc_q0) * dc_co + co, scattered to
                              // the output voxel (2d + (q >> 2), 2h + ((q >> 1) & 1), 2w + (q & 1)) of a [2D, 2H, 2W] tensor
   double* stats;
@@ -136,7 +138,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   for (int i = threadIdx.x; i < kConvEpiWarps * 256 * 2; i += kConvThreads) (&stat_acc[0][0][0])[i] = 0.f;
-  for (int i = threadIdx.x; i < p.cout; i += kConvThreads) { s_scale[i] = p.scale[i]; s_shift[i] = p.shift[i]; }
+  for (int i = threadIdx.x; i < (p.fold ? p.cout >> 1 : p.cout); i += kConvThreads) { s_scale[i] = p.scale[i]; s_shift[i] = p.shift[i]; }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -258,14 +260,15 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
     const int row = quarter * 32 + lane;
     const int hl = row >> 3, wl = row & 7;
     const int mycol = (lane >> 1) & 15;
+    const int cout_out = p.fold ? p.cout >> 1 : p.cout;
     int cur_n = -1;
     int iter = 0;
     auto flush_stats = [&](int n) {
       if (p.stats == nullptr || n < 0) return;
       __syncwarp();
-      for (int c = lane; c < p.cout; c += 32) {
-        atomicAdd(&p.stats[(static_cast<size_t>(n) * p.cout + c) * 2 + 0], static_cast<double>(stat_acc[ew][c][0]));
-        atomicAdd(&p.stats[(static_cast<size_t>(n) * p.cout + c) * 2 + 1], static_cast<double>(stat_acc[ew][c][1]));
+      for (int c = lane; c < cout_out; c += 32) {
+        atomicAdd(&p.stats[(static_cast<size_t>(n) * cout_out + c) * 2 + 0], static_cast<double>(stat_acc[ew][c][0]));
+        atomicAdd(&p.stats[(static_cast<size_t>(n) * cout_out + c) * 2 + 1], static_cast<double>(stat_acc[ew][c][1]));
         stat_acc[ew][c][0] = 0.f;
         stat_acc[ew][c][1] = 0.f;
       }
@@ -324,10 +327,18 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
           }
         }
       } else
-      for (int c0 = cgrp * 16; c0 < p.cout; c0 += 32) {
+      for (int c0 = cgrp * 16; c0 < cout_out; c0 += 32) {
         uint32_t r[16];
         tmem_ld16(taddr + c0, r);
-        tmem_ld_wait();
+        if (p.fold) {
+          uint32_t r2[16];
+          tmem_ld16(taddr + c0 + cout_out, r2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+        } else {
+          tmem_ld_wait();
+        }
         float v[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -396,7 +407,11 @@ static int launch_conv_tc(const void* in_c8, int cb_total_in, const uint8_t* chu
                           const void* wpack, int N, int D, int H, int W, int cout, int k, int dil,
                           const float* scale, const float* shift, int relu, float* out_f32, void* out_hi,
                           void* out_lo, int cb_total_out, int cb_out_off, double* stats, int* err_flag,
-                          int max_ctas, const uint32_t* tap_mask, int dc_co, int dc_q0, cudaStream_t stream) {
+                          int max_ctas, const uint32_t* tap_mask, int dc_co, int dc_q0, int fold, cudaStream_t stream) {
+  DP_REQUIRE(fold == 0 || (cout <= 128 && dc_co == 0), "dp_conv3d_tc: fold needs C_out <= 128");
+  const int cout_real = cout;
+  if (fold) cout *= 2;                 // MMA columns per tile
+  (void)cout_real;
   DP_REQUIRE(cout % 16 == 0 && cout >= 16 && cout <= 256, "dp_conv3d_tc: C_out=%d must be a multiple of 16 in [16,256]", cout);
   DP_REQUIRE(k >= 1 && k <= 7 && (k & 1), "dp_conv3d_tc: kernel size %d unsupported", k);
   DP_REQUIRE(n_chunks >= 1 && n_chunks <= 192, "dp_conv3d_tc: n_chunks=%d out of range", n_chunks);
@@ -446,7 +461,7 @@ static int launch_conv_tc(const void* in_c8, int cb_total_in, const uint8_t* chu
   p.out_f32 = out_f32; p.out_hi = static_cast<__half*>(out_hi); p.out_lo = static_cast<__half*>(out_lo);
   p.cb_total_out = cb_total_out; p.cb_out_off = cb_out_off;
   p.stats = stats; p.err_flag = err_flag;
-  p.dc_co = dc_co; p.dc_q0 = dc_q0;
+  p.dc_co = dc_co; p.dc_q0 = dc_q0; p.fold = fold;
   uint32_t cols = 32;
   while (cols < static_cast<uint32_t>(2 * T * cout)) cols <<= 1;
   p.tmem_cols = cols;
@@ -492,10 +507,10 @@ extern "C" int dp_conv3d_tc(const void* in_c8, int cb_total_in, const uint8_t* c
                             const void* wpack, int N, int D, int H, int W, int cout, int k, int dil,
                             const float* scale, const float* shift, int relu, float* out_f32, void* out_hi,
                             void* out_lo, int cb_total_out, int cb_out_off, double* stats, int* err_flag,
-                            int max_ctas, const uint32_t* tap_mask, cudaStream_t stream) {
+                            int max_ctas, const uint32_t* tap_mask, int fold, cudaStream_t stream) {
   return dp::launch_conv_tc(in_c8, cb_total_in, chunk_cb, n_chunks, wpack, N, D, H, W, cout, k, dil, scale, shift, relu,
                             out_f32, out_hi, out_lo, cb_total_out, cb_out_off, stats, err_flag, max_ctas, tap_mask, 0, 0,
-                            stream);
+                            fold, stream);
 }
 
 extern "C" int dp_deconv2x_tc(const void* in_c8, int cb_total_in, const uint8_t* chunk_cb, int n_chunks,
@@ -507,5 +522,5 @@ extern "C" int dp_deconv2x_tc(const void* in_c8, int cb_total_in, const uint8_t*
              "dp_deconv2x_tc: C_out=%d, parities [%d, %d) do not fit one 256-column launch", cout, q0, q0 + nq);
   DP_REQUIRE(out_hi != nullptr, "dp_deconv2x_tc: no output tensor given");
   return launch_conv_tc(in_c8, cb_total_in, chunk_cb, n_chunks, wpack, N, D, H, W, nq * cout, 1, 1, scale, shift, 0,
-                        nullptr, out_hi, out_lo, cb_total_out, cb_out_off, nullptr, err_flag, 0, nullptr, cout, q0, stream);
+                        nullptr, out_hi, out_lo, cb_total_out, cb_out_off, nullptr, err_flag, 0, nullptr, cout, q0, 0, stream);
 }

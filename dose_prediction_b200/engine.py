@@ -23,6 +23,7 @@ ACT_ID = {None: ACT_NONE, "none": ACT_NONE, "relu": ACT_RELU, "lrelu": ACT_LRELU
 STATS_DOUBLES = 1 << 20
 STACK_TILES = int(os.environ.get("DP_STACK_TILES", "0"))
 FOLD_P3 = os.environ.get("DP_FOLD_P3", "1") != "0"
+FOLD_TC_MAX = int(os.environ.get("DP_FOLD_TC_MAX", "32"))        # plain tcgen05 conv: fold [W_hi | W_lo] into N up to this C_out
 POINTWISE_CW = os.environ.get("DP_POINTWISE_CW", "1") != "0"     # bring-up switch: constant-bank weights for static 1^3 convs
 DECONV_TC = os.environ.get("DP_DECONV_TC", "1") != "0"          # bring-up switch: k2s2 transposed convs of c8 inputs on the tensor cores
 STACKED_CONV = os.environ.get("DP_STACKED_CONV", "1") != "0"    # bring-up switch between the two tcgen05 conv kernels
@@ -448,7 +449,8 @@ class Plan:
         Co = wshape[0]
         stacked = STACKED_CONV and dil == 1 and k in (3, 7) and Co in (16, 32) and tap_mask_fn is None
         fold = stacked and mode == "p3" and Co == 16 and FOLD_P3
-        wp, chunks, nch = self.pack_conv_tc(weight, parts, "p3f" if fold else mode, stacked=stacked)
+        fold_tc = (not stacked) and mode == "p3" and Co <= FOLD_TC_MAX and FOLD_P3
+        wp, chunks, nch = self.pack_conv_tc(weight, parts, "p3f" if (fold or fold_tc) else mode, stacked=stacked)
         if out_raw is not None:
             of32, ohi, olo, cbt, cbo = out_raw.t.data_ptr(), None, None, out_raw.cb_total, 0
             st = out_raw.stats if stats is None else stats
@@ -469,7 +471,7 @@ class Plan:
         self.count_flops("dp_conv3d_tc", flops if tap_mask_fn is None else tap_mask_fn.flops)
         self.add("dp_conv3d_tc", a0.buf.data_ptr(), a0.cb_total, chunks, nch, wp.data_ptr(), a0.N, D, H, W, Co, k, dil,
                  scale.data_ptr(), shift.data_ptr(), int(relu), of32, ohi, olo, cbt, cbo,
-                 st.data_ptr() if st is not None else None, self.err.data_ptr(), 0, masks)
+                 st.data_ptr() if st is not None else None, self.err.data_ptr(), 0, masks, int(fold_tc))
 
     def conv_direct(self, a, weight, k, stride, dil, scale, shift, relu, out_raw=None, out_act=None, stats=None):
         """generic direct conv on one Act whose C is a multiple of 8 (stride-2 convs of net_A)."""

@@ -49,11 +49,13 @@ int dp_device_sm_count(void);
  *   wpack      fp16 [k(kd)][n_chunks][k(kh)][k(kw)][2][cout][8]
  *   out_f32    c8 fp32 output or NULL;  out_hi/out_lo  c8 fp16 output (lo optional) or NULL
  *   tap_mask   optional host array [n_chunks] (k <= 3): bit (kd*k+kh)*k+kw set = tap present; lets the
- *              stride-2 convs of c3d.py:49-61 run as sparse 3^3 convs over a space-to-depth input     */
+ *              stride-2 convs of c3d.py:49-61 run as sparse 3^3 convs over a space-to-depth input
+ *   fold       1: wpack holds 2*cout columns per tap, [W_hi | W_lo] for hi chunks and [W_hi | 0] for lo chunks; the
+ *              epilogue adds column c and c + cout (the 3-term operand split with each hi chunk read once)   */
 int dp_conv3d_tc(const void* in_c8, int cb_total_in, const uint8_t* chunk_cb, int n_chunks, const void* wpack,
                  int N, int D, int H, int W, int cout, int k, int dil, const float* scale, const float* shift,
                  int relu, float* out_f32, void* out_hi, void* out_lo, int cb_total_out, int cb_out_off,
-                 double* stats, int* err_flag, int max_ctas, const uint32_t* tap_mask, cudaStream_t stream);
+                 double* stats, int* err_flag, int max_ctas, const uint32_t* tap_mask, int fold, cudaStream_t stream);
 
 /* Same convolution for C_out in {16,32}, k in {3,7}, dilation 1, with the k depth taps stacked into the MMA
  * N dimension (N = k*C_out) and a sliding ring of output-plane accumulators in TMEM (conv_stack.cu): the

@@ -52,6 +52,9 @@ def _act_from(P, x, lo):
     (16, 16, 3, 2, (12, 16, 16), "p1"),         # dilation 2
     (9, 16, 3, 1, (16, 16, 16), "p3"),          # padded input channels + 3-term operand split
     (32, 32, 3, 1, (8, 16, 8), "p2"),
+    (32, 32, 3, 2, (8, 16, 16), "p3"),          # plain kernel, [W_hi | W_lo] folded into N (C_out <= 32)
+    (16, 32, 5, 1, (6, 12, 20), "p3"),          # folded, k = 5, ragged tiles
+    (48, 64, 3, 1, (8, 16, 16), "p3"),          # plain kernel, unfolded 3-term split
 ])
 def test_conv3d_tc_matches_torch(cin, cout, k, dil, dims, mode):
     torch.manual_seed(0)
