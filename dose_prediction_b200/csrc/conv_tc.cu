@@ -409,9 +409,7 @@ static int launch_conv_tc(const void* in_c8, int cb_total_in, const uint8_t* chu
                           void* out_lo, int cb_total_out, int cb_out_off, double* stats, int* err_flag,
                           int max_ctas, const uint32_t* tap_mask, int dc_co, int dc_q0, int fold, cudaStream_t stream) {
   DP_REQUIRE(fold == 0 || (cout <= 128 && dc_co == 0), "dp_conv3d_tc: fold needs C_out <= 128");
-  const int cout_real = cout;
-  if (fold) cout *= 2;                 // MMA columns per tile
-  (void)cout_real;
+  if (fold) cout *= 2;                 // MMA columns per tile; everything below sizes by the MMA N
   DP_REQUIRE(cout % 16 == 0 && cout >= 16 && cout <= 256, "dp_conv3d_tc: C_out=%d must be a multiple of 16 in [16,256]", cout);
   DP_REQUIRE(k >= 1 && k <= 7 && (k & 1), "dp_conv3d_tc: kernel size %d unsupported", k);
   DP_REQUIRE(n_chunks >= 1 && n_chunks <= 192, "dp_conv3d_tc: n_chunks=%d out of range", n_chunks);
