@@ -380,6 +380,25 @@ conv3d_stack_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_co
       }
       __syncwarp();
     };
+    float ts1[32], ts2[32];                  // this thread's sum / sum of squares per output channel (NO <= 32)
+#pragma unroll
+    for (int j = 0; j < 32; ++j) { ts1[j] = 0.f; ts2[j] = 0.f; }
+    auto fold_item_stats = [&]() {
+      if (p.stats == nullptr) return;
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        if (cc * 16 >= NO) break;
+        float a[16], b[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { a[j] = ts1[cc * 16 + j]; b[j] = ts2[cc * 16 + j]; ts1[cc * 16 + j] = 0.f; ts2[cc * 16 + j] = 0.f; }
+        const float s1 = colsum16s(a, lane);
+        const float s2 = colsum16s(b, lane);
+        if ((lane & 1) == 0) {
+          stat_acc[ew][cc * 16 + mycol][0] += s1;
+          stat_acc[ew][cc * 16 + mycol][1] += s2;
+        }
+      }
+    };
     const size_t plane = static_cast<size_t>(p.D) * p.H * p.W;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
       const Item it = decode_item<KS>(p, item);
@@ -414,14 +433,13 @@ conv3d_stack_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_co
               v[j] = valid ? x : 0.f;
             }
             if (p.stats != nullptr) {
-              float sq[16];
+              // per-thread partial sums over the item; the cross-lane reduction happens once per item (fold_item_stats)
+              if (c0 == 0) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) sq[j] = v[j] * v[j];
-              const float s1 = colsum16s(v, lane);
-              const float s2 = colsum16s(sq, lane);
-              if ((lane & 1) == 0) {
-                stat_acc[ew][c0 + mycol][0] += s1;
-                stat_acc[ew][c0 + mycol][1] += s2;
+                for (int j = 0; j < 16; ++j) { ts1[j] += v[j]; ts2[j] = fmaf(v[j], v[j], ts2[j]); }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { ts1[16 + j] += v[j]; ts2[16 + j] = fmaf(v[j], v[j], ts2[16 + j]); }
               }
             }
             if (valid) {
@@ -454,6 +472,7 @@ conv3d_stack_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_co
         __syncwarp();
         if (lane == 0) mbar_arrive(&free_bar[slot]);
       }
+      fold_item_stats();
     }
     flush_stats(cur_n);
   }
