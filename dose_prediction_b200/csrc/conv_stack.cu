@@ -367,6 +367,7 @@ conv3d_stack_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_co
     const int row = quarter * 32 + lane;
     const int hl = row >> 3, wl = row & 7;
     const int mycol = (lane >> 1) & 15;
+    const float relu_floor = p.relu ? 0.f : -INFINITY;      // one FMNMX per value instead of a predicated pair
     int cur_n = -1;
     uint32_t pc = 0;
     auto flush_stats = [&](int n) {
@@ -429,10 +430,10 @@ conv3d_stack_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_co
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               float x = fmaf(__uint_as_float(r[j]), s_scale[c0 + j], s_shift[c0 + j]);
-              if (p.relu) x = fmaxf(x, 0.f);
-              v[j] = valid ? x : 0.f;
+              x = fmaxf(x, relu_floor);
+              v[j] = x;
             }
-            if (p.stats != nullptr) {
+            if (p.stats != nullptr && valid) {
               // per-thread partial sums over the item; the cross-lane reduction happens once per item (fold_item_stats)
               if (c0 == 0) {
 #pragma unroll

@@ -261,6 +261,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
     const int hl = row >> 3, wl = row & 7;
     const int mycol = (lane >> 1) & 15;
     const int cout_out = p.fold ? p.cout >> 1 : p.cout;
+    const float relu_floor = p.relu ? 0.f : -INFINITY;      // one FMNMX per value instead of a predicated pair
     int cur_n = -1;
     int iter = 0;
     auto flush_stats = [&](int n) {
@@ -343,8 +344,12 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           float x = fmaf(__uint_as_float(r[j]), s_scale[c0 + j], s_shift[c0 + j]);
-          if (p.relu) x = fmaxf(x, 0.f);
-          v[j] = valid ? x : 0.f;
+          x = fmaxf(x, relu_floor);
+          v[j] = x;
+        }
+        if (!valid) {                                     // edge tiles only: rows outside the volume must not count
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = 0.f;
         }
         if (p.stats != nullptr) {
           float sq[16];
