@@ -25,6 +25,7 @@ STACK_TILES = int(os.environ.get("DP_STACK_TILES", "0"))
 FOLD_P3 = os.environ.get("DP_FOLD_P3", "1") != "0"
 FOLD_TC_MAX = int(os.environ.get("DP_FOLD_TC_MAX", "32"))        # plain tcgen05 conv: fold [W_hi | W_lo] into N up to this C_out
 POINTWISE_CW = os.environ.get("DP_POINTWISE_CW", "1") != "0"     # bring-up switch: constant-bank weights for static 1^3 convs
+POINTWISE_TC = os.environ.get("DP_POINTWISE_TC", "1") != "0"    # bring-up switch: wide coarse-level 1^3 convs on the tensor cores
 DECONV_TC = os.environ.get("DP_DECONV_TC", "1") != "0"          # bring-up switch: k2s2 transposed convs of c8 inputs on the tensor cores
 STACKED_CONV = os.environ.get("DP_STACKED_CONV", "1") != "0"    # bring-up switch between the two tcgen05 conv kernels
 EPS = 1e-5
@@ -566,6 +567,19 @@ class Plan:
         if out_planar is not None:
             out_b += 4 * Co
         ncb = sum(ceil_div(c, 8) for c in Cs)
+        if (not self.training and POINTWISE_TC and ncb >= 12 and Co % 16 == 0 and out_raw is not None and out_act is None
+                and out_planar is None and out_act_fn is None and all(c % 16 == 0 for c in Cs)):
+            # wide 1^3 convs of the coarse levels (128 / 256 input channels, few voxels): the SIMT kernel is latency
+            # bound there (0.2 ms per launch), so materialise act(IN(src)) once (a few MB) and contract on the tensor cores
+            wide = any(isinstance(t, Raw) or t.lo_off is not None for t, _, _ in srcs)
+            dims = tuple(srcs[0][0].t.shape[2:5]) if isinstance(srcs[0][0], Raw) else srcs[0][0].dims
+            slots = self.new_concat(N, Cs, dims, lo=wide)
+            for (t, st_, act), z in zip(srcs, slots):
+                self.norm_act(t, z, stats=st_, act=act, identity=(st_ is None and not isinstance(t, Raw)))
+            scale, shift = self.affine(Co, bias=bias)
+            self.conv_tc(list(slots), weight.detach().reshape(Co, sum(Cs), 1, 1, 1), 1, 1, "p3" if wide else "p1", scale, shift,
+                         False, out_raw=out_raw)
+            return
         use_cw = not self.training and ncb in (1, 2, 3, 4, 6, 8) and POINTWISE_CW
         self.count_bytes("dp_pointwise_conv_cw" if use_cw else "dp_pointwise_conv", N * vox * (in_b * ceil_div(Co, 16) + out_b))
         if use_cw:

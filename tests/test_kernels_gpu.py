@@ -266,6 +266,37 @@ def test_pointwise_two_sources_with_norm_on_load():
     assert _rel(planar.cpu(), F.conv3d(x3.double().cpu(), w[:1, :C].double().cpu(), bias[:1].double().cpu())) < 1e-5
 
 
+@pytest.mark.parametrize("wide", [False, True])
+def test_pointwise_wide_coarse_level_goes_through_the_tensor_cores(wide):
+    """128 input channels (two 64-channel sources with IN + Mish on load) -> 64: engine.pointwise materialises the
+    activated sources once and contracts with dp_conv3d_tc (k = 1); fp16 sources take fp16 operands, hi/lo sources
+    the 3-term split."""
+    torch.manual_seed(16)
+    dev = torch.device("cuda:0")
+    N, C, dims = 2, 64, (4, 8, 16)
+    x3, x7 = torch.randn(N, C, *dims, device=dev) + 1, torch.randn(N, C, *dims, device=dev) * 3
+    w = torch.randn(C, 2 * C, 1, 1, 1, device=dev) / (2 * C) ** 0.5
+    bias = torch.randn(C, device=dev)
+    P = _plan()
+    a3, a7 = _act_from(P, x3, wide), _act_from(P, x7, wide)
+    st3, st7 = P.new_stats(N, C), P.new_stats(N, C)
+    y3, y7 = P.new_act(N, C, dims, lo=wide), P.new_act(N, C, dims, lo=wide)
+    P.norm_act(a3, y3, identity=True, stats_out=st3)
+    P.norm_act(a7, y7, identity=True, stats_out=st7)
+    out = P.get_raw(N, C, dims)
+    P.pointwise([(y3, st3, "mish"), (y7, st7, "mish")], w, bias, out_raw=out)
+    P.run()
+    _finish(P)
+    assert any(st[2] == "dp_conv3d_tc" for st in P.steps)
+    e3, e7 = (x3, x7) if wide else (_h(x3), _h(x7))
+    cat = torch.cat((F.mish(F.instance_norm(e3.double().cpu(), eps=1e-5)), F.mish(F.instance_norm(e7.double().cpu(), eps=1e-5))), 1)
+    want = F.conv3d(cat, w.double().cpu(), bias.double().cpu())
+    got = _raw_to_ncdhw(out.t).cpu()
+    assert _rel(got, want) < (2e-5 if wide else 2e-3)
+    st = out.stats.view(N, C, 2).cpu()
+    assert torch.allclose(st[..., 0], got.double().sum((2, 3, 4)), rtol=1e-4, atol=1e-2)
+
+
 def test_deconv2x_c8_and_token_inputs():
     torch.manual_seed(7)
     dev = torch.device("cuda:0")
