@@ -56,6 +56,7 @@ _SIGNATURES = {
     "dp_dice_ce": [P, I, P, I, I, L, P, I, F, P, I, P],
     "dp_dice_ce_finalize": [P, I, I, L, P, P],
     "dp_adamw": [P, P, P, P, L, F, F, F, F, F, I, F, P, P],
+    "dp_adamw_dev": [P, P, P, P, L, F, F, F, F, F, F, P, P, P],
     "dp_grad_check": [P, L, P, P],
     "dp_pack_conv_weight": [P, I, I, I, I, P, P, I, I, P, P],
     "dp_cast_f16": [P, L, P, P],

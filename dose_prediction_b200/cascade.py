@@ -116,6 +116,11 @@ class CascadeStream:
         for ct, ptv in batches:            # pinned host tensors [B,1,S,S,S]
             out = stream.submit(ct, ptv)   # returns the pinned host dose of the PREVIOUS submit (or None)
         last = stream.flush()
+
+    Buffer lifetimes: submit() returns only after its H2D copies have completed, so the caller may refill ct / ptv
+    right away (the usual loader pattern).  The tensor submit() / flush() return is one of two internal pinned
+    buffers: it stays valid until the second submit() after the one that returned it — copy it out if it must live
+    longer.  A tcgen05 pipeline fault flagged by any kernel of a batch raises when that batch's result is handed out.
     """
 
     def __init__(self, casc):
@@ -127,6 +132,7 @@ class CascadeStream:
         self.stage = [(torch.empty(shape, device=dev), torch.empty(shape, device=dev)) for _ in range(2)]
         self.out_dev = [torch.empty(tuple(casc.dose.shape), device=dev) for _ in range(2)]
         self.out_host = [torch.empty(tuple(casc.dose.shape)).pin_memory() for _ in range(2)]
+        self.err_host = [torch.zeros(1, dtype=torch.int32).pin_memory() for _ in range(2)]
         self.staged = [torch.cuda.Event() for _ in range(2)]
         self.computed = [torch.cuda.Event() for _ in range(2)]
         self.copied = [torch.cuda.Event() for _ in range(2)]
@@ -155,20 +161,26 @@ class CascadeStream:
         with torch.cuda.stream(self.d2h):
             self.d2h.wait_event(self.computed[k])
             self.out_host[k].copy_(self.out_dev[k], non_blocking=True)
+            self.err_host[k].copy_(self.casc.plan.err, non_blocking=True)
             self.copied[k].record(self.d2h)
         prev, self.pending = self.pending, k
         self.i += 1
+        self.staged[k].synchronize()          # the caller's pinned inputs have been read: they may be refilled now
         if prev is None:
             return None
-        self.copied[prev].synchronize()
-        return self.out_host[prev]
+        return self._collect(prev)
+
+    def _collect(self, k):
+        self.copied[k].synchronize()
+        if int(self.err_host[k][0]) != 0:
+            raise RuntimeError("libdose_b200: an in-kernel mbarrier wait timed out (pipeline protocol error)")
+        return self.out_host[k]
 
     def flush(self):
         if self.pending is None:
             return None
-        self.copied[self.pending].synchronize()
-        out, self.pending = self.out_host[self.pending], None
-        return out
+        k, self.pending = self.pending, None
+        return self._collect(k)
 
 
 def postprocess_dose(prediction, possible_dose_mask):

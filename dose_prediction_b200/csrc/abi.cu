@@ -1,5 +1,6 @@
 // Host-side plumbing shared by the C-ABI entry points: thread-local error string, CUDA error
 // translation, cuTensorMapEncodeTiled via the runtime's driver entry point, device queries.
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -62,14 +63,26 @@ int encode_tiled(CUtensorMap* map, CUtensorMapDataType dtype, uint32_t rank, con
   return 0;
 }
 
+constexpr int kMaxDevices = 64;
+
 int sm_count() {
-  static int n = 0;
+  static std::atomic<int> cache[kMaxDevices];            // per device: a process may drive GPUs of different sizes
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 148;
+  int n = cache[dev].load(std::memory_order_relaxed);
   if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-      n = 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cache[dev].store(n, std::memory_order_relaxed);
   }
   return n;
+}
+
+bool first_use_on_device(int family) {
+  static std::atomic<unsigned char> done[kMaxDevices][KF_COUNT];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices || family < 0 || family >= KF_COUNT) return true;
+  // racing threads may both see "first" and both set the (idempotent) attribute: harmless
+  return done[dev][family].exchange(1, std::memory_order_acq_rel) == 0;
 }
 
 }  // namespace dp

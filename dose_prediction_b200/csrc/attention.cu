@@ -306,11 +306,9 @@ static int launch_attention(const void* q, const void* k, const void* vt, int BH
     const uint32_t box[3] = {64, HD, 1};
     if (int rc = encode_tiled(&tv, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, vt, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
   }
-  static bool configured = false;
-  if (!configured) {
+  if (first_use_on_device(HD == 64 ? KF_ATTN64 : KF_ATTN128)) {
     DP_CHECK(cudaFuncSetAttribute(attention_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(AttnCfg<HD>::kSmem)));
-    configured = true;
   }
   dim3 grid((T + 127) / 128, BH);
   attention_kernel<HD><<<grid, kAttnThreads, AttnCfg<HD>::kSmem, stream>>>(tq, tk, tv, p);

@@ -59,7 +59,8 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded spin: a protocol bug must surface as an error flag, never as a hung GPU box.
+// Bounded spin: a protocol bug must surface as an error (flag + __trap -> sticky launch failure), never as a hung GPU
+// box and never as silently wrong results.
 // mbar_wait      : latency-critical waiter (the MMA-issuing warp) — polls back to back.
 // mbar_wait_relaxed : producer / epilogue warps — sleep between polls so their spin loops do not take
 //                  issue slots from the MMA warp sharing the SM sub-partition (ncu: 72 % of all warp
@@ -71,6 +72,8 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* e
     if (it > 4096) __nanosleep(64);
   }
   if (err_flag) atomicExch(err_flag, 1);
+  __threadfence_system();
+  __trap();              // a protocol fault must never yield silent garbage: the launch fails, the context reports it
   return false;
 }
 __device__ __forceinline__ bool mbar_wait_relaxed(uint64_t* bar, uint32_t parity, int* err_flag) {
@@ -81,6 +84,8 @@ __device__ __forceinline__ bool mbar_wait_relaxed(uint64_t* bar, uint32_t parity
     if (mbar_try_wait(bar, parity)) return true;
   }
   if (err_flag) atomicExch(err_flag, 1);
+  __threadfence_system();
+  __trap();
   return false;
 }
 
@@ -235,6 +240,10 @@ int encode_tiled(CUtensorMap* map, CUtensorMapDataType dtype, uint32_t rank, con
                  const uint64_t* dims, const uint64_t* strides_bytes /* rank-1 */, const uint32_t* box,
                  CUtensorMapSwizzle swizzle);
 int sm_count();
+// true exactly once per (current CUDA device, family): function attributes (max dynamic shared memory) are per device,
+// so every device a process drives configures its kernels on first use (no process-wide flag).
+enum KernelFamily : int { KF_CONV_STACK = 0, KF_CONV_TC, KF_GEMM128, KF_GEMM256, KF_ATTN64, KF_ATTN128, KF_WGRAD, KF_POINTWISE_TC, KF_COUNT };
+bool first_use_on_device(int family);
 }  // namespace dp
 
 #define DP_CHECK(call)                                   \

@@ -557,7 +557,7 @@ extern "C" int dp_conv3d_stack(const void* in_c8, int cb_total_in, const uint8_t
   p.scale = scale; p.shift = shift; p.relu = relu;
   p.out_f32 = out_f32; p.out_hi = static_cast<__half*>(out_hi); p.out_lo = static_cast<__half*>(out_lo);
   p.cb_total_out = cb_total_out; p.cb_out_off = cb_out_off; p.stats = stats; p.err_flag = err_flag;
-  { const char* dbg = getenv("DP_STACK_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
+  { static const int dbg = [] { const char* e = getenv("DP_STACK_DEBUG"); return e ? atoi(e) : 0; }(); p.debug = dbg; }   // read once
 
   CUtensorMap tmap;
   const uint64_t dims[5] = {8, static_cast<uint64_t>(W), static_cast<uint64_t>(H), static_cast<uint64_t>(D),
@@ -573,8 +573,7 @@ extern "C" int dp_conv3d_stack(const void* in_c8, int cb_total_in, const uint8_t
   KernelFn fn = nullptr;
   if (k == 3) fn = T == 4 ? conv3d_stack_kernel<3, 4> : (T == 2 ? conv3d_stack_kernel<3, 2> : conv3d_stack_kernel<3, 1>);
   else fn = T == 4 ? conv3d_stack_kernel<7, 4> : (T == 2 ? conv3d_stack_kernel<7, 2> : conv3d_stack_kernel<7, 1>);
-  static bool configured = false;
-  if (!configured) {
+  if (first_use_on_device(KF_CONV_STACK)) {
     const int max_smem = 212 * 1024;
     DP_CHECK(cudaFuncSetAttribute(conv3d_stack_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     DP_CHECK(cudaFuncSetAttribute(conv3d_stack_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
@@ -582,7 +581,6 @@ extern "C" int dp_conv3d_stack(const void* in_c8, int cb_total_in, const uint8_t
     DP_CHECK(cudaFuncSetAttribute(conv3d_stack_kernel<7, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     DP_CHECK(cudaFuncSetAttribute(conv3d_stack_kernel<7, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     DP_CHECK(cudaFuncSetAttribute(conv3d_stack_kernel<7, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    configured = true;
   }
   int grid = sms < p.num_items ? sms : p.num_items;
   fn<<<grid, kStackThreads, smem, stream>>>(tmap, p);

@@ -483,15 +483,13 @@ static int launch_conv_tc(const void* in_c8, int cb_total_in, const uint8_t* chu
   int grid = sm_count();
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
   if (grid > p.num_tiles) grid = p.num_tiles;
-  static bool configured = false;
-  if (!configured) {
+  if (first_use_on_device(KF_CONV_TC)) {
     const int max_smem = 8 * 25 * 1024 + 1024 + 4096;
 #define DP_TC_ATTR(K_, T_) DP_CHECK(cudaFuncSetAttribute(conv3d_tc_kernel<K_, T_>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem))
     DP_TC_ATTR(1, 1); DP_TC_ATTR(1, 2); DP_TC_ATTR(1, 4);
     DP_TC_ATTR(3, 1); DP_TC_ATTR(3, 2); DP_TC_ATTR(3, 4);
     DP_TC_ATTR(5, 1); DP_TC_ATTR(7, 1); DP_TC_ATTR(7, 2);
 #undef DP_TC_ATTR
-    configured = true;
   }
 #define DP_TC_LAUNCH(K_, T_) conv3d_tc_kernel<K_, T_><<<grid, kConvThreads, smem, stream>>>(tmap, p)
   switch (k) {

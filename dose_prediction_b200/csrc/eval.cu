@@ -242,10 +242,14 @@ __global__ void __launch_bounds__(256) dice_counts_kernel(const float* logits, c
   }
 }
 // dice[n][c] = 2 I / (G + P) (NaN when the class is absent from the label, like monai); mean over the non-NaN foreground entries
+// monai 0.7.0 do_metric_reduction(f, "mean"): NaN entries (class absent from the label) are ignored; first the mean over
+// the classes of each sample, then the mean over the samples that have at least one class; 0 when there is none.
 __global__ void dice_finalize_kernel(const unsigned long long* counts, int N, int C, float* dice, float* mean_dice) {
-  double sum = 0.0;
-  int cnt = 0;
-  for (int n = 0; n < N; ++n)
+  double batch_sum = 0.0;
+  int batch_cnt = 0;
+  for (int n = 0; n < N; ++n) {
+    double sum = 0.0;
+    int cnt = 0;
     for (int c = 0; c < C; ++c) {
       const unsigned long long* q = counts + static_cast<size_t>(n) * 48 + c * 3;
       float d = nanf("");
@@ -253,7 +257,9 @@ __global__ void dice_finalize_kernel(const unsigned long long* counts, int N, in
       dice[n * C + c] = d;
       if (c >= 1 && q[1] > 0) { sum += d; ++cnt; }
     }
-  *mean_dice = cnt ? static_cast<float>(sum / cnt) : nanf("");
+    if (cnt) { batch_sum += sum / cnt; ++batch_cnt; }
+  }
+  *mean_dice = batch_cnt ? static_cast<float>(batch_sum / batch_cnt) : 0.f;
 }
 
 static inline unsigned eblk(long long n, int threads, unsigned cap) {

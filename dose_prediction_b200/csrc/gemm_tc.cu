@@ -369,10 +369,8 @@ static int launch_gemm_bn(const void* A, const void* B, dp::GemmParams& p, int a
       return rc;
   }
   const size_t smem = static_cast<size_t>(GemmCfg<BN>::kStages) * GemmCfg<BN>::kStage + 1024;
-  static bool configured = false;
-  if (!configured) {
+  if (first_use_on_device(BN == 256 ? KF_GEMM256 : KF_GEMM128)) {
     DP_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    configured = true;
   }
   int grid = sm_count();
   if (grid > p.num_tiles) grid = p.num_tiles;

@@ -293,18 +293,24 @@ __global__ void batch_combine_kernel(double* a, int N, int C, int k, long long v
                                      float* running_var, float momentum) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= C * k) return;
-  double s = 0.0;
-  for (int n = 0; n < N; ++n) s += a[static_cast<size_t>(n) * C * k + i];
-  s /= N;
-  for (int n = 0; n < N; ++n) a[static_cast<size_t>(n) * C * k + i] = s;
-  if (running_mean != nullptr && k == 2 && (i & 1) == 0) {
+  // with running statistics (k == 2: {sum, sumsq}) ONE thread owns both slots of a channel: the running variance
+  // needs the original sumsq values, which a neighbouring thread would otherwise be overwriting concurrently
+  const bool pair = running_mean != nullptr && k == 2;
+  if (pair && (i & 1)) return;
+  const int nslots = pair ? 2 : 1;
+  double m[2] = {0.0, 0.0};
+  for (int q = 0; q < nslots; ++q) {
+    double s = 0.0;
+    for (int n = 0; n < N; ++n) s += a[static_cast<size_t>(n) * C * k + i + q];
+    m[q] = s / N;
+  }
+  for (int q = 0; q < nslots; ++q)
+    for (int n = 0; n < N; ++n) a[static_cast<size_t>(n) * C * k + i + q] = m[q];
+  if (pair) {
     const int c = i >> 1;
-    double ss = 0.0;
-    for (int n = 0; n < N; ++n) ss += a[static_cast<size_t>(n) * C * k + i + 1];
-    ss /= N;
     const double cnt = static_cast<double>(vox) * N;
-    const double mean = s / vox;
-    double var = ss / vox - mean * mean;
+    const double mean = m[0] / vox;
+    double var = m[1] / vox - mean * mean;
     if (var < 0.0) var = 0.0;
     const double unbiased = cnt > 1.0 ? var * cnt / (cnt - 1.0) : var;
     running_mean[c] = static_cast<float>((1.0 - momentum) * running_mean[c] + momentum * mean);
@@ -644,6 +650,36 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* p, const float* g, fl
   const float denom = sqrtf(vi) / bc2_sqrt + eps;
   pi -= (lr / bc1) * (mi / denom);
   p[i] = pi;
+}
+// Same update with the optimizer step counter kept ON THE DEVICE (state[0] = completed steps, state[1] = consecutive
+// skipped steps, state[2] = total skipped steps): a step skipped for non-finite gradients must not advance the bias
+// correction, and the host never has to read found_inf back to know the step number.
+__global__ void __launch_bounds__(256) adamw_dev_kernel(float* p, const float* g, float* m, float* v, long long n, float lr,
+                                                        float b1, float b2, float eps, float wd, float inv_scale,
+                                                        const int* found_inf, const int* state) {
+  if (found_inf != nullptr && *found_inf != 0) return;
+  __shared__ float s_bc[2];
+  if (threadIdx.x == 0) {
+    const float step = static_cast<float>(state[0] + 1);
+    s_bc[0] = 1.f - powf(b1, step);
+    s_bc[1] = sqrtf(1.f - powf(b2, step));
+  }
+  __syncthreads();
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const float gi = g[i] * inv_scale;
+  const float mi = b1 * m[i] + (1.f - b1) * gi;
+  const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+  m[i] = mi;
+  v[i] = vi;
+  float pi = p[i] * (1.f - lr * wd);
+  const float denom = sqrtf(vi) / s_bc[1] + eps;
+  pi -= (lr / s_bc[0]) * (mi / denom);
+  p[i] = pi;
+}
+__global__ void adam_state_kernel(const int* found_inf, int* state) {
+  if (found_inf != nullptr && *found_inf != 0) { state[1] += 1; state[2] += 1; }
+  else { state[0] += 1; state[1] = 0; }
 }
 __global__ void __launch_bounds__(256) grad_check_kernel(const float* g, long long n, int* found_inf) {
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
@@ -1162,6 +1198,17 @@ extern "C" int dp_adamw(float* p, const float* g, float* m, float* v, long long 
   adamw_kernel<<<nblk(n, 256), 256, 0, stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2, inv_scale,
                                                   found_inf);
   return check_cuda(cudaGetLastError(), "adamw");
+}
+
+extern "C" int dp_adamw_dev(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                            float eps, float weight_decay, float inv_scale, const int* found_inf, int* state,
+                            cudaStream_t stream) {
+  DP_REQUIRE(state != nullptr, "adamw_dev: device optimizer state {steps, consecutive skips, total skips} required");
+  adamw_dev_kernel<<<nblk(n, 256), 256, 0, stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, inv_scale, found_inf,
+                                                      state);
+  DP_CHECK(cudaGetLastError());
+  adam_state_kernel<<<1, 1, 0, stream>>>(found_inf, state);
+  return check_cuda(cudaGetLastError(), "adamw_dev");
 }
 
 extern "C" int dp_grad_check(const float* g, long long n, int* found_inf, cudaStream_t stream) {

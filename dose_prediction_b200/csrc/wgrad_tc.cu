@@ -291,10 +291,8 @@ extern "C" int dp_conv3d_wgrad_tc(const void* x_c8, int x_cb_total, const uint8_
   const size_t smem = 2 * static_cast<size_t>(p.g_buf_bytes) + static_cast<size_t>(kWgXStages) * p.x_stage_bytes + 1024;
   constexpr size_t kMaxSmem = 200 * 1024;      // + static barriers stays under the 227 KB opt-in limit
   DP_REQUIRE(smem <= kMaxSmem, "conv3d_wgrad_tc: %zu bytes of shared memory", smem);
-  static bool configured = false;
-  if (!configured) {
+  if (first_use_on_device(KF_WGRAD)) {
     DP_CHECK(cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kMaxSmem)));
-    configured = true;
   }
   dim3 grid(static_cast<unsigned>(n_chunks * (cout / 16) * p.n_kdg), static_cast<unsigned>(splits));
   conv_wgrad_tc_kernel<<<grid, kWgThreads, smem, stream>>>(x_map, g_map, p);

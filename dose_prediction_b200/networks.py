@@ -696,12 +696,20 @@ class _PlanCache:
     def get(self, module, key, builder):
         ver = tuple(t._version for t in list(module.parameters()) + list(module.buffers()))
         ptrs = tuple(t.data_ptr() for t in module.parameters())
+        ver = (ver, getattr(module, "_dp_epoch", 0))      # bumped by invalidate_plans(): raw-pointer updates (trainers)
         if self.version != (ver, ptrs):
             self.plans.clear()
             self.version = (ver, ptrs)
         if key not in self.plans:
             self.plans[key] = builder()
         return self.plans[key]
+
+
+def invalidate_plans(model):
+    """Mark every cached inference plan under `model` stale.  The trainers update parameters and BatchNorm running
+    statistics through raw device pointers (dp_adamw / dp_batch_combine), which moves no tensor version counter."""
+    for m in model.modules():
+        object.__setattr__(m, "_dp_epoch", getattr(m, "_dp_epoch", 0) + 1)
 
 
 def _check_input(module, x, channels):

@@ -616,6 +616,21 @@ def allreduce_mean_(flat, group=None):
     return flat
 
 
+def unused_parameter_names(model):
+    """parameters that live in state_dict() but that no forward touches: the ViT cls_token, MainSubsetModel.out
+    (dose_pyfer.py:301-305) and conv3 of monai-0.7 UnetResBlocks whose input and output channels agree."""
+    out = set()
+    for mn, m in model.named_modules():
+        pre = mn + "." if mn else ""
+        if isinstance(m, nw._PatchEmbedding):
+            out.add(pre + "cls_token")
+        if isinstance(m, nw.MainSubsetModel):
+            out.update(pre + "out." + n for n, _ in m.out.named_parameters())
+        if isinstance(m, nw.UnetResBlock) and not m.downsample:
+            out.update(pre + "conv3." + n for n, _ in m.conv3.named_parameters())
+    return out
+
+
 class _Trainer:
     """Shared host side of the training steps: re-homes the trainable parameters into one flat fp32 buffer
     (+ flat gradient / Adam moment buffers), builds the static launch list once, replays it per step."""
@@ -628,10 +643,19 @@ class _Trainer:
         self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
         self.loss_scale = float(loss_scale)
         self.group = process_group
-        self.step_count = 0
+        self.step_count = 0                     # steps submitted; the bias-correction step lives on the device (opt_state)
+        self.opt_state = torch.zeros(3, dtype=torch.int32, device=dev)      # {completed, consecutive skips, total skips}
+        # parameters the forward never touches get grad None in the reference, so torch.optim.AdamW / bnb Adam skip them
+        # entirely (no decay either): keep them out of the flat optimizer range
+        unused = unused_parameter_names(model)
         for n, p in model.named_parameters():
             p.requires_grad_(bool(trainable(n)))
-        self.params = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+        self.params = [(n, p) for n, p in model.named_parameters() if p.requires_grad and n not in unused]
+        self.unused = [(n, p) for n, p in model.named_parameters() if p.requires_grad and n in unused]
+        # BatchNorm3d bookkeeping the reference's modules do in train mode: num_batches_tracked += 1 per forward
+        self._bn_counters = [m.num_batches_tracked for m in model.modules()
+                             if isinstance(m, nn.BatchNorm3d) and m.num_batches_tracked is not None
+                             and any(q.requires_grad for q in m.parameters())]
         total = sum((p.numel() + 3) // 4 * 4 for _, p in self.params)
         self.flat_p = torch.zeros(total, device=dev)
         self.flat_g = torch.zeros(total, device=dev)
@@ -680,8 +704,12 @@ class _Trainer:
             self.tail_off = self.offsets[names[first]][0]
         self._tail_work = None
 
+    skip_allreduce = False      # measurement only (bench.py): time the step without its collective
+
     def _start_tail_allreduce(self):
         import torch.distributed as dist
+        if self.skip_allreduce:
+            return
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
             self._tail_work = dist.all_reduce(self.flat_g[self.tail_off:], group=self.group, async_op=True)
 
@@ -689,13 +717,15 @@ class _Trainer:
         P = self.P
         P.refresh_weights()
         P.run()
+        if self._bn_counters:
+            torch._foreach_add_(self._bn_counters, 1)
         if self._tail_work is not None:            # bucket 2 (decoders + heads) has been in flight since the mark
             import torch.distributed as dist
             dist.all_reduce(self.flat_g[:self.tail_off], group=self.group)
             self._tail_work.wait()
             self._tail_work = None
             self.flat_g.div_(dist.get_world_size(self.group))
-        else:
+        elif not self.skip_allreduce:
             allreduce_mean_(self.flat_g, self.group)
         return self.loss
 
@@ -705,14 +735,35 @@ class _Trainer:
         lib = self.P.lib
         self.found_inf.zero_()
         _lib.check(lib.dp_grad_check(self.flat_g.data_ptr(), self.total, self.found_inf.data_ptr(), s), "dp_grad_check")
-        _lib.check(lib.dp_adamw(self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.flat_m.data_ptr(), self.flat_v.data_ptr(),
-                                self.total, self.lr, self.betas[0], self.betas[1], self.eps, self.wd, self.step_count,
-                                1.0 / self.loss_scale, self.found_inf.data_ptr(), s), "dp_adamw")
+        _lib.check(lib.dp_adamw_dev(self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.flat_m.data_ptr(),
+                                    self.flat_v.data_ptr(), self.total, self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
+                                    1.0 / self.loss_scale, self.found_inf.data_ptr(), self.opt_state.data_ptr(), s),
+                   "dp_adamw_dev")
+        # the parameters (and BatchNorm running statistics) just changed through raw pointers: no tensor version
+        # counter moved, so tell every cached inference plan of this model that its packed weights are stale
+        nw.invalidate_plans(self.model)
+        if self.step_count % self.HEALTH_EVERY == 0:
+            self.check_health()
+
+    HEALTH_EVERY = 64
+    MAX_CONSECUTIVE_SKIPS = 16
+
+    def check_health(self):
+        """host sync: raises if a tcgen05 pipeline fault was flagged or if the static loss scale keeps overflowing
+        (every step skipped: training would otherwise stall silently)."""
+        self.P.check_device_errors()
+        done, consec, total = (int(x) for x in self.opt_state.tolist())
+        if consec >= self.MAX_CONSECUTIVE_SKIPS:
+            raise RuntimeError(f"{consec} consecutive optimizer steps skipped for non-finite gradients (loss_scale="
+                               f"{self.loss_scale:g} overflows fp16): rebuild the trainer with a smaller loss_scale")
+        return {"completed_steps": done, "consecutive_skips": consec, "skipped_steps": total}
 
     def grads(self):
         """{parameter name: unscaled fp32 gradient} (copies; for tests / inspection)."""
-        return {n: (self.flat_g[o:o + k] / self.loss_scale).view(p.shape).clone()
-                for (n, p), (o, k) in ((np_, self.offsets[np_[0]]) for np_ in self.params)}
+        out = {n: (self.flat_g[o:o + k] / self.loss_scale).view(p.shape).clone()
+               for (n, p), (o, k) in ((np_, self.offsets[np_[0]]) for np_ in self.params)}
+        out.update({n: torch.zeros_like(p) for n, p in self.unused})      # autograd leaves these None (never used)
+        return out
 
 
 class DoseTrainer(_Trainer):

@@ -304,6 +304,11 @@ int dp_dice_ce_finalize(const double* acc, int N, int C, long long vox, float* l
  * (dp_grad_check) the update is skipped.                                                                */
 int dp_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
              float weight_decay, int step, float inv_scale, const int* found_inf, cudaStream_t stream);
+/* dp_adamw with the step counter on the device: state = int[3] {completed steps, consecutive skipped steps, total
+ * skipped steps}; a step skipped for non-finite gradients does not advance the bias correction (torch.optim.AdamW
+ * under GradScaler behaves the same way).                                                                       */
+int dp_adamw_dev(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+                 float weight_decay, float inv_scale, const int* found_inf, int* state, cudaStream_t stream);
 int dp_grad_check(const float* g, long long n, int* found_inf, cudaStream_t stream);
 
 /* Per-step re-packing of the live fp32 parameters into the kernels' fp16 operand layouts (what the inference

@@ -59,14 +59,19 @@ def dice_metric(logits, label):
     """monai 0.7.0 DiceMetric(include_background=False, reduction="mean", get_not_nans=False) applied to
     post_pred = AsDiscrete(argmax=True, to_onehot=True) and post_label (OARSegmentation/config.py:69-70,
     train_light_transeg.py:199-216): compute_meandice gives 2|y & y_pred| / (|y| + |y_pred|) per (batch, class), NaN when
-    the class is absent from y; the mean ignores NaNs.  (un-vendored monai code, restated.)"""
+    the class is absent from y; monai.metrics.utils.do_metric_reduction(f, "mean") then averages in TWO steps, ignoring
+    NaNs: over the classes of each sample first, then over the samples that have at least one class present (0 when no
+    sample has one).  (un-vendored monai code, restated.)"""
     n_cls = logits.shape[1]
     pred = logits.argmax(1)
     lab = label[:, 0].astype(np.int64)
-    vals = []
+    per_sample = []
     for b in range(logits.shape[0]):
+        vals = []
         for c in range(1, n_cls):
             y, yp = lab[b] == c, pred[b] == c
             if y.sum() > 0:
                 vals.append(2.0 * np.logical_and(y, yp).sum() / (y.sum() + yp.sum()))
-    return float(np.mean(vals)) if vals else float("nan")
+        if vals:
+            per_sample.append(float(np.mean(vals)))
+    return float(np.mean(per_sample)) if per_sample else 0.0

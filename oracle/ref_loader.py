@@ -4,7 +4,9 @@ Puts `oracle/monai_compat` (for `import monai`) and `/root/reference` on sys.pat
   DosePrediction.Models.Networks.dose_pyfer   (dose_pyfer.py:325 Model)
   OARSegmentation.Models.Networks.oar_transeg (oar_transeg.py:14 Model)
   DosePrediction.Train.loss                   (loss.py:50 GenLoss)
-Never used on the GPU box (no /root/reference there) and never by the product.
+On the GPU box (no /root/reference there) the same imports resolve against oracle/_ref, the git-ignored copy of exactly
+these files that oracle/make_ref.py makes in the build container; only tests/, bench.py's reference arm / cpu_baseline
+and __graft_entry__.smoke() may use this module, never the product.
 """
 import contextlib
 import importlib
@@ -12,8 +14,20 @@ import io
 import os
 import sys
 
-REFERENCE_ROOT = os.environ.get("DP_REFERENCE_ROOT", "/root/reference")
-_COMPAT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "monai_compat")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_PREBUILT = os.path.join(_HERE, "_ref")          # oracle/make_ref.py: unmodified copies of the files the path imports
+
+
+def _default_root():
+    if os.environ.get("DP_REFERENCE_ROOT"):
+        return os.environ["DP_REFERENCE_ROOT"]
+    if os.path.isdir("/root/reference/DosePrediction"):
+        return "/root/reference"
+    return _PREBUILT                                # the GPU box: /root/reference does not exist there
+
+
+REFERENCE_ROOT = _default_root()
+_COMPAT = os.path.join(_HERE, "monai_compat")
 
 
 def available() -> bool:

@@ -373,10 +373,10 @@ def dose_pyfer_train_step(sd: SD, x, gt, lr=1e-4, weight_decay=1e-4, delta1=10.0
         new_stats = dict(BN_TRAIN)
     finally:
         BN_TRAIN = None
+    # parameters the forward never touches keep grad None: torch.optim.AdamW (and bnb Adam8bit) skip them entirely
+    # (no weight decay either); they are reported with a zero gradient
     grads = {k: (leaf[k].grad if leaf[k].grad is not None else torch.zeros_like(leaf[k])) for k in train_keys}
     params = [leaf[k] for k in train_keys]
-    for p_, k in zip(params, train_keys):
-        p_.grad = grads[k]
     torch.optim.AdamW(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay).step()
     new = {k: leaf[k].detach() for k in train_keys}
     new.update(new_stats)
@@ -420,9 +420,7 @@ def oar_transeg_train_step(sd: SD, x, label, lr=1e-4, weight_decay=1e-5, betas=(
     finally:
         BN_TRAIN = None
     grads = {k: (leaf[k].grad if leaf[k].grad is not None else torch.zeros_like(leaf[k])) for k in train_keys}
-    params = [leaf[k] for k in train_keys]
-    for p_, k in zip(params, train_keys):
-        p_.grad = grads[k]
+    params = [leaf[k] for k in train_keys]                   # grad None (unused parameters): skipped by AdamW
     torch.optim.AdamW(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay).step()
     new = {k: leaf[k].detach() for k in train_keys}
     new.update(new_stats)

@@ -7,9 +7,10 @@ import sys
 from conftest import ROOT
 
 
-def _run(extra):
+def _run(extra, env=None):
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--size", "32", "--steps", "1",
-                          "--warmup", "0"] + extra, capture_output=True, text=True, timeout=600, cwd=ROOT)
+                          "--warmup", "0"] + extra, capture_output=True, text=True, timeout=600, cwd=ROOT,
+                         env=dict(os.environ, **(env or {})))
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.strip()]
     assert len(lines) == 1, out.stdout
@@ -23,8 +24,16 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
         assert key in line, key
     assert line["impl"] == "reference" and line["metric"] == "cascade_volumes_per_sec_128cubed" and line["unit"] == "volumes/s"
     assert line["value"] > 0 and line["higher_is_better"] is True and line["vs_baseline"] is None
-    assert "workload" in line["config"] and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    # the reference's own modules when /root/reference or oracle/_ref is there (kind "reference"), else the oracle port
+    from oracle import ref_loader
+    assert line["cpu_baseline"]["kind"] == ("reference" if ref_loader.available() else "port")
+    assert "workload" in line["config"] and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_reference_arm_falls_back_to_the_oracle_port():
+    line = _run([], env={"DP_BENCH_PORT": "1"})
+    assert line["cpu_baseline"]["kind"] == "port" and line["value"] > 0
 
 
 def test_reference_arm_of_the_training_workload():
