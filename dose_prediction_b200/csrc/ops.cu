@@ -255,6 +255,80 @@ __global__ void __launch_bounds__(256, 4) norm_act_kernel(const NormActParams p)
   if (want_stats) block_accumulate_sums(a1, a2, p.stats_out, static_cast<size_t>(n) * p.C + cb * 8);
 }
 
+// ------------------------------------------------------------------ InstanceNorm apply + 1x1x1 head in one pass
+// The decoder outputs feed both the next level and a C -> {1, 8} head (dose_convertors dose_pyfer.py:290-300,316-317,
+// conv_out_A :353,359, the seg logits base_blocks.py:151).  As a separate launch the head re-read the whole activation
+// (and spent 16 FMA columns on 1 output channel); here the thread that normalises a voxel keeps all its channels in
+// registers and adds the head's dot products, so the head costs one planar fp32 store.
+struct NormHeadParams {
+  const float* raw_f32; int in_cb_total;
+  const double* stats; const float* gamma; const float* beta; int act;
+  __half* out_hi; __half* out_lo; int out_cb_total, out_cb_off;
+  const float* head_w; const float* head_b; int head_co;       // [head_co][C] fp32, [head_co]
+  float* head_out;                                              // NCDHW fp32 [N][head_co][vox]
+  int C, ncb; long long vox; double inv_vox;
+};
+constexpr int NH_MAXC = 128, NH_MAXCO = 8;
+
+template <int CO>
+__global__ void __launch_bounds__(256) norm_act_head_kernel(const NormHeadParams p) {
+  __shared__ float s_mean[NH_MAXC], s_rstd[NH_MAXC], s_gamma[NH_MAXC], s_beta[NH_MAXC];   // same arithmetic as norm_act_kernel
+  __shared__ float s_w[CO][NH_MAXC];
+  const int n = blockIdx.y;
+  const int cpad = p.ncb * 8;
+  const bool affine = p.gamma != nullptr;
+  for (int c = threadIdx.x; c < cpad; c += blockDim.x) {
+    float m = 0.f, r = 0.f;                              // padded channels: (x - 0) * 0 = 0 through every activation
+    if (c < p.C) finalize_stats(p.stats, static_cast<size_t>(n) * p.C + c, p.inv_vox, m, r);
+    s_mean[c] = m;
+    s_rstd[c] = r;
+    s_gamma[c] = (affine && c < p.C) ? p.gamma[c] : 1.f;
+    s_beta[c] = (affine && c < p.C) ? p.beta[c] : 0.f;
+  }
+  for (int i = threadIdx.x; i < CO * cpad; i += blockDim.x) {
+    const int co = i / cpad, c = i % cpad;
+    s_w[co][c] = (c < p.C && co < p.head_co) ? p.head_w[co * p.C + c] : 0.f;
+  }
+  __syncthreads();
+  const long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (v >= p.vox) return;
+  float acc[CO];
+#pragma unroll
+  for (int co = 0; co < CO; ++co) acc[co] = (p.head_b && co < p.head_co) ? __ldg(&p.head_b[co]) : 0.f;
+  for (int cb = 0; cb < p.ncb; ++cb) {
+    float y[8];
+    load8f(p.raw_f32, ((static_cast<size_t>(n) * p.in_cb_total + cb) * p.vox + v) * 8, y);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) y[j] = (y[j] - s_mean[cb * 8 + j]) * s_rstd[cb * 8 + j];
+    if (affine) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) y[j] = fmaf(y[j], s_gamma[cb * 8 + j], s_beta[cb * 8 + j]);
+    }
+    act8(y, p.act);
+    if (p.out_hi) {
+      store8p(p.out_hi, p.out_lo, ((static_cast<size_t>(n) * p.out_cb_total + p.out_cb_off + cb) * p.vox + v) * 8, y);
+      if (p.out_lo == nullptr) {                           // the head must see what every other consumer of this tensor sees
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y[j] = __half2float(__float2half_rn(y[j]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float h = __half2float(__float2half_rn(y[j]));
+          y[j] = h + __half2float(__float2half_rn(y[j] - h));
+        }
+      }
+    }
+#pragma unroll
+    for (int co = 0; co < CO; ++co) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[co] = fmaf(y[j], s_w[co][cb * 8 + j], acc[co]);
+    }
+  }
+#pragma unroll
+  for (int co = 0; co < CO; ++co)
+    if (co < p.head_co) p.head_out[(static_cast<size_t>(n) * p.head_co + co) * p.vox + v] = acc[co];
+}
+
 // ------------------------------------------------------------------ 1x1x1 convolution, normalise-on-load, <=3 sources
 struct PwSource {
   const __half* hi; const __half* lo; const float* raw; int cb_total, cb_off, C;
@@ -1041,6 +1115,25 @@ extern "C" int dp_norm_act(const float* raw_f32, const void* raw_hi, const void*
   p.s2d_cb_off = s2d_cb_off; p.D = D; p.H = H > 0 ? H : 1; p.W = W > 0 ? W : 1;
   dim3 grid(blocks_for(vox, 256 * NA_IT), N * p.ncb);
   norm_act_kernel<<<grid, 256, 0, stream>>>(p);
+  DP_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dp_norm_act_head(const float* raw_f32, int in_cb_total, const double* stats, const float* gamma, const float* beta,
+                                int act, void* out_hi, void* out_lo, int out_cb_total, int out_cb_off, const float* head_w,
+                                const float* head_b, int head_co, float* head_out, int N, int C, long long vox,
+                                cudaStream_t stream) {
+  DP_REQUIRE(raw_f32 != nullptr && stats != nullptr && head_w != nullptr && head_out != nullptr, "dp_norm_act_head: missing operand");
+  DP_REQUIRE(C >= 1 && C <= NH_MAXC && head_co >= 1 && head_co <= NH_MAXCO, "dp_norm_act_head: C=%d (<= %d), head_co=%d (<= %d)",
+             C, NH_MAXC, head_co, NH_MAXCO);
+  NormHeadParams p{};
+  p.raw_f32 = raw_f32; p.in_cb_total = in_cb_total; p.stats = stats; p.gamma = gamma; p.beta = beta; p.act = act;
+  p.out_hi = static_cast<__half*>(out_hi); p.out_lo = static_cast<__half*>(out_lo); p.out_cb_total = out_cb_total;
+  p.out_cb_off = out_cb_off; p.head_w = head_w; p.head_b = head_b; p.head_co = head_co; p.head_out = head_out;
+  p.C = C; p.ncb = (C + 7) / 8; p.vox = vox; p.inv_vox = 1.0 / static_cast<double>(vox);
+  dim3 grid(blocks_for(vox, 256), N);
+  if (head_co == 1) norm_act_head_kernel<1><<<grid, 256, 0, stream>>>(p);
+  else norm_act_head_kernel<NH_MAXCO><<<grid, 256, 0, stream>>>(p);
   DP_CHECK(cudaGetLastError());
   return 0;
 }

@@ -23,6 +23,7 @@ ACT_ID = {None: ACT_NONE, "none": ACT_NONE, "relu": ACT_RELU, "lrelu": ACT_LRELU
 STATS_DOUBLES = 1 << 20
 STACK_TILES = int(os.environ.get("DP_STACK_TILES", "0"))
 FOLD_P3 = os.environ.get("DP_FOLD_P3", "1") != "0"
+FUSE_HEADS = os.environ.get("DP_FUSE_HEADS", "1") != "0"         # bring-up switch: 1^3 heads folded into the producing norm_act
 FOLD_TC_MAX = int(os.environ.get("DP_FOLD_TC_MAX", "32"))        # plain tcgen05 conv: fold [W_hi | W_lo] into N up to this C_out
 POINTWISE_CW = os.environ.get("DP_POINTWISE_CW", "1") != "0"     # bring-up switch: constant-bank weights for static 1^3 convs
 POINTWISE_TC = os.environ.get("DP_POINTWISE_TC", "1") != "0"    # bring-up switch: wide coarse-level 1^3 convs on the tensor cores
@@ -131,6 +132,7 @@ class Plan:
         self.training = False    # training plans re-derive packed weights from the live parameters every step
         self.refresh = []        # (packed tensor, function returning its new value)
         self.refresh_launches = []   # (C entry point name, args): device-side re-packing of live parameters
+        self._na_producer = {}       # (buffer ptr, cb_off) -> the plain norm_act launch that wrote that activation
 
     # ------------------------------------------------------------------ memory
     def zeros(self, shape, dtype):
@@ -521,6 +523,10 @@ class Plan:
                 return 0
             return 4 if isinstance(t, Raw) else (4 if t.lo_off is not None else 2)
         self.count_bytes("dp_norm_act", N * vox * cpad * (_bytes(src) + _bytes(res) + _bytes(out) + _bytes(s2d)))
+        if isinstance(src, Raw) and res is None and s2d is None and stats_out is None and out is not None and not identity \
+                and not self.training:
+            # remembered so that a 1^3 head reading `out` can be folded into this launch (Plan.head)
+            self._na_producer[(out.buf.data_ptr(), out.cb_off)] = (len(self.steps), src, stats, gamma, beta, act, out, N, C, vox)
         self.add("dp_norm_act", rf, rh, rl, icb, ioff, stats.data_ptr() if stats is not None else None,
                  gamma.data_ptr() if gamma is not None else None, beta.data_ptr() if beta is not None else None,
                  ACT_ID[act], eh, el, er, es, ecb, eoff, ACT_ID[act_after_res], oh, ol, ocb, ooff,
@@ -528,6 +534,24 @@ class Plan:
                  s2d.hi_ptr if s2d is not None else None, s2d.lo_ptr if s2d is not None else None,
                  s2d.cb_total if s2d is not None else 0, s2d.cb_off if s2d is not None else 0,
                  *(tuple(2 * d for d in s2d.dims) if s2d is not None else (0, 0, 0)))
+
+    def head(self, a, weight, bias, out_planar):
+        """1x1x1 conv C -> head_co (+bias) of activation `a` into NCDHW fp32 (dose heads, conv_out_A, seg logits).
+        Folded into the norm_act launch that produced `a` when there is one; else a pointwise launch."""
+        Co = weight.shape[0]
+        prod = self._na_producer.get((a.buf.data_ptr(), a.cb_off)) if FUSE_HEADS else None
+        if prod is None or Co > 8 or a.C > 128 or prod[8] != a.C:
+            return self.pointwise([(a, None, None)], weight, bias, out_planar=out_planar)
+        idx, src, stats, gamma, beta, act, out, N, C, vox = prod
+        assert self.steps[idx][2] == "dp_norm_act"
+        w = self.dev(weight.reshape(Co, -1))
+        b = self.dev(bias) if bias is not None else None
+        self.count_bytes("dp_norm_act", N * vox * 4 * Co)
+        args = (src.t.data_ptr(), src.cb_total, stats.data_ptr(), gamma.data_ptr() if gamma is not None else None,
+                beta.data_ptr() if beta is not None else None, ACT_ID[act], out.hi_ptr, out.lo_ptr, out.cb_total, out.cb_off,
+                w.data_ptr(), b.data_ptr() if b is not None else None, Co, out_planar.data_ptr(), N, C, vox)
+        self.steps[idx] = (getattr(self.lib, "dp_norm_act_head"), args, "dp_norm_act_head")
+        del self._na_producer[(a.buf.data_ptr(), a.cb_off)]
 
     def pointwise(self, srcs, weight, bias, out_raw=None, out_act=None, out_planar=None, out_act_fn=None):
         """1x1x1 conv over cat(srcs); srcs: list of (Act|Raw, stats|None, act|None)."""

@@ -827,7 +827,7 @@ def _emit_main_subset(P, net, parts):
     outs = []
     for d, conv in zip(decs, net.dose_convertors):
         y = P.zeros((d.N, net.out_ch) + d.dims, torch.float32)
-        P.pointwise([(d, None, None)], conv[0].weight, conv[0].bias, out_planar=y)
+        P.head(d, conv[0].weight, conv[0].bias, y)
         outs.append(y)
     return outs
 
@@ -866,7 +866,7 @@ def emit_dose_pyfer(P, model, x_act, a_out):
     _emit_base_unet(P, model.net_A, x_act, a_out)
     N, dims = x_act.N, x_act.dims
     out_A = P.zeros((N, model.out_ch) + dims, torch.float32)
-    P.pointwise([(a_out, None, None)], model.conv_out_A.weight, model.conv_out_A.bias, out_planar=out_A)
+    P.head(a_out, model.conv_out_A.weight, model.conv_out_A.bias, out_A)
     outs = _emit_main_subset(P, model.net_B, [a_out, x_act])
     return out_A, outs
 
@@ -963,7 +963,7 @@ def emit_oar_transeg(P, model, x_act):
                        prec_deep=PREC_SEG_DEEP)
     d = decs[0]
     logits = P.zeros((d.N, model.out_channels) + d.dims, torch.float32)
-    P.pointwise([(d, None, None)], model.out.conv.conv.weight, model.out.conv.conv.bias, out_planar=logits)
+    P.head(d, model.out.conv.conv.weight, model.out.conv.conv.bias, logits)
     return logits
 
 

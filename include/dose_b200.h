@@ -121,6 +121,14 @@ int dp_norm_act(const float* raw_f32, const void* raw_hi, const void* raw_lo, in
                 int N, int C, long long vox, void* s2d_hi, void* s2d_lo, int s2d_cb_total, int s2d_cb_off, int D, int H,
                 int W, cudaStream_t stream);
 
+/* dp_norm_act (raw fp32 in, no residual) fused with the 1x1x1 head that consumes its result: the dose heads
+ * (dose_pyfer.py:290-300,316-317), conv_out_A (:353,359) and the seg logits (base_blocks.py:151-165).
+ * head_w fp32 [head_co][C], head_b [head_co] or NULL, head_out NCDHW fp32 [N][head_co][vox]; head_co <= 8, C <= 128.
+ * The head contracts the values exactly as stored (fp16, or the fp16 hi+lo pair when out_lo is given).    */
+int dp_norm_act_head(const float* raw_f32, int in_cb_total, const double* stats, const float* gamma, const float* beta,
+                     int act, void* out_hi, void* out_lo, int out_cb_total, int out_cb_off, const float* head_w,
+                     const float* head_b, int head_co, float* head_out, int N, int C, long long vox, cudaStream_t stream);
+
 /* nn.Conv3d k=1 over the channel-concatenation of up to three sources, each normalised/activated on
  * load: blocks_MDUNet.py:145-157 (cat(x3,x7) -> 1^3), monai UnetResBlock.conv3, heads dose_pyfer.py:290-300,353,
  * base_blocks.py:151 (seg logits).  Output: raw c8 fp32 (+stats), c8 fp16, or NCDHW fp32 (out_planar).
