@@ -23,6 +23,7 @@ ACT_ID = {None: ACT_NONE, "none": ACT_NONE, "relu": ACT_RELU, "lrelu": ACT_LRELU
 STATS_DOUBLES = 1 << 20
 STACK_TILES = int(os.environ.get("DP_STACK_TILES", "0"))
 FOLD_P3 = os.environ.get("DP_FOLD_P3", "1") != "0"
+POINTWISE_TCK = os.environ.get("DP_POINTWISE_TCK", "1") != "0"  # bring-up switch: 1^3 convs on tcgen05 with normalise-on-load
 FUSE_HEADS = os.environ.get("DP_FUSE_HEADS", "1") != "0"         # bring-up switch: 1^3 heads folded into the producing norm_act
 FOLD_TC_MAX = int(os.environ.get("DP_FOLD_TC_MAX", "32"))        # plain tcgen05 conv: fold [W_hi | W_lo] into N up to this C_out
 POINTWISE_CW = os.environ.get("DP_POINTWISE_CW", "1") != "0"     # bring-up switch: constant-bank weights for static 1^3 convs
@@ -591,6 +592,25 @@ class Plan:
         if out_planar is not None:
             out_b += 4 * Co
         ncb = sum(ceil_div(c, 8) for c in Cs)
+        if (not self.training and POINTWISE_TCK and Co in (16, 32, 64) and ncb <= 16 and out_planar is None
+                and out_act_fn is None and ((out_raw is not None) != (out_act is not None))):
+            # tcgen05 contraction; the sources' pending IN + activation are applied by the threads staging the A operand
+            Wp = torch.zeros((Co, (ncb + (ncb & 1)) * 8), device=self.device)
+            wl = weight.detach().reshape(Co, -1).to(self.device, torch.float32)
+            kp = lb = 0
+            for c in Cs:
+                Wp[:, kp:kp + c] = wl[:, lb:lb + c]
+                kp += ceil_div(c, 8) * 8
+                lb += c
+            whi = Wp.half()
+            wlo = (Wp - whi.float()).half()
+            wpk = torch.cat((whi, wlo), 0).view(2 * Co, -1, 8).permute(1, 0, 2).contiguous()      # [K/8][2*Co][8]
+            self.keep.append(wpk)
+            self.count_flops("dp_pointwise_tc", 2.0 * N * vox * sum(Cs) * Co)
+            self.count_bytes("dp_pointwise_tc", N * vox * (in_b + out_b))
+            self.add("dp_pointwise_tc", len(srcs), *arrs, wpk.data_ptr(), b.data_ptr() if b is not None else None, Co, N, vox,
+                     of, oh, ol, ocb, ooff, st, self.err.data_ptr())
+            return
         if (not self.training and POINTWISE_TC and ncb >= 12 and Co % 16 == 0 and out_raw is not None and out_act is None
                 and out_planar is None and out_act_fn is None and all(c % 16 == 0 for c in Cs)):
             # wide 1^3 convs of the coarse levels (128 / 256 input channels, few voxels): the SIMT kernel is latency

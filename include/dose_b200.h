@@ -144,6 +144,18 @@ int dp_pointwise_conv(int nsrc, const void* const* src_hi, const void* const* sr
  * travel as kernel parameters and are consumed from the constant bank as FFMA operands (no weight loads: the
  * shared-memory return path was what bounded dp_pointwise_conv).  Padded input channel blocks (8 channels each, per
  * source) must number 1, 2, 3, 4, 6 or 8.                                                                     */
+/* The same 1x1x1 convolution on tcgen05 tensor cores (csrc/pointwise_tc.cu): the staging threads apply each source's
+ * pending InstanceNorm + activation, split the fp32 result into an fp16 hi+lo pair and write it straight into the UMMA
+ * operand layout; 3-term operand split (A_hi.[W_hi|W_lo] + A_lo.W_hi), fp32 accumulation in TMEM.
+ *   wpack  fp16 [K/8][2*cout][8]: rows 0..cout-1 = fp16(W), rows cout..2cout-1 = fp16(W - fp16(W)); K = every source's
+ *          channels padded to whole 8-channel blocks, then to a multiple of 16; cout in {16, 32, 64}, K <= 128.
+ * Output: raw c8 fp32 (+ statistics) or c8 fp16 hi[/lo].                                                      */
+int dp_pointwise_tc(int nsrc, const void* const* src_hi, const void* const* src_lo, const float* const* src_raw,
+                    const int* src_cb_total, const int* src_cb_off, const int* src_C, const double* const* src_stats,
+                    const int* src_act, const void* wpack, const float* bias, int cout, int N, long long vox,
+                    float* out_raw, void* out_hi, void* out_lo, int out_cb_total, int out_cb_off, double* stats_out,
+                    int* err_flag, cudaStream_t stream);
+
 int dp_pointwise_conv_cw(int nsrc, const void* const* src_hi, const void* const* src_lo, const float* const* src_raw,
                          const int* src_cb_total, const int* src_cb_off, const int* src_C,
                          const double* const* src_stats, const int* src_act, const float* w_host, const float* bias_host,

@@ -287,7 +287,7 @@ def test_pointwise_wide_coarse_level_goes_through_the_tensor_cores(wide):
     P.pointwise([(y3, st3, "mish"), (y7, st7, "mish")], w, bias, out_raw=out)
     P.run()
     _finish(P)
-    assert any(st[2] == "dp_conv3d_tc" for st in P.steps)
+    assert any(st[2] in ("dp_conv3d_tc", "dp_pointwise_tc") for st in P.steps)
     e3, e7 = (x3, x7) if wide else (_h(x3), _h(x7))
     cat = torch.cat((F.mish(F.instance_norm(e3.double().cpu(), eps=1e-5)), F.mish(F.instance_norm(e7.double().cpu(), eps=1e-5))), 1)
     want = F.conv3d(cat, w.double().cpu(), bias.double().cpu())
@@ -295,6 +295,56 @@ def test_pointwise_wide_coarse_level_goes_through_the_tensor_cores(wide):
     assert _rel(got, want) < (2e-5 if wide else 2e-3)
     st = out.stats.view(N, C, 2).cpu()
     assert torch.allclose(st[..., 0], got.double().sum((2, 3, 4)), rtol=1e-4, atol=1e-2)
+
+
+@pytest.mark.parametrize("Cs,Co,dims,acts,lo,out_act", [
+    ((16, 9), 16, (5, 6, 7), (None, None), True, False),          # res-block conv3 of net_B: cat(out_net_A, x), ragged tile
+    ((16, 16), 16, (8, 16, 16), ("relu", "relu"), True, False),    # seg decoder 1^3: hi/lo sources, IN + ReLU on load
+    ((32, 32), 32, (4, 8, 12), ("mish", "mish"), False, False),    # dose decoder 1^3: fp16 sources, IN + Mish on load
+    ((64, 64), 64, (3, 5, 9), ("mish", "mish"), False, False),     # K = 128, C_out = 64 (shuffle-reduced statistics)
+    ((16, 16), 16, (4, 8, 8), (None, None), False, True),          # OldModels TRANSEG: bare 1^3 conv, fp16 output
+    ((8, 8, 8), 16, (4, 4, 8), ("lrelu", None, "relu"), True, False)])   # odd number of 8-channel blocks (zero block)
+def test_pointwise_tc_matches_torch(Cs, Co, dims, acts, lo, out_act):
+    """dp_pointwise_tc: tcgen05 1^3 conv with InstanceNorm + activation applied on load, vs fp64 torch."""
+    torch.manual_seed(60 + sum(Cs) + Co)
+    dev = torch.device("cuda:0")
+    N = 2
+    xs = [torch.randn(N, c, *dims, device=dev) * (1 + i) + 0.5 * i for i, c in enumerate(Cs)]
+    w = torch.randn(Co, sum(Cs), 1, 1, 1, device=dev) / sum(Cs) ** 0.5
+    bias = torch.randn(Co, device=dev)
+    P = _plan()
+    srcs, refs = [], []
+    for x, act in zip(xs, acts):
+        a = _act_from(P, x, lo)
+        e = x if lo else _h(x)
+        if act is None:
+            srcs.append((a, None, None))
+            refs.append(e.double().cpu())
+        else:
+            st = P.new_stats(N, x.shape[1])
+            y = P.new_act(N, x.shape[1], dims, lo=lo)
+            P.norm_act(a, y, identity=True, stats_out=st)
+            srcs.append((y, st, act))
+            f = {"relu": F.relu, "mish": F.mish, "lrelu": lambda t: F.leaky_relu(t, 0.01)}[act]
+            refs.append(f(F.instance_norm(e.double().cpu(), eps=1e-5)))
+    want = F.conv3d(torch.cat(refs, 1), w.double().cpu(), bias.double().cpu())
+    if out_act:
+        out = P.new_act(N, Co, dims, lo=True)
+        P.pointwise(srcs, w, bias, out_act=out)
+        y = torch.zeros(N, Co, *dims, device=dev)
+        P.unpack(out, y)
+    else:
+        out = P.get_raw(N, Co, dims)
+        P.pointwise(srcs, w, bias, out_raw=out)
+    P.run()
+    _finish(P)
+    assert any(st[2] == "dp_pointwise_tc" for st in P.steps)
+    got = (y if out_act else _raw_to_ncdhw(out.t)).cpu()
+    assert _rel(got, want) < 2e-5
+    if not out_act:
+        st = out.stats.view(N, Co, 2).cpu()
+        assert torch.allclose(st[..., 0], got.double().sum((2, 3, 4)), rtol=1e-4, atol=1e-2)
+        assert torch.allclose(st[..., 1], (got.double() ** 2).sum((2, 3, 4)), rtol=1e-4, atol=1e-2)
 
 
 def test_deconv2x_c8_and_token_inputs():
