@@ -218,6 +218,10 @@ class Plan:
         return t
 
     def refresh_weights(self):
+        with torch.cuda.device(self.device):
+            self._refresh_weights()
+
+    def _refresh_weights(self):
         s = torch.cuda.current_stream(self.device).cuda_stream
         for name, args in self.refresh_launches:
             rc = getattr(self.lib, name)(*args, s)
@@ -238,6 +242,12 @@ class Plan:
         return t
 
     def run(self):
+        # kernels launch on the CURRENT device: make it this plan's device for the duration of the replay, so that one
+        # process can drive several GPUs (one plan / handle per device) without the caller switching devices
+        with torch.cuda.device(self.device):
+            self._run()
+
+    def _run(self):
         s = torch.cuda.current_stream(self.device).cuda_stream
         if self.stats_used:
             self.stats[:self.stats_used].zero_()
@@ -334,20 +344,22 @@ class Plan:
 
     def capture(self):
         """Record run() into a CUDA graph (launch-bound replay); falls back to nothing — errors raise."""
-        st = torch.cuda.Stream(self.device)
-        st.wait_stream(torch.cuda.current_stream(self.device))
-        with torch.cuda.stream(st):
-            self.run()
-        torch.cuda.current_stream(self.device).wait_stream(st)
-        torch.cuda.synchronize(self.device)
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            self.run()
-        self.graph = g
+        with torch.cuda.device(self.device):
+            st = torch.cuda.Stream(self.device)
+            st.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(st):
+                self.run()
+            torch.cuda.current_stream(self.device).wait_stream(st)
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.run()
+            self.graph = g
 
     def replay(self):
         if self.graph is not None:
-            self.graph.replay()
+            with torch.cuda.device(self.device):
+                self.graph.replay()
         else:
             self.run()
 
