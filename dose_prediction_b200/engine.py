@@ -247,12 +247,18 @@ class Plan:
         with torch.cuda.device(self.device):
             self._run()
 
-    def _run(self):
+    def run_range(self, start, stop, zero_stats):
+        """replay steps[start:stop] only (the autograd shims run the forward and the backward halves of a training
+        launch list separately); zero_stats: this range begins a new forward pass"""
+        with torch.cuda.device(self.device):
+            self._run(start, stop, zero_stats)
+
+    def _run(self, start=0, stop=None, zero_stats=True):
         s = torch.cuda.current_stream(self.device).cuda_stream
-        if self.stats_used:
+        if self.stats_used and zero_stats:
             self.stats[:self.stats_used].zero_()
         n = 0
-        for fn, args, name in self.steps:
+        for fn, args, name in (self.steps if (start == 0 and stop is None) else self.steps[start:stop]):
             if fn is None:
                 if name == "py":
                     args[0]()

@@ -213,6 +213,10 @@ class UnetrUpBlock(nn.Module):
         self.transp_conv = _conv_layer(in_channels, out_channels, 2, 2, transposed=True)
         self.conv_block = UnetBasicBlock(out_channels + out_channels, out_channels)
 
+    def forward(self, inp, skip):
+        """monai UnetrUpBlock.forward: transp_conv(inp) -> cat(out, skip) -> conv_block."""
+        return _up_block_forward(self, inp, skip)
+
 
 class UnetrBasicBlock(nn.Module):
     def __init__(self, in_channels, out_channels):
@@ -323,6 +327,11 @@ class ModifiedUnetrUpBlock(nn.Module):
         self.act = act
         self.transp_conv = _conv_layer(in_channels, out_channels, 2, 2, transposed=True)
         self.conv_block = MultiUnetBasicBlock(out_channels + out_channels, out_channels, act=act, multiS_conv=multiS_conv, old=old)
+
+    def forward(self, inp, skip):
+        """base_blocks.py:136-141: transp_conv(inp) -> cat(out, skip) -> conv_block.  inp [B,C_in,d,h,w], skip
+        [B,C_out,2d,2h,2w] fp32 CUDA -> [B,C_out,2d,2h,2w]."""
+        return _up_block_forward(self, inp, skip)
 
 
 class ModifiedUnetOutBlock(nn.Module):
@@ -669,21 +678,36 @@ def _emit_unetr(P, vit, enc_blocks, dec_blocks, parts, taps, prec, prec_deep=Non
     N, dims = parts[0].N, parts[0].dims
     fs = enc_blocks[0].layer.conv1.conv.weight.shape[0]
     precs = [prec, prec, prec_deep or prec, prec_deep or prec]          # per level, fine -> coarse
-    z, hs = _emit_vit(P, vit, parts, N, dims, taps)
     sizes = [dims, tuple(d // 2 for d in dims), tuple(d // 4 for d in dims), tuple(d // 8 for d in dims)]
     cats = [P.new_concat(N, [fs << i, fs << i], sizes[i], lo=precs[i].lo) for i in range(4)]     # [deconv out | skip]
-    _emit_res_block(P, enc_blocks[0].layer, parts, cats[0][1], precs[0])
-    _emit_pr_up(P, enc_blocks[1], hs[taps[0]], cats[1][1], precs[1])
-    _emit_pr_up(P, enc_blocks[2], hs[taps[1]], cats[2][1], precs[2])
-    _emit_pr_up(P, enc_blocks[3], hs[taps[2]], cats[3][1], precs[3])
+    z = _emit_unetr_encoder(P, vit, enc_blocks, parts, taps, precs, [c[1] for c in cats])
+    return _emit_unetr_decoder(P, dec_blocks, z, cats, precs)
+
+
+def _emit_unetr_encoder(P, vit, enc_blocks, parts, taps, precs, skip_slots):
+    """ViTEncoder.forward (dose_pyfer.py:124-144) / the encoder half of oar_transeg Model.forward: ViT, then the four conv
+    skips written into `skip_slots` (usually the second halves of the decoder's concat buffers); returns the z12 tokens."""
+    N, dims = parts[0].N, parts[0].dims
+    z, hs = _emit_vit(P, vit, parts, N, dims, taps)
+    _emit_res_block(P, enc_blocks[0].layer, parts, skip_slots[0], precs[0])
+    _emit_pr_up(P, enc_blocks[1], hs[taps[0]], skip_slots[1], precs[1])
+    _emit_pr_up(P, enc_blocks[2], hs[taps[1]], skip_slots[2], precs[2])
+    _emit_pr_up(P, enc_blocks[3], hs[taps[2]], skip_slots[3], precs[3])
+    return z
+
+
+def _emit_unetr_decoder(P, dec_blocks, z, cats, precs):
+    """PyMSCDecoder.forward (dose_pyfer.py:232-239) / decoder5..2 of oar_transeg: coarse to fine; cats[lvl] = the
+    [deconv out | skip] concat buffer of level lvl.  Returns [dec1 (full res), dec2, dec3, dec4]."""
     decs = []
     inp = z
     for lvl, blk in zip((3, 2, 1, 0), dec_blocks):
-        out = P.new_act(N, fs << lvl, sizes[lvl], lo=precs[lvl].lo)
+        N, C, dims = cats[lvl][1].N, cats[lvl][1].C, cats[lvl][1].dims
+        out = P.new_act(N, C, dims, lo=precs[lvl].lo)
         _emit_up_block(P, blk, inp, cats[lvl], out, precs[lvl])
         decs.append(out)
         inp = out
-    return decs[::-1]          # [dec1 (full res), dec2, dec3, dec4]
+    return decs[::-1]
 
 
 class _PlanCache:
@@ -723,6 +747,35 @@ def _check_input(module, x, channels):
     return x.detach().to(torch.float32).contiguous()
 
 
+def _check_tensor(module, t, channels=None):
+    if module.training:
+        raise RuntimeError("dose_prediction_b200: this sub-module's forward is inference only (call .eval()); train-mode "
+                           "forward is built for the top-level networks (Model, OARTranseg / TRANSEG)")
+    if not (t.is_cuda and t.dim() == 5):
+        raise RuntimeError("expected a CUDA tensor [B,C,D,H,W]; dose_prediction_b200 has no CPU fallback")
+    if channels is not None and t.shape[1] != channels:
+        raise ValueError(f"expected {channels} input channels, got {t.shape[1]}")
+    return t.detach().to(torch.float32).contiguous()
+
+
+def _run_block(module, inputs, builder):
+    """sub-block forward: one cached plan per input shapes; builder(P, shapes) must set P.inputs (static fp32 NCDHW
+    tensors to fill) and P.result (callable)."""
+    if not hasattr(module, "_cache"):
+        object.__setattr__(module, "_cache", _PlanCache())
+    key = (tuple(tuple(t.shape) for t in inputs), inputs[0].device.index)
+
+    def build():
+        P = Plan(inputs[0].device)
+        builder(P, [tuple(t.shape) for t in inputs])
+        return P
+    plan = module._cache.get(module, key, build)
+    for dst, src in zip(plan.inputs, inputs):
+        dst.copy_(src)
+    plan.replay()
+    return plan.result()
+
+
 def _run_single(module, x, plan_fn):
     x = _check_input(module, x, module.in_ch)
     if not hasattr(module, "_cache"):
@@ -745,6 +798,27 @@ def _plan_base_unet(net, shape, device):
     P.unpack(out, y)
     P.result = lambda: y.clone()
     return P
+
+
+def _up_block_forward(blk, inp, skip):
+    Ci, Co = blk.transp_conv.conv.weight.shape[0], blk.transp_conv.conv.weight.shape[1]
+    inp, skip = _check_tensor(blk, inp, Ci), _check_tensor(blk, skip, Co)
+    if tuple(skip.shape[2:]) != tuple(2 * d for d in inp.shape[2:]) or skip.shape[0] != inp.shape[0]:
+        raise ValueError(f"skip {tuple(skip.shape)} does not match the 2x up-sampled input {tuple(inp.shape)}")
+
+    def build(P, shapes):
+        N, dims_in, dims = shapes[0][0], shapes[0][2:], shapes[1][2:]
+        P.inputs = [P.zeros(shapes[0], torch.float32), P.zeros(shapes[1], torch.float32)]
+        a = P.new_act(N, Ci, dims_in, lo=True)
+        P.pack_input(P.inputs[0], a)
+        cat = P.new_concat(N, [Co, Co], dims, lo=True)
+        P.pack_input(P.inputs[1], cat[1])
+        out = P.new_act(N, Co, dims, lo=True)
+        _emit_up_block(P, blk, a, cat, out, PREC_SEG)             # stand-alone block: the high-precision recipe
+        y = P.zeros((N, Co) + tuple(dims), torch.float32)
+        P.unpack(out, y)
+        P.result = lambda: y.clone()
+    return _run_block(blk, [inp, skip], build)
 
 
 # =========================================================================== DOSE-PYFER
@@ -775,6 +849,35 @@ class ViTEncoder(nn.Module):
         self.skip4 = UnetrPrUpBlock(hidden_size, feature_size * 8, num_layer=0)
         self.proj_axes = (0, spatial_dims + 1) + tuple(d + 1 for d in range(spatial_dims))
         self.proj_view_shape = list(self.feat_size) + [self.hidden_size]
+        self.in_ch = in_channels
+
+    def proj_feat(self, x):
+        """dose_pyfer.py:118-122: [B,N,C] -> [B,C,h,w,d]."""
+        x = x.view([x.size(0)] + self.proj_view_shape)
+        return x.permute(self.proj_axes).contiguous()
+
+    def forward(self, x_in):
+        """dose_pyfer.py:124-144: x_in [B,C,S,S,S] -> [enc1 [B,fs,S^3], enc2 [B,2fs,(S/2)^3], enc3, enc4, enc5 [B,768,(S/16)^3]]."""
+        x = _check_tensor(self, x_in, self.in_ch)
+        enc = self
+
+        def build(P, shapes):
+            N, dims = shapes[0][0], tuple(shapes[0][2:])
+            P.inputs = [P.zeros(shapes[0], torch.float32)]
+            x_act = P.new_act(N, enc.in_ch, dims, lo=False)
+            P.pack_input(P.inputs[0], x_act)
+            fs = enc.skip1.layer.conv1.conv.weight.shape[0]
+            i = enc.num_layers // 4
+            slots = [P.new_act(N, fs << l, tuple(d >> l for d in dims)) for l in range(4)]
+            z = _emit_unetr_encoder(P, enc.vit, (enc.skip1, enc.skip2, enc.skip3, enc.skip4), [x_act], (i, 2 * i, 3 * i),
+                                    [PREC_NET_B] * 4, slots)
+            outs = []
+            for a in slots:
+                y = P.zeros((N, a.C) + a.dims, torch.float32)
+                P.unpack(a, y)
+                outs.append(y)
+            P.result = lambda: [o.clone() for o in outs] + [enc.proj_feat(z.t.float())]
+        return _run_block(self, [x], build)
 
 
 class PyMSCDecoder(nn.Module):
@@ -789,6 +892,35 @@ class PyMSCDecoder(nn.Module):
             else:
                 blk = UnetrUpBlock(chans[i], chans[i + 1])
             setattr(self, name, blk)
+
+    def forward(self, out_encoder):
+        """dose_pyfer.py:232-239: [enc1, enc2, enc3, enc4, enc5] (NCDHW fp32 CUDA) -> [dec1, dec2, dec3, dec4]."""
+        if len(out_encoder) != 5:
+            raise ValueError("PyMSCDecoder.forward expects the five encoder outputs")
+        ts = [_check_tensor(self, t) for t in out_encoder]
+        dec = self
+
+        def build(P, shapes):
+            N = shapes[0][0]
+            P.inputs = [P.zeros(sh, torch.float32) for sh in shapes]
+            cats = []
+            for l in range(4):
+                C, dims = shapes[l][1], tuple(shapes[l][2:])
+                cat = P.new_concat(N, [C, C], dims)
+                P.pack_input(P.inputs[l], cat[1])
+                cats.append(cat)
+            hidden, grid = shapes[4][1], tuple(shapes[4][2:])
+            tok = P.zeros((N, grid[0] * grid[1] * grid[2], hidden), torch.float16)       # proj_feat inverted: tokens
+            P.add_py(lambda: tok.copy_(P.inputs[4].flatten(2).transpose(1, 2)))
+            decs = _emit_unetr_decoder(P, (dec.decoder4, dec.decoder3, dec.decoder2, dec.decoder1), Tokens(tok, grid), cats,
+                                       [PREC_NET_B] * 4)
+            outs = []
+            for a in decs:
+                y = P.zeros((N, a.C) + a.dims, torch.float32)
+                P.unpack(a, y)
+                outs.append(y)
+            P.result = lambda: [o.clone() for o in outs]
+        return _run_block(self, ts, build)
 
 
 class MainSubsetModel(nn.Module):
@@ -857,7 +989,12 @@ class Model(nn.Module):
         self.conv_out_A = nn.Conv3d(list_ch_A[1], out_ch, kernel_size=1, padding=0, bias=True)
 
     def forward(self, x):
-        """x [B,9,S,S,S] fp32 CUDA -> [output_A [B,1,S^3], [dose_S, dose_S/2, dose_S/4, dose_S/8]]."""
+        """x [B,9,S,S,S] fp32 CUDA -> [output_A [B,1,S^3], [dose_S, dose_S/2, dose_S/4, dose_S/8]].
+        eval(): the inference plan.  train(): the same call as one torch.autograd node (training.autograd_forward), so
+        `loss.backward()` / `optimizer.step()` of Pyfer.training_step (train_light_pyfer.py:122-143) work unchanged."""
+        if self.training:
+            from . import training
+            return training.autograd_forward(self, x)
         return _run_single(self, x, lambda m, shape, dev: plan_dose_pyfer(m, shape, dev))
 
 
@@ -941,7 +1078,11 @@ class OARTranseg(nn.Module):
         self.proj_view_shape = list(self.feat_size) + [self.hidden_size]
 
     def forward(self, x_in):
-        """x_in [B,in_channels,S,S,S] fp32 CUDA -> logits [B,out_channels,S,S,S] fp32."""
+        """x_in [B,in_channels,S,S,S] fp32 CUDA -> logits [B,out_channels,S,S,S] fp32.  train(): one torch.autograd node
+        (training.autograd_forward_seg), so Transeg.training_step's loss.backward() works unchanged."""
+        if self.training:
+            from . import training
+            return training.autograd_forward_seg(self, x_in)
         return _run_single(self, x_in, lambda m, shape, dev: plan_oar_transeg(m, shape, dev))
 
 

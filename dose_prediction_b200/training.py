@@ -649,6 +649,13 @@ class _Trainer:
         # entirely (no decay either): keep them out of the flat optimizer range
         unused = unused_parameter_names(model)
         for n, p in model.named_parameters():
+            if getattr(self, "external", False):
+                # autograd shim: the caller owns requires_grad; the static backward list covers every used parameter of
+                # the trained sub-network, so partial freezing inside it is not built
+                if bool(trainable(n)) and not p.requires_grad and n not in unused:
+                    raise NotImplementedError(f"train-mode forward: parameter {n} is frozen; only whole-network "
+                                              "(net_A / conv_out_A) freezing is built")
+                continue
             p.requires_grad_(bool(trainable(n)))
         self.params = [(n, p) for n, p in model.named_parameters() if p.requires_grad and n not in unused]
         self.unused = [(n, p) for n, p in model.named_parameters() if p.requires_grad and n in unused]
@@ -758,6 +765,20 @@ class _Trainer:
                                f"{self.loss_scale:g} overflows fp16): rebuild the trainer with a smaller loss_scale")
         return {"completed_steps": done, "consecutive_skips": consec, "skipped_steps": total}
 
+    def _external_flat_grad(self):
+        """autograd shims: the unscaled flat gradient as a FRESH tensor (autograd may keep it as .grad); all-zero when the
+        loss-scaled fp16 backward overflowed (the optimizer step is then a no-op, like a GradScaler skip).  No
+        all-reduce here: under the shim the caller's DDP wrapper owns the gradient exchange."""
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        self.found_inf.zero_()
+        _lib.check(self.P.lib.dp_grad_check(self.flat_g.data_ptr(), self.total, self.found_inf.data_ptr(), s), "dp_grad_check")
+        flat = torch.where(self.found_inf.bool(), torch.zeros((), device=self.device), self.flat_g * (1.0 / self.loss_scale))
+        nw.invalidate_plans(self.model)          # BatchNorm running statistics moved in the forward half
+        return flat
+
+    def _param_grads(self, flat):
+        return tuple(flat[o:o + k].view(p.shape) for (n, p), (o, k) in ((np_, self.offsets[np_[0]]) for np_ in self.params))
+
     def grads(self):
         """{parameter name: unscaled fp32 gradient} (copies; for tests / inspection)."""
         out = {n: (self.flat_g[o:o + k] / self.loss_scale).view(p.shape).clone()
@@ -773,7 +794,7 @@ class DoseTrainer(_Trainer):
     buffer; state_dict() keeps working).  freeze=True as in the reference (net_A / conv_out_A get no gradient)."""
 
     def __init__(self, model, batch, size, lr=1e-4, weight_decay=1e-4, delta1=10.0, delta2=8.0, freeze=True,
-                 betas=(0.9, 0.999), eps=1e-8, loss_scale=4096.0, process_group=None, probe=None):
+                 betas=(0.9, 0.999), eps=1e-8, loss_scale=4096.0, process_group=None, probe=None, external_grads=False):
         """probe (tests only): list of four tensors R_i shaped like the dose outputs; the backward pass then starts
         from dL/dpred_i = R_i (a linear loss sum <pred_i, R_i>) instead of the GenLoss gradient, whose sign()
         makes gradient parity ill-conditioned."""
@@ -781,6 +802,10 @@ class DoseTrainer(_Trainer):
             raise RuntimeError("training path: freeze=True only (net_A frozen, train_light_pyfer.py:85-88)")
         self.batch, self.size = batch, size
         self.delta1, self.delta2, self.probe = delta1, delta2, probe
+        # external_grads (the autograd shim, autograd_forward below): the loss lives in the caller's torch code; the
+        # backward half of the launch list starts from dL/dpred_i written into self.up_grads by the autograd engine
+        self.external = bool(external_grads)
+        self.up_grads = []
         self._setup(model, lambda n: not (n.startswith("net_A") or n.startswith("conv_out_A")), lr, weight_decay, betas, eps,
                     loss_scale, process_group)
         self._set_tail(("net_B.decoder.", "net_B.dose_convertors.", "net_B.out."))
@@ -803,18 +828,22 @@ class DoseTrainer(_Trainer):
         P.training = True
         outs = _t_main_subset(P, m.net_B, [a_out, x_act])
         self.outs = outs
+        self.fwd_end = len(P.steps)              # steps[:fwd_end] = the forward pass, steps[fwd_end:] = loss + backward
         # ---- GenLoss forward
         acc = P.zeros((2 * len(outs),), torch.float64)
-        P.add_zero(acc)
         sizes = [o.shape[2] for o in outs]
-        for i, o in enumerate(outs):
-            P.add("dp_masked_l1", o.data_ptr(), P.gt.data_ptr(), N, S, sizes[i], acc[2 * i:].data_ptr(), 0, 0.0, None)
-        P.add("dp_genloss_finalize", acc.data_ptr(), len(outs), float(self.delta1), float(self.delta2), self.loss.data_ptr())
+        if not self.external:
+            P.add_zero(acc)
+            for i, o in enumerate(outs):
+                P.add("dp_masked_l1", o.data_ptr(), P.gt.data_ptr(), N, S, sizes[i], acc[2 * i:].data_ptr(), 0, 0.0, None)
+            P.add("dp_genloss_finalize", acc.data_ptr(), len(outs), float(self.delta1), float(self.delta2), self.loss.data_ptr())
         # ---- backward
         for i, o in enumerate(outs):
             g = P.zeros(tuple(o.shape), torch.float32)
             coef = self.loss_scale * (self.delta1 if i == 0 else self.delta2 / (len(outs) - 1))
-            if self.probe is not None:
+            if self.external:
+                self.up_grads.append(g)
+            elif self.probe is not None:
                 r = (self.probe[i].to(self.device, torch.float32) * self.loss_scale).contiguous()
                 P.add_py(lambda g=g, r=r: g.copy_(r))
             else:
@@ -837,6 +866,102 @@ class DoseTrainer(_Trainer):
     def outputs(self):
         return [self.out_A.clone(), [o.clone() for o in self.outs]]
 
+    # ---- the two halves of the launch list, for the autograd shim
+    def run_forward(self, x):
+        self.P.x_in.copy_(x.to(torch.float32), non_blocking=True)
+        self.P.refresh_weights()
+        self.P.run_range(0, self.fwd_end, True)
+        if self._bn_counters:
+            torch._foreach_add_(self._bn_counters, 1)
+
+    def run_backward(self, grads):
+        """grads: dL/dpred_i (or None) for the four dose outputs -> flat fp32 gradient of the trainable parameters
+        (a fresh buffer, unscaled; all-zero when the loss-scaled fp16 backward overflowed: the step is then a no-op)"""
+        for g, up in zip(grads, self.up_grads):
+            if g is None:
+                up.zero_()
+            else:
+                torch.mul(g.to(self.device, torch.float32), self.loss_scale, out=up)
+        self.P.run_range(self.fwd_end, None, False)
+        return self._external_flat_grad()
+
+
+class _DoseTrainFunction(torch.autograd.Function):
+    """train-mode `model(x)` as ONE autograd node: forward = the forward half of the static launch list, backward = the
+    backward half, started from whatever dL/dpred the caller's loss (GenLoss, train_light_pyfer.py:131) produced."""
+
+    @staticmethod
+    def forward(ctx, tr, x, *params):
+        tr.run_forward(x)
+        ctx.tr = tr
+        out_A = tr.out_A.clone()
+        ctx.mark_non_differentiable(out_A)
+        return (out_A,) + tuple(o.clone() for o in tr.outs)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_a, *g_outs):
+        tr = ctx.tr
+        return (None, None) + tr._param_grads(tr.run_backward(list(g_outs)))
+
+
+class _SegTrainFunction(torch.autograd.Function):
+    """train-mode OAR-TRANSEG `model(x)` as one autograd node (Transeg.training_step, train_light_transeg.py:184-198)."""
+
+    @staticmethod
+    def forward(ctx, tr, x, *params):
+        tr.run_forward(x)
+        ctx.tr = tr
+        return tr.logits()
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        tr = ctx.tr
+        return (None, None) + tr._param_grads(tr.run_backward(g))
+
+
+def autograd_forward_seg(model, x):
+    """networks.OARTranseg / TRANSEG .forward in train mode: logits wired into torch autograd."""
+    if not (x.is_cuda and x.dim() == 5):
+        raise RuntimeError("expected a CUDA tensor [B,C,D,H,W]; dose_prediction_b200 has no CPU fallback")
+    if x.shape[1] != model.in_ch:
+        raise ValueError(f"expected {model.in_ch} input channels, got {x.shape[1]}")
+    flags = tuple(p.requires_grad for p in model.parameters())
+    cache = model.__dict__.setdefault("_train_ctx", {})
+    key = (tuple(x.shape), x.device.index)
+    tr = cache.get(key)
+    if tr is None or tr._flags != flags:
+        cache.clear()
+        tr = SegTrainer(model, x.shape[0], x.shape[2], external_grads=True)
+        tr._flags = flags
+        cache[key] = tr
+    return _SegTrainFunction.apply(tr, x.detach(), *[p for _, p in tr.params])
+
+
+def autograd_forward(model, x):
+    """networks.Model.forward in train mode (Pyfer.training_step, train_light_pyfer.py:122-143: `output = self(input_)`,
+    then Lightning's loss.backward() and optimizer.step()): returns [output_A, [dose_S, .., dose_S/8]] wired into torch
+    autograd; .grad lands on the module's own parameters, any torch / bitsandbytes optimizer can step them."""
+    if not (x.is_cuda and x.dim() == 5):
+        raise RuntimeError("expected a CUDA tensor [B,C,D,H,W]; dose_prediction_b200 has no CPU fallback")
+    if x.shape[1] != model.in_ch:
+        raise ValueError(f"expected {model.in_ch} input channels, got {x.shape[1]}")
+    flags = tuple(p.requires_grad for p in model.parameters())
+    if any(p.requires_grad for n, p in model.named_parameters() if n.startswith("net_A") or n.startswith("conv_out_A")):
+        raise NotImplementedError("train-mode forward: net_A / conv_out_A must be frozen (requires_grad=False), as "
+                                  "Pyfer(freeze=True) does (train_light_pyfer.py:85-88); freeze=False is not built")
+    cache = model.__dict__.setdefault("_train_ctx", {})
+    key = (tuple(x.shape), x.device.index)
+    tr = cache.get(key)
+    if tr is None or tr._flags != flags:
+        cache.clear()                              # one resident training plan per module
+        tr = DoseTrainer(model, x.shape[0], x.shape[2], external_grads=True)
+        tr._flags = tuple(p.requires_grad for p in model.parameters())
+        cache[key] = tr
+    outs = _DoseTrainFunction.apply(tr, x.detach(), *[p for _, p in tr.params])
+    return [outs[0], list(outs[1:])]
+
 
 class SegTrainer(_Trainer):
     """One OAR-TRANSEG training step per call (`Transeg.training_step` + `configure_optimizers`,
@@ -845,8 +970,9 @@ class SegTrainer(_Trainer):
     model: dose_prediction_b200.networks.OARTranseg (Models/, mode_model=0) or networks.TRANSEG (OldModels/, mode_model=1)."""
 
     def __init__(self, model, batch, size, lr=1e-4, weight_decay=1e-5, betas=(0.9, 0.999), eps=1e-8, loss_scale=4096.0,
-                 process_group=None, probe=None):
+                 process_group=None, probe=None, external_grads=False):
         self.batch, self.size, self.probe = batch, size, probe
+        self.external = bool(external_grads)
         self._setup(model, lambda n: True, lr, weight_decay, betas, eps, loss_scale, process_group)
         self._set_tail(("decoder5.", "decoder4.", "decoder3.", "decoder2.", "out."))
         self._emit()
@@ -867,12 +993,17 @@ class SegTrainer(_Trainer):
                         (m.decoder5, m.decoder4, m.decoder3, m.decoder2), [x_act], (3, 6, 9))
         raw = P.t_pointwise([decs[0]], m.out.conv.conv)          # logits, c8 fp32 (C classes in block 0)
         self.logits_raw = raw
+        self.fwd_end = len(P.steps)
         acc = P.zeros((N * 24 + 2,), torch.float64)
-        P.add_zero(acc)
-        P.add("dp_dice_ce", raw.t.data_ptr(), raw.cb_total, P.label.data_ptr(), N, C, vox, acc.data_ptr(), 0, 0.0, None, 0)
-        P.add("dp_dice_ce_finalize", acc.data_ptr(), N, C, vox, self.loss.data_ptr())
+        if not self.external:
+            P.add_zero(acc)
+            P.add("dp_dice_ce", raw.t.data_ptr(), raw.cb_total, P.label.data_ptr(), N, C, vox, acc.data_ptr(), 0, 0.0, None, 0)
+            P.add("dp_dice_ce_finalize", acc.data_ptr(), N, C, vox, self.loss.data_ptr())
         g16 = P.new_act(N, C, dims)
-        if self.probe is not None:
+        if self.external:
+            self.up_grad = P.zeros((N, C) + dims, torch.float32)          # loss_scale * dL/dlogits, filled by autograd
+            P.pack_input(self.up_grad, g16)
+        elif self.probe is not None:
             r = (self.probe.to(self.device, torch.float32) * self.loss_scale).contiguous()
             P.keep.append(r)
             P.pack_input(r, g16)
@@ -891,6 +1022,18 @@ class SegTrainer(_Trainer):
         loss = self.forward_backward(ct, label)
         self._optimizer_step()
         return loss
+
+    def run_forward(self, ct):
+        self.P.x_in.copy_(ct.to(torch.float32), non_blocking=True)
+        self.P.refresh_weights()
+        self.P.run_range(0, self.fwd_end, True)
+        if self._bn_counters:
+            torch._foreach_add_(self._bn_counters, 1)
+
+    def run_backward(self, g):
+        torch.mul(g.to(self.device, torch.float32), self.loss_scale, out=self.up_grad)
+        self.P.run_range(self.fwd_end, None, False)
+        return self._external_flat_grad()
 
     def logits(self):
         """[B,C,S,S,S] fp32 logits of the last forward (copy)."""

@@ -43,8 +43,12 @@ def test_no_cpu_fallback():
     m = networks.OARTranseg(1, 8, 32, pos_embed="perceptron").eval()
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m(torch.zeros(1, 1, 32, 32, 32))
-    with pytest.raises(RuntimeError, match="eval"):
+    # train mode is the autograd shim (training.autograd_forward_seg): CUDA only as well
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
         networks.OARTranseg(1, 8, 32, pos_embed="perceptron").train()(torch.zeros(1, 1, 32, 32, 32))
+    # sub-networks keep an inference-only forward
+    with pytest.raises(RuntimeError, match="eval"):
+        networks.BaseUNet(9, [-1, 16, 32, 64, 128, 256]).train()(torch.zeros(1, 9, 32, 32, 32))
 
 
 @pytest.mark.skipif(not ref_loader.available(), reason="reference tree only exists in the build container")
@@ -85,3 +89,27 @@ def test_variant_constructors_match_live_reference_layout():
     ref3 = ref_loader.build_seg(32, pos_embed="conv")
     ours3 = networks.OARTranseg(1, 8, (32, 32, 32), pos_embed="conv")
     assert _manifest_of(ours3) == _manifest_of(ref3)
+
+
+def test_reference_named_modules_export_the_reference_class_names():
+    """a user of the reference swaps the import path, not the names."""
+    from dose_prediction_b200 import base_blocks, c3d, dose_pyfer, networks, oar_transeg
+    assert dose_pyfer.Model is networks.Model and dose_pyfer.create_pretrained_unet is networks.create_pretrained_unet
+    assert {"ViTEncoder", "PyMSCDecoder", "MainSubsetModel"} <= set(dose_pyfer.__all__)
+    assert oar_transeg.Model is networks.OARTranseg and oar_transeg.TRANSEG is networks.TRANSEG
+    assert c3d.BaseUNet is networks.BaseUNet and base_blocks.ModifiedUnetrUpBlock is networks.ModifiedUnetrUpBlock
+    import inspect
+    for cls, params in ((base_blocks.ModifiedUnetrUpBlock, ["inp", "skip"]), (dose_pyfer.ViTEncoder, ["x_in"]),
+                        (dose_pyfer.PyMSCDecoder, ["out_encoder"]), (oar_transeg.Model, ["x_in"]), (dose_pyfer.Model, ["x"])):
+        assert list(inspect.signature(cls.forward).parameters)[1:] == params, cls
+
+
+def test_cpu_tensors_and_train_mode_sub_blocks_fail_loudly():
+    import pytest
+    import torch
+    from dose_prediction_b200 import networks
+    blk = networks.ModifiedUnetrUpBlock(3, 32, 16, 2)
+    with pytest.raises(RuntimeError):
+        blk(torch.zeros(1, 32, 4, 4, 4), torch.zeros(1, 16, 8, 8, 8))          # train mode
+    with pytest.raises(RuntimeError):
+        blk.eval()(torch.zeros(1, 32, 4, 4, 4), torch.zeros(1, 16, 8, 8, 8))   # CPU tensor: no fallback
