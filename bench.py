@@ -343,6 +343,11 @@ def measure_train(B, S, steps, warmup, dev, world, rank, local, detail=False):
         tr.step(x_d, gt_d)
     torch.cuda.synchronize(dev)
     tr.check_health()
+    graphed = os.environ.get("DP_TRAIN_GRAPH", "1") != "0"
+    if graphed:
+        tr.capture()                     # the step as CUDA graphs (collectives stay eager NCCL calls between the segments)
+        tr.step(x_d, gt_d)
+        torch.cuda.synchronize(dev)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -384,7 +389,7 @@ def measure_train(B, S, steps, warmup, dev, world, rank, local, detail=False):
                                   f"{S}^3, batch {B} per GPU (BASELINE.json configs[3])", "batch_per_gpu": B, "size": S,
                       "parallelism": f"data-parallel x{world}, one NCCL all-reduce of the flat fp32 gradient buffer "
                                      f"({tr.total} elements)" if world > 1 else "single GPU",
-                      "loss_scale": tr.loss_scale, "trainable_parameters": tr.total,
+                      "loss_scale": tr.loss_scale, "trainable_parameters": tr.total, "cuda_graph": graphed,
                       "l2": f"no flush: per-step working set {P.bytes_alloc / 2**30:.1f} GiB >> 126 MB L2"}}
     peaks = _peaks()
     out["frac_of_tensor_peak"] = out["achieved_tflops_per_gpu"] / peaks["tflops"]

@@ -202,9 +202,11 @@ class Plan:
     def kernels_per_step(self):
         return sum(self.step_kernels)
 
-    def add_py(self, fn):
-        """host-side plumbing (parameter-layout conversion, collectives) at this point of every replay."""
-        self.steps.append((None, (fn,), "py"))
+    def add_py(self, fn, capturable=True):
+        """host-side plumbing at this point of every replay.  capturable: the function only enqueues device work on the
+        current stream (torch ops), so it may be recorded into a CUDA graph; False for collectives / anything that must
+        run on the host every step (such a step splits the launch list into separately captured graph segments)."""
+        self.steps.append((None, (fn,), "py" if capturable else "py_host"))
         self.step_flops.append(0.0)
         self.step_kernels.append(0)
 
@@ -260,7 +262,7 @@ class Plan:
         n = 0
         for fn, args, name in (self.steps if (start == 0 and stop is None) else self.steps[start:stop]):
             if fn is None:
-                if name == "py":
+                if name in ("py", "py_host"):
                     args[0]()
                 else:
                     args[0].zero_()
@@ -288,7 +290,7 @@ class Plan:
         evs = []
         for fn, args, name in self.steps:
             if fn is None:
-                args[0]() if name == "py" else args[0].zero_()
+                args[0]() if name in ("py", "py_host") else args[0].zero_()
                 continue
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
@@ -326,7 +328,7 @@ class Plan:
             evs = []
             for fn, args, name in self.steps:
                 if fn is None:
-                    args[0]() if name == "py" else args[0].zero_()
+                    args[0]() if name in ("py", "py_host") else args[0].zero_()
                     continue
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(stream)

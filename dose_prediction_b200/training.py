@@ -694,7 +694,7 @@ class _Trainer:
         for entry in reversed(P.tape):
             if isinstance(entry, tuple) and entry[0] == "mark":
                 if entry[1] == "decoders" and self.tail_off is not None:
-                    P.add_py(self._start_tail_allreduce)
+                    P.add_py(self._start_tail_allreduce, capturable=False)
                 continue
             entry()
             for acc64, g, n in P.finalizers[done:]:
@@ -720,12 +720,53 @@ class _Trainer:
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
             self._tail_work = dist.all_reduce(self.flat_g[self.tail_off:], group=self.group, async_op=True)
 
+    # ------------------------------------------------------------------ CUDA-graph replay of the whole step
+    graphs = None
+
+    def capture(self):
+        """Record the training step into CUDA graphs: {weight re-packing + launch list up to the first host-side step},
+        {the rest of the launch list}, {gradient check + AdamW}.  The only host-side steps are the collectives of the
+        data-parallel gradient exchange (they stay eager NCCL calls between the graph segments), so on one GPU the step is
+        three graph launches instead of ~950 kernel launches.  Call after at least one eager step (warm-up)."""
+        P = self.P
+        bounds = [i for i, (fn, _, name) in enumerate(P.steps) if fn is None and name == "py_host"]
+        ranges, a = [], 0
+        for b in bounds:
+            ranges.append((a, b))
+            a = b + 1
+        ranges.append((a, len(P.steps)))
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize(self.device)
+            segs = []
+            for i, (a, b) in enumerate(ranges):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    if i == 0:
+                        P._refresh_weights()
+                    P._run(a, b, zero_stats=(i == 0))
+                    if i == len(ranges) - 1 and self._bn_counters:
+                        torch._foreach_add_(self._bn_counters, 1)
+                segs.append(g)
+            opt = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(opt):
+                self._optimizer_launches()
+            self.graphs = (segs, [P.steps[b][1][0] for b in bounds], opt)
+        return self
+
     def _run(self):
         P = self.P
-        P.refresh_weights()
-        P.run()
-        if self._bn_counters:
-            torch._foreach_add_(self._bn_counters, 1)
+        if self.graphs is not None:
+            segs, hosts, _ = self.graphs
+            with torch.cuda.device(self.device):
+                for i, g in enumerate(segs):
+                    g.replay()
+                    if i < len(hosts):
+                        hosts[i]()
+        else:
+            P.refresh_weights()
+            P.run()
+            if self._bn_counters:
+                torch._foreach_add_(self._bn_counters, 1)
         if self._tail_work is not None:            # bucket 2 (decoders + heads) has been in flight since the mark
             import torch.distributed as dist
             dist.all_reduce(self.flat_g[:self.tail_off], group=self.group)
@@ -738,6 +779,18 @@ class _Trainer:
 
     def _optimizer_step(self):
         self.step_count += 1
+        if self.graphs is not None:
+            with torch.cuda.device(self.device):
+                self.graphs[2].replay()
+        else:
+            self._optimizer_launches()
+        # the parameters (and BatchNorm running statistics) just changed through raw pointers: no tensor version
+        # counter moved, so tell every cached inference plan of this model that its packed weights are stale
+        nw.invalidate_plans(self.model)
+        if self.step_count % self.HEALTH_EVERY == 0:
+            self.check_health()
+
+    def _optimizer_launches(self):
         s = torch.cuda.current_stream(self.device).cuda_stream
         lib = self.P.lib
         self.found_inf.zero_()
@@ -746,11 +799,6 @@ class _Trainer:
                                     self.flat_v.data_ptr(), self.total, self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
                                     1.0 / self.loss_scale, self.found_inf.data_ptr(), self.opt_state.data_ptr(), s),
                    "dp_adamw_dev")
-        # the parameters (and BatchNorm running statistics) just changed through raw pointers: no tensor version
-        # counter moved, so tell every cached inference plan of this model that its packed weights are stale
-        nw.invalidate_plans(self.model)
-        if self.step_count % self.HEALTH_EVERY == 0:
-            self.check_health()
 
     HEALTH_EVERY = 64
     MAX_CONSECUTIVE_SKIPS = 16

@@ -389,3 +389,28 @@ def test_sub_block_forwards_match_the_oracle():
         want = torch_ref.modified_unetr_up_block(dsd, pre, inp.cpu(), skip.cpu(), "mish")
     assert tuple(got.shape) == (1, 16, 16, 16, 16)
     assert _rel(got, want) < 1e-2
+
+
+def test_captured_training_step_replays_the_eager_schedule():
+    """DoseTrainer.capture(): the step as CUDA graphs must reproduce the eager launch list bit for bit."""
+    from dose_prediction_b200 import synth
+    from dose_prediction_b200.training import DoseTrainer
+    S, B = 32, 2
+    vol = synth.make_batch(B, S, seed=1234)
+    x, gt = vol["dose_input"].to(DEV), vol["gt"].to(DEV)
+    losses = {}
+    for mode in ("eager", "graph"):
+        model, _ = _train_model(S)
+        tr = DoseTrainer(model, B, S, lr=1e-3, weight_decay=1e-4)
+        out = [float(tr.step(x, gt))]
+        if mode == "graph":
+            tr.capture()
+        out += [float(tr.step(x, gt)) for _ in range(4)]
+        torch.cuda.synchronize()
+        tr.check_health()
+        losses[mode] = out
+        final = {k: v.clone() for k, v in model.state_dict().items()} if mode == "eager" else final
+        if mode == "graph":
+            for k, v in model.state_dict().items():
+                assert torch.equal(v, final[k]), k
+    assert losses["eager"] == losses["graph"], losses
