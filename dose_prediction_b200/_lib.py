@@ -25,6 +25,8 @@ _SIGNATURES = {
     "dp_pack_ncdhw": [P, I, I, L, P, P, I, I, P],
     "dp_unpack_c8": [P, P, I, I, I, I, L, P, P],
     "dp_norm_act": [P, P, P, I, I, P, P, P, I, P, P, P, P, I, I, I, P, P, I, I, P, I, I, L, P, P, I, I, I, I, I, P],
+    "dp_conv3d_c1": [P, P, P, I, I, I, I, P, I, P, P, P],
+    "dp_norm_act_resx": [P, I, P, P, P, P, I, P, P, I, I, I, I, L, P],
     "dp_norm_act_head": [P, I, P, P, P, I, P, P, I, I, P, P, I, P, I, I, L, P],
     "dp_pointwise_conv": [I, P, P, P, P, P, P, P, P, P, P, I, I, L, P, P, P, I, I, P, P, I, P],
     "dp_pointwise_tc": [I, P, P, P, P, P, P, P, P, P, P, I, I, L, P, P, P, I, I, P, P, P],

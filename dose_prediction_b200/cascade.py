@@ -47,7 +47,7 @@ class CascadePlan:
         if sw_roi is None:
             seg_x = P.new_act(batch, seg_model.in_ch, dims, lo=True)
             P.pack_input(self.ct, seg_x)
-            self.logits = emit_oar_transeg(P, seg_model, seg_x)
+            self.logits = emit_oar_transeg(P, seg_model, seg_x, x_planar=self.ct)
         else:
             self.logits = self._emit_sliding_window(P, seg_model, batch, size, sw_roi, sw_batch, overlap)
         a_out, dose_x = P.new_concat(batch, [dose_model.net_A.list_ch[1], dose_model.in_ch], dims, lo=True)

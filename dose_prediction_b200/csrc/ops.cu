@@ -182,6 +182,10 @@ struct NormActParams {
   // optional second copy in space-to-depth layout: channel block (parity*ncb + cb) of a half-resolution
   // tensor, parity = (d&1)*4 + (h&1)*2 + (w&1); feeds the stride-2 convs as sparse stride-1 convs
   __half* s2d_hi; __half* s2d_lo; int s2d_cb_total, s2d_cb_off, D, H, W;
+  // closed-form residual branch norm3(conv3(x)) of a res block whose input x has ONE channel (seg encoder1): conv3 is
+  // w_c * x, so its InstanceNorm is w_c (x - mean_x) / sqrt(w_c^2 var_x + eps): an affine map of x per output channel,
+  // evaluated here from the planar fp32 input instead of materialising conv3's 16-channel output
+  const float* res_x; const float* res_w; const double* res_xstats;
 };
 
 constexpr int NA_IT = 4;      // voxel chunks per block: amortises the statistics prologue
@@ -204,13 +208,22 @@ __global__ void __launch_bounds__(256, 4) norm_act_kernel(const NormActParams p)
     if (which == 0) {
       s_gamma[j] = (p.gamma && c < p.C) ? p.gamma[c] : 1.f;
       s_beta[j] = (p.gamma && c < p.C) ? p.beta[c] : 0.f;
+    } else if (p.res_x != nullptr) {
+      // residual = a_c * x + b_c, stored as (x - mean_x) * a_c in the (mean, rstd) slots
+      const double sx = p.res_xstats[n * 2], sxx = p.res_xstats[n * 2 + 1];
+      const double mx = sx * inv;
+      double vx = sxx * inv - mx * mx;
+      if (vx < 0.0) vx = 0.0;
+      const float wc = c < p.C ? p.res_w[c] : 0.f;
+      s_mean[1][j] = static_cast<float>(mx);
+      s_rstd[1][j] = wc * rsqrtf(wc * wc * static_cast<float>(vx) + 1e-5f);
     }
   }
   __syncthreads();
   float mean0[8], rstd0[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { mean0[j] = s_mean[0][j]; rstd0[j] = s_rstd[0][j]; }
-  const bool has_res = p.res_hi || p.res_raw;
+  const bool has_res = p.res_hi || p.res_raw || p.res_x;
   const bool affine = p.gamma != nullptr;
   const bool want_stats = p.stats_out != nullptr;
   float a1[8], a2[8];
@@ -234,7 +247,11 @@ __global__ void __launch_bounds__(256, 4) norm_act_kernel(const NormActParams p)
     if (has_res) {
       float r8[8];
       const size_t r_off = ((static_cast<size_t>(n) * p.res_cb_total + p.res_cb_off + cb) * p.vox + v) * 8;
-      if (p.res_raw) load8f(p.res_raw, r_off, r8); else load8(p.res_hi, p.res_lo, r_off, r8);
+      if (p.res_x) {
+        const float xv = __ldg(&p.res_x[static_cast<size_t>(n) * p.vox + v]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r8[j] = xv;
+      } else if (p.res_raw) load8f(p.res_raw, r_off, r8); else load8(p.res_hi, p.res_lo, r_off, r8);
 #pragma unroll
       for (int j = 0; j < 8; ++j) y[j] += (r8[j] - s_mean[1][j]) * s_rstd[1][j];
       act8(y, p.act_after_res);
@@ -1113,6 +1130,22 @@ extern "C" int dp_norm_act(const float* raw_f32, const void* raw_hi, const void*
   p.out_cb_off = out_cb_off; p.stats_out = stats_out; p.C = C; p.ncb = (C + 7) / 8; p.vox = vox; p.inv_vox = 1.0 / static_cast<double>(vox);
   p.s2d_hi = static_cast<__half*>(s2d_hi); p.s2d_lo = static_cast<__half*>(s2d_lo); p.s2d_cb_total = s2d_cb_total;
   p.s2d_cb_off = s2d_cb_off; p.D = D; p.H = H > 0 ? H : 1; p.W = W > 0 ? W : 1;
+  dim3 grid(blocks_for(vox, 256 * NA_IT), N * p.ncb);
+  norm_act_kernel<<<grid, 256, 0, stream>>>(p);
+  DP_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dp_norm_act_resx(const float* raw_f32, int in_cb_total, const double* stats, const float* res_x, const float* res_w,
+                                const double* res_xstats, int act_after_res, void* out_hi, void* out_lo, int out_cb_total,
+                                int out_cb_off, int N, int C, long long vox, cudaStream_t stream) {
+  DP_REQUIRE(raw_f32 && stats && res_x && res_w && res_xstats && out_hi, "dp_norm_act_resx: missing operand");
+  NormActParams p{};
+  p.raw_f32 = raw_f32; p.in_cb_total = in_cb_total; p.stats = stats; p.act = ACT_NONE;
+  p.res_x = res_x; p.res_w = res_w; p.res_xstats = res_xstats; p.act_after_res = act_after_res;
+  p.out_hi = static_cast<__half*>(out_hi); p.out_lo = static_cast<__half*>(out_lo); p.out_cb_total = out_cb_total;
+  p.out_cb_off = out_cb_off; p.C = C; p.ncb = (C + 7) / 8; p.vox = vox; p.inv_vox = 1.0 / static_cast<double>(vox);
+  p.H = 1; p.W = 1;
   dim3 grid(blocks_for(vox, 256 * NA_IT), N * p.ncb);
   norm_act_kernel<<<grid, 256, 0, stream>>>(p);
   DP_CHECK(cudaGetLastError());

@@ -23,6 +23,7 @@ ACT_ID = {None: ACT_NONE, "none": ACT_NONE, "relu": ACT_RELU, "lrelu": ACT_LRELU
 STATS_DOUBLES = 1 << 20
 STACK_TILES = int(os.environ.get("DP_STACK_TILES", "0"))
 FOLD_P3 = os.environ.get("DP_FOLD_P3", "1") != "0"
+CONV_C1 = os.environ.get("DP_CONV_C1", "1") != "0"              # bring-up switch: one-channel 3^3 conv + closed-form residual (seg encoder1)
 POINTWISE_TCK = os.environ.get("DP_POINTWISE_TCK", "1") != "0"  # bring-up switch: 1^3 convs on tcgen05 with normalise-on-load
 FUSE_HEADS = os.environ.get("DP_FUSE_HEADS", "1") != "0"         # bring-up switch: 1^3 heads folded into the producing norm_act
 FOLD_TC_MAX = int(os.environ.get("DP_FOLD_TC_MAX", "32"))        # plain tcgen05 conv: fold [W_hi | W_lo] into N up to this C_out
@@ -555,6 +556,34 @@ class Plan:
                  s2d.hi_ptr if s2d is not None else None, s2d.lo_ptr if s2d is not None else None,
                  s2d.cb_total if s2d is not None else 0, s2d.cb_off if s2d is not None else 0,
                  *(tuple(2 * d for d in s2d.dims) if s2d is not None else (0, 0, 0)))
+
+    def conv3_c1(self, x_planar, weight, bias, out_raw):
+        """3^3 conv of a one-channel planar fp32 volume [N,1,D,H,W] -> Raw (16 channels), exact fp32 (csrc/conv_small.cu).
+        Returns the [N][2] fp64 {sum x, sum x^2} statistics of the input (re-zeroed every replay)."""
+        N, _, D, H, W = x_planar.shape
+        assert weight.shape[0] == 16 and weight.shape[1] == 1 and weight.shape[2] == 3
+        wh = weight.detach().to("cpu", torch.float32).contiguous()
+        wa = (ctypes.c_float * wh.numel())(*wh.flatten().tolist())
+        ba = None
+        if bias is not None:
+            ba = (ctypes.c_float * 16)(*bias.detach().to("cpu", torch.float32).tolist())
+        xstats = self.new_stats(N, 1)
+        self.keep.append((wa, ba))
+        self.count_flops("dp_conv3d_c1", 2.0 * N * D * H * W * 27 * 16)
+        self.count_bytes("dp_conv3d_c1", N * D * H * W * (4 + 64))
+        self.add("dp_conv3d_c1", x_planar.data_ptr(), ctypes.cast(wa, ctypes.c_void_p),
+                 ctypes.cast(ba, ctypes.c_void_p) if ba is not None else None, N, D, H, W, out_raw.t.data_ptr(), out_raw.cb_total,
+                 out_raw.stats.data_ptr(), xstats.data_ptr())
+        return xstats
+
+    def norm_act_resx(self, src, out, x_planar, w1, xstats, act_after_res):
+        """out = act(IN(src) + norm3(conv3(x))) for a one-channel x: the residual branch in closed form (dp_norm_act_resx)."""
+        N, vox = src.t.shape[0], src.t.shape[2] * src.t.shape[3] * src.t.shape[4]
+        w = self.dev(w1.reshape(-1))
+        cpad = ceil_div(src.C, 8) * 8
+        self.count_bytes("dp_norm_act", N * vox * (cpad * (4 + (4 if out.lo_off is not None else 2)) + 4))
+        self.add("dp_norm_act_resx", src.t.data_ptr(), src.cb_total, src.stats.data_ptr(), x_planar.data_ptr(), w.data_ptr(),
+                 xstats.data_ptr(), ACT_ID[act_after_res], out.hi_ptr, out.lo_ptr, out.cb_total, out.cb_off, N, src.C, vox)
 
     def head(self, a, weight, bias, out_planar):
         """1x1x1 conv C -> head_co (+bias) of activation `a` into NCDHW fp32 (dose heads, conv_out_A, seg logits).

@@ -527,18 +527,30 @@ def _emit_vit(P, vit, parts, N, S, taps):
     return Tokens(z, grid), hs
 
 
-def _emit_res_block(P, blk, parts, out, prec):
-    """monai UnetResBlock.forward (k3 s1, InstanceNorm no affine, LeakyReLU 0.01)."""
+def _emit_res_block(P, blk, parts, out, prec, x_planar=None):
+    """monai UnetResBlock.forward (k3 s1, InstanceNorm no affine, LeakyReLU 0.01).
+    x_planar: the block's input as a planar fp32 tensor when it has ONE channel (seg encoder1): conv1 then runs as an exact
+    fp32 direct conv and the residual branch norm3(conv3(x)) is evaluated in closed form (engine.conv3_c1 / norm_act_resx)."""
     N, dims = parts[0].N, parts[0].dims
     Co = blk.conv1.conv.weight.shape[0]
     one, zero = P.affine(Co)
     raw1 = P.get_raw(N, Co, dims)
-    P.conv_tc(parts, blk.conv1.conv.weight, 3, 1, prec.conv3, one, zero, False, out_raw=raw1)
+    from .engine import CONV_C1
+    c1 = (x_planar is not None and CONV_C1 and Co == 16 and len(parts) == 1 and parts[0].C == 1 and blk.downsample
+          and not P.training)
+    if c1:
+        xstats = P.conv3_c1(x_planar, blk.conv1.conv.weight, None, raw1)
+    else:
+        P.conv_tc(parts, blk.conv1.conv.weight, 3, 1, prec.conv3, one, zero, False, out_raw=raw1)
     a1 = P.new_act(N, Co, dims, lo=prec.lo)
     P.norm_act(raw1, a1, act="lrelu")
     P.release(raw1)
     raw2 = P.get_raw(N, Co, dims)
     P.conv_tc([a1], blk.conv2.conv.weight, 3, 1, prec.conv3, one, zero, False, out_raw=raw2)
+    if c1:
+        P.norm_act_resx(raw2, out, x_planar, blk.conv3.conv.weight, xstats, "lrelu")
+        P.release(raw2)
+        return
     if blk.downsample:
         raw3 = P.get_raw(N, Co, dims)
         P.pointwise([(a, None, None) for a in parts], blk.conv3.conv.weight, None, out_raw=raw3)
@@ -671,7 +683,7 @@ def _emit_up_block(P, blk, inp, skip_slot_pair, out, prec):
         _emit_conv_3_1(P, cov, skip_slot_pair, out, prec)
 
 
-def _emit_unetr(P, vit, enc_blocks, dec_blocks, parts, taps, prec, prec_deep=None):
+def _emit_unetr(P, vit, enc_blocks, dec_blocks, parts, taps, prec, prec_deep=None, x_planar=None):
     """Shared UNETR-shaped body of MainSubsetModel.forward (dose_pyfer.py:311-319) and oar_transeg Model.forward
     (oar_transeg.py:171-185).  enc_blocks = (res-block, prup2, prup3, prup4); dec_blocks from coarse to fine.
     prec_deep: precision recipe of the two coarsest levels (1/4 and 1/8 resolution), default = prec."""
@@ -680,16 +692,16 @@ def _emit_unetr(P, vit, enc_blocks, dec_blocks, parts, taps, prec, prec_deep=Non
     precs = [prec, prec, prec_deep or prec, prec_deep or prec]          # per level, fine -> coarse
     sizes = [dims, tuple(d // 2 for d in dims), tuple(d // 4 for d in dims), tuple(d // 8 for d in dims)]
     cats = [P.new_concat(N, [fs << i, fs << i], sizes[i], lo=precs[i].lo) for i in range(4)]     # [deconv out | skip]
-    z = _emit_unetr_encoder(P, vit, enc_blocks, parts, taps, precs, [c[1] for c in cats])
+    z = _emit_unetr_encoder(P, vit, enc_blocks, parts, taps, precs, [c[1] for c in cats], x_planar=x_planar)
     return _emit_unetr_decoder(P, dec_blocks, z, cats, precs)
 
 
-def _emit_unetr_encoder(P, vit, enc_blocks, parts, taps, precs, skip_slots):
+def _emit_unetr_encoder(P, vit, enc_blocks, parts, taps, precs, skip_slots, x_planar=None):
     """ViTEncoder.forward (dose_pyfer.py:124-144) / the encoder half of oar_transeg Model.forward: ViT, then the four conv
     skips written into `skip_slots` (usually the second halves of the decoder's concat buffers); returns the z12 tokens."""
     N, dims = parts[0].N, parts[0].dims
     z, hs = _emit_vit(P, vit, parts, N, dims, taps)
-    _emit_res_block(P, enc_blocks[0].layer, parts, skip_slots[0], precs[0])
+    _emit_res_block(P, enc_blocks[0].layer, parts, skip_slots[0], precs[0], x_planar=x_planar)
     _emit_pr_up(P, enc_blocks[1], hs[taps[0]], skip_slots[1], precs[1])
     _emit_pr_up(P, enc_blocks[2], hs[taps[1]], skip_slots[2], precs[2])
     _emit_pr_up(P, enc_blocks[3], hs[taps[2]], skip_slots[3], precs[3])
@@ -1098,10 +1110,12 @@ class TRANSEG(OARTranseg):
                          norm_name, conv_block, res_block, dropout_rate, spatial_dims, _old_blocks=True)
 
 
-def emit_oar_transeg(P, model, x_act):
+def emit_oar_transeg(P, model, x_act, x_planar=None):
+    """x_planar: the same input as a planar fp32 [N,1,D,H,W] tensor, when the caller has one (lets the one-channel
+    encoder1 convs run in exact fp32 straight from it)."""
     decs = _emit_unetr(P, model.vit, (model.encoder1, model.encoder2, model.encoder3, model.encoder4),
                        (model.decoder5, model.decoder4, model.decoder3, model.decoder2), [x_act], (3, 6, 9), PREC_SEG,
-                       prec_deep=PREC_SEG_DEEP)
+                       prec_deep=PREC_SEG_DEEP, x_planar=x_planar if model.in_ch == 1 else None)
     d = decs[0]
     logits = P.zeros((d.N, model.out_channels) + d.dims, torch.float32)
     P.head(d, model.out.conv.conv.weight, model.out.conv.conv.bias, logits)
@@ -1114,7 +1128,7 @@ def plan_oar_transeg(model, shape, device):
     P.x_in = P.zeros(tuple(shape), torch.float32)
     x_act = P.new_act(N, model.in_ch, dims, lo=True)
     P.pack_input(P.x_in, x_act)
-    logits = emit_oar_transeg(P, model, x_act)
+    logits = emit_oar_transeg(P, model, x_act, x_planar=P.x_in)
     P.outputs = logits
     P.result = lambda: logits.clone()
     return P

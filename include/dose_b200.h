@@ -121,6 +121,20 @@ int dp_norm_act(const float* raw_f32, const void* raw_hi, const void* raw_lo, in
                 int N, int C, long long vox, void* s2d_hi, void* s2d_lo, int s2d_cb_total, int s2d_cb_off, int D, int H,
                 int W, cudaStream_t stream);
 
+/* 3x3x3 convolution (pad 1, stride 1) of a ONE-channel planar fp32 volume to 16 channels, exact fp32 on the CUDA cores
+ * (csrc/conv_small.cu): monai UnetResBlock.conv1 of the seg net's encoder1 (oar_transeg.py:92-100, in_channels = 1).
+ * w_host / bias_host are HOST arrays ([16][1][3][3][3], [16] or NULL) passed as kernel parameters.  Output: raw c8 fp32
+ * (+ statistics [N][16][2]); xstats [N][2] receives {sum x, sum x^2} of the input per image (zero it first).     */
+int dp_conv3d_c1(const float* x_planar, const float* w_host, const float* bias_host, int N, int D, int H, int W,
+                 float* out_raw, int out_cb_total, double* stats, double* xstats, cudaStream_t stream);
+
+/* dp_norm_act for the tail of that res block: out = act(IN(raw) + norm3(conv3(x))) where conv3 is the 1x1x1 conv
+ * 1 -> C of the same one-channel input x (res_w [C]) — its InstanceNorm is the affine map
+ * w_c (x - mean_x) / sqrt(w_c^2 var_x + eps) of x, evaluated from res_x (planar fp32) and res_xstats [N][2].   */
+int dp_norm_act_resx(const float* raw_f32, int in_cb_total, const double* stats, const float* res_x, const float* res_w,
+                     const double* res_xstats, int act_after_res, void* out_hi, void* out_lo, int out_cb_total,
+                     int out_cb_off, int N, int C, long long vox, cudaStream_t stream);
+
 /* dp_norm_act (raw fp32 in, no residual) fused with the 1x1x1 head that consumes its result: the dose heads
  * (dose_pyfer.py:290-300,316-317), conv_out_A (:353,359) and the seg logits (base_blocks.py:151-165).
  * head_w fp32 [head_co][C], head_b [head_co] or NULL, head_out NCDHW fp32 [N][head_co][vox]; head_co <= 8, C <= 128.

@@ -347,6 +347,36 @@ def test_pointwise_tc_matches_torch(Cs, Co, dims, acts, lo, out_act):
         assert torch.allclose(st[..., 1], (got.double() ** 2).sum((2, 3, 4)), rtol=1e-4, atol=1e-2)
 
 
+@pytest.mark.parametrize("dims", [(16, 16, 32), (9, 13, 40)])        # second: ragged tiles in every direction
+def test_one_channel_res_block_direct_conv_and_closed_form_residual(dims):
+    """monai UnetResBlock with in_channels = 1 (seg encoder1): conv1 as the exact fp32 direct conv (dp_conv3d_c1) and the
+    residual branch norm3(conv3(x)) in closed form inside the norm pass (dp_norm_act_resx), vs fp64 torch."""
+    from dose_prediction_b200 import networks
+    torch.manual_seed(31)
+    dev = torch.device("cuda:0")
+    N = 2
+    x = torch.randn(N, 1, *dims, device=dev) * 0.7 + 0.3
+    blk = networks.UnetResBlock(1, 16).to(dev).eval()
+    with torch.no_grad():
+        for prm in blk.parameters():
+            prm.mul_(3.0)
+    P = _plan()
+    a = _act_from(P, x, True)
+    out = P.new_act(N, 16, dims, lo=True)
+    networks._emit_res_block(P, blk, [a], out, networks.PREC_SEG, x_planar=x)
+    y = torch.zeros(N, 16, *dims, device=dev)
+    P.unpack(out, y)
+    P.run()
+    _finish(P)
+    assert any(st[2] == "dp_conv3d_c1" for st in P.steps) and any(st[2] == "dp_norm_act_resx" for st in P.steps)
+    xd = x.double().cpu()
+    w1, w2, w3 = (c.conv.weight.double().cpu() for c in (blk.conv1, blk.conv2, blk.conv3))
+    h = F.leaky_relu(F.instance_norm(F.conv3d(xd, w1, padding=1), eps=1e-5), 0.01)
+    h = F.instance_norm(F.conv3d(h, w2, padding=1), eps=1e-5)
+    want = F.leaky_relu(h + F.instance_norm(F.conv3d(xd, w3), eps=1e-5), 0.01)
+    assert _rel(y.cpu(), want) < 2e-5
+
+
 def test_deconv2x_c8_and_token_inputs():
     torch.manual_seed(7)
     dev = torch.device("cuda:0")
