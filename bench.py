@@ -169,10 +169,13 @@ def cpu_baseline(cpu, size, volumes=3, seed=1234):
             "sample": f"{volumes} x {size}^3 cascade volume(s), {cpu.what}, fp32, {dt:.1f} s"}, vol, out
 
 
-def parity_check(cpu, vol, cpu_out, got_logits, got_structures, got_dose):
-    """the benchmarked plan's volume 0 against the CPU implementation (north_star tolerances)."""
+def parity_check(cpu, vol, cpu_out, got_logits, got_dose, ptv, ct):
+    """the benchmarked plan's volume 0 against the CPU implementation (north_star tolerances).  The timed plan does not
+    write the 9-channel structures tensor out (nothing downstream needs it); the hand-off of the GPU's own logits is
+    recomputed here with the oracle's handoff(), which the GPU kernel matches bit for bit (tests/test_kernels_gpu.py)."""
     from oracle import torch_ref
     logits, st, dose = cpu_out
+    got_structures = torch_ref.handoff(got_logits, ptv, ct)
     _, _, dose_same = cpu(vol, structures=got_structures)       # dose net alone on the GPU path's own structures
     rep = {"logits_rel_l2": torch_ref.rel_l2(got_logits, logits),
            "argmax_agree": float((got_logits.argmax(1) == logits.argmax(1)).float().mean()),
@@ -456,7 +459,7 @@ def main():
 
     B, S = args.batch, args.size
     seg, dose = build_models(S, dev, seg_size=args.sw_roi or None)
-    casc = CascadePlan(seg, dose, B, S, dev, graph=False, sw_roi=args.sw_roi or None, keep_structures=True)
+    casc = CascadePlan(seg, dose, B, S, dev, graph=False, sw_roi=args.sw_roi or None)
     plan = casc.plan
     # synthetic volumes: this rank's shard of a job of world*B volumes (weak scaling), pinned on the host
     vols = synth.make_batch(B, S, seed=1234 + rank * B)
@@ -547,11 +550,15 @@ def main():
     top_label, top = max(by_shape.items(), key=lambda kv: kv[1]["ms"])
     avg_ms = top["ms"] / top["n"]
     ach = top["flops"] / (avg_ms / 1e3) / 1e12
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    if os.path.exists(tpath):
-        with open(tpath) as f:
-            traffic = json.load(f).get(f"{dominant} {top_label}")
+    traffic = family_traffic = None
+    for tname in ("r2_traffic.json", "r1_traffic.json"):       # ncu dram__bytes_read.sum + dram__bytes_write.sum (profiles/)
+        tpath = os.path.join(ROOT, "profiles", tname)
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                tj = json.load(f)
+            traffic = tj.get(f"{dominant} {top_label}")
+            family_traffic = tj.get(f"family {dominant} batch {B} size {S}")
+            break
     # headline = the dominant kernel over ALL its launches of the step (every shape it runs, the slow 3^3 ones included);
     # its heaviest launch shape is reported beside it as a sub-field
     best_shape = {"launch": top_label, "achieved": ach, "frac": ach / peaks["tflops"], "launches_per_step": top["n"],
@@ -560,7 +567,8 @@ def main():
                   "frac_of_burst": (ach / peaks["tflops_burst"]) if peaks["tflops_burst"] else None}
     roofline = dict(family_headline)
     roofline.update({"scope": "all launches of the dominant kernel in one step (algorithmic FLOPs / summed CUDA-event time)",
-                     "traffic": None, "peak_burst": peaks["tflops_burst"],
+                     "traffic": family_traffic, "traffic_unit": "DRAM bytes per step over all launches of this kernel (ncu)",
+                     "peak_burst": peaks["tflops_burst"],
                      "frac_of_burst": (family_headline["achieved"] / peaks["tflops_burst"]) if peaks["tflops_burst"] else None,
                      "heaviest_launch_shape": best_shape})
     # HBM-bound fused kernels: algorithmic bytes (every input and output moved once) / summed launch time
@@ -575,7 +583,7 @@ def main():
     # ---- outputs of the benchmarked plan for the in-run parity check (volume 0 of this rank's batch)
     casc.run()
     torch.cuda.synchronize(dev)
-    got = (casc.logits[:1].float().cpu(), casc.structures[:1].float().cpu(), casc.dose[:1].float().cpu()) if rank == 0 else None
+    got = (casc.logits[:1].float().cpu(), casc.dose[:1].float().cpu(), vols["ptv"][:1], vols["ct"][:1]) if rank == 0 else None
     gpu_launches = plan.kernels_per_step
     bytes_alloc = plan.bytes_alloc
     seg_sd = {k: v.cpu() for k, v in seg.state_dict().items()}

@@ -85,7 +85,8 @@ _SIGNATURES = {
 
 def exported_symbols():
     """Every symbol include/dose_b200.h declares (checked by tests/test_abi.py)."""
-    return sorted(list(_SIGNATURES) + ["dp_last_error", "dp_abi_version", "dp_device_sm_count", "dp_dvh_workspace_bytes"])
+    return sorted(list(_SIGNATURES) + ["dp_last_error", "dp_abi_version", "dp_device_sm_count", "dp_dvh_workspace_bytes",
+                                       "dp_handle_create", "dp_handle_device", "dp_handle_destroy"])
 
 
 def lib():
@@ -104,6 +105,12 @@ def lib():
         handle.dp_abi_version.restype = c_int
         handle.dp_device_sm_count.restype = c_int
         handle.dp_dvh_workspace_bytes.restype = c_longlong
+        handle.dp_handle_create.restype = c_void_p
+        handle.dp_handle_create.argtypes = [c_int]
+        handle.dp_handle_device.restype = c_int
+        handle.dp_handle_device.argtypes = [c_void_p]
+        handle.dp_handle_destroy.restype = None
+        handle.dp_handle_destroy.argtypes = [c_void_p]
         _LIB = handle
     return _LIB
 

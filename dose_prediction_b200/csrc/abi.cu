@@ -2,6 +2,8 @@
 // translation, cuTensorMapEncodeTiled via the runtime's driver entry point, device queries.
 #include <atomic>
 #include <cstdarg>
+#include <mutex>
+#include <unordered_map>
 #include <cstdio>
 #include <cstring>
 
@@ -41,8 +43,59 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+// ---- tensor-map cache (one per process, keyed by everything cuTensorMapEncodeTiled sees).  The plans replay the same
+// (buffer, shape, box) combinations every step; in eager replays (training, profiling) each launch used to re-encode its
+// maps through the driver (~1-2 us each, ~700 per training step).  A CUtensorMap is a plain 128-byte value, so cached
+// copies stay valid for as long as the device buffer does; dp_handle_destroy() drops them.
+namespace {
+struct MapKey {
+  uint64_t v[16];
+  bool operator==(const MapKey& o) const { return memcmp(v, o.v, sizeof(v)) == 0; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    uint64_t h = 1469598103934665603ull;
+    for (uint64_t x : k.v) { h ^= x; h *= 1099511628211ull; }
+    return static_cast<size_t>(h);
+  }
+};
+std::mutex g_map_mutex;
+std::unordered_map<MapKey, CUtensorMap, MapKeyHash>& map_cache() {
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> c;
+  return c;
+}
+}  // namespace
+
+void clear_tensor_map_cache() {
+  std::lock_guard<std::mutex> lock(g_map_mutex);
+  map_cache().clear();
+}
+
+static int encode_tiled_uncached(CUtensorMap* map, CUtensorMapDataType dtype, uint32_t rank, const void* base, const uint64_t* dims,
+                                 const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle);
+
 int encode_tiled(CUtensorMap* map, CUtensorMapDataType dtype, uint32_t rank, const void* base, const uint64_t* dims,
                  const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle) {
+  MapKey key{};
+  key.v[0] = reinterpret_cast<uint64_t>(base);
+  key.v[1] = (static_cast<uint64_t>(dtype) << 40) | (static_cast<uint64_t>(rank) << 32) | static_cast<uint64_t>(swizzle);
+  for (uint32_t i = 0; i < rank && i < 5; ++i) key.v[2 + i] = dims[i];
+  for (uint32_t i = 0; i + 1 < rank && i < 4; ++i) key.v[7 + i] = strides_bytes[i];
+  for (uint32_t i = 0; i < rank && i < 5; ++i) key.v[11 + i] = box[i];
+  {
+    std::lock_guard<std::mutex> lock(g_map_mutex);
+    auto it = map_cache().find(key);
+    if (it != map_cache().end()) { *map = it->second; return 0; }
+  }
+  if (int rc = encode_tiled_uncached(map, dtype, rank, base, dims, strides_bytes, box, swizzle)) return rc;
+  std::lock_guard<std::mutex> lock(g_map_mutex);
+  if (map_cache().size() > 65536) map_cache().clear();          // bound the cache (plans rebuilt with fresh buffers)
+  map_cache()[key] = *map;
+  return 0;
+}
+
+static int encode_tiled_uncached(CUtensorMap* map, CUtensorMapDataType dtype, uint32_t rank, const void* base, const uint64_t* dims,
+                                 const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) {
     set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
@@ -90,3 +143,25 @@ bool first_use_on_device(int family) {
 extern "C" const char* dp_last_error(void) { return dp::g_err; }
 extern "C" int dp_abi_version(void) { return 1; }
 extern "C" int dp_device_sm_count(void) { return dp::sm_count(); }
+
+// ---- dp_handle: the per-device library state a host integration owns explicitly.  The library keeps no other mutable
+// state than what a handle stands for: the kernels' per-device function attributes (configured on first use) and the
+// tensor-map cache.  Creating a handle selects nothing globally (entry points act on the CALLER's current device and
+// stream, like the CUDA runtime); destroying the last handle of a process drops the cached tensor maps.
+struct dp_handle { int device; };
+static std::atomic<int> g_handles{0};
+extern "C" dp_handle* dp_handle_create(int device) {
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
+    dp::set_error("dp_handle_create: device %d not present (%d visible)", device, count);
+    return nullptr;
+  }
+  g_handles.fetch_add(1);
+  return new dp_handle{device};
+}
+extern "C" int dp_handle_device(const dp_handle* h) { return h ? h->device : -1; }
+extern "C" void dp_handle_destroy(dp_handle* h) {
+  if (h == nullptr) return;
+  delete h;
+  if (g_handles.fetch_sub(1) == 1) dp::clear_tensor_map_cache();
+}

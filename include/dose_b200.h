@@ -39,6 +39,15 @@ const char* dp_last_error(void);
 int dp_abi_version(void);
 int dp_device_sm_count(void);
 
+/* Per-device library state (SURVEY 8b "opaque dp_handle*").  The entry points below act on the caller's CURRENT device and
+ * stream (as the CUDA runtime does) and keep no global mutable state beyond what a handle stands for: per-device kernel
+ * attributes, configured on first use on each device, and the process-wide tensor-map (CUtensorMap) cache, dropped when
+ * the last handle is destroyed.  One handle per device / rank; NULL on an invalid device (see dp_last_error).        */
+typedef struct dp_handle dp_handle;
+dp_handle* dp_handle_create(int device);
+int dp_handle_device(const dp_handle* h);
+void dp_handle_destroy(dp_handle* h);
+
 /* nn.Conv3d stride 1, odd k<=7, dilation dil, "same" padding, on tcgen05 tensor cores.
  * Replaces: blocks_MDUNet.py:68,71 (3^3), :102,105 (7^3), :166-187 (dilated), c3d.py:16,30 (stride-1
  * SingleConv/UpConv convs), monai UnetResBlock.conv1/conv2.  Fused epilogue: y = acc*scale[c]+shift[c]

@@ -70,3 +70,16 @@ def test_sass_contains_blackwell_tensor_and_tma_instructions():
     sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
     assert "UTCHMMA" in sass and "UTMALDG" in sass and "LDTM" in sass
     assert "HMMA." not in sass.replace("UTCHMMA", "")
+
+
+def test_handle_create_without_a_gpu_reports_an_error():
+    """dp_handle_create validates the device; on a box without GPUs it returns NULL and sets dp_last_error (no crash)."""
+    import torch
+    handle = _lib.lib()
+    if torch.cuda.is_available():
+        h = handle.dp_handle_create(0)
+        assert h and handle.dp_handle_device(h) == 0
+        handle.dp_handle_destroy(h)
+    bad = handle.dp_handle_create(4096)
+    assert not bad and b"dp_handle_create" in handle.dp_last_error()
+    handle.dp_handle_destroy(None)
