@@ -891,6 +891,32 @@ patchify_kernel(const __half* __restrict__ in, int cb_total, int cb_off, int ncb
   *reinterpret_cast<uint4*>(out + (static_cast<size_t>(n) * ntok + tok) * K + ((static_cast<size_t>(cb) * 16 + p1) * 16 + p2) * 128 + p3 * 8) = val;
 }
 
+// The same flatten for a ONE-channel planar fp32 volume (the seg net's CT input): K = 4096 = (p1, p2, p3) exactly as the
+// Linear weight stores it, instead of the c8 path's K = 8 * 4096 with seven zero channels.  One thread = 8 consecutive p3.
+__global__ void __launch_bounds__(256)
+patchify_planar_kernel(const float* __restrict__ in, int S0, int S1, int S2, __half* out) {
+  const int g1 = S1 / 16, g2 = S2 / 16;
+  const unsigned total = static_cast<unsigned>(S0 / 16) * g1 * g2 * 512u;          // 4096 / 8 vectors per token
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int n = blockIdx.y;
+  unsigned t = i;
+  const int p3h = static_cast<int>(t & 1u); t >>= 1;
+  const int p2 = static_cast<int>(t & 15u); t >>= 4;
+  const int p1 = static_cast<int>(t & 15u); t >>= 4;
+  const int tok = static_cast<int>(t);
+  const int gz = tok % g2, gy = (tok / g2) % g1, gx = tok / (g2 * g1);
+  const size_t vol = static_cast<size_t>(S0) * S1 * S2;
+  const size_t vox = (static_cast<size_t>(gx * 16 + p1) * S1 + (gy * 16 + p2)) * S2 + (gz * 16 + p3h * 8);
+  float x[8];
+  ld_global_v8f(in + static_cast<size_t>(n) * vol + vox, x);
+  __align__(16) __half2 h[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(x[2 * j], x[2 * j + 1]);
+  const size_t ntok = static_cast<size_t>(S0 / 16) * g1 * g2;
+  *reinterpret_cast<uint4*>(out + (static_cast<size_t>(n) * ntok + tok) * 4096 + (p1 * 16 + p2) * 16 + p3h * 8) = *reinterpret_cast<const uint4*>(h);
+}
+
 // ------------------------------------------------------------------ cascade hand-off (train_light_linked_model.py:156-167)
 // logits [N,8,X,Y,Z] fp32 -> argmax (first maximum wins) -> 7 one-hot OAR masks, spatially transposed
 // (x,y,z)->(z,y,x), + PTV (not transposed) + CT (transposed) -> dose-net input, written both as the c8
@@ -1401,6 +1427,16 @@ extern "C" int dp_patchify(const void* in_c8, int cb_total, int cb_off, int ncb,
   DP_REQUIRE(total < (1LL << 31), "dp_patchify: %lld vectors per image exceed the 32-bit index range", total);
   dim3 grid(blocks_for(total, 256), N);
   patchify_kernel<<<grid, 256, 0, stream>>>(static_cast<const __half*>(in_c8), cb_total, cb_off, ncb, S0, S1, S2, static_cast<__half*>(out));
+  DP_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dp_patchify_planar(const float* in_planar, int N, int S0, int S1, int S2, void* out, cudaStream_t stream) {
+  DP_REQUIRE(S0 % 16 == 0 && S1 % 16 == 0 && S2 % 16 == 0, "dp_patchify_planar: volume %dx%dx%d is not a multiple of the patch size 16", S0, S1, S2);
+  const long long total = static_cast<long long>(S0 / 16) * (S1 / 16) * (S2 / 16) * 512;
+  DP_REQUIRE(total < (1LL << 31), "dp_patchify_planar: %lld vectors per image exceed the 32-bit index range", total);
+  dim3 grid(blocks_for(total, 256), N);
+  patchify_planar_kernel<<<grid, 256, 0, stream>>>(in_planar, S0, S1, S2, static_cast<__half*>(out));
   DP_CHECK(cudaGetLastError());
   return 0;
 }

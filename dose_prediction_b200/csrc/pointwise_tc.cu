@@ -412,7 +412,7 @@ static int launch_ptc2(const PtcParams& p, int N, cudaStream_t stream) {
   (void)resident;
   (void)per_sm;
   PtcParams q = p;
-  q.tiles_per_cta = p.tiles / 64;                        // 128^3: 32 tiles (512 CTAs per image), 32^3: 4, <= 16^3: 1
+  q.tiles_per_cta = p.tiles / 256;                       // 128^3: 32 tiles (512 CTAs per image), 64^3: 8 (256 CTAs), <= 32^3: 1
   if (q.tiles_per_cta > 32) q.tiles_per_cta = 32;
   if (q.tiles_per_cta < 1) q.tiles_per_cta = 1;
   const int ctas = (p.tiles + q.tiles_per_cta - 1) / q.tiles_per_cta;

@@ -452,14 +452,18 @@ def _emit_base_unet(P, net, x_act, out_act, prec=PREC_NET_A):
     return out_act
 
 
-def _emit_vit(P, vit, parts, N, S, taps):
-    """monai ViT.forward (perceptron patch embedding) -> (LN(x_L) tokens, {layer index: hidden-state tokens})."""
+def _emit_vit(P, vit, parts, N, S, taps, x_planar=None):
+    """monai ViT.forward (perceptron patch embedding) -> (LN(x_L) tokens, {layer index: hidden-state tokens}).
+    x_planar: the ONE-channel input as planar fp32 (seg net): the patch matrix is then built straight from it with
+    K = 4096 (dp_patchify_planar) instead of K = 8 * 4096 through the c8 copy."""
     hidden, heads, L = vit.hidden_size, vit.num_heads, vit.num_layers
     hd = hidden // heads
     grid = tuple(s // 16 for s in S)
     T = grid[0] * grid[1] * grid[2]
     M = N * T
     first = parts[0]
+    planar = (x_planar is not None and len(parts) == 1 and parts[0].C == 1 and not P.training
+              and os.environ.get("DP_PATCHIFY_PLANAR", "1") != "0")
     ncb = sum(ceil_div(a.C, 8) if i == len(parts) - 1 else blocks16(a.C) for i, a in enumerate(parts))
     # logical channel -> slot inside the contiguous block range starting at parts[0].cb_off
     slots, base = [], 0
@@ -475,13 +479,21 @@ def _emit_vit(P, vit, parts, N, S, taps):
     else:
         lin = vit.patch_embedding.patch_embeddings[1]
         w = lin.weight.detach().to(P.device, torch.float32).view(hidden, 16, 16, 16, Cin)
-    wfull = torch.zeros((hidden, 16, 16, 16, ncb * 8), device=P.device)
-    wfull[..., torch.tensor(slots, device=P.device)] = w
-    wpe = wfull.view(hidden, 16, 16, 16, ncb, 8).permute(0, 4, 1, 2, 3, 5).reshape(hidden, K).contiguous().half()
-    del w, wfull
-    P.keep.append(wpe)
-    A = P.zeros((M, K), torch.float16)
-    P.patchify(first, ncb, A)
+    if planar:
+        K = 4096
+        wpe = w.reshape(hidden, K).contiguous().half()           # (p1, p2, p3, c = 1): already the planar flatten order
+        del w
+        P.keep.append(wpe)
+        A = P.zeros((M, K), torch.float16)
+        P.add("dp_patchify_planar", x_planar.data_ptr(), N, S[0], S[1], S[2], A.data_ptr())
+    else:
+        wfull = torch.zeros((hidden, 16, 16, 16, ncb * 8), device=P.device)
+        wfull[..., torch.tensor(slots, device=P.device)] = w
+        wpe = wfull.view(hidden, 16, 16, 16, ncb, 8).permute(0, 4, 1, 2, 3, 5).reshape(hidden, K).contiguous().half()
+        del w, wfull
+        P.keep.append(wpe)
+        A = P.zeros((M, K), torch.float16)
+        P.patchify(first, ncb, A)
     x = P.zeros((M, hidden), torch.float32)
     pos = P.dev(vit.patch_embedding.position_embeddings.reshape(T, hidden))
     tiles = ceil_div(M, 128) * ceil_div(hidden, 128)
@@ -700,7 +712,7 @@ def _emit_unetr_encoder(P, vit, enc_blocks, parts, taps, precs, skip_slots, x_pl
     """ViTEncoder.forward (dose_pyfer.py:124-144) / the encoder half of oar_transeg Model.forward: ViT, then the four conv
     skips written into `skip_slots` (usually the second halves of the decoder's concat buffers); returns the z12 tokens."""
     N, dims = parts[0].N, parts[0].dims
-    z, hs = _emit_vit(P, vit, parts, N, dims, taps)
+    z, hs = _emit_vit(P, vit, parts, N, dims, taps, x_planar=x_planar)
     _emit_res_block(P, enc_blocks[0].layer, parts, skip_slots[0], precs[0], x_planar=x_planar)
     _emit_pr_up(P, enc_blocks[1], hs[taps[0]], skip_slots[1], precs[1])
     _emit_pr_up(P, enc_blocks[2], hs[taps[1]], skip_slots[2], precs[2])

@@ -232,6 +232,10 @@ int dp_softmax(const float* s, int rows, int cols, int ld_in, void* p, int ld_ou
 int dp_patchify(const void* in_c8, int cb_total, int cb_off, int ncb, int N, int S0, int S1, int S2, void* out,
                 cudaStream_t stream);
 
+/* The same Rearrange for a ONE-channel planar fp32 volume [N][S0][S1][S2] (the seg net's CT input): out fp16
+ * [N * tokens][4096], K order (p1, p2, p3) = the reference Linear weight's own column order.                */
+int dp_patchify_planar(const float* in_planar, int N, int S0, int S1, int S2, void* out, cudaStream_t stream);
+
 /* Cascade hand-off: argmax(8) -> one-hot -> drop background -> permute(0,3,2,1) -> cat(ptv, oars, ct^T)
  * (train_light_linked_model.py:156-167, OARSegmentation/config.py:70).  Writes the dose net's c8 input
  * (2 channel blocks: [PTV,7 OARs] [CT,0...]) and optionally NCDHW fp32 structures [N,9,S,S,S].        */
