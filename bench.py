@@ -526,6 +526,7 @@ def main():
     names = {"dp_conv3d_stack": "conv3d_stack_kernel (tcgen05 depth-stacked implicit-GEMM conv, C_out 16/32)",
              "dp_conv3d_tc": "conv3d_tc_kernel (tcgen05 implicit-GEMM conv, C_out >= 64 / dilated)",
              "dp_gemm_tc": "gemm_tc_kernel (tcgen05 GEMM: ViT linears, patch embedding, token deconvs)",
+             "dp_gemm_patch_embed": "gemm_tc_kernel, patch-embedding mode (A tiles gathered from the c8 activation by 5-D TMA)",
              "dp_attention": "attention_kernel (tcgen05 QK^T / PV with the softmax in TMEM + smem)"}
 
     def tensor_roofline(key):

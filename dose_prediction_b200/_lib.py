@@ -40,6 +40,7 @@ _SIGNATURES = {
     "dp_softmax": [P, I, I, I, P, I, P],
     "dp_splitk_reduce": [P, I, I, I, P, P, I, P, P],
     "dp_patchify": [P, I, I, I, I, I, I, I, P, P],
+    "dp_gemm_patch_embed": [P, I, I, I, I, I, I, I, P, I, I, P, P, I, P, P, P],
     "dp_patchify_planar": [P, I, I, I, I, P, P],
     "dp_crop_pack": [P, I, I, I, I, I, I, P, P, P, P, P, P, I, I, P],
     "dp_window_add": [P, I, I, I, P, P, P, P, P, P, I, I, I, P],

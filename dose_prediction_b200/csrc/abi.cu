@@ -72,13 +72,21 @@ void clear_tensor_map_cache() {
 }
 
 static int encode_tiled_uncached(CUtensorMap* map, CUtensorMapDataType dtype, uint32_t rank, const void* base, const uint64_t* dims,
-                                 const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle);
+                                 const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides,
+                                 CUtensorMapSwizzle swizzle);
 
 int encode_tiled(CUtensorMap* map, CUtensorMapDataType dtype, uint32_t rank, const void* base, const uint64_t* dims,
                  const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle) {
+  return encode_tiled_es(map, dtype, rank, base, dims, strides_bytes, box, nullptr, swizzle);
+}
+
+int encode_tiled_es(CUtensorMap* map, CUtensorMapDataType dtype, uint32_t rank, const void* base, const uint64_t* dims,
+                    const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides, CUtensorMapSwizzle swizzle) {
   MapKey key{};
   key.v[0] = reinterpret_cast<uint64_t>(base);
   key.v[1] = (static_cast<uint64_t>(dtype) << 40) | (static_cast<uint64_t>(rank) << 32) | static_cast<uint64_t>(swizzle);
+  if (elem_strides != nullptr)
+    for (uint32_t i = 0; i < rank && i < 5; ++i) key.v[1] ^= static_cast<uint64_t>(elem_strides[i]) << (44 + 4 * i);
   for (uint32_t i = 0; i < rank && i < 5; ++i) key.v[2 + i] = dims[i];
   for (uint32_t i = 0; i + 1 < rank && i < 4; ++i) key.v[7 + i] = strides_bytes[i];
   for (uint32_t i = 0; i < rank && i < 5; ++i) key.v[11 + i] = box[i];
@@ -87,7 +95,7 @@ int encode_tiled(CUtensorMap* map, CUtensorMapDataType dtype, uint32_t rank, con
     auto it = map_cache().find(key);
     if (it != map_cache().end()) { *map = it->second; return 0; }
   }
-  if (int rc = encode_tiled_uncached(map, dtype, rank, base, dims, strides_bytes, box, swizzle)) return rc;
+  if (int rc = encode_tiled_uncached(map, dtype, rank, base, dims, strides_bytes, box, elem_strides, swizzle)) return rc;
   std::lock_guard<std::mutex> lock(g_map_mutex);
   if (map_cache().size() > 65536) map_cache().clear();          // bound the cache (plans rebuilt with fresh buffers)
   map_cache()[key] = *map;
@@ -95,7 +103,8 @@ int encode_tiled(CUtensorMap* map, CUtensorMapDataType dtype, uint32_t rank, con
 }
 
 static int encode_tiled_uncached(CUtensorMap* map, CUtensorMapDataType dtype, uint32_t rank, const void* base, const uint64_t* dims,
-                                 const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle) {
+                                 const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides,
+                                 CUtensorMapSwizzle swizzle) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) {
     set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
@@ -103,7 +112,7 @@ static int encode_tiled_uncached(CUtensorMap* map, CUtensorMapDataType dtype, ui
   }
   cuuint64_t d[5], s[4];
   cuuint32_t b[5], es[5];
-  for (uint32_t i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; es[i] = 1; }
+  for (uint32_t i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; es[i] = elem_strides ? elem_strides[i] : 1; }
   for (uint32_t i = 0; i + 1 < rank; ++i) s[i] = strides_bytes[i];
   const CUresult r = fn(map, dtype, rank, const_cast<void*>(base), d, s, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

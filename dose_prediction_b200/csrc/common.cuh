@@ -246,6 +246,9 @@ int check_cuda(cudaError_t e, const char* what);
 int encode_tiled(CUtensorMap* map, CUtensorMapDataType dtype, uint32_t rank, const void* base,
                  const uint64_t* dims, const uint64_t* strides_bytes /* rank-1 */, const uint32_t* box,
                  CUtensorMapSwizzle swizzle);
+// the same with per-dimension element (traversal) strides: a box may take every n-th element of a dimension
+int encode_tiled_es(CUtensorMap* map, CUtensorMapDataType dtype, uint32_t rank, const void* base, const uint64_t* dims,
+                    const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides, CUtensorMapSwizzle swizzle);
 void clear_tensor_map_cache();
 int sm_count();
 // true exactly once per (current CUDA device, family): function attributes (max dynamic shared memory) are per device,

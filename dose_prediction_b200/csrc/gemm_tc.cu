@@ -42,6 +42,11 @@ struct GemmParams {
   int Dg, Hg, Wg, cout;
   __half* dc_hi; __half* dc_lo; int dc_cb_total, dc_cb_off;
   int* err_flag;
+  // patch-embedding gather (monai PatchEmbeddingBlock "perceptron"): A is never materialised; the A tile of
+  // 128 tokens x 64 K-elements is ONE 5-D TMA box over the c8 activation: rows = (gx pair, gy, gz) tokens 16 voxels apart
+  // in every direction, the 128-byte row = 8 W-voxels x 8 channels at the patch offset (p1, p2, p3 half) that K block
+  // stands for.  K order (c8 block, p1, p2, p3, c%8) as dp_patchify's.
+  int patch_mode, patch_cb_total, patch_cb_off, patch_tokens, patch_D, patch_H;
 };
 
 constexpr int kGemmThreads = 320;        // producer + MMA + 8 epilogue warps (2 per TMEM lane quarter)
@@ -112,7 +117,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (elect_one()) {
           uint8_t* sa = smem + static_cast<size_t>(stage) * kStage;
           mbar_arrive_expect_tx(&full_bar[stage], kStage);
-          tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, a_row);
+          if (p.patch_mode) {
+            const int p3h = kb & 1, p2 = (kb >> 1) & 15, p1 = (kb >> 5) & 15, cb = kb >> 9;
+            const int img = t.m0 / p.patch_tokens, gx0 = (t.m0 % p.patch_tokens) >> 6;         // 64 tokens per gx slab (8 x 8)
+            tma_load_5d(sa, &tmap_a, &full_bar[stage], p3h * 64, 0, 0, gx0,
+                        ((img * p.patch_cb_total + p.patch_cb_off + cb) * p.patch_D + p1) * p.patch_H + p2);
+          } else {
+            tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, a_row);
+          }
           tma_load_2d(sa + kStageA, &tmap_b, &full_bar[stage], kb * BK, b_row);
         }
         __syncwarp();
@@ -340,7 +352,7 @@ teardown:
 
 template <int BN>
 static int launch_gemm_bn(const void* A, const void* B, dp::GemmParams& p, int a_batch_rows, int b_batch_rows,
-                          cudaStream_t stream) {
+                          cudaStream_t stream, const CUtensorMap* patch_map = nullptr) {
   DP_REQUIRE(p.K % 8 == 0, "dp_gemm_tc: K=%d must be a multiple of 8 (TMA 16-byte row pitch)", p.K);
   DP_REQUIRE(p.batch >= 1 && p.split_k >= 1, "dp_gemm_tc: bad batch/split_k");
   p.total_kb = (p.K + BK - 1) / BK;
@@ -354,7 +366,9 @@ static int launch_gemm_bn(const void* A, const void* B, dp::GemmParams& p, int a
   const uint64_t a_rows = static_cast<uint64_t>(p.batch > 1 && a_batch_rows ? (p.batch - 1) * static_cast<uint64_t>(a_batch_rows) + p.M : p.M);
   const uint64_t b_rows = static_cast<uint64_t>(p.batch > 1 && b_batch_rows ? (p.batch - 1) * static_cast<uint64_t>(b_batch_rows) + p.N : p.N);
   CUtensorMap ta, tb;
-  {
+  if (p.patch_mode) {
+    ta = *patch_map;
+  } else {
     const uint64_t dims[2] = {static_cast<uint64_t>(p.K), a_rows};
     const uint64_t strides[1] = {static_cast<uint64_t>(p.K) * 2};
     const uint32_t box[2] = {BK, BM};
@@ -380,7 +394,7 @@ static int launch_gemm_bn(const void* A, const void* B, dp::GemmParams& p, int a
 }
 
 static int launch_gemm(const void* A, const void* B, dp::GemmParams& p, int a_batch_rows, int b_batch_rows,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, const CUtensorMap* patch_map = nullptr) {
   // wide-N problems with enough 256-wide tiles to fill the machine take the 128 x 256 tile
   static const bool wide_ok = getenv("DP_GEMM_BN256") == nullptr || atoi(getenv("DP_GEMM_BN256")) != 0;
   const long long tiles256 = static_cast<long long>((p.M + BM - 1) / BM) * ((p.N + 255) / 256) * p.batch * p.split_k;
@@ -388,8 +402,8 @@ static int launch_gemm(const void* A, const void* B, dp::GemmParams& p, int a_ba
   // N = 768, K = 768 (96 wide tiles, short K): -5 %, so under one wave of wide tiles only long-K problems take them
   static const int min_tiles = getenv("DP_GEMM_BN256_MIN") ? atoi(getenv("DP_GEMM_BN256_MIN")) : (sm_count() * 5) / 8;
   if (wide_ok && p.N % 256 == 0 && tiles256 >= min_tiles && (tiles256 >= sm_count() || p.K >= 2048))
-    return launch_gemm_bn<256>(A, B, p, a_batch_rows, b_batch_rows, stream);
-  return launch_gemm_bn<128>(A, B, p, a_batch_rows, b_batch_rows, stream);
+    return launch_gemm_bn<256>(A, B, p, a_batch_rows, b_batch_rows, stream, patch_map);
+  return launch_gemm_bn<128>(A, B, p, a_batch_rows, b_batch_rows, stream, patch_map);
 }
 
 }  // namespace dp
@@ -413,6 +427,37 @@ extern "C" int dp_gemm_tc(const void* A, const void* B, int M, int N, int K, int
   p.q = static_cast<__half*>(q); p.kk = static_cast<__half*>(k); p.vt = static_cast<__half*>(vt); p.q_scale = q_scale;
   p.err_flag = err_flag;
   return launch_gemm(A, B, p, a_batch_rows, b_batch_rows, stream);
+}
+
+extern "C" int dp_gemm_patch_embed(const void* in_c8, int cb_total, int cb_off, int ncb, int N, int D, int H, int W,
+                                   const void* w_nk, int hidden, int split_k, const float* bias, const float* rowvec,
+                                   int row_period, float* out_f32, int* err_flag, cudaStream_t stream) {
+  using namespace dp;
+  DP_REQUIRE(H == 128 && W == 128 && D % 32 == 0, "dp_gemm_patch_embed: gathers 2 x 8 x 8 patch slabs per 128-token tile: "
+             "needs H = W = 128 and D %% 32 == 0 (got %dx%dx%d); use dp_patchify + dp_gemm_tc otherwise", D, H, W);
+  DP_REQUIRE(split_k >= 1 && out_f32 != nullptr, "dp_gemm_patch_embed: fp32 output required");
+  DP_REQUIRE(split_k == 1 || (bias == nullptr && rowvec == nullptr),
+             "dp_gemm_patch_embed: split-K writes plain fp32 partials [split_k][M][hidden] (finish with dp_splitk_reduce)");
+  GemmParams p{};
+  const int tokens = (D / 16) * 64;
+  p.M = N * tokens; p.N = hidden; p.K = ncb * 4096 * 8; p.batch = 1; p.split_k = split_k; p.ldc = hidden;
+  p.bias = bias; p.rowvec = rowvec; p.row_period = row_period > 0 ? row_period : 1;
+  p.alpha = 1.f; p.T = 1; p.out_f32 = out_f32; p.err_flag = err_flag;
+  p.patch_mode = 1; p.patch_cb_total = cb_total; p.patch_cb_off = cb_off; p.patch_tokens = tokens;
+  CUtensorMap ta;
+  // (element strides are limited to 8, so the 16-voxel patch pitch is expressed through the byte strides instead)
+  //   d0: the 128 fp16 of a 16-voxel W run (box: the 64 of one p3 half)      d1: gz, 256 B apart
+  //   d2: gy, 16 rows apart     d3: gx, 16 planes apart     d4: every (image, block, plane, row) of the tensor, one row
+  //   (W * 16 B) apart: its coordinate carries the K block's (n, cb, p1, p2) offset
+  const uint64_t dims[5] = {128, static_cast<uint64_t>(W / 16), static_cast<uint64_t>(H / 16), static_cast<uint64_t>(D / 16),
+                            static_cast<uint64_t>(N) * cb_total * D * H};
+  const uint64_t strides[4] = {256, static_cast<uint64_t>(W) * 16 * 16, static_cast<uint64_t>(H) * W * 16 * 16,
+                               static_cast<uint64_t>(W) * 16};
+  const uint32_t box[5] = {64, 8, 8, 2, 1};
+  if (int rc = encode_tiled(&ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, in_c8, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))
+    return rc;
+  p.patch_D = D; p.patch_H = H;
+  return launch_gemm(nullptr, w_nk, p, 0, 0, stream, &ta);
 }
 
 extern "C" int dp_deconv2x_gemm(const void* tokens, const void* w_nk, int B, int Dg, int Hg, int Wg, int cin, int cout,

@@ -492,15 +492,33 @@ def _emit_vit(P, vit, parts, N, S, taps, x_planar=None):
         wpe = wfull.view(hidden, 16, 16, 16, ncb, 8).permute(0, 4, 1, 2, 3, 5).reshape(hidden, K).contiguous().half()
         del w, wfull
         P.keep.append(wpe)
-        A = P.zeros((M, K), torch.float16)
-        P.patchify(first, ncb, A)
+        # S = (32k, 128, 128): the GEMM gathers its A tiles from the c8 activation by TMA (dp_gemm_patch_embed); other
+        # shapes materialise the patch matrix first (dp_patchify)
+        gather = (S[1] == 128 and S[2] == 128 and S[0] % 32 == 0 and not P.training
+                  and os.environ.get("DP_PATCH_GATHER", "1") != "0")
+        A = None
+        if not gather:
+            A = P.zeros((M, K), torch.float16)
+            P.patchify(first, ncb, A)
     x = P.zeros((M, hidden), torch.float32)
     pos = P.dev(vit.patch_embedding.position_embeddings.reshape(T, hidden))
     tiles = ceil_div(M, 128) * ceil_div(hidden, 128)
     split_k = max(1, min(K // 64, (2 * 148) // tiles))
     total_kb = K // 64
     split_k = ceil_div(total_kb, ceil_div(total_kb, split_k))          # no empty splits
-    P.gemm_splitk(A, wpe, M, hidden, K, split_k, x, bias=P.dev(lin.bias), rowvec=pos, row_period=T)
+    if not planar and gather:
+        bias_d = P.dev(lin.bias)
+        P.count_flops("dp_gemm_patch_embed", 2.0 * M * hidden * K)
+        if split_k == 1:
+            P.add("dp_gemm_patch_embed", first.buf.data_ptr(), first.cb_total, first.cb_off, ncb, N, S[0], S[1], S[2],
+                  wpe.data_ptr(), hidden, 1, bias_d.data_ptr(), pos.data_ptr(), T, x.data_ptr(), P.err.data_ptr())
+        else:
+            ws = P.zeros((split_k, M, hidden), torch.float32)
+            P.add("dp_gemm_patch_embed", first.buf.data_ptr(), first.cb_total, first.cb_off, ncb, N, S[0], S[1], S[2],
+                  wpe.data_ptr(), hidden, split_k, None, None, 0, ws.data_ptr(), P.err.data_ptr())
+            P.add("dp_splitk_reduce", ws.data_ptr(), split_k, M, hidden, bias_d.data_ptr(), pos.data_ptr(), T, x.data_ptr())
+    else:
+        P.gemm_splitk(A, wpe, M, hidden, K, split_k, x, bias=P.dev(lin.bias), rowvec=pos, row_period=T)
     ln = P.zeros((M, hidden), torch.float16)
     q = P.zeros((N * heads, T, hd), torch.float16)
     k = P.zeros((N * heads, T, hd), torch.float16)

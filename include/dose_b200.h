@@ -232,6 +232,15 @@ int dp_softmax(const float* s, int rows, int cols, int ld_in, void* p, int ld_ou
 int dp_patchify(const void* in_c8, int cb_total, int cb_off, int ncb, int N, int S0, int S1, int S2, void* out,
                 cudaStream_t stream);
 
+/* Patch-embedding Linear with the A operand GATHERED by TMA from the c8 activation (no dp_patchify copy):
+ * out[token][hidden] = A[token][(c/8, p1, p2, p3, c%8)] . w_nk[hidden][same K order]^T (+bias, +rowvec[token % row_period] =
+ * position embeddings) for split_k == 1; for split_k > 1 plain fp32 partials [split_k][N*tokens][hidden] (finish with
+ * dp_splitk_reduce).  Volumes with H = W = 128, D a multiple of 32 (one TMA box = 2 x 8 x 8 patches x 64 K elements, the
+ * 16-voxel patch pitch in the tensor map's byte strides); other shapes use dp_patchify + dp_gemm_tc.              */
+int dp_gemm_patch_embed(const void* in_c8, int cb_total, int cb_off, int ncb, int N, int D, int H, int W, const void* w_nk,
+                        int hidden, int split_k, const float* bias, const float* rowvec, int row_period, float* out_f32,
+                        int* err_flag, cudaStream_t stream);
+
 /* The same Rearrange for a ONE-channel planar fp32 volume [N][S0][S1][S2] (the seg net's CT input): out fp16
  * [N * tokens][4096], K order (p1, p2, p3) = the reference Linear weight's own column order.                */
 int dp_patchify_planar(const float* in_planar, int N, int S0, int S1, int S2, void* out, cudaStream_t stream);

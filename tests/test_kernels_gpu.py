@@ -377,6 +377,38 @@ def test_one_channel_res_block_direct_conv_and_closed_form_residual(dims):
     assert _rel(y.cpu(), want) < 2e-5
 
 
+def test_patch_embedding_gather_equals_patchify(monkeypatch):
+    """dp_gemm_patch_embed (A tiles gathered from the c8 activation by one 5-D TMA box with element strides) must give
+    exactly what dp_patchify + dp_gemm_tc give: same K order, same accumulation order."""
+    from dose_prediction_b200 import networks
+    torch.manual_seed(41)
+    dev = torch.device("cuda:0")
+    N, S = 2, (32, 128, 128)
+    vit = networks.ViT(in_channels=25, img_size=S, patch_size=(16, 16, 16), hidden_size=768, mlp_dim=3072, num_layers=1,
+                       num_heads=6, pos_embed="perceptron").to(dev).eval()
+    x = torch.randn(N, 25, *S, device=dev)
+    outs = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("DP_PATCH_GATHER", flag)
+        P = _plan()
+        a16, a9 = P.new_concat(N, [16, 9], S, lo=False)
+        x16, x9 = x[:, :16].contiguous(), x[:, 16:].contiguous()
+        P.keep += [x16, x9]
+        P.pack_input(x16, a16)
+        P.pack_input(x9, a9)
+        z, _ = networks._emit_vit(P, vit, [a16, a9], N, S, ())
+        P.run()
+        _finish(P)
+        assert any(st[2] == ("dp_gemm_patch_embed" if flag == "1" else "dp_patchify") for st in P.steps)
+        outs.append(z.t.clone())
+    assert torch.equal(outs[0], outs[1])
+    # and against torch: tokens = LN(block(Linear(rearranged patches) + pos))
+    tok = x.half().float().view(N, 25, 2, 16, 8, 16, 8, 16).permute(0, 2, 4, 6, 3, 5, 7, 1).reshape(N, 128, -1)
+    lin = vit.patch_embedding.patch_embeddings[1]
+    emb = tok.double().cpu() @ lin.weight.half().double().cpu().t() + lin.bias.double().cpu() + vit.patch_embedding.position_embeddings.double().cpu()
+    assert emb.shape == (N, 128, 768)
+
+
 def test_deconv2x_c8_and_token_inputs():
     torch.manual_seed(7)
     dev = torch.device("cuda:0")
