@@ -64,6 +64,8 @@ _SIGNATURES = {
     "dp_adamw": [P, P, P, P, L, F, F, F, F, F, I, F, P, P],
     "dp_adamw_dev": [P, P, P, P, L, F, F, F, F, F, F, P, P, P],
     "dp_grad_check": [P, L, P, P],
+    "dp_quantize_blockwise": [P, L, P, P, P, P],
+    "dp_dequantize_blockwise": [P, P, P, L, P, P],
     "dp_pack_conv_weight": [P, I, I, I, I, P, P, I, I, P, P],
     "dp_cast_f16": [P, L, P, P],
     "dp_layernorm_bwd": [P, P, P, P, I, I, P, P, P, P],

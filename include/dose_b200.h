@@ -367,6 +367,13 @@ int dp_adamw_dev(float* p, const float* g, float* m, float* v, long long n, floa
                  float weight_decay, float inv_scale, const int* found_inf, int* state, cudaStream_t stream);
 int dp_grad_check(const float* g, long long n, int* found_inf, cudaStream_t stream);
 
+/* bitsandbytes 8-bit optimizer-state layout (bnb.optim.Adam8bit, train_light_pyfer.py:194-197): block-wise (2048 elements)
+ * quantisation of a state tensor to uint8 codes into a sorted 256-entry code book times the block's absmax, and back.
+ * codes_u8 [n], absmax [ceil(n / 2048)], qmap256 fp32 [256] (bnb's "dynamic" map; optim8bit.create_dynamic_map).      */
+int dp_quantize_blockwise(const float* x, long long n, const float* qmap256, void* codes_u8, float* absmax, cudaStream_t stream);
+int dp_dequantize_blockwise(const void* codes_u8, const float* absmax, const float* qmap256, long long n, float* x,
+                            cudaStream_t stream);
+
 /* Per-step re-packing of the live fp32 parameters into the kernels' fp16 operand layouts (what the inference
  * plans do once on the host side): conv weights [cout][cin][k][k][k] -> dp_conv3d_tc / dp_conv3d_stack layout for
  * 16-channel chunks holding logical input channels chunk_ci0[] .. +chunk_nci[]; transpose_flip = 1 reads the
