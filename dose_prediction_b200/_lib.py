@@ -84,6 +84,9 @@ _SIGNATURES = {
     # ---- input pipeline
     "dp_prepare_input": [P, P, P, P, P, P, I, I, I, F, F, F, P, P, P],
     "dp_flip_rot90": [P, P, I, I, I, I, I, I, I, I, P],
+    "dp_permute_flip": [P, P, I, I, I, I, I, I, I, I, I, I, P],
+    "dp_posneg_count": [P, I, P, I, F, L, P, P],
+    "dp_posneg_crop": [P, I, P, I, F, I, I, I, I, I, P, P, I, P, P, P, P],
 }
 
 

@@ -437,6 +437,24 @@ int dp_prepare_input(const void* const* ptv_u8, const void* const* oar_u8, const
 int dp_flip_rot90(const float* in, float* out, int C, int S0, int S1, int S2, int flip0, int flip1, int flip2, int k,
                   cudaStream_t stream);
 
+/* Orientationd(axcodes="RAS") (dataloader_OpenKBP_monai.py:182): out axis a = in axis perm[a], reversed when flip[a]
+ * (the transposes + flips nibabel's ornt_transform prescribes; the host derives them from the NIfTI affine). */
+int dp_permute_flip(const float* in, float* out, int C, int S0, int S1, int S2, int perm0, int perm1, int perm2, int flip0,
+                    int flip1, int flip2, cudaStream_t stream);
+
+/* RandCropByPosNegLabeld (monai 0.7.0; dataloader_OpenKBP_monai.py:206-215, OARSegmentation/DataLoader/provided_dataset.py:
+ * 158-167).  Foreground = any label channel > 0, background = any image channel > image_threshold and not foreground
+ * (image NULL: every non-foreground voxel).  dp_posneg_count: per 4096-voxel block {foreground, background} counts
+ * (block_counts int[blocks][2]); the host draws the samples with numpy RandomState semantics from the totals and names,
+ * per sample, {block, rank inside the block, want_foreground} (pick_dev int[n][3], device memory).  dp_posneg_crop: finds
+ * those voxels, clamps the centres like correct_crop_centers, writes the crop origins (roi_start_dev int[n][3]) and crops
+ * every source [C_i][S0][S1][S2] to dst_i [n][C_i][R][R][R].  src / src_channels / dst: HOST arrays.                */
+int dp_posneg_count(const float* label, int label_channels, const float* image, int image_channels, float image_threshold,
+                    long long vox, int* block_counts, cudaStream_t stream);
+int dp_posneg_crop(const float* label, int label_channels, const float* image, int image_channels, float image_threshold,
+                   int S0, int S1, int S2, int R, int n_samples, const int* pick_dev, int* roi_start_dev, int n_src,
+                   const float* const* src, const int* src_channels, float* const* dst, cudaStream_t stream);
+
 /* Seg validation metric: monai 0.7.0 DiceMetric(include_background=False, reduction="mean") on one-hot(argmax(logits))
  * vs the label map (OARSegmentation/train_light_transeg.py:199-216).  logits: NCDHW fp32 [N][C][vox]; label: fp32 class
  * index [N][vox]; counts: uint64[N*48] scratch; dice: float[N][C] (NaN where the class is absent from the label);

@@ -39,3 +39,80 @@ def augment(x, flips=(False, False, False), k=0):
     if k:
         x = np.rot90(x, k, axes=(1, 2))
     return np.ascontiguousarray(x)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Round 2: LoadImaged / Orientationd / RandCropByPosNegLabeld.  monai 0.7.0 and nibabel are un-vendored and absent offline:
+# restated from their published sources (parity unpinned); the functions below are what tests/ compare the device path to.
+def write_nifti(path, data, affine, slope=1.0, inter=0.0):
+    """minimal single-file NIfTI-1 writer (test fixture generator for pipeline.read_nifti; sform carries the affine)."""
+    import gzip
+    import struct
+    data = np.asarray(data)
+    code = {np.dtype("u1"): 2, np.dtype("i2"): 4, np.dtype("i4"): 8, np.dtype("f4"): 16, np.dtype("f8"): 64}[data.dtype]
+    hdr = bytearray(348)
+    struct.pack_into("<i", hdr, 0, 348)
+    dim = [data.ndim] + list(data.shape) + [1] * (7 - data.ndim)
+    struct.pack_into("<8h", hdr, 40, *dim)
+    struct.pack_into("<h", hdr, 70, code)
+    struct.pack_into("<h", hdr, 72, data.dtype.itemsize * 8)
+    zooms = np.sqrt((np.asarray(affine)[:3, :3] ** 2).sum(0))
+    struct.pack_into("<8f", hdr, 76, 1.0, *zooms, 1.0, 1.0, 1.0, 1.0)
+    struct.pack_into("<3f", hdr, 108, 352.0, slope, inter)
+    struct.pack_into("<2h", hdr, 252, 0, 1)                        # qform_code 0, sform_code 1
+    struct.pack_into("<12f", hdr, 280, *np.asarray(affine, dtype=np.float64)[:3].reshape(-1))
+    hdr[344:348] = b"n+1\0"
+    payload = bytes(hdr) + b"\0\0\0\0" + data.tobytes(order="F")
+    opener = gzip.open if str(path).endswith(".gz") else open
+    with opener(path, "wb") as f:
+        f.write(payload)
+
+
+def apply_orientation(arr, perm, flips):
+    """nibabel.orientations.apply_orientation on the spatial axes of [C,S0,S1,S2]: output axis a = input axis perm[a], flipped."""
+    out = np.transpose(arr, (0,) + tuple(p + 1 for p in perm))
+    for a, f in enumerate(flips):
+        if f:
+            out = np.flip(out, axis=a + 1)
+    return np.ascontiguousarray(out)
+
+
+def rand_crop_by_pos_neg_label(arrays, label, image, spatial_size, pos, neg, num_samples, image_threshold, rand_state):
+    """monai 0.7.0 RandCropByPosNegLabeld: map_binary_to_indices + generate_pos_neg_label_crop_centers +
+    correct_crop_centers + SpatialCrop(roi_center, roi_size)."""
+    R = int(spatial_size)
+    shape = label.shape[1:]
+    label_flat = np.any(label, axis=0).ravel()
+    fg = np.nonzero(label_flat)[0]
+    if image is not None:
+        img_flat = np.any(image > image_threshold, axis=0).ravel()
+        bg = np.nonzero(np.logical_and(img_flat, ~label_flat))[0]
+    else:
+        bg = np.nonzero(~label_flat)[0]
+    pos_ratio = pos / (pos + neg)
+    if not len(fg) or not len(bg):
+        if not len(fg) and not len(bg):
+            raise ValueError("No sampling location available.")
+        pos_ratio = 0 if not len(fg) else 1
+    outs = [[] for _ in arrays]
+    starts = []
+    for _ in range(num_samples):
+        idx = fg if rand_state.rand() < pos_ratio else bg
+        center = list(np.unravel_index(idx[rand_state.randint(len(idx))], shape))
+        valid_start = np.floor_divide([R] * 3, 2)
+        valid_end = np.subtract(np.asarray(shape) + np.array(1), np.asarray([R] * 3) / np.array(2)).astype(np.uint16)
+        for i in range(3):
+            if valid_start[i] == valid_end[i]:
+                valid_end[i] += 1
+        for i, c in enumerate(center):
+            ci = c
+            if c < valid_start[i]:
+                ci = valid_start[i]
+            if c >= valid_end[i]:
+                ci = valid_end[i] - 1
+            center[i] = int(ci)
+        start = [max(c - R // 2, 0) for c in center]
+        starts.append(start)
+        for o, a in zip(outs, arrays):
+            o.append(a[:, start[0]:start[0] + R, start[1]:start[1] + R, start[2]:start[2] + R])
+    return [np.stack(o) for o in outs], np.asarray(starts, dtype=np.int32)
