@@ -81,6 +81,7 @@ _SIGNATURES = {
     "dp_dose_stats": [P, P, P, L, P, I, P, P, P, P, P],
     "dp_dvh_metrics": [P, P, P, I, P, L, F, P, P, P, P],
     "dp_dice_metric": [P, P, I, I, L, P, P, P, P],
+    "dp_hd95": [P, P, I, I, I, I, F, P, P, P],
     # ---- input pipeline
     "dp_prepare_input": [P, P, P, P, P, P, I, I, I, F, F, F, P, P, P],
     "dp_flip_rot90": [P, P, I, I, I, I, I, I, I, I, P],
@@ -93,7 +94,7 @@ _SIGNATURES = {
 def exported_symbols():
     """Every symbol include/dose_b200.h declares (checked by tests/test_abi.py)."""
     return sorted(list(_SIGNATURES) + ["dp_last_error", "dp_abi_version", "dp_device_sm_count", "dp_dvh_workspace_bytes",
-                                       "dp_handle_create", "dp_handle_device", "dp_handle_destroy"])
+                                       "dp_handle_create", "dp_handle_device", "dp_handle_destroy", "dp_hd95_workspace_bytes"])
 
 
 def lib():
@@ -112,6 +113,8 @@ def lib():
         handle.dp_abi_version.restype = c_int
         handle.dp_device_sm_count.restype = c_int
         handle.dp_dvh_workspace_bytes.restype = c_longlong
+        handle.dp_hd95_workspace_bytes.restype = c_longlong
+        handle.dp_hd95_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int]
         handle.dp_handle_create.restype = c_void_p
         handle.dp_handle_create.argtypes = [c_int]
         handle.dp_handle_device.restype = c_int

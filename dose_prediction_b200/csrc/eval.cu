@@ -262,6 +262,97 @@ __global__ void dice_finalize_kernel(const unsigned long long* counts, int N, in
   *mean_dice = batch_cnt ? static_cast<float>(batch_sum / batch_cnt) : 0.f;
 }
 
+// ------------------------------------------------------------------ 95th-percentile Hausdorff distance (seg val / test)
+// monai 0.7.0 HausdorffDistanceMetric(include_background=False, percentile=95) on one-hot(argmax) vs one-hot(label)
+// (OARSegmentation/train_light_transeg.py:158-166,199-216): per class, the surface voxels of both masks
+// (mask ^ binary_erosion(mask), 6-neighbourhood, outside = background), the Euclidean distance of every surface voxel of one
+// mask to the nearest surface voxel of the other (monai: distance_transform_edt), np.percentile(.., 95) in both directions,
+// the larger of the two.  Surfaces are a few 10^4 voxels, so the exact nearest-surface search is done by brute force over
+// compacted coordinate lists; squared distances are integers, so a histogram over d^2 gives exact order statistics.
+__global__ void __launch_bounds__(256)
+hd_edges_kernel(const float* __restrict__ logits, const float* __restrict__ label, int C, int D, int H, int W, int cap,
+                int* coords /* [2][C][cap] packed */, int* counts /* [2][C] */) {
+  const long long vox = static_cast<long long>(D) * H * W;
+  const long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (v >= vox) return;
+  const int w = static_cast<int>(v % W), h = static_cast<int>((v / W) % H), d = static_cast<int>(v / (static_cast<long long>(W) * H));
+  auto cls_pred = [&](long long u) {
+    int best = 0;
+    float bv = logits[u];
+    for (int c = 1; c < C; ++c) { const float x = logits[c * vox + u]; if (x > bv) { bv = x; best = c; } }
+    return best;
+  };
+  auto cls_gt = [&](long long u) { return static_cast<int>(label[u]); };
+  for (int which = 0; which < 2; ++which) {
+    const int c = which == 0 ? cls_pred(v) : cls_gt(v);
+    if (c < 1 || c >= C) continue;
+    bool edge = (d == 0 || d == D - 1 || h == 0 || h == H - 1 || w == 0 || w == W - 1);
+    const long long nb[6] = {v - static_cast<long long>(W) * H, v + static_cast<long long>(W) * H, v - W, v + W, v - 1, v + 1};
+    for (int q = 0; q < 6 && !edge; ++q) edge = (which == 0 ? cls_pred(nb[q]) : cls_gt(nb[q])) != c;
+    if (edge) {
+      const int slot = atomicAdd(&counts[which * C + c], 1);
+      if (slot < cap) coords[(static_cast<size_t>(which) * C + c) * cap + slot] = (d << 20) | (h << 10) | w;
+    }
+  }
+}
+// grid: (source-point blocks, class, direction); direction 0 = pred surface -> gt surface, 1 = gt -> pred
+__global__ void __launch_bounds__(256)
+hd_dist_kernel(const int* __restrict__ coords, const int* __restrict__ counts, int C, int cap, int nbins, int* hist /* [2][C][nbins] */) {
+  const int c = blockIdx.y, dir = blockIdx.z;
+  if (c < 1) return;
+  const int na = min(counts[dir * C + c], cap), nb = min(counts[(1 - dir) * C + c], cap);
+  const int* A = coords + (static_cast<size_t>(dir) * C + c) * cap;
+  const int* B = coords + (static_cast<size_t>(1 - dir) * C + c) * cap;
+  __shared__ int tile[1024];
+  for (int base = blockIdx.x * blockDim.x; base < na; base += gridDim.x * blockDim.x) {
+    const int i = base + threadIdx.x;
+    const int p = i < na ? A[i] : 0;
+    const int pd = p >> 20, ph = (p >> 10) & 1023, pw = p & 1023;
+    int best = 0x7fffffff;
+    for (int t0 = 0; t0 < nb; t0 += 1024) {
+      __syncthreads();
+      for (int j = threadIdx.x; j < 1024 && t0 + j < nb; j += blockDim.x) tile[j] = B[t0 + j];
+      __syncthreads();
+      const int lim = min(1024, nb - t0);
+      for (int j = 0; j < lim; ++j) {
+        const int q = tile[j];
+        const int dd = pd - (q >> 20), dh = ph - ((q >> 10) & 1023), dw = pw - (q & 1023);
+        best = min(best, dd * dd + dh * dh + dw * dw);
+      }
+    }
+    if (i < na && nb > 0) atomicAdd(&hist[(static_cast<size_t>(dir) * C + c) * nbins + min(best, nbins - 1)], 1);
+  }
+}
+// one thread per (class, direction): np.percentile(distances, pct) with linear interpolation from the d^2 histogram
+__global__ void hd_percentile_kernel(const int* __restrict__ hist, const int* __restrict__ counts, int C, int cap, int nbins, float pct,
+                                     float* hd /* [C] */) {
+  const int c = threadIdx.x;
+  if (c >= C) return;
+  if (c < 1) { hd[c] = nanf(""); return; }
+  float out[2];
+  for (int dir = 0; dir < 2; ++dir) {
+    const int na = min(counts[dir * C + c], cap), nb = min(counts[(1 - dir) * C + c], cap);
+    if (na == 0) { out[dir] = nanf(""); continue; }                // no surface on the source side: np.nan
+    if (nb == 0) { out[dir] = INFINITY; continue; }                 // nothing to measure to: inf
+    const double q = static_cast<double>(na - 1) * pct / 100.0;
+    const long long k0 = static_cast<long long>(floor(q)), k1 = min(static_cast<long long>(na - 1), k0 + 1);
+    const double frac = q - static_cast<double>(k0);
+    const int* hcd = hist + (static_cast<size_t>(dir) * C + c) * nbins;
+    long long seen = 0;
+    double v0 = 0.0, v1 = 0.0;
+    bool got0 = false;
+    for (int b = 0; b < nbins; ++b) {
+      const long long nxt = seen + hcd[b];
+      if (!got0 && k0 < nxt) { v0 = sqrt(static_cast<double>(b)); got0 = true; }
+      if (k1 < nxt) { v1 = sqrt(static_cast<double>(b)); break; }
+      seen = nxt;
+    }
+    out[dir] = static_cast<float>(v0 + (v1 - v0) * frac);
+  }
+  // max(distance_1, distance_2) with numpy semantics: nan propagates
+  hd[c] = (isnan(out[0]) || isnan(out[1])) ? nanf("") : fmaxf(out[0], out[1]);
+}
+
 static inline unsigned eblk(long long n, int threads, unsigned cap) {
   const long long b = (n + threads - 1) / threads;
   return static_cast<unsigned>(b < cap ? b : cap);
@@ -322,4 +413,31 @@ extern "C" int dp_dice_metric(const float* logits, const float* label, int N, in
   DP_CHECK(cudaGetLastError());
   dice_finalize_kernel<<<1, 1, 0, stream>>>(counts, N, C, dice, mean_dice);
   return check_cuda(cudaGetLastError(), "dice_metric");
+}
+
+extern "C" long long dp_hd95_workspace_bytes(int C, int D, int H, int W) {
+  const long long vox = static_cast<long long>(D) * H * W;
+  const long long cap = vox / 4 + 1024;
+  const long long nbins = static_cast<long long>(D - 1) * (D - 1) + static_cast<long long>(H - 1) * (H - 1) +
+                          static_cast<long long>(W - 1) * (W - 1) + 2;
+  return (2LL * C * cap + 2LL * C + 2LL * C * nbins) * 4;
+}
+
+extern "C" int dp_hd95(const float* logits, const float* label, int C, int D, int H, int W, float percentile, void* workspace,
+                       float* hd, cudaStream_t stream) {
+  DP_REQUIRE(C >= 2 && C <= 16 && D <= 1023 && H <= 1023 && W <= 1023, "hd95: 2..16 classes, dims <= 1023");
+  DP_REQUIRE(percentile >= 0.f && percentile <= 100.f, "hd95: percentile should be within [0, 100], got %f", percentile);
+  const long long vox = static_cast<long long>(D) * H * W;
+  const int cap = static_cast<int>(vox / 4 + 1024);
+  const int nbins = (D - 1) * (D - 1) + (H - 1) * (H - 1) + (W - 1) * (W - 1) + 2;
+  int* coords = static_cast<int*>(workspace);
+  int* counts = coords + 2LL * C * cap;
+  int* hist = counts + 2 * C;
+  DP_CHECK(cudaMemsetAsync(counts, 0, (2LL * C + 2LL * C * nbins) * sizeof(int), stream));
+  hd_edges_kernel<<<static_cast<unsigned>((vox + 255) / 256), 256, 0, stream>>>(logits, label, C, D, H, W, cap, coords, counts);
+  DP_CHECK(cudaGetLastError());
+  hd_dist_kernel<<<dim3(64, C, 2), 256, 0, stream>>>(coords, counts, C, cap, nbins, hist);
+  DP_CHECK(cudaGetLastError());
+  hd_percentile_kernel<<<1, 32, 0, stream>>>(hist, counts, C, cap, nbins, percentile, hd);
+  return check_cuda(cudaGetLastError(), "hd95");
 }

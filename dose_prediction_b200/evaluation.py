@@ -103,3 +103,29 @@ def dice_metric(logits, label):
     _lib.check(lib.dp_dice_metric(x.data_ptr(), lab.data_ptr(), N, C, vox, counts.data_ptr(), dice.data_ptr(), mean.data_ptr(),
                                   torch.cuda.current_stream(x.device).cuda_stream), "dp_dice_metric")
     return mean, dice
+
+
+def hd95_metric(logits, label, percentile=95.0):
+    """HausdorffDistanceMetric(include_background=False, percentile=95, reduction="mean") of one-hot(argmax(logits)) vs the label
+    map, as Transeg.validation_step / test_step compute it (OARSegmentation/train_light_transeg.py:158-166,199-216).
+    logits [N,C,D,H,W] fp32 CUDA, label [N,1,D,H,W] class indices.  Returns (mean [1], hd [N,C]) on the device; the mean
+    follows monai's do_metric_reduction(.., "mean"): NaN entries ignored, classes first, then samples."""
+    if not logits.is_cuda:
+        raise RuntimeError("dose_prediction_b200 evaluates on CUDA devices only (no CPU fallback)")
+    lib = _lib.lib()
+    x = logits.contiguous().float()
+    lab = label.to(x.device).contiguous().float()
+    N, C, D, H, W = x.shape
+    ws = torch.empty(int(lib.dp_hd95_workspace_bytes(C, D, H, W)), dtype=torch.uint8, device=x.device)
+    hd = torch.empty((N, C), device=x.device)
+    s = torch.cuda.current_stream(x.device).cuda_stream
+    with torch.cuda.device(x.device):
+        for n in range(N):
+            _lib.check(lib.dp_hd95(x[n].data_ptr(), lab[n].data_ptr(), C, D, H, W, float(percentile), ws.data_ptr(),
+                                   hd[n].data_ptr(), s), "dp_hd95")
+    f = hd[:, 1:]
+    ok = ~torch.isnan(f)
+    per = torch.where(ok, f, torch.zeros_like(f)).sum(1) / ok.sum(1).clamp_min(1)
+    has = ok.any(1)
+    mean = (per * has).sum() / has.sum().clamp_min(1)
+    return mean.reshape(1), hd

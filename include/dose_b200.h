@@ -423,6 +423,15 @@ long long dp_dvh_workspace_bytes(void);
 int dp_dvh_metrics(const float* pred, const float* gt, const float* masks, int n_struct, const int* is_target, long long vox,
                    float voxels_in_tenth_of_cc, void* workspace, float* out, float* dvh_dif, cudaStream_t stream);
 
+/* Seg validation / test metric: monai 0.7.0 HausdorffDistanceMetric(include_background=False, percentile=95) on
+ * one-hot(argmax(logits)) vs the label map for ONE volume (OARSegmentation/train_light_transeg.py:158-166,199-216):
+ * surface voxels (mask ^ binary_erosion(mask)), exact Euclidean distance to the other surface, np.percentile in both
+ * directions, the larger one.  logits [C][D][H][W] fp32, label [D][H][W] fp32 class indices, hd float[C] (class 0 = NaN;
+ * NaN when a class has no surface on either side as source, inf when only the target surface is missing).          */
+long long dp_hd95_workspace_bytes(int C, int D, int H, int W);
+int dp_hd95(const float* logits, const float* label, int C, int D, int H, int W, float percentile, void* workspace, float* hd,
+            cudaStream_t stream);
+
 /* ======================================================================== input pipeline
  * The numpy / monai transforms of DosePrediction/DataLoader/dataloader_OpenKBP_monai.py:160-243 after the files
  * are read.  dp_prepare_input: raw arrays [A][B][C] (masks uint8, NULL = structure absent; CT int16 or fp32 HU;

@@ -75,3 +75,42 @@ def dice_metric(logits, label):
         if vals:
             per_sample.append(float(np.mean(vals)))
     return float(np.mean(per_sample)) if per_sample else 0.0
+
+
+def hd95_metric(logits, label, percentile=95):
+    """monai 0.7.0 HausdorffDistanceMetric(include_background=False, percentile=95) on AsDiscrete(argmax, to_onehot) vs the
+    one-hot label (OARSegmentation/train_light_transeg.py:158-166,199-216; un-vendored monai code, restated with the same scipy
+    calls it makes): get_mask_edges (crop to the joint bounding box, mask ^ binary_erosion(mask)), get_surface_distance
+    (distance_transform_edt of the other surface's complement), np.percentile both ways, max.  Returns hd [N, C-1]."""
+    from scipy.ndimage import binary_erosion, distance_transform_edt
+    n_cls = logits.shape[1]
+    pred = logits.argmax(1)
+    lab = label[:, 0].astype(np.int64)
+    out = np.empty((logits.shape[0], n_cls - 1))
+
+    def one_way(e_src, e_dst):
+        if not np.any(e_dst):
+            dis = np.inf * np.ones_like(e_dst, dtype=np.float64)
+        else:
+            if not np.any(e_src):
+                dis = np.inf * np.ones_like(e_dst, dtype=np.float64)
+                return np.asarray(dis[e_dst])
+            dis = distance_transform_edt(~e_dst)
+        return np.asarray(dis[e_src])
+
+    for b in range(logits.shape[0]):
+        for c in range(1, n_cls):
+            sp, sg = pred[b] == c, lab[b] == c
+            if not np.any(sp | sg):
+                out[b, c - 1] = np.nan
+                continue
+            idx = np.nonzero(sp | sg)
+            box = tuple(slice(i.min(), i.max() + 1) for i in idx)
+            sp, sg = sp[box], sg[box]
+            ep, eg = binary_erosion(sp) ^ sp, binary_erosion(sg) ^ sg
+            d = []
+            for src, dst in ((ep, eg), (eg, ep)):
+                sd = one_way(src, dst)
+                d.append(np.nan if sd.shape == (0,) else np.percentile(sd, percentile))
+            out[b, c - 1] = max(d[0], d[1]) if not (np.isnan(d[0]) or np.isnan(d[1])) else np.nan
+    return out

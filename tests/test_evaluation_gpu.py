@@ -92,3 +92,27 @@ def test_dice_metric_matches_oracle():
     want = eval_ref.dice_metric(logits.numpy(), label.numpy())
     assert abs(float(mean) - want) < 1e-6
     assert torch.isnan(dice[1, 3]).item() and not torch.isnan(dice[0, 3]).item()
+
+
+def test_hd95_matches_the_scipy_restatement_of_monai():
+    """dp_hd95 (brute-force exact nearest-surface search + d^2 histogram) vs oracle/eval_ref.hd95_metric, which makes the same
+    scipy calls monai 0.7.0's HausdorffDistanceMetric makes (binary_erosion, distance_transform_edt, np.percentile)."""
+    import numpy as np
+    from dose_prediction_b200 import synth
+    from dose_prediction_b200.evaluation import hd95_metric
+    from oracle import eval_ref
+    vol = synth.make_batch(2, 48, seed=8)
+    label = synth.oar_labels(vol["oars"])
+    label[1][label[1] == 3] = 0                                   # class 3 absent from the second volume's label
+    torch.manual_seed(0)
+    onehot = torch.nn.functional.one_hot(label[:, 0].long(), 8).permute(0, 4, 1, 2, 3).float()
+    logits = 1.5 * onehot + torch.randn(2, 8, 48, 48, 48)          # noisy prediction: ragged surfaces, stray voxels
+    logits[0, 5] = -10.0                                           # class 5 never predicted in the first volume
+    mean, hd = hd95_metric(logits.to(DEV), label.to(DEV))
+    torch.cuda.synchronize()
+    want = eval_ref.hd95_metric(logits.numpy(), label.numpy())
+    got = hd[:, 1:].cpu().numpy()
+    assert np.array_equal(np.isnan(got), np.isnan(want)) and np.array_equal(np.isinf(got), np.isinf(want))
+    fin = np.isfinite(want)
+    assert fin.sum() >= 10 and np.allclose(got[fin], want[fin], rtol=1e-6, atol=1e-5)
+    assert np.isfinite(float(mean)) or np.isinf(float(mean))
