@@ -487,6 +487,293 @@ teardown:
   }
 }
 
+
+// ===================================================================================================================
+// 3^3, C_out = 16, 3-term operand split folded into N with a SPLIT-HALF column layout (fold == 2).
+//
+// Why: the folded layout above keeps [W_hi | W_lo] per ring slot, so the x_lo chunks (which only need W_hi) still issue
+// N = 128 MMAs against [W_hi | 0].  On a power-capped B200 the MMA stream's cost is its executed columns
+// (scripts/micro/mma_mix.cu: N = 128 + 128 per tap 65.4 ms, N = 128 + 64 54.0 ms for the same MMA count), so here a
+// tile's 128 TMEM columns are [x.W_hi: slot 0..3 x 16 | x_hi.W_lo: slot 0..3 x 16]: hi chunks issue N = 128 against
+// [W_hi rows | W_lo rows], lo chunks N = 64 against the W_hi rows alone.
+//
+// The ring runs over VIRTUAL planes as well: an item streams input planes z0..z1 and every input plane dz feeds ring
+// planes dz-1, dz, dz+1 whether or not they are real output planes of the item (d0 <= q < d1); the epilogue hands the
+// slots of virtual planes straight back.  Every input plane is therefore an interior plane — one full-width MMA per
+// tap and tile, no clipped windows.  A new plane's slot is not contiguous any more (16 hi + 16 lo columns), so the first
+// tap of an input plane is: two N = 16 MMAs with accumulate = 0 on the new plane's columns, then one N = 128 MMA against
+// a copy of that tap's weights whose new-plane rows are zero as well (wpack tail: one such block per rotation).  The
+// first input plane of an item overwrites the whole ring (all four slots are waited free).
+template <int TT>
+__global__ void __launch_bounds__(kStackThreads, 1)
+conv3d_stack3h_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ StackParams p) {
+  constexpr int KS = 3, pad = 1, G = 4;
+  constexpr uint32_t kTileCols = 128, kTapBytes = 32u * 128u, kTapB16 = kTapBytes >> 4;
+  constexpr size_t kChunkHalfs = 9 * 2 * 128 * 8, kFirstHalfs = 2 * 128 * 8;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  __shared__ uint64_t a_full[kMaxAStages], a_empty[kMaxAStages];
+  __shared__ uint64_t b_full[kMaxBStages], b_empty[kMaxBStages];
+  __shared__ uint64_t done_bar[G], free_bar[G];
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ float stat_acc[kStackEpiWarps][16][2];
+  __shared__ float s_scale[16], s_shift[16];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  constexpr uint32_t n_issuers = TT >= 2 ? 2 : 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_in);
+    for (int i = 0; i < p.a_stages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], n_issuers); }
+    for (int i = 0; i < p.b_stages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], n_issuers); }
+    for (int i = 0; i < G; ++i) { mbar_init(&done_bar[i], n_issuers); mbar_init(&free_bar[i], kStackEpiWarps); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(&tmem_base_smem);
+  for (int i = threadIdx.x; i < kStackEpiWarps * 16 * 2; i += kStackThreads) (&stat_acc[0][0][0])[i] = 0.f;
+  if (threadIdx.x < 16) { s_scale[threadIdx.x] = p.scale[threadIdx.x]; s_shift[threadIdx.x] = p.shift[threadIdx.x]; }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+  const size_t rot_w_halfs = kChunkHalfs * p.n_chunks;
+  const int nh = p.n_chunks >> 1;                          // chunks [0, nh): x_hi blocks, [nh, n_chunks): x_lo blocks
+
+  if (warp == 0) {
+    // ===================================================================== producer
+    int ia = 0, ib = 0;
+    uint32_t pa = 0, pb = 0;
+    uint32_t pc_base = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      const Item it = decode_item<KS>(p, item);
+      for (int dz = it.z0; dz <= it.z1; ++dz) {
+        const uint32_t rot = (pc_base + static_cast<uint32_t>(dz - it.z0)) & 3u;      // slot of ring plane dz - 1
+        for (int c = 0; c < p.n_chunks; ++c) {
+          if (!mbar_wait_relaxed(&a_empty[ia], pa ^ 1, p.err_flag)) goto teardown;
+          if (elect_one()) {
+            if (p.debug & 2) {
+              mbar_arrive(&a_full[ia]);
+            } else {
+              mbar_arrive_expect_tx(&a_full[ia], p.a_bytes);
+              tma_load_5d(smem + static_cast<size_t>(ia) * p.a_stride, &tmap_in, &a_full[ia], 0, it.w0 - pad, it.h0 - pad, dz,
+                          it.n * p.cb_total_in + p.chunk_cb[c]);
+            }
+          }
+          __syncwarp();
+          if (++ia == p.a_stages) { ia = 0; pa ^= 1; }
+          if (!mbar_wait_relaxed(&b_empty[ib], pb ^ 1, p.err_flag)) goto teardown;
+          if (elect_one()) {
+            if (p.debug & 1) {
+              mbar_arrive(&b_full[ib]);
+            } else {
+              uint8_t* sb = smem + p.b_off + static_cast<size_t>(ib) * p.b_stride;
+              mbar_arrive_expect_tx(&b_full[ib], 9u * kTapBytes + (c == 0 ? kTapBytes : 0u));
+              bulk_load_1d(sb, p.wpack + rot * rot_w_halfs + static_cast<size_t>(c) * kChunkHalfs, 9u * kTapBytes, &b_full[ib]);
+              if (c == 0) bulk_load_1d(sb + 9u * kTapBytes, p.wpack + 4 * rot_w_halfs + rot * kFirstHalfs, kTapBytes, &b_full[ib]);
+            }
+          }
+          __syncwarp();
+          if (++ib == p.b_stages) { ib = 0; pb ^= 1; }
+        }
+      }
+      pc_base += static_cast<uint32_t>(it.z1 - it.z0 + 3);
+    }
+  } else if (warp == 1 || (warp == kStackMmaWarpB && TT >= 2)) {
+    // ===================================================================== MMA issuers (see conv3d_stack_kernel)
+    constexpr int TTs = TT >= 2 ? TT / 2 : TT;
+    const int t_off = (warp == 1) ? 0 : TTs;
+    if (elect_one()) {
+      const uint32_t idesc_hi = make_idesc_f16(128, 128), idesc_lo = make_idesc_f16(128, 64), idesc_16 = make_idesc_f16(128, 16);
+      const uint32_t a_lo_c = (static_cast<uint32_t>(p.PH * p.PWw) & 0x3FFFu) << 16;
+      const uint32_t a_hi = (static_cast<uint32_t>(p.PWw) & 0x3FFFu) | (1u << 14);
+      const uint32_t b_lo_c = 128u << 16;                                 // LBO: k-half pitch = 128 rows x 16 B
+      const uint32_t b_hi = 8u | (1u << 14);
+      const uint32_t smem16 = smem_u32(smem) >> 4;
+      const uint32_t a_stride16 = p.a_stride >> 4, b_stride16 = p.b_stride >> 4, b_off16 = p.b_off >> 4;
+      const uint32_t tm0 = tmem_base + static_cast<uint32_t>(t_off) * kTileCols;
+      const uint32_t a_toff = static_cast<uint32_t>(t_off) * 8;
+      int ia = 0, ib = 0;
+      uint32_t pa = 0, pb = 0;
+      uint32_t pc_base = 0;
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+        const Item it = decode_item<KS>(p, item);
+        const int my_tiles = max(0, min(TTs, it.ntile - t_off));
+        const bool all_tiles = (my_tiles == TTs);
+        for (int dz = it.z0; dz <= it.z1; ++dz) {
+          const uint32_t pc_old = pc_base + static_cast<uint32_t>(dz - it.z0);     // ring plane dz - 1
+          const uint32_t pc_new = pc_old + 2;                                      // ring plane dz + 1
+          const bool item_start = (dz == it.z0);
+          if (item_start) {
+            for (uint32_t i = 0; i < 4; ++i) {
+              const uint32_t pc = pc_base + i;
+              if (!mbar_wait(&free_bar[pc & 3u], ((pc >> 2) & 1u) ^ 1u, p.err_flag)) goto teardown;
+            }
+          } else {
+            if (!mbar_wait(&free_bar[pc_new & 3u], ((pc_new >> 2) & 1u) ^ 1u, p.err_flag)) goto teardown;
+          }
+          tc_fence_after();
+          const uint32_t sn16 = (pc_new & 3u) * 16u;
+          for (int c = 0; c < p.n_chunks; ++c) {
+            if (!mbar_wait(&a_full[ia], pa, p.err_flag)) goto teardown;
+            if (!mbar_wait(&b_full[ib], pb, p.err_flag)) goto teardown;
+            tc_fence_after();
+            const uint32_t a_c = a_lo_c + smem16 + static_cast<uint32_t>(ia) * a_stride16 + a_toff;
+            const uint32_t b_lo = b_lo_c + smem16 + b_off16 + static_cast<uint32_t>(ib) * b_stride16;
+            const uint32_t idesc = c < nh ? idesc_hi : idesc_lo;
+            if (c == 0) {
+              // first tap of this input plane
+              for (int t = 0; t < my_tiles; ++t) {
+                const uint32_t d = tm0 + t * kTileCols, a = a_c + t * 8;
+                if (item_start) {
+                  umma_split(d, a, a_hi, b_lo, b_hi, idesc_hi, 0u);
+                } else {
+                  umma_split(d + sn16, a, a_hi, b_lo + sn16, b_hi, idesc_16, 0u);
+                  umma_split(d + 64u + sn16, a, a_hi, b_lo + 64u + sn16, b_hi, idesc_16, 0u);
+                  umma_split(d, a, a_hi, b_lo + 9u * kTapB16, b_hi, idesc_hi, 1u);
+                }
+              }
+              if (all_tiles) {
+                issue_taps<2, TTs>(tm0, kTileCols, a_c + 1, a_hi, b_lo + kTapB16, b_hi, kTapB16, idesc_hi);
+                issue_taps<3, TTs>(tm0, kTileCols, a_c + p.PWw, a_hi, b_lo + 3 * kTapB16, b_hi, kTapB16, idesc_hi);
+                issue_taps<3, TTs>(tm0, kTileCols, a_c + 2 * p.PWw, a_hi, b_lo + 6 * kTapB16, b_hi, kTapB16, idesc_hi);
+              } else {
+                for (int tap = 1; tap < 9; ++tap)
+                  for (int t = 0; t < my_tiles; ++t)
+                    umma_split(tm0 + t * kTileCols, a_c + (tap / 3) * p.PWw + (tap % 3) + t * 8, a_hi, b_lo + tap * kTapB16, b_hi, idesc_hi, 1u);
+              }
+            } else if (all_tiles) {
+#pragma unroll
+              for (int r3 = 0; r3 < 3; ++r3)
+                issue_taps<3, TTs>(tm0, kTileCols, a_c + r3 * p.PWw, a_hi, b_lo + r3 * 3 * kTapB16, b_hi, kTapB16, idesc);
+            } else {
+              for (int tap = 0; tap < 9; ++tap)
+                for (int t = 0; t < my_tiles; ++t)
+                  umma_split(tm0 + t * kTileCols, a_c + (tap / 3) * p.PWw + (tap % 3) + t * 8, a_hi, b_lo + tap * kTapB16, b_hi, idesc, 1u);
+            }
+            umma_commit(&b_empty[ib]);
+            if (++ib == p.b_stages) { ib = 0; pb ^= 1; }
+            umma_commit(&a_empty[ia]);
+            if (++ia == p.a_stages) { ia = 0; pa ^= 1; }
+          }
+          // ring planes completed by this input plane: dz - 1, and at the item's last input plane the two younger ones too
+          umma_commit(&done_bar[pc_old & 3u]);
+          if (dz == it.z1) {
+            umma_commit(&done_bar[(pc_old + 1) & 3u]);
+            umma_commit(&done_bar[(pc_old + 2) & 3u]);
+          }
+        }
+        pc_base += static_cast<uint32_t>(it.z1 - it.z0 + 3);
+      }
+    }
+  } else if (warp >= 2 && warp < 2 + kStackEpiWarps) {
+    // ===================================================================== epilogue (warps 2..9)
+    const int quarter = warp & 3;
+    const int ew = warp - 2;
+    const int tgrp = ew >> 2;
+    const int row = quarter * 32 + lane;
+    const int hl = row >> 3, wl = row & 7;
+    const int mycol = (lane >> 1) & 15;
+    const float relu_floor = p.relu ? 0.f : -INFINITY;
+    int cur_n = -1;
+    uint32_t pc = 0;
+    auto flush_stats = [&](int n) {
+      if (p.stats == nullptr || n < 0) return;
+      __syncwarp();
+      if (lane < 16) {
+        atomicAdd(&p.stats[(static_cast<size_t>(n) * 16 + lane) * 2 + 0], static_cast<double>(stat_acc[ew][lane][0]));
+        atomicAdd(&p.stats[(static_cast<size_t>(n) * 16 + lane) * 2 + 1], static_cast<double>(stat_acc[ew][lane][1]));
+        stat_acc[ew][lane][0] = 0.f;
+        stat_acc[ew][lane][1] = 0.f;
+      }
+      __syncwarp();
+    };
+    float ts1[16], ts2[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { ts1[j] = 0.f; ts2[j] = 0.f; }
+    const size_t plane = static_cast<size_t>(p.D) * p.H * p.W;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      const Item it = decode_item<KS>(p, item);
+      if (it.n != cur_n) { flush_stats(cur_n); cur_n = it.n; }
+      const int h = it.h0 + hl;
+      for (int q = it.z0 - 1; q <= it.z1 + 1; ++q, ++pc) {
+        const uint32_t slot = pc & 3u;
+        if (!mbar_wait_relaxed(&done_bar[slot], (pc >> 2) & 1u, p.err_flag)) goto teardown;
+        tc_fence_after();
+        if (q >= it.d0 && q < it.d1 && !(p.debug & 4)) {
+          for (int t = tgrp; t < it.ntile; t += 2) {
+            const int w = it.w0 + t * 8 + wl;
+            const bool valid = (h < p.H) && (w < p.W);
+            const size_t vox = (static_cast<size_t>(q) * p.H + h) * p.W + w;
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(t) * kTileCols + slot * 16u;
+            uint32_t r[16], r2[16];
+            tmem_ld16(taddr, r);
+            tmem_ld16(taddr + 64u, r2);
+            tmem_ld_wait();
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float x = fmaf(__uint_as_float(r[j]) + __uint_as_float(r2[j]), s_scale[j], s_shift[j]);
+              v[j] = fmaxf(x, relu_floor);
+            }
+            if (valid) {
+              if (p.stats != nullptr) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { ts1[j] += v[j]; ts2[j] = fmaf(v[j], v[j], ts2[j]); }
+              }
+#pragma unroll
+              for (int b = 0; b < 2; ++b) {
+                const size_t cb = static_cast<size_t>(it.n) * p.cb_total_out + p.cb_out_off + b;
+                const size_t off = (cb * plane + vox) * 8;
+                if (p.out_f32 != nullptr) {
+                  float y8[8];
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) y8[j] = v[b * 8 + j];
+                  st_global_v8f(p.out_f32 + off, y8);
+                }
+                if (p.out_hi != nullptr) {
+                  __align__(16) __half hi[8];
+                  __align__(16) __half lo[8];
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) {
+                    hi[j] = __float2half_rn(v[b * 8 + j]);
+                    lo[j] = __float2half_rn(v[b * 8 + j] - __half2float(hi[j]));
+                  }
+                  *reinterpret_cast<uint4*>(p.out_hi + off) = *reinterpret_cast<const uint4*>(hi);
+                  if (p.out_lo != nullptr) *reinterpret_cast<uint4*>(p.out_lo + off) = *reinterpret_cast<const uint4*>(lo);
+                }
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&free_bar[slot]);
+      }
+      if (p.stats != nullptr) {          // cross-lane reduction of the item's per-thread partial sums
+        float a[16], b[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { a[j] = ts1[j]; b[j] = ts2[j]; ts1[j] = 0.f; ts2[j] = 0.f; }
+        const float s1 = colsum16s(a, lane);
+        const float s2 = colsum16s(b, lane);
+        if ((lane & 1) == 0) {
+          stat_acc[ew][mycol][0] += s1;
+          stat_acc[ew][mycol][1] += s2;
+        }
+      }
+    }
+    flush_stats(cur_n);
+  }
+
+teardown:
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
 }  // namespace dp
 
 extern "C" int dp_conv3d_stack(const void* in_c8, int cb_total_in, const uint8_t* chunk_cb, int n_chunks,
@@ -497,13 +784,13 @@ extern "C" int dp_conv3d_stack(const void* in_c8, int cb_total_in, const uint8_t
   using namespace dp;
   DP_REQUIRE(k == 3 || k == 7, "dp_conv3d_stack: kernel size %d unsupported (3 or 7)", k);
   DP_REQUIRE(cout == 16 || (cout == 32 && !fold), "dp_conv3d_stack: C_out=%d unsupported (16, or 32 without fold)", cout);
-  const int cout_out = cout;
+  DP_REQUIRE(fold >= 0 && fold <= 2 && (fold != 2 || (k == 3 && n_chunks % 2 == 0)), "dp_conv3d_stack: fold=%d needs k=3 and hi+lo chunks", fold);
+  const bool split_half = (fold == 2);           // conv3d_stack3h_kernel: [W_hi | W_lo] halves of a tile's 128 columns
   cout = fold ? 2 * cout : cout;                 // MMA columns per ring slot
   DP_REQUIRE(n_chunks >= 1 && n_chunks <= 96, "dp_conv3d_stack: n_chunks=%d out of range", n_chunks);
   DP_REQUIRE(out_f32 != nullptr || out_hi != nullptr, "dp_conv3d_stack: no output tensor given");
   StackParams p{};
   p.N = N; p.D = D; p.H = H; p.W = W; p.n_chunks = n_chunks; p.cb_total_in = cb_total_in; p.cout = cout; p.fold = fold ? 1 : 0;
-  (void)cout_out;
   for (int i = 0; i < n_chunks; ++i) p.chunk_cb[i] = chunk_cb[i];
   p.tiles_h = (H + 15) / 16;
   p.tiles_w = (W + 7) / 8;
@@ -545,7 +832,7 @@ extern "C" int dp_conv3d_stack(const void* in_c8, int cb_total_in, const uint8_t
   if (p.tps < 1) p.tps = 1;
   if (p.tps > k * k) p.tps = k * k;
   p.n_bst = (k * k + p.tps - 1) / p.tps;
-  p.b_bytes = static_cast<uint32_t>(p.tps) * tap_b;
+  p.b_bytes = static_cast<uint32_t>(p.tps + (split_half ? 1 : 0)) * tap_b;     // split-half: + the first-tap block
   p.b_stride = ((p.b_bytes + 1023u) / 1024u) * 1024u;
   p.a_stages = 3;
   p.b_off = p.a_stages * p.a_stride;
@@ -571,7 +858,8 @@ extern "C" int dp_conv3d_stack(const void* in_c8, int cb_total_in, const uint8_t
   const size_t smem = static_cast<size_t>(p.b_off) + static_cast<size_t>(p.b_stages) * p.b_stride + 1024;
   typedef void (*KernelFn)(const CUtensorMap, const StackParams);
   KernelFn fn = nullptr;
-  if (k == 3) fn = T == 4 ? conv3d_stack_kernel<3, 4> : (T == 2 ? conv3d_stack_kernel<3, 2> : conv3d_stack_kernel<3, 1>);
+  if (split_half) fn = T == 4 ? conv3d_stack3h_kernel<4> : (T == 2 ? conv3d_stack3h_kernel<2> : conv3d_stack3h_kernel<1>);
+  else if (k == 3) fn = T == 4 ? conv3d_stack_kernel<3, 4> : (T == 2 ? conv3d_stack_kernel<3, 2> : conv3d_stack_kernel<3, 1>);
   else fn = T == 4 ? conv3d_stack_kernel<7, 4> : (T == 2 ? conv3d_stack_kernel<7, 2> : conv3d_stack_kernel<7, 1>);
   if (first_use_on_device(KF_CONV_STACK)) {
     const int max_smem = 212 * 1024;
@@ -581,6 +869,9 @@ extern "C" int dp_conv3d_stack(const void* in_c8, int cb_total_in, const uint8_t
     DP_CHECK(cudaFuncSetAttribute(conv3d_stack_kernel<7, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     DP_CHECK(cudaFuncSetAttribute(conv3d_stack_kernel<7, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     DP_CHECK(cudaFuncSetAttribute(conv3d_stack_kernel<7, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    DP_CHECK(cudaFuncSetAttribute(conv3d_stack3h_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    DP_CHECK(cudaFuncSetAttribute(conv3d_stack3h_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    DP_CHECK(cudaFuncSetAttribute(conv3d_stack3h_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   }
   int grid = sms < p.num_items ? sms : p.num_items;
   fn<<<grid, kStackThreads, smem, stream>>>(tmap, p);

@@ -190,7 +190,11 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer (warp-uniform loop, one elected lane issues)
-    const uint32_t idesc = make_idesc_f16(128, p.cout);
+    const uint32_t idesc_full = make_idesc_f16(128, p.cout);
+    // folded 3-term split: chunks [n_chunks/2, n_chunks) are the x_lo blocks, which only need the W_hi half of the columns
+    // (executed MMA columns are what a power-capped B200 charges for: scripts/micro/mma_mix.cu)
+    const uint32_t idesc_lo = p.fold ? make_idesc_f16(128, p.cout >> 1) : idesc_full;
+    const int first_lo_chunk = p.fold ? (p.n_chunks >> 1) : p.n_chunks;
     // descriptor halves: lo = start>>4 | LBO>>4 << 16 ; hi = SBO>>4 | version(1) << 14 | layout(0) << 29
     const uint32_t a_lo_c = (static_cast<uint32_t>(p.kd_s * p.PHs * p.PW) & 0x3FFFu) << 16;   // LBO = c8-block pitch
     const uint32_t a_hi = (static_cast<uint32_t>(p.PW) & 0x3FFFu) | (1u << 14);               // SBO = patch row pitch
@@ -221,6 +225,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
               const uint32_t sa16 = smem_u32(smem + static_cast<size_t>(stage) * p.stage_bytes) >> 4;
               uint32_t b16 = sa16 + (p.a_bytes_al >> 4);
               const uint32_t mask = p.tap_mask[c];
+              const uint32_t idesc = c < first_lo_chunk ? idesc_full : idesc_lo;
               for (int kdl = 0; kdl < p.kd_s; ++kdl) {
                 for (int khl = 0; khl < cnt; ++khl) {
                   uint32_t a16 = sa16 + static_cast<uint32_t>((kdl * p.PHs + khl * p.dil) * p.PW);

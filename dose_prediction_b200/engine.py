@@ -26,6 +26,7 @@ FOLD_P3 = os.environ.get("DP_FOLD_P3", "1") != "0"
 CONV_C1 = os.environ.get("DP_CONV_C1", "1") != "0"              # bring-up switch: one-channel 3^3 conv + closed-form residual (seg encoder1)
 POINTWISE_TCK = os.environ.get("DP_POINTWISE_TCK", "1") != "0"  # bring-up switch: 1^3 convs on tcgen05 with normalise-on-load
 FUSE_HEADS = os.environ.get("DP_FUSE_HEADS", "1") != "0"         # bring-up switch: 1^3 heads folded into the producing norm_act
+STACK_SPLIT_HALF = os.environ.get("DP_STACK_SPLIT_HALF", "1") != "0"   # bring-up switch: split-half folded 3^3 stacked conv
 FOLD_TC_MAX = int(os.environ.get("DP_FOLD_TC_MAX", "32"))        # plain tcgen05 conv: fold [W_hi | W_lo] into N up to this C_out
 POINTWISE_CW = os.environ.get("DP_POINTWISE_CW", "1") != "0"     # bring-up switch: constant-bank weights for static 1^3 convs
 POINTWISE_TC = os.environ.get("DP_POINTWISE_TC", "1") != "0"    # bring-up switch: wide coarse-level 1^3 convs on the tensor cores
@@ -373,7 +374,7 @@ class Plan:
             self.run()
 
     # ------------------------------------------------------------------ weight packing
-    def pack_conv_tc(self, w, parts, mode, stacked=False, _values_only=False):
+    def pack_conv_tc(self, w, parts, mode, stacked=False, _values_only=False, split_half=False):
         """w [Co,Ci,k,k,k] fp32 (or a function returning it) -> fp16 [kd][chunk][kh][kw][2][Co][8] + per-chunk
         input block table.  mode p1: x_hi.W_hi;  p2: + x_lo.W_hi;  p3: + x_hi.W_lo  (operand splitting by K expansion)."""
         w_src = w
@@ -414,7 +415,18 @@ class Plan:
             for r in range(G):
                 idx = torch.tensor([(sl - r) % G for sl in range(G)], device=self.device)
                 rots.append(Z.index_select(4, idx).permute(1, 5, 6, 2, 4, 0, 3))
-            W = torch.stack(rots, dim=0).contiguous().half()
+            W = torch.stack(rots, dim=0).contiguous()
+            if split_half:
+                # conv3d_stack3h_kernel (k = 3, fold): a tap's 128 rows are [W_hi: slot 0..3 x 16 | W_lo: slot 0..3 x 16]
+                # instead of [W_hi | W_lo] per slot; tail = per rotation tap (0,0) of chunk 0 with the rows of the newest
+                # ring plane (slot r + 2) zeroed as well (the first tap of an input plane, see the kernel header)
+                assert k == 3 and Co == 32 and mode == "p3f"
+                W = W.view(G, nch, k, k, 2, G, 2, 16, 8).permute(0, 1, 2, 3, 4, 6, 5, 7, 8).contiguous()
+                first = W[:, 0, 0, 0].clone()                          # [rot][khalf][half][slot][16][8]
+                for r in range(G):
+                    first[r, :, :, (r + 2) % G] = 0
+                W = torch.cat((W.reshape(-1), first.reshape(-1)))
+            W = W.half()
         else:         # [kd][chunk][kh][kw][khalf][co][e]
             W = W.permute(4, 1, 5, 6, 2, 0, 3).contiguous().half()
         if _values_only:
@@ -433,7 +445,8 @@ class Plan:
                 self.refresh_launches.append(("dp_pack_conv_weight", (w_src.param.data_ptr(), Co, Ci, k, int(w_src.transpose_flip),
                                                                       *arrs, nch, int(stacked), W.data_ptr())))
             else:
-                self.refresh.append((W, lambda: self.pack_conv_tc(w_src, parts, mode, stacked, _values_only=True)))
+                self.refresh.append((W, lambda: self.pack_conv_tc(w_src, parts, mode, stacked, _values_only=True,
+                                                                  split_half=split_half)))
         assert max(chunks) < 256
         arr = (ctypes.c_uint8 * nch)(*chunks)
         self.keep.append(arr)
@@ -474,8 +487,11 @@ class Plan:
         Co = wshape[0]
         stacked = STACKED_CONV and dil == 1 and k in (3, 7) and Co in (16, 32) and tap_mask_fn is None
         fold = stacked and mode == "p3" and Co == 16 and FOLD_P3
+        if fold and k == 3 and STACK_SPLIT_HALF:
+            fold = 2                    # split-half column layout: x_lo chunks issue N = 64 (conv3d_stack3h_kernel)
         fold_tc = (not stacked) and mode == "p3" and Co <= FOLD_TC_MAX and FOLD_P3
-        wp, chunks, nch = self.pack_conv_tc(weight, parts, "p3f" if (fold or fold_tc) else mode, stacked=stacked)
+        wp, chunks, nch = self.pack_conv_tc(weight, parts, "p3f" if (fold or fold_tc) else mode, stacked=stacked,
+                                            split_half=(fold == 2))
         if out_raw is not None:
             of32, ohi, olo, cbt, cbo = out_raw.t.data_ptr(), None, None, out_raw.cb_total, 0
             st = out_raw.stats if stats is None else stats

@@ -73,7 +73,11 @@ int dp_conv3d_tc(const void* in_c8, int cb_total_in, const uint8_t* chunk_cb, in
  *   seg_len      output planes per work item along D (0 = choose for load balance)
  *   tiles_per_cta  adjacent W tiles sharing one weight stream (0 = default)
  *   fold         1 (cout == 16): weights carry 2*cout rows per slot ([W_hi | W_lo] for hi chunks, [W_hi | 0] for
- *                lo chunks); the epilogue adds the two halves — the 3-term operand split in 2 MMAs per chunk  */
+ *                lo chunks); the epilogue adds the two halves — the 3-term operand split in 2 MMAs per chunk
+ *                2 (cout == 16, k == 3; chunks = x_hi blocks then x_lo blocks): split-half layout, wpack_stack fp16
+ *                [4 rotations][n_chunks][kh][kw][2][W_hi rows: 4 slots x 16 | W_lo rows: 4 slots x 16][8] followed by
+ *                [4 rotations][2][128][8] = tap (0,0) of chunk 0 with the newest plane's rows zeroed too; x_lo chunks
+ *                issue N = 64 (the W_hi rows) instead of N = 128 against a zero half                               */
 int dp_conv3d_stack(const void* in_c8, int cb_total_in, const uint8_t* chunk_cb, int n_chunks, const void* wpack_stack,
                     int N, int D, int H, int W, int cout, int k, const float* scale, const float* shift, int relu,
                     float* out_f32, void* out_hi, void* out_lo, int cb_total_out, int cb_out_off, double* stats,

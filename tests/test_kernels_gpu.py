@@ -50,7 +50,10 @@ def _act_from(P, x, lo):
     (64, 64, 3, 1, (8, 16, 16), "p1"),
     (128, 256, 3, 1, (4, 8, 8), "p1"),          # H < 16 (masked rows), N = 256
     (16, 16, 3, 2, (12, 16, 16), "p1"),         # dilation 2
-    (9, 16, 3, 1, (16, 16, 16), "p3"),          # padded input channels + 3-term operand split
+    (9, 16, 3, 1, (16, 16, 16), "p3"),          # padded input channels + 3-term operand split (split-half stacked kernel)
+    (32, 16, 3, 1, (9, 20, 40), "p3"),          # split-half stacked: 4 chunks, ragged H, a partial W-tile group (5 tiles)
+    (16, 16, 3, 1, (1, 16, 16), "p3"),          # split-half stacked: a single plane (item start == item end)
+    (16, 16, 3, 1, (2, 8, 8), "p3"),            # split-half stacked: one tile per CTA, masked rows
     (32, 32, 3, 1, (8, 16, 8), "p2"),
     (32, 32, 3, 2, (8, 16, 16), "p3"),          # plain kernel, [W_hi | W_lo] folded into N (C_out <= 32)
     (16, 32, 5, 1, (6, 12, 20), "p3"),          # folded, k = 5, ragged tiles
@@ -82,6 +85,36 @@ def test_conv3d_tc_matches_torch(cin, cout, k, dil, dims, mode):
     st = raw.stats.view(N, cout, 2).cpu()
     assert torch.allclose(st[..., 0], want.sum((2, 3, 4)), rtol=1e-4, atol=1e-2)
     assert torch.allclose(st[..., 1], (want ** 2).sum((2, 3, 4)), rtol=1e-4, atol=1e-2)
+
+
+def test_conv3d_stack_split_half_many_items_per_cta_and_old_layout(monkeypatch):
+    """more work items than SMs (the ring's plane counter carries over from item to item), hi/lo fp16 output with ReLU,
+    and the slot-major folded layout (DP_STACK_SPLIT_HALF=0) giving the same numbers"""
+    from dose_prediction_b200 import engine
+    torch.manual_seed(3)
+    dev = torch.device("cuda:0")
+    N, C, dims = 5, 16, (8, 128, 128)
+    x = torch.randn(N, C, *dims, device=dev)
+    w = torch.randn(C, C, 3, 3, 3, device=dev) / (C * 27) ** 0.5
+    bias = torch.randn(C, device=dev) * 0.1
+    outs = []
+    for split in (True, False):
+        monkeypatch.setattr(engine, "STACK_SPLIT_HALF", split)
+        P = _plan()
+        a = _act_from(P, x, lo=True)
+        out = P.new_act(N, C, dims, lo=True)
+        st = P.new_stats(N, C)
+        P.conv_tc([a], w, 3, 1, "p3", *P.affine(C, bias=bias), True, out_act=out, stats=st)
+        y = torch.zeros(N, C, *dims, device=dev)
+        P.unpack(out, y)
+        P.run()
+        _finish(P)
+        outs.append((y, st.view(N, C, 2).clone()))
+    want = F.relu(F.conv3d(x.double(), w.double(), bias.double(), padding=1))
+    for y, st in outs:
+        assert _rel(y, want) < 2e-5
+        assert torch.allclose(st[..., 0], want.sum((2, 3, 4)), rtol=1e-4, atol=1e-1)
+    assert _rel(outs[0][0], outs[1][0]) < 1e-6
 
 
 def test_conv3d_tc_concat_parts_bn_fold_relu_fp16_out():
