@@ -58,7 +58,8 @@ _SIGNATURES = {
     "dp_deconv2x_bwd_data": [I, P, P, P, P, I, I, I, P, I, I, I, I, I, P, I, I, P, P],
     "dp_head_bwd": [P, P, P, I, I, I, P, I, L, P, I, I, P, P, P],
     "dp_masked_l1": [P, P, I, I, I, P, I, F, P, P],
-    "dp_genloss_finalize": [P, I, F, F, P, P],
+    "dp_genloss_finalize": [P, I, F, F, P, F, P, P],
+    "dp_lerp2x_bwd": [P, L, I, L, P, P],
     "dp_dice_ce": [P, I, P, I, I, L, P, I, F, P, I, P],
     "dp_dice_ce_finalize": [P, I, I, L, P, P],
     "dp_adamw": [P, P, P, P, L, F, F, F, F, F, I, F, P, P],

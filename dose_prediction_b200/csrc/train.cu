@@ -624,12 +624,48 @@ __global__ void __launch_bounds__(256) masked_l1_kernel(const float* pred, const
   }
 }
 // loss = delta1 * L1(full) + delta2 * mean_i L1(scale i)   (loss.py:96-112)
-__global__ void genloss_finalize_kernel(const double* acc, int n_scales, float delta1, float delta2, float* loss) {
+__global__ void genloss_finalize_kernel(const double* acc, int n_scales, float delta1, float delta2, const double* acc_a,
+                                        float weight_a, float* loss) {
   double l = delta1 * acc[0] / acc[1];
+  if (acc_a != nullptr) l += weight_a * acc_a[0] / acc_a[1];          // casecade and not freez: + 0.5 * L1(pred_A) (loss.py:114-115)
   double ds = 0.0;
   for (int i = 1; i < n_scales; ++i) ds += acc[2 * i] / acc[2 * i + 1];
   if (n_scales > 1) l += delta2 * ds / (n_scales - 1);
   *loss = static_cast<float>(l);
+}
+
+// ------------------------------------------------------------------ adjoint of the 2x linear interpolation along one axis
+// F.interpolate(scale_factor=2, mode='trilinear', align_corners=True) (c3d.py:36) is separable; its backward is three of
+// these passes (D, H, W).  g [outer][2L][inner][8] fp32 -> out [outer][L][inner][8]:
+//   out[i] = sum_o g[o] * ((i0(o) == i) * (1 - l(o)) + (i1(o) == i) * l(o)),  src(o) = o (L-1)/(2L-1), i0 = floor(src),
+//   i1 = min(i0 + 1, L - 1), l = src - i0 — the forward kernel's float arithmetic, so this is its exact transpose.
+// Gather form (deterministic): only o in [2i-2, 2i+3] can reach input i.
+__global__ void __launch_bounds__(256) lerp2x_bwd_kernel(const float* __restrict__ g, long long outer, int L, long long inner,
+                                                         float* __restrict__ out) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= outer * L * inner) return;
+  const long long in_ = idx % inner;
+  const int i = static_cast<int>((idx / inner) % L);
+  const long long o_ = idx / (inner * L);
+  const int Lo = 2 * L;
+  const float s = Lo > 1 ? static_cast<float>(L - 1) / static_cast<float>(Lo - 1) : 0.f;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  const int o_lo = max(0, 2 * i - 2), o_hi = min(Lo - 1, 2 * i + 3);
+  for (int o = o_lo; o <= o_hi; ++o) {
+    const float f = s * o;
+    const int i0 = static_cast<int>(f), i1 = min(i0 + 1, L - 1);
+    const float l = f - i0;
+    const float wgt = (i0 == i ? 1.f - l : 0.f) + (i1 == i ? l : 0.f);
+    if (wgt != 0.f) {
+      float x[8];
+      ld_global_v8f(g + ((o_ * Lo + o) * inner + in_) * 8, x);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(wgt, x[j], acc[j]);
+    }
+  }
+  st_global_v8f(out + idx * 8, acc);
 }
 
 // ------------------------------------------------------------------ fused AdamW over a flat parameter buffer
@@ -1183,9 +1219,15 @@ extern "C" int dp_masked_l1(const float* pred, const float* gt, int N, int S, in
   return check_cuda(cudaGetLastError(), "masked_l1");
 }
 
-extern "C" int dp_genloss_finalize(const double* acc, int n_scales, float delta1, float delta2, float* loss,
-                                   cudaStream_t stream) {
-  genloss_finalize_kernel<<<1, 1, 0, stream>>>(acc, n_scales, delta1, delta2, loss);
+extern "C" int dp_lerp2x_bwd(const float* g, long long outer, int len_in, long long inner, float* out, cudaStream_t stream) {
+  DP_REQUIRE(outer > 0 && len_in > 0 && inner > 0, "lerp2x_bwd: empty tensor");
+  lerp2x_bwd_kernel<<<nblk(outer * len_in * inner, 256), 256, 0, stream>>>(g, outer, len_in, inner, out);
+  return check_cuda(cudaGetLastError(), "lerp2x_bwd");
+}
+
+extern "C" int dp_genloss_finalize(const double* acc, int n_scales, float delta1, float delta2, const double* acc_a,
+                                   float weight_a, float* loss, cudaStream_t stream) {
+  genloss_finalize_kernel<<<1, 1, 0, stream>>>(acc, n_scales, delta1, delta2, acc_a, weight_a, loss);
   return check_cuda(cudaGetLastError(), "genloss_finalize");
 }
 

@@ -101,21 +101,21 @@ class TrainPlan(Plan):
         return self.zeros((n,), torch.float32).fill_(1.0)
 
     # ------------------------------------------------------------------ differentiable emitters
-    def t_conv(self, parts, conv, k, dil=1, need_dgrad=True):
-        """nn.Conv3d (stride 1) on fp16 operands -> Raw (+ instance statistics).  Backward: wgrad + dgrad."""
+    def t_conv(self, parts, conv, k, dil=1, need_dgrad=True, mode="p1"):
+        """nn.Conv3d (stride 1) on fp16 operands (mode p3: the 3-term hi/lo operand split of the inference recipe, for
+        net_A) -> Raw (+ instance statistics).  Backward: wgrad + dgrad, both on fp16 operands."""
         a0 = parts[0]
         N, dims = a0.N, a0.dims
         w = conv.weight
         Co, Ci = w.shape[0], w.shape[1]
         raw = self.get_raw(N, Co, dims)
         shift = conv.bias if conv.bias is not None else self.zeros((Co,), torch.float32)
-        self.conv_tc(parts, LiveWeight(w), k, dil, "p1", self.ones(Co), shift.detach(), False, out_raw=raw)
+        self.conv_tc(parts, LiveWeight(w), k, dil, mode, self.ones(Co), shift.detach(), False, out_raw=raw)
 
         def bwd():
             g16 = self.raw_grad.pop(raw.t.data_ptr())
             self.conv_wgrad(parts, g16, w, k, dil)
-            if need_dgrad:
-                assert Ci % 16 == 0
+            if need_dgrad and Ci % 16 == 0:
                 graw = self.new_graw(N, Ci, dims)
                 self.conv_tc([g16], LiveWeight(w, transpose_flip=True), k, dil, "p1", self.ones(Ci),
                              self.zeros((Ci,), torch.float32), False, out_raw=graw)
@@ -123,12 +123,33 @@ class TrainPlan(Plan):
                 for a in parts:
                     self.add_act_grad(a, (graw.t, graw.cb_total, off // 8))
                     off += a.C
+            elif need_dgrad:
+                # cat(net_A output, 9 network-input channels): only the leading parts that fill whole 16-channel chunks
+                # carry a gradient (the network input needs none) — a dgrad conv over that slice of the weight
+                lead, c0 = [], 0
+                for a in parts:
+                    if a.C % 16:
+                        break
+                    lead.append(a)
+                    c0 += a.C
+                assert lead, "data gradient requested for an input without whole 16-channel parts"
+                graw = self.new_graw(N, c0, dims)
+                self.conv_tc([g16], lambda: w.detach()[:, :c0].flip(2, 3, 4).transpose(0, 1), k, dil, "p1", self.ones(c0),
+                             self.zeros((c0,), torch.float32), False, out_raw=graw)
+                off = 0
+                for a in lead:
+                    self.add_act_grad(a, (graw.t, graw.cb_total, off // 8))
+                    off += a.C
         self.tape.append(bwd)
         return raw
 
-    def conv_wgrad(self, parts, g16, w, k, dil):
+    def conv_wgrad(self, parts, g16, w, k, dil, out=None):
+        """dW of a stride-1 conv into the flat gradient slot of `w`, or (out given: a [Co, Ci, k, k, k] fp32 tensor whose
+        shape stands in for the weight's) into `out` — the space-to-depth form of a stride-2 conv."""
         a0 = parts[0]
         D, H, W = a0.dims
+        if out is not None:
+            w = out
         Co, Ci = w.shape[0], w.shape[1]
         cbs, ci0, nci, base = [], [], [], 0
         for a in parts:
@@ -158,10 +179,102 @@ class TrainPlan(Plan):
             self.count_flops("dp_conv3d_wgrad", flops)
             self.add("dp_conv3d_wgrad", a0.buf.data_ptr(), a0.cb_total, *arrs, len(cbs), g16.buf.data_ptr(), g16.cb_total,
                      g16.cb_off, a0.N, D, H, W, Ci, Co, k, dil, ws.data_ptr(), splits)
-        self.add("dp_splitk_reduce", ws.data_ptr(), splits, 1, w.numel(), None, None, 0, self.grad(w).data_ptr())
+        self.add("dp_splitk_reduce", ws.data_ptr(), splits, 1, w.numel(), None, None, 0,
+                 (out if out is not None else self.grad(w)).data_ptr())
 
-    def t_norm(self, src, out, act=None, res=None, act_after_res=None, bn=None, stats=None, stats_out=None, identity=False):
-        """InstanceNorm3d (or train-mode BatchNorm3d `bn`) + activation (+ residual) -> out Act.
+    def t_conv_s2(self, s2d_in, src_act, conv, mode="p3"):
+        """nn.Conv3d k3 s2 p1 (c3d.py:49-61) as the tap-masked stride-1 conv over the space-to-depth copy `s2d_in` (8*C
+        channels at half resolution, written by the producing norm pass) of `src_act` -> Raw.  Backward: the weight
+        gradient of the virtual [Co, 8C, 3,3,3] weight on the tensor cores, of which the 27 real taps are gathered; the data
+        gradient as a dense conv producing the space-to-depth gradient, scattered back to full resolution."""
+        w = conv.weight
+        Co, C = w.shape[0], w.shape[1]
+        N, dims = s2d_in.N, s2d_in.dims
+        vox = dims[0] * dims[1] * dims[2]
+        _, class_masks = nw._s2d_weight(w.detach())
+        raw = self.get_raw(N, Co, dims)
+        shift = conv.bias if conv.bias is not None else self.zeros((Co,), torch.float32)
+        fn = nw._S2DMask(C, class_masks, 2.0 * N * vox * 27 * C * Co)
+        self.conv_tc([s2d_in], lambda: nw._s2d_weight(w.detach())[0], 3, 1, mode, self.ones(Co), shift.detach(), False,
+                     out_raw=raw, tap_mask_fn=fn)
+
+        def bwd():
+            g16 = self.raw_grad.pop(raw.t.data_ptr())
+            dws = self.zeros((Co, 8 * C, 3, 3, 3), torch.float32)
+            self.conv_wgrad([s2d_in], g16, None, 3, 1, out=dws)
+            gw = self.grad(w)
+            taps = [(cls, td, th, tw, kd, kh, kw) for cls in range(8)
+                    for td, kd in nw._S2D_TAPS[(cls >> 2) & 1] for th, kh in nw._S2D_TAPS[(cls >> 1) & 1]
+                    for tw, kw in nw._S2D_TAPS[cls & 1]]
+
+            def gather():
+                v = dws.view(Co, 8, C, 3, 3, 3)
+                for cls, td, th, tw, kd, kh, kw in taps:
+                    gw[:, :, kd, kh, kw].copy_(v[:, cls, :, td, th, tw])
+            self.add_py(gather)
+            # the dense dgrad conv has 8*C output channels; the tcgen05 conv takes at most 256 per launch
+            nsl = max(1, (8 * C) // 256)
+            per = 8 * C // nsl
+            cps = per // C                                     # parity classes per slice
+            gss = []
+            for j in range(nsl):
+                gs = self.new_graw(N, per, dims)
+                self.conv_tc([g16], lambda j=j: nw._s2d_weight(w.detach())[0].flip(2, 3, 4).transpose(0, 1)[j * per:(j + 1) * per],
+                             3, 1, "p1", self.ones(per), self.zeros((per,), torch.float32), False, out_raw=gs)
+                gss.append(gs)
+            gr = self.new_graw(N, C, src_act.dims)
+
+            def depth_to_space():
+                dst = gr.t.view(N, C // 8, dims[0], 2, dims[1], 2, dims[2], 2, 8)
+                for j, gs in enumerate(gss):
+                    v = gs.t.view(N, cps, C // 8, dims[0], dims[1], dims[2], 8)
+                    for q in range(cps):
+                        cls = j * cps + q
+                        dst[:, :, :, (cls >> 2) & 1, :, (cls >> 1) & 1, :, cls & 1].copy_(v[:, q])
+            self.add_py(depth_to_space)
+            self.add_act_grad(src_act, (gr.t, gr.cb_total, 0))
+        self.tape.append(bwd)
+        return raw
+
+    def t_upsample(self, src, out):
+        """F.interpolate(scale_factor=2, mode='trilinear', align_corners=True) (c3d.py:36); backward = its transpose, three
+        separable gather passes (dp_lerp2x_bwd)."""
+        self.upsample2x(src, out)
+
+        def bwd():
+            dy = self.act_grads.pop(self._key(out))
+            N, ncb = src.N, blocks16(src.C)
+            D, H, W = src.dims
+            g = self.sum_sources(dy, N, ncb, 8 * src.vox)
+            t1 = self.zeros((N, ncb, D, 2 * H, 2 * W, 8), torch.float32)
+            t2 = self.zeros((N, ncb, D, H, 2 * W, 8), torch.float32)
+            gr = self.new_graw(N, src.C, src.dims)
+            self.add("dp_lerp2x_bwd", g.data_ptr(), N * ncb, D, 4 * H * W, t1.data_ptr())
+            self.add("dp_lerp2x_bwd", t1.data_ptr(), N * ncb * D, H, 2 * W, t2.data_ptr())
+            self.add("dp_lerp2x_bwd", t2.data_ptr(), N * ncb * D * H, W, 1, gr.t.data_ptr())
+            self.add_act_grad(src, (gr.t, gr.cb_total, 0))
+        self.tape.append(bwd)
+
+    def sum_sources(self, srcs, N, ncb, vox):
+        """the gradient contributions [(fp32 c8 tensor, cb_total, cb_off)] of one ncb-block activation as ONE contiguous
+        fp32 tensor [N][ncb][vox][8] (a single full-tensor contribution is used in place)"""
+        t0, cbt0, off0 = srcs[0]
+        if len(srcs) == 1 and off0 == 0 and cbt0 == ncb:
+            return t0
+        views = [t.view(N, cbt, -1)[:, off:off + ncb] for t, cbt, off in srcs]
+        dst = self.zeros((N, ncb, vox * 8), torch.float32)
+
+        def run():
+            torch.add(views[0], views[1], out=dst) if len(views) > 1 else dst.copy_(views[0])
+            for v in views[2:]:
+                dst.add_(v)
+        self.add_py(run)
+        return dst
+
+    def t_norm(self, src, out, act=None, res=None, act_after_res=None, bn=None, stats=None, stats_out=None, identity=False,
+               affine=None, s2d=None):
+        """InstanceNorm3d (affine: an nn.InstanceNorm3d(affine=True) whose weight / bias train, c3d.py:17) or train-mode
+        BatchNorm3d `bn` + activation (+ residual) -> out Act (+ its space-to-depth copy s2d).
         identity=True: no normalisation (the block output is the raw conv output, OldModels conv_3_1)."""
         if isinstance(src, Raw):
             N, C = src.t.shape[0], src.C
@@ -175,11 +288,15 @@ class TrainPlan(Plan):
             self.add("dp_batch_combine", st.data_ptr(), N, C, 2, vox, bn.running_mean.data_ptr(), bn.running_var.data_ptr(),
                      float(bn.momentum))
             gamma, beta = bn.weight.detach(), bn.bias.detach()
+        elif affine is not None:
+            gamma, beta = affine.weight.detach(), affine.bias.detach()
         self.norm_act(src, out, stats=st, gamma=gamma, beta=beta, act=act, res=res, act_after_res=act_after_res,
-                      stats_out=stats_out, identity=identity)
+                      stats_out=stats_out, identity=identity, s2d=s2d)
 
         def bwd():
             dy = self.act_grads.pop(self._key(out))
+            if len(dy) > 3:                   # net_A's output with freeze=False: head, res-block convs, patch embedding
+                dy = [(self.sum_sources(dy, N, blocks16(C), vox), blocks16(C), 0)]
             bsum = self.zeros((N * C * 6,), torch.float64)
             self.add_zero(bsum)
             if isinstance(src, Raw):
@@ -221,9 +338,10 @@ class TrainPlan(Plan):
             if bn is not None:
                 self.add("dp_batch_combine", bsum.data_ptr(), N, C, 6, vox, None, None, 0.0)
             self.add("dp_norm_act_bwd", *common, bsum.data_ptr(), 1, *tail)
-            if bn is not None:
-                self.add("dp_affine_grad", bsum.data_ptr(), N, C, self.grad(bn.weight).data_ptr(),
-                         self.grad(bn.bias).data_ptr(), 1.0)
+            if bn is not None or affine is not None:
+                mod = bn if bn is not None else affine
+                self.add("dp_affine_grad", bsum.data_ptr(), N, C, self.grad(mod.weight).data_ptr(),
+                         self.grad(mod.bias).data_ptr(), 1.0)
         self.tape.append(bwd)
 
     def t_pointwise(self, srcs, conv, need_dgrad=True):
@@ -332,8 +450,9 @@ class TrainPlan(Plan):
             self.gemm(dy16, wT, M, in_f, out_f, out_f32=dx)
         return dx
 
-    def t_vit(self, vit, parts, N, S, taps):
-        """monai ViT forward (perceptron patch embedding) with every intermediate kept + its backward."""
+    def t_vit(self, vit, parts, N, S, taps, dgrad_first=False):
+        """monai ViT forward (perceptron patch embedding) with every intermediate kept + its backward.
+        dgrad_first: also the data gradient of the patch embedding w.r.t. parts[0] (net_A's output when it trains)."""
         P = self
         hidden, heads, L = vit.hidden_size, vit.num_heads, vit.num_layers
         hd = hidden // heads
@@ -486,6 +605,24 @@ class TrainPlan(Plan):
                 g = dwp.view(hidden, ncb, 16, 16, 16, 8).permute(0, 2, 3, 4, 1, 5).reshape(hidden, 16, 16, 16, ncb * 8)
                 gw.view(hidden, 16, 16, 16, Cin).copy_(g[..., slot_idx])
             P.add_py(unpack_pe)
+            if dgrad_first:
+                # dA = dx Wpe restricted to the K columns of parts[0] (its channel blocks lead the (block, p1, p2, p3, e)
+                # flatten order), un-patchified into a c8 fp32 gradient
+                a0 = parts[0]
+                nb0 = blocks16(a0.C)
+                K0 = nb0 * 4096 * 8
+                wT = P.derived(lambda: pack_pe()[:, :K0].t().contiguous())          # [K0, hidden] fp16
+                dx16 = P.zeros((M, hidden), torch.float16)
+                P.add("dp_add", dx.data_ptr(), None, M * hidden, None, dx16.data_ptr())
+                dA = f32(M, K0)
+                P.gemm(dx16, wT, M, K0, hidden, out_f32=dA)
+                gr = P.new_graw(N, a0.C, tuple(S))
+
+                def unpatchify():
+                    v = dA.view(N, grid[0], grid[1], grid[2], nb0, 16, 16, 16, 8).permute(0, 4, 1, 5, 2, 6, 3, 7, 8)
+                    gr.t.view(N, nb0, grid[0], 16, grid[1], 16, grid[2], 16, 8).copy_(v)
+                P.add_py(unpatchify)
+                P.add_act_grad(a0, (gr.t, gr.cb_total, 0))
         P.tape.append(bwd)
         return Tokens(z, grid), hs
 
@@ -565,15 +702,16 @@ def _t_conv_3_1_old(P, blk, parts, out):
     P.t_norm(raw, out, identity=True)
 
 
-def _t_unetr(P, vit, enc_blocks, dec_blocks, parts, taps):
+def _t_unetr(P, vit, enc_blocks, dec_blocks, parts, taps, input_grad=False):
     """UNETR-shaped body shared by MainSubsetModel.forward (dose_pyfer.py:311-319) and oar_transeg Model.forward
-    (oar_transeg.py:171-185) in train mode; returns the decoder outputs [full res, /2, /4, /8]."""
+    (oar_transeg.py:171-185) in train mode; returns the decoder outputs [full res, /2, /4, /8].
+    input_grad: the network input carries a gradient (parts[0] = net_A's output with freeze=False)."""
     N, dims = parts[0].N, parts[0].dims
     fs = enc_blocks[0].layer.conv1.conv.weight.shape[0]
-    z, hs = P.t_vit(vit, parts, N, dims, taps)
+    z, hs = P.t_vit(vit, parts, N, dims, taps, dgrad_first=input_grad)
     sizes = [dims, tuple(d // 2 for d in dims), tuple(d // 4 for d in dims), tuple(d // 8 for d in dims)]
     cats = [P.new_concat(N, [fs << l, fs << l], sizes[l]) for l in range(4)]
-    _t_res_block(P, enc_blocks[0].layer, parts, cats[0][1], need_dgrad=False)
+    _t_res_block(P, enc_blocks[0].layer, parts, cats[0][1], need_dgrad=input_grad)
     _t_pr_up(P, enc_blocks[1], hs[taps[0]], cats[1][1])
     _t_pr_up(P, enc_blocks[2], hs[taps[1]], cats[2][1])
     _t_pr_up(P, enc_blocks[3], hs[taps[2]], cats[3][1])
@@ -594,12 +732,55 @@ def _t_unetr(P, vit, enc_blocks, dec_blocks, parts, taps):
     return decs[::-1]
 
 
-def _t_main_subset(P, net, parts):
+def _t_base_unet(P, net, x_act, out_act):
+    """c3d.py:118-149 BaseUNet in train mode (freeze=False): Encoder (:41-72, stride-2 SingleConvs on the space-to-depth
+    copy), Decoder (:75-115, trilinear UpConvs), InstanceNorm3d(affine=True) + ReLU after every conv; forward with the
+    3-term operand split of the inference recipe, backward on fp16 operands.  The final tensor lands in out_act."""
+    N, dims0 = x_act.N, x_act.dims
+    ch = net.list_ch
+    if any(d % 16 for d in dims0) or any(c % 16 for c in ch[1:]):
+        raise RuntimeError("training net_A (freeze=False): sizes must be multiples of 16 (space-to-depth stride-2 convs)")
+    dims = [tuple(d >> s for d in dims0) for s in range(5)]
+    cat = {s: P.new_concat(N, [ch[s], ch[s]], dims[s - 1], lo=True) for s in (1, 2, 3, 4)}
+
+    def conv_norm(parts, single, out, need_dgrad=True, s2d_out=None):
+        raw = P.t_conv(parts, single[0], 3, need_dgrad=need_dgrad, mode="p3")
+        P.t_norm(raw, out, act="relu", affine=single[1], s2d=s2d_out)
+    h, s2d = x_act, None
+    for s in range(1, 6):
+        enc = getattr(net.encoder, f"encoder_{s}")
+        a = P.new_act(N, ch[s], dims[s - 1], lo=True)
+        if s == 1:
+            conv_norm([h], enc[0].single_conv, a, need_dgrad=False)          # the network input needs no gradient
+        else:
+            raw = P.t_conv_s2(s2d, h, enc[0].single_conv[0])
+            P.t_norm(raw, a, act="relu", affine=enc[0].single_conv[1])
+        dst = cat[s][1] if s <= 4 else P.new_act(N, ch[s], dims[s - 1], lo=True)
+        s2d = P.new_act(N, 8 * ch[s], dims[s], lo=True) if s <= 4 else None
+        conv_norm([a], enc[1].single_conv, dst, s2d_out=s2d)
+        h = dst
+    for s in (4, 3, 2, 1):
+        up = P.new_act(N, ch[s + 1], dims[s - 1], lo=True)
+        P.t_upsample(h, up)
+        conv_norm([up], getattr(net.decoder, f"upconv_{s}").conv, cat[s][0])
+        dec = getattr(net.decoder, f"decoder_conv_{s}")
+        last = (s == 1)
+        d0 = out_act if last else P.new_act(N, ch[s], dims[s - 1], lo=True)
+        conv_norm(cat[s], dec[0].single_conv, d0)
+        h = d0
+        if not last:
+            d1 = P.new_act(N, ch[s], dims[s - 1], lo=True)
+            conv_norm([h], dec[1].single_conv, d1)
+            h = d1
+    return out_act
+
+
+def _t_main_subset(P, net, parts, input_grad=False):
     """MainSubsetModel.forward (dose_pyfer.py:311-319) in train mode; returns the four planar dose outputs."""
     enc, dec = net.encoder, net.decoder
     i = enc.num_layers // 4
     decs = _t_unetr(P, enc.vit, (enc.skip1, enc.skip2, enc.skip3, enc.skip4),
-                    (dec.decoder4, dec.decoder3, dec.decoder2, dec.decoder1), parts, (i, 2 * i, 3 * i))
+                    (dec.decoder4, dec.decoder3, dec.decoder2, dec.decoder1), parts, (i, 2 * i, 3 * i), input_grad=input_grad)
     return [P.t_head(d, conv[0]) for d, conv in zip(decs, net.dose_convertors)]
 
 
@@ -839,23 +1020,25 @@ class DoseTrainer(_Trainer):
     """One DOSE-PYFER training step per call: `loss = trainer.step(input_[B,9,S,S,S], gt[B,2,S,S,S])`.
 
     model: dose_prediction_b200.networks.Model on a CUDA device (parameters are re-homed into one flat fp32
-    buffer; state_dict() keeps working).  freeze=True as in the reference (net_A / conv_out_A get no gradient)."""
+    buffer; state_dict() keeps working).  freeze=True as in the reference's default (net_A / conv_out_A get no gradient);
+    freeze=False (the other value of Pyfer's constructor flag, train_light_pyfer.py:61-88) trains every parameter: the
+    backward pass continues through net_A (strided convs, trilinear up-sampling, affine InstanceNorm) and GenLoss gains
+    0.5 * L1(net_A's own prediction) (loss.py:114-115)."""
 
     def __init__(self, model, batch, size, lr=1e-4, weight_decay=1e-4, delta1=10.0, delta2=8.0, freeze=True,
                  betas=(0.9, 0.999), eps=1e-8, loss_scale=4096.0, process_group=None, probe=None, external_grads=False):
         """probe (tests only): list of four tensors R_i shaped like the dose outputs; the backward pass then starts
         from dL/dpred_i = R_i (a linear loss sum <pred_i, R_i>) instead of the GenLoss gradient, whose sign()
         makes gradient parity ill-conditioned."""
-        if not freeze:
-            raise RuntimeError("training path: freeze=True only (net_A frozen, train_light_pyfer.py:85-88)")
+        self.freeze = bool(freeze)
         self.batch, self.size = batch, size
         self.delta1, self.delta2, self.probe = delta1, delta2, probe
         # external_grads (the autograd shim, autograd_forward below): the loss lives in the caller's torch code; the
         # backward half of the launch list starts from dL/dpred_i written into self.up_grads by the autograd engine
         self.external = bool(external_grads)
         self.up_grads = []
-        self._setup(model, lambda n: not (n.startswith("net_A") or n.startswith("conv_out_A")), lr, weight_decay, betas, eps,
-                    loss_scale, process_group)
+        self._setup(model, lambda n: not self.freeze or not (n.startswith("net_A") or n.startswith("conv_out_A")), lr,
+                    weight_decay, betas, eps, loss_scale, process_group)
         self._set_tail(("net_B.decoder.", "net_B.dose_convertors.", "net_B.out."))
         self._emit()
 
@@ -869,36 +1052,50 @@ class DoseTrainer(_Trainer):
         P.add_zero(self.flat_g)
         P.add_zero(P.arena)
         P.pack_input(P.x_in, x_act)
-        P.training = False          # frozen net_A: inference emitter, weights packed once (InstanceNorm: no running stats)
-        nw._emit_base_unet(P, m.net_A, x_act, a_out)
-        self.out_A = P.zeros((N, m.out_ch) + dims, torch.float32)
-        P.pointwise([(a_out, None, None)], m.conv_out_A.weight, m.conv_out_A.bias, out_planar=self.out_A)
-        P.training = True
-        outs = _t_main_subset(P, m.net_B, [a_out, x_act])
+        if self.freeze:
+            P.training = False      # frozen net_A: inference emitter, weights packed once (InstanceNorm: no running stats)
+            nw._emit_base_unet(P, m.net_A, x_act, a_out)
+            self.out_A = P.zeros((N, m.out_ch) + dims, torch.float32)
+            P.pointwise([(a_out, None, None)], m.conv_out_A.weight, m.conv_out_A.bias, out_planar=self.out_A)
+            P.training = True
+        else:
+            _t_base_unet(P, m.net_A, x_act, a_out)
+            self.out_A = P.t_head(a_out, m.conv_out_A)
+        outs = _t_main_subset(P, m.net_B, [a_out, x_act], input_grad=not self.freeze)
         self.outs = outs
         self.fwd_end = len(P.steps)              # steps[:fwd_end] = the forward pass, steps[fwd_end:] = loss + backward
         # ---- GenLoss forward
-        acc = P.zeros((2 * len(outs),), torch.float64)
+        acc = P.zeros((2 * len(outs) + 2,), torch.float64)
+        acc_a = None if self.freeze else acc[2 * len(outs):]          # net_A's own L1 term (freeze=False)
         sizes = [o.shape[2] for o in outs]
         if not self.external:
             P.add_zero(acc)
             for i, o in enumerate(outs):
                 P.add("dp_masked_l1", o.data_ptr(), P.gt.data_ptr(), N, S, sizes[i], acc[2 * i:].data_ptr(), 0, 0.0, None)
-            P.add("dp_genloss_finalize", acc.data_ptr(), len(outs), float(self.delta1), float(self.delta2), self.loss.data_ptr())
+            if acc_a is not None:
+                P.add("dp_masked_l1", self.out_A.data_ptr(), P.gt.data_ptr(), N, S, S, acc_a.data_ptr(), 0, 0.0, None)
+            P.add("dp_genloss_finalize", acc.data_ptr(), len(outs), float(self.delta1), float(self.delta2),
+                  acc_a.data_ptr() if acc_a is not None else None, 0.5, self.loss.data_ptr())
         # ---- backward
-        for i, o in enumerate(outs):
+        heads = list(outs) + ([] if self.freeze else [self.out_A])     # freeze=False: net_A's prediction is a fifth head
+        for i, o in enumerate(heads):
             g = P.zeros(tuple(o.shape), torch.float32)
-            coef = self.loss_scale * (self.delta1 if i == 0 else self.delta2 / (len(outs) - 1))
+            if i == len(outs):
+                coef, sz, a_i = self.loss_scale * 0.5, S, acc_a
+            else:
+                coef, sz, a_i = self.loss_scale * (self.delta1 if i == 0 else self.delta2 / (len(outs) - 1)), sizes[i], acc[2 * i:]
             if self.external:
                 self.up_grads.append(g)
-            elif self.probe is not None:
+            elif self.probe is not None and i < len(self.probe):
                 r = (self.probe[i].to(self.device, torch.float32) * self.loss_scale).contiguous()
                 P.add_py(lambda g=g, r=r: g.copy_(r))
+            elif self.probe is not None:
+                pass                                  # probe without an entry for this head: zero gradient
             else:
-                P.add("dp_masked_l1", o.data_ptr(), P.gt.data_ptr(), N, S, sizes[i], acc[2 * i:].data_ptr(), 1, float(coef),
-                      g.data_ptr())
+                P.add("dp_masked_l1", o.data_ptr(), P.gt.data_ptr(), N, S, sz, a_i.data_ptr(), 1, float(coef), g.data_ptr())
             P.planar_grad[o.data_ptr()] = g
         self._finish_emit()
+        P.act_grads.pop(P._key(x_act), None)          # gradients w.r.t. the network input are not needed
 
     def forward_backward(self, x, gt):
         """forward + loss + backward; gradients (times loss_scale) are left in the flat gradient buffer."""
@@ -943,14 +1140,15 @@ class _DoseTrainFunction(torch.autograd.Function):
         tr.run_forward(x)
         ctx.tr = tr
         out_A = tr.out_A.clone()
-        ctx.mark_non_differentiable(out_A)
+        if tr.freeze:
+            ctx.mark_non_differentiable(out_A)
         return (out_A,) + tuple(o.clone() for o in tr.outs)
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, g_a, *g_outs):
         tr = ctx.tr
-        return (None, None) + tr._param_grads(tr.run_backward(list(g_outs)))
+        return (None, None) + tr._param_grads(tr.run_backward(list(g_outs) + ([] if tr.freeze else [g_a])))
 
 
 class _SegTrainFunction(torch.autograd.Function):
@@ -996,15 +1194,17 @@ def autograd_forward(model, x):
     if x.shape[1] != model.in_ch:
         raise ValueError(f"expected {model.in_ch} input channels, got {x.shape[1]}")
     flags = tuple(p.requires_grad for p in model.parameters())
-    if any(p.requires_grad for n, p in model.named_parameters() if n.startswith("net_A") or n.startswith("conv_out_A")):
-        raise NotImplementedError("train-mode forward: net_A / conv_out_A must be frozen (requires_grad=False), as "
-                                  "Pyfer(freeze=True) does (train_light_pyfer.py:85-88); freeze=False is not built")
+    a_flags = [p.requires_grad for n, p in model.named_parameters() if n.startswith("net_A") or n.startswith("conv_out_A")]
+    if any(a_flags) and not all(a_flags):
+        raise NotImplementedError("train-mode forward: net_A / conv_out_A must be frozen as a whole (Pyfer(freeze=True), "
+                                  "train_light_pyfer.py:85-88) or trained as a whole (freeze=False)")
+    freeze = not any(a_flags)
     cache = model.__dict__.setdefault("_train_ctx", {})
     key = (tuple(x.shape), x.device.index)
     tr = cache.get(key)
     if tr is None or tr._flags != flags:
         cache.clear()                              # one resident training plan per module
-        tr = DoseTrainer(model, x.shape[0], x.shape[2], external_grads=True)
+        tr = DoseTrainer(model, x.shape[0], x.shape[2], external_grads=True, freeze=freeze)
         tr._flags = tuple(p.requires_grad for p in model.parameters())
         cache[key] = tr
     outs = _DoseTrainFunction.apply(tr, x.detach(), *[p for _, p in tr.params])

@@ -348,8 +348,14 @@ int dp_head_bwd(const float* g, const void* x_hi, const void* x_lo, int x_cb_tot
  * acc[0] += sum |p-t|, acc[1] += #mask;  phase 1: dpred = coef * sign(p-t) / acc[1].                     */
 int dp_masked_l1(const float* pred, const float* gt, int N, int S, int s, double* acc, int phase, float coef,
                  float* dpred, cudaStream_t stream);
-/* loss = delta1 * acc[0]/acc[1] + delta2 * mean_{i>=1} acc[2i]/acc[2i+1]   (loss.py:96-112) */
-int dp_genloss_finalize(const double* acc, int n_scales, float delta1, float delta2, float* loss, cudaStream_t stream);
+/* loss = delta1 * acc[0]/acc[1] + delta2 * mean_{i>=1} acc[2i]/acc[2i+1]   (loss.py:96-112)
+ *        [+ weight_a * acc_a[0]/acc_a[1]: the net_A term of `casecade and not freez`, loss.py:114-115; acc_a may be NULL] */
+int dp_genloss_finalize(const double* acc, int n_scales, float delta1, float delta2, const double* acc_a, float weight_a,
+                        float* loss, cudaStream_t stream);
+/* Adjoint of the 2x linear interpolation (align_corners=True) along one axis: g fp32 [outer][2*len_in][inner][8] ->
+ * out [outer][len_in][inner][8].  Three passes (D, H, W) = backward of F.interpolate(scale_factor=2, 'trilinear',
+ * align_corners=True) in UpConv.forward (c3d.py:35-38) on c8 fp32 tensors; deterministic gather. */
+int dp_lerp2x_bwd(const float* g, long long outer, int len_in, long long inner, float* out, cudaStream_t stream);
 
 /* Seg training loss: monai 0.7.0 DiceCELoss(to_onehot_y=True, softmax=True) as used at
  * OARSegmentation/train_light_transeg.py:148,186.  logits: c8 fp32 with C <= 8 classes in channel block 0; label:

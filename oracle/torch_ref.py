@@ -331,9 +331,10 @@ def sliding_window_logits(sd: SD, ct, roi: int = 96, sw_batch: int = 4, overlap:
 
 
 # --------------------------------------------------------------------------- training loss
-def gen_loss(predictions, gt, delta1=10.0, delta2=8.0):
-    """DosePrediction/Train/loss.py:69-119 GenLoss.forward(mode='train', casecade=True, freez=True,
-    huber=False), with downSample :57-67 (trilinear align_corners GT, nearest-exact mask)."""
+def gen_loss(predictions, gt, delta1=10.0, delta2=8.0, freeze=True):
+    """DosePrediction/Train/loss.py:69-119 GenLoss.forward(mode='train', casecade=True, freez=freeze,
+    huber=False), with downSample :57-67 (trilinear align_corners GT, nearest-exact mask); freez=False adds
+    0.5 * L1 of net_A's own prediction over the possible-dose mask (:114-115)."""
     gt_dose, mask = gt[:, 0:1], gt[:, 1:]
     preds = predictions[1]
     size = gt.shape[-1]
@@ -346,28 +347,35 @@ def gen_loss(predictions, gt, delta1=10.0, delta2=8.0):
         l_ds = l_ds + F.l1_loss(p_i[sel], g_i[sel])
     l_ds = l_ds / (len(preds) - 1)
     sel = mask > 0
-    return delta1 * F.l1_loss(preds[0][sel], gt_dose[sel]) + delta2 * l_ds
+    loss = delta1 * F.l1_loss(preds[0][sel], gt_dose[sel]) + delta2 * l_ds
+    if not freeze:
+        loss = loss + 0.5 * F.l1_loss(predictions[0][sel], gt_dose[sel])
+    return loss
 
 
 def dose_pyfer_train_step(sd: SD, x, gt, lr=1e-4, weight_decay=1e-4, delta1=10.0, delta2=8.0, betas=(0.9, 0.999),
-                          eps=1e-8, probe=None, **kw):
+                          eps=1e-8, probe=None, freeze=True, **kw):
     """Pyfer.training_step + one optimizer step (DosePrediction/Train/train_light_pyfer.py:85-88,122-143,194-197):
-    train-mode forward (freeze=True: net_A.* / conv_out_A.* get no gradient), GenLoss, autograd, AdamW with fp32
+    train-mode forward (freeze=True: net_A.* / conv_out_A.* get no gradient; freeze=False, the other value of the
+    constructor flag :61-88: every parameter trains and GenLoss gains its net_A term), GenLoss, autograd, AdamW with fp32
     state (the reference's bnb Adam8bit quantises the same update's state to 8 bit; not restated).
     Returns (loss, {name: grad}, {name: updated parameter or running statistic}, forward outputs)."""
     global BN_TRAIN
     is_buffer = lambda k: k.endswith("running_mean") or k.endswith("running_var") or k.endswith("num_batches_tracked")
     leaf = {k: v.detach().clone() for k, v in sd.items()}
-    train_keys = [k for k in leaf if not (k.startswith("net_A") or k.startswith("conv_out_A")) and not is_buffer(k)
-                  and leaf[k].is_floating_point()]
+    train_keys = [k for k in leaf if (not freeze or not (k.startswith("net_A") or k.startswith("conv_out_A")))
+                  and not is_buffer(k) and leaf[k].is_floating_point()]
     for k in train_keys:
         leaf[k].requires_grad_(True)
     BN_TRAIN = {}
     try:
         out = dose_pyfer_forward(leaf, x, **kw)
-        loss = gen_loss(out, gt, delta1, delta2)
+        loss = gen_loss(out, gt, delta1, delta2, freeze=freeze)
         if probe is not None:      # linear loss sum <pred_i, R_i>: smooth gradients for backward-pass parity tests
-            sum((o * r).sum() for o, r in zip(out[1], probe)).backward()
+            lin = sum((o * r).sum() for o, r in zip(out[1], probe))
+            if len(probe) > len(out[1]):          # freeze=False: a fifth probe tensor for net_A's own prediction
+                lin = lin + (out[0] * probe[len(out[1])]).sum()
+            lin.backward()
         else:
             loss.backward()
         new_stats = dict(BN_TRAIN)

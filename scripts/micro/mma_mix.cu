@@ -16,7 +16,7 @@ __device__ __forceinline__ void mma(uint32_t d, uint32_t a_lo, uint32_t a_hi, ui
                ::"r"(d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(1u) : "memory");
 }
 
-__global__ void __launch_bounds__(128, 1) mma_mix(int Na, int Nb, int planes, int aligned, long long* out) {
+__global__ void __launch_bounds__(128, 1) mma_mix(int Na, int Nb, int planes, int aligned, int M, long long* out) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t bar[2];
   __shared__ uint32_t tbase;
@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(128, 1) mma_mix(int Na, int Nb, int planes, in
   if ((warp == 1 || warp == 2) && lane == 0) {
     const int w = warp - 1;
     const uint32_t PW = aligned ? 40u : 34u, PH = 18u;               // patch row pitch in 16-B units
-    const uint32_t ia = make_idesc_f16(128, Na), ib = make_idesc_f16(128, Nb > 0 ? Nb : 16);
+    const uint32_t ia = make_idesc_f16(M, Na), ib = make_idesc_f16(M, Nb > 0 ? Nb : 16);
     const uint32_t sa16 = smem_u32(smem) >> 4, sb16 = (smem_u32(smem) + 100 * 1024) >> 4;
     const uint32_t a_hi = PW | (1u << 14), b_hi = 8u | (1u << 14);
     const uint32_t a_lo_c = ((PH * PW) & 0x3FFFu) << 16, b_lo_c = (128u << 16);
@@ -71,13 +71,14 @@ int main() {
   const int smem = 200 * 1024;
   cudaFuncSetAttribute(mma_mix, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-  const int cfg[][2] = {{128, 128}, {128, 64}, {96, 96}, {96, 48}, {64, 64}, {64, 0}, {48, 0}, {128, 0}, {96, 0}, {256, 0}, {32, 0}, {16, 0}};
+  const int cfg[][2] = {{128, 128}, {128, 64}, {64, 0}, {112, 0}, {128, 0}, {48, 0}, {32, 0}, {16, 0}};
+  for (int M = 128; M >= 64; M -= 64)
   for (int aligned = 0; aligned < 2; ++aligned)
     for (auto& c : cfg) {
       const int planes = 20000;
       for (int rep = 0; rep < 2; ++rep) {       // second repetition = warm (sustained) number
         cudaEventRecord(e0);
-        mma_mix<<<148, 128, smem>>>(c[0], c[1], planes, aligned, d);
+        mma_mix<<<148, 128, smem>>>(c[0], c[1], planes, aligned, M, d);
         cudaEventRecord(e1);
         cudaError_t e = cudaDeviceSynchronize();
         float ms; cudaEventElapsedTime(&ms, e0, e1);
@@ -85,8 +86,8 @@ int main() {
         double avg = 0; for (int i = 0; i < 148; ++i) avg += h[i]; avg /= 148;
         const double mmas = planes * 9.0 * 4 * (c[1] ? 2 : 1);     // per CTA (both issuers)
         const double cols = planes * 9.0 * 4 * (c[0] + c[1]);
-        if (rep) printf("aligned=%d Na=%3d Nb=%3d : %6.1f cycles per tap (4 tiles, both chunks), %5.1f per MMA, %6.2f ms wall, %6.0f TF/s executed, clk %.0f MHz  %s\n",
-               aligned, c[0], c[1], avg / (planes * 9.0), avg / mmas * 1.0, ms, cols * 128 * 16 * 2 * 148 / (ms * 1e-3) / 1e12,
+        if (rep) printf("M=%d aligned=%d Na=%3d Nb=%3d : %6.1f cycles per tap (4 tiles, both chunks), %5.1f per MMA, %6.2f ms wall, %6.0f TF/s executed, clk %.0f MHz  %s\n",
+               M, aligned, c[0], c[1], avg / (planes * 9.0), avg / mmas * 1.0, ms, cols * 128 * 16 * 2 * 148 / (ms * 1e-3) / 1e12,
                avg / (ms * 1e-3) / 1e6, cudaGetErrorString(e));
       }
     }

@@ -97,6 +97,28 @@ def test_train_step_matches_reference_fixture(dose_sd32):
     assert (new[w].flatten()[idx] - torch.from_numpy(g["p/" + w])).abs().max() < 2.5e-4      # lr * O(1) per Adam step
 
 
+def test_unfrozen_train_step_matches_reference_fixture(dose_sd32):
+    """freeze=False (train_light_pyfer.py:61-88; GenLoss freez=False, loss.py:114-115): the oracle's step == the reference
+    modules' own autograd with every parameter trainable (gradients through net_A: strided convs, trilinear upsampling)."""
+    vol = synth.make_batch(2, 32, seed=1234)
+    g = np.load(os.path.join(GOLDEN, "train32_unfrozen.npz"))
+    loss, grads, new, _ = torch_ref.dose_pyfer_train_step(dose_sd32, vol["dose_input"], vol["gt"], lr=1e-4, weight_decay=1e-4,
+                                                          freeze=False)
+    assert abs(float(loss) - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    names, norms = list(g["names"]), g["norms"]
+    assert any(n.startswith("net_A.") for n in names) and "conv_out_A.weight" in names
+    gmax = norms.max()
+    for n, want in zip(names, norms):
+        got = float(grads[n].double().norm())
+        assert abs(got - want) <= 2e-3 * want + 1e-6 * gmax, n
+        idx = torch_ref.sample_idx(grads[n].numel())
+        ref = torch.from_numpy(g["g/" + n])
+        assert (grads[n].flatten()[idx] - ref).abs().max() <= 5e-3 * ref.abs().max() + 1e-6 * gmax, n
+    w = "net_A.encoder.encoder_2.0.single_conv.0.weight"          # a stride-2 convolution of net_A
+    idx = torch_ref.sample_idx(new[w].numel())
+    assert (new[w].flatten()[idx] - torch.from_numpy(g["p/" + w])).abs().max() < 2.5e-4
+
+
 def test_seg_train_step_matches_reference_fixture(seg_sd32):
     """oracle seg train step (train-mode BN, DiceCE, autograd) == the reference module's own autograd."""
     vol = synth.make_batch(2, 32, seed=1234)

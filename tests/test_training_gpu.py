@@ -477,6 +477,97 @@ def test_training_step_matches_oracle_32():
     assert float(mine.abs().max()) < 1.2e-4
 
 
+def test_lerp2x_bwd_is_the_transpose_of_the_trilinear_upsample():
+    """three dp_lerp2x_bwd passes == autograd of F.interpolate(scale_factor=2, 'trilinear', align_corners=True) (c3d.py:36)"""
+    from dose_prediction_b200 import _lib
+    lib = _lib.lib()
+    torch.manual_seed(5)
+    N, C, (D, H, W) = 2, 16, (3, 5, 8)
+    g = torch.randn(N, C, 2 * D, 2 * H, 2 * W, device=DEV)
+    x = torch.zeros(N, C, D, H, W, device=DEV, dtype=torch.float64, requires_grad=True)
+    F.interpolate(x, scale_factor=2, mode="trilinear", align_corners=True).backward(g.double())
+    g8 = _ncdhw_to_c8(g)
+    ncb = C // 8
+    t1 = torch.zeros(N, ncb, D, 2 * H, 2 * W, 8, device=DEV)
+    t2 = torch.zeros(N, ncb, D, H, 2 * W, 8, device=DEV)
+    out = torch.zeros(N, ncb, D, H, W, 8, device=DEV)
+    s = torch.cuda.current_stream().cuda_stream
+    _lib.check(lib.dp_lerp2x_bwd(g8.data_ptr(), N * ncb, D, 4 * H * W, t1.data_ptr(), s))
+    _lib.check(lib.dp_lerp2x_bwd(t1.data_ptr(), N * ncb * D, H, 2 * W, t2.data_ptr(), s))
+    _lib.check(lib.dp_lerp2x_bwd(t2.data_ptr(), N * ncb * D * H, W, 1, out.data_ptr(), s))
+    torch.cuda.synchronize()
+    assert _rel(_c8_to_ncdhw(out, C), x.grad) < 1e-6
+
+
+def test_unfrozen_training_step_matches_oracle_32():
+    """Pyfer(freeze=False) (train_light_pyfer.py:61-88; GenLoss freez=False, loss.py:114-115): every parameter trains, the
+    backward pass runs through net_A (stride-2 convs on the space-to-depth copy, trilinear up-sampling, affine InstanceNorm,
+    the patch-embedding / res-block data gradients into net_A's output); vs the oracle pinned to the reference's autograd
+    (tests/golden/train32_unfrozen.npz)."""
+    from dose_prediction_b200 import synth
+    from dose_prediction_b200.training import DoseTrainer
+    from oracle import torch_ref
+    model, sd = _dose_model(32)
+    vol = synth.make_batch(2, 32, seed=1234)
+    loss_ref, grads_ref, new_ref, outs_ref = torch_ref.dose_pyfer_train_step(sd, vol["dose_input"], vol["gt"], lr=1e-4,
+                                                                             weight_decay=1e-4, freeze=False)
+    tr = DoseTrainer(model, 2, 32, lr=1e-4, weight_decay=1e-4, freeze=False)
+    before = {k: v.clone() for k, v in model.state_dict().items()}
+    loss = tr.step(vol["dose_input"].to(DEV), vol["gt"].to(DEV))
+    torch.cuda.synchronize()
+    tr.P.check_device_errors()
+    assert abs(float(loss) - float(loss_ref)) <= 2e-3 * abs(float(loss_ref))
+    outs = tr.outputs()
+    assert _rel(outs[0], outs_ref[0]) < 1e-2
+    for a, b in zip(outs[1], outs_ref[1]):
+        assert _rel(a, b) < 1e-2
+    g = tr.grads()
+    gmax = max(float(v.norm()) for v in grads_ref.values())
+    checked_a = 0
+    worst = (1.0, None)
+    for n, ref in grads_ref.items():
+        if float(ref.norm()) < 1e-4 * gmax:
+            assert float(g[n].norm()) < 1e-3 * gmax, n
+            continue
+        cos = float(F.cosine_similarity(g[n].flatten().double().cpu(), ref.flatten().double(), dim=0))
+        worst = min(worst, (cos, n))
+        assert cos > 0.99, (n, cos)
+        assert abs(float(g[n].norm()) / float(ref.norm()) - 1.0) < 0.06, n
+        checked_a += n.startswith("net_A.") or n.startswith("conv_out_A")
+    print("worst gradient cosine", worst)
+    assert checked_a >= 2 * 19 + 1            # 19 convs of net_A (weights) + their affine InstanceNorms, conv_out_A
+    after = model.state_dict()
+    for w in ("net_A.encoder.encoder_2.0.single_conv.0.weight", "net_A.decoder.upconv_1.conv.0.weight", "conv_out_A.weight"):
+        mine, want = (after[w] - before[w]).flatten().cpu(), (new_ref[w] - sd[w]).flatten()
+        assert float((mine.sign() == want.sign()).float().mean()) > 0.95, w
+        assert 0.0 < float(mine.abs().max()) < 1.2e-4, w
+
+
+def test_unfrozen_autograd_forward_trains_net_a():
+    """train-mode model(x) with every parameter requiring grad (freeze=False under the unchanged reference training code):
+    out_A is differentiable, .grad lands on net_A's parameters and equals the fused trainer's gradient"""
+    from dose_prediction_b200 import synth
+    from dose_prediction_b200.training import DoseTrainer
+    from oracle import torch_ref
+    model, sd = _dose_model(32)
+    vol = synth.make_batch(2, 32, seed=1234)
+    x, gt = vol["dose_input"].to(DEV), vol["gt"].to(DEV)
+    out = model(x)
+    assert out[0].requires_grad
+    loss = torch_ref.gen_loss(out, gt, 10.0, 8.0, freeze=False)
+    loss.backward()
+    ga = model.net_A.encoder.encoder_3[0].single_conv[0].weight.grad.clone()
+    gc = model.conv_out_A.weight.grad.clone()
+    assert float(ga.norm()) > 0 and float(gc.norm()) > 0
+    model2, _ = _dose_model(32)
+    tr = DoseTrainer(model2, 2, 32, freeze=False)
+    loss2 = tr.forward_backward(x, gt)
+    g2 = tr.grads()
+    assert abs(float(loss) - float(loss2)) <= 1e-4 * abs(float(loss2))
+    assert _rel(ga, g2["net_A.encoder.encoder_3.0.single_conv.0.weight"]) < 2e-3
+    assert _rel(gc, g2["conv_out_A.weight"]) < 2e-3
+
+
 def test_training_reduces_the_loss():
     from dose_prediction_b200 import synth
     from dose_prediction_b200.training import DoseTrainer
