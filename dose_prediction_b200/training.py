@@ -702,6 +702,36 @@ def _t_conv_3_1_old(P, blk, parts, out):
     P.t_norm(raw, out, identity=True)
 
 
+def _t_dual_dilated(P, blk, parts, out):
+    """blocks_MDUNet.py:194-215 (multiS_conv=False) in train mode: dilation 1 / 2 / 3 branches (conv -> IN -> act twice),
+    cat, 1^3 conv, IN, act.  Dilated weight gradients run through the CUDA-core dp_conv3d_wgrad."""
+    N, dims = parts[0].N, parts[0].dims
+    act = blk.act
+    C = blk.conv_3.conv[0].weight.shape[0]
+    zs = P.new_concat(N, [C, C, C], dims)
+    for br, z in zip((blk.conv_3, blk.conv_5, blk.conv_7), zs):
+        c = br.conv
+        raw = P.t_conv(parts, c[0], 3, dil=br.dil)
+        a = P.new_act(N, C, dims)
+        P.t_norm(raw, a, act=act)
+        raw = P.t_conv([a], c[3], 3, dil=br.dil)
+        P.t_norm(raw, z, act=act)
+    raw = P.t_pointwise(zs, blk.conv[0])
+    P.t_norm(raw, out, act=act)
+
+
+def _t_basic_block(P, blk, parts, out):
+    """monai 0.7.0 UnetBasicBlock.forward (the conv block of UnetrUpBlock, mode_multi_dec=False) in train mode:
+    conv3 -> IN -> LeakyReLU(0.01) twice."""
+    N, dims = parts[0].N, parts[0].dims
+    Co = blk.conv1.conv.weight.shape[0]
+    raw = P.t_conv(parts, blk.conv1.conv, 3)
+    a = P.new_act(N, Co, dims)
+    P.t_norm(raw, a, act="lrelu")
+    raw = P.t_conv([a], blk.conv2.conv, 3)
+    P.t_norm(raw, out, act="lrelu")
+
+
 def _t_unetr(P, vit, enc_blocks, dec_blocks, parts, taps, input_grad=False):
     """UNETR-shaped body shared by MainSubsetModel.forward (dose_pyfer.py:311-319) and oar_transeg Model.forward
     (oar_transeg.py:171-185) in train mode; returns the decoder outputs [full res, /2, /4, /8].
@@ -718,15 +748,19 @@ def _t_unetr(P, vit, enc_blocks, dec_blocks, parts, taps, input_grad=False):
     P.tape.append(("mark", "decoders"))          # everything recorded after this point runs its backward before it
     decs, inp = [], z
     for lvl, blk in zip((3, 2, 1, 0), dec_blocks):
-        cov = getattr(getattr(blk, "conv_block", None), "cov_", None)
-        if not isinstance(cov, (nw.conv_3_1, nw.conv_3_1_old)):
-            raise RuntimeError("training path covers the multi-scale decoder (mode_multi_dec=True, multiS_conv=True)")
         out = P.new_act(N, fs << lvl, sizes[lvl])
         P.t_deconv(inp, blk.transp_conv.conv.weight, cats[lvl][0])
-        if isinstance(cov, nw.conv_3_1_old):
+        cov = getattr(getattr(blk, "conv_block", None), "cov_", None)
+        if isinstance(blk, nw.UnetrUpBlock):                   # mode_multi_dec=False: monai UnetrUpBlock
+            _t_basic_block(P, blk.conv_block, cats[lvl], out)
+        elif isinstance(cov, nw.conv_3_1_old):
             _t_conv_3_1_old(P, cov, cats[lvl], out)
-        else:
+        elif isinstance(cov, nw.DualDilatedBlock):             # multiS_conv=False
+            _t_dual_dilated(P, cov, cats[lvl], out)
+        elif isinstance(cov, nw.conv_3_1):
             _t_conv_3_1(P, cov, cats[lvl], out)
+        else:
+            raise RuntimeError(f"training path: unknown decoder block {type(blk).__name__}")
         decs.append(out)
         inp = out
     return decs[::-1]

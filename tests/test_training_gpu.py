@@ -568,6 +568,45 @@ def test_unfrozen_autograd_forward_trains_net_a():
     assert _rel(gc, g2["conv_out_A.weight"]) < 2e-3
 
 
+@pytest.mark.parametrize("variant", ["dual_dilated_relu", "unetr_up_block"])
+def test_decoder_variants_training_step_matches_oracle_32(variant):
+    """the other two decoders the constructor flags reach, in train mode: multiS_conv=False (DualDilatedBlock: dilation
+    1 / 2 / 3 branches, blocks_MDUNet.py:194-215) with act='relu', and mode_multi_dec=False (monai UnetrUpBlock)."""
+    from dose_prediction_b200 import networks, synth
+    from dose_prediction_b200.training import DoseTrainer
+    from oracle import synth_ckpt, torch_ref
+    kw_model, kw_ref = (dict(multiS_conv=False, act="relu"), dict(multiS_conv=False, act="relu")) \
+        if variant == "dual_dilated_relu" else (dict(mode_multi_dec=False), {})
+    model = networks.Model(9, 1, [-1, 16, 32, 64, 128, 256], img_size=(32,) * 3, **kw_model)
+    sd = synth_ckpt.make_state_dict(synth_ckpt.manifest_of(model), seed=7)
+    model.load_state_dict(sd, strict=True)
+    model.to(DEV).train()
+    vol = synth.make_batch(2, 32, seed=1234)
+    loss_ref, grads_ref, _, outs_ref = torch_ref.dose_pyfer_train_step(sd, vol["dose_input"], vol["gt"], **kw_ref)
+    tr = DoseTrainer(model, 2, 32)
+    loss = tr.step(vol["dose_input"].to(DEV), vol["gt"].to(DEV))
+    torch.cuda.synchronize()
+    tr.P.check_device_errors()
+    assert abs(float(loss) - float(loss_ref)) <= 2e-3 * abs(float(loss_ref))
+    for a, b in zip(tr.outputs()[1], outs_ref[1]):
+        assert _rel(a, b) < 1e-2
+    g = tr.grads()
+    gmax = max(float(v.norm()) for v in grads_ref.values())
+    checked = 0
+    for n, ref in grads_ref.items():
+        if float(ref.norm()) < 1e-4 * gmax:
+            assert float(g[n].norm()) < 1e-3 * gmax, n
+            continue
+        cos = float(F.cosine_similarity(g[n].flatten().double().cpu(), ref.flatten().double(), dim=0))
+        # ReLU everywhere + the sign() of the L1 loss: the fp16 forward's 1e-3 difference flips more masks than with Mish
+        # (measured worst tensor: 0.988, an encoder deconv behind ~20 nonlinear layers)
+        assert cos > 0.98, (n, cos)
+        # (the heads' scalar biases are sums of +-1 / count that nearly cancel: absolute slack relative to the largest tensor)
+        assert abs(float(g[n].norm()) - float(ref.norm())) < 0.06 * float(ref.norm()) + 1e-3 * gmax, n
+        checked += 1
+    assert checked > 100
+
+
 def test_training_reduces_the_loss():
     from dose_prediction_b200 import synth
     from dose_prediction_b200.training import DoseTrainer
