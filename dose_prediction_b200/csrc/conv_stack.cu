@@ -37,6 +37,8 @@ struct StackParams {
   int a_stages, b_stages;
   uint32_t a_bytes, a_stride, b_bytes, b_stride, b_off;
   int tiles_h, wgroups, nseg, num_items, tiles_w;
+  int balanced;             // 1: every CTA streams one contiguous share of the (column, plane) space (ItemIter), 0: fixed D segments
+  long long total_planes;   // columns x D
   const __half* wpack;      // [G rotations][chunk][kh][kw][2][G*cout][8]
   const float* scale;
   const float* shift;
@@ -128,6 +130,55 @@ __device__ __forceinline__ Item decode_item(const StackParams& p, int item) {
   return it;
 }
 
+// Work distribution.  A column = (image, H tile, W tile group); its D planes are streamed in order.  Fixed D segments dealt
+// round-robin leave the busiest SM with ceil(items / SMs) x (L + k - 1) planes (at 128^3, batch 8, k = 7: 7 x 38 = 266 input
+// planes against 256 x 128 / 148 = 221 output planes per SM).  Balanced mode instead cuts the linearised (column, plane) space
+// into one contiguous share per CTA; a share crosses at most two column boundaries, so it costs its planes plus <= 3 halos
+// (221 + 3 x 6).  Cut points closer than kMinSeg planes to a column boundary snap onto it (no one-plane segments, whose halo
+// would be all of their work).
+constexpr int kMinSeg = 4;
+
+__device__ __forceinline__ long long snap_cut(const StackParams& p, long long raw) {
+  const long long d = raw % p.D;
+  if (d < kMinSeg) return raw - d;
+  if (p.D - d < kMinSeg) return raw + (p.D - d);
+  return raw;
+}
+
+struct ItemIter {
+  long long pos, end;
+  int item;
+  __device__ __forceinline__ explicit ItemIter(const StackParams& p) {
+    item = blockIdx.x;
+    pos = snap_cut(p, static_cast<long long>(blockIdx.x) * p.total_planes / gridDim.x);
+    end = (blockIdx.x + 1 == gridDim.x) ? p.total_planes : snap_cut(p, static_cast<long long>(blockIdx.x + 1) * p.total_planes / gridDim.x);
+  }
+  template <int KS>
+  __device__ __forceinline__ bool next(const StackParams& p, Item& it) {
+    if (!p.balanced) {
+      if (item >= p.num_items) return false;
+      it = decode_item<KS>(p, item);
+      item += gridDim.x;
+      return true;
+    }
+    if (pos >= end) return false;
+    constexpr int pad = (KS - 1) / 2;
+    int t = static_cast<int>(pos / p.D);
+    it.d0 = static_cast<int>(pos % p.D);
+    it.d1 = static_cast<int>(min(static_cast<long long>(p.D), it.d0 + (end - pos)));
+    const int wg = t % p.wgroups; t /= p.wgroups;
+    const int th = t % p.tiles_h;
+    it.n = t / p.tiles_h;
+    it.z0 = max(0, it.d0 - pad);
+    it.z1 = min(p.D - 1, it.d1 - 1 + pad);
+    it.h0 = th * 16;
+    it.w0 = wg * p.T * 8;
+    it.ntile = min(p.T, p.tiles_w - wg * p.T);
+    pos += it.d1 - it.d0;
+    return true;
+  }
+};
+
 template <int KS, int TT>
 __global__ void __launch_bounds__(kStackThreads, 1)
 conv3d_stack_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ StackParams p) {
@@ -174,8 +225,8 @@ conv3d_stack_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_co
     int ia = 0, ib = 0;
     uint32_t pa = 0, pb = 0;
     uint32_t pc_base = 0;
-    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-      const Item it = decode_item<KS>(p, item);
+    Item it;
+    for (ItemIter iter(p); iter.template next<KS>(p, it);) {
       for (int dz = it.z0; dz <= it.z1; ++dz) {
         const uint32_t rot = (pc_base + static_cast<uint32_t>(dz - pad - it.d0)) & gmask;   // slot of (virtual) plane dz-pad
         for (int c = 0; c < p.n_chunks; ++c) {
@@ -237,8 +288,8 @@ conv3d_stack_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_co
     int ia = 0, ib = 0;
     uint32_t pa = 0, pb = 0;
     uint32_t pc_base = 0;                      // running plane counter of this item's plane d0
-    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-      const Item it = decode_item<KS>(p, item);
+    Item it;
+    for (ItemIter iter(p); iter.template next<KS>(p, it);) {
       const int my_tiles = max(0, min(TTs, it.ntile - t_off));
       const bool all_tiles = (my_tiles == TTs);
       for (int dz = it.z0; dz <= it.z1; ++dz) {
@@ -401,8 +452,8 @@ conv3d_stack_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_co
       }
     };
     const size_t plane = static_cast<size_t>(p.D) * p.H * p.W;
-    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-      const Item it = decode_item<KS>(p, item);
+    Item it;
+    for (ItemIter iter(p); iter.template next<KS>(p, it);) {
       if (it.n != cur_n) { flush_stats(cur_n); cur_n = it.n; }
       const int h = it.h0 + hl;
       for (int d = it.d0; d < it.d1; ++d, ++pc) {
@@ -545,8 +596,8 @@ conv3d_stack3h_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
     int ia = 0, ib = 0;
     uint32_t pa = 0, pb = 0;
     uint32_t pc_base = 0;
-    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-      const Item it = decode_item<KS>(p, item);
+    Item it;
+    for (ItemIter iter(p); iter.template next<KS>(p, it);) {
       for (int dz = it.z0; dz <= it.z1; ++dz) {
         const uint32_t rot = (pc_base + static_cast<uint32_t>(dz - it.z0)) & 3u;      // slot of ring plane dz - 1
         for (int c = 0; c < p.n_chunks; ++c) {
@@ -596,8 +647,8 @@ conv3d_stack3h_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
       int ia = 0, ib = 0;
       uint32_t pa = 0, pb = 0;
       uint32_t pc_base = 0;
-      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-        const Item it = decode_item<KS>(p, item);
+      Item it;
+      for (ItemIter iter(p); iter.template next<KS>(p, it);) {
         const int my_tiles = max(0, min(TTs, it.ntile - t_off));
         const bool all_tiles = (my_tiles == TTs);
         for (int dz = it.z0; dz <= it.z1; ++dz) {
@@ -692,8 +743,8 @@ conv3d_stack3h_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
 #pragma unroll
     for (int j = 0; j < 16; ++j) { ts1[j] = 0.f; ts2[j] = 0.f; }
     const size_t plane = static_cast<size_t>(p.D) * p.H * p.W;
-    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-      const Item it = decode_item<KS>(p, item);
+    Item it;
+    for (ItemIter iter(p); iter.template next<KS>(p, it);) {
       if (it.n != cur_n) { flush_stats(cur_n); cur_n = it.n; }
       const int h = it.h0 + hl;
       for (int q = it.z0 - 1; q <= it.z1 + 1; ++q, ++pc) {
@@ -823,6 +874,11 @@ extern "C" int dp_conv3d_stack(const void* in_c8, int cb_total_in, const uint8_t
   p.L = L;
   p.nseg = (D + L - 1) / L;
   p.num_items = N * p.nseg * p.tiles_h * p.wgroups;
+  static const bool no_balance = [] { const char* e = getenv("DP_STACK_BALANCED"); return e && atoi(e) == 0; }();   // A/B switch
+  p.total_planes = static_cast<long long>(N) * p.tiles_h * p.wgroups * D;
+  // balanced shares pay off when a share is long against the snapping granularity; small layers (a few planes per SM)
+  // keep the fixed segments (measured at 32^3, batch 8: balanced +25 %)
+  p.balanced = (seg_len <= 0 && !no_balance && p.total_planes >= 4LL * kMinSeg * sms) ? 1 : 0;
   p.PH = 16 + k - 1;
   p.PWw = 8 * T + k - 1;
   p.a_bytes = 2u * p.PH * p.PWw * 16u;
@@ -874,6 +930,10 @@ extern "C" int dp_conv3d_stack(const void* in_c8, int cb_total_in, const uint8_t
     DP_CHECK(cudaFuncSetAttribute(conv3d_stack3h_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   }
   int grid = sms < p.num_items ? sms : p.num_items;
+  if (p.balanced) {          // one contiguous share of >= 2 planes per CTA
+    const long long want = p.total_planes / 2 > 0 ? p.total_planes / 2 : 1;
+    grid = static_cast<int>(want < sms ? want : sms);
+  }
   fn<<<grid, kStackThreads, smem, stream>>>(tmap, p);
   DP_CHECK(cudaGetLastError());
   return 0;
