@@ -253,7 +253,7 @@ void clear_tensor_map_cache();
 int sm_count();
 // true exactly once per (current CUDA device, family): function attributes (max dynamic shared memory) are per device,
 // so every device a process drives configures its kernels on first use (no process-wide flag).
-enum KernelFamily : int { KF_CONV_STACK = 0, KF_CONV_TC, KF_GEMM128, KF_GEMM256, KF_ATTN64, KF_ATTN128, KF_WGRAD, KF_POINTWISE_TC16, KF_POINTWISE_TC32, KF_POINTWISE_TC64, KF_COUNT };
+enum KernelFamily : int { KF_CONV_STACK = 0, KF_CONV_TC, KF_GEMM128, KF_GEMM256, KF_GEMM_PAIR128, KF_GEMM_PAIR256, KF_ATTN64, KF_ATTN128, KF_WGRAD, KF_POINTWISE_TC16, KF_POINTWISE_TC32, KF_POINTWISE_TC64, KF_COUNT };
 bool first_use_on_device(int family);
 }  // namespace dp
 

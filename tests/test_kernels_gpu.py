@@ -165,6 +165,50 @@ def test_gemm_tc_matches_torch(M, N, K, split):
     assert _rel(out.cpu(), want) < 1e-5
 
 
+_PAIR_CHECK = r"""
+import sys, torch, torch.nn.functional as F
+sys.path.insert(0, %r)
+from dose_prediction_b200.engine import Plan
+dev = torch.device("cuda:0")
+torch.manual_seed(12)
+for M, N, K, act in [(4096, 3072, 768, "gelu"), (4096, 768, 3072, None), (384, 768, 768, None), (1000, 256, 64, None),
+                     (4096, 2304, 768, None)]:
+    A = (torch.randn(M, K, device=dev) / K ** 0.5).half()
+    B = torch.randn(N, K, device=dev).half()
+    bias = torch.randn(N, device=dev)
+    x = torch.randn(M, N, device=dev)
+    x0 = x.clone()
+    P = Plan(dev)
+    if act:
+        g16 = P.zeros((M, N), torch.float16)
+        P.gemm(A, B, M, N, K, bias=bias, act=act, out_f16=g16)
+    else:
+        P.gemm(A, B, M, N, K, bias=bias, resid=x, out_f32=x)
+    P.run()
+    torch.cuda.synchronize()
+    P.check_device_errors()
+    lin = A.double() @ B.double().t() + bias.double()
+    got, want, tol = (g16.double(), F.gelu(lin), 1e-3) if act else (x.double(), lin + x0.double(), 1e-5)
+    err = float((got - want).norm() / want.norm())
+    assert err < tol, (M, N, K, err)
+print("pair ok")
+"""
+
+
+@pytest.mark.parametrize("mode", ["1", "128", "256"])
+def test_gemm_cta_pair_kernel_matches_torch(mode):
+    """the cta_group::2 kernel (256 x 256 / 256 x 128 tiles over CTA pairs; off by default, DP_GEMM_PAIR selects it, read once
+    per process -> a subprocess): several tiles per pair (both TMEM accumulators in flight), long and short K, M not a multiple
+    of the pair tile, bias + GELU / residual epilogues"""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, DP_GEMM_PAIR=mode)
+    r = subprocess.run([sys.executable, "-c", _PAIR_CHECK % root], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "pair ok" in r.stdout, r.stdout + r.stderr
+
+
 def test_gemm_tc_epilogues_gelu_residual_fp16():
     torch.manual_seed(3)
     dev = torch.device("cuda:0")
