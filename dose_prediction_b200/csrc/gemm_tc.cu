@@ -47,6 +47,7 @@ struct GemmParams {
   // in every direction, the 128-byte row = 8 W-voxels x 8 channels at the patch offset (p1, p2, p3 half) that K block
   // stands for.  K order (c8 block, p1, p2, p3, c%8) as dp_patchify's.
   int patch_mode, patch_cb_total, patch_cb_off, patch_tokens, patch_D, patch_H;
+  int debug;                 // timing experiments only (DP_GEMM_DEBUG): 1 = epilogue hands the accumulator straight back, 2 = no MMAs
 };
 
 constexpr int kGemmThreads = 320;        // producer + MMA + 8 epilogue warps (2 per TMEM lane quarter)
@@ -310,6 +311,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const uint32_t sb16 = sa16 + (kStageA >> 4);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
+            if (p.debug & 2) break;
             asm volatile(
                 "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
                 "mov.b64 da, {%1, %2};\n\t"
@@ -341,8 +343,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int slot = iter & 1;
       if (!mbar_wait_relaxed(&acc_full[slot], (iter >> 1) & 1, p.err_flag)) goto teardown;
       tc_fence_after();
-      gemm_epilogue_tile<BN>(p, t, tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(slot * BN), quarter,
-                             chalf, lane, vecN);
+      if (!(p.debug & 1))
+        gemm_epilogue_tile<BN>(p, t, tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(slot * BN), quarter,
+                               chalf, lane, vecN);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[slot]);
@@ -613,6 +616,7 @@ static int launch_gemm_bn(const void* A, const void* B, dp::GemmParams& p, int a
   if (first_use_on_device(BN == 256 ? KF_GEMM256 : KF_GEMM128)) {
     DP_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   }
+  { static const int dbg = [] { const char* e = getenv("DP_GEMM_DEBUG"); return e ? atoi(e) : 0; }(); p.debug = dbg; }
   int grid = sm_count();
   if (grid > p.num_tiles) grid = p.num_tiles;
   gemm_tc_kernel<BN><<<grid, kGemmThreads, smem, stream>>>(ta, tb, p);
