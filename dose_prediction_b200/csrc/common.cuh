@@ -24,6 +24,19 @@ __device__ __forceinline__ float mish_fast(float x) {
   return x * (u * r);
 }
 
+// GELU(x) = x Phi(x) with erf from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7 absolute, far below the fp16 rounding of the
+// stored activation) on the raw rcp / ex2 units: ~14 instructions against ~40 of erff().  Used by the GEMM epilogue of the
+// inference MLP (fc1 + GELU), whose epilogue is ALU-issue bound (profiles/r3_gemm_pair.md); the training kernels keep erff.
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * z * 1.4426950408889634f));
+  const float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f), 0.254829592f);
+  const float erf_abs = fmaf(-poly, e, 1.f);
+  return 0.5f * x * (1.f + copysignf(erf_abs, x));
+}
+
 __device__ __forceinline__ float act_apply(float x, int act) {
   switch (act) {
     case ACT_RELU: return fmaxf(x, 0.f);

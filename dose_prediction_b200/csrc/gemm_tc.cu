@@ -148,7 +148,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, const Ge
         }
         if (p.act == ACT_GELU) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = 0.5f * v[j] * (1.f + erff(v[j] * 0.70710678118654752f));
+          for (int j = 0; j < 16; ++j) v[j] = gelu_fast(v[j]);
         } else if (p.act) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = act_apply(v[j], p.act);
