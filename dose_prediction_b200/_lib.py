@@ -29,7 +29,7 @@ _SIGNATURES = {
     "dp_norm_act_resx": [P, I, P, P, P, P, I, P, P, I, I, I, I, L, P],
     "dp_norm_act_head": [P, I, P, P, P, I, P, P, I, I, P, P, I, P, I, I, L, P],
     "dp_pointwise_conv": [I, P, P, P, P, P, P, P, P, P, P, I, I, L, P, P, P, I, I, P, P, I, P],
-    "dp_pointwise_tc": [I, P, P, P, P, P, P, P, P, P, P, I, I, L, P, P, P, I, I, P, P, P],
+    "dp_pointwise_tc": [I, P, P, P, P, P, P, P, P, P, P, P, P, I, I, L, P, P, P, I, I, P, P, P],
     "dp_pointwise_conv_cw": [I, P, P, P, P, P, P, P, P, P, P, I, I, L, P, P, P, I, I, P, P, I, P],
     "dp_deconv2x": [P, P, L, L, L, I, I, I, I, I, I, P, P, P, I, I, P],
     "dp_deconv2x_tc": [P, I, P, I, P, I, I, I, I, I, I, I, P, P, P, P, I, I, P, P],

@@ -30,6 +30,8 @@ struct PtcBlock {
   long long n_stride;                                      // elements between images
   const double* stats; int stat_c0, stat_C;                // instance statistics of the source (or null), channel of j = 0
   int act;
+  const double* stats0; int act0;                          // optional FIRST stage: act0(IN(x; stats0)), then IN(.; stats) + act —
+                                                           // conv_block_3's closing IN + ReLU straight from its raw conv output
 };
 struct PtcParams {
   PtcBlock blk[kPtcMaxKb];
@@ -122,8 +124,8 @@ __device__ __forceinline__ void ptc_load(const PtcBlock& B, int n, long long v, 
 }
 
 // registers -> fp32 values -> (x - mean) * rstd -> activation -> fp16 hi / lo rows of the A operand
-__device__ __forceinline__ void ptc_stage(const PtcBlock& B, const PtcVec& r, const float* mean /* -mean*rstd */, const float* rstd, bool valid,
-                                          uint8_t* dst_hi, uint8_t* dst_lo) {
+__device__ __forceinline__ void ptc_stage(const PtcBlock& B, const PtcVec& r, const float* mean /* -mean*rstd */, const float* rstd,
+                                          const float* mean0, const float* rstd0, bool valid, uint8_t* dst_hi, uint8_t* dst_lo) {
   float x[8];
   if (B.raw != nullptr) {
     x[0] = __uint_as_float(r.a.x); x[1] = __uint_as_float(r.a.y); x[2] = __uint_as_float(r.a.z); x[3] = __uint_as_float(r.a.w);
@@ -139,6 +141,11 @@ __device__ __forceinline__ void ptc_stage(const PtcBlock& B, const PtcVec& r, co
     }
   }
   if (valid) {
+    if (B.stats0 != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = fmaf(x[j], rstd0[j], mean0[j]);
+      ptc_act8(x, B.act0);
+    }
     if (B.stats != nullptr) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) x[j] = fmaf(x[j], rstd[j], mean[j]);
@@ -170,6 +177,7 @@ __global__ void __launch_bounds__(128, (NKB > 0 && NKB <= 4) ? 4 : 2) pointwise_
   __shared__ uint64_t mma_bar[2];
   __shared__ uint32_t tmem_base_smem;
   __shared__ float s_mean[kPtcMaxKb * 8], s_rstd[kPtcMaxKb * 8], s_bias[CO];
+  __shared__ float s_mean0[kPtcMaxKb * 8], s_rstd0[kPtcMaxKb * 8];       // first-stage constants (PtcBlock::stats0)
   __shared__ float s_stat[4][CO][2];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -191,6 +199,13 @@ __global__ void __launch_bounds__(128, (NKB > 0 && NKB <= 4) ? 4 : 2) pointwise_
     }
     s_mean[i] = -m * r;                                           // x * rstd + (-mean * rstd): one FFMA per element
     s_rstd[i] = r;
+    float m0 = 0.f, r0 = 1.f;
+    if (B.stats0 != nullptr) {
+      if (c < B.stat_C) ptc_finalize_stats(B.stats0, static_cast<size_t>(n) * B.stat_C + c, p.inv_vox, m0, r0);
+      else r0 = 0.f;
+    }
+    s_mean0[i] = -m0 * r0;
+    s_rstd0[i] = r0;
   }
   for (int i = tid; i < CO; i += 128) s_bias[i] = p.bias ? p.bias[i] : 0.f;
   for (int i = tid; i < 4 * CO * 2; i += 128) (&s_stat[0][0][0])[i] = 0.f;
@@ -309,7 +324,7 @@ __global__ void __launch_bounds__(128, (NKB > 0 && NKB <= 4) ? 4 : 2) pointwise_
       uint8_t* sh = a_stage + static_cast<size_t>(buf) * stage_bytes + tid * 16;
 #pragma unroll
       for (int kb = 0; kb < NKB; ++kb)
-        ptc_stage(p.blk[kb], cur[kb], &s_mean[kb * 8], &s_rstd[kb * 8], valid, sh + kb * 2048, sh + (NKB + kb) * 2048);
+        ptc_stage(p.blk[kb], cur[kb], &s_mean[kb * 8], &s_rstd[kb * 8], &s_mean0[kb * 8], &s_rstd0[kb * 8], valid, sh + kb * 2048, sh + (NKB + kb) * 2048);
       {
         const int nt = tile + 1;
         const long long vn = static_cast<long long>(nt) * 128 + tid;
@@ -350,7 +365,7 @@ __global__ void __launch_bounds__(128, (NKB > 0 && NKB <= 4) ? 4 : 2) pointwise_
       for (int kb = 0; kb < nkb; ++kb) {
         PtcVec r;
         ptc_load(p.blk[kb], n, v, valid, r);
-        ptc_stage(p.blk[kb], r, &s_mean[kb * 8], &s_rstd[kb * 8], valid, sh + kb * 2048, sh + (nkb + kb) * 2048);
+        ptc_stage(p.blk[kb], r, &s_mean[kb * 8], &s_rstd[kb * 8], &s_mean0[kb * 8], &s_rstd0[kb * 8], valid, sh + kb * 2048, sh + (nkb + kb) * 2048);
       }
       fence_proxy_async();               // generic-proxy smem writes -> visible to the tensor core (async proxy)
       tc_fence_before();                 // this thread's TMEM loads of the previous tile are complete (tcgen05.wait::ld)
@@ -433,7 +448,8 @@ static int launch_ptc(const PtcParams& p, int N, cudaStream_t stream) {
 
 extern "C" int dp_pointwise_tc(int nsrc, const void* const* src_hi, const void* const* src_lo, const float* const* src_raw,
                                const int* src_cb_total, const int* src_cb_off, const int* src_C,
-                               const double* const* src_stats, const int* src_act, const void* wpack, const float* bias,
+                               const double* const* src_stats, const int* src_act, const double* const* src_stats0,
+                               const int* src_act0, const void* wpack, const float* bias,
                                int cout, int N, long long vox, float* out_raw, void* out_hi, void* out_lo, int out_cb_total,
                                int out_cb_off, double* stats_out, int* err_flag, cudaStream_t stream) {
   using namespace dp;
@@ -459,6 +475,8 @@ extern "C" int dp_pointwise_tc(int nsrc, const void* const* src_hi, const void* 
       B.stats = src_stats ? src_stats[s] : nullptr;
       B.stat_c0 = b * 8; B.stat_C = src_C[s];
       B.act = src_act ? src_act[s] : 0;
+      B.stats0 = src_stats0 ? src_stats0[s] : nullptr;
+      B.act0 = (src_act0 && B.stats0) ? src_act0[s] : 0;
     }
   }
   if (kb & 1) ++kb;                    // K steps are 16 channels: an all-null block stages zeros

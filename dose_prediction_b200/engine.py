@@ -619,10 +619,19 @@ class Plan:
         self.steps[idx] = (getattr(self.lib, "dp_norm_act_head"), args, "dp_norm_act_head")
         del self._na_producer[(a.buf.data_ptr(), a.cb_off)]
 
+    def pointwise_tc_ok(self, Cs, Co):
+        """whether pointwise() will take the tcgen05 kernel for these source channel counts (the only path that can apply a
+        two-stage normalisation on load)"""
+        return (not self.training and POINTWISE_TCK and Co in (16, 32, 64) and sum(ceil_div(c, 8) for c in Cs) <= 16)
+
     def pointwise(self, srcs, weight, bias, out_raw=None, out_act=None, out_planar=None, out_act_fn=None):
-        """1x1x1 conv over cat(srcs); srcs: list of (Act|Raw, stats|None, act|None)."""
+        """1x1x1 conv over cat(srcs); srcs: list of (Act|Raw, stats|None, act|None) or, with a first normalisation stage
+        applied before that one, (Raw, stats, act, stats0, act0) (tcgen05 path only: check pointwise_tc_ok)."""
         hi, lo, raw, cbt, cbo, Cs, sts, acts = [], [], [], [], [], [], [], []
-        for t, st, act in srcs:
+        sts0, acts0 = [], []
+        for t, st, act, *pre in srcs:
+            sts0.append(pre[0].data_ptr() if pre else None)
+            acts0.append(ACT_ID[pre[1]] if pre else 0)
             if isinstance(t, Raw):
                 hi.append(None); lo.append(None); raw.append(t.t.data_ptr()); cbt.append(t.cb_total); cbo.append(0)
                 N, vox = t.t.shape[0], t.t.shape[2] * t.t.shape[3] * t.t.shape[4]
@@ -639,6 +648,9 @@ class Plan:
         arrs = [_lib.ptr_array(hi), _lib.ptr_array(lo), _lib.ptr_array(raw), _lib.int_array(cbt), _lib.int_array(cbo),
                 _lib.int_array(Cs), _lib.ptr_array(sts), _lib.int_array(acts)]
         self.keep.append(arrs)
+        two_stage = any(x is not None for x in sts0)
+        arrs0 = [_lib.ptr_array(sts0), _lib.int_array(acts0)] if two_stage else [None, None]
+        self.keep.append(arrs0)
         of = oh = ol = op = st = None
         ocb = ooff = 0
         if out_raw is not None:
@@ -648,7 +660,7 @@ class Plan:
             oh, ol, ocb, ooff = out_act.hi_ptr, out_act.lo_ptr, out_act.cb_total, out_act.cb_off
         if out_planar is not None:
             op = out_planar.data_ptr()
-        in_b = sum((ceil_div(t.C, 8) * 8) * (4 if isinstance(t, Raw) or t.lo_off is not None else 2) for t, _, _ in srcs)
+        in_b = sum((ceil_div(t.C, 8) * 8) * (4 if isinstance(t, Raw) or t.lo_off is not None else 2) for t, *_ in srcs)
         out_b = 0
         if out_raw is not None:
             out_b += 4 * ceil_div(Co, 8) * 8
@@ -673,9 +685,10 @@ class Plan:
             self.keep.append(wpk)
             self.count_flops("dp_pointwise_tc", 2.0 * N * vox * sum(Cs) * Co)
             self.count_bytes("dp_pointwise_tc", N * vox * (in_b + out_b))
-            self.add("dp_pointwise_tc", len(srcs), *arrs, wpk.data_ptr(), b.data_ptr() if b is not None else None, Co, N, vox,
-                     of, oh, ol, ocb, ooff, st, self.err.data_ptr())
+            self.add("dp_pointwise_tc", len(srcs), *arrs, *arrs0, wpk.data_ptr(), b.data_ptr() if b is not None else None, Co, N,
+                     vox, of, oh, ol, ocb, ooff, st, self.err.data_ptr())
             return
+        assert not two_stage, "pointwise: a two-stage normalisation on load needs the tcgen05 path (pointwise_tc_ok)"
         if (not self.training and POINTWISE_TC and ncb >= 12 and Co % 16 == 0 and out_raw is not None and out_act is None
                 and out_planar is None and out_act_fn is None and all(c % 16 == 0 for c in Cs)):
             # wide 1^3 convs of the coarse levels (128 / 256 input channels, few voxels): the SIMT kernel is latency

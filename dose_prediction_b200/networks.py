@@ -356,6 +356,11 @@ PREC_SEG_DEEP = Precision("p1", "p1", False)  # ... except the two coarsest leve
                                               # (oracle/precision_probe.py: argmax agreement unchanged, 99.95 / 99.91 %)
 
 
+# conv_3_1's 3^3 branch normalised on load by the 1^3 conv (statistics-only pass + two-stage IN in dp_pointwise_tc) instead of
+# materialising relu(IN(raw)).  Correct and 4 bytes / element lighter, but measured NEUTRAL at batch 8 x 128^3 (the read-only
+# statistics pass runs at 3.4 TB/s: 0.41 -> 0.32 ms, while the Mish-on-load 1^3 conv gets 0.03-0.07 ms slower): off by default.
+FUSE_BRANCH_NORM = os.environ.get("DP_FUSE_BRANCH_NORM", "0") != "0"
+
 _S2D_TAPS = {0: ((1, 1),), 1: ((0, 0), (1, 2))}     # input parity -> ((tap of the 3^3 stride-1 conv, original tap), ...)
 
 
@@ -622,12 +627,20 @@ def _emit_conv_3_1(P, blk, parts, out, prec):
     a = P.new_act(N, C, dims, lo=prec.lo)
     P.norm_act(raw, a, act="relu")
     P.release(raw)
-    raw = P.get_raw(N, C, dims)
-    P.conv_tc([a], c3[3].weight, 3, 1, prec.conv3, *P.affine(C, bias=c3[3].bias), False, out_raw=raw)
-    y3 = P.new_act(N, C, dims, lo=prec.lo)
+    raw3 = P.get_raw(N, C, dims)
+    P.conv_tc([a], c3[3].weight, 3, 1, prec.conv3, *P.affine(C, bias=c3[3].bias), False, out_raw=raw3)
     st3 = P.new_stats(N, C)
-    P.norm_act(raw, y3, act="relu", stats_out=st3)
-    P.release(raw)
+    fused3 = FUSE_BRANCH_NORM and P.pointwise_tc_ok([C, C], blk.conv[0].weight.shape[0])
+    if fused3:
+        # relu(IN(raw3)) is never materialised: one statistics-only pass (reads raw3), then the 1^3 conv applies IN + ReLU and
+        # the block's IN + act on load, straight from the fp32 conv output (8 instead of 12 bytes per element moved)
+        P.norm_act(raw3, None, act="relu", stats_out=st3)
+        src3 = (raw3, st3, act, raw3.stats, "relu")
+    else:
+        y3 = P.new_act(N, C, dims, lo=prec.lo)
+        P.norm_act(raw3, y3, act="relu", stats_out=st3)
+        P.release(raw3)
+        src3 = (y3, st3, act)
     # --- 7^3 branch: conv -> BN -> ReLU -> conv -> BN -> ReLU -> IN -> act
     a7 = P.new_act(N, C, dims, lo=(prec.conv7 != "p1"))
     P.conv_tc(parts, c7[0].weight, 7, 1, prec.conv7, *P.affine(C, bias=c7[0].bias, bn=c7[1]), True, out_act=a7)
@@ -636,7 +649,9 @@ def _emit_conv_3_1(P, blk, parts, out, prec):
     P.conv_tc([a7], c7[3].weight, 7, 1, prec.conv7, *P.affine(C, bias=c7[3].bias, bn=c7[4]), True, out_act=y7, stats=st7)
     # --- cat -> 1^3 conv -> IN -> act
     raw = P.get_raw(N, C, dims)
-    P.pointwise([(y3, st3, act), (y7, st7, act)], blk.conv[0].weight, blk.conv[0].bias, out_raw=raw)
+    P.pointwise([src3, (y7, st7, act)], blk.conv[0].weight, blk.conv[0].bias, out_raw=raw)
+    if fused3:
+        P.release(raw3)
     P.norm_act(raw, out, act=act)
     P.release(raw)
 

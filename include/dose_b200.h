@@ -176,10 +176,14 @@ int dp_pointwise_conv(int nsrc, const void* const* src_hi, const void* const* sr
  * operand layout; 3-term operand split (A_hi.[W_hi|W_lo] + A_lo.W_hi), fp32 accumulation in TMEM.
  *   wpack  fp16 [K/8][2*cout][8]: rows 0..cout-1 = fp16(W), rows cout..2cout-1 = fp16(W - fp16(W)); K = every source's
  *          channels padded to whole 8-channel blocks, then to a multiple of 16; cout in {16, 32, 64}, K <= 128.
+ *   src_stats0 / src_act0 (arrays or NULL; entries may be NULL): an optional FIRST normalisation stage per source,
+ *          x -> act0(IN(x; stats0)) before IN(.; stats) + act — conv_block_3's closing "IN, ReLU" (blocks_MDUNet.py:64-78)
+ *          followed by conv_3_1's IN + act (:150-157), both applied straight from the raw conv output.
  * Output: raw c8 fp32 (+ statistics) or c8 fp16 hi[/lo].                                                      */
 int dp_pointwise_tc(int nsrc, const void* const* src_hi, const void* const* src_lo, const float* const* src_raw,
                     const int* src_cb_total, const int* src_cb_off, const int* src_C, const double* const* src_stats,
-                    const int* src_act, const void* wpack, const float* bias, int cout, int N, long long vox,
+                    const int* src_act, const double* const* src_stats0, const int* src_act0, const void* wpack,
+                    const float* bias, int cout, int N, long long vox,
                     float* out_raw, void* out_hi, void* out_lo, int out_cb_total, int out_cb_off, double* stats_out,
                     int* err_flag, cudaStream_t stream);
 

@@ -424,6 +424,57 @@ def test_pointwise_tc_matches_torch(Cs, Co, dims, acts, lo, out_act):
         assert torch.allclose(st[..., 1], (got.double() ** 2).sum((2, 3, 4)), rtol=1e-4, atol=1e-2)
 
 
+def test_pointwise_tc_two_stage_norm_on_load_and_stats_only_pass():
+    """conv_3_1's 3^3 branch without its materialised output: a statistics-only norm pass over the raw conv output, then the
+    1^3 conv applying relu(IN(raw)) and IN + Mish on load (PtcBlock::stats0) — vs fp64 torch and vs the materialised path"""
+    torch.manual_seed(77)
+    dev = torch.device("cuda:0")
+    N, C, dims = 2, 16, (6, 10, 12)
+    x3 = torch.randn(N, C, *dims, device=dev) * 2 + 0.3
+    x7 = torch.randn(N, C, *dims, device=dev)
+    w = torch.randn(C, 2 * C, 1, 1, 1, device=dev) / (2 * C) ** 0.5
+    bias = torch.randn(C, device=dev)
+    outs = []
+    for fused in (True, False):
+        P = _plan()
+        raw3 = _raw_with_stats(P, x3)
+        a7 = _act_from(P, x7, True)
+        st7, y7 = P.new_stats(N, C), P.new_act(N, C, dims, lo=True)
+        P.norm_act(a7, y7, identity=True, stats_out=st7)
+        st3 = P.new_stats(N, C)
+        if fused:
+            P.norm_act(raw3, None, act="relu", stats_out=st3)
+            src3 = (raw3, st3, "mish", raw3.stats, "relu")
+        else:
+            y3 = P.new_act(N, C, dims, lo=True)
+            P.norm_act(raw3, y3, act="relu", stats_out=st3)
+            src3 = (y3, st3, "mish")
+        out = P.get_raw(N, C, dims)
+        P.pointwise([src3, (y7, st7, "mish")], w, bias, out_raw=out)
+        P.run()
+        _finish(P)
+        assert any(st[2] == "dp_pointwise_tc" for st in P.steps)
+        outs.append(_raw_to_ncdhw(out.t).cpu())
+    r3 = F.mish(F.instance_norm(F.relu(F.instance_norm(x3.double().cpu(), eps=1e-5)), eps=1e-5))
+    r7 = F.mish(F.instance_norm(x7.double().cpu(), eps=1e-5))
+    want = F.conv3d(torch.cat((r3, r7), 1), w.double().cpu(), bias.double().cpu())
+    assert _rel(outs[0], want) < 2e-5 and _rel(outs[1], want) < 2e-5
+    assert _rel(outs[0], outs[1]) < 2e-6
+
+
+def _raw_with_stats(P, x):
+    """fp32 NCDHW tensor -> Raw (c8 fp32) with its {sum, sumsq} instance statistics filled in"""
+    N, C = x.shape[0], x.shape[1]
+    raw = P.get_raw(N, C, tuple(x.shape[2:]))
+    raw.t.copy_(x.view(N, C // 8, 8, *x.shape[2:]).permute(0, 1, 3, 4, 5, 2))
+    raw.stats.view(N, C, 2)[..., 0] = x.double().sum((2, 3, 4))
+    raw.stats.view(N, C, 2)[..., 1] = (x.double() ** 2).sum((2, 3, 4))
+    pinned = raw.stats.clone()
+    P.keep.append(pinned)
+    P.add_py(lambda: raw.stats.copy_(pinned))          # Plan.run() zeroes the statistics arena at the start of a replay
+    return raw
+
+
 @pytest.mark.parametrize("dims", [(16, 16, 32), (9, 13, 40)])        # second: ragged tiles in every direction
 def test_one_channel_res_block_direct_conv_and_closed_form_residual(dims):
     """monai UnetResBlock with in_channels = 1 (seg encoder1): conv1 as the exact fp32 direct conv (dp_conv3d_c1) and the
