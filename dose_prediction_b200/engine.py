@@ -413,7 +413,7 @@ class Plan:
             Z = torch.cat((W.flip(4), torch.zeros_like(W[:, :, :, :, :1])), dim=4)            # dim 4 indexed by j
             rots = []
             for r in range(G):
-                idx = torch.tensor([(sl - r) % G for sl in range(G)], device=self.device)
+                idx = self._rot_index(G, r)
                 rots.append(Z.index_select(4, idx).permute(1, 5, 6, 2, 4, 0, 3))
             W = torch.stack(rots, dim=0).contiguous()
             if split_half:
@@ -451,6 +451,14 @@ class Plan:
         arr = (ctypes.c_uint8 * nch)(*chunks)
         self.keep.append(arr)
         return W, arr, nch
+
+    def _rot_index(self, G, r):
+        """device index tensor of ring rotation r (cached: re-packing may run inside a CUDA-graph capture, where a fresh
+        host -> device copy is not allowed)"""
+        cache = self.__dict__.setdefault("_rot_cache", {})
+        if (G, r) not in cache:
+            cache[(G, r)] = torch.tensor([(sl - r) % G for sl in range(G)], device=self.device)
+        return cache[(G, r)]
 
     def affine(self, Co, bias=None, bn=None):
         """epilogue y = acc*scale + shift from a conv bias and/or eval-mode BatchNorm3d (running stats)."""
