@@ -805,6 +805,149 @@ upsample2x_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ i
   if (out_lo != nullptr) st_global_v8u(out_lo + o0, lo);
 }
 
+// Quad variant (default): a thread owns source position (jd, jh, k) and produces the 2 x 2 x 2 output voxels
+// (2jd + pd, 2jh + ph, 2k + o).  With align_corners the source index of output 2j + p lies in [j - 1 + p, j + p], so those four
+// output rows need only the 3 x 3 source rows (jd - 1 .. jd + 1) x (jh - 1 .. jh + 1) at column k: 9 gathers for four rows
+// instead of 16, 9 independent loads in flight per thread, and the index arithmetic / barrier amortised over 256 output bytes
+// per thread.  Interpolation weights are l = s * o - (j - 1 + p) against the clamped neighbours (identical to torch's
+// floor-based form except exactly AT a knot, where both give the knot's value).
+template <int UP_COLS>
+__global__ void __launch_bounds__(256, 2)
+upsample2x_quad_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo, int in_cb_total, int in_cb_off,
+                       int ncb, int D, int H, int W, __half* out_hi, __half* out_lo, int out_cb_total, int out_cb_off) {
+  constexpr int TR = 256 / UP_COLS;
+  __shared__ float4 sm[TR][4][2][UP_COLS + 2];          // [thread row][pd * 2 + ph][channel half][column + 1]
+  const int Do = 2 * D, Ho = 2 * H, Wo = 2 * W;
+  const int kk = threadIdx.x & (UP_COLS - 1), r = threadIdx.x / UP_COLS;
+  const int chunks = (W + UP_COLS - 1) / UP_COLS;
+  const int k0 = (blockIdx.x % chunks) * UP_COLS, jh = (blockIdx.x / chunks) * TR + r;
+  const int k = k0 + kk;
+  const int jd = blockIdx.y;
+  const int cb = blockIdx.z % ncb, n = blockIdx.z / ncb;
+  const bool active = jh < H && k < W;
+  const float sd = Do > 1 ? static_cast<float>(D - 1) / static_cast<float>(Do - 1) : 0.f;
+  const float sh = Ho > 1 ? static_cast<float>(H - 1) / static_cast<float>(Ho - 1) : 0.f;
+  const float sw = Wo > 1 ? static_cast<float>(W - 1) / static_cast<float>(Wo - 1) : 0.f;
+  const size_t vox_i = static_cast<size_t>(D) * H * W;
+  if (active) {
+    float ld[2], lh[2];
+#pragma unroll
+    for (int pp = 0; pp < 2; ++pp) {
+      ld[pp] = sd * (2 * jd + pp) - static_cast<float>(jd - 1 + pp);
+      lh[pp] = sh * (2 * jh + pp) - static_cast<float>(jh - 1 + pp);
+    }
+    const size_t base = (static_cast<size_t>(n) * in_cb_total + in_cb_off + cb) * vox_i;
+    size_t rowoff[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        rowoff[i][j] = base + (static_cast<size_t>(min(max(jd - 1 + i, 0), D - 1)) * H + min(max(jh - 1 + j, 0), H - 1)) * W;
+    // corner weights of source slot i for output parity p: slot p carries 1 - l, slot p + 1 carries l
+    float wd[2][3], wh[2][3];
+#pragma unroll
+    for (int pp = 0; pp < 2; ++pp)
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        wd[pp][i] = i == pp ? 1.f - ld[pp] : (i == pp + 1 ? ld[pp] : 0.f);
+        wh[pp][i] = i == pp ? 1.f - lh[pp] : (i == pp + 1 ? lh[pp] : 0.f);
+      }
+    auto blend = [&](int col, int slot) {
+      float a[4][8];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) a[q][c] = 0.f;
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          float v[8];
+          load8(in_hi, in_lo, (rowoff[i][j] + col) * 8, v);
+#pragma unroll
+          for (int pd = 0; pd < 2; ++pd)
+#pragma unroll
+            for (int ph = 0; ph < 2; ++ph) {
+              if (i < pd || i > pd + 1 || j < ph || j > ph + 1) continue;        // compile-time: this slot is no corner
+              const float wgt = wd[pd][i] * wh[ph][j];
+#pragma unroll
+              for (int c = 0; c < 8; ++c) a[pd * 2 + ph][c] = fmaf(wgt, v[c], a[pd * 2 + ph][c]);
+            }
+        }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        sm[r][q][0][slot] = make_float4(a[q][0], a[q][1], a[q][2], a[q][3]);
+        sm[r][q][1][slot] = make_float4(a[q][4], a[q][5], a[q][6], a[q][7]);
+      }
+    };
+    blend(k, kk + 1);
+    // halo columns of the chunk: a clamped neighbour IS this thread's own column (no second gather)
+    if (kk == 0) {
+      if (k == 0) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { sm[r][q][0][0] = sm[r][q][0][1]; sm[r][q][1][0] = sm[r][q][1][1]; }
+      } else {
+        blend(k - 1, 0);
+      }
+    }
+    if (kk == UP_COLS - 1 || k == W - 1) {
+      if (k == W - 1) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { sm[r][q][0][kk + 2] = sm[r][q][0][kk + 1]; sm[r][q][1][kk + 2] = sm[r][q][1][kk + 1]; }
+      } else {
+        blend(k + 1, kk + 2);
+      }
+    }
+  }
+  __syncthreads();
+  if (!active) return;
+  float cw[2][3];
+#pragma unroll
+  for (int o = 0; o < 2; ++o) {
+    const float fw = sw * (2 * k + o);
+    const int w0 = static_cast<int>(fw);
+    const float lw = fw - w0;
+    const int pos = w0 - (k - 1);                       // 0 or 1
+    cw[o][0] = pos == 0 ? 1.f - lw : 0.f;
+    cw[o][1] = pos == 0 ? lw : 1.f - lw;
+    cw[o][2] = pos == 0 ? 0.f : lw;
+  }
+  const size_t vox_o = vox_i * 8;
+  const size_t obase = (static_cast<size_t>(n) * out_cb_total + out_cb_off + cb) * vox_o;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float acc[2][8];
+#pragma unroll
+    for (int o = 0; o < 2; ++o)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[o][j] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float4 lo4 = sm[r][q][0][kk + c], hi4 = sm[r][q][1][kk + c];
+      const float x[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc[0][j] = fmaf(cw[0][c], x[j], acc[0][j]);
+        acc[1][j] = fmaf(cw[1][c], x[j], acc[1][j]);
+      }
+    }
+    const size_t o0 = (obase + (static_cast<size_t>(2 * jd + (q >> 1)) * Ho + (2 * jh + (q & 1))) * Wo + 2 * k) * 8;
+    uint32_t hi[8], lo[8];
+#pragma unroll
+    for (int o = 0; o < 2; ++o)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const __half2 h2 = __floats2half2_rn(acc[o][2 * j], acc[o][2 * j + 1]);
+        const float2 f = __half22float2(h2);
+        const __half2 l2 = __floats2half2_rn(acc[o][2 * j] - f.x, acc[o][2 * j + 1] - f.y);
+        hi[o * 4 + j] = *reinterpret_cast<const uint32_t*>(&h2);
+        lo[o * 4 + j] = *reinterpret_cast<const uint32_t*>(&l2);
+      }
+    st_global_v8u(out_hi + o0, hi);
+    if (out_lo != nullptr) st_global_v8u(out_lo + o0, lo);
+  }
+}
+
 // ------------------------------------------------------------------ LayerNorm over the last dim (one warp per row)
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, int rows,
@@ -1383,6 +1526,22 @@ extern "C" int dp_upsample2x(const void* in_hi, const void* in_lo, int in_cb_tot
   int cols = 8;
   while (cols < 64 && cols < W) cols <<= 1;
   const int rows = 256 / cols, chunks = (W + cols - 1) / cols;
+  static const bool quad = [] { const char* e = getenv("DP_UPSAMPLE_QUAD"); return !e || atoi(e) != 0; }();   // A/B switch
+  if (quad) {
+    dim3 qgrid(static_cast<unsigned>(chunks * ((H + rows - 1) / rows)), D, N * ncb);
+#define DP_UPQ_LAUNCH(C_) upsample2x_quad_kernel<C_><<<qgrid, 256, 0, stream>>>(static_cast<const __half*>(in_hi), \
+      static_cast<const __half*>(in_lo), in_cb_total, in_cb_off, ncb, D, H, W, static_cast<__half*>(out_hi),        \
+      static_cast<__half*>(out_lo), out_cb_total, out_cb_off)
+    switch (cols) {
+      case 8: DP_UPQ_LAUNCH(8); break;
+      case 16: DP_UPQ_LAUNCH(16); break;
+      case 32: DP_UPQ_LAUNCH(32); break;
+      default: DP_UPQ_LAUNCH(64); break;
+    }
+#undef DP_UPQ_LAUNCH
+    DP_CHECK(cudaGetLastError());
+    return 0;
+  }
   dim3 grid(static_cast<unsigned>(chunks * ((2 * H + rows - 1) / rows)), 2 * D, N * ncb);
 #define DP_UP_LAUNCH(C_) upsample2x_kernel<C_><<<grid, 256, 0, stream>>>(static_cast<const __half*>(in_hi), \
       static_cast<const __half*>(in_lo), in_cb_total, in_cb_off, ncb, D, H, W, static_cast<__half*>(out_hi),  \
