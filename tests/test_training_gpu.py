@@ -322,7 +322,7 @@ def test_genloss_forward_backward_matches_oracle():
     pd = [p.detach().to(DEV).contiguous() for p in preds]
     for i, p in enumerate(pd):
         _lib.check(lib.dp_masked_l1(p.data_ptr(), gtd.data_ptr(), 2, 32, 32 >> i, acc[2 * i:].data_ptr(), 0, 0.0, None, s))
-    _lib.check(lib.dp_genloss_finalize(acc.data_ptr(), 4, 10.0, 8.0, out.data_ptr(), s))
+    _lib.check(lib.dp_genloss_finalize(acc.data_ptr(), 4, 10.0, 8.0, None, 0.0, out.data_ptr(), s))
     assert abs(float(out) - float(loss)) <= 1e-5 * abs(float(loss))
     for i, p in enumerate(pd):
         g = torch.empty_like(p)
