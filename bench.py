@@ -552,7 +552,7 @@ def main():
     avg_ms = top["ms"] / top["n"]
     ach = top["flops"] / (avg_ms / 1e3) / 1e12
     traffic = family_traffic = None
-    for tname in ("r2_traffic.json", "r1_traffic.json"):       # ncu dram__bytes_read.sum + dram__bytes_write.sum (profiles/)
+    for tname in ("r3_traffic.json", "r2_traffic.json", "r1_traffic.json"):       # ncu dram__bytes_read.sum + dram__bytes_write.sum (profiles/)
         tpath = os.path.join(ROOT, "profiles", tname)
         if os.path.exists(tpath):
             with open(tpath) as f:

@@ -147,11 +147,31 @@ __device__ __forceinline__ long long snap_cut(const StackParams& p, long long ra
 
 struct ItemIter {
   long long pos, end;
-  int item;
+  int item, full_left, full_col;
   __device__ __forceinline__ explicit ItemIter(const StackParams& p) {
     item = blockIdx.x;
-    pos = snap_cut(p, static_cast<long long>(blockIdx.x) * p.total_planes / gridDim.x);
-    end = (blockIdx.x + 1 == gridDim.x) ? p.total_planes : snap_cut(p, static_cast<long long>(blockIdx.x + 1) * p.total_planes / gridDim.x);
+    // phase 1: whole columns dealt round-robin (CTAs b and b + 1 stream ADJACENT columns at the same depth, so their H / W
+    // halos meet in L2: with contiguous shares alone the neighbours drift apart in depth and the 7^3 layers' DRAM traffic
+    // rose from 1.07x to 1.75x of the algorithmic bytes); phase 2: the remaining columns as one contiguous share per CTA
+    const long long cols = p.total_planes / p.D;
+    full_left = static_cast<int>(cols / gridDim.x);
+    full_col = blockIdx.x;
+    const long long base = static_cast<long long>(full_left) * gridDim.x * p.D, rest = p.total_planes - base;
+    pos = base + snap_cut(p, static_cast<long long>(blockIdx.x) * rest / gridDim.x);
+    end = (blockIdx.x + 1 == gridDim.x) ? p.total_planes : base + snap_cut(p, static_cast<long long>(blockIdx.x + 1) * rest / gridDim.x);
+  }
+  template <int KS>
+  __device__ __forceinline__ void column(const StackParams& p, int col, Item& it) {
+    constexpr int pad = (KS - 1) / 2;
+    int t = col;
+    const int wg = t % p.wgroups; t /= p.wgroups;
+    const int th = t % p.tiles_h;
+    it.n = t / p.tiles_h;
+    it.z0 = max(0, it.d0 - pad);
+    it.z1 = min(p.D - 1, it.d1 - 1 + pad);
+    it.h0 = th * 16;
+    it.w0 = wg * p.T * 8;
+    it.ntile = min(p.T, p.tiles_w - wg * p.T);
   }
   template <int KS>
   __device__ __forceinline__ bool next(const StackParams& p, Item& it) {
@@ -161,19 +181,18 @@ struct ItemIter {
       item += gridDim.x;
       return true;
     }
+    if (full_left > 0) {
+      it.d0 = 0;
+      it.d1 = p.D;
+      column<KS>(p, full_col, it);
+      full_col += gridDim.x;
+      --full_left;
+      return true;
+    }
     if (pos >= end) return false;
-    constexpr int pad = (KS - 1) / 2;
-    int t = static_cast<int>(pos / p.D);
     it.d0 = static_cast<int>(pos % p.D);
     it.d1 = static_cast<int>(min(static_cast<long long>(p.D), it.d0 + (end - pos)));
-    const int wg = t % p.wgroups; t /= p.wgroups;
-    const int th = t % p.tiles_h;
-    it.n = t / p.tiles_h;
-    it.z0 = max(0, it.d0 - pad);
-    it.z1 = min(p.D - 1, it.d1 - 1 + pad);
-    it.h0 = th * 16;
-    it.w0 = wg * p.T * 8;
-    it.ntile = min(p.T, p.tiles_w - wg * p.T);
+    column<KS>(p, static_cast<int>(pos / p.D), it);
     pos += it.d1 - it.d0;
     return true;
   }
