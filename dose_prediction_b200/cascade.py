@@ -4,6 +4,7 @@ the per-rank volume sharding used for multi-GPU inference (volumes are independe
 """
 import torch
 
+from . import engine
 from .engine import Plan
 from .networks import emit_dose_pyfer, emit_oar_transeg
 
@@ -55,6 +56,8 @@ class CascadePlan:
         P.handoff(self.logits, self.ptv, self.ct, dose_x, self.structures)
         self.out_A, self.outs = emit_dose_pyfer(P, dose_model, dose_x, a_out)
         self.plan = P
+        if engine.COMPACT:
+            P.compact()
         if graph:
             P.capture()
 

@@ -25,6 +25,7 @@ STACK_TILES = int(os.environ.get("DP_STACK_TILES", "0"))
 FOLD_P3 = os.environ.get("DP_FOLD_P3", "1") != "0"
 CONV_C1 = os.environ.get("DP_CONV_C1", "1") != "0"              # bring-up switch: one-channel 3^3 conv + closed-form residual (seg encoder1)
 POINTWISE_TCK = os.environ.get("DP_POINTWISE_TCK", "1") != "0"  # bring-up switch: 1^3 convs on tcgen05 with normalise-on-load
+COMPACT = os.environ.get("DP_COMPACT", "1") != "0"             # liveness-packed activation arena for inference plans (Plan.compact)
 FUSE_HEADS = os.environ.get("DP_FUSE_HEADS", "1") != "0"         # bring-up switch: 1^3 heads folded into the producing norm_act
 STACK_SPLIT_HALF = os.environ.get("DP_STACK_SPLIT_HALF", "1") != "0"   # bring-up switch: split-half folded 3^3 stacked conv
 FOLD_TC_MAX = int(os.environ.get("DP_FOLD_TC_MAX", "32"))        # plain tcgen05 conv: fold [W_hi | W_lo] into N up to this C_out
@@ -136,6 +137,7 @@ class Plan:
         self.refresh = []        # (packed tensor, function returning its new value)
         self.refresh_launches = []   # (C entry point name, args): device-side re-packing of live parameters
         self._na_producer = {}       # (buffer ptr, cb_off) -> the plain norm_act launch that wrote that activation
+        self._poolable = []          # activation / pre-norm buffers compact() may overlay by liveness (fully written tensors only)
 
     # ------------------------------------------------------------------ memory
     def zeros(self, shape, dtype):
@@ -144,19 +146,24 @@ class Plan:
         self.keep.append(t)
         return t
 
-    def new_buf(self, N, cb_total, dims):
-        return self.zeros((N, cb_total) + tuple(dims) + (8,), torch.float16)
+    def new_buf(self, N, cb_total, dims, poolable=False):
+        t = self.zeros((N, cb_total) + tuple(dims) + (8,), torch.float16)
+        if poolable:
+            self._poolable.append(t)
+        return t
 
     def new_act(self, N, C, dims, lo=False):
         nb = blocks16(C)
-        buf = self.new_buf(N, nb * (2 if lo else 1), dims)
+        # channel counts that are not a multiple of 16 leave padding blocks nobody writes: they rely on the zero fill of
+        # their own allocation and are never overlaid with other tensors
+        buf = self.new_buf(N, nb * (2 if lo else 1), dims, poolable=(C % 16 == 0))
         return Act(buf, 0, C, nb if lo else None)
 
     def new_concat(self, N, Cs, dims, lo=False):
         """one buffer holding the channel concatenation of len(Cs) tensors (torch.cat made free)."""
         nbs = [blocks16(c) for c in Cs]
         tot = sum(nbs)
-        buf = self.new_buf(N, tot * (2 if lo else 1), dims)
+        buf = self.new_buf(N, tot * (2 if lo else 1), dims, poolable=all(c % 16 == 0 for c in Cs))
         acts, off = [], 0
         for c, nb in zip(Cs, nbs):
             acts.append(Act(buf, off, c, tot + off if lo else None))
@@ -174,7 +181,12 @@ class Plan:
     def get_raw(self, N, C, dims, with_stats=True):
         key = (N, blocks16(C)) + tuple(dims)
         free = self.pool.setdefault(key, [])
-        t = free.pop() if free else self.zeros((N, blocks16(C)) + tuple(dims) + (8,), torch.float32)
+        if free:
+            t = free.pop()
+        else:
+            t = self.zeros((N, blocks16(C)) + tuple(dims) + (8,), torch.float32)
+            if C % 16 == 0:
+                self._poolable.append(t)
         return Raw(t, C, self.new_stats(N, C) if with_stats else None)
 
     def release(self, raw):
@@ -372,6 +384,95 @@ class Plan:
                 self.graph.replay()
         else:
             self.run()
+
+    # ------------------------------------------------------------------ liveness-packed activation arena
+    def compact(self):
+        """Overlay the plan's activation / pre-norm buffers in ONE arena by liveness.  Every launch is a
+        (C function, args) tuple, so a buffer's lifetime is [first, last] launch whose arguments point into it; buffers whose
+        lifetimes do not overlap share addresses (largest first, first fit).  Launch arguments (plain pointers and the
+        pointer arrays of the multi-source entry points) are rewritten and the tensors re-bound to the arena with set_(), so
+        Act / Raw objects held elsewhere stay valid.  Only fully written tensors take part (see new_act); plans with
+        host-side steps (trainers, sliding-window accumulation) are left as they are.  Returns (bytes before, bytes after)."""
+        if self.training or self.graph is not None or not self._poolable:
+            return None
+        if any(fn is None and name in ("py", "py_host") for fn, _, name in self.steps):
+            return None
+        bufs = []
+        for t in {id(t): t for t in self._poolable}.values():
+            nbytes = t.numel() * t.element_size()
+            bufs.append({"t": t, "ptr": t.data_ptr(), "n": nbytes, "first": None, "last": None})
+        bufs.sort(key=lambda b: b["ptr"])
+        import bisect
+        starts = [b["ptr"] for b in bufs]
+
+        def find(v):
+            if not isinstance(v, int) or v < (1 << 40):
+                return None
+            i = bisect.bisect_right(starts, v) - 1
+            if i >= 0 and v < bufs[i]["ptr"] + bufs[i]["n"]:
+                return bufs[i]
+            return None
+
+        def touch(b, i):
+            b["first"] = i if b["first"] is None else b["first"]
+            b["last"] = i
+
+        arrays = {}
+        for i, (fn, args, name) in enumerate(self.steps):
+            if fn is None:                      # "zero" steps re-zero plan-owned accumulators, never pooled buffers
+                continue
+            for a in args:
+                if isinstance(a, ctypes.Array) and a._type_ is ctypes.c_void_p:
+                    arrays[id(a)] = a
+                    for v in a:
+                        b = find(v)
+                        if b is not None:
+                            touch(b, i)
+                else:
+                    b = find(a)
+                    if b is not None:
+                        touch(b, i)
+        live = [b for b in bufs if b["first"] is not None]
+        if not live:
+            return None
+        placed = []
+        for b in sorted(live, key=lambda b: -b["n"]):
+            size = (b["n"] + 1023) // 1024 * 1024
+            taken = sorted((q["off"], q["off"] + q["size"]) for q in placed
+                           if not (q["last"] < b["first"] or b["last"] < q["first"]))
+            off = 0
+            for lo, hi in taken:
+                if off + size <= lo:
+                    break
+                off = max(off, hi)
+            b["off"], b["size"] = off, size
+            placed.append(b)
+        total = max(b["off"] + b["size"] for b in placed)
+        before = sum(b["n"] for b in live)
+        arena = torch.zeros(total, dtype=torch.uint8, device=self.device)
+        base = arena.data_ptr()
+
+        def remap(v):
+            b = find(v)
+            if b is None or "off" not in b:
+                return v
+            return base + b["off"] + (v - b["ptr"])
+        for a in arrays.values():
+            for j in range(len(a)):
+                if a[j] is not None:
+                    a[j] = remap(a[j])
+        self.steps = [(fn, args if fn is None else tuple(remap(a) for a in args), name) for fn, args, name in self.steps]
+        self._na_producer = {}
+        pooled = {id(b["t"]) for b in placed}
+        for b in placed:
+            t = b["t"]
+            t.set_(arena[b["off"]:b["off"] + b["n"]].view(t.dtype).view(t.shape))
+        self.keep = [k for k in self.keep if not (isinstance(k, torch.Tensor) and id(k) in pooled)]
+        self.keep.append(arena)
+        self.pool = {}
+        self.bytes_alloc += total - before
+        self.arena_bytes = (before, total)
+        return before, total
 
     # ------------------------------------------------------------------ weight packing
     def pack_conv_tc(self, w, parts, mode, stacked=False, _values_only=False, split_half=False):

@@ -24,6 +24,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
+from . import engine
 from .engine import Act, Plan, Raw, Tokens, blocks16, ceil_div
 
 
@@ -783,6 +784,8 @@ class _PlanCache:
             self.version = (ver, ptrs)
         if key not in self.plans:
             self.plans[key] = builder()
+            if engine.COMPACT:
+                self.plans[key].compact()
         return self.plans[key]
 
 

@@ -414,3 +414,32 @@ def test_captured_training_step_replays_the_eager_schedule():
             for k, v in model.state_dict().items():
                 assert torch.equal(v, final[k]), k
     assert losses["eager"] == losses["graph"], losses
+
+
+def test_liveness_arena_is_bit_identical_and_smaller(monkeypatch):
+    """Plan.compact(): activation / pre-norm buffers overlaid by liveness in one arena — the cascade's outputs must not change
+    by a bit (eager and as a CUDA graph), over several replays with different inputs, and the activation memory must shrink"""
+    from dose_prediction_b200 import engine, synth
+    from dose_prediction_b200.cascade import CascadePlan
+    from test_networks_gpu import _dose_model, _sd, _seg_model
+    outs, mem = {}, {}
+    batches = [synth.make_batch(2, 32, seed=300 + i) for i in range(3)]
+    for compact in (False, True):
+        monkeypatch.setattr(engine, "COMPACT", compact)
+        for graph in (False, True):
+            casc = CascadePlan(_seg_model(32, _sd("oar_transeg", 32, 1)), _dose_model(32, _sd("dose_pyfer", 32, 0)), 2, 32, "cuda:0",
+                               graph=graph)
+            res = []
+            for b in batches:
+                res.append((casc(b["ct"].cuda(), b["ptv"].cuda()).clone(), casc.logits.clone()))
+            torch.cuda.synchronize()
+            casc.plan.check_device_errors()
+            outs[(compact, graph)] = res
+            mem[(compact, graph)] = (casc.plan.bytes_alloc, getattr(casc.plan, "arena_bytes", None))
+    for graph in (False, True):
+        for (d0, l0), (d1, l1) in zip(outs[(False, graph)], outs[(True, graph)]):
+            assert torch.equal(d0, d1) and torch.equal(l0, l1)
+    before, after = mem[(True, False)][1]
+    print("activation bytes %d -> arena %d" % (before, after))
+    assert after < 0.7 * before
+    assert mem[(True, False)][0] < mem[(False, False)][0]
