@@ -10,8 +10,11 @@
 //
 // Operands: q, k [BH][T][HD] fp16 (q pre-scaled by hd^-0.5 in the qkv GEMM epilogue), v^T [BH][HD][Tp] fp16 (zero
 // padded key axis, 8 | Tp), all read through 3-D TMA maps so that rows / keys past T are zero-filled per head.
-// Warp roles (192 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2..5 softmax + epilogue
-// (thread <-> TMEM lane <-> query row).  TMEM: 128 columns S + HD columns O (256 allocated: two CTAs per SM).
+// Warp roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2..9 softmax + epilogue: thread <->
+// TMEM lane <-> query row, and the TWO warps of a lane quarter split the 128 key columns of a score block (and the columns
+// of O) in halves — the softmax warps were the issue-bound part (ncu: 47 % issue-active at four warps); the halves' row
+// maxima / row sums are combined once per pass through shared memory.  TMEM: 128 columns S + HD columns O (256 allocated:
+// two CTAs per SM).
 #include "common.cuh"
 #include "dose_b200.h"
 
@@ -23,7 +26,8 @@ struct AttnParams {
   int* err_flag;
 };
 
-constexpr int kAttnThreads = 192;
+constexpr int kAttnThreads = 320;
+constexpr int kAttnSoftmaxWarps = 8;
 constexpr int kAttnKStages = 2;
 
 template <int HD> struct AttnCfg {
@@ -80,6 +84,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   __shared__ uint64_t q_full, k_full[kAttnKStages], k_empty[kAttnKStages], v_full, v_empty;
   __shared__ uint64_t s_full, s_empty, p_full, p_empty, o_full;
   __shared__ uint32_t tmem_base_smem;
+  __shared__ float xch[2][128];                                     // row maximum / row sum of the other column half
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + Cfg::kQBytes;
@@ -97,8 +102,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     mbar_init(&q_full, 1);
     for (int i = 0; i < kAttnKStages; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
     mbar_init(&v_full, 1); mbar_init(&v_empty, 1);
-    mbar_init(&s_full, 1); mbar_init(&s_empty, 4);
-    mbar_init(&p_full, 4); mbar_init(&p_empty, 1);
+    mbar_init(&s_full, 1); mbar_init(&s_empty, kAttnSoftmaxWarps);
+    mbar_init(&p_full, kAttnSoftmaxWarps); mbar_init(&p_empty, 1);
     mbar_init(&o_full, 1);
     fence_barrier_init();
   }
@@ -179,8 +184,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       __syncwarp();
     }
   } else {
-    // ===================================================================== softmax + epilogue (warps 2..5)
+    // ===================================================================== softmax + epilogue (warps 2..9)
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;                               // key columns [64 half, 64 half + 64) of every score block
     const int row = quarter * 32 + lane;                            // TMEM lane == query row of the tile
     const uint32_t t_s = tmem_s + (static_cast<uint32_t>(quarter * 32) << 16);
     const uint32_t t_o = tmem_o + (static_cast<uint32_t>(quarter * 32) << 16);
@@ -192,7 +198,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       if (!mbar_wait(&s_full, it & 1, p.err_flag)) goto teardown;
       tc_fence_after();
 #pragma unroll 1
-      for (int c0 = 0; c0 < 128; c0 += 32) {
+      for (int c0 = half * 64; c0 < half * 64 + 64; c0 += 32) {
         uint32_t r[2][16];
         tmem_ld16(t_s + c0, r[0]);
         tmem_ld16(t_s + c0 + 16, r[1]);
@@ -207,6 +213,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty);
     }
+    // the row maximum over both column halves
+    xch[half][row] = m;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    m = fmaxf(m, xch[half ^ 1][row]);
+    asm volatile("bar.sync 1, 256;" ::: "memory");                  // xch is reused for the row sums
     // ---- pass 2: P = exp(S - m) -> smem, l = sum P
     const float mb = m * kLog2e;
     float l0 = 0.f, l1 = 0.f;
@@ -218,12 +229,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       tc_fence_after();
       if (!mbar_wait(&p_empty, (j & 1) ^ 1, p.err_flag)) goto teardown;     // P V_{j-1} has read the tile
 #pragma unroll 1
-      for (int c0 = 0; c0 < 128; c0 += 32) {
+      for (int c0 = half * 64; c0 < half * 64 + 64; c0 += 32) {
         uint32_t r[2][16];
         tmem_ld16(t_s + c0, r[0]);
         tmem_ld16(t_s + c0 + 16, r[1]);
         tmem_ld_wait();
-        if (c0 == 96) {                                             // S is in registers: release it for Q K_{j+1}^T
+        if (c0 == half * 64 + 32) {                                 // S is in registers: release it for Q K_{j+1}^T
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&s_empty);
@@ -255,12 +266,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     if (!mbar_wait_relaxed(&o_full, 0, p.err_flag)) goto teardown;
     tc_fence_after();
     {
-      const float inv_l = 1.f / (l0 + l1);
+      xch[half][row] = l0 + l1;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float inv_l = 1.f / (xch[0][row] + xch[1][row]);
       const int t = q0 + row;
       const int b = bh / p.heads, hh = bh % p.heads;
       __half* dst = p.out + (static_cast<size_t>(b) * p.T + t) * p.ld_out + hh * HD;
 #pragma unroll 1
-      for (int c0 = 0; c0 < HD; c0 += 32) {
+      for (int c0 = half * (HD / 2); c0 < (half + 1) * (HD / 2); c0 += 32) {
         uint32_t r[2][16];
         tmem_ld16(t_o + c0, r[0]);
         tmem_ld16(t_o + c0 + 16, r[1]);
