@@ -22,7 +22,7 @@ __global__ void __launch_bounds__(128, 1) mma_mix(int Na, int Nb, int planes, in
   __shared__ uint32_t tbase;
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < 160 * 1024 / 2; i += blockDim.x) {       // random operands in [-1, 1): power draw depends on the data
+  for (int i = threadIdx.x; i < 196 * 1024 / 2; i += blockDim.x) {       // random operands in [-1, 1): power draw depends on the data
     uint32_t h = (i + 1) * 2654435761u; h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
     reinterpret_cast<__half*>(smem)[i] = __float2half_rn((h & 0xFFFF) / 32768.0f - 1.0f);
   }
@@ -37,8 +37,10 @@ __global__ void __launch_bounds__(128, 1) mma_mix(int Na, int Nb, int planes, in
     const uint32_t ia = make_idesc_f16(M, Na), ib = make_idesc_f16(M, Nb > 0 ? Nb : 16);
     const uint32_t sa16 = smem_u32(smem) >> 4, sb16 = (smem_u32(smem) + 100 * 1024) >> 4;
     const uint32_t a_hi = PW | (1u << 14), b_hi = 8u | (1u << 14);
-    const uint32_t a_lo_c = ((PH * PW) & 0x3FFFu) << 16, b_lo_c = (128u << 16);
-    const uint32_t tap_b16 = (32u * 128u) >> 4;                      // [2][128 rows][8] fp16 per tap
+    const uint32_t a_lo_c = ((PH * PW) & 0x3FFFu) << 16, b_lo_c = ((Na > 128 ? 256u : 128u) << 16);
+    const uint32_t brows = Na > 128 ? 256u : 128u;
+    const uint32_t tap_b16 = (32u * brows) >> 4;                     // [2][rows][8] fp16 per tap
+    const uint32_t tile_cols = Na > 128 ? 256u : 128u;
     const uint32_t a_stage16 = (2u * PH * PW * 16u + 1023u) / 1024u * 64u;
     long long t0 = clock64();
     for (int pl = 0; pl < planes; ++pl) {
@@ -53,8 +55,8 @@ __global__ void __launch_bounds__(128, 1) mma_mix(int Na, int Nb, int planes, in
 #pragma unroll
           for (int kw = 0; kw < 3; ++kw)
 #pragma unroll
-            for (int t = 0; t < 2; ++t)
-              mma(tb + (w * 2 + t) * 128, ac + kh * PW + (aligned ? 0 : kw) + t * 8, a_hi, (b_lo_c | sb16) + (kh * 3 + kw) * tap_b16, b_hi, idesc);
+            for (int t = 0; t < (Na > 128 ? 1 : 2); ++t)
+              mma(tb + (w * (Na > 128 ? 1 : 2) + t) * tile_cols, ac + kh * PW + (aligned ? 0 : kw) + t * 8, a_hi, (b_lo_c | sb16) + (kh * 3 + kw) * tap_b16, b_hi, idesc);
       }
     }
     umma_commit(&bar[w]);
@@ -71,9 +73,9 @@ int main() {
   const int smem = 200 * 1024;
   cudaFuncSetAttribute(mma_mix, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-  const int cfg[][2] = {{128, 128}, {128, 64}, {64, 0}, {112, 0}, {128, 0}, {48, 0}, {32, 0}, {16, 0}};
-  for (int M = 128; M >= 64; M -= 64)
-  for (int aligned = 0; aligned < 2; ++aligned)
+  const int cfg[][2] = {{128, 128}, {128, 64}, {256, 0}, {256, 128}, {256, 256}, {192, 0}, {160, 0}, {128, 0}};
+  for (int M = 128; M >= 128; M -= 64)
+  for (int aligned = 0; aligned < 1; ++aligned)
     for (auto& c : cfg) {
       const int planes = 20000;
       for (int rep = 0; rep < 2; ++rep) {       // second repetition = warm (sustained) number
@@ -84,8 +86,8 @@ int main() {
         float ms; cudaEventElapsedTime(&ms, e0, e1);
         long long h[148]; cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
         double avg = 0; for (int i = 0; i < 148; ++i) avg += h[i]; avg /= 148;
-        const double mmas = planes * 9.0 * 4 * (c[1] ? 2 : 1);     // per CTA (both issuers)
-        const double cols = planes * 9.0 * 4 * (c[0] + c[1]);
+        const double mmas = planes * 9.0 * (c[0] > 128 ? 2 : 4) * (c[1] ? 2 : 1);     // per CTA (both issuers)
+        const double cols = planes * 9.0 * (c[0] > 128 ? 2 : 4) * (c[0] + c[1]);
         if (rep) printf("M=%d aligned=%d Na=%3d Nb=%3d : %6.1f cycles per tap (4 tiles, both chunks), %5.1f per MMA, %6.2f ms wall, %6.0f TF/s executed, clk %.0f MHz  %s\n",
                M, aligned, c[0], c[1], avg / (planes * 9.0), avg / mmas * 1.0, ms, cols * 128 * 16 * 2 * 148 / (ms * 1e-3) / 1e12,
                avg / (ms * 1e-3) / 1e6, cudaGetErrorString(e));
