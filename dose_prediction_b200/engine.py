@@ -419,7 +419,10 @@ class Plan:
 
         arrays = {}
         for i, (fn, args, name) in enumerate(self.steps):
-            if fn is None:                      # "zero" steps re-zero plan-owned accumulators, never pooled buffers
+            if fn is None:                      # "zero" step: the tensor it re-zeroes is in use at this point
+                b = find(args[0].data_ptr()) if isinstance(args[0], torch.Tensor) else None
+                if b is not None:
+                    touch(b, i)
                 continue
             for a in args:
                 if isinstance(a, ctypes.Array) and a._type_ is ctypes.c_void_p:

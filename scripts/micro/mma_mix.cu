@@ -1,6 +1,6 @@
 // Micro-benchmark: sustained rate of the depth-stacked conv's MMA stream for different column counts per chunk.
 // Mimics conv3d_stack_kernel<3,4>'s issue pattern: two issuing warps x 2 tiles, per "plane" 9 taps x {chunk a: N = Na,
-// chunk b: N = Nb} (Nb = 0: one chunk), A descriptors of the real halo patch (SBO = 34 x 16 B, taps shift the start by
+// chunk b: N = Nb} (Nb = 0: one chunk; Na > 128: one 256-column tile per issuer), A descriptors of the real halo patch (SBO = 34 x 16 B, taps shift the start by
 // 16 B / one patch row), B advancing one tap block per tap.  Reports SM cycles AND wall time (power capping shows up in
 // the latter only).   nvcc -arch=sm_100a -O3 -o mma_mix mma_mix.cu && ./mma_mix
 #include <cstdio>
