@@ -56,6 +56,7 @@ struct ConvTcParams {
   uint32_t tmem_cols;
   uint8_t chunk_cb[192];
   uint32_t tap_mask[192];    // per K-chunk bit mask over the k^3 taps (bit (kd*k+kh)*k+kw); zero bits are skipped
+  int masked;                // tap masks given (k = 3, one depth plane and all three kernel rows per stage)
 };
 
 constexpr int kConvThreads = 320;       // producer + MMA + 8 epilogue warps (2 per TMEM lane quarter)
@@ -99,6 +100,20 @@ __device__ __forceinline__ float colsum16(const float (&v)[16], int lane) {
   const float keep = h1 ? c[1] : c[0], send = h1 ? c[0] : c[1];
   float r = keep + __shfl_xor_sync(0xffffffffu, send, 2);
   r += __shfl_xor_sync(0xffffffffu, r, 1);
+  return r;
+}
+
+// Tap-masked (space-to-depth) convs: the valid taps of one depth plane form a rectangle [h0, h1] x [w0, w1] of the 3 x 3
+// in-plane taps (the mask is a product set per input parity class), typically 1-4 of 9.  Producer and issuer derive the
+// rectangle from the mask; only its weight blocks are copied, packed row by row (a stage was 20 KB of patch + 18 KB of
+// weights for 1-4 MMAs per tile: the layers ran at the L2 -> SM bandwidth).
+struct TapRect { int h0, h1, w0, w1; };
+__device__ __forceinline__ TapRect tap_rect3(uint32_t m9) {
+  TapRect r;
+  const uint32_t rows = ((m9 & 7u) ? 1u : 0u) | (((m9 >> 3) & 7u) ? 2u : 0u) | (((m9 >> 6) & 7u) ? 4u : 0u);
+  const uint32_t cols = (m9 | (m9 >> 3) | (m9 >> 6)) & 7u;
+  r.h0 = __ffs(rows) - 1; r.h1 = 31 - __clz(rows);
+  r.w0 = __ffs(cols) - 1; r.w1 = 31 - __clz(cols);
   return r;
 }
 
@@ -174,6 +189,16 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
             if (elect_one()) {
               uint8_t* sa = smem + static_cast<size_t>(stage) * p.stage_bytes;
               uint8_t* sb = sa + p.a_bytes_al;
+              if (KS == 3 && p.masked) {
+                // only the valid taps' weight blocks, packed row by row
+                const TapRect tr = tap_rect3((p.tap_mask[c] >> (kd0 * 9)) & 0x1FFu);
+                const uint32_t nw = static_cast<uint32_t>(tr.w1 - tr.w0 + 1), nh = static_cast<uint32_t>(tr.h1 - tr.h0 + 1);
+                mbar_arrive_expect_tx(&full_bar[stage], p.a_bytes + nh * nw * tap_b_bytes);
+                tma_load_5d(sa, &tmap_in, &full_bar[stage], 0, w0 - p.pad, h0 - p.pad, dz, n * p.cb_total_in + p.chunk_cb[c]);
+                for (uint32_t r = 0; r < nh; ++r)
+                  bulk_load_1d(sb + r * nw * tap_b_bytes, wsrc + static_cast<size_t>((tr.h0 + r) * 3 + tr.w0) * 16 * p.cout,
+                               nw * tap_b_bytes, &full_bar[stage]);
+              } else {
               const uint32_t b_bytes = static_cast<uint32_t>(cnt * KS) * tap_b_bytes;
               mbar_arrive_expect_tx(&full_bar[stage], p.a_bytes + b_bytes * p.kd_s);
               tma_load_5d(sa, &tmap_in, &full_bar[stage], 0, w0 - p.pad, h0 - p.pad + kh0 * p.dil, dz,
@@ -181,6 +206,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
               for (int kdl = 0; kdl < p.kd_s; ++kdl)
                 bulk_load_1d(sb + kdl * b_bytes, wsrc + kdl * kd_w_halfs + static_cast<size_t>(kh0) * KS * 16 * p.cout,
                              b_bytes, &full_bar[stage]);
+              }
             }
             __syncwarp();
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -226,6 +252,20 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
               uint32_t b16 = sa16 + (p.a_bytes_al >> 4);
               const uint32_t mask = p.tap_mask[c];
               const uint32_t idesc = c < first_lo_chunk ? idesc_full : idesc_lo;
+              if (KS == 3 && p.masked) {
+                const TapRect tr = tap_rect3((mask >> (kdg * 9)) & 0x1FFu);
+                for (int kh = tr.h0; kh <= tr.h1; ++kh)
+                  for (int kw = tr.w0; kw <= tr.w1; ++kw) {
+                    const uint32_t a16 = sa16 + static_cast<uint32_t>(kh * p.dil * p.PW + kw * p.dil);
+#pragma unroll
+                    for (int tt = 0; tt < TG; ++tt)
+                      if (TG == 1 || tt < ntile)
+                        umma_f16_ss_split(tmem_d + static_cast<uint32_t>(tt * p.cout), a_lo_c | ((a16 + tt * 8) & 0x3FFFu), a_hi,
+                                          b_lo_c | (b16 & 0x3FFFu), b_hi, idesc, accumulate);
+                    accumulate = 1;
+                    b16 += tap_b16;
+                  }
+              } else
               for (int kdl = 0; kdl < p.kd_s; ++kdl) {
                 for (int khl = 0; khl < cnt; ++khl) {
                   uint32_t a16 = sa16 + static_cast<uint32_t>((kdl * p.PHs + khl * p.dil) * p.PW);
@@ -429,7 +469,8 @@ static int launch_conv_tc(const void* in_c8, int cb_total_in, const uint8_t* chu
   p.k = k; p.dil = dil; p.pad = dil * (k - 1) / 2;
   p.n_chunks = n_chunks; p.cb_total_in = cb_total_in; p.cout = cout;
   for (int i = 0; i < n_chunks; ++i) { p.chunk_cb[i] = chunk_cb[i]; p.tap_mask[i] = tap_mask ? tap_mask[i] : 0xFFFFFFFFu; }
-  DP_REQUIRE(tap_mask == nullptr || k <= 3, "dp_conv3d_tc: tap masks are supported for k <= 3 only");
+  DP_REQUIRE(tap_mask == nullptr || k == 3, "dp_conv3d_tc: tap masks are supported for k = 3 only");
+  p.masked = tap_mask != nullptr ? 1 : 0;
   // W-tile groups: for k <= 3 the layer is bound by the L2 -> SM weight stream (every 128-voxel tile re-reads all
   // weights), so T adjacent tiles share one stage; bounded by the double-buffered accumulators (2*T*cout <= 512 columns)
   p.tiles_w = (W + 7) / 8;
@@ -449,7 +490,21 @@ static int launch_conv_tc(const void* in_c8, int cb_total_in, const uint8_t* chu
     return ((a + 127) / 128) * 128 + sd * s * k * tap_b;
   };
   if (stage_bytes_for(kd_s, kh_s) > 64 * 1024) kd_s = 1;     // whole-depth stages only when they stay small
-  while (kh_s > 1 && stage_bytes_for(kd_s, kh_s) > 56 * 1024) --kh_s;
+  int masked_taps = 0;                                        // tap-masked convs: weight area = the largest valid tap rectangle
+  if (tap_mask != nullptr) {
+    for (int c = 0; c < n_chunks; ++c)
+      for (int kd = 0; kd < 3; ++kd) {
+        const uint32_t m9 = (tap_mask[c] >> (kd * 9)) & 0x1FFu;
+        if (!m9) continue;
+        const uint32_t rows = ((m9 & 7u) ? 1u : 0u) | (((m9 >> 3) & 7u) ? 2u : 0u) | (((m9 >> 6) & 7u) ? 4u : 0u);
+        const uint32_t cols = (m9 | (m9 >> 3) | (m9 >> 6)) & 7u;
+        auto span = [](uint32_t b) { int lo = 0, hi = 2; while (!((b >> lo) & 1u)) ++lo; while (!((b >> hi) & 1u)) --hi; return hi - lo + 1; };
+        const int area = span(rows) * span(cols);
+        if (area > masked_taps) masked_taps = area;
+      }
+    DP_REQUIRE(masked_taps >= 1, "dp_conv3d_tc: every tap is masked");
+  }
+  while (!masked_taps && kh_s > 1 && stage_bytes_for(kd_s, kh_s) > 56 * 1024) --kh_s;
   p.kd_s = kd_s;
   p.n_kdg = k / kd_s;
   p.kh_s = kh_s;
@@ -458,6 +513,8 @@ static int launch_conv_tc(const void* in_c8, int cb_total_in, const uint8_t* chu
   p.a_bytes = 2u * kd_s * p.PHs * p.PW * 16u;
   p.a_bytes_al = ((p.a_bytes + 127u) / 128u) * 128u;
   p.stage_bytes = ((static_cast<uint32_t>(stage_bytes_for(kd_s, kh_s)) + 1023u) / 1024u) * 1024u;
+  if (masked_taps)              // all three kernel rows of the patch, but only the valid rectangle's weight blocks
+    p.stage_bytes = ((p.a_bytes_al + static_cast<uint32_t>(masked_taps * tap_b) + 1023u) / 1024u) * 1024u;
   int stages = static_cast<int>((200u * 1024u) / p.stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   DP_REQUIRE(stages >= 2, "dp_conv3d_tc: stage of %u bytes does not fit twice in shared memory", p.stage_bytes);
