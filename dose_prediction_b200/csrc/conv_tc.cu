@@ -57,6 +57,11 @@ struct ConvTcParams {
   uint8_t chunk_cb[192];
   uint32_t tap_mask[192];    // per K-chunk bit mask over the k^3 taps (bit (kd*k+kh)*k+kw); zero bits are skipped
   int masked;                // tap masks given (k = 3, one depth plane and all three kernel rows per stage)
+  // depth-pair mode (fold == 2): a tile covers output planes (d, d + 1); the MMA columns are [plane d: C_out | plane d + 1:
+  // C_out] and the k + 1 "virtual" depth taps v = 0..k carry the weight rows [W[kd = v] | W[kd = v - 1]] (zero where the tap
+  // does not exist): input plane d + v - pad is read ONCE for both output planes, and an N = 64 MMA (48 cycles for 64
+  // columns, scripts/micro/mma_mix.cu) becomes an N = 128 MMA (64 cycles for 128)
+  int dpair, Dt, acc_bufs;   // Dt = d-tiles per image (D, or ceil(D / 2)); accumulator buffers in TMEM (2, or 1 when T * cout fills it)
 };
 
 constexpr int kConvThreads = 320;       // producer + MMA + 8 epilogue warps (2 per TMEM lane quarter)
@@ -153,7 +158,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   for (int i = threadIdx.x; i < kConvEpiWarps * 256 * 2; i += kConvThreads) (&stat_acc[0][0][0])[i] = 0.f;
-  for (int i = threadIdx.x; i < (p.fold ? p.cout >> 1 : p.cout); i += kConvThreads) { s_scale[i] = p.scale[i]; s_shift[i] = p.shift[i]; }
+  for (int i = threadIdx.x; i < ((p.fold || p.dpair) ? p.cout >> 1 : p.cout); i += kConvThreads) { s_scale[i] = p.scale[i]; s_shift[i] = p.shift[i]; }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -172,8 +177,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
       int t = tile;
       const int tw = (t % p.groups_w) * p.T; t /= p.groups_w;
       const int th = t % p.tiles_h; t /= p.tiles_h;
-      const int d = t % p.D;
-      const int n = t / p.D;
+      const int d = (t % p.Dt) << p.dpair;
+      const int n = t / p.Dt;
       const int h0 = th * 16, w0 = tw * 8;
       for (int kdg = 0; kdg < p.n_kdg; ++kdg) {
         const int kd0 = kdg * p.kd_s;
@@ -231,10 +236,11 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
     uint32_t phase = 0;
     int iter = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++iter) {
-      const int d = (tile / tiles_per_plane) % p.D;
+      const int d = ((tile / tiles_per_plane) % p.Dt) << p.dpair;
       const int ntile = min(p.T, p.tiles_w - (tile % p.groups_w) * p.T);
-      const int slot = iter & 1;
-      if (!mbar_wait(&tmem_empty_bar[slot], ((iter >> 1) & 1) ^ 1, p.err_flag)) goto teardown;
+      const int slot = p.acc_bufs == 2 ? (iter & 1) : 0;
+      const int use = p.acc_bufs == 2 ? (iter >> 1) : iter;
+      if (!mbar_wait(&tmem_empty_bar[slot], (use & 1) ^ 1, p.err_flag)) goto teardown;
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(slot * p.T * p.cout);
       uint32_t accumulate = 0;
@@ -305,7 +311,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
     const int row = quarter * 32 + lane;
     const int hl = row >> 3, wl = row & 7;
     const int mycol = (lane >> 1) & 15;
-    const int cout_out = p.fold ? p.cout >> 1 : p.cout;
+    const int cout_out = (p.fold || p.dpair) ? p.cout >> 1 : p.cout;
     const float relu_floor = p.relu ? 0.f : -INFINITY;      // one FMNMX per value instead of a predicated pair
     int cur_n = -1;
     int iter = 0;
@@ -325,12 +331,13 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
       int t = tile;
       const int tw0 = (t % p.groups_w) * p.T; t /= p.groups_w;
       const int th = t % p.tiles_h; t /= p.tiles_h;
-      const int d = t % p.D;
-      const int n = t / p.D;
+      const int d = (t % p.Dt) << p.dpair;
+      const int n = t / p.Dt;
       if (n != cur_n) { flush_stats(cur_n); cur_n = n; }
       const int ntile = min(p.T, p.tiles_w - tw0);
-      const int slot = iter & 1;
-      if (!mbar_wait_relaxed(&tmem_full_bar[slot], (iter >> 1) & 1, p.err_flag)) goto teardown;
+      const int slot = p.acc_bufs == 2 ? (iter & 1) : 0;
+      const int use = p.acc_bufs == 2 ? (iter >> 1) : iter;
+      if (!mbar_wait_relaxed(&tmem_full_bar[slot], use & 1, p.err_flag)) goto teardown;
       tc_fence_after();
       for (int tt = 0; tt < ntile; ++tt) {
       const int h = th * 16 + hl, w = (tw0 + tt) * 8 + wl;
@@ -373,9 +380,13 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
           }
         }
       } else
+      for (int half = 0; half <= p.dpair; ++half) {       // depth-pair mode: columns [0, C_out) = plane d, [C_out, 2 C_out) = d + 1
+      if (d + half >= p.D) break;
+      const size_t vox = (static_cast<size_t>(d + half) * p.H + h) * p.W + w;
+      const uint32_t thalf = taddr + static_cast<uint32_t>(half * cout_out);
       for (int c0 = cgrp * 16; c0 < cout_out; c0 += 32) {
         uint32_t r[16];
-        tmem_ld16(taddr + c0, r);
+        tmem_ld16(thalf + c0, r);
         if (p.fold) {
           uint32_t r2[16];
           tmem_ld16(taddr + c0 + cout_out, r2);
@@ -433,6 +444,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
         }
       }
       }
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[slot]);
@@ -459,7 +471,11 @@ static int launch_conv_tc(const void* in_c8, int cb_total_in, const uint8_t* chu
                           void* out_lo, int cb_total_out, int cb_out_off, double* stats, int* err_flag,
                           int max_ctas, const uint32_t* tap_mask, int dc_co, int dc_q0, int fold, cudaStream_t stream) {
   DP_REQUIRE(fold == 0 || (cout <= 128 && dc_co == 0), "dp_conv3d_tc: fold needs C_out <= 128");
-  if (fold) cout *= 2;                 // MMA columns per tile; everything below sizes by the MMA N
+  const bool dpair = (fold == 2);      // depth-pair mode: two output planes per tile, k + 1 virtual depth taps
+  DP_REQUIRE(!dpair || (dil == 1 && tap_mask == nullptr && cout <= 64 && D >= 2), "dp_conv3d_tc: depth-pair mode needs dilation 1, "
+             "no tap masks, C_out <= 64 and D >= 2");
+  if (dpair) fold = 0;
+  if (fold || dpair) cout *= 2;        // MMA columns per tile; everything below sizes by the MMA N
   DP_REQUIRE(cout % 16 == 0 && cout >= 16 && cout <= 256, "dp_conv3d_tc: C_out=%d must be a multiple of 16 in [16,256]", cout);
   DP_REQUIRE(k >= 1 && k <= 7 && (k & 1), "dp_conv3d_tc: kernel size %d unsupported", k);
   DP_REQUIRE(n_chunks >= 1 && n_chunks <= 192, "dp_conv3d_tc: n_chunks=%d out of range", n_chunks);
@@ -476,6 +492,7 @@ static int launch_conv_tc(const void* in_c8, int cb_total_in, const uint8_t* chu
   p.tiles_w = (W + 7) / 8;
   int T = 1;
   if (k <= 3) T = cout <= 64 ? 4 : (cout <= 128 ? 2 : 1);
+  else if (k == 7 && dpair) T = 4;     // one accumulator buffer of 4 x 128 columns: the 4 KB weight blocks are shared by 4 tiles
   else if (k == 7 && cout <= 128) T = 2;
   while (T > 1 && T > p.tiles_w) T >>= 1;
   p.T = T;
@@ -483,7 +500,7 @@ static int launch_conv_tc(const void* in_c8, int cb_total_in, const uint8_t* chu
   p.PW = 8 * T + (k - 1) * dil;
   // stage sizing: as many kh rows per stage as fit ~56 KB, then as many stages as fit ~200 KB
   const int tap_b = 32 * cout;
-  int kh_s = k, kd_s = (dil == 1 && tap_mask == nullptr) ? k : 1;   // tap-masked (space-to-depth) convs: per-depth stages, empty ones skipped
+  int kh_s = k, kd_s = (dil == 1 && tap_mask == nullptr && !dpair) ? k : 1;   // tap-masked (space-to-depth) convs: per-depth stages, empty ones skipped
   auto stage_bytes_for = [&](int sd, int s) {
     const int phs = 16 + (s - 1) * dil;
     const int a = 2 * sd * phs * p.PW * 16;
@@ -506,7 +523,10 @@ static int launch_conv_tc(const void* in_c8, int cb_total_in, const uint8_t* chu
   }
   while (!masked_taps && kh_s > 1 && stage_bytes_for(kd_s, kh_s) > 56 * 1024) --kh_s;
   p.kd_s = kd_s;
-  p.n_kdg = k / kd_s;
+  p.n_kdg = dpair ? k + 1 : k / kd_s;
+  p.dpair = dpair ? 1 : 0;
+  p.Dt = dpair ? (D + 1) / 2 : D;
+  p.acc_bufs = (2 * T * cout <= 512) ? 2 : 1;
   p.kh_s = kh_s;
   p.n_khg = (k + kh_s - 1) / kh_s;
   p.PHs = 16 + (kh_s - 1) * dil;
@@ -520,7 +540,7 @@ static int launch_conv_tc(const void* in_c8, int cb_total_in, const uint8_t* chu
   DP_REQUIRE(stages >= 2, "dp_conv3d_tc: stage of %u bytes does not fit twice in shared memory", p.stage_bytes);
   p.stages = stages;
   p.tiles_h = (H + 15) / 16;
-  p.num_tiles = N * D * p.tiles_h * p.groups_w;
+  p.num_tiles = N * p.Dt * p.tiles_h * p.groups_w;
   p.wpack = static_cast<const __half*>(wpack);
   p.scale = scale; p.shift = shift; p.relu = relu;
   p.out_f32 = out_f32; p.out_hi = static_cast<__half*>(out_hi); p.out_lo = static_cast<__half*>(out_lo);
@@ -528,7 +548,8 @@ static int launch_conv_tc(const void* in_c8, int cb_total_in, const uint8_t* chu
   p.stats = stats; p.err_flag = err_flag;
   p.dc_co = dc_co; p.dc_q0 = dc_q0; p.fold = fold;
   uint32_t cols = 32;
-  while (cols < static_cast<uint32_t>(2 * T * cout)) cols <<= 1;
+  while (cols < static_cast<uint32_t>(p.acc_bufs * T * cout)) cols <<= 1;
+  DP_REQUIRE(cols <= 512, "dp_conv3d_tc: %d tiles x %d columns do not fit TMEM", T, cout);
   p.tmem_cols = cols;
 
   CUtensorMap tmap;
@@ -550,7 +571,7 @@ static int launch_conv_tc(const void* in_c8, int cb_total_in, const uint8_t* chu
 #define DP_TC_ATTR(K_, T_) DP_CHECK(cudaFuncSetAttribute(conv3d_tc_kernel<K_, T_>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem))
     DP_TC_ATTR(1, 1); DP_TC_ATTR(1, 2); DP_TC_ATTR(1, 4);
     DP_TC_ATTR(3, 1); DP_TC_ATTR(3, 2); DP_TC_ATTR(3, 4);
-    DP_TC_ATTR(5, 1); DP_TC_ATTR(7, 1); DP_TC_ATTR(7, 2);
+    DP_TC_ATTR(5, 1); DP_TC_ATTR(7, 1); DP_TC_ATTR(7, 2); DP_TC_ATTR(7, 4);
 #undef DP_TC_ATTR
   }
 #define DP_TC_LAUNCH(K_, T_) conv3d_tc_kernel<K_, T_><<<grid, kConvThreads, smem, stream>>>(tmap, p)
@@ -558,7 +579,7 @@ static int launch_conv_tc(const void* in_c8, int cb_total_in, const uint8_t* chu
     case 1: if (T == 4) DP_TC_LAUNCH(1, 4); else if (T == 2) DP_TC_LAUNCH(1, 2); else DP_TC_LAUNCH(1, 1); break;
     case 3: if (T == 4) DP_TC_LAUNCH(3, 4); else if (T == 2) DP_TC_LAUNCH(3, 2); else DP_TC_LAUNCH(3, 1); break;
     case 5: DP_TC_LAUNCH(5, 1); break;
-    default: if (T == 2) DP_TC_LAUNCH(7, 2); else DP_TC_LAUNCH(7, 1); break;
+    default: if (T == 4) DP_TC_LAUNCH(7, 4); else if (T == 2) DP_TC_LAUNCH(7, 2); else DP_TC_LAUNCH(7, 1); break;
   }
 #undef DP_TC_LAUNCH
   DP_CHECK(cudaGetLastError());

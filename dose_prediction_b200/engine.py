@@ -28,6 +28,7 @@ POINTWISE_TCK = os.environ.get("DP_POINTWISE_TCK", "1") != "0"  # bring-up switc
 COMPACT = os.environ.get("DP_COMPACT", "1") != "0"             # liveness-packed activation arena for inference plans (Plan.compact)
 FUSE_HEADS = os.environ.get("DP_FUSE_HEADS", "1") != "0"         # bring-up switch: 1^3 heads folded into the producing norm_act
 STACK_SPLIT_HALF = os.environ.get("DP_STACK_SPLIT_HALF", "1") != "0"   # bring-up switch: split-half folded 3^3 stacked conv
+DEPTH_PAIR = os.environ.get("DP_DEPTH_PAIR", "1") != "0"       # plain conv kernel: two output planes per tile for 7^3, C_out = 64
 FOLD_TC_MAX = int(os.environ.get("DP_FOLD_TC_MAX", "32"))        # plain tcgen05 conv: fold [W_hi | W_lo] into N up to this C_out
 POINTWISE_CW = os.environ.get("DP_POINTWISE_CW", "1") != "0"     # bring-up switch: constant-bank weights for static 1^3 convs
 POINTWISE_TC = os.environ.get("DP_POINTWISE_TC", "1") != "0"    # bring-up switch: wide coarse-level 1^3 convs on the tensor cores
@@ -478,7 +479,7 @@ class Plan:
         return before, total
 
     # ------------------------------------------------------------------ weight packing
-    def pack_conv_tc(self, w, parts, mode, stacked=False, _values_only=False, split_half=False):
+    def pack_conv_tc(self, w, parts, mode, stacked=False, _values_only=False, split_half=False, dpair=False):
         """w [Co,Ci,k,k,k] fp32 (or a function returning it) -> fp16 [kd][chunk][kh][kw][2][Co][8] + per-chunk
         input block table.  mode p1: x_hi.W_hi;  p2: + x_lo.W_hi;  p3: + x_hi.W_lo  (operand splitting by K expansion)."""
         w_src = w
@@ -532,7 +533,12 @@ class Plan:
                 W = torch.cat((W.reshape(-1), first.reshape(-1)))
             W = W.half()
         else:         # [kd][chunk][kh][kw][khalf][co][e]
-            W = W.permute(4, 1, 5, 6, 2, 0, 3).contiguous().half()
+            W = W.permute(4, 1, 5, 6, 2, 0, 3).contiguous()
+            if dpair:
+                # depth-pair mode of dp_conv3d_tc: k + 1 virtual depth taps, rows [W[kd = v] | W[kd = v - 1]] (zeros at the ends)
+                z = torch.zeros_like(W[:1])
+                W = torch.cat((torch.cat((W, z), 0), torch.cat((z, W), 0)), dim=5).contiguous()
+            W = W.half()
         if _values_only:
             return W
         self.keep.append(W)
@@ -550,7 +556,7 @@ class Plan:
                                                                       *arrs, nch, int(stacked), W.data_ptr())))
             else:
                 self.refresh.append((W, lambda: self.pack_conv_tc(w_src, parts, mode, stacked, _values_only=True,
-                                                                  split_half=split_half)))
+                                                                  split_half=split_half, dpair=dpair)))
         assert max(chunks) < 256
         arr = (ctypes.c_uint8 * nch)(*chunks)
         self.keep.append(arr)
@@ -602,8 +608,11 @@ class Plan:
         if fold and k == 3 and STACK_SPLIT_HALF:
             fold = 2                    # split-half column layout: x_lo chunks issue N = 64 (conv3d_stack3h_kernel)
         fold_tc = (not stacked) and mode == "p3" and Co <= FOLD_TC_MAX and FOLD_P3
+        # 7^3 convs with C_out = 64 (plain kernel, N = 64 MMAs): two output planes per tile -> N = 128 (dp_conv3d_tc fold = 2)
+        dpair = (DEPTH_PAIR and not stacked and not self.training and mode == "p1" and k == 7 and Co == 64 and dil == 1
+                 and tap_mask_fn is None and D >= 2)
         wp, chunks, nch = self.pack_conv_tc(weight, parts, "p3f" if (fold or fold_tc) else mode, stacked=stacked,
-                                            split_half=(fold == 2))
+                                            split_half=(fold == 2), dpair=dpair)
         if out_raw is not None:
             of32, ohi, olo, cbt, cbo = out_raw.t.data_ptr(), None, None, out_raw.cb_total, 0
             st = out_raw.stats if stats is None else stats
@@ -624,7 +633,7 @@ class Plan:
         self.count_flops("dp_conv3d_tc", flops if tap_mask_fn is None else tap_mask_fn.flops)
         self.add("dp_conv3d_tc", a0.buf.data_ptr(), a0.cb_total, chunks, nch, wp.data_ptr(), a0.N, D, H, W, Co, k, dil,
                  scale.data_ptr(), shift.data_ptr(), int(relu), of32, ohi, olo, cbt, cbo,
-                 st.data_ptr() if st is not None else None, self.err.data_ptr(), 0, masks, int(fold_tc))
+                 st.data_ptr() if st is not None else None, self.err.data_ptr(), 0, masks, 2 if dpair else int(fold_tc))
 
     def conv_direct(self, a, weight, k, stride, dil, scale, shift, relu, out_raw=None, out_act=None, stats=None):
         """generic direct conv on one Act whose C is a multiple of 8 (stride-2 convs of net_A)."""

@@ -60,7 +60,10 @@ void dp_handle_destroy(dp_handle* h);
  *   tap_mask   optional host array [n_chunks] (k <= 3): bit (kd*k+kh)*k+kw set = tap present; lets the
  *              stride-2 convs of c3d.py:49-61 run as sparse 3^3 convs over a space-to-depth input
  *   fold       1: wpack holds 2*cout columns per tap, [W_hi | W_lo] for hi chunks and [W_hi | 0] for lo chunks; the
- *              epilogue adds column c and c + cout (the 3-term operand split with each hi chunk read once)   */
+ *              epilogue adds column c and c + cout (the 3-term operand split with each hi chunk read once)
+ *              2 (cout <= 64, dilation 1): depth-pair mode — a tile covers output planes (d, d + 1); wpack fp16
+ *              [k + 1 virtual depth taps v][n_chunks][kh][kw][2][2*cout][8], rows [W[kd = v] | W[kd = v - 1]] (zero where
+ *              the tap does not exist): every input plane is read once for both output planes with N = 2*cout columns */
 int dp_conv3d_tc(const void* in_c8, int cb_total_in, const uint8_t* chunk_cb, int n_chunks, const void* wpack,
                  int N, int D, int H, int W, int cout, int k, int dil, const float* scale, const float* shift,
                  int relu, float* out_f32, void* out_hi, void* out_lo, int cb_total_out, int cb_out_off,

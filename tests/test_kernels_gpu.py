@@ -45,7 +45,9 @@ def _act_from(P, x, lo):
 @pytest.mark.parametrize("cin,cout,k,dil,dims,mode", [
     (16, 16, 3, 1, (16, 16, 16), "p1"),
     (32, 16, 7, 1, (9, 20, 12), "p1"),          # ragged H/W tiles, 2 K-chunks, full 7x7 stage
-    (16, 64, 7, 1, (8, 16, 16), "p1"),          # kh-group split stages
+    (16, 64, 7, 1, (8, 16, 16), "p1"),          # kh-group split stages; depth-pair mode (two output planes per tile, N = 128)
+    (32, 64, 7, 1, (5, 16, 40), "p1"),          # depth-pair mode: odd D (half-empty last pair), 5 W tiles (partial group), 2 chunks
+    (16, 64, 7, 1, (2, 8, 8), "p1"),            # depth-pair mode: a single pair, masked rows
     (16, 128, 7, 1, (4, 16, 8), "p1"),          # one kh row per stage
     (64, 64, 3, 1, (8, 16, 16), "p1"),
     (128, 256, 3, 1, (4, 8, 8), "p1"),          # H < 16 (masked rows), N = 256
