@@ -343,7 +343,6 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
       const int h = th * 16 + hl, w = (tw0 + tt) * 8 + wl;
       const bool valid = (h < p.H) && (w < p.W);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>((slot * p.T + tt) * p.cout);
-      const size_t vox = (static_cast<size_t>(d) * p.H + h) * p.W + w;
       if (p.dc_co > 0) {
         // transposed conv: the W-neighbours l = 0 / 1 of an output voxel pair are the column chunks c and c + dc_co;
         // one thread converts both and writes whole 32-byte sectors (st.global.v8) per channel block
