@@ -95,8 +95,8 @@ def test_conv3d_stack_split_half_many_items_per_cta_and_old_layout(monkeypatch):
     from dose_prediction_b200 import engine
     torch.manual_seed(3)
     dev = torch.device("cuda:0")
-    N, C, dims = 5, 16, (8, 128, 128)
-    x = torch.randn(N, C, *dims, device=dev)
+    N, C, dims = 5, 16, (16, 128, 128)        # 160 columns x 16 planes: the two-phase balanced distribution (a whole column per CTA,
+    x = torch.randn(N, C, *dims, device=dev)  # then contiguous shares of the other 12) — smaller problems keep fixed segments
     w = torch.randn(C, C, 3, 3, 3, device=dev) / (C * 27) ** 0.5
     bias = torch.randn(C, device=dev) * 0.1
     outs = []
@@ -117,6 +117,29 @@ def test_conv3d_stack_split_half_many_items_per_cta_and_old_layout(monkeypatch):
         assert _rel(y, want) < 2e-5
         assert torch.allclose(st[..., 0], want.sum((2, 3, 4)), rtol=1e-4, atol=1e-1)
     assert _rel(outs[0][0], outs[1][0]) < 1e-6
+
+
+def test_conv3d_stack_7_balanced_distribution_matches_torch():
+    """the 7^3 depth-stacked kernel under the two-phase balanced work distribution (160 columns > 148 SMs, shares that start
+    and end inside a column: clipped ring windows at arbitrary depths), fp16 operands, folded eval BatchNorm + ReLU"""
+    torch.manual_seed(8)
+    dev = torch.device("cuda:0")
+    N, C, dims = 5, 16, (16, 128, 128)
+    x = torch.randn(N, C, *dims, device=dev)
+    w = torch.randn(C, C, 7, 7, 7, device=dev) / (C * 343) ** 0.5
+    bias = torch.randn(C, device=dev) * 0.1
+    P = _plan()
+    a = _act_from(P, x, lo=False)
+    raw = P.get_raw(N, C, dims)
+    P.conv_tc([a], w, 7, 1, "p1", *P.affine(C, bias=bias), False, out_raw=raw)
+    P.run()
+    _finish(P)
+    want = F.conv3d(_h(x).double(), _h(w).double(), bias.double(), padding=3)
+    got = _raw_to_ncdhw(raw.t)
+    assert _rel(got, want) < 2e-5
+    st = raw.stats.view(N, C, 2)
+    assert torch.allclose(st[..., 0], want.sum((2, 3, 4)), rtol=1e-4, atol=1e-1)
+    assert torch.allclose(st[..., 1], (want ** 2).sum((2, 3, 4)), rtol=1e-4, atol=1e-1)
 
 
 def test_conv3d_tc_concat_parts_bn_fold_relu_fp16_out():
